@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py — robot-GBP-iterations/s of the GBP iterate hot path on B200.
+
+A "step" is one simulation tick of the hot path over the whole synthetic swarm:
+neighbour search / InterRobot factor maintenance, the two prior updates, and
+`iterate_gbp_v2` with the config's schedule (10 internal + 10 external,
+interleave-evenly => 10 sub-steps, each one robot-GBP-iteration per robot).
+
+  value  robots x sub-steps x steps / device time, swarm resident in HBM
+  e2e    same through the C ABI with HOST buffers each step (comms mask and
+         waypoint indices in, every variable's mean out)
+  roofline  dominant kernel k_iterate<EXT,INT>: algorithmic bytes per launch
+            (192*(5E+7F) + 704*V per robot-iteration) / its
+            average CUDA-event duration, against MEASURED_PEAKS.json
+  cpu_baseline  the oracle (C++ restatement of the reference algorithm) timed
+            on the host cores on a bounded sample of the same workload
+
+`--impl reference` times that CPU restatement alone (the Rust reference cannot be
+built in this image: no rustc/cargo).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "robot_gbp_iterations_per_sec"
+UNIT = "robot-GBP-iterations/s"
+
+
+def algorithmic_bytes_per_robot_iteration(V: int, K: float, e_obs: int, e_trk: int) -> float:
+    """messages counted as the reference's 192-byte payloads."""
+    E = 2 * (V - 1) + e_obs * (V - 2) + e_trk * (V - 2)
+    F = K * (V - 1)
+    return 192.0 * (5 * E + 7 * F) + 704.0 * V
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def build_workload(name: str, robots: int):
+    from magics_b200 import scenarios
+
+    if name == "rings":
+        return scenarios.rings(robots)
+    if name == "lattice":
+        side = int(round(robots ** 0.5))
+        return scenarios.lattice(side, max(1, robots // side))
+    raise ValueError(name)
+
+
+def run_cpu(sw, threads: int, ticks: int):
+    """Oracle timing: whole ticks, wall clock (best of `ticks` after one warm-up tick)."""
+    from oracle.oracle import OracleWorld, schedule
+
+    o = OracleWorld(sw.cfg, threads=threads)
+    sw.add_to(o)
+    oi, oe = schedule(sw.cfg.schedule_kind, sw.cfg.iterations_internal, sw.cfg.iterations_external)
+    substeps = int(np.sum(oi & oe)) or int(max(oi.sum(), oe.sum()))
+    o.step()  # warm-up: creates the InterRobot factors
+    best = float("inf")
+    for _ in range(ticks):
+        t = time.perf_counter()
+        o.step()
+        best = min(best, time.perf_counter() - t)
+    o.close()
+    return sw.n * substeps / best, best, substeps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="rings", choices=["rings", "lattice"])
+    ap.add_argument("--robots", type=int, default=100_000, help="robots per GPU (weak scaling)")
+    ap.add_argument("--cpu-robots", type=int, default=3000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sw = build_workload(args.workload, args.cpu_robots)
+        vals = []
+        for _ in range(max(1, min(args.steps, 3))):
+            v, secs, substeps = run_cpu(sw, cores, max(1, args.warmup))
+            vals.append((v, secs))
+        v, secs = max(vals)
+        K = None
+        line = {
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{sw.name} (bounded CPU sample of {args.workload}-{args.robots})",
+                       "V": int(sw.cfg.num_variables), "schedule": "interleave-evenly 10/10"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sw.n} robots of the {args.workload} workload, 1 sim tick, best of "
+                                       f"{max(1, args.warmup)}; C++ restatement of the reference algorithm "
+                                       "(Rust toolchain absent)"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from magics_b200 import World
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    sw = build_workload(args.workload, args.robots)
+    cfg = sw.cfg
+    g = World(cfg, device=local_rank)
+    sw.add_to(g)
+    from magics_b200 import gbp_schedule
+
+    oi, oe = gbp_schedule(cfg.schedule_kind, cfg.iterations_internal, cfg.iterations_external)
+    substeps = int(np.sum(oi & oe))
+    n = sw.n
+
+    def barrier():
+        g.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ------------------------------------------
+    for _ in range(args.warmup):
+        g.step()
+    g.set_profiling(True)
+    launches0 = g.kernel_launches
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    g.timer_start()
+    for _ in range(args.steps):
+        g.step()
+    ms = g.timer_stop_ms()
+    barrier()
+    clocks = sampler.stop()
+    launches = g.kernel_launches - launches0
+    prof = g.read_profile()
+    g.set_profiling(False)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = n * world * substeps * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers ------------------
+    ant = np.ones(n, np.uint8)
+    wpi = np.ones(n, np.int32)
+    barrier()
+    t0 = time.perf_counter()
+    g.timer_start()
+    for _ in range(args.steps):
+        g.set_comms(ant, None)
+        g.set_waypoint_index(wpi)
+        g.step()
+        means = g.read_beliefs(eta=False, lam=False, mean=True, cov=False, valid=False)["mean"]
+    ms_e2e = g.timer_stop_ms()
+    barrier()
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([max(ms_e2e, wall_e2e)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = n * world * substeps * args.steps / (float(t.item()) * 1e-3)
+
+    if rank == 0:
+        deg = float(np.diff(g.read_connections()[0]).mean())
+        peak, peak_kind = measured_peak_gbs()
+        bytes_iter = algorithmic_bytes_per_robot_iteration(cfg.num_variables, deg, int(cfg.enable_obstacle),
+                                                           int(cfg.enable_tracking))
+        dom = prof.get("iterate_ext_int", {"count": 0, "ms": 0.0})
+        roof = None
+        if dom["count"]:
+            avg_s = dom["ms"] * 1e-3 / dom["count"]
+            achieved = bytes_iter * n / avg_s / 1e9
+            roof = {"bound": "hbm", "kernel": "k_iterate<EXT,INT>", "achieved": achieved, "peak": peak,
+                    "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "avg_launch_ms": avg_s * 1e3, "launches_timed": dom["count"],
+                    "algorithmic_bytes_per_robot_iteration": bytes_iter, "mean_neighbours": deg}
+        cpu = None
+        if not args.no_cpu_baseline:
+            swc = build_workload(args.workload, args.cpu_robots)
+            v, secs, _ = run_cpu(swc, cores, 2)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{swc.n} robots of the {args.workload} workload, 1 sim tick ({substeps} sub-steps), "
+                             f"best of 2 after warm-up, {secs * 1e3:.1f} ms; C++ restatement of the reference "
+                             "algorithm (Rust toolchain absent)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{sw.name}: {n} robots/GPU x V={cfg.num_variables}, mean K={deg:.2f}, "
+                                   "dyn+obstacle+interrobot factors, interleave-evenly 10/10",
+                       "robots_total": n * world, "sub_steps_per_step": substeps,
+                       "l2": "inputs larger than L2 (store >> 126 MB)"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ant.nbytes + wpi.nbytes),
+                    "d2h_bytes_per_step": int(means.nbytes)},
+            "roofline": roof, "cpu_baseline": cpu, "profile_ms": prof,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,224 @@
+/* gbp_b200.h — C ABI of the B200-native Gaussian Belief Propagation engine.
+ *
+ * This is the drop-in boundary for the hot path of AU-Master-Thesis/magics
+ * (per-tick GBP iteration over every robot's factor graph + InterRobot factor
+ * creation + Obstacle SDF lookup).  The reference has no FFI of its own: the seam
+ * is the public method set of its `FactorGraph` component and the FixedUpdate
+ * systems of `RobotPlugin`.  Every entry point below names the reference
+ * interface it replaces (paths relative to the reference checkout,
+ * crates/magics/src/...).  A per-robot API would serialise the GPU, so each
+ * reference method becomes ONE world-level call that does the same thing for
+ * every robot at once; the Rust `FactorGraph` facade forwards to these
+ * (INTEGRATION.md shows the -sys binding).
+ *
+ * Conventions
+ *   - plain C types only, no torch / CUDA types in any signature;
+ *   - all pointers are HOST pointers borrowed for the duration of the call;
+ *   - every function returns 0 on success, <0 on error (gbp_last_error());
+ *     numerical degeneracy is never an error, it stays in-band (validity flags)
+ *     exactly as in the reference (variable.rs:276-297, marginalise_factor_distance.rs:79-81);
+ *   - a world handle is not re-entrant: one host thread per handle;
+ *   - robots are identified by their index in insertion order; this index is
+ *     the total order the reference derives from bevy `Entity` (id.rs:25-61) and
+ *     is what fixes inbox order, InterRobot slot order and robot_number order.
+ */
+#ifndef GBP_B200_H
+#define GBP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GBP_DOFS 4 /* factorgraph/mod.rs:21 */
+
+/* gbp_config::GbpIterationScheduleKind (gbp_config/src/lib.rs:360-376) */
+enum gbp_schedule_kind {
+  GBP_SCHEDULE_CENTERED = 0,
+  GBP_SCHEDULE_INTERLEAVE_EVENLY = 1,
+  GBP_SCHEDULE_SOON_AS_POSSIBLE = 2,
+  GBP_SCHEDULE_LATE_AS_POSSIBLE = 3,
+  GBP_SCHEDULE_HALF_BEGINNING_HALF_END = 4
+};
+
+enum gbp_status {
+  GBP_OK = 0,
+  GBP_ERR_BAD_HANDLE = -1,
+  GBP_ERR_BAD_ARGUMENT = -2,
+  GBP_ERR_CUDA = -3,
+  GBP_ERR_NCCL = -4,
+  GBP_ERR_STATE = -5
+};
+
+/* The scalars of gbp_config::Config that cross the boundary.
+ * f32 fields are f32 in the reference and are widened with f64::from exactly
+ * where the reference widens them (robot.rs:1238-1240,1272,1318,1517-1522). */
+typedef struct gbp_config {
+  int32_t num_variables;           /* V = variable_timesteps.len() (spawner.rs:559-569) */
+  float sigma_factor_dynamics;     /* GbpSection (gbp_config/src/lib.rs:544-594) */
+  float sigma_factor_interrobot;
+  float sigma_factor_obstacle;
+  float sigma_factor_tracking;
+  float safety_distance_multiplier; /* robot.inter-robot-safety-distance-multiplier */
+  float comms_radius;               /* robot.communication.radius (robot.rs:1372) */
+  float target_speed;               /* robot.target-speed (robot.rs:2207, 1225) */
+  float delta_t;                    /* 1/simulation.hz as f32: Time::delta_seconds (robot.rs:2205,2309) */
+  float tracking_switch_padding;      /* TrackingSection (lib.rs:502-537) */
+  float tracking_attraction_distance;
+  uint8_t enable_dynamic;           /* FactorsEnabledSection (lib.rs:454-494) */
+  uint8_t enable_interrobot;
+  uint8_t enable_obstacle;
+  uint8_t enable_tracking;
+  int32_t schedule_kind;            /* enum gbp_schedule_kind */
+  int32_t iterations_internal;      /* GbpIterationSchedule.internal (cast `as u8`, robot.rs:1782) */
+  int32_t iterations_external;
+  double world_width;               /* obstacle::WorldSize (robot.rs:1258-1263) */
+  double world_height;
+} gbp_config_t;
+
+typedef struct gbp_world gbp_world_t; /* opaque */
+
+/* Thread-local description of the last error on this thread. */
+const char *gbp_last_error(void);
+
+/* ---- gbp_schedule crate ------------------------------------------------ */
+/* GbpSchedule::schedule(GbpScheduleParams{internal,external})
+ * (gbp_schedule/src/schedules/mod.rs:60-81; dispatch gbp_config/src/lib.rs:378-400).
+ * Writes max(internal,external) entries into out_internal/out_external (0/1)
+ * and returns that count (<= 255), or <0 on error. */
+int gbp_schedule(int32_t kind, uint8_t internal, uint8_t external,
+                 uint8_t *out_internal, uint8_t *out_external);
+
+/* utils::get_variable_timesteps (utils.rs:35-75).  Returns the count written
+ * (capacity must be >= lookahead_multiple*(n+1)); <0 on error. */
+int gbp_variable_timesteps(uint32_t lookahead_horizon, uint32_t lookahead_multiple,
+                           uint32_t *out, int32_t capacity);
+
+/* ---- world lifetime ---------------------------------------------------- */
+/* Replaces scenario load + reset_robot_number_generator (robot.rs:121-144).
+ * device: CUDA device ordinal. */
+gbp_world_t *gbp_world_create(const gbp_config_t *cfg, int32_t device);
+void gbp_world_destroy(gbp_world_t *w);
+
+/* Replaces the `Sdf(SdfImage)` resource cloned into every ObstacleFactor
+ * (simulation_loader.rs:52, robot.rs:1274): RGB8, row 0 = top, uploaded once. */
+int gbp_world_set_sdf(gbp_world_t *w, const uint8_t *rgb8, int32_t width, int32_t height);
+
+/* Replaces RobotBundle::new for n robots (robot.rs:1134-1355): V variables
+ * (prior 1e30*I on first/last, non-finite -> 0 on the rest, variable.rs:146-148),
+ * V-1 Dynamic, V-2 Obstacle, V-2 Tracking factors.
+ *   radii[n]            f32 robot radius (t0 = radius/2/target_speed in f32, :1225)
+ *   timesteps[V]        variable_timesteps (shared by the world)
+ *   init_means[n*V*4]   f64 initial variable means (already widened from f32, :1212-1217)
+ *   positions[n*2]      f32 Transform.translation (x, z) (spawner.rs:530)
+ *   wp_offsets[n+1], wp_xy[2*wp_offsets[n]]  f32 waypoint polyline of each robot
+ *                       (mission route; also the TrackingFactor path, :1316-1322)
+ * Robot ids are assigned consecutively in insertion order. */
+int gbp_world_add_robots(gbp_world_t *w, int32_t n, const float *radii,
+                         const uint32_t *timesteps, const double *init_means,
+                         const float *positions, const int32_t *wp_offsets,
+                         const float *wp_xy);
+
+int32_t gbp_world_num_robots(const gbp_world_t *w);
+
+/* ---- per-tick systems (RobotPlugin FixedUpdate chain, robot.rs:85-108) -- */
+/* update_robot_neighbours + delete_interrobot_factors + create_interrobot_factors
+ * (robot.rs:1362-1586; FactorGraph::delete_interrobot_factors_connected_to
+ * factorgraph.rs:380-436; add_internal_edge/add_external_edge :304-353).
+ * Sort-based spatial hash; connectivity, creation order and robot_number are
+ * bit-exact with the reference's all-pairs search. */
+int gbp_world_update_topology(gbp_world_t *w);
+
+/* update_failed_comms result (robot.rs:1593-1601): antenna_active[n] (0/1), and
+ * mission.state.idle() (robot.rs:1791,1806): idle[n] (0/1).  NULL = all active / none idle. */
+int gbp_world_set_comms(gbp_world_t *w, const uint8_t *antenna_active, const uint8_t *idle);
+
+/* Mission::next_waypoint (robot.rs:2214): index into each robot's polyline of the
+ * waypoint the horizon moves toward; <0 or >= len means "no more waypoints". */
+int gbp_world_set_waypoint_index(gbp_world_t *w, const int32_t *next_index);
+
+/* update_prior_of_horizon_state (robot.rs:2182-2283) for every robot. */
+int gbp_world_update_prior_of_horizon_state(gbp_world_t *w);
+/* update_prior_of_current_state_v3 (robot.rs:2286-2338) for every robot;
+ * also advances the f32 Transform used by the neighbour search. */
+int gbp_world_update_prior_of_current_state(gbp_world_t *w);
+
+/* FactorGraph::change_prior_of_variable (factorgraph.rs:494-528) for one
+ * variable index of every robot listed: robots[m], new_means[m*4]. */
+int gbp_world_change_prior_of_variable(gbp_world_t *w, int32_t variable_index, int32_t m,
+                                       const int32_t *robots, const double *new_means);
+
+/* iterate_gbp_v2 (robot.rs:1769-1861) with the config's schedule. */
+int gbp_world_iterate(gbp_world_t *w);
+/* Same with an explicit schedule: n sub-steps of (internal[i], external[i]). */
+int gbp_world_iterate_schedule(gbp_world_t *w, int32_t n, const uint8_t *internal,
+                               const uint8_t *external);
+
+/* The four FactorGraph half-iterations, each for every (non-idle / antenna-on)
+ * robot, with the delivery loops of iterate_gbp_v2 folded in:
+ *   internal_factor_iteration   factorgraph.rs:688-714
+ *   internal_variable_iteration factorgraph.rs:762-790
+ *   external_factor_iteration   factorgraph.rs:719-760 + delivery robot.rs:1814-1831
+ *   external_variable_iteration factorgraph.rs:794-826 + delivery robot.rs:1843-1858
+ * The internal pair and the external pair must each be called in this order
+ * (as iterate_gbp_v2 does); the engine executes a pair as one fused pass when
+ * the second half is requested and returns GBP_ERR_STATE on any other order. */
+int gbp_world_internal_factor_iteration(gbp_world_t *w);
+int gbp_world_internal_variable_iteration(gbp_world_t *w);
+int gbp_world_external_factor_iteration(gbp_world_t *w);
+int gbp_world_external_variable_iteration(gbp_world_t *w);
+
+/* One full tick = FixedUpdate chain items 1-7. */
+int gbp_world_step(gbp_world_t *w);
+
+/* ---- setters used by the UI hooks (ui/settings.rs:437,495,590) ---------- */
+/* FactorGraph::change_factor_enabled (factorgraph.rs:1529-1539); kind: 0 dyn 1 ir 2 obs 3 trk */
+int gbp_world_change_factor_enabled(gbp_world_t *w, int32_t kind, uint8_t enabled);
+/* FactorGraph::update_inter_robot_safety_distance_multiplier (factorgraph.rs:892) */
+int gbp_world_set_safety_distance_multiplier(gbp_world_t *w, float multiplier);
+int gbp_world_set_schedule(gbp_world_t *w, int32_t kind, int32_t internal, int32_t external);
+
+/* ---- read-back (visualisers / export read these fields) ----------------- */
+/* VariableBelief of every variable (variable.rs:39-54): any pointer may be NULL.
+ *   eta[n*V*4], lam[n*V*16] row-major, mean[n*V*4], cov[n*V*16], valid[n*V] */
+int gbp_world_read_beliefs(gbp_world_t *w, double *eta, double *lam, double *mean,
+                           double *cov, uint8_t *valid);
+/* Transform.translation (x, z) of every robot, f32[n*2]. */
+int gbp_world_read_positions(gbp_world_t *w, float *xy);
+/* RobotConnections.robots_connected_with as CSR: offsets[n+1], neighbours sorted
+ * ascending; robot_number[e] = RobotNumberGenerator value of the FIRST (i=1)
+ * InterRobot factor robot r created toward neighbours[e] (robot.rs:1527).
+ * Pass capacity of the neighbour arrays; returns edge count or <0. */
+int64_t gbp_world_read_connections(gbp_world_t *w, int64_t *offsets, int32_t *neighbours,
+                                   int64_t *robot_number, int64_t capacity);
+/* ObstacleFactor::measure pixel lookup (obstacle.rs:141-188) for m points:
+ * xy[m*2] f64 -> px[m], py[m] (u32 after the saturating cast) and value[m]. */
+int gbp_world_sdf_lookup(gbp_world_t *w, int32_t m, const double *xy, uint32_t *px,
+                         uint32_t *py, double *value);
+/* FactorGraph::factor_count / node_count style totals (factorgraph.rs:247-276):
+ * out[0]=variables out[1]=dynamic out[2]=obstacle out[3]=tracking out[4]=interrobot. */
+int gbp_world_node_counts(gbp_world_t *w, int64_t out[5]);
+/* number of GPU kernels this handle has launched so far (bench `gpu_launches`) */
+int64_t gbp_world_kernel_launches(const gbp_world_t *w);
+/* Optional per-launch CUDA-event timing on the engine's stream (bench.py's
+ * roofline leg): accumulated count / device milliseconds per kernel family. */
+enum gbp_profile_kind {
+  GBP_PROFILE_ITERATE_INT = 0,     /* k_iterate<EXT=0,INT=1> */
+  GBP_PROFILE_ITERATE_EXT = 1,     /* k_iterate<EXT=1,INT=0> */
+  GBP_PROFILE_ITERATE_EXT_INT = 2, /* k_iterate<EXT=1,INT=1>, the dominant kernel */
+  GBP_PROFILE_TOPOLOGY = 3,        /* whole gbp_world_update_topology */
+  GBP_PROFILE_PRIORS = 4,          /* horizon + current prior kernels */
+  GBP_PROFILE_KINDS = 5
+};
+int gbp_world_set_profiling(gbp_world_t *w, int32_t on);
+int gbp_world_read_profile(gbp_world_t *w, int32_t kind, int64_t *count, double *total_ms);
+/* device time helpers for bench.py: record/elapsed on the engine's own stream. */
+int gbp_world_sync(gbp_world_t *w);
+int gbp_world_timer_start(gbp_world_t *w);
+int gbp_world_timer_stop_ms(gbp_world_t *w, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GBP_B200_H */

@@ -1,0 +1,491 @@
+// gbp_iterate.cuh — the fused GBP iteration kernel.
+//
+// One thread per (robot, variable index i); a robot's V threads sit in one warp
+// (32/V robots per warp).  Thread i owns variable i, the messages variable i
+// holds from Dynamic factors i-1 and i, Obstacle factor i, Tracking factor i and
+// from every neighbour's InterRobot factor at i.
+//
+//   EXT half  = FactorGraph::external_factor_iteration   (factorgraph.rs:719-760)
+//             + delivery                                  (robot.rs:1814-1831)
+//             + FactorGraph::external_variable_iteration  (factorgraph.rs:794-826)
+//             + delivery                                  (robot.rs:1843-1858)
+//   INT half  = FactorGraph::internal_factor_iteration    (factorgraph.rs:688-714)
+//             + FactorGraph::internal_variable_iteration  (factorgraph.rs:762-790)
+//
+// The reference pushes every InterRobot message from the factor's owner A to the
+// other robot B.  Here B PULLS: the only thing A's factor needs from A is the
+// message A's variable sent it, which is A's published belief record (the entry
+// for A's own InterRobot factors in A's variable inboxes is permanently Empty,
+// factorgraph.rs:745-753, so the variable answers with its full belief,
+// variable.rs:305-306).  So B evaluates A's factor itself from pub[p][A] and the
+// position mean B last sent it, and the message never leaves B's registers
+// except as the "mirror" record B keeps for later sums.  The only cross-robot
+// traffic of a sub-step is therefore the read of neighbours' pub records, and a
+// launch boundary is needed only between INT(t) and EXT(t): EXT(t) and INT(t+1)
+// run fused in one launch.
+#pragma once
+#include "gbp_math.cuh"
+#include "gbp_store.cuh"
+
+namespace gbp {
+
+constexpr int kIterBlock = 128;
+
+GBP_DEV double dot2(const double (&a)[2], const double (&b)[2]) { return (0.0 + a[0] * b[0]) + a[1] * b[1]; }
+GBP_DEV double norm2(double x, double y) { return sqrt((0.0 + x * x) + y * y); }
+
+// ObstacleFactor::measure (factor/obstacle.rs:141-188).
+GBP_DEV double sdf_measure(const Store &s, double x_pos, double y_pos, uint32_t *opx = nullptr,
+                           uint32_t *opy = nullptr) {
+  const double x_offset = s.world_w / 2.0, y_offset = s.world_h / 2.0;
+  const double x_scale = double(uint32_t(s.sdf_w)) / s.world_w;
+  const double y_scale = double(uint32_t(s.sdf_h)) / s.world_h;
+  const uint32_t xp = sat_u32((x_pos + x_offset) * x_scale);
+  const uint32_t yp = sat_u32((-y_pos + y_offset) * y_scale);
+  if (opx) *opx = xp;
+  if (opy) *opy = yp;
+  if (!(xp < uint32_t(s.sdf_w) && yp < uint32_t(s.sdf_h))) return 0.0;
+  const uint8_t red = s.sdf[size_t(yp) * size_t(s.sdf_w) + xp];
+  return 1.0 - double(red) / 255.0;
+}
+
+// Sum of the messages variable i holds from its own non-InterRobot factors, in
+// FactorId order dyn(i-1) < dyn(i) < obs(i) < trk(i) (id.rs:25-61; creation order
+// robot.rs:1228-1334), added onto (ae, al) (variable.rs:263-271).
+GBP_DEV void add_internal(const Store &s, int64_t vi, int i, double (&ae)[4], double (&al)[16]) {
+  const int64_t NV = s.NV;
+  const int V = s.V;
+  if (i >= 1) {
+    const double f = s.m_dynL[vi];
+    if (!is_empty_marker(f)) {
+      ae[0] = ae[0] + f;
+#pragma unroll
+      for (int k = 1; k < 4; ++k) ae[k] = ae[k] + s.m_dynL[k * NV + vi];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) al[k] = al[k] + s.m_dynL[(4 + k) * NV + vi];
+    }
+  }
+  if (i <= V - 2) {
+    const double f = s.m_dynR[vi];
+    if (!is_empty_marker(f)) {
+      ae[0] = ae[0] + f;
+#pragma unroll
+      for (int k = 1; k < 4; ++k) ae[k] = ae[k] + s.m_dynR[k * NV + vi];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) al[k] = al[k] + s.m_dynR[(4 + k) * NV + vi];
+    }
+  }
+  if (i >= 1 && i <= V - 2) {
+    const double j0 = s.m_obs[vi];
+    if (!is_empty_marker(j0)) {
+      const double j2 = s.m_obs[2 * NV + vi];
+      const double J[4] = {j0, s.m_obs[NV + vi], j2, j2};
+      unary_add(J, s.m_obs[3 * NV + vi], s.lm_obs, ae, al);
+    }
+    const double t0 = s.m_trk[vi];
+    if (!is_empty_marker(t0)) {
+      const double J[2] = {t0, s.m_trk[NV + vi]};
+      const double v0 = s.m_trk[2 * NV + vi];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const double g = J[k] * s.lm_trk;
+        ae[k] = ae[k] + g * v0;
+#pragma unroll
+        for (int l = 0; l < 2; ++l) al[k * 4 + l] = al[k * 4 + l] + g * J[l];
+      }
+    }
+  }
+}
+
+GBP_DEV void add_mirror(const Store &s, int64_t m, double (&ae)[4], double (&al)[16]) {
+  const double f = s.mir[m];
+  if (is_empty_marker(f)) return;
+  ae[0] = ae[0] + f;
+  ae[1] = ae[1] + s.mir[s.EV + m];
+  al[0] = al[0] + s.mir[2 * s.EV + m];
+  al[1] = al[1] + s.mir[3 * s.EV + m];
+  al[4] = al[4] + s.mir[4 * s.EV + m];
+  al[5] = al[5] + s.mir[5 * s.EV + m];
+}
+
+GBP_DEV void load_prior(const Store &s, int64_t vi, double (&ae)[4], double (&al)[16]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) ae[k] = s.prior_eta[k * s.NV + vi];
+  const double pl = s.prior_lam[vi];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) al[k] = (k % 5 == 0) ? pl : 0.0;
+}
+
+GBP_DEV void shfl_vec(double (&v)[20], bool &flag, int delta_up, unsigned lane) {
+  // delta_up > 0: take from lane - delta; < 0: take from lane + |delta|
+#pragma unroll
+  for (int k = 0; k < 20; ++k)
+    v[k] = delta_up > 0 ? __shfl_up_sync(0xffffffffu, v[k], delta_up)
+                        : __shfl_down_sync(0xffffffffu, v[k], -delta_up);
+  const int f = flag ? 1 : 0;
+  flag = (delta_up > 0 ? __shfl_up_sync(0xffffffffu, f, delta_up)
+                       : __shfl_down_sync(0xffffffffu, f, -delta_up)) != 0;
+}
+
+// TrackingFactor::skip + measure + jacobian (factor/tracking.rs:171-381) for
+// variable vi of robot r at linearisation point x.  Writes the message record.
+GBP_DEV void tracking_update(const Store &s, int64_t r, int64_t vi, const double (&x)[4]) {
+  const int64_t NV = s.NV;
+  bool skip = false;
+  int32_t timeout = s.trk_timeout[vi];
+  if (timeout >= 0) {
+    if (timeout == 0) {
+      timeout = -1;
+    } else {
+      timeout -= 1;
+      skip = true;
+    }
+    s.trk_timeout[vi] = timeout;
+  }
+  const int32_t w0 = s.wp_off[r];
+  const uint32_t npath = uint32_t(s.wp_off[r + 1] - w0);
+  uint32_t rec = s.trk_record[vi];
+  if (!skip && (npath < 2 || rec >= npath - 1)) skip = true;
+  if (skip) {
+    s.m_trk[vi] = empty_marker();
+    return;
+  }
+  const float *wp = s.wp_xy + 2 * size_t(w0);
+  const double x_pos[2] = {x[0], x[1]};
+  const double cs[2] = {double(wp[2 * rec]), double(wp[2 * rec + 1])};
+  const double ce[2] = {double(wp[2 * rec + 2]), double(wp[2 * rec + 3])};
+  const double line[2] = {ce[0] - cs[0], ce[1] - cs[1]};
+  const double rel[2] = {x_pos[0] - cs[0], x_pos[1] - cs[1]};
+  const double t = dot2(rel, line) / dot2(line, line);
+  const double cur[2] = {cs[0] + t * line[0], cs[1] + t * line[1]};
+  const double d0 = s.trk_switch_padding, d1 = d0 * 0.01;
+  const double cur_to_end = norm2(ce[0] - cur[0], ce[1] - cur[1]);
+  bool have_prev = false;
+  double pp[2] = {0.0, 0.0};
+  if (rec > 0) {
+    const double ps[2] = {double(wp[2 * rec - 2]), double(wp[2 * rec - 1])};
+    const double pe[2] = {cs[0], cs[1]};  // previous_end is the current start (same f32 pair)
+    const double pl[2] = {pe[0] - ps[0], pe[1] - ps[1]};
+    const double prel[2] = {x_pos[0] - ps[0], x_pos[1] - ps[1]};
+    const double tp = dot2(prel, pl) / dot2(pl, pl);
+    pp[0] = ps[0] + tp * pl[0];
+    pp[1] = ps[1] + tp * pl[1];
+    const double cur_to_prev_end = norm2(pe[0] - cur[0], pe[1] - cur[1]);
+    const double prev_to_prev_end = norm2(cs[0] - pp[0], cs[1] - pp[1]);
+    have_prev = cur_to_prev_end < d0 && cur_to_prev_end > d1 && prev_to_prev_end < d0;
+  }
+  if (cur_to_end < d0) {  // Tracking::increment_record (tracking.rs:55-65)
+    rec = min(rec + 1u, npath - 2u);
+    s.trk_record[vi] = rec;
+  }
+  double mp[2];
+  if (have_prev) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) mp[k] = x_pos[k] + ((cur[k] - x_pos[k]) + (pp[k] - x_pos[k]));
+  } else {
+    double ln[2] = {line[0], line[1]};
+    const double mag = norm2(line[0], line[1]);
+    if (!(mag == 0.0 || isinf(mag))) {
+      ln[0] /= mag;
+      ln[1] /= mag;
+    }
+    const double vn = norm2(x[2], x[3]);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) mp[k] = cur[k] + ln[k] * vn / 5.0;
+  }
+  const double dist = norm2(mp[0] - x_pos[0], mp[1] - x_pos[1]);
+  const double ad = s.trk_attraction;
+  const double meas = dist < ad ? dist / ad : 1.0;
+  const float lx = float(mp[0]), ly = float(mp[1]);
+  s.trk_last[vi] = lx;
+  s.trk_last[NV + vi] = ly;
+  s.trk_value[vi] = meas;
+  // jacobian (tracking.rs:171-194) from the measurement just stored
+  const double j0 = (1.0 / meas) * (x_pos[0] - double(lx));
+  const double j1 = (1.0 / meas) * (x_pos[1] - double(ly));
+  const double v0 = ((0.0 + j0 * x[0]) + j1 * x[1]) + (0.0 - meas);
+  s.m_trk[vi] = j0;
+  s.m_trk[NV + vi] = j1;
+  s.m_trk[2 * NV + vi] = v0;
+}
+
+// ObstacleFactor update: measure + first_order_jacobian (factor/mod.rs:102-128,
+// obstacle.rs:129-188) at linearisation point x; six SDF lookups, perturb and
+// restore sequence kept so that x+d-d rounding reaches the same pixels.
+GBP_DEV void obstacle_update(const Store &s, int64_t vi, const double (&x)[4]) {
+  const int64_t NV = s.NV;
+  const double h = sdf_measure(s, x[0], x[1]);
+  const double h0 = sdf_measure(s, x[0], x[1]);
+  const double delta = s.jac_delta;
+  double px = x[0], py = x[1];
+  px += delta;
+  const double h1 = sdf_measure(s, px, py);
+  px -= delta;
+  py += delta;
+  const double h2 = sdf_measure(s, px, py);
+  py -= delta;
+  const double h3 = sdf_measure(s, px, py);  // columns 2 and 3 perturb the velocity only
+  const double j0 = (h1 - h0) / delta, j1 = (h2 - h0) / delta, j2 = (h3 - h0) / delta;
+  const double v0 = ((((0.0 + j0 * x[0]) + j1 * x[1]) + j2 * x[2]) + j2 * x[3]) + (0.0 - h);
+  s.m_obs[vi] = j0;
+  s.m_obs[NV + vi] = j1;
+  s.m_obs[2 * NV + vi] = j2;
+  s.m_obs[3 * NV + vi] = v0;
+}
+
+template <bool EXT, bool INT>
+__global__ void __launch_bounds__(kIterBlock)
+    k_iterate(const __grid_constant__ Store s, const int p, const uint32_t epoch) {
+  const int V = s.V;
+  const int rpw = 32 / V;
+  const unsigned lane = threadIdx.x & 31u;
+  const int64_t warp = (int64_t(blockIdx.x) * kIterBlock + threadIdx.x) >> 5;
+  const int rl = int(lane) / V;
+  const int i = int(lane) - rl * V;
+  const int64_t r = warp * rpw + rl;
+  const bool live = rl < rpw && r < s.Nloc;
+  const int64_t NV = s.NV;
+  const int64_t vi = live ? r * V + i : 0;
+
+  bool idle = true, ant = false;
+  if (live) {
+    idle = s.idle[r] != 0;
+    ant = s.antenna[r] != 0;
+  }
+  const bool do_ext = EXT && live && !idle && ant;
+  const bool do_int = INT && live && !idle;
+  const double *const pubr = s.pub[p];
+  double *const pubw = s.pub[1 - p];
+
+  // running mean: VariableBelief.mean survives an update that cannot invert
+  // (variable.rs:276-297)
+  double mu[4] = {0.0, 0.0, 0.0, 0.0};
+  if (do_ext || do_int) {
+    const double *rec = s.latest[r] ? s.bel_ext : pubr;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mu[k] = rec[(20 + k) * NV + vi];
+  }
+  uint32_t itf = live ? s.iter_factor[r] : 0u;
+
+  // =================== external half ====================================
+  if (do_ext) {
+    double ae[4], al[16];
+    load_prior(s, vi, ae, al);
+    const int64_t e0 = s.eoff[r];
+    const int64_t e1 = (i >= 1) ? s.eoff[r + 1] : e0;  // variable 0 has no InterRobot factors
+    const int64_t elow = e0 + s.nlow[r];  // edges [e0, elow) have a lower robot id than r
+    double mu_sent[2] = {0.0, 0.0}, mu_born[2] = {0.0, 0.0};
+    if (e1 > e0) {
+      mu_sent[0] = s.mu_ext[vi];
+      mu_sent[1] = s.mu_ext[NV + vi];
+    }
+    bool added = false;
+    for (int64_t e = e0; e < e1; ++e) {
+      const int A = s.enbr[e];
+      if (!added && e >= elow) {
+        add_internal(s, vi, i, ae, al);
+        added = true;
+      }
+      const int64_t m = e * (V - 1) + (i - 1);
+      const bool a_act = s.en_ir && s.antenna[A] != 0 && s.idle[A] == 0;
+      if (a_act) {
+        const int64_t va = int64_t(A) * V + i;
+        const bool a_ne = s.pub_epoch[p][va] > s.e_birth[e];
+        double etaA[4], lamA[16], muA[2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) etaA[k] = a_ne ? pubr[k * NV + va] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) lamA[k] = a_ne ? pubr[(4 + k) * NV + va] : 0.0;
+        muA[0] = a_ne ? pubr[20 * NV + va] : 0.0;
+        muA[1] = a_ne ? pubr[21 * NV + va] : 0.0;
+        double mb[2] = {mu_sent[0], mu_sent[1]};
+        if (s.e_new[e]) {
+          mb[0] = s.mu_new[vi];
+          mb[1] = s.mu_new[NV + vi];
+        }
+        const double tiny = s.tiny_scale * double(s.e_rnum[e] + uint64_t(i - 1));
+        double me[2], ml[4];
+        const bool ok = interrobot_message(e < elow, muA, mb, a_ne, etaA, lamA, s.e_dsafe[e], tiny,
+                                           s.lm_ir, me, ml);
+        if (ok) {
+          s.mir[m] = me[0];
+          s.mir[s.EV + m] = me[1];
+          s.mir[2 * s.EV + m] = ml[0];
+          s.mir[3 * s.EV + m] = ml[1];
+          s.mir[4 * s.EV + m] = ml[2];
+          s.mir[5 * s.EV + m] = ml[3];
+          ae[0] = ae[0] + me[0];
+          ae[1] = ae[1] + me[1];
+          al[0] = al[0] + ml[0];
+          al[1] = al[1] + ml[1];
+          al[4] = al[4] + ml[2];
+          al[5] = al[5] + ml[3];
+        } else {
+          s.mir[m] = empty_marker();
+        }
+      } else {
+        add_mirror(s, m, ae, al);  // undelivered: the variable keeps the old message
+      }
+    }
+    if (!added) add_internal(s, vi, i, ae, al);
+    double cov[16];
+    bool valid = false;
+    const bool taken = belief_moments(ae, al, mu, cov, valid);
+    if (taken) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) s.cov[k * NV + vi] = cov[k];
+      s.valid[vi] = valid ? 1 : 0;
+    }
+    s.mu_ext[vi] = mu[0];
+    s.mu_ext[NV + vi] = mu[1];
+    if (!INT || !do_int) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s.bel_ext[k * NV + vi] = ae[k];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) s.bel_ext[(4 + k) * NV + vi] = al[k];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s.bel_ext[(20 + k) * NV + vi] = mu[k];
+    }
+    itf += 1;
+  }
+  if (EXT) {
+    __syncwarp();
+    if (do_ext && i == 1 && s.en_ir) {
+      for (int64_t e = s.eoff[r]; e < s.eoff[r + 1]; ++e) {
+        const int A = s.enbr[e];
+        if (s.e_new[e] && s.antenna[A] != 0 && s.idle[A] == 0) s.e_new[e] = 0;
+      }
+    }
+  }
+
+  // =================== internal half ====================================
+  if (INT) {
+    // ---- variable -> Dynamic factor messages of the previous variable
+    // iteration, rebuilt as (record - factor's own last message) (variable.rs:301-330)
+    double toR[20], toL[20];
+    bool own_ne = false;
+    if (do_int) {
+      own_ne = s.pub_epoch[p][vi] > 0u;
+      double R[20];
+#pragma unroll
+      for (int k = 0; k < 20; ++k) R[k] = pubr[k * NV + vi];
+      const double fr = (i <= V - 2) ? s.m_dynR[vi] : empty_marker();
+      if (!is_empty_marker(fr)) {
+        toR[0] = R[0] - fr;
+#pragma unroll
+        for (int k = 1; k < 20; ++k) toR[k] = R[k] - s.m_dynR[k * NV + vi];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 20; ++k) toR[k] = R[k];
+      }
+      const double fl = (i >= 1) ? s.m_dynL[vi] : empty_marker();
+      if (!is_empty_marker(fl)) {
+        toL[0] = R[0] - fl;
+#pragma unroll
+        for (int k = 1; k < 20; ++k) toL[k] = R[k] - s.m_dynL[k * NV + vi];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 20; ++k) toL[k] = R[k];
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 20; ++k) toR[k] = toL[k] = 0.0;
+    }
+    bool fromL_ne = own_ne, fromR_ne = own_ne;
+    shfl_vec(toR, fromL_ne, 1, lane);    // lane i receives var i-1 -> dyn(i-1)
+    shfl_vec(toL, fromR_ne, -1, lane);   // lane i receives var i+1 -> dyn(i)
+    if (do_int) {
+      if (s.en_dyn) {
+        if (i >= 1) {  // Dynamic factor i-1 -> variable i (slot 1)
+          const DynM M = dyn_potential(s.dyn_dt[vi - 1], s.qs_dyn);
+          double oe[4], ol[16], ne[4], nl[16];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) oe[k] = toR[k];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) ol[k] = toR[4 + k];
+          if (dyn_message<1>(M, fromL_ne, oe, ol, ne, nl)) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s.m_dynL[k * NV + vi] = ne[k];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) s.m_dynL[(4 + k) * NV + vi] = nl[k];
+          } else {
+            s.m_dynL[vi] = empty_marker();
+          }
+        }
+        if (i <= V - 2) {  // Dynamic factor i -> variable i (slot 0)
+          const DynM M = dyn_potential(s.dyn_dt[vi], s.qs_dyn);
+          double oe[4], ol[16], ne[4], nl[16];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) oe[k] = toL[k];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) ol[k] = toL[4 + k];
+          if (dyn_message<0>(M, fromR_ne, oe, ol, ne, nl)) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s.m_dynR[k * NV + vi] = ne[k];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) s.m_dynR[(4 + k) * NV + vi] = nl[k];
+          } else {
+            s.m_dynR[vi] = empty_marker();
+          }
+        }
+      }
+      if (i >= 1 && i <= V - 2 && (s.en_obs || s.en_trk)) {
+        // linearisation point = mean of the variable's last message (factor/mod.rs:336-349)
+        double x[4], x0[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          x[k] = pubr[(20 + k) * NV + vi];
+          x0[k] = own_ne ? x[k] : 0.0;  // Obstacle inbox starts Empty (factorgraph.rs:310-322)
+        }
+        if (s.en_obs) obstacle_update(s, vi, x0);
+        // Tracking factors are skipped until iteration_count.factor >= 10
+        // (factorgraph.rs:701); their inbox starts with the variable's belief
+        if (s.en_trk && itf >= 10u) tracking_update(s, r, vi, x);
+      }
+      itf += 1;
+
+      // ---- belief update + new record (variable.rs:251-297)
+      double ae[4], al[16];
+      load_prior(s, vi, ae, al);
+      const int64_t e0 = s.eoff[r];
+      const int64_t e1 = (i >= 1) ? s.eoff[r + 1] : e0;
+      const int64_t elow = e0 + s.nlow[r];
+      bool added = false;
+      for (int64_t e = e0; e < e1; ++e) {
+        if (!added && e >= elow) {
+          add_internal(s, vi, i, ae, al);
+          added = true;
+        }
+        add_mirror(s, e * (V - 1) + (i - 1), ae, al);
+      }
+      if (!added) add_internal(s, vi, i, ae, al);
+      double cov[16];
+      bool valid = false;
+      const bool taken = belief_moments(ae, al, mu, cov, valid);
+      if (taken) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) s.cov[k * NV + vi] = cov[k];
+        s.valid[vi] = valid ? 1 : 0;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pubw[k * NV + vi] = ae[k];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) pubw[(4 + k) * NV + vi] = al[k];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pubw[(20 + k) * NV + vi] = mu[k];
+      s.pub_epoch[1 - p][vi] = epoch;
+    } else if (live) {
+      // idle robot: its record is carried over to the other buffer unchanged
+#pragma unroll
+      for (int k = 0; k < kRec; ++k) pubw[k * NV + vi] = pubr[k * NV + vi];
+      s.pub_epoch[1 - p][vi] = s.pub_epoch[p][vi];
+    }
+  }
+  if (live && i == 0) {
+    s.iter_factor[r] = itf;
+    if (do_int) s.latest[r] = 0;
+    else if (do_ext) s.latest[r] = 1;
+  }
+}
+
+}  // namespace gbp

@@ -1,0 +1,267 @@
+// gbp_math.cuh — per-node FP64 math of the GBP hot path, register resident.
+//
+// Every routine states the reference function it implements (paths relative to
+// crates/magics/src in the reference).  The evaluation order of each sum and
+// product follows the order the reference's ndarray expressions produce
+// (k-ascending accumulation from 0 for mat*mat, left-to-right for the short
+// dot products), with structurally-zero terms dropped: adding an exact 0 or
+// multiplying by an exact +-1 does not change an IEEE result, so the bits match
+// a literal evaluation as long as the file is compiled with -fmad=false.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define GBP_DEV __device__ __forceinline__
+
+namespace gbp {
+
+// An inbox slot holding Message::empty() (message.rs:134-135) is encoded in the
+// first double of its record by a NaN with a private payload; arithmetic NaNs
+// never carry this payload, so a NaN-poisoned (non-empty) message stays distinct.
+constexpr unsigned long long kEmptyBits = 0x7FF8DEADBEEF0001ULL;
+GBP_DEV double empty_marker() { return __longlong_as_double((long long)kEmptyBits); }
+GBP_DEV bool is_empty_marker(double x) {
+  return (unsigned long long)__double_as_longlong(x) == kEmptyBits;
+}
+
+// 3x3 minor of a row-major 4x4 with row SR and column SC removed; the
+// determinant expression is ndarray-inverse's explicit expansion (third-party
+// `Inverse::det`, call sites marginalise_factor_distance.rs:79, variable.rs:278).
+template <int SR, int SC>
+GBP_DEV double minor3(const double (&m)[16]) {
+  constexpr int r0 = SR == 0 ? 1 : 0, r1 = SR <= 1 ? 2 : 1, r2 = SR <= 2 ? 3 : 2;
+  constexpr int c0 = SC == 0 ? 1 : 0, c1 = SC <= 1 ? 2 : 1, c2 = SC <= 2 ? 3 : 2;
+  const double a = m[r0 * 4 + c0], b = m[r0 * 4 + c1], c = m[r0 * 4 + c2];
+  const double d = m[r1 * 4 + c0], e = m[r1 * 4 + c1], f = m[r1 * 4 + c2];
+  const double g = m[r2 * 4 + c0], h = m[r2 * 4 + c1], i = m[r2 * 4 + c2];
+  return a * e * i + b * f * g + c * d * h - c * e * g - b * d * i - a * f * h;
+}
+
+// `Inverse::inv` for 4x4: adjugate / det, None iff det == 0.
+GBP_DEV bool inv4(const double (&m)[16], double (&o)[16]) {
+  const double m00 = minor3<0, 0>(m), m01 = minor3<0, 1>(m), m02 = minor3<0, 2>(m),
+               m03 = minor3<0, 3>(m);
+  const double det = m[0] * m00 - m[1] * m01 + m[2] * m02 - m[3] * m03;
+  if (det == 0.0) return false;
+  o[0] = m00 / det;
+  o[4] = -m01 / det;
+  o[8] = m02 / det;
+  o[12] = -m03 / det;
+  o[1] = -minor3<1, 0>(m) / det;
+  o[5] = minor3<1, 1>(m) / det;
+  o[9] = -minor3<1, 2>(m) / det;
+  o[13] = minor3<1, 3>(m) / det;
+  o[2] = minor3<2, 0>(m) / det;
+  o[6] = -minor3<2, 1>(m) / det;
+  o[10] = minor3<2, 2>(m) / det;
+  o[14] = -minor3<2, 3>(m) / det;
+  o[3] = -minor3<3, 0>(m) / det;
+  o[7] = minor3<3, 1>(m) / det;
+  o[11] = -minor3<3, 2>(m) / det;
+  o[15] = minor3<3, 3>(m) / det;
+  return true;
+}
+// Rows 0 and 1 of the inverse only (all an InterRobot Schur complement reads).
+GBP_DEV bool inv4_rows01(const double (&m)[16], double (&r0)[4], double (&r1)[4]) {
+  const double m00 = minor3<0, 0>(m), m01 = minor3<0, 1>(m), m02 = minor3<0, 2>(m),
+               m03 = minor3<0, 3>(m);
+  const double det = m[0] * m00 - m[1] * m01 + m[2] * m02 - m[3] * m03;
+  if (det == 0.0) return false;
+  r0[0] = m00 / det;
+  r1[0] = -m01 / det;
+  r0[1] = -minor3<1, 0>(m) / det;
+  r1[1] = minor3<1, 1>(m) / det;
+  r0[2] = minor3<2, 0>(m) / det;
+  r1[2] = -minor3<2, 1>(m) / det;
+  r0[3] = -minor3<3, 0>(m) / det;
+  r1[3] = minor3<3, 1>(m) / det;
+  return true;
+}
+
+// VariableNode::update_belief_and_create_factor_responses, the part after the
+// inbox sum (variable.rs:273-297): mean / covariance from (eta, lam).
+// Returns true when the covariance was (re)computed; mu is only overwritten
+// when the new covariance is finite.
+GBP_DEV bool belief_moments(const double (&eta)[4], const double (&lam)[16], double (&mu)[4],
+                            double (&cov)[16], bool &valid) {
+  bool nz = false;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) nz = nz || (lam[k] - 1e-6 > 0.0);
+  if (!nz) return false;
+  if (!inv4(lam, cov)) return false;
+  bool fin = true;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) fin = fin && isfinite(cov[k]);
+  valid = fin;
+  if (fin) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      mu[r] = 0.0 + cov[r * 4 + 0] * eta[0] + cov[r * 4 + 1] * eta[1] + cov[r * 4 + 2] * eta[2] +
+              cov[r * 4 + 3] * eta[3];
+  }
+  return true;
+}
+
+// Scalar 4x4 pattern M of the DynamicFactor potential Lambda_p = J^T Qi^-1 J over
+// (pos_i, vel_i, pos_i+1, vel_i+1); the 8x8 is M (x) I2 (dynamic.rs:22-52 and
+// factor/mod.rs:391-394).  qs = 1/sigma^2.
+struct DynM {
+  double m[4][4];
+};
+GBP_DEV DynM dyn_potential(double dt, double qs) {
+  const double p3 = 1.0 / ((dt * dt) * dt);
+  const double p2 = 1.0 / (dt * dt);
+  const double q11 = (12.0 * p3) * qs, q12 = (-6.0 * p2) * qs, q22 = (4.0 / dt) * qs;
+  const double a[4] = {q11, dt * q11 + q12, -q11, -q12};
+  const double b[4] = {q12, dt * q12 + q22, -q12, -q22};
+  DynM r;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    r.m[k][0] = a[k];
+    r.m[k][1] = a[k] * dt + b[k];
+    r.m[k][2] = -a[k];
+    r.m[k][3] = -b[k];
+  }
+  return r;
+}
+
+// FactorNode::update for a DynamicFactor, one outgoing message
+// (factor/mod.rs:412-450 + marginalise_factor_distance.rs:55-127).
+// KEEP = 0: message to the first variable (slot 0), marginalising slot 1;
+// KEEP = 1: message to the second.  `oe`/`ol` is the OTHER variable's message
+// (eta, Lambda) if `other_nonempty`.  Returns false for Message::empty().
+template <int KEEP>
+GBP_DEV bool dyn_message(const DynM &M, bool other_nonempty, const double (&oe)[4],
+                         const double (&ol)[16], double (&eta)[4], double (&lam)[16]) {
+  constexpr int A = KEEP * 2, B = (1 - KEEP) * 2;  // scalar-block offsets in M
+  // Lambda_bb = potential block + other message; index (kk, dim) -> kk*2 + dim
+  double bb[16];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const bool same = (r & 1) == (c & 1);
+      if (same) {
+        const double p = M.m[B + (r >> 1)][B + (c >> 1)];
+        bb[r * 4 + c] = other_nonempty ? p + ol[r * 4 + c] : p;
+      } else {
+        bb[r * 4 + c] = other_nonempty ? 0.0 + ol[r * 4 + c] : 0.0;
+      }
+    }
+  double bi[16];
+  if (!inv4(bb, bi)) return false;
+  double eb[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) eb[k] = other_nonempty ? 0.0 + oe[k] : 0.0;
+  // T = Lambda_ab * Binv ; Lambda_ab[(rr,d)][(kk,d)] = M[A+rr][B+kk]
+  double T[16];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int d = r & 1, rr = r >> 1;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      T[r * 4 + c] = M.m[A + rr][B + 0] * bi[(0 + d) * 4 + c] + M.m[A + rr][B + 1] * bi[(2 + d) * 4 + c];
+  }
+  bool inf = false;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const double te =
+        0.0 + T[r * 4 + 0] * eb[0] + T[r * 4 + 1] * eb[1] + T[r * 4 + 2] * eb[2] + T[r * 4 + 3] * eb[3];
+    eta[r] = 0.0 - te;  // eta_p == 0 exactly for the dynamic factor
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int dc = c & 1, cc = c >> 1;
+      // (T * Lambda_ba)[r][c], Lambda_ba[(kk,dc)][(cc,dc)] = M[B+kk][A+cc]
+      const double tl = T[r * 4 + dc] * M.m[B + 0][A + cc] + T[r * 4 + 2 + dc] * M.m[B + 1][A + cc];
+      const double aa = ((r & 1) == dc) ? M.m[A + (r >> 1)][A + cc] : 0.0;
+      const double v = aa - tl;
+      lam[r * 4 + c] = v;
+      inf = inf || isinf(v);
+    }
+  }
+  return !inf;
+}
+
+// One-row measurement factors (Obstacle / Tracking): the message is the whole
+// potential (marginalise_factor_distance.rs:63-72), Lambda[k][l] = (J_k*lm)*J_l,
+// eta[k] = (J_k*lm)*v0 with v0 = J.x + (z - h) (factor/mod.rs:391-401).
+GBP_DEV void unary_add(const double (&J)[4], double v0, double lm, double (&eta)[4],
+                       double (&lam)[16]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double g = J[k] * lm;
+    eta[k] = eta[k] + g * v0;
+#pragma unroll
+    for (int l = 0; l < 4; ++l) lam[k * 4 + l] = lam[k * 4 + l] + g * J[l];
+  }
+}
+
+// FactorNode::update for an InterRobotFactor, only the message to the variable of
+// the robot that is NOT the sender of (etaA, lamA, muA)
+// (interrobot.rs:91-226, factor/mod.rs:334-454, marginalise_factor_distance.rs).
+//   a_first    robot A's variable is slot 0 (A's id < B's id, id.rs:83-118)
+//   muA/muB    position part of the linearisation point of each slot (zeros if empty)
+//   a_nonempty whether A's variable message exists (else only the potential)
+//   dsafe      safety distance, tiny the factor's tiny_offset, lm = 1/sigma^2
+// Output: eta[0..1], lam 2x2 (rows/cols 0..1 of the 4x4; the rest is exactly 0).
+GBP_DEV bool interrobot_message(bool a_first, const double (&muA)[2], const double (&muB)[2],
+                                bool a_nonempty, const double (&etaA)[4],
+                                const double (&lamA)[16], double dsafe, double tiny, double lm,
+                                double (&eta)[2], double (&lam)[4]) {
+  const double x0 = a_first ? muA[0] : muB[0], x1 = a_first ? muA[1] : muB[1];
+  const double x4 = a_first ? muB[0] : muA[0], x5 = a_first ? muB[1] : muA[1];
+  const double e0 = x0 - x4, e1 = x1 - x5;
+  if ((0.0 + e0 * e0) + e1 * e1 >= dsafe * dsafe) return false;  // InterRobotFactor::skip
+  const double d0 = e0 + tiny, d1 = e1 + tiny;
+  const double rad = sqrt((0.0 + d0 * d0) + d1 * d1);
+  double j0[2] = {0.0, 0.0}, j4[2] = {0.0, 0.0}, h = 0.0;
+  if (rad <= dsafe) {
+    const double ca = -1.0 / dsafe / rad, cb = 1.0 / dsafe / rad;
+    j0[0] = ca * d0;
+    j0[1] = ca * d1;
+    j4[0] = cb * d0;
+    j4[1] = cb * d1;
+    h = 1.0 * (1.0 - rad / dsafe);
+  }
+  // J.x via ndarray's unrolled_dot pairing (p0+p4)+(p1+p5), then + (z - h)
+  const double v0 = ((0.0 + (j0[0] * x0 + j4[0] * x4)) + (j0[1] * x1 + j4[1] * x5)) + (0.0 - h);
+  const double jA[2] = {a_first ? j0[0] : j4[0], a_first ? j0[1] : j4[1]};
+  const double jB[2] = {a_first ? j4[0] : j0[0], a_first ? j4[1] : j0[1]};
+  const double gA[2] = {jA[0] * lm, jA[1] * lm}, gB[2] = {jB[0] * lm, jB[1] * lm};
+  double bb[16], eb[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const double p = (r < 2 && c < 2) ? gA[r] * jA[c] : 0.0;
+      bb[r * 4 + c] = a_nonempty ? p + lamA[r * 4 + c] : p;
+    }
+    const double pe = (r < 2) ? gA[r] * v0 : 0.0;
+    eb[r] = a_nonempty ? pe + etaA[r] : pe;
+  }
+  double i0[4], i1[4];
+  if (!inv4_rows01(bb, i0, i1)) return false;
+  bool inf = false;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const double ab0 = gB[r] * jA[0], ab1 = gB[r] * jA[1];  // Lambda_ab row r
+    double T[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) T[c] = ab0 * i0[c] + ab1 * i1[c];
+    const double te = 0.0 + T[0] * eb[0] + T[1] * eb[1] + T[2] * eb[2] + T[3] * eb[3];
+    eta[r] = gB[r] * v0 - te;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const double tl = T[0] * (gA[0] * jB[c]) + T[1] * (gA[1] * jB[c]);
+      const double v = gB[r] * jB[c] - tl;
+      lam[r * 2 + c] = v;
+      inf = inf || isinf(v);
+    }
+  }
+  return !inf;
+}
+
+// Rust `as u32` (saturating; obstacle.rs:153-155).
+GBP_DEV uint32_t sat_u32(double v) { return __double2uint_rz(v); }
+
+}  // namespace gbp

@@ -1,0 +1,97 @@
+// gbp_store.cuh — structure-of-arrays device store of every robot's factor graph.
+//
+// Replaces the reference's one-FactorGraph-component-per-robot storage
+// (factorgraph/factorgraph.rs:74-120: petgraph nodes + BTreeMap inboxes of boxed
+// ndarray payloads) by flat planes in HBM.  A "plane" is one scalar component
+// for every variable of every robot, index vi = robot*V + i, so a warp reading
+// one component touches consecutive doubles.
+//
+// What is stored is the minimum from which every inbox of the reference can be
+// rebuilt bit-for-bit:
+//   pub[p]   belief record (eta4, Lambda16, mu4) of each variable as of its last
+//            internal variable iteration / change_prior — this IS the message
+//            every own factor and every neighbour's InterRobot factor holds from
+//            it, up to subtracting the factor's own last message (variable.rs:301-330)
+//   m_*      the factor->variable messages of the own Dynamic/Obstacle/Tracking
+//            factors (variable inbox entries)
+//   mir      the messages a robot's variables hold from the InterRobot factors
+//            owned by its neighbours ("mirror" factors), one per (edge, i)
+//   mu_ext   position mean each variable last sent to external factors
+// pub is double buffered: a fused pass reads neighbours' records from pub[p]
+// while writing its own new record to pub[1-p].
+#pragma once
+#include <cstdint>
+
+namespace gbp {
+
+constexpr int kRec = 24;  // eta 0..3, lambda 4..19 (row major), mu 20..23
+
+struct Store {
+  int32_t N;     // robots resident on this device (local + ghost slots)
+  int32_t Nloc;  // robots this device iterates (slots [0, Nloc))
+  int32_t V;     // variables per robot
+  int64_t NV;    // plane stride = capacity * V
+
+  // ---- per variable -------------------------------------------------------
+  double *prior_eta;     // [4][NV]   VariablePrior.information_vector
+  double *prior_lam;     // [NV]      diagonal of VariablePrior.precision_matrix
+  double *pub[2];        // [24][NV]  belief record seen by factors (double buffered)
+  uint32_t *pub_epoch[2];  // [NV]    epoch of the last write of that record (0 = never)
+  double *bel_ext;       // [24][NV]  belief after the last external variable iteration
+  double *mu_ext;        // [2][NV]   position mean last delivered to external factors
+  double *mu_new;        // [2][NV]   belief position mean when the newest edges were created
+  double *cov;           // [16][NV]  VariableBelief.covariance_matrix
+  uint8_t *valid;        // [NV]      VariableBelief.valid
+  double *m_dynL;        // [20][NV]  message from Dynamic factor i-1 (eta4, Lambda16)
+  double *m_dynR;        // [20][NV]  message from Dynamic factor i
+  double *m_obs;         // [4][NV]   Obstacle message as (J0, J1, J2=J3, v0)
+  double *m_trk;         // [3][NV]   Tracking message as (J0, J1, v0)
+  double *dyn_dt;        // [NV]      delta_t of Dynamic factor i (f32 widened)
+  uint32_t *trk_record;  // [NV]      Tracking.record
+  int32_t *trk_timeout;  // [NV]      TrackingFactor.timeout (-1 = None)
+  float *trk_last;       // [2][NV]   LastMeasurement.pos (f32)
+  double *trk_value;     // [NV]      LastMeasurement.value
+
+  // ---- per robot ----------------------------------------------------------
+  float *radius;          // [cap]
+  float *t0;              // [cap]
+  float *pos;             // [2][cap]  Transform.translation x / z
+  uint8_t *antenna;       // [cap]     RadioAntenna.active
+  uint8_t *idle;          // [cap]     mission.state.idle()
+  uint8_t *finished;      // [cap]     FinishedPath
+  uint8_t *latest;        // [cap]     0: pub[p] holds the current belief, 1: bel_ext
+  uint32_t *iter_factor;  // [cap]     FactorGraph.iteration_count.factor
+  int32_t *gid;           // [cap]     global robot id of the slot (== slot on one GPU)
+  int32_t *next_wp;       // [cap]
+  int32_t *wp_off;        // [cap+1]
+  float *wp_xy;           // [2*total] interleaved x,y
+  int64_t cap;            // robot capacity (stride of per-robot planes)
+
+  // ---- edges: (receiver robot B, neighbour A), CSR by B, A ascending ------
+  int64_t *eoff;       // [Nloc+1]
+  int32_t *nlow;       // [Nloc] number of neighbours with a lower global id (inbox order, id.rs:25-61)
+  int32_t *enbr;       // [E]   slot of A
+  double *e_dsafe;     // [E]   safety distance of A's factor: multiplier * radius_A
+  uint64_t *e_rnum;    // [E]   robot_number of A's factor toward B at i = 1
+  uint32_t *e_birth;   // [E]   epoch at which the edge was created
+  uint8_t *e_new;      // [E]   1 until B's first delivered external variable message
+  double *mir;         // [6][E*(V-1)]  eta0, eta1, lam00, lam01, lam10, lam11
+  int64_t E;
+  int64_t EV;          // plane stride of mir = Ecap*(V-1)
+
+  // ---- environment ----------------------------------------------------------
+  const uint8_t *sdf;  // red channel, row 0 = top
+  int32_t sdf_w, sdf_h;
+  double world_w, world_h, jac_delta;
+
+  // ---- scalars widened once (robot.rs:1238-1240,1272,1318,1517-1522) ------
+  double qs_dyn;   // 1/sigma_dynamics^2
+  double lm_ir;    // 1/sigma_interrobot^2
+  double lm_obs;   // 1/sigma_obstacle^2
+  double lm_trk;   // 1/sigma_tracking^2
+  double tiny_scale;  // f64::from(1e-6_f32)
+  double trk_switch_padding, trk_attraction;
+  uint8_t en_dyn, en_ir, en_obs, en_trk;
+};
+
+}  // namespace gbp

@@ -1,0 +1,199 @@
+// gbp_topology.cuh — InterRobot factor creation / deletion on the device.
+//
+// Replaces update_robot_neighbours (planner/robot.rs:1362-1384, an all-pairs
+// O(N^2) f32 distance test), delete_interrobot_factors (:1386-1439) and
+// create_interrobot_factors (:1441-1586) by a sort-based spatial hash:
+//   1. cell = floor(pos / (1.001 * comms radius)); key = hash(cell) (k_cell_keys)
+//   2. radix sort (key, robot) (cub::DeviceRadixSort)
+//   3. per robot: scan the 3x3 neighbouring cells by binary search in the sorted
+//      keys, test the reference's exact f32 predicate !(R < |a-b|), count, then
+//      fill; each robot's list is sorted by robot id (BTreeSet order)
+//   4. diff against the previous CSR: surviving edges keep their state, new
+//      edges get robot_number in the reference's creation order (robots in id
+//      order -> new neighbours ascending -> i = 1..V-1, robot.rs:1500-1541).
+// Connectivity, ordering and robot_number are bit-exact; nothing is approximate.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "gbp_math.cuh"
+#include "gbp_store.cuh"
+
+namespace gbp {
+
+__host__ __device__ inline uint32_t cell_hash(int32_t cx, int32_t cz) {
+  uint32_t h = uint32_t(cx) * 0x9E3779B1u ^ (uint32_t(cz) * 0x85EBCA77u + 0xC2B2AE3Du);
+  h ^= h >> 15;
+  h *= 0x2C1B3C6Du;
+  h ^= h >> 12;
+  return h;
+}
+
+// glam Vec3::distance on Transform.translation (x, -1.5, z) in f32, no FMA
+// (robot.rs:1373-1374): sqrt((dx*dx + dy*dy) + dz*dz) with dy = 0.
+__device__ __forceinline__ bool within_comms(float ax, float az, float bx, float bz, float R) {
+  const float dx = __fsub_rn(ax, bx), dz = __fsub_rn(az, bz);
+  const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(0.0f, 0.0f)), __fmul_rn(dz, dz));
+  const float d = __fsqrt_rn(d2);
+  return !(R < d);
+}
+
+__global__ void k_cell_keys(int32_t n, const float *__restrict__ px, const float *__restrict__ pz,
+                            double cell, int32_t *cx, int32_t *cz, uint32_t *keys, int32_t *idx) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int32_t x = int32_t(floor(double(px[r]) / cell)), z = int32_t(floor(double(pz[r]) / cell));
+  cx[r] = x;
+  cz[r] = z;
+  keys[r] = cell_hash(x, z);
+  idx[r] = r;
+}
+
+__device__ __forceinline__ int32_t lower_bound_u32(const uint32_t *a, int32_t n, uint32_t key) {
+  int32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int32_t mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// Pass 1 (FILL = false): count robots within comms range of each of the robots
+// [first, first+count).  Pass 2 (FILL = true): write them and sort ascending.
+// `gid` maps a slot to its global robot id (the reference's Entity order).
+template <bool FILL>
+__global__ void k_neighbours(int32_t nall, int32_t first, int32_t count, const float *__restrict__ px,
+                             const float *__restrict__ pz, const int32_t *__restrict__ cx,
+                             const int32_t *__restrict__ cz, const uint32_t *__restrict__ keys_sorted,
+                             const int32_t *__restrict__ idx_sorted, float R, int64_t *cnt_or_off,
+                             int32_t *nbr) {
+  const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const int32_t r = first + t;
+  const float ax = px[r], az = pz[r];
+  const int32_t mx = cx[r], mz = cz[r];
+  int64_t n = 0;
+  const int64_t base = FILL ? cnt_or_off[t] : 0;
+  for (int dz = -1; dz <= 1; ++dz)
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int32_t qx = mx + dx, qz = mz + dz;
+      const uint32_t key = cell_hash(qx, qz);
+      for (int32_t j = lower_bound_u32(keys_sorted, nall, key); j < nall && keys_sorted[j] == key; ++j) {
+        const int32_t o = idx_sorted[j];
+        if (o == r || cx[o] != qx || cz[o] != qz) continue;
+        if (!within_comms(ax, az, px[o], pz[o], R)) continue;
+        if (FILL) nbr[base + n] = o;
+        ++n;
+      }
+    }
+  if (!FILL) {
+    cnt_or_off[t] = n;
+  } else {
+    // insertion sort by robot id (BTreeSet<Entity> order, robot.rs:1369-1382)
+    int32_t *a = nbr + base;
+    for (int64_t u = 1; u < n; ++u) {
+      const int32_t v = a[u];
+      int64_t w = u - 1;
+      while (w >= 0 && a[w] > v) {
+        a[w + 1] = a[w];
+        --w;
+      }
+      a[w + 1] = v;
+    }
+  }
+}
+
+// For every robot r in [0, n): match its new neighbour list against the old one.
+//   map[e]    old edge index of new edge e, or -1 when the edge is new
+//   newcnt[r] number of new edges of r, nlow[r] neighbours with a lower id
+__global__ void k_edge_diff(int32_t n, const int64_t *__restrict__ noff, const int32_t *__restrict__ nnbr,
+                            const int64_t *__restrict__ ooff, const int32_t *__restrict__ onbr,
+                            int32_t n_old, int64_t *map, int64_t *newcnt, int32_t *nlow) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  int64_t lo0 = 0, hi0 = 0;
+  if (r < n_old && ooff) {
+    lo0 = ooff[r];
+    hi0 = ooff[r + 1];
+  }
+  int64_t fresh = 0;
+  int32_t low = 0;
+  for (int64_t e = noff[r]; e < noff[r + 1]; ++e) {
+    const int32_t a = nnbr[e];
+    if (a < r) ++low;
+    int64_t lo = lo0, hi = hi0;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (onbr[mid] < a) lo = mid + 1;
+      else hi = mid;
+    }
+    const bool found = lo < hi0 && onbr[lo] == a;
+    map[e] = found ? lo : -1;
+    if (!found) ++fresh;
+  }
+  newcnt[r] = fresh;
+  nlow[r] = low;
+}
+
+// Per new-CSR edge (r <- a): carry over or initialise the edge scalars.
+// robot_number of a's factor toward r at i=1 = counter0 + (V-1) * (rank of the
+// directed pair (a, r) among all new pairs ordered by (a, r)).
+__global__ void k_edge_assign(int32_t n, int32_t V, const int64_t *__restrict__ noff,
+                              const int32_t *__restrict__ nnbr, const int64_t *__restrict__ map,
+                              const int64_t *__restrict__ newoff, const float *__restrict__ radius,
+                              double safety_mult, uint64_t counter0, uint32_t epoch,
+                              const double *__restrict__ o_dsafe, const uint64_t *__restrict__ o_rnum,
+                              const uint32_t *__restrict__ o_birth, const uint8_t *__restrict__ o_new,
+                              double *e_dsafe, uint64_t *e_rnum, uint32_t *e_birth, uint8_t *e_new) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  for (int64_t e = noff[r]; e < noff[r + 1]; ++e) {
+    const int32_t a = nnbr[e];
+    const int64_t old = map[e];
+    e_dsafe[e] = safety_mult * double(radius[a]);
+    if (old >= 0) {
+      e_rnum[e] = o_rnum[old];
+      e_birth[e] = o_birth[old];
+      e_new[e] = o_new[old];
+    } else {
+      int64_t rank = 0;
+      for (int64_t e2 = noff[a]; e2 < noff[a + 1]; ++e2)
+        if (map[e2] < 0 && nnbr[e2] < r) ++rank;
+      e_rnum[e] = counter0 + uint64_t(V - 1) * uint64_t(newoff[a] + rank);
+      e_birth[e] = epoch;
+      e_new[e] = 1;
+    }
+  }
+}
+
+// Mirror messages of surviving edges move to their new slot; new edges start
+// Empty (add_external_edge, factorgraph.rs:340-353).
+__global__ void k_mirror_move(int64_t total, int32_t Vm1, const int64_t *__restrict__ map,
+                              const double *__restrict__ omir, int64_t oEV, double *nmir, int64_t nEV) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int64_t e = t / Vm1, i = t - e * Vm1;
+  const int64_t old = map[e];
+  if (old < 0) {
+    nmir[t] = empty_marker();
+    return;
+  }
+  const int64_t o = old * Vm1 + i;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) nmir[k * nEV + t] = omir[k * oEV + o];
+}
+
+// Snapshot of the current belief position mean of robots that gained edges:
+// the new factor's inbox entry for this robot's variable is its belief at
+// creation time (robot.rs:1557-1585, variable.rs:234-240).
+__global__ void k_snapshot_mu_new(Store s, int p, const int64_t *__restrict__ newcnt) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= int64_t(s.Nloc) * s.V) return;
+  const int64_t r = t / s.V;
+  if (newcnt[r] == 0) return;
+  const double *rec = s.latest[r] ? s.bel_ext : s.pub[p];
+  s.mu_new[t] = rec[20 * s.NV + t];
+  s.mu_new[s.NV + t] = rec[21 * s.NV + t];
+}
+
+}  // namespace gbp

@@ -1,0 +1,229 @@
+"""Synthetic swarm generators for the BASELINE.json configs.
+
+Everything here is host-side INPUT construction in numpy: robot placement,
+`variable_timesteps`, and the initial variable means of `RobotBundle::new`
+(crates/magics/src/planner/robot.rs:1157-1192, f32 arithmetic).  The outputs
+are plain arrays accepted by both `magics_b200.World.add_robots` and the test
+oracle, so a parity test feeds identical bits to both sides.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field, replace
+
+import numpy as np
+
+from .config import GbpConfig
+from .world import get_variable_timesteps
+
+f32 = np.float32
+
+
+@dataclass
+class Swarm:
+    cfg: GbpConfig
+    radii: np.ndarray        # (n,) f32
+    timesteps: np.ndarray    # (V,) u32
+    init_means: np.ndarray   # (n, V, 4) f64
+    positions: np.ndarray    # (n, 2) f32
+    wp_offsets: np.ndarray   # (n+1,) i32
+    wp_xy: np.ndarray        # (sum, 2) f32
+    sdf: np.ndarray | None = None  # (h, w, 3) u8
+    name: str = ""
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def n(self) -> int:
+        return int(self.radii.shape[0])
+
+    def add_to(self, world):
+        if self.sdf is not None:
+            world.set_sdf(self.sdf)
+        world.add_robots(self.radii, self.timesteps, self.init_means, self.positions, self.wp_offsets, self.wp_xy)
+        return world
+
+    def slice(self, lo: int, hi: int) -> "Swarm":
+        a, b = int(self.wp_offsets[lo]), int(self.wp_offsets[hi])
+        return replace(self, radii=self.radii[lo:hi], init_means=self.init_means[lo:hi],
+                       positions=self.positions[lo:hi], wp_offsets=(self.wp_offsets[lo:hi + 1] - a).astype(np.int32),
+                       wp_xy=self.wp_xy[a:b])
+
+
+def lookahead_horizon(target_speed: float, planning_horizon: float) -> int:
+    """(target_speed * planning_horizon) as u32, f32 product (spawner.rs:563-564)."""
+    return int(f32(target_speed) * f32(planning_horizon))
+
+
+def initial_means(start_xy: np.ndarray, goal_xy: np.ndarray, timesteps: np.ndarray, target_speed: float,
+                  planning_horizon: float) -> np.ndarray:
+    """RobotBundle::new initial variable means (robot.rs:1157-1192) for routes start -> goal.
+
+    Vec4 state (x, y, vx, vy) in f32; the initial velocity points at the first
+    waypoint with magnitude target_speed (spawner.rs:470-482) and the last
+    waypoint inherits it (spawner.rs:528-530), so start2goal has zero velocity part.
+    """
+    s = np.asarray(start_xy, f32)
+    g = np.asarray(goal_xy, f32)
+    d = g - s
+    length = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]).astype(f32)
+    safe = np.where(length > 0, length, f32(1))
+    unit = (d / safe[:, None]).astype(f32)
+    unit[length == 0] = 0
+    vel = (unit * f32(target_speed)).astype(f32)
+    start4 = np.concatenate([s, vel], axis=1).astype(f32)
+    reach = np.minimum(length, f32(planning_horizon) * f32(target_speed)).astype(f32)
+    s2g4 = np.concatenate([d, np.zeros_like(d)], axis=1).astype(f32)
+    inv_len = (f32(1) / safe).astype(f32)
+    horizon4 = (start4 + reach[:, None] * (s2g4 * inv_len[:, None]).astype(f32)).astype(f32)
+    ts = np.asarray(timesteps, np.uint32)
+    frac = (ts.astype(f32) / f32(ts[-1])).astype(f32)  # variable_timestep as f32 / last as f32
+    diff = (horizon4 - start4).astype(f32)
+    means = (start4[:, None, :] + (diff[:, None, :] * frac[None, :, None]).astype(f32)).astype(f32)
+    return means.astype(np.float64)
+
+
+def _finish(cfg, radii, starts, goals, timesteps, planning_horizon, sdf=None, name="", waypoints=None, meta=None):
+    n = starts.shape[0]
+    if waypoints is None:
+        wp_xy = np.stack([starts, goals], axis=1).reshape(-1, 2).astype(f32)
+        wp_off = (np.arange(n + 1) * 2).astype(np.int32)
+        first = goals
+    else:
+        wp_off = np.zeros(n + 1, np.int32)
+        wp_off[1:] = np.cumsum([len(w) for w in waypoints])
+        wp_xy = np.concatenate(waypoints, axis=0).astype(f32)
+        first = np.stack([w[1] for w in waypoints]).astype(f32)
+    means = initial_means(starts, first, timesteps, cfg.target_speed, planning_horizon)
+    return Swarm(cfg=cfg, radii=np.asarray(radii, f32), timesteps=np.asarray(timesteps, np.uint32), init_means=means,
+                 positions=np.asarray(starts, f32), wp_offsets=wp_off, wp_xy=wp_xy, sdf=sdf, name=name,
+                 meta=meta or {})
+
+
+def white_sdf(w=200, h=200):
+    return np.full((h, w, 3), 255, np.uint8)
+
+
+def synthetic_sdf(w, h, seed=0, n_rect=24, blur_px=4.0):
+    """Deterministic SDF-like image: dark rectangles on white, Gaussian blurred.
+    (Stand-in for env_to_png::env_to_sdf_image, which is SURVEY §8 next-2.)"""
+    from scipy.ndimage import gaussian_filter
+
+    rng = np.random.default_rng(seed)
+    img = np.full((h, w), 255.0)
+    for _ in range(n_rect):
+        rw, rh = rng.integers(max(2, w // 40), max(3, w // 8)), rng.integers(max(2, h // 40), max(3, h // 8))
+        x0, y0 = rng.integers(0, w - rw), rng.integers(0, h - rh)
+        img[y0:y0 + rh, x0:x0 + rw] = 0.0
+    img = gaussian_filter(img, blur_px)
+    u8 = np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    return np.repeat(u8[:, :, None], 3, axis=2)
+
+
+def circle(n=30, circle_radius=50.0, robot_radius=1.5, cfg: GbpConfig | None = None, planning_horizon=5.0,
+           lookahead_multiple=3):
+    """Config 1: `Circle Experiment` geometry with the default config.toml scalars."""
+    cfg = cfg or GbpConfig(world_width=100.0, world_height=100.0)
+    ts = get_variable_timesteps(lookahead_horizon(cfg.target_speed, planning_horizon), lookahead_multiple)
+    cfg = replace(cfg, num_variables=int(ts.shape[0]))
+    ang = (np.arange(n, dtype=np.float64) * (2.0 * np.pi / n))
+    starts = np.stack([circle_radius * np.cos(ang), circle_radius * np.sin(ang)], axis=1).astype(f32)
+    goals = (-starts).astype(f32)
+    return _finish(cfg, np.full(n, robot_radius, f32), starts, goals, ts, planning_horizon, sdf=white_sdf(),
+                   name=f"circle-{n}")
+
+
+def rings(n=100_000, spacing=8.0, ring_gap=44.0, r0=400.0, cfg: GbpConfig | None = None, planning_horizon=5.0,
+          lookahead_multiple=3, robot_radius=1.0, seed=0):
+    """Config 4: synthetic circle swarm, concentric rings with `spacing` metres
+    between robots along a ring (K ~ 4 at comms radius 20) and rings further
+    apart than 2x the comms radius; goal = antipode on the own ring."""
+    cfg = cfg or GbpConfig(target_speed=3.6, world_width=100.0, world_height=100.0)
+    ts = get_variable_timesteps(lookahead_horizon(cfg.target_speed, planning_horizon), lookahead_multiple)
+    cfg = replace(cfg, num_variables=int(ts.shape[0]))
+    xs, ys = [], []
+    left, k = n, 0
+    while left > 0:
+        rad = r0 + k * ring_gap
+        m = min(left, max(8, int(2.0 * np.pi * rad / spacing)))
+        ang = np.arange(m, dtype=np.float64) * (2.0 * np.pi / max(m, int(2.0 * np.pi * rad / spacing)))
+        xs.append(rad * np.cos(ang))
+        ys.append(rad * np.sin(ang))
+        left -= m
+        k += 1
+    starts = np.stack([np.concatenate(xs), np.concatenate(ys)], axis=1).astype(f32)
+    goals = (-starts).astype(f32)
+    return _finish(cfg, np.full(n, robot_radius, f32), starts, goals, ts, planning_horizon, sdf=white_sdf(),
+                   name=f"rings-{n}", meta={"rings": k})
+
+
+def lattice(nx=1000, ny=1000, pitch=12.0, cfg: GbpConfig | None = None, planning_horizon=5.0, lookahead_multiple=3,
+            robot_radius=1.0, goal_ahead=500.0):
+    """Config 5: uniform grid, every interior robot has K = 8 at comms radius 20
+    (4 at `pitch`, 4 at pitch*sqrt(2)); all head +x toward a goal 500 m ahead.
+    Robot id = row-major (iy * nx + ix) so vertical slabs / rows are contiguous."""
+    cfg = cfg or GbpConfig(target_speed=3.6, world_width=100.0, world_height=100.0)
+    ts = get_variable_timesteps(lookahead_horizon(cfg.target_speed, planning_horizon), lookahead_multiple)
+    cfg = replace(cfg, num_variables=int(ts.shape[0]))
+    ix, iy = np.meshgrid(np.arange(nx), np.arange(ny))
+    x = (ix.reshape(-1) - (nx - 1) / 2.0) * pitch
+    y = (iy.reshape(-1) - (ny - 1) / 2.0) * pitch
+    starts = np.stack([x, y], axis=1).astype(f32)
+    goals = (starts + np.array([goal_ahead, 0.0], f32)).astype(f32)
+    n = nx * ny
+    return _finish(cfg, np.full(n, robot_radius, f32), starts, goals, ts, planning_horizon, sdf=white_sdf(),
+                   name=f"lattice-{nx}x{ny}", meta={"nx": nx, "ny": ny, "pitch": pitch})
+
+
+def junction_twoway(per_lane=3, seed=0):
+    """Config 2: `Structured Junction Twoway` scalars (all four factor kinds, V=12),
+    12 lanes (4 arms x {left, straight, right}) through a '+' junction with a
+    waypoint at the junction centre; lateral jitter from a fixed-seed PCG."""
+    cfg = GbpConfig(sigma_factor_dynamics=0.1, sigma_factor_interrobot=0.005, sigma_factor_obstacle=0.005,
+                    sigma_factor_tracking=0.15, safety_distance_multiplier=2.5, comms_radius=20.0, target_speed=5.0,
+                    enable_tracking=1, world_width=100.0, world_height=100.0)
+    ts = get_variable_timesteps(lookahead_horizon(cfg.target_speed, 5.0), 3)
+    cfg = replace(cfg, num_variables=int(ts.shape[0]))
+    rng = np.random.default_rng(seed)
+    arms = np.array([[-45.0, 0.0], [45.0, 0.0], [0.0, -45.0], [0.0, 45.0]])
+    wps, starts = [], []
+    for a in range(4):
+        for b in range(4):
+            if a == b:
+                continue
+            for k in range(per_lane):
+                direction = -arms[a] / np.linalg.norm(arms[a])
+                normal = np.array([-direction[1], direction[0]])
+                lateral = rng.uniform(-2.0, 2.0)
+                s = arms[a] - direction * (6.0 * k) * 0 + direction * (-6.0 * k) + normal * lateral
+                mid = normal * lateral * 0.5
+                e = arms[b] + normal * rng.uniform(-2.0, 2.0)
+                wps.append(np.array([s, mid, e], f32))
+                starts.append(s)
+    starts = np.array(starts, f32)
+    n = starts.shape[0]
+    # '+' shaped road: white (free) cross on dark background, blur sigma 2 px
+    from scipy.ndimage import gaussian_filter
+
+    img = np.zeros((200, 200))
+    img[84:116, :] = 255.0
+    img[:, 84:116] = 255.0
+    u8 = np.clip(np.rint(gaussian_filter(img, 2.0)), 0, 255).astype(np.uint8)
+    sdf = np.repeat(u8[:, :, None], 3, axis=2)
+    goals = np.array([w[1] for w in wps], f32)
+    return _finish(cfg, np.full(n, 1.0, f32), starts, goals, ts, 5.0, sdf=sdf, name=f"junction-twoway-{n}",
+                   waypoints=wps)
+
+
+def complex_environment(n=19, seed=0):
+    """Config 3: `Collaborative Complex` sizes: world 250x175, SDF 2000x1400, V=12,
+    obstacle factors on, tracking off; robots cross the map left <-> right."""
+    cfg = GbpConfig(sigma_factor_interrobot=0.005, sigma_factor_obstacle=0.005, target_speed=5.0,
+                    world_width=250.0, world_height=175.0)
+    ts = get_variable_timesteps(lookahead_horizon(cfg.target_speed, 5.0), 3)
+    cfg = replace(cfg, num_variables=int(ts.shape[0]))
+    rng = np.random.default_rng(seed)
+    y = np.linspace(-80.0, 80.0, n)
+    side = np.where(np.arange(n) % 2 == 0, -1.0, 1.0)
+    starts = np.stack([side * 118.0 + rng.uniform(-2, 2, n), y], axis=1).astype(f32)
+    goals = np.stack([-side * 118.0, y[::-1]], axis=1).astype(f32)
+    sdf = synthetic_sdf(2000, 1400, seed=seed, n_rect=40, blur_px=4.0)
+    return _finish(cfg, np.full(n, 1.0, f32), starts, goals, ts, 5.0, sdf=sdf, name=f"complex-{n}")

@@ -1,0 +1,268 @@
+"""Host-side mirror of the reference's FactorGraph / RobotPlugin interface for the
+GBP hot path, forwarding to the CUDA engine through the C ABI (include/gbp_b200.h).
+
+Method names follow the reference (crates/magics/src/planner/robot.rs and
+factorgraph/factorgraph.rs): `update_topology` = update_robot_neighbours +
+delete/create_interrobot_factors, `update_prior_of_horizon_state`,
+`update_prior_of_current_state`, `iterate` = iterate_gbp_v2, and the four
+`*_iteration` half-steps.  There is no CPU path: the library must be built
+(`__graft_entry__.build()`) and a CUDA device must be present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .config import CConfig, GbpConfig
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libgbp_b200.so")
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree CUDA engine; raises if it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} is missing: build the CUDA engine first (python -c 'import __graft_entry__ as g; g.build()'). "
+            "magics_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(path)
+    lib.gbp_last_error.restype = C.c_char_p
+    lib.gbp_world_create.restype = C.c_void_p
+    lib.gbp_world_create.argtypes = [C.POINTER(CConfig), C.c_int32]
+    lib.gbp_world_destroy.argtypes = [C.c_void_p]
+    lib.gbp_world_read_connections.restype = C.c_int64
+    lib.gbp_world_kernel_launches.restype = C.c_int64
+    lib.gbp_world_kernel_launches.argtypes = [C.c_void_p]
+    lib.gbp_world_num_robots.argtypes = [C.c_void_p]
+    _LIB = lib
+    return lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def gbp_schedule(kind: int, internal: int, external: int):
+    """GbpSchedule::schedule (gbp_schedule/src/schedules/mod.rs:60-81)."""
+    lib = load_library()
+    oi = np.zeros(256, np.uint8)
+    oe = np.zeros(256, np.uint8)
+    n = lib.gbp_schedule(C.c_int32(kind), C.c_uint8(internal), C.c_uint8(external), _p(oi, C.c_uint8), _p(oe, C.c_uint8))
+    if n < 0:
+        raise ValueError(lib.gbp_last_error().decode())
+    return oi[:n].astype(bool), oe[:n].astype(bool)
+
+
+def get_variable_timesteps(lookahead_horizon: int, lookahead_multiple: int) -> np.ndarray:
+    """utils::get_variable_timesteps (utils.rs:35-75)."""
+    lib = load_library()
+    out = np.zeros(4096, np.uint32)
+    n = lib.gbp_variable_timesteps(C.c_uint32(lookahead_horizon), C.c_uint32(lookahead_multiple), _p(out, C.c_uint32), 4096)
+    if n < 0:
+        raise ValueError(lib.gbp_last_error().decode())
+    return out[:n].copy()
+
+
+class World:
+    """All robots' factor graphs on one B200 (device store + fused kernels)."""
+
+    def __init__(self, cfg: GbpConfig, device: int = 0):
+        self._lib = load_library()
+        self.cfg = cfg
+        self.V = int(cfg.num_variables)
+        self._c = cfg.to_c()
+        self._h = self._lib.gbp_world_create(C.byref(self._c), int(device))
+        if not self._h:
+            raise RuntimeError("gbp_world_create failed: " + self._lib.gbp_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gbp_world_destroy(C.c_void_p(self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _call(self, name, *args):
+        rc = getattr(self._lib, name)(C.c_void_p(self._h), *args)
+        if rc < 0:
+            raise RuntimeError(f"{name} failed ({rc}): " + self._lib.gbp_last_error().decode())
+        return rc
+
+    @property
+    def num_robots(self) -> int:
+        return int(self._lib.gbp_world_num_robots(C.c_void_p(self._h)))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._lib.gbp_world_kernel_launches(C.c_void_p(self._h)))
+
+    # ---- construction ----------------------------------------------------
+    def set_sdf(self, rgb8: np.ndarray):
+        rgb8 = np.ascontiguousarray(rgb8, np.uint8)
+        h, w = rgb8.shape[:2]
+        self._call("gbp_world_set_sdf", _p(rgb8, C.c_uint8), C.c_int32(w), C.c_int32(h))
+
+    def add_robots(self, radii, timesteps, init_means, positions, wp_offsets, wp_xy):
+        radii = np.ascontiguousarray(radii, np.float32)
+        timesteps = np.ascontiguousarray(timesteps, np.uint32)
+        init_means = np.ascontiguousarray(init_means, np.float64)
+        positions = np.ascontiguousarray(positions, np.float32)
+        wp_offsets = np.ascontiguousarray(wp_offsets, np.int32)
+        wp_xy = np.ascontiguousarray(wp_xy, np.float32)
+        n = radii.shape[0]
+        if timesteps.shape[0] != self.V or init_means.size != n * self.V * 4:
+            raise ValueError("add_robots: shape mismatch")
+        self._call("gbp_world_add_robots", C.c_int32(n), _p(radii, C.c_float), _p(timesteps, C.c_uint32),
+                   _p(init_means, C.c_double), _p(positions, C.c_float), _p(wp_offsets, C.c_int32),
+                   _p(wp_xy, C.c_float))
+
+    # ---- per-tick systems ------------------------------------------------
+    def update_topology(self):
+        self._call("gbp_world_update_topology")
+
+    def set_comms(self, antenna_active=None, idle=None):
+        a = None if antenna_active is None else np.ascontiguousarray(antenna_active, np.uint8)
+        i = None if idle is None else np.ascontiguousarray(idle, np.uint8)
+        self._call("gbp_world_set_comms", _p(a, C.c_uint8), _p(i, C.c_uint8))
+
+    def set_waypoint_index(self, idx):
+        idx = np.ascontiguousarray(idx, np.int32)
+        self._call("gbp_world_set_waypoint_index", _p(idx, C.c_int32))
+
+    def update_prior_of_horizon_state(self):
+        self._call("gbp_world_update_prior_of_horizon_state")
+
+    def update_prior_of_current_state(self):
+        self._call("gbp_world_update_prior_of_current_state")
+
+    def change_prior_of_variable(self, variable_index, robots, new_means):
+        robots = np.ascontiguousarray(robots, np.int32)
+        new_means = np.ascontiguousarray(new_means, np.float64)
+        self._call("gbp_world_change_prior_of_variable", C.c_int32(variable_index), C.c_int32(robots.shape[0]),
+                   _p(robots, C.c_int32), _p(new_means, C.c_double))
+
+    def iterate(self):
+        self._call("gbp_world_iterate")
+
+    def iterate_schedule(self, internal, external):
+        i = np.ascontiguousarray(internal, np.uint8)
+        e = np.ascontiguousarray(external, np.uint8)
+        self._call("gbp_world_iterate_schedule", C.c_int32(i.shape[0]), _p(i, C.c_uint8), _p(e, C.c_uint8))
+
+    def internal_factor_iteration(self):
+        self._call("gbp_world_internal_factor_iteration")
+
+    def internal_variable_iteration(self):
+        self._call("gbp_world_internal_variable_iteration")
+
+    def external_factor_iteration(self):
+        self._call("gbp_world_external_factor_iteration")
+
+    def external_variable_iteration(self):
+        self._call("gbp_world_external_variable_iteration")
+
+    def step(self):
+        self._call("gbp_world_step")
+
+    def change_factor_enabled(self, kind, enabled):
+        self._call("gbp_world_change_factor_enabled", C.c_int32(kind), C.c_uint8(int(enabled)))
+
+    def set_safety_distance_multiplier(self, m):
+        self._call("gbp_world_set_safety_distance_multiplier", C.c_float(m))
+
+    def set_schedule(self, kind, internal, external):
+        self._call("gbp_world_set_schedule", C.c_int32(kind), C.c_int32(internal), C.c_int32(external))
+
+    # ---- read-back -------------------------------------------------------
+    def read_beliefs(self, eta=True, lam=True, mean=True, cov=True, valid=True):
+        n, V = self.num_robots, self.V
+        out = {}
+        a_eta = np.zeros((n, V, 4)) if eta else None
+        a_lam = np.zeros((n, V, 4, 4)) if lam else None
+        a_mean = np.zeros((n, V, 4)) if mean else None
+        a_cov = np.zeros((n, V, 4, 4)) if cov else None
+        a_valid = np.zeros((n, V), np.uint8) if valid else None
+        self._call("gbp_world_read_beliefs", _p(a_eta, C.c_double), _p(a_lam, C.c_double), _p(a_mean, C.c_double),
+                   _p(a_cov, C.c_double), _p(a_valid, C.c_uint8))
+        if eta:
+            out["eta"] = a_eta
+        if lam:
+            out["lam"] = a_lam
+        if mean:
+            out["mean"] = a_mean
+        if cov:
+            out["cov"] = a_cov
+        if valid:
+            out["valid"] = a_valid.astype(bool)
+        return out
+
+    def read_positions(self):
+        xy = np.zeros((self.num_robots, 2), np.float32)
+        self._call("gbp_world_read_positions", _p(xy, C.c_float))
+        return xy
+
+    def read_connections(self):
+        n = self.num_robots
+        counts = self.node_counts()
+        cap = max(1, int(counts[4]) // max(1, self.V - 1))
+        off = np.zeros(n + 1, np.int64)
+        nb = np.zeros(cap, np.int32)
+        rn = np.zeros(cap, np.int64)
+        e = self._lib.gbp_world_read_connections(C.c_void_p(self._h), _p(off, C.c_int64), _p(nb, C.c_int32),
+                                                 _p(rn, C.c_int64), C.c_int64(cap))
+        if e < 0:
+            raise RuntimeError("gbp_world_read_connections failed: " + self._lib.gbp_last_error().decode())
+        return off, nb[:e].copy(), rn[:e].copy()
+
+    def sdf_lookup(self, xy):
+        xy = np.ascontiguousarray(xy, np.float64)
+        m = xy.shape[0]
+        px, py, val = np.zeros(m, np.uint32), np.zeros(m, np.uint32), np.zeros(m)
+        self._call("gbp_world_sdf_lookup", C.c_int32(m), _p(xy, C.c_double), _p(px, C.c_uint32), _p(py, C.c_uint32),
+                   _p(val, C.c_double))
+        return px, py, val
+
+    def node_counts(self):
+        out = np.zeros(5, np.int64)
+        self._call("gbp_world_node_counts", _p(out, C.c_int64))
+        return out
+
+    PROFILE_KINDS = ("iterate_int", "iterate_ext", "iterate_ext_int", "topology", "priors")
+
+    def set_profiling(self, on: bool):
+        self._call("gbp_world_set_profiling", C.c_int32(int(on)))
+
+    def read_profile(self) -> dict:
+        out = {}
+        for k, name in enumerate(self.PROFILE_KINDS):
+            cnt, ms = C.c_int64(0), C.c_double(0)
+            self._call("gbp_world_read_profile", C.c_int32(k), C.byref(cnt), C.byref(ms))
+            out[name] = {"count": int(cnt.value), "ms": float(ms.value)}
+        return out
+
+    # ---- timing helpers (CUDA events on the engine's own stream) ----------
+    def sync(self):
+        self._call("gbp_world_sync")
+
+    def timer_start(self):
+        self._call("gbp_world_timer_start")
+
+    def timer_stop_ms(self) -> float:
+        ms = C.c_float(0)
+        self._call("gbp_world_timer_stop_ms", C.byref(ms))
+        return float(ms.value)

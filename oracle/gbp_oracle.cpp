@@ -1,0 +1,1390 @@
+// gbp_oracle.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// A deliberately literal, single-source CPU restatement of the GBP hot path of
+// AU-Master-Thesis/magics (Rust), used only as the parity checker by tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+// Nothing under magics_b200/ may include, link or call this file.
+//
+// The reference cannot be compiled here (no Rust toolchain, ~600 crates, nightly),
+// so this follows the Rust source function by function; every function cites the
+// file:line it restates (paths relative to /root/reference/crates/magics/src
+// unless another crate is named).  It keeps the reference's data-structure
+// choices on purpose: one graph object per robot, heap-allocated dynamically
+// sized vectors/matrices (ndarray stand-ins), ordered-map inboxes keyed by
+// (graph id, node index) (BTreeMap stand-ins), boxed optional message payloads.
+//
+// PARITY PINNING.  Pinned by the reference's own tests: marginalise block
+// extraction / single-neighbour pass-through (marginalise_factor_distance.rs:182-233),
+// get_variable_timesteps (utils.rs:95-133), the gbp_schedule sequence tests.
+// PARITY UNPINNED for FactorNode::update, the factors' measure/jacobian, the
+// belief update and a whole GBP iterate: the reference ships no test or golden
+// vector for them, and the 4x4 `.inv()` comes from the un-vendored third-party
+// crate ndarray-inverse 0.1.9 (Cargo.lock:4870-4873).  Its published algorithm
+// (determinant by explicit expansion; inverse = adjugate / det; None iff det == 0)
+// is restated in `inv()` below.  ndarray 0.15.6 `.dot` is restated as: mat*mat =
+// k-ascending accumulation from 0 (matrixmultiply), mat*vec = per-row
+// `unrolled_dot` (ndarray numeric_util.rs: eight partial sums combined
+// (p0+p4)+(p1+p5)+(p2+p6)+(p3+p7), then the tail sequentially).
+//
+// Build: g++ -O2 -std=c++17 -ffp-contract=off -pthread -shared -fPIC (see Makefile).
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <memory>
+#include <optional>
+#include <set>
+#include <atomic>
+#include <string>
+#include <thread>
+#include <utility>
+#include <vector>
+
+namespace {
+
+constexpr int DOFS = 4;  // factorgraph/mod.rs:21
+
+// Stand-in for Bevy's ComputeTaskPool behind Query::par_iter_mut (robot.rs:1789):
+// dynamic chunks of `grain` items over `threads` std::threads.
+template <class F>
+void parallel_for(int n, int threads, int grain, F &&body) {
+  if (threads <= 1 || n <= grain) {
+    for (int i = 0; i < n; ++i) body(i);
+    return;
+  }
+  std::atomic<int> next{0};
+  auto worker = [&]() {
+    for (;;) {
+      int b = next.fetch_add(grain);
+      if (b >= n) break;
+      int e = std::min(n, b + grain);
+      for (int i = b; i < e; ++i) body(i);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < threads; ++t) pool.emplace_back(worker);
+  worker();
+  for (auto &t : pool) t.join();
+}
+
+// ---------------------------------------------------------------------------
+// gbp_linalg stand-ins (crates/gbp_linalg/src/lib.rs:31-128): heap vectors.
+// ---------------------------------------------------------------------------
+using Vec = std::vector<double>;
+struct Mat {
+  int r = 0, c = 0;
+  std::vector<double> a;
+  Mat() = default;
+  Mat(int r_, int c_) : r(r_), c(c_), a(size_t(r_) * c_, 0.0) {}
+  double &operator()(int i, int j) { return a[size_t(i) * c + j]; }
+  double operator()(int i, int j) const { return a[size_t(i) * c + j]; }
+  static Mat eye(int n) {
+    Mat m(n, n);
+    for (int i = 0; i < n; ++i) m(i, i) = 1.0;
+    return m;
+  }
+};
+
+// ndarray numeric_util::unrolled_dot (contiguous slices).
+double unrolled_dot(const double *xs, const double *ys, int len) {
+  double sum = 0.0, p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  while (len >= 8) {
+    for (int k = 0; k < 8; ++k) p[k] = p[k] + xs[k] * ys[k];
+    xs += 8;
+    ys += 8;
+    len -= 8;
+  }
+  sum = sum + (p[0] + p[4]);
+  sum = sum + (p[1] + p[5]);
+  sum = sum + (p[2] + p[6]);
+  sum = sum + (p[3] + p[7]);
+  for (int i = 0; i < len && i < 7; ++i) sum = sum + xs[i] * ys[i];
+  return sum;
+}
+// Array2.dot(Array2): matrixmultiply gemm, k ascending, accumulator starts at 0.
+Mat matmul(const Mat &A, const Mat &B) {
+  Mat C(A.r, B.c);
+  for (int i = 0; i < A.r; ++i)
+    for (int j = 0; j < B.c; ++j) {
+      double acc = 0.0;
+      for (int k = 0; k < A.c; ++k) acc = acc + A(i, k) * B(k, j);
+      C(i, j) = acc;
+    }
+  return C;
+}
+// Array2.dot(Array1): row.dot(x) per row.
+Vec matvec(const Mat &A, const Vec &x) {
+  Vec y(A.r);
+  for (int i = 0; i < A.r; ++i) y[i] = unrolled_dot(&A.a[size_t(i) * A.c], x.data(), A.c);
+  return y;
+}
+Mat transpose(const Mat &A) {
+  Mat T(A.c, A.r);
+  for (int i = 0; i < A.r; ++i)
+    for (int j = 0; j < A.c; ++j) T(j, i) = A(i, j);
+  return T;
+}
+// VectorNorm::euclidean_norm (gbp_linalg/src/lib.rs:68-70): sqrt(fold(0, acc + x*x)).
+double euclidean_norm(const Vec &v) {
+  double acc = 0.0;
+  for (double x : v) acc = acc + x * x;
+  return std::sqrt(acc);
+}
+// NdarrayVectorExt::normalized (gbp_linalg/src/lib.rs:113-124).
+Vec normalized(Vec v) {
+  double mag = euclidean_norm(v);
+  if (mag == 0.0 || std::isinf(mag)) return v;
+  for (double &x : v) x /= mag;
+  return v;
+}
+
+// ndarray-inverse 0.1.9 `Inverse::inv` (third party, not under /root/reference):
+// determinant by explicit expansion, inverse = transposed cofactors / det,
+// `None` iff det == 0.  Call sites: marginalise_factor_distance.rs:79,
+// variable.rs:153, variable.rs:278.
+double det3(double a, double b, double c, double d, double e, double f, double g, double h,
+            double i) {
+  return a * e * i + b * f * g + c * d * h - c * e * g - b * d * i - a * f * h;
+}
+double minor4(const Mat &m, int sr, int sc) {
+  double s[9];
+  int n = 0;
+  for (int i = 0; i < 4; ++i) {
+    if (i == sr) continue;
+    for (int j = 0; j < 4; ++j) {
+      if (j == sc) continue;
+      s[n++] = m(i, j);
+    }
+  }
+  return det3(s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], s[8]);
+}
+double det4(const Mat &m) {
+  // Laplace expansion along row 0.
+  return m(0, 0) * minor4(m, 0, 0) - m(0, 1) * minor4(m, 0, 1) + m(0, 2) * minor4(m, 0, 2) -
+         m(0, 3) * minor4(m, 0, 3);
+}
+std::optional<Mat> inv(const Mat &m) {
+  // only 4x4 occurs on the hot path (DOFS = 4)
+  double det = det4(m);
+  if (det == 0.0) return std::nullopt;  // NaN det is "not zero", like Float::is_zero()
+  Mat out(4, 4);
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      double sign = ((i + j) % 2 == 0) ? 1.0 : -1.0;
+      out(j, i) = (sign * minor4(m, i, j)) / det;
+    }
+  return out;
+}
+
+// ---------------------------------------------------------------------------
+// message.rs:18-53,121-173 — Message{payload: Option<Box<Payload>>}
+// ---------------------------------------------------------------------------
+struct Payload {
+  Vec eta;
+  Mat lam;
+  Vec mu;
+};
+struct Message {
+  std::shared_ptr<Payload> payload;  // None == Message::empty()
+  static Message empty() { return Message{}; }
+  static Message make(Vec eta, Mat lam, Vec mu) {
+    Message m;
+    m.payload = std::make_shared<Payload>(Payload{std::move(eta), std::move(lam), std::move(mu)});
+    return m;
+  }
+  bool is_empty() const { return !payload; }
+};
+
+// id.rs:25-61,83-118 — (graph id, node index), ordered by graph id then index.
+using NodeId = std::pair<int, int>;
+using Inbox = std::map<NodeId, Message>;  // BTreeMap (message.rs:210-217)
+
+struct Cfg {  // mirror of gbp_config_t (include/gbp_b200.h), same field order
+  int32_t num_variables;
+  float sigma_factor_dynamics, sigma_factor_interrobot, sigma_factor_obstacle,
+      sigma_factor_tracking;
+  float safety_distance_multiplier, comms_radius, target_speed, delta_t;
+  float tracking_switch_padding, tracking_attraction_distance;
+  uint8_t enable_dynamic, enable_interrobot, enable_obstacle, enable_tracking;
+  int32_t schedule_kind, iterations_internal, iterations_external;
+  double world_width, world_height;
+};
+
+struct Sdf {
+  int w = 0, h = 0;
+  std::vector<uint8_t> rgb;
+};
+
+enum Kind { DYNAMIC = 0, INTERROBOT = 1, OBSTACLE = 2, TRACKING = 3 };
+
+// factor/mod.rs:597-650 FactorState + the kind-specific fields of the four
+// live factor kinds (dynamic.rs, interrobot.rs, obstacle.rs, tracking.rs).
+struct Factor {
+  Kind kind;
+  int graph;       // factorgraph_id
+  int index;       // node index
+  bool enabled;    // factor/mod.rs:147
+  Inbox inbox;     // keyed by VariableId
+  Vec z;           // initial_measurement
+  Mat meas_prec;   // measurement_precision
+  Vec lin;         // linearisation_point
+  // dynamic.rs
+  Mat cached_jacobian;
+  // interrobot.rs:40-47
+  double safety_distance = 0, robot_radius = 0, tiny_offset = 0;
+  int ext_robot = -1, ext_var = -1;
+  int own_var = -1;  // index of the (first) own-graph variable the factor is attached to
+  uint64_t robot_number = 0;
+  // obstacle.rs
+  const Sdf *sdf = nullptr;
+  double world_w = 0, world_h = 0, jac_delta = 0;
+  // tracking.rs:15-28,72-79
+  std::vector<std::pair<float, float>> path;
+  size_t trk_index = 1, trk_record = 0;
+  float last_pos[2] = {0, 0};
+  double last_value = 0;
+  std::optional<size_t> timeout;
+  float switch_padding = 1.0f, attraction_distance = 2.0f;
+  // last obstacle pixel (for bit-exact indexing checks)
+  uint32_t last_px = 0, last_py = 0;
+};
+
+// FactorState::new (factor/mod.rs:626-643): eye(len(z)) / strength^2.
+void init_state(Factor &f, Vec z, double strength, int neighbours) {
+  int m = int(z.size());
+  f.z = std::move(z);
+  f.meas_prec = Mat::eye(m);
+  double s2 = strength * strength;  // Float::powi(strength, 2)
+  for (double &x : f.meas_prec.a) x = x / s2;
+  f.lin.assign(size_t(DOFS) * neighbours, 0.0);
+}
+
+// DynamicFactor::new (factor/dynamic.rs:22-52).
+void init_dynamic(Factor &f, double strength, double delta_t) {
+  const int h = DOFS / 2;
+  Mat eye = Mat::eye(h);
+  double qs = 1.0 / (strength * strength);         // powi(strength, -2)
+  double p3 = 1.0 / ((delta_t * delta_t) * delta_t);  // powi(delta_t, -3)
+  double p2 = 1.0 / (delta_t * delta_t);            // powi(delta_t, -2)
+  Mat qc(h, h);
+  for (int i = 0; i < h * h; ++i) qc.a[i] = qs * eye.a[i];
+  Mat qi(DOFS, DOFS);
+  for (int i = 0; i < h; ++i)
+    for (int j = 0; j < h; ++j) {
+      qi(i, j) = (12.0 * p3) * qc(i, j);
+      qi(i, j + h) = (-6.0 * p2) * qc(i, j);
+      qi(i + h, j) = (-6.0 * p2) * qc(i, j);
+      qi(i + h, j + h) = (4.0 / delta_t) * qc(i, j);
+    }
+  f.meas_prec = qi;
+  Mat J(DOFS, DOFS * 2);
+  for (int i = 0; i < h; ++i)
+    for (int j = 0; j < h; ++j) {
+      double e = eye(i, j);
+      J(i, j) = e;
+      J(i, j + h) = delta_t * e;
+      J(i, j + 2 * h) = -1.0 * e;
+      J(i, j + 3 * h) = 0.0;
+      J(i + h, j) = 0.0;
+      J(i + h, j + h) = e;
+      J(i + h, j + 2 * h) = 0.0;
+      J(i + h, j + 3 * h) = -1.0 * e;
+    }
+  f.cached_jacobian = J;
+}
+
+// ObstacleFactor::measure (factor/obstacle.rs:141-188).
+// Rust `as u32` saturates: NaN -> 0, negative -> 0, overflow -> u32::MAX.
+uint32_t sat_u32(double v) {
+  if (std::isnan(v)) return 0;
+  if (v <= 0.0) return 0;
+  if (v >= 4294967295.0) return 4294967295u;
+  return uint32_t(v);  // truncation toward zero
+}
+double sdf_measure(const Sdf &sdf, double world_w, double world_h, double x_pos, double y_pos,
+                   uint32_t *opx, uint32_t *opy) {
+  double x_offset = world_w / 2.0;
+  double y_offset = world_h / 2.0;
+  double x_scale = double(uint32_t(sdf.w)) / world_w;
+  double y_scale = double(uint32_t(sdf.h)) / world_h;
+  uint32_t x_pixel = sat_u32((x_pos + x_offset) * x_scale);
+  uint32_t y_pixel = sat_u32((-y_pos + y_offset) * y_scale);
+  if (opx) *opx = x_pixel;
+  if (opy) *opy = y_pixel;
+  // image::ImageBuffer::get_pixel_checked: x < width && y < height
+  if (!(x_pixel < uint32_t(sdf.w) && y_pixel < uint32_t(sdf.h))) return 0.0;
+  uint8_t red = sdf.rgb[(size_t(y_pixel) * sdf.w + x_pixel) * 3];
+  return 1.0 - double(red) / 255.0;
+}
+
+// Factor::measure dispatch (factor/mod.rs:556-563).
+Vec measure(Factor &f, const Vec &x) {
+  switch (f.kind) {
+    case DYNAMIC:  // dynamic.rs:74-76
+      return matvec(f.cached_jacobian, x);
+    case INTERROBOT: {  // interrobot.rs:165-204 (+ :91-107)
+      Vec m(f.z.size(), 0.0);
+      Vec d(2);
+      for (int i = 0; i < 2; ++i) d[i] = (x[i] - x[DOFS + i]);
+      for (int i = 0; i < 2; ++i) d[i] += f.tiny_offset;
+      double radius = euclidean_norm(d);
+      if (radius <= f.safety_distance) m[0] = 1.0 * (1.0 - radius / f.safety_distance);
+      return m;
+    }
+    case OBSTACLE: {
+      double v = sdf_measure(*f.sdf, f.world_w, f.world_h, x[0], x[1], &f.last_px, &f.last_py);
+      return Vec{v};
+    }
+    case TRACKING: {  // tracking.rs:197-346
+      size_t rec = f.trk_record;
+      Vec x_pos{x[0], x[1]}, x_vel{x[2], x[3]};
+      auto seg = [&](size_t k, Vec &s, Vec &e) {
+        s = {double(f.path[k].first), double(f.path[k].second)};
+        e = {double(f.path[k + 1].first), double(f.path[k + 1].second)};
+      };
+      auto dot2 = [](const Vec &a, const Vec &b) { return unrolled_dot(a.data(), b.data(), 2); };
+      Vec cs, ce;
+      seg(rec, cs, ce);
+      Vec line{ce[0] - cs[0], ce[1] - cs[1]};
+      Vec rel{x_pos[0] - cs[0], x_pos[1] - cs[1]};
+      double t = dot2(rel, line) / dot2(line, line);
+      Vec cur{cs[0] + t * line[0], cs[1] + t * line[1]};
+      double d0 = double(f.switch_padding), d1 = d0 * 0.01;
+      double cur_to_end = euclidean_norm(Vec{ce[0] - cur[0], ce[1] - cur[1]});
+      bool have_prev = false;
+      Vec prevp;
+      if (rec > 0) {
+        Vec ps, pe;
+        seg(rec - 1, ps, pe);
+        Vec pl{pe[0] - ps[0], pe[1] - ps[1]};
+        Vec prel{x_pos[0] - ps[0], x_pos[1] - ps[1]};
+        double tp = dot2(prel, pl) / dot2(pl, pl);
+        Vec pp{ps[0] + tp * pl[0], ps[1] + tp * pl[1]};
+        double cur_to_prev_end = euclidean_norm(Vec{pe[0] - cur[0], pe[1] - cur[1]});
+        double prev_to_prev_end = euclidean_norm(Vec{cs[0] - pp[0], cs[1] - pp[1]});
+        if (cur_to_prev_end < d0 && cur_to_prev_end > d1 && prev_to_prev_end < d0) {
+          have_prev = true;
+          prevp = pp;
+        }
+      }
+      if (cur_to_end < d0) {  // Tracking::increment_record (tracking.rs:55-65)
+        f.trk_record = std::min(f.trk_record + 1, f.path.size() - 2);
+      }
+      Vec mp(2);
+      if (have_prev) {
+        for (int i = 0; i < 2; ++i) {
+          double x_to_cur = cur[i] - x_pos[i];
+          double x_to_prev = prevp[i] - x_pos[i];
+          mp[i] = x_pos[i] + (x_to_cur + x_to_prev);
+        }
+      } else {
+        Vec ln = normalized(line);
+        double vn = euclidean_norm(x_vel);
+        for (int i = 0; i < 2; ++i) mp[i] = cur[i] + ln[i] * vn / 5.0;
+      }
+      double dist = euclidean_norm(Vec{mp[0] - x_pos[0], mp[1] - x_pos[1]});
+      double ad = double(f.attraction_distance);
+      double meas = dist < ad ? dist / ad : 1.0;
+      f.last_pos[0] = float(mp[0]);
+      f.last_pos[1] = float(mp[1]);
+      f.last_value = meas;
+      return Vec{meas};
+    }
+  }
+  return {};
+}
+
+double jacobian_delta(const Factor &f) {
+  switch (f.kind) {
+    case DYNAMIC: return 1e-8;
+    case INTERROBOT: return 1e-2;
+    case OBSTACLE: return f.jac_delta;  // obstacle.rs:98-102
+    case TRACKING: return 1e-8;
+  }
+  return 0;
+}
+
+// Factor::first_order_jacobian (factor/mod.rs:102-128).
+Mat first_order_jacobian(Factor &f, Vec x) {
+  Vec h0 = measure(f, x);
+  Mat J(int(h0.size()), int(x.size()));
+  double delta = jacobian_delta(f);
+  for (size_t i = 0; i < x.size(); ++i) {
+    x[i] += delta;
+    Vec h1 = measure(f, x);
+    for (size_t r = 0; r < h0.size(); ++r) J(int(r), int(i)) = (h1[r] - h0[r]) / delta;
+    x[i] -= delta;
+  }
+  return J;
+}
+
+// Factor::jacobian dispatch (factor/mod.rs:541-552).
+Mat jacobian(Factor &f, const Vec &x) {
+  switch (f.kind) {
+    case DYNAMIC: return f.cached_jacobian;
+    case INTERROBOT: {  // interrobot.rs:121-161
+      Mat J(int(f.z.size()), DOFS * 2);
+      Vec d(2);
+      for (int i = 0; i < 2; ++i) d[i] = (x[i] - x[DOFS + i]);
+      for (int i = 0; i < 2; ++i) d[i] += f.tiny_offset;
+      double radius = euclidean_norm(d);
+      if (radius <= f.safety_distance) {
+        double a = -1.0 / f.safety_distance / radius;
+        double b = 1.0 / f.safety_distance / radius;
+        for (int i = 0; i < 2; ++i) {
+          J(0, i) = a * d[i];
+          J(0, DOFS + i) = b * d[i];
+        }
+      }
+      return J;
+    }
+    case OBSTACLE: return first_order_jacobian(f, x);  // obstacle.rs:129-137
+    case TRACKING: {  // tracking.rs:171-194
+      Mat J(1, DOFS);
+      double h0 = f.last_value;
+      for (int i = 0; i < 2; ++i) {
+        double xd = x[i] - double(f.last_pos[i]);
+        J(0, i) = (1.0 / h0) * xd;
+      }
+      return J;
+    }
+  }
+  return {};
+}
+
+// Factor::skip dispatch (factor/mod.rs:565-572).
+bool skip(Factor &f) {
+  switch (f.kind) {
+    case DYNAMIC:
+    case OBSTACLE: return false;
+    case INTERROBOT: {  // interrobot.rs:213-226
+      double sq = 0.0;
+      for (int i = 0; i < 2; ++i) {
+        double d = f.lin[i] - f.lin[DOFS + i];
+        sq = sq + d * d;  // mapv(powi 2).sum()
+      }
+      return sq >= f.safety_distance * f.safety_distance;
+    }
+    case TRACKING: {  // tracking.rs:362-381
+      if (f.timeout) {
+        if (*f.timeout == 0) f.timeout.reset();
+        else {
+          f.timeout = *f.timeout - 1;
+          return true;
+        }
+      }
+      // the reference computes `len - 1` on usize; an empty path never occurs
+      // once a route exists (robot.rs:1316-1322 builds it from >= 2 waypoints)
+      if (f.path.size() < 2 || f.trk_record >= f.path.size() - 1) return true;
+      return false;
+    }
+  }
+  return false;
+}
+
+// extract_submatrices_from_precision_matrix / the inline slicing of
+// marginalise_factor_distance (factor/marginalise_factor_distance.rs:22-52,74-102):
+// "a" = rows/cols [marg_idx, marg_idx+4); "b" = everything after it when
+// marg_idx == 0, everything before it otherwise.
+struct Blocks {
+  Mat aa, ab, ba, bb;
+};
+Blocks extract_blocks(const Mat &lam, int marg_idx) {
+  int n = lam.r, nb = n - DOFS;
+  auto bi = [&](int k) { return marg_idx == 0 ? DOFS + k : k; };
+  Blocks b{Mat(DOFS, DOFS), Mat(DOFS, nb), Mat(nb, DOFS), Mat(nb, nb)};
+  for (int i = 0; i < DOFS; ++i)
+    for (int j = 0; j < DOFS; ++j) b.aa(i, j) = lam(marg_idx + i, marg_idx + j);
+  for (int i = 0; i < DOFS; ++i)
+    for (int j = 0; j < nb; ++j) {
+      b.ab(i, j) = lam(marg_idx + i, bi(j));
+      b.ba(j, i) = lam(bi(j), marg_idx + i);
+    }
+  for (int i = 0; i < nb; ++i)
+    for (int j = 0; j < nb; ++j) b.bb(i, j) = lam(bi(i), bi(j));
+  return b;
+}
+
+// marginalise_factor_distance (factor/marginalise_factor_distance.rs:55-127).
+Message marginalise_factor_distance(const Vec &eta, const Mat &lam, int marg_idx) {
+  int n = int(eta.size());
+  if (n == DOFS) return Message::make(eta, lam, Vec(n, 0.0));
+  int nb = n - DOFS;
+  Blocks b = extract_blocks(lam, marg_idx);
+  auto lam_bb_inv = inv(b.bb);
+  if (!lam_bb_inv) return Message::empty();
+  Vec eta_a(DOFS), eta_b(nb);
+  for (int i = 0; i < DOFS; ++i) eta_a[i] = eta[marg_idx + i];
+  for (int i = 0; i < nb; ++i) eta_b[i] = eta[marg_idx == 0 ? DOFS + i : i];
+  Mat t = matmul(b.ab, *lam_bb_inv);
+  Vec te = matvec(t, eta_b);
+  Mat t2 = matmul(b.ab, *lam_bb_inv);  // the reference computes it twice (:114-115)
+  Mat tl = matmul(t2, b.ba);
+  Vec eta_o(DOFS);
+  Mat lam_o(DOFS, DOFS);
+  for (int i = 0; i < DOFS; ++i) eta_o[i] = eta_a[i] - te[i];
+  for (int i = 0; i < DOFS * DOFS; ++i) lam_o.a[i] = b.aa.a[i] - tl.a[i];
+  for (double v : lam_o.a)
+    if (std::isinf(v)) return Message::empty();
+  return Message::make(eta_o, lam_o, Vec(DOFS, 0.0));
+}
+
+// FactorNode::update (factor/mod.rs:334-454).
+std::vector<std::pair<NodeId, Message>> factor_update(Factor &f) {
+  int i = 0;
+  for (auto &kv : f.inbox) {
+    if (size_t(i + 1) * DOFS > f.lin.size()) break;  // cannot happen: |inbox| <= neighbours
+    if (!kv.second.is_empty())
+      for (int k = 0; k < DOFS; ++k) f.lin[i * DOFS + k] = kv.second.payload->mu[k];
+    else
+      for (int k = 0; k < DOFS; ++k) f.lin[i * DOFS + k] = 0.0;
+    ++i;
+  }
+  std::vector<std::pair<NodeId, Message>> out;
+  if (skip(f)) {
+    for (auto &kv : f.inbox) out.emplace_back(kv.first, Message::empty());
+    return out;
+  }
+  Vec h = measure(f, f.lin);
+  Mat J = jacobian(f, f.lin);
+  Mat Jt = transpose(J);
+  Mat JtL = matmul(Jt, f.meas_prec);
+  Mat lam_p = matmul(JtL, J);
+  Vec residual(f.z.size());
+  for (size_t k = 0; k < f.z.size(); ++k) residual[k] = f.z[k] - h[k];
+  Vec jx = matvec(J, f.lin);
+  for (size_t k = 0; k < jx.size(); ++k) jx[k] = jx[k] + residual[k];
+  Mat JtL2 = matmul(Jt, f.meas_prec);
+  Vec eta_p = matvec(JtL2, jx);
+
+  int marg = 0;
+  for (auto &to : f.inbox) {
+    Vec eta = eta_p;
+    Mat lam = lam_p;
+    int j = 0;
+    for (auto &other : f.inbox) {
+      if (other.first != to.first && !other.second.is_empty()) {
+        const Payload &p = *other.second.payload;
+        for (int a = 0; a < DOFS; ++a) eta[j * DOFS + a] += p.eta[a];
+        for (int a = 0; a < DOFS; ++a)
+          for (int b = 0; b < DOFS; ++b) lam(j * DOFS + a, j * DOFS + b) += p.lam(a, b);
+      }
+      ++j;
+    }
+    out.emplace_back(to.first, marginalise_factor_distance(eta, lam, marg));
+    marg += DOFS;
+  }
+  return out;
+}
+
+// variable.rs:15-54,86-106
+struct Variable {
+  int graph, index;
+  Vec prior_eta;
+  Mat prior_lam;
+  Vec eta, mu;
+  Mat lam, cov;
+  bool valid;
+  Inbox inbox;  // keyed by FactorId
+};
+
+// VariableNode::new (variable.rs:140-166).
+Variable make_variable(int graph, int index, const Vec &prior_mean, Mat prior_lam) {
+  bool finite = true;
+  for (double v : prior_lam.a) finite = finite && std::isfinite(v);
+  if (!finite) std::fill(prior_lam.a.begin(), prior_lam.a.end(), 0.0);
+  Variable v;
+  v.graph = graph;
+  v.index = index;
+  v.prior_eta = matvec(prior_lam, prior_mean);
+  auto sigma = inv(prior_lam);
+  v.cov = sigma ? *sigma : Mat(DOFS, DOFS);
+  v.prior_lam = prior_lam;
+  v.eta = v.prior_eta;
+  v.lam = prior_lam;
+  v.mu = prior_mean;
+  v.valid = true;
+  for (double c : v.cov.a) v.valid = v.valid && std::isfinite(c);
+  return v;
+}
+// VariableNode::prepare_message (variable.rs:234-240).
+Message prepare_message(const Variable &v) { return Message::make(v.eta, v.lam, v.mu); }
+
+// VariableNode::change_prior (variable.rs:203-230).
+std::vector<std::pair<NodeId, Message>> change_prior(Variable &v, const Vec &mean) {
+  v.prior_eta = matvec(v.prior_lam, mean);
+  v.mu = mean;
+  std::vector<std::pair<NodeId, Message>> out;
+  for (auto &kv : v.inbox) out.emplace_back(kv.first, prepare_message(v));
+  for (auto &kv : v.inbox) kv.second = Message::empty();
+  return out;
+}
+
+// VariableNode::update_belief_and_create_factor_responses (variable.rs:251-342).
+std::vector<std::pair<NodeId, Message>> variable_update(Variable &v) {
+  v.eta = v.prior_eta;
+  v.lam = v.prior_lam;
+  for (auto &kv : v.inbox) {
+    if (kv.second.is_empty()) continue;
+    const Payload &p = *kv.second.payload;
+    for (int a = 0; a < DOFS; ++a) v.eta[a] = v.eta[a] + p.eta[a];
+    for (int a = 0; a < DOFS * DOFS; ++a) v.lam.a[a] = v.lam.a[a] + p.lam.a[a];
+  }
+  bool precision_not_zero = false;
+  for (double x : v.lam.a) precision_not_zero = precision_not_zero || (x - 1e-6 > 0.0);
+  if (precision_not_zero) {
+    if (auto cov = inv(v.lam)) {
+      v.cov = *cov;
+      v.valid = true;
+      for (double c : v.cov.a) v.valid = v.valid && std::isfinite(c);
+      if (v.valid) v.mu = matvec(v.cov, v.eta);
+    }
+  }
+  std::vector<std::pair<NodeId, Message>> out;
+  for (auto &kv : v.inbox) {
+    if (kv.second.is_empty()) {
+      out.emplace_back(kv.first, prepare_message(v));
+    } else {
+      const Payload &p = *kv.second.payload;
+      Vec e(DOFS), m(DOFS);
+      Mat l(DOFS, DOFS);
+      for (int a = 0; a < DOFS; ++a) e[a] = v.eta[a] - p.eta[a];
+      for (int a = 0; a < DOFS * DOFS; ++a) l.a[a] = v.lam.a[a] - p.lam.a[a];
+      for (int a = 0; a < DOFS; ++a) m[a] = v.mu[a] - p.mu[a];
+      out.emplace_back(kv.first, Message::make(e, l, m));
+    }
+  }
+  return out;
+}
+
+// factorgraph.rs:74-120 — one graph per robot.  Node indices: variables 0..V-1,
+// then factors in creation order (petgraph StableGraph; free-slot reuse after
+// deletion only permutes indices of a robot's OWN InterRobot factors, whose
+// entries in own-variable inboxes are permanently Empty, so it has no effect).
+struct Graph {
+  int id;
+  std::vector<Variable> vars;
+  std::map<int, Factor> factors;  // node index -> factor (factor_indices order)
+  int next_index = 0;
+  uint64_t iter_factor = 0, iter_variable = 0;
+};
+
+// FactorNode::receive_message_from (factor/mod.rs:307-318).
+void factor_receive(Factor &f, NodeId from, const Message &m) {
+  if (!f.enabled) return;
+  f.inbox[from] = m;
+}
+
+struct Robot {
+  Graph g;
+  float radius, t0;
+  float pos[2];  // Transform.translation.x / .z
+  bool antenna = true, idle = false, finished = false;
+  std::set<int> within, connected;  // RobotConnections
+  std::vector<std::pair<float, float>> waypoints;
+  int next_wp = 1;
+};
+
+struct World {
+  Cfg cfg;
+  Sdf sdf;
+  std::vector<uint32_t> timesteps;
+  std::vector<Robot> robots;
+  uint64_t robot_number = 1;  // RobotNumberGenerator (robot.rs:121-144)
+  int threads = 1;
+};
+
+// FactorGraph::add_internal_edge (factorgraph.rs:304-330).
+void add_internal_edge(Graph &g, int var, int fidx) {
+  Variable &v = g.vars[var];
+  v.inbox[{g.id, fidx}] = Message::empty();
+  Message vm = prepare_message(v);
+  Factor &f = g.factors.at(fidx);
+  if (f.kind == TRACKING) factor_receive(f, {g.id, var}, vm);
+  else factor_receive(f, {g.id, var}, Message::empty());
+}
+
+// RobotBundle::new (planner/robot.rs:1134-1355).
+void add_robot(World &w, float radius, const double *means, const float *pos,
+               const float *wp_xy, int nwp) {
+  const Cfg &c = w.cfg;
+  int V = c.num_variables;
+  w.robots.emplace_back();
+  Robot &r = w.robots.back();
+  int id = int(w.robots.size()) - 1;
+  r.g.id = id;
+  r.radius = radius;
+  r.pos[0] = pos[0];
+  r.pos[1] = pos[1];
+  for (int k = 0; k < nwp; ++k) r.waypoints.emplace_back(wp_xy[2 * k], wp_xy[2 * k + 1]);
+  for (int i = 0; i < V; ++i) {  // :1179-1223
+    double sigma = (i == 0 || i == V - 1) ? 1e30 : std::numeric_limits<double>::infinity();
+    Mat P(DOFS, DOFS);
+    for (int a = 0; a < DOFS; ++a) P(a, a) = sigma;  // from_diag_elem
+    Vec m(means + size_t(i) * DOFS, means + size_t(i + 1) * DOFS);
+    r.g.vars.push_back(make_variable(id, i, m, P));
+  }
+  r.g.next_index = V;
+  r.t0 = radius / 2.0f / c.target_speed;  // :1225 (f32)
+  for (int i = 0; i < V - 1; ++i) {        // :1228-1255
+    float delta_t = r.t0 * float(w.timesteps[i + 1] - w.timesteps[i]);
+    Factor f;
+    f.kind = DYNAMIC;
+    f.graph = id;
+    f.index = r.g.next_index++;
+    f.enabled = c.enable_dynamic;
+    init_state(f, Vec(DOFS, 0.0), double(c.sigma_factor_dynamics), 2);
+    init_dynamic(f, double(c.sigma_factor_dynamics), double(delta_t));
+    int fi = f.index;
+    f.own_var = i;
+    r.g.factors.emplace(fi, std::move(f));
+    add_internal_edge(r.g, i + 1, fi);
+    add_internal_edge(r.g, i, fi);
+  }
+  for (int i = 1; i < V - 1; ++i) {  // :1269-1285
+    Factor f;
+    f.kind = OBSTACLE;
+    f.graph = id;
+    f.index = r.g.next_index++;
+    f.enabled = c.enable_obstacle;
+    init_state(f, Vec{0.0}, double(c.sigma_factor_obstacle), 1);
+    f.sdf = &w.sdf;
+    f.world_w = c.world_width;
+    f.world_h = c.world_height;
+    f.jac_delta = (c.world_width / double(uint32_t(w.sdf.w)) +
+                   c.world_height / double(uint32_t(w.sdf.h))) / 2.0;  // obstacle.rs:98-102
+    int fi = f.index;
+    f.own_var = i;
+    r.g.factors.emplace(fi, std::move(f));
+    add_internal_edge(r.g, i, fi);
+  }
+  for (int i = 1; i < V - 1; ++i) {  // :1305-1334
+    Factor f;
+    f.kind = TRACKING;
+    f.graph = id;
+    f.index = r.g.next_index++;
+    f.enabled = c.enable_tracking;
+    init_state(f, Vec{0.0}, double(c.sigma_factor_tracking), 1);
+    f.lin = Vec{means[size_t(i) * DOFS], means[size_t(i) * DOFS + 1], 0.0, 0.0};
+    f.path = r.waypoints;
+    f.last_pos[0] = float(f.lin[0]);
+    f.last_pos[1] = float(f.lin[1]);
+    f.last_value = 0.0;
+    f.switch_padding = c.tracking_switch_padding;
+    f.attraction_distance = c.tracking_attraction_distance;
+    int fi = f.index;
+    f.own_var = i;
+    r.g.factors.emplace(fi, std::move(f));
+    add_internal_edge(r.g, i, fi);
+  }
+}
+
+// update_robot_neighbours (planner/robot.rs:1362-1384): glam Vec3::distance in f32.
+void update_neighbours(World &w) {
+  int n = int(w.robots.size());
+  float R = w.cfg.comms_radius;
+  parallel_for(n, w.threads, 64, [&](int a) {
+    Robot &ra = w.robots[a];
+    ra.within.clear();
+    for (int b = 0; b < n; ++b) {
+      if (b == a) continue;
+      float dx = ra.pos[0] - w.robots[b].pos[0];
+      float dy = 0.0f;
+      float dz = ra.pos[1] - w.robots[b].pos[1];
+      float d = std::sqrt((dx * dx + dy * dy) + dz * dz);
+      if (R < d) continue;
+      ra.within.insert(b);
+    }
+  });
+}
+
+// FactorGraph::delete_interrobot_factors_connected_to (factorgraph.rs:380-436).
+void delete_ir_connected_to(Graph &g, int other) {
+  std::vector<int> removed;
+  for (auto &v : g.vars)
+    for (auto it = v.inbox.begin(); it != v.inbox.end();)
+      it = (it->first.first == other) ? v.inbox.erase(it) : std::next(it);
+  for (auto it = g.factors.begin(); it != g.factors.end();) {
+    if (it->second.kind == INTERROBOT && it->second.ext_robot == other) {
+      removed.push_back(it->first);
+      it = g.factors.erase(it);
+    } else ++it;
+  }
+  for (auto &v : g.vars)
+    for (int fi : removed) v.inbox.erase({g.id, fi});
+}
+
+// delete_interrobot_factors (planner/robot.rs:1386-1439).  The reference funnels
+// the (robot, lost neighbour) pairs through a HashMap<RobotId, RobotId>, which
+// drops pairs when one robot loses several neighbours in a tick;
+// every lost pair is deleted here (the symmetric pair covers it in the reference
+// whenever the quirk does not trigger).
+void delete_interrobot_factors(World &w) {
+  std::vector<std::pair<int, int>> pairs;
+  for (auto &r : w.robots) {
+    std::vector<int> lost;
+    for (int c : r.connected)
+      if (!r.within.count(c)) lost.push_back(c);
+    for (int c : lost) {
+      pairs.emplace_back(r.g.id, c);
+      r.connected.erase(c);
+    }
+  }
+  for (auto &p : pairs) {
+    delete_ir_connected_to(w.robots[p.first].g, p.second);
+    delete_ir_connected_to(w.robots[p.second].g, p.first);
+  }
+}
+
+// create_interrobot_factors (planner/robot.rs:1441-1586).
+void create_interrobot_factors(World &w) {
+  const Cfg &c = w.cfg;
+  int V = c.num_variables;
+  struct Ext { int robot, fidx, other, i; };
+  std::vector<Ext> ext;
+  for (auto &r : w.robots) {
+    std::vector<int> fresh;
+    for (int o : r.within)
+      if (!r.connected.count(o)) fresh.push_back(o);  // BTreeSet::difference, ascending
+    for (int other : fresh) {
+      for (int i = 1; i < V; ++i) {
+        Factor f;
+        f.kind = INTERROBOT;
+        f.graph = r.g.id;
+        f.index = r.g.next_index++;
+        f.enabled = c.enable_interrobot;
+        init_state(f, Vec(DOFS, 0.0), double(c.sigma_factor_interrobot), 2);
+        f.robot_radius = double(r.radius);
+        f.safety_distance = double(c.safety_distance_multiplier) * f.robot_radius;
+        f.ext_robot = other;
+        f.ext_var = i;
+        f.robot_number = w.robot_number++;
+        f.tiny_offset = double(1e-6f) * double(f.robot_number);  // interrobot.rs:52,75
+        int fi = f.index;
+        f.own_var = i;
+        r.g.factors.emplace(fi, std::move(f));
+        add_internal_edge(r.g, i, fi);
+        ext.push_back({r.g.id, fi, other, i});
+      }
+      r.connected.insert(other);
+    }
+  }
+  struct Tmp { int robot, fidx; Message m; NodeId from; };
+  std::vector<Tmp> tmp;
+  for (auto &e : ext) {  // add_external_edge (factorgraph.rs:340-353)
+    Graph &og = w.robots[e.other].g;
+    og.vars[e.i].inbox[{e.robot, e.fidx}] = Message::empty();
+    tmp.push_back({e.robot, e.fidx, prepare_message(og.vars[e.i]), {e.other, e.i}});
+  }
+  for (auto &t : tmp) {
+    auto it = w.robots[t.robot].g.factors.find(t.fidx);
+    if (it != w.robots[t.robot].g.factors.end()) factor_receive(it->second, t.from, t.m);
+  }
+}
+
+// FactorGraph::internal_factor_iteration (factorgraph.rs:688-714).
+void internal_factor_iteration(Graph &g) {
+  for (auto &kv : g.factors) {
+    Factor &f = kv.second;
+    if (!f.enabled) continue;
+    if (f.kind == INTERROBOT) continue;
+    if (f.kind == TRACKING && g.iter_factor < 10) continue;
+    auto msgs = factor_update(f);
+    for (auto &m : msgs) g.vars[m.first.second].inbox[{g.id, f.index}] = m.second;
+  }
+  g.iter_factor += 1;
+}
+// FactorGraph::internal_variable_iteration (factorgraph.rs:762-790).
+void internal_variable_iteration(Graph &g) {
+  for (auto &v : g.vars) {
+    auto msgs = variable_update(v);
+    for (auto &m : msgs) {
+      if (m.first.first != g.id) continue;
+      auto it = g.factors.find(m.first.second);
+      if (it == g.factors.end()) continue;
+      if (!it->second.enabled) continue;
+      factor_receive(it->second, {g.id, v.index}, m.second);
+    }
+  }
+  g.iter_variable += 1;
+}
+struct Routed { NodeId from, to; Message m; };
+// FactorGraph::external_factor_iteration (factorgraph.rs:719-760).
+void external_factor_iteration(Graph &g, std::vector<Routed> &out) {
+  for (auto &kv : g.factors) {
+    Factor &f = kv.second;
+    if (f.kind != INTERROBOT || !f.enabled) continue;
+    auto msgs = factor_update(f);
+    for (auto &m : msgs)
+      if (m.first.first != g.id) out.push_back({{g.id, f.index}, m.first, m.second});
+  }
+  g.iter_factor += 1;
+}
+// FactorGraph::external_variable_iteration (factorgraph.rs:794-826).
+void external_variable_iteration(Graph &g, std::vector<Routed> &out) {
+  for (auto &v : g.vars) {
+    auto msgs = variable_update(v);
+    for (auto &m : msgs)
+      if (m.first.first != g.id) out.push_back({{g.id, v.index}, m.first, m.second});
+  }
+  g.iter_variable += 1;
+}
+
+void world_internal(World &w, bool factors, bool variables) {
+  int n = int(w.robots.size());
+  // query.par_iter_mut() (robot.rs:1789-1800): threads over robots
+  parallel_for(n, w.threads, 16, [&](int i) {
+    Robot &r = w.robots[i];
+    if (r.idle) return;
+    if (factors) internal_factor_iteration(r.g);
+    if (variables) internal_variable_iteration(r.g);
+  });
+}
+void world_external_factor(World &w) {  // robot.rs:1803-1831 (single thread)
+  std::vector<Routed> msgs;
+  for (auto &r : w.robots) {
+    if (!r.antenna || r.idle) continue;
+    external_factor_iteration(r.g, msgs);
+  }
+  for (auto &m : msgs) {
+    Robot &t = w.robots[m.to.first];
+    if (!t.antenna || t.idle) continue;
+    t.g.vars[m.to.second].inbox[m.from] = m.m;
+  }
+}
+void world_external_variable(World &w) {  // robot.rs:1833-1858 (single thread)
+  std::vector<Routed> msgs;
+  for (auto &r : w.robots) {
+    if (!r.antenna || r.idle) continue;
+    external_variable_iteration(r.g, msgs);
+  }
+  for (auto &m : msgs) {
+    Robot &t = w.robots[m.to.first];
+    if (!t.antenna || t.idle) continue;
+    auto it = t.g.factors.find(m.to.second);
+    if (it != t.g.factors.end()) factor_receive(it->second, m.from, m.m);
+  }
+}
+
+// gbp_schedule crate ---------------------------------------------------------
+// interleave_evenly.rs:40-110
+void ie_recurse(uint8_t *s, int len, int n) {
+  int max = len, half = max / 2;
+  auto fill_cycle = [&](int times) {
+    for (int i = 0; i < len; ++i) s[i] = (i % times) == 0;
+  };
+  if (n == max) { std::fill(s, s + len, 1); return; }
+  if (n == 0) { std::fill(s, s + len, 0); return; }
+  bool on = n % 2 == 1, om = max % 2 == 1;
+  if (on && om) {
+    if (max % n == 0) fill_cycle(max / n);
+    else {
+      int k = n / 2;
+      ie_recurse(s, half, k);
+      s[half] = 1;
+      ie_recurse(s + half + 1, len - half - 1, k);
+      std::reverse(s + half + 1, s + len);
+    }
+  } else if (!on && om) {
+    int k = n / 2;
+    ie_recurse(s, half, k);
+    std::reverse(s, s + half);
+    s[half] = 0;
+    ie_recurse(s + half + 1, len - half - 1, k);
+  } else if (!on && !om) {
+    if (max % n == 0) fill_cycle(max / n);
+    else {
+      int k = n / 2;
+      ie_recurse(s, half, k);
+      ie_recurse(s + half, len - half, k);
+    }
+  } else {
+    int k = n / 2;
+    ie_recurse(s, half, k + 1);
+    std::reverse(s, s + half);
+    ie_recurse(s + half, len - half, k);
+  }
+}
+void expand(int kind, int n, int max, uint8_t *out) {
+  switch (kind) {
+    case 0: {  // centered.rs:12-49
+      for (int idx = 0; idx < max; ++idx) {
+        if (n == 0 && max == 1) { out[idx] = 0; continue; }
+        int mid = max / 2, hn = n / 2;
+        int start = mid >= hn ? mid - hn : 0;
+        int end = (start + n <= max) ? start + n - 1 : max - 1;
+        out[idx] = idx >= start && idx <= end;
+      }
+      break;
+    }
+    case 1: ie_recurse(out, max, n); break;
+    case 2:  // soon_as_possible.rs:26-49
+      for (int i = 0; i < max; ++i) out[i] = i < n;
+      break;
+    case 3:  // late_as_possible.rs:29-50
+      for (int i = 0; i < max; ++i) out[i] = (n == max) ? 1 : (n == 0 ? 0 : i >= max - n);
+      break;
+    case 4: {  // half_beginning_half_end.rs:19-45
+      int hn = n / 2, rem = n % 2, sm = hn, em = max - hn - rem;
+      for (int i = 0; i < max; ++i) out[i] = (i < sm || i >= em);
+      break;
+    }
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C entry points for ctypes (tests / bench only)
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int gbpo_schedule(int32_t kind, uint8_t internal, uint8_t external, uint8_t *oi, uint8_t *oe) {
+  if (kind < 0 || kind > 4) return -2;
+  int max = std::max(internal, external);
+  expand(kind, internal, max, oi);
+  expand(kind, external, max, oe);
+  return max;
+}
+
+// utils::get_variable_timesteps (utils.rs:35-75), f32 arithmetic with mul_add.
+int gbpo_variable_timesteps(uint32_t h, uint32_t m, uint32_t *out, int32_t cap) {
+  uint32_t n = 1 + uint32_t(0.5f * (-1.0f + std::sqrt(1.0f + 8.0f * float(h) / float(m))));
+  int cnt = 0;
+  for (uint32_t i = 0; i < m * (n + 1); ++i) {
+    uint32_t section = i / m;
+    float f = std::fmaf(float(m) / 2.0f, float(section),
+                        std::fmaf(float(section), -float(m), float(i))) *
+              (float(section) + 1.0f);
+    if (cnt >= cap) return -2;
+    if (f >= float(h)) { out[cnt++] = h; break; }
+    out[cnt++] = uint32_t(f);
+  }
+  return cnt;
+}
+
+// marginalise_factor_distance on raw arrays (n = 4 or 8), for the reference KATs.
+int gbpo_marginalise(int n, const double *eta, const double *lam, int marg_idx, double *oeta,
+                     double *olam, double *omu) {
+  Vec e(eta, eta + n);
+  Mat l(n, n);
+  std::copy(lam, lam + n * n, l.a.begin());
+  Message m = marginalise_factor_distance(e, l, marg_idx);
+  if (m.is_empty()) return 0;
+  std::copy(m.payload->eta.begin(), m.payload->eta.end(), oeta);
+  std::copy(m.payload->lam.a.begin(), m.payload->lam.a.end(), olam);
+  std::copy(m.payload->mu.begin(), m.payload->mu.end(), omu);
+  return int(m.payload->eta.size());
+}
+// block extraction of an 8x8 (reference KATs marginalise_factor_distance.rs:182-210)
+int gbpo_extract_blocks(const double *lam, int marg_idx, double *aa, double *ab, double *ba, double *bb) {
+  Mat l(8, 8);
+  std::copy(lam, lam + 64, l.a.begin());
+  Blocks b = extract_blocks(l, marg_idx);
+  std::copy(b.aa.a.begin(), b.aa.a.end(), aa);
+  std::copy(b.ab.a.begin(), b.ab.a.end(), ab);
+  std::copy(b.ba.a.begin(), b.ba.a.end(), ba);
+  std::copy(b.bb.a.begin(), b.bb.a.end(), bb);
+  return 0;
+}
+int gbpo_inv4(const double *m, double *out) {
+  Mat a(4, 4);
+  std::copy(m, m + 16, a.a.begin());
+  auto r = inv(a);
+  if (!r) return 0;
+  std::copy(r->a.begin(), r->a.end(), out);
+  return 1;
+}
+
+void *gbpo_create(const void *cfg) {
+  World *w = new World();
+  std::memcpy(&w->cfg, cfg, sizeof(Cfg));
+  w->sdf.w = 1;
+  w->sdf.h = 1;
+  w->sdf.rgb = {255, 255, 255};
+  return w;
+}
+int gbpo_config_size(void) { return int(sizeof(Cfg)); }
+void gbpo_destroy(void *p) { delete static_cast<World *>(p); }
+void gbpo_set_threads(void *p, int t) { static_cast<World *>(p)->threads = t < 1 ? 1 : t; }
+
+int gbpo_set_sdf(void *p, const uint8_t *rgb, int w_, int h_) {
+  World *w = static_cast<World *>(p);
+  if (!w->robots.empty()) return -5;  // obstacle factors capture jac_delta at creation
+  w->sdf.w = w_;
+  w->sdf.h = h_;
+  w->sdf.rgb.assign(rgb, rgb + size_t(w_) * h_ * 3);
+  return 0;
+}
+int gbpo_add_robots(void *p, int n, const float *radii, const uint32_t *timesteps,
+                    const double *means, const float *pos, const int32_t *wp_off,
+                    const float *wp_xy) {
+  World *w = static_cast<World *>(p);
+  int V = w->cfg.num_variables;
+  w->timesteps.assign(timesteps, timesteps + V);
+  w->robots.reserve(w->robots.size() + n);
+  for (int i = 0; i < n; ++i)
+    add_robot(*w, radii[i], means + size_t(i) * V * DOFS, pos + 2 * i, wp_xy + 2 * wp_off[i],
+              wp_off[i + 1] - wp_off[i]);
+  return 0;
+}
+int gbpo_num_robots(void *p) { return int(static_cast<World *>(p)->robots.size()); }
+
+int gbpo_update_topology(void *p) {
+  World *w = static_cast<World *>(p);
+  update_neighbours(*w);
+  delete_interrobot_factors(*w);
+  create_interrobot_factors(*w);
+  return 0;
+}
+int gbpo_set_comms(void *p, const uint8_t *antenna, const uint8_t *idle) {
+  World *w = static_cast<World *>(p);
+  for (size_t i = 0; i < w->robots.size(); ++i) {
+    w->robots[i].antenna = antenna ? antenna[i] != 0 : true;
+    w->robots[i].idle = idle ? idle[i] != 0 : false;
+  }
+  return 0;
+}
+int gbpo_set_waypoint_index(void *p, const int32_t *idx) {
+  World *w = static_cast<World *>(p);
+  for (size_t i = 0; i < w->robots.size(); ++i) w->robots[i].next_wp = idx[i];
+  return 0;
+}
+
+// FactorGraph::change_prior_of_variable (factorgraph.rs:494-528) + the caller's
+// deferred delivery to other graphs' factors (robot.rs:2272-2282).
+static void change_prior_of_variable(World &w, int robot, int var, const Vec &mean,
+                                     std::vector<Routed> &deferred) {
+  Graph &g = w.robots[robot].g;
+  auto msgs = change_prior(g.vars[var], mean);
+  for (auto &m : msgs) {
+    if (m.first.first == g.id) {
+      auto it = g.factors.find(m.first.second);
+      if (it != g.factors.end()) factor_receive(it->second, {g.id, var}, m.second);
+    } else {
+      deferred.push_back({{g.id, var}, m.first, m.second});
+    }
+  }
+}
+static void deliver_to_factors(World &w, std::vector<Routed> &msgs) {
+  for (auto &m : msgs) {
+    auto &fs = w.robots[m.to.first].g.factors;
+    auto it = fs.find(m.to.second);
+    if (it != fs.end()) factor_receive(it->second, m.from, m.m);
+  }
+}
+
+// update_prior_of_horizon_state (planner/robot.rs:2182-2283).
+int gbpo_update_prior_of_horizon_state(void *p) {
+  World *w = static_cast<World *>(p);
+  double delta_t = double(w->cfg.delta_t);
+  double max_speed = double(w->cfg.target_speed);
+  std::vector<Routed> deferred;
+  for (auto &r : w->robots) {
+    if (r.finished || r.idle) continue;
+    if (r.next_wp < 0 || r.next_wp >= int(r.waypoints.size())) {
+      r.finished = true;
+      continue;
+    }
+    if (w->cfg.iterations_internal == 0) continue;
+    Variable &hv = r.g.vars.back();
+    Vec wp{double(r.waypoints[r.next_wp].first), double(r.waypoints[r.next_wp].second)};
+    Vec h2w{wp[0] - hv.mu[0], wp[1] - hv.mu[1]};
+    double dist = euclidean_norm(h2w);
+    Vec dir = normalized(h2w);
+    double sp = std::fmin(max_speed, dist);
+    Vec nv{sp * dir[0], sp * dir[1]};
+    Vec nm{hv.mu[0] + nv[0] * delta_t, hv.mu[1] + nv[1] * delta_t, nv[0], nv[1]};
+    hv.mu = nm;
+    change_prior_of_variable(*w, r.g.id, int(r.g.vars.size()) - 1, nm, deferred);
+  }
+  deliver_to_factors(*w, deferred);
+  return 0;
+}
+// update_prior_of_current_state_v3 (planner/robot.rs:2286-2338).
+int gbpo_update_prior_of_current_state(void *p) {
+  World *w = static_cast<World *>(p);
+  std::vector<Routed> deferred;
+  for (auto &r : w->robots) {
+    if (r.idle) continue;
+    float time_scale = w->cfg.delta_t / r.t0;
+    Variable &c = r.g.vars[0];
+    Variable &nx = r.g.vars[1];
+    Vec change(DOFS), upd(DOFS);
+    for (int k = 0; k < DOFS; ++k) change[k] = double(time_scale) * (nx.mu[k] - c.mu[k]);
+    for (int k = 0; k < DOFS; ++k) upd[k] = c.mu[k] + change[k];
+    change_prior_of_variable(*w, r.g.id, 0, upd, deferred);
+    r.pos[0] += float(change[0]);
+    r.pos[1] += float(change[1]);
+  }
+  return 0;
+}
+int gbpo_change_prior_of_variable(void *p, int var, int m, const int32_t *robots,
+                                  const double *means) {
+  World *w = static_cast<World *>(p);
+  std::vector<Routed> deferred;
+  for (int k = 0; k < m; ++k)
+    change_prior_of_variable(*w, robots[k], var, Vec(means + 4 * k, means + 4 * k + 4), deferred);
+  deliver_to_factors(*w, deferred);
+  return 0;
+}
+
+int gbpo_internal_factor_iteration(void *p) { world_internal(*static_cast<World *>(p), true, false); return 0; }
+int gbpo_internal_variable_iteration(void *p) { world_internal(*static_cast<World *>(p), false, true); return 0; }
+int gbpo_external_factor_iteration(void *p) { world_external_factor(*static_cast<World *>(p)); return 0; }
+int gbpo_external_variable_iteration(void *p) { world_external_variable(*static_cast<World *>(p)); return 0; }
+
+// iterate_gbp_v2 (planner/robot.rs:1769-1861).
+int gbpo_iterate_schedule(void *p, int n, const uint8_t *internal, const uint8_t *external) {
+  World *w = static_cast<World *>(p);
+  for (int s = 0; s < n; ++s) {
+    if (internal[s]) world_internal(*w, true, true);
+    if (external[s]) {
+      world_external_factor(*w);
+      world_external_variable(*w);
+    }
+  }
+  return 0;
+}
+int gbpo_iterate(void *p) {
+  World *w = static_cast<World *>(p);
+  uint8_t oi[256], oe[256];
+  int n = gbpo_schedule(w->cfg.schedule_kind, uint8_t(w->cfg.iterations_internal),
+                        uint8_t(w->cfg.iterations_external), oi, oe);
+  if (n < 0) return n;
+  return gbpo_iterate_schedule(p, n, oi, oe);
+}
+int gbpo_step(void *p) {  // FixedUpdate chain (robot.rs:85-108), comms mask supplied by caller
+  gbpo_update_topology(p);
+  gbpo_update_prior_of_horizon_state(p);
+  gbpo_update_prior_of_current_state(p);
+  return gbpo_iterate(p);
+}
+
+int gbpo_change_factor_enabled(void *p, int kind, uint8_t en) {  // factorgraph.rs:1529-1539
+  World *w = static_cast<World *>(p);
+  for (auto &r : w->robots)
+    for (auto &kv : r.g.factors)
+      if (int(kv.second.kind) == kind) kv.second.enabled = en;
+  uint8_t *flags[4] = {&w->cfg.enable_dynamic, &w->cfg.enable_interrobot, &w->cfg.enable_obstacle,
+                       &w->cfg.enable_tracking};
+  if (kind >= 0 && kind < 4) *flags[kind] = en;
+  return 0;
+}
+int gbpo_set_safety_distance_multiplier(void *p, float mult) {  // factorgraph.rs:892
+  World *w = static_cast<World *>(p);
+  w->cfg.safety_distance_multiplier = mult;
+  for (auto &r : w->robots)
+    for (auto &kv : r.g.factors)
+      if (kv.second.kind == INTERROBOT)
+        kv.second.safety_distance = double(mult) * kv.second.robot_radius;
+  return 0;
+}
+int gbpo_set_schedule(void *p, int kind, int internal, int external) {
+  World *w = static_cast<World *>(p);
+  w->cfg.schedule_kind = kind;
+  w->cfg.iterations_internal = internal;
+  w->cfg.iterations_external = external;
+  return 0;
+}
+
+int gbpo_read_beliefs(void *p, double *eta, double *lam, double *mean, double *cov,
+                      uint8_t *valid) {
+  World *w = static_cast<World *>(p);
+  size_t k = 0;
+  for (auto &r : w->robots)
+    for (auto &v : r.g.vars) {
+      if (eta) std::copy(v.eta.begin(), v.eta.end(), eta + 4 * k);
+      if (lam) std::copy(v.lam.a.begin(), v.lam.a.end(), lam + 16 * k);
+      if (mean) std::copy(v.mu.begin(), v.mu.end(), mean + 4 * k);
+      if (cov) std::copy(v.cov.a.begin(), v.cov.a.end(), cov + 16 * k);
+      if (valid) valid[k] = v.valid;
+      ++k;
+    }
+  return 0;
+}
+int gbpo_read_positions(void *p, float *xy) {
+  World *w = static_cast<World *>(p);
+  for (size_t i = 0; i < w->robots.size(); ++i) {
+    xy[2 * i] = w->robots[i].pos[0];
+    xy[2 * i + 1] = w->robots[i].pos[1];
+  }
+  return 0;
+}
+int64_t gbpo_read_connections(void *p, int64_t *offsets, int32_t *nbrs, int64_t *robot_number,
+                              int64_t cap) {
+  World *w = static_cast<World *>(p);
+  int64_t e = 0;
+  for (size_t i = 0; i < w->robots.size(); ++i) {
+    Robot &r = w->robots[i];
+    offsets[i] = e;
+    for (int o : r.connected) {
+      if (e >= cap) return -2;
+      nbrs[e] = o;
+      uint64_t first = 0;
+      for (auto &kv : r.g.factors)
+        if (kv.second.kind == INTERROBOT && kv.second.ext_robot == o && kv.second.ext_var == 1)
+          first = kv.second.robot_number;
+      robot_number[e] = int64_t(first);
+      ++e;
+    }
+  }
+  offsets[w->robots.size()] = e;
+  return e;
+}
+int gbpo_sdf_lookup(void *p, int m, const double *xy, uint32_t *px, uint32_t *py, double *val) {
+  World *w = static_cast<World *>(p);
+  for (int i = 0; i < m; ++i)
+    val[i] = sdf_measure(w->sdf, w->cfg.world_width, w->cfg.world_height, xy[2 * i], xy[2 * i + 1],
+                         px + i, py + i);
+  return 0;
+}
+int gbpo_node_counts(void *p, int64_t out[5]) {
+  World *w = static_cast<World *>(p);
+  for (int i = 0; i < 5; ++i) out[i] = 0;
+  for (auto &r : w->robots) {
+    out[0] += int64_t(r.g.vars.size());
+    for (auto &kv : r.g.factors) {
+      switch (kv.second.kind) {
+        case DYNAMIC: out[1]++; break;
+        case OBSTACLE: out[2]++; break;
+        case TRACKING: out[3]++; break;
+        case INTERROBOT: out[4]++; break;
+      }
+    }
+  }
+  return 0;
+}
+// Inbox introspection for white-box tests: the message a variable holds from
+// the mirror InterRobot factor owned by `from_robot` (returns 0 if Empty/absent).
+int gbpo_read_mirror_message(void *p, int robot, int var, int from_robot, double *eta,
+                             double *lam) {
+  World *w = static_cast<World *>(p);
+  for (auto &kv : w->robots[robot].g.vars[var].inbox) {
+    if (kv.first.first != from_robot) continue;
+    if (kv.second.is_empty()) return 0;
+    std::copy(kv.second.payload->eta.begin(), kv.second.payload->eta.end(), eta);
+    std::copy(kv.second.payload->lam.a.begin(), kv.second.payload->lam.a.end(), lam);
+    return 1;
+  }
+  return 0;
+}
+// Tracking factor state of robot r, variable i: record, last_pos (f32), last_value.
+int gbpo_read_tracking(void *p, int robot, int var, int64_t *record, float *pos, double *value) {
+  World *w = static_cast<World *>(p);
+  for (auto &kv : w->robots[robot].g.factors) {
+    Factor &f = kv.second;
+    if (f.kind != TRACKING || f.own_var != var) continue;
+    *record = int64_t(f.trk_record);
+    pos[0] = f.last_pos[0];
+    pos[1] = f.last_pos[1];
+    *value = f.last_value;
+    return 1;
+  }
+  return 0;
+}
+
+}  // extern "C"

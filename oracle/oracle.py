@@ -1,0 +1,269 @@
+"""ctypes wrapper around oracle/_build/libgbp_oracle.so — TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import
+this module; nothing in magics_b200/ does.  The wrapper mirrors the method names
+of magics_b200.World so a parity test can drive both with the same code.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libgbp_oracle.so")
+
+
+class OracleConfig(C.Structure):
+    # same field order as gbp_config_t (include/gbp_b200.h)
+    _fields_ = [
+        ("num_variables", C.c_int32),
+        ("sigma_factor_dynamics", C.c_float),
+        ("sigma_factor_interrobot", C.c_float),
+        ("sigma_factor_obstacle", C.c_float),
+        ("sigma_factor_tracking", C.c_float),
+        ("safety_distance_multiplier", C.c_float),
+        ("comms_radius", C.c_float),
+        ("target_speed", C.c_float),
+        ("delta_t", C.c_float),
+        ("tracking_switch_padding", C.c_float),
+        ("tracking_attraction_distance", C.c_float),
+        ("enable_dynamic", C.c_uint8),
+        ("enable_interrobot", C.c_uint8),
+        ("enable_obstacle", C.c_uint8),
+        ("enable_tracking", C.c_uint8),
+        ("schedule_kind", C.c_int32),
+        ("iterations_internal", C.c_int32),
+        ("iterations_external", C.c_int32),
+        ("world_width", C.c_double),
+        ("world_height", C.c_double),
+    ]
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the committed Makefile (g++ only)."""
+    src = os.path.join(_HERE, "gbp_oracle.cpp")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-s"] + (["-B"] if force else []), check=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.gbpo_create.restype = C.c_void_p
+        _lib.gbpo_create.argtypes = [C.c_void_p]
+        _lib.gbpo_read_connections.restype = C.c_int64
+        assert _lib.gbpo_config_size() == C.sizeof(OracleConfig)
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def schedule(kind: int, internal: int, external: int):
+    oi = np.zeros(256, np.uint8)
+    oe = np.zeros(256, np.uint8)
+    n = lib().gbpo_schedule(C.c_int32(kind), C.c_uint8(internal), C.c_uint8(external),
+                            _p(oi, C.c_uint8), _p(oe, C.c_uint8))
+    assert n >= 0
+    return oi[:n].astype(bool), oe[:n].astype(bool)
+
+
+def variable_timesteps(horizon: int, multiple: int) -> np.ndarray:
+    out = np.zeros(4096, np.uint32)
+    n = lib().gbpo_variable_timesteps(C.c_uint32(horizon), C.c_uint32(multiple), _p(out, C.c_uint32), 4096)
+    assert n >= 0
+    return out[:n].copy()
+
+
+def marginalise(eta: np.ndarray, lam: np.ndarray, marg_idx: int):
+    """marginalise_factor_distance; returns None for Message::empty()."""
+    eta = np.ascontiguousarray(eta, np.float64)
+    lam = np.ascontiguousarray(lam, np.float64)
+    n = eta.shape[0]
+    oeta, olam, omu = np.zeros(n), np.zeros((n, n)), np.zeros(n)
+    k = lib().gbpo_marginalise(n, _p(eta, C.c_double), _p(lam, C.c_double), marg_idx,
+                               _p(oeta, C.c_double), _p(olam, C.c_double), _p(omu, C.c_double))
+    if k == 0:
+        return None
+    return oeta[:k].copy(), olam.reshape(-1)[: k * k].reshape(k, k).copy(), omu[:k].copy()
+
+
+def extract_blocks(lam8: np.ndarray, marg_idx: int):
+    lam8 = np.ascontiguousarray(lam8, np.float64)
+    aa, ab, ba, bb = (np.zeros((4, 4)) for _ in range(4))
+    lib().gbpo_extract_blocks(_p(lam8, C.c_double), marg_idx, _p(aa, C.c_double), _p(ab, C.c_double),
+                              _p(ba, C.c_double), _p(bb, C.c_double))
+    return aa, ab, ba, bb
+
+
+def inv4(m: np.ndarray):
+    m = np.ascontiguousarray(m, np.float64)
+    out = np.zeros((4, 4))
+    ok = lib().gbpo_inv4(_p(m, C.c_double), _p(out, C.c_double))
+    return out if ok else None
+
+
+class OracleWorld:
+    """Same surface as magics_b200.World, executed by the CPU restatement."""
+
+    def __init__(self, cfg, threads: int = 1):
+        self._cfg = OracleConfig(**{f[0]: getattr(cfg, f[0]) for f in OracleConfig._fields_})
+        self._h = lib().gbpo_create(C.byref(self._cfg))
+        self.V = int(cfg.num_variables)
+        self._lib = lib()
+        self._lib.gbpo_set_threads(C.c_void_p(self._h), threads)
+
+    def close(self):
+        if self._h:
+            self._lib.gbpo_destroy(C.c_void_p(self._h))
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def _call(self, name, *args):
+        rc = getattr(self._lib, name)(C.c_void_p(self._h), *args)
+        if rc < 0:
+            raise RuntimeError(f"oracle {name} failed: {rc}")
+        return rc
+
+    @property
+    def num_robots(self):
+        return self._lib.gbpo_num_robots(C.c_void_p(self._h))
+
+    def set_threads(self, t):
+        self._lib.gbpo_set_threads(C.c_void_p(self._h), int(t))
+
+    def set_sdf(self, rgb8: np.ndarray):
+        rgb8 = np.ascontiguousarray(rgb8, np.uint8)
+        h, w = rgb8.shape[:2]
+        self._call("gbpo_set_sdf", _p(rgb8, C.c_uint8), w, h)
+
+    def add_robots(self, radii, timesteps, init_means, positions, wp_offsets, wp_xy):
+        radii = np.ascontiguousarray(radii, np.float32)
+        timesteps = np.ascontiguousarray(timesteps, np.uint32)
+        init_means = np.ascontiguousarray(init_means, np.float64)
+        positions = np.ascontiguousarray(positions, np.float32)
+        wp_offsets = np.ascontiguousarray(wp_offsets, np.int32)
+        wp_xy = np.ascontiguousarray(wp_xy, np.float32)
+        n = radii.shape[0]
+        assert timesteps.shape[0] == self.V and init_means.size == n * self.V * 4
+        self._call("gbpo_add_robots", n, _p(radii, C.c_float), _p(timesteps, C.c_uint32),
+                   _p(init_means, C.c_double), _p(positions, C.c_float), _p(wp_offsets, C.c_int32),
+                   _p(wp_xy, C.c_float))
+
+    def update_topology(self):
+        self._call("gbpo_update_topology")
+
+    def set_comms(self, antenna_active=None, idle=None):
+        a = None if antenna_active is None else np.ascontiguousarray(antenna_active, np.uint8)
+        i = None if idle is None else np.ascontiguousarray(idle, np.uint8)
+        self._call("gbpo_set_comms", _p(a, C.c_uint8), _p(i, C.c_uint8))
+
+    def set_waypoint_index(self, idx):
+        idx = np.ascontiguousarray(idx, np.int32)
+        self._call("gbpo_set_waypoint_index", _p(idx, C.c_int32))
+
+    def update_prior_of_horizon_state(self):
+        self._call("gbpo_update_prior_of_horizon_state")
+
+    def update_prior_of_current_state(self):
+        self._call("gbpo_update_prior_of_current_state")
+
+    def change_prior_of_variable(self, variable_index, robots, new_means):
+        robots = np.ascontiguousarray(robots, np.int32)
+        new_means = np.ascontiguousarray(new_means, np.float64)
+        self._call("gbpo_change_prior_of_variable", int(variable_index), robots.shape[0],
+                   _p(robots, C.c_int32), _p(new_means, C.c_double))
+
+    def iterate(self):
+        self._call("gbpo_iterate")
+
+    def iterate_schedule(self, internal, external):
+        i = np.ascontiguousarray(internal, np.uint8)
+        e = np.ascontiguousarray(external, np.uint8)
+        self._call("gbpo_iterate_schedule", i.shape[0], _p(i, C.c_uint8), _p(e, C.c_uint8))
+
+    def internal_factor_iteration(self):
+        self._call("gbpo_internal_factor_iteration")
+
+    def internal_variable_iteration(self):
+        self._call("gbpo_internal_variable_iteration")
+
+    def external_factor_iteration(self):
+        self._call("gbpo_external_factor_iteration")
+
+    def external_variable_iteration(self):
+        self._call("gbpo_external_variable_iteration")
+
+    def step(self):
+        self._call("gbpo_step")
+
+    def change_factor_enabled(self, kind, enabled):
+        self._call("gbpo_change_factor_enabled", int(kind), C.c_uint8(int(enabled)))
+
+    def set_safety_distance_multiplier(self, m):
+        self._call("gbpo_set_safety_distance_multiplier", C.c_float(m))
+
+    def set_schedule(self, kind, internal, external):
+        self._call("gbpo_set_schedule", int(kind), int(internal), int(external))
+
+    def read_beliefs(self):
+        n, V = self.num_robots, self.V
+        eta = np.zeros((n, V, 4))
+        lam = np.zeros((n, V, 4, 4))
+        mean = np.zeros((n, V, 4))
+        cov = np.zeros((n, V, 4, 4))
+        valid = np.zeros((n, V), np.uint8)
+        self._call("gbpo_read_beliefs", _p(eta, C.c_double), _p(lam, C.c_double), _p(mean, C.c_double),
+                   _p(cov, C.c_double), _p(valid, C.c_uint8))
+        return dict(eta=eta, lam=lam, mean=mean, cov=cov, valid=valid.astype(bool))
+
+    def read_positions(self):
+        xy = np.zeros((self.num_robots, 2), np.float32)
+        self._call("gbpo_read_positions", _p(xy, C.c_float))
+        return xy
+
+    def read_connections(self, capacity=None):
+        n = self.num_robots
+        cap = capacity or max(1, n * 64)
+        while True:
+            off = np.zeros(n + 1, np.int64)
+            nb = np.zeros(cap, np.int32)
+            rn = np.zeros(cap, np.int64)
+            e = self._lib.gbpo_read_connections(C.c_void_p(self._h), _p(off, C.c_int64), _p(nb, C.c_int32),
+                                                _p(rn, C.c_int64), C.c_int64(cap))
+            if e >= 0:
+                return off, nb[:e].copy(), rn[:e].copy()
+            cap *= 4
+
+    def sdf_lookup(self, xy):
+        xy = np.ascontiguousarray(xy, np.float64)
+        m = xy.shape[0]
+        px, py, val = np.zeros(m, np.uint32), np.zeros(m, np.uint32), np.zeros(m)
+        self._call("gbpo_sdf_lookup", m, _p(xy, C.c_double), _p(px, C.c_uint32), _p(py, C.c_uint32),
+                   _p(val, C.c_double))
+        return px, py, val
+
+    def node_counts(self):
+        out = np.zeros(5, np.int64)
+        self._call("gbpo_node_counts", _p(out, C.c_int64))
+        return out
+
+    def read_tracking(self, robot, var):
+        rec = C.c_int64(0)
+        pos = np.zeros(2, np.float32)
+        val = C.c_double(0)
+        ok = self._call("gbpo_read_tracking", int(robot), int(var), C.byref(rec), _p(pos, C.c_float), C.byref(val))
+        return (rec.value, pos, val.value) if ok else None
