@@ -5,6 +5,7 @@
 // state lives in the device store (gbp_store.cuh).  No CPU fallback exists:
 // every entry point that computes launches CUDA kernels on the world's stream.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -346,6 +347,20 @@ struct gbp_world {
   std::vector<int32_t> wp_off{0};
   std::vector<float> wp_xy;
   uint8_t *sdf_dev = nullptr;
+  // two edge sets: the live one and a spare the next topology change is built into
+  struct EdgeSet {
+    int32_t *enbr = nullptr;
+    double *e_dsafe = nullptr;
+    uint64_t *e_rnum = nullptr;
+    uint32_t *e_birth = nullptr;
+    uint8_t *e_new = nullptr;
+    double *mir = nullptr;
+    int64_t *map = nullptr;
+    int64_t cap = 0;
+  } edges[2];
+  int cur = 0;
+  int32_t *t_nlow = nullptr;
+  int64_t *t_result_dev = nullptr, *t_result_host = nullptr;
   bool pending_internal_factor = false, pending_external_factor = false;
   // topology scratch
   int32_t *t_cx = nullptr, *t_cz = nullptr, *t_idx = nullptr, *t_idx_sorted = nullptr;
@@ -487,8 +502,44 @@ int run_schedule(gbp_world *w, int n, const uint8_t *internal, const uint8_t *ex
   return 0;
 }
 
+using EdgeSet = gbp_world::EdgeSet;
+
+void bind_edge_set(gbp_world *w) {
+  const EdgeSet &e = w->edges[w->cur];
+  Store &s = w->s;
+  s.enbr = e.enbr;
+  s.e_dsafe = e.e_dsafe;
+  s.e_rnum = e.e_rnum;
+  s.e_birth = e.e_birth;
+  s.e_new = e.e_new;
+  s.mir = e.mir;
+  s.EV = e.cap * (s.V - 1);
+}
+
+int grow_edge_set(gbp_world *w, EdgeSet *e, int64_t cap) {
+  CK(cudaStreamSynchronize(w->stream));
+  cudaFree(e->enbr); cudaFree(e->e_dsafe); cudaFree(e->e_rnum); cudaFree(e->e_birth); cudaFree(e->e_new);
+  cudaFree(e->mir); cudaFree(e->map);
+  const int Vm1 = w->s.V - 1;
+  CK(dalloc(e->enbr, size_t(cap)));
+  CK(dalloc(e->e_dsafe, size_t(cap)));
+  CK(dalloc(e->e_rnum, size_t(cap)));
+  CK(dalloc(e->e_birth, size_t(cap)));
+  CK(dalloc(e->e_new, size_t(cap)));
+  CK(dalloc(e->map, size_t(cap)));
+  CK(dalloc(e->mir, size_t(6) * size_t(cap) * Vm1));
+  e->cap = cap;
+  return 0;
+}
+
 int ensure_topology_scratch(gbp_world *w, int64_t n) {
+  if (!w->t_result_dev) {
+    CK(dalloc(w->t_result_dev, 2));
+    CK(cudaMallocHost(reinterpret_cast<void **>(&w->t_result_host), 2 * sizeof(int64_t)));
+  }
   if (n <= w->t_cap) return 0;
+  cudaFree(w->t_nlow);
+  CK(dalloc(w->t_nlow, n));
   cudaFree(w->t_cx); cudaFree(w->t_cz); cudaFree(w->t_idx); cudaFree(w->t_idx_sorted);
   cudaFree(w->t_keys); cudaFree(w->t_keys_sorted); cudaFree(w->t_cnt); cudaFree(w->t_off);
   cudaFree(w->t_newcnt); cudaFree(w->t_newoff); cudaFree(w->t_cub);
@@ -583,7 +634,10 @@ void gbp_world_destroy(gbp_world_t *w) {
                   s.mu_ext, s.mu_new, s.cov, s.valid, s.m_dynL, s.m_dynR, s.m_obs, s.m_trk, s.dyn_dt,
                   s.trk_record, s.trk_timeout, s.trk_last, s.trk_value, s.radius, s.t0, s.pos, s.antenna,
                   s.idle, s.finished, s.latest, s.iter_factor, s.gid, s.next_wp, s.wp_off, s.wp_xy, s.eoff,
-                  s.nlow, s.enbr, s.e_dsafe, s.e_rnum, s.e_birth, s.e_new, s.mir, w->sdf_dev, w->t_cx,
+                  s.nlow, w->edges[0].enbr, w->edges[0].e_dsafe, w->edges[0].e_rnum, w->edges[0].e_birth,
+                  w->edges[0].e_new, w->edges[0].mir, w->edges[0].map, w->edges[1].enbr, w->edges[1].e_dsafe,
+                  w->edges[1].e_rnum, w->edges[1].e_birth, w->edges[1].e_new, w->edges[1].mir, w->edges[1].map,
+                  w->t_nlow, w->t_result_dev, w->sdf_dev, w->t_cx,
                   w->t_cz, w->t_idx, w->t_idx_sorted, w->t_keys, w->t_keys_sorted, w->t_cnt, w->t_off,
                   w->t_newcnt, w->t_newoff, w->t_cub};
   for (void *q : ptrs) cudaFree(q);
@@ -595,6 +649,7 @@ void gbp_world_destroy(gbp_world_t *w) {
   cudaEventDestroy(w->ev0);
   cudaEventDestroy(w->ev1);
   cudaStreamDestroy(w->stream);
+  if (w->t_result_host) cudaFreeHost(w->t_result_host);
   delete w;
 }
 
@@ -744,61 +799,52 @@ int gbp_world_update_topology(gbp_world_t *w) {
   size_t cb = w->t_cub_bytes;
   CK(cub::DeviceRadixSort::SortPairs(w->t_cub, cb, w->t_keys, w->t_keys_sorted, w->t_idx, w->t_idx_sorted, n, 0, 32, st));
   gbp::k_neighbours<false><<<blocks_for(n, T), T, 0, st>>>(n, 0, n, s.pos, s.pos + s.cap, w->t_cx, w->t_cz,
-                                                           w->t_keys_sorted, w->t_idx_sorted, R, w->t_cnt, nullptr);
+                                                           w->t_keys_sorted, w->t_idx_sorted, R, w->t_cnt, nullptr, 0);
   CK(cudaMemsetAsync(w->t_cnt + n, 0, sizeof(int64_t), st));
   cb = w->t_cub_bytes;
   CK(cub::DeviceScan::ExclusiveSum(w->t_cub, cb, w->t_cnt, w->t_off, n + 1, st));
-  int64_t E1 = 0;
-  CK(cudaMemcpyAsync(&E1, w->t_off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
   w->launches += 4;
-  int32_t *nnbr = nullptr;
-  int64_t *map = nullptr;
-  CK(dalloc(nnbr, size_t(E1)));
-  CK(dalloc(map, size_t(E1)));
-  gbp::k_neighbours<true><<<blocks_for(n, T), T, 0, st>>>(n, 0, n, s.pos, s.pos + s.cap, w->t_cx, w->t_cz,
-                                                          w->t_keys_sorted, w->t_idx_sorted, R, w->t_off, nnbr);
-  gbp::k_edge_diff<<<blocks_for(n, T), T, 0, st>>>(n, w->t_off, nnbr, s.eoff, s.enbr, n, map, w->t_newcnt, s.nlow);
-  CK(cudaMemsetAsync(w->t_newcnt + n, 0, sizeof(int64_t), st));
-  cb = w->t_cub_bytes;
-  CK(cub::DeviceScan::ExclusiveSum(w->t_cub, cb, w->t_newcnt, w->t_newoff, n + 1, st));
-  int64_t total_new = 0;
-  CK(cudaMemcpyAsync(&total_new, w->t_newoff + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  w->launches += 3;
-  if (total_new == 0 && E1 == s.E) {  // connectivity unchanged: keep the store as is
-    cudaFree(nnbr);
-    cudaFree(map);
-    return 0;
+  // The new CSR is written straight into the spare edge set; one host sync per
+  // tick reads (edge count, new edge count).  If the spare set is too small the
+  // guarded kernels did nothing: grow it and run them again.
+  EdgeSet *spare = &w->edges[1 - w->cur];
+  int64_t E1 = 0, total_new = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    gbp::k_neighbours<true><<<blocks_for(n, T), T, 0, st>>>(n, 0, n, s.pos, s.pos + s.cap, w->t_cx, w->t_cz,
+                                                            w->t_keys_sorted, w->t_idx_sorted, R, w->t_off,
+                                                            spare->enbr, spare->cap);
+    gbp::k_edge_diff<<<blocks_for(n, T), T, 0, st>>>(n, w->t_off, spare->enbr, s.eoff, s.enbr, n, spare->map,
+                                                     w->t_newcnt, w->t_nlow, spare->cap);
+    CK(cudaMemsetAsync(w->t_newcnt + n, 0, sizeof(int64_t), st));
+    cb = w->t_cub_bytes;
+    CK(cub::DeviceScan::ExclusiveSum(w->t_cub, cb, w->t_newcnt, w->t_newoff, n + 1, st));
+    gbp::k_topology_result<<<1, 1, 0, st>>>(w->t_off, w->t_newoff, n, w->t_result_dev);
+    CK(cudaMemcpyAsync(w->t_result_host, w->t_result_dev, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    w->launches += 4;
+    E1 = w->t_result_host[0];
+    total_new = w->t_result_host[1];
+    if (E1 <= spare->cap) break;
+    if (int rc = grow_edge_set(w, spare, E1 + E1 / 4 + 1024)) return rc;
   }
+  if (total_new == 0 && E1 == s.E) return 0;  // connectivity unchanged: keep the store as is
   w->epoch += 1;
   const int Vm1 = s.V - 1;
-  double *e_dsafe = nullptr, *mir = nullptr;
-  uint64_t *e_rnum = nullptr;
-  uint32_t *e_birth = nullptr;
-  uint8_t *e_new = nullptr;
-  CK(dalloc(e_dsafe, size_t(E1)));
-  CK(dalloc(e_rnum, size_t(E1)));
-  CK(dalloc(e_birth, size_t(E1)));
-  CK(dalloc(e_new, size_t(E1)));
-  const int64_t nEV = std::max<int64_t>(E1 * Vm1, 1);
-  CK(dalloc(mir, size_t(6) * size_t(nEV)));
-  gbp::k_edge_assign<<<blocks_for(n, T), T, 0, st>>>(n, s.V, w->t_off, nnbr, map, w->t_newoff, s.radius,
+  gbp::k_edge_assign<<<blocks_for(n, T), T, 0, st>>>(n, s.V, w->t_off, spare->enbr, spare->map, w->t_newoff, s.radius,
                                                      double(w->cfg.safety_distance_multiplier), w->robot_number,
-                                                     w->epoch, s.e_dsafe, s.e_rnum, s.e_birth, s.e_new, e_dsafe,
-                                                     e_rnum, e_birth, e_new);
+                                                     w->epoch, s.e_dsafe, s.e_rnum, s.e_birth, s.e_new,
+                                                     spare->e_dsafe, spare->e_rnum, spare->e_birth, spare->e_new);
   if (E1 > 0)
-    gbp::k_mirror_move<<<blocks_for(E1 * Vm1, 256), 256, 0, st>>>(E1 * Vm1, Vm1, map, s.mir, s.EV, mir, nEV);
+    gbp::k_mirror_move<<<blocks_for(E1 * Vm1, 256), 256, 0, st>>>(E1 * Vm1, Vm1, spare->map, s.mir, s.EV,
+                                                                  spare->mir, spare->cap * Vm1);
   gbp::k_snapshot_mu_new<<<blocks_for(int64_t(n) * s.V, 256), 256, 0, st>>>(s, w->p, w->t_newcnt);
   CK(cudaGetLastError());
   w->launches += 3;
   CK(cudaMemcpyAsync(s.eoff, w->t_off, size_t(n + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
-  CK(cudaStreamSynchronize(st));
-  cudaFree(s.enbr); cudaFree(s.e_dsafe); cudaFree(s.e_rnum); cudaFree(s.e_birth); cudaFree(s.e_new);
-  cudaFree(s.mir); cudaFree(map);
-  s.enbr = nnbr; s.e_dsafe = e_dsafe; s.e_rnum = e_rnum; s.e_birth = e_birth; s.e_new = e_new; s.mir = mir;
+  CK(cudaMemcpyAsync(s.nlow, w->t_nlow, size_t(n) * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  w->cur = 1 - w->cur;
+  bind_edge_set(w);
   s.E = E1;
-  s.EV = nEV;
   w->robot_number += uint64_t(Vm1) * uint64_t(total_new);
   return 0;
 }

@@ -262,6 +262,7 @@ GBP_DEV bool interrobot_message(bool a_first, const double (&muA)[2], const doub
 }
 
 // Rust `as u32` (saturating; obstacle.rs:153-155).
-GBP_DEV uint32_t sat_u32(double v) { return __double2uint_rz(v); }
+// cvt.rzi.u32.f64 saturates out-of-range values like Rust but maps NaN to 2^31; Rust maps NaN to 0.
+GBP_DEV uint32_t sat_u32(double v) { return isnan(v) ? 0u : __double2uint_rz(v); }
 
 }  // namespace gbp

@@ -66,9 +66,10 @@ __global__ void k_neighbours(int32_t nall, int32_t first, int32_t count, const f
                              const float *__restrict__ pz, const int32_t *__restrict__ cx,
                              const int32_t *__restrict__ cz, const uint32_t *__restrict__ keys_sorted,
                              const int32_t *__restrict__ idx_sorted, float R, int64_t *cnt_or_off,
-                             int32_t *nbr) {
+                             int32_t *nbr, int64_t nbr_cap) {
   const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= count) return;
+  if (FILL && cnt_or_off[count] > nbr_cap) return;  // host regrows and relaunches
   const int32_t r = first + t;
   const float ax = px[r], az = pz[r];
   const int32_t mx = cx[r], mz = cz[r];
@@ -108,9 +109,13 @@ __global__ void k_neighbours(int32_t nall, int32_t first, int32_t count, const f
 //   newcnt[r] number of new edges of r, nlow[r] neighbours with a lower id
 __global__ void k_edge_diff(int32_t n, const int64_t *__restrict__ noff, const int32_t *__restrict__ nnbr,
                             const int64_t *__restrict__ ooff, const int32_t *__restrict__ onbr,
-                            int32_t n_old, int64_t *map, int64_t *newcnt, int32_t *nlow) {
+                            int32_t n_old, int64_t *map, int64_t *newcnt, int32_t *nlow, int64_t cap) {
   const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
+  if (noff[n] > cap) {
+    newcnt[r] = 0;
+    return;
+  }
   int64_t lo0 = 0, hi0 = 0;
   if (r < n_old && ooff) {
     lo0 = ooff[r];
@@ -164,6 +169,11 @@ __global__ void k_edge_assign(int32_t n, int32_t V, const int64_t *__restrict__ 
       e_new[e] = 1;
     }
   }
+}
+
+__global__ void k_topology_result(const int64_t *noff, const int64_t *newoff, int32_t n, int64_t *out) {
+  out[0] = noff[n];
+  out[1] = newoff[n];
 }
 
 // Mirror messages of surviving edges move to their new slot; new edges start
