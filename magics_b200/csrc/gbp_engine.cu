@@ -195,8 +195,6 @@ __global__ void k_init_vars(Store s, int p, int64_t first, int64_t count) {
   s.valid[vi] = fin ? 1 : 0;
   s.mu_ext[vi] = mu[0];
   s.mu_ext[NV + vi] = mu[1];
-  s.mu_new[vi] = mu[0];
-  s.mu_new[NV + vi] = mu[1];
   s.m_dynL[vi] = gbp::empty_marker();
   s.m_dynR[vi] = gbp::empty_marker();
   s.m_obs[vi] = gbp::empty_marker();
@@ -232,14 +230,18 @@ __device__ void change_prior_dev(const Store &s, int p, uint32_t epoch, int64_t 
   s.pub_epoch[p][vi] = epoch;
   s.mu_ext[vi] = nm[0];
   s.mu_ext[NV + vi] = nm[1];
-  s.mu_new[vi] = nm[0];
-  s.mu_new[NV + vi] = nm[1];
   s.m_dynL[vi] = gbp::empty_marker();
   s.m_dynR[vi] = gbp::empty_marker();
   s.m_obs[vi] = gbp::empty_marker();
   s.m_trk[vi] = gbp::empty_marker();
   if (var >= 1 && s.eoff)
-    for (int64_t e = s.eoff[r]; e < s.eoff[r + 1]; ++e) s.mir[e * (s.V - 1) + (var - 1)] = gbp::empty_marker();
+    for (int64_t e = s.eoff[r]; e < s.eoff[r + 1]; ++e) {
+      const int64_t m = e * (s.V - 1) + (var - 1);
+      s.mir[m] = gbp::empty_marker();
+      // external factors receive the new mean whatever the antenna state (robot.rs:2272-2282)
+      s.mu_frozen[m] = nm[0];
+      s.mu_frozen[s.EV + m] = nm[1];
+    }
 }
 
 // update_prior_of_horizon_state (planner/robot.rs:2182-2283), one thread per robot.
@@ -353,8 +355,9 @@ struct gbp_world {
     double *e_dsafe = nullptr;
     uint64_t *e_rnum = nullptr;
     uint32_t *e_birth = nullptr;
-    uint8_t *e_new = nullptr;
+    uint8_t *e_frozen = nullptr;
     double *mir = nullptr;
+    double *mu_frozen = nullptr;
     int64_t *map = nullptr;
     int64_t cap = 0;
   } edges[2];
@@ -511,21 +514,23 @@ void bind_edge_set(gbp_world *w) {
   s.e_dsafe = e.e_dsafe;
   s.e_rnum = e.e_rnum;
   s.e_birth = e.e_birth;
-  s.e_new = e.e_new;
+  s.e_frozen = e.e_frozen;
   s.mir = e.mir;
+  s.mu_frozen = e.mu_frozen;
   s.EV = e.cap * (s.V - 1);
 }
 
 int grow_edge_set(gbp_world *w, EdgeSet *e, int64_t cap) {
   CK(cudaStreamSynchronize(w->stream));
-  cudaFree(e->enbr); cudaFree(e->e_dsafe); cudaFree(e->e_rnum); cudaFree(e->e_birth); cudaFree(e->e_new);
-  cudaFree(e->mir); cudaFree(e->map);
+  cudaFree(e->enbr); cudaFree(e->e_dsafe); cudaFree(e->e_rnum); cudaFree(e->e_birth); cudaFree(e->e_frozen);
+  cudaFree(e->mir); cudaFree(e->map); cudaFree(e->mu_frozen);
   const int Vm1 = w->s.V - 1;
   CK(dalloc(e->enbr, size_t(cap)));
   CK(dalloc(e->e_dsafe, size_t(cap)));
   CK(dalloc(e->e_rnum, size_t(cap)));
   CK(dalloc(e->e_birth, size_t(cap)));
-  CK(dalloc(e->e_new, size_t(cap)));
+  CK(dalloc(e->e_frozen, size_t(cap)));
+  CK(dalloc(e->mu_frozen, size_t(2) * size_t(cap) * Vm1));
   CK(dalloc(e->map, size_t(cap)));
   CK(dalloc(e->mir, size_t(6) * size_t(cap) * Vm1));
   e->cap = cap;
@@ -631,12 +636,13 @@ void gbp_world_destroy(gbp_world_t *w) {
   cudaStreamSynchronize(w->stream);
   Store &s = w->s;
   void *ptrs[] = {s.prior_eta, s.prior_lam, s.pub[0], s.pub[1], s.pub_epoch[0], s.pub_epoch[1], s.bel_ext,
-                  s.mu_ext, s.mu_new, s.cov, s.valid, s.m_dynL, s.m_dynR, s.m_obs, s.m_trk, s.dyn_dt,
+                  s.mu_ext, s.cov, s.valid, s.m_dynL, s.m_dynR, s.m_obs, s.m_trk, s.dyn_dt,
                   s.trk_record, s.trk_timeout, s.trk_last, s.trk_value, s.radius, s.t0, s.pos, s.antenna,
                   s.idle, s.finished, s.latest, s.iter_factor, s.gid, s.next_wp, s.wp_off, s.wp_xy, s.eoff,
                   s.nlow, w->edges[0].enbr, w->edges[0].e_dsafe, w->edges[0].e_rnum, w->edges[0].e_birth,
-                  w->edges[0].e_new, w->edges[0].mir, w->edges[0].map, w->edges[1].enbr, w->edges[1].e_dsafe,
-                  w->edges[1].e_rnum, w->edges[1].e_birth, w->edges[1].e_new, w->edges[1].mir, w->edges[1].map,
+                  w->edges[0].e_frozen, w->edges[0].mir, w->edges[0].map, w->edges[0].mu_frozen, w->edges[1].enbr,
+                  w->edges[1].e_dsafe, w->edges[1].e_rnum, w->edges[1].e_birth, w->edges[1].e_frozen,
+                  w->edges[1].mir, w->edges[1].map, w->edges[1].mu_frozen,
                   w->t_nlow, w->t_result_dev, w->sdf_dev, w->t_cx,
                   w->t_cz, w->t_idx, w->t_idx_sorted, w->t_keys, w->t_keys_sorted, w->t_cnt, w->t_off,
                   w->t_newcnt, w->t_newoff, w->t_cub};
@@ -696,7 +702,6 @@ int gbp_world_add_robots(gbp_world_t *w, int32_t n, const float *radii, const ui
   CK(regrow(s.pub_epoch[1], 1, oldNV, newNV, used, st));
   CK(regrow(s.bel_ext, gbp::kRec, oldNV, newNV, used, st));
   CK(regrow(s.mu_ext, 2, oldNV, newNV, used, st));
-  CK(regrow(s.mu_new, 2, oldNV, newNV, used, st));
   CK(regrow(s.cov, 16, oldNV, newNV, used, st));
   CK(regrow(s.valid, 1, oldNV, newNV, used, st));
   CK(regrow(s.m_dynL, 20, oldNV, newNV, used, st));
@@ -832,12 +837,12 @@ int gbp_world_update_topology(gbp_world_t *w) {
   const int Vm1 = s.V - 1;
   gbp::k_edge_assign<<<blocks_for(n, T), T, 0, st>>>(n, s.V, w->t_off, spare->enbr, spare->map, w->t_newoff, s.radius,
                                                      double(w->cfg.safety_distance_multiplier), w->robot_number,
-                                                     w->epoch, s.e_dsafe, s.e_rnum, s.e_birth, s.e_new,
-                                                     spare->e_dsafe, spare->e_rnum, spare->e_birth, spare->e_new);
+                                                     w->epoch, s.e_dsafe, s.e_rnum, s.e_birth, s.e_frozen,
+                                                     spare->e_dsafe, spare->e_rnum, spare->e_birth, spare->e_frozen);
   if (E1 > 0)
-    gbp::k_mirror_move<<<blocks_for(E1 * Vm1, 256), 256, 0, st>>>(E1 * Vm1, Vm1, spare->map, s.mir, s.EV,
-                                                                  spare->mir, spare->cap * Vm1);
-  gbp::k_snapshot_mu_new<<<blocks_for(int64_t(n) * s.V, 256), 256, 0, st>>>(s, w->p, w->t_newcnt);
+    gbp::k_mirror_move<<<blocks_for(E1 * Vm1, 256), 256, 0, st>>>(s, w->p, E1 * Vm1, Vm1, w->t_off, spare->map, s.mir,
+                                                                  s.mu_frozen, s.EV, spare->mir, spare->mu_frozen,
+                                                                  spare->cap * Vm1);
   CK(cudaGetLastError());
   w->launches += 3;
   CK(cudaMemcpyAsync(s.eoff, w->t_off, size_t(n + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));

@@ -30,6 +30,9 @@
 namespace gbp {
 
 constexpr int kIterBlock = 128;
+#ifndef GBP_ITER_MIN_BLOCKS
+#define GBP_ITER_MIN_BLOCKS 3
+#endif
 
 GBP_DEV double dot2(const double (&a)[2], const double (&b)[2]) { return (0.0 + a[0] * b[0]) + a[1] * b[1]; }
 GBP_DEV double norm2(double x, double y) { return sqrt((0.0 + x * x) + y * y); }
@@ -234,7 +237,7 @@ GBP_DEV void obstacle_update(const Store &s, int64_t vi, const double (&x)[4]) {
 }
 
 template <bool EXT, bool INT>
-__global__ void __launch_bounds__(kIterBlock)
+__global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
     k_iterate(const __grid_constant__ Store s, const int p, const uint32_t epoch) {
   const int V = s.V;
   const int rpw = 32 / V;
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(kIterBlock)
     const int64_t e0 = s.eoff[r];
     const int64_t e1 = (i >= 1) ? s.eoff[r + 1] : e0;  // variable 0 has no InterRobot factors
     const int64_t elow = e0 + s.nlow[r];  // edges [e0, elow) have a lower robot id than r
-    double mu_sent[2] = {0.0, 0.0}, mu_born[2] = {0.0, 0.0};
+    double mu_sent[2] = {0.0, 0.0};
     if (e1 > e0) {
       mu_sent[0] = s.mu_ext[vi];
       mu_sent[1] = s.mu_ext[NV + vi];
@@ -299,9 +302,9 @@ __global__ void __launch_bounds__(kIterBlock)
         muA[0] = a_ne ? pubr[20 * NV + va] : 0.0;
         muA[1] = a_ne ? pubr[21 * NV + va] : 0.0;
         double mb[2] = {mu_sent[0], mu_sent[1]};
-        if (s.e_new[e]) {
-          mb[0] = s.mu_new[vi];
-          mb[1] = s.mu_new[NV + vi];
+        if (s.e_frozen[e]) {
+          mb[0] = s.mu_frozen[m];
+          mb[1] = s.mu_frozen[s.EV + m];
         }
         const double tiny = s.tiny_scale * double(s.e_rnum[e] + uint64_t(i - 1));
         double me[2], ml[4];
@@ -325,6 +328,12 @@ __global__ void __launch_bounds__(kIterBlock)
         }
       } else {
         add_mirror(s, m, ae, al);  // undelivered: the variable keeps the old message
+        // ... and A's factor keeps the mean it already holds from this variable
+        // while this variable's belief moves on (robot.rs:1851): freeze it
+        if (!s.e_frozen[e]) {
+          s.mu_frozen[m] = mu_sent[0];
+          s.mu_frozen[s.EV + m] = mu_sent[1];
+        }
       }
     }
     if (!added) add_internal(s, vi, i, ae, al);
@@ -350,10 +359,12 @@ __global__ void __launch_bounds__(kIterBlock)
   }
   if (EXT) {
     __syncwarp();
-    if (do_ext && i == 1 && s.en_ir) {
+    if (do_ext && i == 1) {
+      // delivered edges hold mu_ext again; undelivered ones are (stay) frozen
       for (int64_t e = s.eoff[r]; e < s.eoff[r + 1]; ++e) {
         const int A = s.enbr[e];
-        if (s.e_new[e] && s.antenna[A] != 0 && s.idle[A] == 0) s.e_new[e] = 0;
+        const uint8_t fr = (s.en_ir && s.antenna[A] != 0 && s.idle[A] == 0) ? 0 : 1;
+        if (s.e_frozen[e] != fr) s.e_frozen[e] = fr;
       }
     }
   }

@@ -16,7 +16,8 @@
 //            factors (variable inbox entries)
 //   mir      the messages a robot's variables hold from the InterRobot factors
 //            owned by its neighbours ("mirror" factors), one per (edge, i)
-//   mu_ext   position mean each variable last sent to external factors
+//   mu_ext   position mean each variable last sent to external factors (per-edge override
+//            mu_frozen while an edge has not received the latest one)
 // pub is double buffered: a fused pass reads neighbours' records from pub[p]
 // while writing its own new record to pub[1-p].
 #pragma once
@@ -39,7 +40,6 @@ struct Store {
   uint32_t *pub_epoch[2];  // [NV]    epoch of the last write of that record (0 = never)
   double *bel_ext;       // [24][NV]  belief after the last external variable iteration
   double *mu_ext;        // [2][NV]   position mean last delivered to external factors
-  double *mu_new;        // [2][NV]   belief position mean when the newest edges were created
   double *cov;           // [16][NV]  VariableBelief.covariance_matrix
   uint8_t *valid;        // [NV]      VariableBelief.valid
   double *m_dynL;        // [20][NV]  message from Dynamic factor i-1 (eta4, Lambda16)
@@ -74,7 +74,10 @@ struct Store {
   double *e_dsafe;     // [E]   safety distance of A's factor: multiplier * radius_A
   uint64_t *e_rnum;    // [E]   robot_number of A's factor toward B at i = 1
   uint32_t *e_birth;   // [E]   epoch at which the edge was created
-  uint8_t *e_new;      // [E]   1 until B's first delivered external variable message
+  uint8_t *e_frozen;   // [E]   1 while A's factor holds an older mean of B than mu_ext (see mu_frozen)
+  double *mu_frozen;   // [2][E*(V-1)] position mean of B's variable that A's factor holds while the
+                       //   edge is frozen: B's belief at edge creation (robot.rs:1557-1585), or the
+                       //   last mean delivered before A's antenna went off (robot.rs:1851)
   double *mir;         // [6][E*(V-1)]  eta0, eta1, lam00, lam01, lam10, lam11
   int64_t E;
   int64_t EV;          // plane stride of mir = Ecap*(V-1)

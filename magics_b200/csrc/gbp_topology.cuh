@@ -148,8 +148,8 @@ __global__ void k_edge_assign(int32_t n, int32_t V, const int64_t *__restrict__ 
                               const int64_t *__restrict__ newoff, const float *__restrict__ radius,
                               double safety_mult, uint64_t counter0, uint32_t epoch,
                               const double *__restrict__ o_dsafe, const uint64_t *__restrict__ o_rnum,
-                              const uint32_t *__restrict__ o_birth, const uint8_t *__restrict__ o_new,
-                              double *e_dsafe, uint64_t *e_rnum, uint32_t *e_birth, uint8_t *e_new) {
+                              const uint32_t *__restrict__ o_birth, const uint8_t *__restrict__ o_frozen,
+                              double *e_dsafe, uint64_t *e_rnum, uint32_t *e_birth, uint8_t *e_frozen) {
   const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   for (int64_t e = noff[r]; e < noff[r + 1]; ++e) {
@@ -159,14 +159,14 @@ __global__ void k_edge_assign(int32_t n, int32_t V, const int64_t *__restrict__ 
     if (old >= 0) {
       e_rnum[e] = o_rnum[old];
       e_birth[e] = o_birth[old];
-      e_new[e] = o_new[old];
+      e_frozen[e] = o_frozen[old];
     } else {
       int64_t rank = 0;
       for (int64_t e2 = noff[a]; e2 < noff[a + 1]; ++e2)
         if (map[e2] < 0 && nnbr[e2] < r) ++rank;
       e_rnum[e] = counter0 + uint64_t(V - 1) * uint64_t(newoff[a] + rank);
       e_birth[e] = epoch;
-      e_new[e] = 1;
+      e_frozen[e] = 1;  // the factor holds the receiver's belief at creation time
     }
   }
 }
@@ -176,34 +176,38 @@ __global__ void k_topology_result(const int64_t *noff, const int64_t *newoff, in
   out[1] = newoff[n];
 }
 
-// Mirror messages of surviving edges move to their new slot; new edges start
-// Empty (add_external_edge, factorgraph.rs:340-353).
-__global__ void k_mirror_move(int64_t total, int32_t Vm1, const int64_t *__restrict__ map,
-                              const double *__restrict__ omir, int64_t oEV, double *nmir, int64_t nEV) {
+// Mirror messages (and frozen means) of surviving edges move to their new slot.
+// New edges start with an Empty mirror message (add_external_edge,
+// factorgraph.rs:340-353) and the receiver's current belief mean as the message
+// its variable "sent" the factor (robot.rs:1557-1585, variable.rs:234-240).
+__global__ void k_mirror_move(Store s, int p, int64_t total, int32_t Vm1, const int64_t *__restrict__ noff,
+                              const int64_t *__restrict__ map, const double *__restrict__ omir,
+                              const double *__restrict__ ofrozen, int64_t oEV, double *nmir,
+                              double *nfrozen, int64_t nEV) {
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const int64_t e = t / Vm1, i = t - e * Vm1;
   const int64_t old = map[e];
   if (old < 0) {
     nmir[t] = empty_marker();
+    // receiver robot r: noff[r] <= e < noff[r+1]
+    int32_t lo = 0, hi = s.Nloc;
+    while (lo < hi) {
+      const int32_t mid = (lo + hi) >> 1;
+      if (noff[mid + 1] <= e) lo = mid + 1;
+      else hi = mid;
+    }
+    const int64_t vi = int64_t(lo) * s.V + (i + 1);
+    const double *rec = s.latest[lo] ? s.bel_ext : s.pub[p];
+    nfrozen[t] = rec[20 * s.NV + vi];
+    nfrozen[nEV + t] = rec[21 * s.NV + vi];
     return;
   }
   const int64_t o = old * Vm1 + i;
 #pragma unroll
   for (int k = 0; k < 6; ++k) nmir[k * nEV + t] = omir[k * oEV + o];
-}
-
-// Snapshot of the current belief position mean of robots that gained edges:
-// the new factor's inbox entry for this robot's variable is its belief at
-// creation time (robot.rs:1557-1585, variable.rs:234-240).
-__global__ void k_snapshot_mu_new(Store s, int p, const int64_t *__restrict__ newcnt) {
-  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (t >= int64_t(s.Nloc) * s.V) return;
-  const int64_t r = t / s.V;
-  if (newcnt[r] == 0) return;
-  const double *rec = s.latest[r] ? s.bel_ext : s.pub[p];
-  s.mu_new[t] = rec[20 * s.NV + t];
-  s.mu_new[s.NV + t] = rec[21 * s.NV + t];
+  nfrozen[t] = ofrozen[o];
+  nfrozen[nEV + t] = ofrozen[oEV + o];
 }
 
 }  // namespace gbp

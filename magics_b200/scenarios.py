@@ -35,8 +35,8 @@ class Swarm:
     def n(self) -> int:
         return int(self.radii.shape[0])
 
-    def add_to(self, world):
-        if self.sdf is not None:
+    def add_to(self, world, set_sdf=True):
+        if set_sdf and self.sdf is not None:
             world.set_sdf(self.sdf)
         world.add_robots(self.radii, self.timesteps, self.init_means, self.positions, self.wp_offsets, self.wp_xy)
         return world

@@ -22,7 +22,8 @@ _LIB = None
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libgbp_b200.so")
+    # GBP_B200_LIB selects an alternative build of the same engine (kernel tuning experiments)
+    return os.environ.get("GBP_B200_LIB") or os.path.join(_HERE, "libgbp_b200.so")
 
 
 def load_library() -> C.CDLL:

@@ -194,6 +194,23 @@ def test_comms_failure_and_idle_masks():
     check(g, o, "comms failure")
 
 
+def test_idle_robots_and_comms_failure_with_topology_changes():
+    """mission.state.idle() robots neither iterate nor receive (robot.rs:1791,1806,1822);
+    antenna failures while robots cross (edges created while a radio is off)."""
+    sw = scenarios.circle(10, circle_radius=16.0)
+    sw.cfg.comms_radius = 11.0
+    g, o = make_pair(sw)
+    rng = np.random.default_rng(11)
+    for tick in range(40):
+        ant = (rng.uniform(size=10) > 0.25).astype(np.uint8)
+        idle = (rng.uniform(size=10) > 0.85).astype(np.uint8) if 5 <= tick < 15 else None
+        for w in (g, o):
+            w.set_comms(ant, idle)
+            w.step()
+        if tick % 5 == 4:
+            check(g, o, f"idle+comms tick {tick}")
+
+
 def test_robots_added_later_join_the_graph():
     sw = scenarios.circle(8, circle_radius=12.0)
     a, b = sw.slice(0, 5), sw.slice(5, 8)
@@ -202,7 +219,7 @@ def test_robots_added_later_join_the_graph():
         a.add_to(w)
         w.step()
         w.step()
-        b.add_to(w)
+        b.add_to(w, set_sdf=False)
         for _ in range(3):
             w.step()
     check(g, o, "late spawn")
