@@ -104,6 +104,16 @@ def measured_peak_gbs():
         return 6650.0, "fallback"
 
 
+def ncu_traffic(workload_name: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per k_iterate<EXT,INT> launch from the committed
+    `ncu --set full` capture of this workload (profiles/iterate_traffic.json), or (None, None)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "iterate_traffic.json")))[workload_name]
+        return float(t["dram_bytes_per_launch"]), t["source"]
+    except Exception:
+        return None, None
+
+
 def build_workload(name: str, robots: int):
     from magics_b200 import scenarios
 
@@ -152,25 +162,37 @@ def main():
     cores = os.cpu_count() or 1
 
     if args.impl == "reference":
+        # The reference's own CPU implementation of the path = the oracle's C++ restatement of the
+        # Rust algorithm (no Rust toolchain here), all host threads, on a bounded
+        # sample of the same workload: W warm-up ticks, then exactly K timed ticks.
         if rank != 0:
             return
+        from oracle.oracle import OracleWorld, schedule
+
         sw = build_workload(args.workload, args.cpu_robots)
-        vals = []
-        for _ in range(max(1, min(args.steps, 3))):
-            v, secs, substeps = run_cpu(sw, cores, max(1, args.warmup))
-            vals.append((v, secs))
-        v, secs = max(vals)
-        K = None
+        o = OracleWorld(sw.cfg, threads=cores)
+        sw.add_to(o)
+        oi, oe = schedule(sw.cfg.schedule_kind, sw.cfg.iterations_internal, sw.cfg.iterations_external)
+        substeps = int(np.sum(oi & oe))
+        for _ in range(max(1, args.warmup)):
+            o.step()
+        t = time.perf_counter()
+        for _ in range(args.steps):
+            o.step()
+        secs = time.perf_counter() - t
+        o.close()
+        v = sw.n * substeps * args.steps / secs
+        sample = (f"{sw.n} robots of the {args.workload} workload ({sw.name}), {args.steps} sim ticks of {substeps} "
+                  f"sub-steps after {max(1, args.warmup)} warm-up; C++ restatement of the reference algorithm "
+                  "(Rust toolchain absent), threads over robots for the internal half, serial external half")
         line = {
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{sw.name} (bounded CPU sample of {args.workload}-{args.robots})",
-                       "V": int(sw.cfg.num_variables), "schedule": "interleave-evenly 10/10"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{sw.n} robots of the {args.workload} workload, 1 sim tick, best of "
-                                       f"{max(1, args.warmup)}; C++ restatement of the reference algorithm "
-                                       "(Rust toolchain absent)"},
+            "warmup": args.warmup, "ms_per_step": secs * 1e3 / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}-{args.robots}: V={int(sw.cfg.num_variables)}, "
+                                   "dyn+obstacle+interrobot factors, interleave-evenly 10/10; CPU arm runs the "
+                                   f"bounded sample {sw.name}"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
         print(json.dumps(line))
@@ -224,9 +246,18 @@ def main():
     ms = float(t.item())
     value = n * world * substeps * args.steps / (ms * 1e-3)
 
-    # ---- end to end through the C ABI with host buffers ------------------
-    ant = np.ones(n, np.uint8)
-    wpi = np.ones(n, np.int32)
+    # ---- end to end through the C ABI with HOST buffers ---------------------
+    # every step: comms mask + waypoint indices host -> device, one sim tick, every variable's
+    # mean device -> host (what the Bevy systems / visualisers read back each tick)
+    from magics_b200 import pinned_empty
+
+    ant = pinned_empty((n,), np.uint8)
+    wpi = pinned_empty((n,), np.int32)
+    means = pinned_empty((n, cfg.num_variables, 4), np.float64)
+    ant[:] = 1
+    wpi[:] = 1
+    for _ in range(2):  # warm the read-back path (scratch allocation)
+        g.read_means_into(means)
     barrier()
     t0 = time.perf_counter()
     g.timer_start()
@@ -234,14 +265,15 @@ def main():
         g.set_comms(ant, None)
         g.set_waypoint_index(wpi)
         g.step()
-        means = g.read_beliefs(eta=False, lam=False, mean=True, cov=False, valid=False)["mean"]
+        g.read_means_into(means)
     ms_e2e = g.timer_stop_ms()
     barrier()
     wall_e2e = (time.perf_counter() - t0) * 1e3
     t = torch.tensor([max(ms_e2e, wall_e2e)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = n * world * substeps * args.steps / (float(t.item()) * 1e-3)
+    e2e_ms = float(t.item())
+    e2e_value = n * world * substeps * args.steps / (e2e_ms * 1e-3)
 
     if rank == 0:
         deg = float(np.diff(g.read_connections()[0]).mean())
@@ -253,10 +285,16 @@ def main():
         if dom["count"]:
             avg_s = dom["ms"] * 1e-3 / dom["count"]
             achieved = bytes_iter * n / avg_s / 1e9
+            traffic, traffic_src = ncu_traffic(sw.name)
             roof = {"bound": "hbm", "kernel": "k_iterate<EXT,INT>", "achieved": achieved, "peak": peak,
-                    "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "traffic_source": traffic_src,
+                    "traffic_frac": (traffic / avg_s / 1e9 / peak) if traffic else None,
                     "avg_launch_ms": avg_s * 1e3, "launches_timed": dom["count"],
-                    "algorithmic_bytes_per_robot_iteration": bytes_iter, "mean_neighbours": deg}
+                    "algorithmic_bytes_per_robot_iteration": bytes_iter, "mean_neighbours": deg,
+                    "note": "achieved counts the reference's 192-byte messages (SURVEY 8d); the engine's "
+                            "compressed store moves `traffic` bytes per launch instead, so frac can exceed 1; "
+                            "traffic_frac = real DRAM bytes / launch time / peak"}
         cpu = None
         if not args.no_cpu_baseline:
             swc = build_workload(args.workload, args.cpu_robots)
@@ -274,8 +312,10 @@ def main():
                        "robots_total": n * world, "sub_steps_per_step": substeps,
                        "l2": "inputs larger than L2 (store >> 126 MB)"},
             "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ant.nbytes + wpi.nbytes),
-                    "d2h_bytes_per_step": int(means.nbytes)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": int(ant.nbytes + wpi.nbytes), "d2h_bytes_per_step": int(means.nbytes),
+                    "what": "per step: set_comms + set_waypoint_index (pinned host -> device), gbp_world_step, "
+                            "all variable means device -> pinned host; max(CUDA events, wall clock)"},
             "roofline": roof, "cpu_baseline": cpu, "profile_ms": prof,
         }
         print(json.dumps(line))

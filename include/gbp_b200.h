@@ -25,6 +25,7 @@
 #ifndef GBP_B200_H
 #define GBP_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -213,6 +214,10 @@ enum gbp_profile_kind {
 };
 int gbp_world_set_profiling(gbp_world_t *w, int32_t on);
 int gbp_world_read_profile(gbp_world_t *w, int32_t kind, int64_t *count, double *total_ms);
+/* Page-locked host memory for the buffers passed to the upload / read-back calls
+ * (any host pointer is accepted; pinned ones make the copies DMA at PCIe speed). */
+void *gbp_host_alloc_pinned(size_t bytes);
+void gbp_host_free_pinned(void *p);
 /* device time helpers for bench.py: record/elapsed on the engine's own stream. */
 int gbp_world_sync(gbp_world_t *w);
 int gbp_world_timer_start(gbp_world_t *w);

@@ -19,4 +19,5 @@ from .config import (  # noqa: F401
     SCHEDULE_SOON_AS_POSSIBLE,
     GbpConfig,
 )
-from .world import World, gbp_schedule, get_variable_timesteps, library_path, load_library  # noqa: F401
+from .world import (World, gbp_schedule, get_variable_timesteps, library_path, load_library,  # noqa: F401
+                    pinned_empty)

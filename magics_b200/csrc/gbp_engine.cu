@@ -372,6 +372,9 @@ struct gbp_world {
   void *t_cub = nullptr;
   size_t t_cub_bytes = 0;
   int64_t t_cap = 0;
+  // grow-only device scratch for read-backs / small uploads (no cudaMalloc per call)
+  void *rb_dev = nullptr;
+  size_t rb_bytes = 0;
   // optional per-launch CUDA-event timing (bench.py roofline leg)
   struct Span {
     int kind;
@@ -506,6 +509,18 @@ int run_schedule(gbp_world *w, int n, const uint8_t *internal, const uint8_t *ex
 }
 
 using EdgeSet = gbp_world::EdgeSet;
+
+int ensure_scratch(gbp_world *w, size_t bytes) {
+  if (bytes <= w->rb_bytes) return 0;
+  CK(cudaStreamSynchronize(w->stream));
+  cudaFree(w->rb_dev);
+  w->rb_dev = nullptr;
+  w->rb_bytes = 0;
+  bytes += bytes / 8 + 4096;
+  CK(cudaMalloc(&w->rb_dev, bytes));
+  w->rb_bytes = bytes;
+  return 0;
+}
 
 void bind_edge_set(gbp_world *w) {
   const EdgeSet &e = w->edges[w->cur];
@@ -645,7 +660,7 @@ void gbp_world_destroy(gbp_world_t *w) {
                   w->edges[1].mir, w->edges[1].map, w->edges[1].mu_frozen,
                   w->t_nlow, w->t_result_dev, w->sdf_dev, w->t_cx,
                   w->t_cz, w->t_idx, w->t_idx_sorted, w->t_keys, w->t_keys_sorted, w->t_cnt, w->t_off,
-                  w->t_newcnt, w->t_newoff, w->t_cub};
+                  w->t_newcnt, w->t_newoff, w->t_cub, w->rb_dev};
   for (void *q : ptrs) cudaFree(q);
   for (auto &sp : w->spans) {
     cudaEventDestroy(sp.a);
@@ -1017,23 +1032,26 @@ int gbp_world_read_beliefs(gbp_world_t *w, double *eta, double *lam, double *mea
   if (set_device(w)) return GBP_ERR_CUDA;
   const int64_t nv = int64_t(w->s.Nloc) * w->s.V;
   if (nv == 0) return 0;
-  double *d_eta = nullptr, *d_lam = nullptr, *d_mean = nullptr, *d_cov = nullptr;
-  uint8_t *d_valid = nullptr;
-  if (eta) CK(dalloc(d_eta, size_t(4) * nv));
-  if (lam) CK(dalloc(d_lam, size_t(16) * nv));
-  if (mean) CK(dalloc(d_mean, size_t(4) * nv));
-  if (cov) CK(dalloc(d_cov, size_t(16) * nv));
-  if (valid) CK(dalloc(d_valid, size_t(nv)));
+  // one grow-only device scratch, carved into the requested AoS arrays
+  const size_t b_eta = eta ? size_t(4) * nv * 8 : 0, b_lam = lam ? size_t(16) * nv * 8 : 0,
+               b_mean = mean ? size_t(4) * nv * 8 : 0, b_cov = cov ? size_t(16) * nv * 8 : 0,
+               b_valid = valid ? size_t(nv) : 0;
+  if (int rc = ensure_scratch(w, b_eta + b_lam + b_mean + b_cov + b_valid)) return rc;
+  char *base = static_cast<char *>(w->rb_dev);
+  double *d_eta = eta ? reinterpret_cast<double *>(base) : nullptr;
+  double *d_lam = lam ? reinterpret_cast<double *>(base + b_eta) : nullptr;
+  double *d_mean = mean ? reinterpret_cast<double *>(base + b_eta + b_lam) : nullptr;
+  double *d_cov = cov ? reinterpret_cast<double *>(base + b_eta + b_lam + b_mean) : nullptr;
+  uint8_t *d_valid = valid ? reinterpret_cast<uint8_t *>(base + b_eta + b_lam + b_mean + b_cov) : nullptr;
   k_gather_beliefs<<<blocks_for(nv, 256), 256, 0, w->stream>>>(w->s, w->p, d_eta, d_lam, d_mean, d_cov, d_valid);
   CK(cudaGetLastError());
   w->launches += 1;
-  if (eta) CK(cudaMemcpyAsync(eta, d_eta, size_t(4) * nv * 8, cudaMemcpyDeviceToHost, w->stream));
-  if (lam) CK(cudaMemcpyAsync(lam, d_lam, size_t(16) * nv * 8, cudaMemcpyDeviceToHost, w->stream));
-  if (mean) CK(cudaMemcpyAsync(mean, d_mean, size_t(4) * nv * 8, cudaMemcpyDeviceToHost, w->stream));
-  if (cov) CK(cudaMemcpyAsync(cov, d_cov, size_t(16) * nv * 8, cudaMemcpyDeviceToHost, w->stream));
-  if (valid) CK(cudaMemcpyAsync(valid, d_valid, size_t(nv), cudaMemcpyDeviceToHost, w->stream));
+  if (eta) CK(cudaMemcpyAsync(eta, d_eta, b_eta, cudaMemcpyDeviceToHost, w->stream));
+  if (lam) CK(cudaMemcpyAsync(lam, d_lam, b_lam, cudaMemcpyDeviceToHost, w->stream));
+  if (mean) CK(cudaMemcpyAsync(mean, d_mean, b_mean, cudaMemcpyDeviceToHost, w->stream));
+  if (cov) CK(cudaMemcpyAsync(cov, d_cov, b_cov, cudaMemcpyDeviceToHost, w->stream));
+  if (valid) CK(cudaMemcpyAsync(valid, d_valid, b_valid, cudaMemcpyDeviceToHost, w->stream));
   CK(cudaStreamSynchronize(w->stream));
-  cudaFree(d_eta); cudaFree(d_lam); cudaFree(d_mean); cudaFree(d_cov); cudaFree(d_valid);
   return 0;
 }
 
@@ -1143,6 +1161,18 @@ int gbp_world_read_profile(gbp_world_t *w, int32_t kind, int64_t *count, double 
   *count = w->prof_count[kind];
   *total_ms = w->prof_ms[kind];
   return 0;
+}
+
+void *gbp_host_alloc_pinned(size_t bytes) {
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    fail(GBP_ERR_CUDA, "gbp_host_alloc_pinned: cudaMallocHost failed");
+    return nullptr;
+  }
+  return p;
+}
+void gbp_host_free_pinned(void *p) {
+  if (p) cudaFreeHost(p);
 }
 
 int gbp_world_sync(gbp_world_t *w) {

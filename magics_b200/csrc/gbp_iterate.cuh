@@ -57,58 +57,64 @@ GBP_DEV double sdf_measure(const Store &s, double x_pos, double y_pos, uint32_t 
 // robot.rs:1228-1334), added onto (ae, al) (variable.rs:263-271).
 GBP_DEV void add_internal(const Store &s, int64_t vi, int i, double (&ae)[4], double (&al)[16]) {
   const int64_t NV = s.NV;
-  const int V = s.V;
-  if (i >= 1) {
-    const double f = s.m_dynL[vi];
-    if (!is_empty_marker(f)) {
-      ae[0] = ae[0] + f;
+  // Every record is loaded whole before its Empty marker is looked at: the slots of
+  // factors a variable does not have (dyn(i-1) of variable 0, ...) hold the marker for
+  // ever, so no index test is needed and no load waits on another load.
+  {
+    double m[20];
 #pragma unroll
-      for (int k = 1; k < 4; ++k) ae[k] = ae[k] + s.m_dynL[k * NV + vi];
+    for (int k = 0; k < 20; ++k) m[k] = s.m_dynL[k * NV + vi];
+    if (!is_empty_marker(m[0])) {
 #pragma unroll
-      for (int k = 0; k < 16; ++k) al[k] = al[k] + s.m_dynL[(4 + k) * NV + vi];
+      for (int k = 0; k < 4; ++k) ae[k] = ae[k] + m[k];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) al[k] = al[k] + m[4 + k];
     }
   }
-  if (i <= V - 2) {
-    const double f = s.m_dynR[vi];
-    if (!is_empty_marker(f)) {
-      ae[0] = ae[0] + f;
+  {
+    double m[20];
 #pragma unroll
-      for (int k = 1; k < 4; ++k) ae[k] = ae[k] + s.m_dynR[k * NV + vi];
+    for (int k = 0; k < 20; ++k) m[k] = s.m_dynR[k * NV + vi];
+    if (!is_empty_marker(m[0])) {
 #pragma unroll
-      for (int k = 0; k < 16; ++k) al[k] = al[k] + s.m_dynR[(4 + k) * NV + vi];
+      for (int k = 0; k < 4; ++k) ae[k] = ae[k] + m[k];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) al[k] = al[k] + m[4 + k];
     }
   }
-  if (i >= 1 && i <= V - 2) {
-    const double j0 = s.m_obs[vi];
-    if (!is_empty_marker(j0)) {
-      const double j2 = s.m_obs[2 * NV + vi];
-      const double J[4] = {j0, s.m_obs[NV + vi], j2, j2};
-      unary_add(J, s.m_obs[3 * NV + vi], s.lm_obs, ae, al);
+  {
+    double o[4], t[3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = s.m_obs[k * NV + vi];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) t[k] = s.m_trk[k * NV + vi];
+    if (!is_empty_marker(o[0])) {
+      const double J[4] = {o[0], o[1], o[2], o[2]};
+      unary_add(J, o[3], s.lm_obs, ae, al);
     }
-    const double t0 = s.m_trk[vi];
-    if (!is_empty_marker(t0)) {
-      const double J[2] = {t0, s.m_trk[NV + vi]};
-      const double v0 = s.m_trk[2 * NV + vi];
+    if (!is_empty_marker(t[0])) {
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        const double g = J[k] * s.lm_trk;
-        ae[k] = ae[k] + g * v0;
+        const double g = t[k] * s.lm_trk;
+        ae[k] = ae[k] + g * t[2];
 #pragma unroll
-        for (int l = 0; l < 2; ++l) al[k * 4 + l] = al[k * 4 + l] + g * J[l];
+        for (int l = 0; l < 2; ++l) al[k * 4 + l] = al[k * 4 + l] + g * t[l];
       }
     }
   }
 }
 
 GBP_DEV void add_mirror(const Store &s, int64_t m, double (&ae)[4], double (&al)[16]) {
-  const double f = s.mir[m];
-  if (is_empty_marker(f)) return;
-  ae[0] = ae[0] + f;
-  ae[1] = ae[1] + s.mir[s.EV + m];
-  al[0] = al[0] + s.mir[2 * s.EV + m];
-  al[1] = al[1] + s.mir[3 * s.EV + m];
-  al[4] = al[4] + s.mir[4 * s.EV + m];
-  al[5] = al[5] + s.mir[5 * s.EV + m];
+  double v[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) v[k] = s.mir[k * s.EV + m];
+  if (is_empty_marker(v[0])) return;
+  ae[0] = ae[0] + v[0];
+  ae[1] = ae[1] + v[1];
+  al[0] = al[0] + v[2];
+  al[1] = al[1] + v[3];
+  al[4] = al[4] + v[4];
+  al[5] = al[5] + v[5];
 }
 
 GBP_DEV void load_prior(const Store &s, int64_t vi, double (&ae)[4], double (&al)[16]) {
@@ -236,6 +242,29 @@ GBP_DEV void obstacle_update(const Store &s, int64_t vi, const double (&x)[4]) {
   s.m_obs[3 * NV + vi] = v0;
 }
 
+// Inputs of one InterRobot edge (receiver r <- neighbour A) for variable i, loaded as one batch
+// with a single dependent level (A = enbr[e] -> everything else), before any arithmetic.
+struct EdgeIn {
+  double rec[22];  // A's published record: eta4, Lambda16, position mean
+  double dsafe;
+  uint64_t rnum;
+  uint32_t epochA, birth;
+  bool act, frozen;
+};
+GBP_DEV void load_edge(const Store &s, const double *__restrict__ pubr, int p, int64_t e, int A, int V, int i,
+                       EdgeIn &x) {
+  const int64_t NV = s.NV;
+  const int64_t va = int64_t(A) * V + i;
+#pragma unroll
+  for (int k = 0; k < 22; ++k) x.rec[k] = pubr[k * NV + va];
+  x.epochA = s.pub_epoch[p][va];
+  x.act = s.en_ir && s.antenna[A] != 0 && s.idle[A] == 0;
+  x.birth = s.e_birth[e];
+  x.frozen = s.e_frozen[e] != 0;
+  x.rnum = s.e_rnum[e];
+  x.dsafe = s.e_dsafe[e];
+}
+
 template <bool EXT, bool INT>
 __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
     k_iterate(const __grid_constant__ Store s, const int p, const uint32_t epoch) {
@@ -283,33 +312,32 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
       mu_sent[1] = s.mu_ext[NV + vi];
     }
     bool added = false;
-    for (int64_t e = e0; e < e1; ++e) {
-      const int A = s.enbr[e];
+    // Everything an edge needs is loaded up front, unconditionally (one dependent level:
+    // enbr[e] -> the rest), and the loads of edge e+1 are issued before the arithmetic of
+    // edge e so their latency hides behind it.
+    auto process = [&](int64_t e, const EdgeIn &x) {
       if (!added && e >= elow) {
         add_internal(s, vi, i, ae, al);
         added = true;
       }
       const int64_t m = e * (V - 1) + (i - 1);
-      const bool a_act = s.en_ir && s.antenna[A] != 0 && s.idle[A] == 0;
-      if (a_act) {
-        const int64_t va = int64_t(A) * V + i;
-        const bool a_ne = s.pub_epoch[p][va] > s.e_birth[e];
+      if (x.act) {
+        const bool a_ne = x.epochA > x.birth;
         double etaA[4], lamA[16], muA[2];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) etaA[k] = a_ne ? pubr[k * NV + va] : 0.0;
+        for (int k = 0; k < 4; ++k) etaA[k] = a_ne ? x.rec[k] : 0.0;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) lamA[k] = a_ne ? pubr[(4 + k) * NV + va] : 0.0;
-        muA[0] = a_ne ? pubr[20 * NV + va] : 0.0;
-        muA[1] = a_ne ? pubr[21 * NV + va] : 0.0;
+        for (int k = 0; k < 16; ++k) lamA[k] = a_ne ? x.rec[4 + k] : 0.0;
+        muA[0] = a_ne ? x.rec[20] : 0.0;
+        muA[1] = a_ne ? x.rec[21] : 0.0;
         double mb[2] = {mu_sent[0], mu_sent[1]};
-        if (s.e_frozen[e]) {
+        if (x.frozen) {  // rare: edge just created, or A's radio was off at the last delivery
           mb[0] = s.mu_frozen[m];
           mb[1] = s.mu_frozen[s.EV + m];
         }
-        const double tiny = s.tiny_scale * double(s.e_rnum[e] + uint64_t(i - 1));
+        const double tiny = s.tiny_scale * double(x.rnum + uint64_t(i - 1));
         double me[2], ml[4];
-        const bool ok = interrobot_message(e < elow, muA, mb, a_ne, etaA, lamA, s.e_dsafe[e], tiny,
-                                           s.lm_ir, me, ml);
+        const bool ok = interrobot_message(e < elow, muA, mb, a_ne, etaA, lamA, x.dsafe, tiny, s.lm_ir, me, ml);
         if (ok) {
           s.mir[m] = me[0];
           s.mir[s.EV + m] = me[1];
@@ -330,11 +358,18 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
         add_mirror(s, m, ae, al);  // undelivered: the variable keeps the old message
         // ... and A's factor keeps the mean it already holds from this variable
         // while this variable's belief moves on (robot.rs:1851): freeze it
-        if (!s.e_frozen[e]) {
+        if (!x.frozen) {
           s.mu_frozen[m] = mu_sent[0];
           s.mu_frozen[s.EV + m] = mu_sent[1];
         }
       }
+    };
+    int A_next = (e0 < e1) ? s.enbr[e0] : 0;
+    for (int64_t e = e0; e < e1; ++e) {
+      EdgeIn x;
+      load_edge(s, pubr, p, e, A_next, V, i, x);
+      if (e + 1 < e1) A_next = s.enbr[e + 1];
+      process(e, x);
     }
     if (!added) add_internal(s, vi, i, ae, al);
     double cov[16];
@@ -380,23 +415,15 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
       double R[20];
 #pragma unroll
       for (int k = 0; k < 20; ++k) R[k] = pubr[k * NV + vi];
-      const double fr = (i <= V - 2) ? s.m_dynR[vi] : empty_marker();
-      if (!is_empty_marker(fr)) {
-        toR[0] = R[0] - fr;
 #pragma unroll
-        for (int k = 1; k < 20; ++k) toR[k] = R[k] - s.m_dynR[k * NV + vi];
-      } else {
+      for (int k = 0; k < 20; ++k) toR[k] = s.m_dynR[k * NV + vi];
 #pragma unroll
-        for (int k = 0; k < 20; ++k) toR[k] = R[k];
-      }
-      const double fl = (i >= 1) ? s.m_dynL[vi] : empty_marker();
-      if (!is_empty_marker(fl)) {
-        toL[0] = R[0] - fl;
+      for (int k = 0; k < 20; ++k) toL[k] = s.m_dynL[k * NV + vi];
+      const bool hasR = !is_empty_marker(toR[0]), hasL = !is_empty_marker(toL[0]);
 #pragma unroll
-        for (int k = 1; k < 20; ++k) toL[k] = R[k] - s.m_dynL[k * NV + vi];
-      } else {
-#pragma unroll
-        for (int k = 0; k < 20; ++k) toL[k] = R[k];
+      for (int k = 0; k < 20; ++k) {
+        toR[k] = hasR ? R[k] - toR[k] : R[k];
+        toL[k] = hasL ? R[k] - toL[k] : R[k];
       }
     } else {
 #pragma unroll

@@ -38,43 +38,96 @@ GBP_DEV double minor3(const double (&m)[16]) {
 }
 
 // `Inverse::inv` for 4x4: adjugate / det, None iff det == 0.
+//
+// The 16 quotients x / det share their divisor.  An IEEE division costs ~15 instructions;
+// divide_all computes the correctly rounded reciprocal y = RN(1/det) once and each quotient as
+//   q0 = RN(x*y);  r = RN(x - q*det) (exact, one FMA);  q = RN(q + r*y)      (twice)
+// which is the correctly rounded x/det whenever q0 is within 1 ulp of it and nothing
+// over/underflows (Markstein's theorem; the second pass makes the 1-ulp premise certain).
+// Operands outside [2^-500, 2^500] (denormals, inf, NaN) take the plain division, so the
+// result is bit-identical to `x / det` for every input.
+GBP_DEV bool exp_in_safe_range(double v) {
+  const unsigned e = (unsigned(__double2hiint(v)) >> 20) & 0x7ffu;
+  return e - 523u < 1001u;  // 2^-500 <= |v| < 2^501
+}
+// out-of-line: the rare operands share one copy of the IEEE division sequence
+__device__ __noinline__ double plain_div(double x, double det) { return x / det; }
+
+// o[k] = c[k] / det for N numerators, bit-identical to the N divisions.
+template <int N>
+GBP_DEV void divide_all(const double (&c)[N], double det, double (&o)[N]) {
+#ifdef GBP_LITERAL_DIV
+#pragma unroll
+  for (int k = 0; k < N; ++k) o[k] = c[k] / det;
+#else
+  bool ok = exp_in_safe_range(det);
+#pragma unroll
+  for (int k = 0; k < N; ++k) ok = ok && (c[k] == 0.0 || exp_in_safe_range(c[k]));
+  if (ok) {
+    const double y = 1.0 / det;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const double q0 = c[k] * y;
+      double r = fma(-q0, det, c[k]);
+      double q = fma(r, y, q0);
+#ifndef GBP_DIV_ONE_STEP
+      r = fma(-q, det, c[k]);
+      q = fma(r, y, q);
+#endif
+      // a zero numerator keeps its IEEE sign through the first product alone
+      o[k] = (c[k] == 0.0) ? q0 : q;
+    }
+  } else {
+#pragma unroll 1
+    for (int k = 0; k < N; ++k) o[k] = plain_div(c[k], det);
+  }
+#endif
+}
+
 GBP_DEV bool inv4(const double (&m)[16], double (&o)[16]) {
-  const double m00 = minor3<0, 0>(m), m01 = minor3<0, 1>(m), m02 = minor3<0, 2>(m),
-               m03 = minor3<0, 3>(m);
-  const double det = m[0] * m00 - m[1] * m01 + m[2] * m02 - m[3] * m03;
+  double c[16];
+  c[0] = minor3<0, 0>(m);
+  c[4] = -minor3<0, 1>(m);
+  c[8] = minor3<0, 2>(m);
+  c[12] = -minor3<0, 3>(m);
+  // Laplace expansion along row 0 (c[4], c[12] carry the cofactor signs; -(a*b) == a*(-b) exactly)
+  const double det = m[0] * c[0] - m[1] * (-c[4]) + m[2] * c[8] - m[3] * (-c[12]);
   if (det == 0.0) return false;
-  o[0] = m00 / det;
-  o[4] = -m01 / det;
-  o[8] = m02 / det;
-  o[12] = -m03 / det;
-  o[1] = -minor3<1, 0>(m) / det;
-  o[5] = minor3<1, 1>(m) / det;
-  o[9] = -minor3<1, 2>(m) / det;
-  o[13] = minor3<1, 3>(m) / det;
-  o[2] = minor3<2, 0>(m) / det;
-  o[6] = -minor3<2, 1>(m) / det;
-  o[10] = minor3<2, 2>(m) / det;
-  o[14] = -minor3<2, 3>(m) / det;
-  o[3] = -minor3<3, 0>(m) / det;
-  o[7] = minor3<3, 1>(m) / det;
-  o[11] = -minor3<3, 2>(m) / det;
-  o[15] = minor3<3, 3>(m) / det;
+  c[1] = -minor3<1, 0>(m);
+  c[5] = minor3<1, 1>(m);
+  c[9] = -minor3<1, 2>(m);
+  c[13] = minor3<1, 3>(m);
+  c[2] = minor3<2, 0>(m);
+  c[6] = -minor3<2, 1>(m);
+  c[10] = minor3<2, 2>(m);
+  c[14] = -minor3<2, 3>(m);
+  c[3] = -minor3<3, 0>(m);
+  c[7] = minor3<3, 1>(m);
+  c[11] = -minor3<3, 2>(m);
+  c[15] = minor3<3, 3>(m);
+  divide_all(c, det, o);
   return true;
 }
 // Rows 0 and 1 of the inverse only (all an InterRobot Schur complement reads).
 GBP_DEV bool inv4_rows01(const double (&m)[16], double (&r0)[4], double (&r1)[4]) {
-  const double m00 = minor3<0, 0>(m), m01 = minor3<0, 1>(m), m02 = minor3<0, 2>(m),
-               m03 = minor3<0, 3>(m);
-  const double det = m[0] * m00 - m[1] * m01 + m[2] * m02 - m[3] * m03;
+  double c[8], o[8];
+  c[0] = minor3<0, 0>(m);
+  c[4] = -minor3<0, 1>(m);
+  const double m02 = minor3<0, 2>(m), m03 = minor3<0, 3>(m);
+  const double det = m[0] * c[0] - m[1] * (-c[4]) + m[2] * m02 - m[3] * m03;
   if (det == 0.0) return false;
-  r0[0] = m00 / det;
-  r1[0] = -m01 / det;
-  r0[1] = -minor3<1, 0>(m) / det;
-  r1[1] = minor3<1, 1>(m) / det;
-  r0[2] = minor3<2, 0>(m) / det;
-  r1[2] = -minor3<2, 1>(m) / det;
-  r0[3] = -minor3<3, 0>(m) / det;
-  r1[3] = minor3<3, 1>(m) / det;
+  c[1] = -minor3<1, 0>(m);
+  c[5] = minor3<1, 1>(m);
+  c[2] = minor3<2, 0>(m);
+  c[6] = -minor3<2, 1>(m);
+  c[3] = -minor3<3, 0>(m);
+  c[7] = minor3<3, 1>(m);
+  divide_all(c, det, o);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    r0[k] = o[k];
+    r1[k] = o[4 + k];
+  }
   return true;
 }
 

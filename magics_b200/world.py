@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -46,6 +47,9 @@ def load_library() -> C.CDLL:
     lib.gbp_world_kernel_launches.restype = C.c_int64
     lib.gbp_world_kernel_launches.argtypes = [C.c_void_p]
     lib.gbp_world_num_robots.argtypes = [C.c_void_p]
+    lib.gbp_host_alloc_pinned.restype = C.c_void_p
+    lib.gbp_host_alloc_pinned.argtypes = [C.c_size_t]
+    lib.gbp_host_free_pinned.argtypes = [C.c_void_p]
     _LIB = lib
     return lib
 
@@ -73,6 +77,22 @@ def get_variable_timesteps(lookahead_horizon: int, lookahead_multiple: int) -> n
     if n < 0:
         raise ValueError(lib.gbp_last_error().decode())
     return out[:n].copy()
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array backed by page-locked host memory (gbp_host_alloc_pinned): host buffers handed to
+    the upload / read-back calls DMA at PCIe speed instead of being staged by the driver.
+    The block is released when the last view of the array is garbage collected."""
+    lib = load_library()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    nbytes = max(1, n * dtype.itemsize)
+    ptr = lib.gbp_host_alloc_pinned(C.c_size_t(nbytes))
+    if not ptr:
+        raise MemoryError("gbp_host_alloc_pinned failed: " + lib.gbp_last_error().decode())
+    buf = (C.c_uint8 * nbytes).from_address(ptr)
+    weakref.finalize(buf, lib.gbp_host_free_pinned, C.c_void_p(ptr))
+    return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
 
 
 class World:
@@ -190,6 +210,13 @@ class World:
         self._call("gbp_world_set_schedule", C.c_int32(kind), C.c_int32(internal), C.c_int32(external))
 
     # ---- read-back -------------------------------------------------------
+    def read_means_into(self, out: np.ndarray):
+        """Variable means of every robot into a caller-owned (n, V, 4) f64 buffer (ideally pinned)."""
+        if out.dtype != np.float64 or not out.flags.c_contiguous or out.size != self.num_robots * self.V * 4:
+            raise ValueError("read_means_into: need a C-contiguous f64 buffer of n*V*4 elements")
+        self._call("gbp_world_read_beliefs", None, None, _p(out, C.c_double), None, None)
+        return out
+
     def read_beliefs(self, eta=True, lam=True, mean=True, cov=True, valid=True):
         n, V = self.num_robots, self.V
         out = {}

@@ -26,7 +26,7 @@
 // `unrolled_dot` (ndarray numeric_util.rs: eight partial sums combined
 // (p0+p4)+(p1+p5)+(p2+p6)+(p3+p7), then the tail sequentially).
 //
-// Build: g++ -O2 -std=c++17 -ffp-contract=off -pthread -shared -fPIC (see Makefile).
+// Build: g++ -O3 -std=c++17 -ffp-contract=off -pthread -shared -fPIC (see Makefile).
 
 #include <algorithm>
 #include <cmath>
