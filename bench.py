@@ -114,14 +114,22 @@ def ncu_traffic(workload_name: str):
         return None, None
 
 
-def build_workload(name: str, robots: int):
+def build_workload(name: str, robots: int, rank: int = 0, world: int = 1):
+    """The robots rank `rank` of `world` owns (a contiguous id range of the global swarm), and the
+    global robot count.  lattice: horizontal slabs of rows (BASELINE config 5); rings: arcs of
+    consecutive robots (config 4)."""
     from magics_b200 import scenarios
+    from magics_b200.sharded import partition
 
     if name == "rings":
-        return scenarios.rings(robots)
+        sw = scenarios.rings(robots)
+        b = partition(sw.n, world)
+        return (sw if world == 1 else sw.slice(int(b[rank]), int(b[rank + 1]))), sw.n
     if name == "lattice":
         side = int(round(robots ** 0.5))
-        return scenarios.lattice(side, max(1, robots // side))
+        ny = max(1, robots // side)
+        b = partition(ny, world)
+        return scenarios.lattice(side, ny, rows=(int(b[rank]), int(b[rank + 1]))), side * ny
     raise ValueError(name)
 
 
@@ -149,12 +157,18 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="rings", choices=["rings", "lattice"])
-    ap.add_argument("--robots", type=int, default=100_000, help="robots per GPU (weak scaling)")
+    ap.add_argument("--workload", default="lattice", choices=["rings", "lattice"])
+    ap.add_argument("--robots", type=int, default=None,
+                    help="robots of the whole swarm (default: lattice 1 000 000, rings 100 000)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: --robots is the whole swarm at every N (BASELINE config 5: 1M robots over "
+                         "1/2/4/8 GPUs); weak: --robots per GPU")
     ap.add_argument("--cpu-robots", type=int, default=3000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    if args.robots is None:
+        args.robots = 1_000_000 if args.workload == "lattice" else 100_000
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -169,7 +183,7 @@ def main():
             return
         from oracle.oracle import OracleWorld, schedule
 
-        sw = build_workload(args.workload, args.cpu_robots)
+        sw, _ = build_workload(args.workload, args.cpu_robots)
         o = OracleWorld(sw.cfg, threads=cores)
         sw.add_to(o)
         oi, oe = schedule(sw.cfg.schedule_kind, sw.cfg.iterations_internal, sw.cfg.iterations_external)
@@ -207,11 +221,22 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    sw = build_workload(args.workload, args.robots)
+    from magics_b200 import gbp_schedule, pinned_empty
+    from magics_b200.dist import broadcast_comm_id, max_over_ranks, sum_over_ranks
+
+    # One swarm, spatially partitioned: rank q owns a contiguous id range (a slab of lattice rows /
+    # an arc of rings) and exchanges the published records of its border robots with its
+    # neighbours by NCCL send/recv before every external half-step.
+    total_robots = args.robots * (world if args.scaling == "weak" else 1)
+    sw, n_total = build_workload(args.workload, total_robots, rank, world)
     cfg = sw.cfg
-    g = World(cfg, device=local_rank)
+    if world > 1:
+        g = World.create_shard(cfg, local_rank, rank, world, broadcast_comm_id(rank))
+    else:
+        g = World(cfg, device=local_rank)
     sw.add_to(g)
-    from magics_b200 import gbp_schedule
+    g.commit_shards()
+    assert g.num_robots_global == n_total
 
     oi, oe = gbp_schedule(cfg.schedule_kind, cfg.iterations_internal, cfg.iterations_external)
     substeps = int(np.sum(oi & oe))
@@ -238,19 +263,15 @@ def main():
     barrier()
     clocks = sampler.stop()
     launches = g.kernel_launches - launches0
+    launches = sum_over_ranks(launches) if world > 1 else launches
     prof = g.read_profile()
     g.set_profiling(False)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = n * world * substeps * args.steps / (ms * 1e-3)
+    ms = max_over_ranks(ms) if world > 1 else ms
+    value = n_total * substeps * args.steps / (ms * 1e-3)
 
     # ---- end to end through the C ABI with HOST buffers ---------------------
     # every step: comms mask + waypoint indices host -> device, one sim tick, every variable's
     # mean device -> host (what the Bevy systems / visualisers read back each tick)
-    from magics_b200 import pinned_empty
-
     ant = pinned_empty((n,), np.uint8)
     wpi = pinned_empty((n,), np.int32)
     means = pinned_empty((n, cfg.num_variables, 4), np.float64)
@@ -269,14 +290,17 @@ def main():
     ms_e2e = g.timer_stop_ms()
     barrier()
     wall_e2e = (time.perf_counter() - t0) * 1e3
-    t = torch.tensor([max(ms_e2e, wall_e2e)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-    e2e_value = n * world * substeps * args.steps / (e2e_ms * 1e-3)
+    e2e_ms = max(ms_e2e, wall_e2e)
+    e2e_ms = max_over_ranks(e2e_ms) if world > 1 else e2e_ms
+    e2e_value = n_total * substeps * args.steps / (e2e_ms * 1e-3)
+    edges_local = float(g.read_connections()[0][-1])
+    edges_total = sum_over_ranks(edges_local) if world > 1 else edges_local
+    ghosts_total = sum_over_ranks(g.num_ghosts) if world > 1 else 0.0
+    h2d_total = sum_over_ranks(ant.nbytes + wpi.nbytes) if world > 1 else float(ant.nbytes + wpi.nbytes)
+    d2h_total = sum_over_ranks(means.nbytes) if world > 1 else float(means.nbytes)
 
     if rank == 0:
-        deg = float(np.diff(g.read_connections()[0]).mean())
+        deg = float(np.diff(g.read_connections()[0]).mean()) if n else 0.0
         peak, peak_kind = measured_peak_gbs()
         bytes_iter = algorithmic_bytes_per_robot_iteration(cfg.num_variables, deg, int(cfg.enable_obstacle),
                                                            int(cfg.enable_tracking))
@@ -297,7 +321,7 @@ def main():
                             "traffic_frac = real DRAM bytes / launch time / peak"}
         cpu = None
         if not args.no_cpu_baseline:
-            swc = build_workload(args.workload, args.cpu_robots)
+            swc, _ = build_workload(args.workload, args.cpu_robots)
             v, secs, _ = run_cpu(swc, cores, 2)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{swc.n} robots of the {args.workload} workload, 1 sim tick ({substeps} sub-steps), "
@@ -305,17 +329,22 @@ def main():
                              "algorithm (Rust toolchain absent)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{sw.name}: {n} robots/GPU x V={cfg.num_variables}, mean K={deg:.2f}, "
-                                   "dyn+obstacle+interrobot factors, interleave-evenly 10/10",
-                       "robots_total": n * world, "sub_steps_per_step": substeps,
+            "config": {"workload": f"{sw.name}: {n_total} robots x V={cfg.num_variables}, mean K="
+                                   f"{edges_total / max(1, n_total):.2f}, dyn+obstacle+interrobot factors, "
+                                   "interleave-evenly 10/10",
+                       "robots_total": n_total, "robots_rank0": n, "sub_steps_per_step": substeps,
+                       "partition": (f"{world} shards of contiguous robot ids (lattice: slabs of rows), "
+                                     f"{int(ghosts_total)} ghost robots in total, NCCL send/recv halo before every "
+                                     "external half-step") if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (store >> 126 MB)"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": int(ant.nbytes + wpi.nbytes), "d2h_bytes_per_step": int(means.nbytes),
+                    "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": int(d2h_total),
                     "what": "per step: set_comms + set_waypoint_index (pinned host -> device), gbp_world_step, "
-                            "all variable means device -> pinned host; max(CUDA events, wall clock)"},
+                            "all variable means device -> pinned host; max(CUDA events, wall clock), max over ranks"},
             "roofline": roof, "cpu_baseline": cpu, "profile_ms": prof,
         }
         print(json.dumps(line))

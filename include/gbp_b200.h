@@ -123,6 +123,44 @@ int gbp_world_add_robots(gbp_world_t *w, int32_t n, const float *radii,
 
 int32_t gbp_world_num_robots(const gbp_world_t *w);
 
+/* ---- multi-GPU: one swarm spatially partitioned over several B200s -------------
+ * The reference iterates all robots in one process (Bevy `Query<&mut FactorGraph>`,
+ * robot.rs:1769-1861); cross-robot traffic is the two delivery loops of
+ * iterate_gbp_v2 (robot.rs:1814-1831, :1843-1858) and the horizon change_prior
+ * messages (robot.rs:2272-2282).  Here each GPU ("shard") owns a contiguous range of
+ * robot ids in rank order and keeps ghost copies of the robots of other shards
+ * that are within comms range of its own.  The per-sub-step halo (published belief
+ * records of border robots) moves by NCCL send/recv over NVLink; it is the only
+ * communication on the iteration path.  Connectivity, inbox order and robot_number
+ * stay globally bit-exact.
+ *
+ * One process per GPU:
+ *   rank 0: gbp_comm_unique_id(id); broadcast id to every rank by any means;
+ *   every rank: w = gbp_world_create_shard(cfg, device, rank, world_size, id);
+ *               gbp_world_add_robots(w, <the robots this rank owns>) ...;
+ *               gbp_world_commit_shards(w);
+ *   then the per-tick calls below, made by every rank in the same order
+ *   (update_topology / update_prior_* / iterate* / *_iteration / step are collective;
+ *   set_comms and change_prior_of_variable act on the own robots but must be
+ *   called by every rank in the same tick, with m = 0 if a rank has nothing to change).
+ * Robot indices in per-robot arrays are LOCAL (0..num_robots-1); neighbour ids returned
+ * by gbp_world_read_connections are GLOBAL (local index + gbp_world_first_global_id). */
+#define GBP_COMM_ID_BYTES 128
+int gbp_comm_unique_id(uint8_t *id /* [GBP_COMM_ID_BYTES] */);
+gbp_world_t *gbp_world_create_shard(const gbp_config_t *cfg, int32_t device, int32_t rank,
+                                    int32_t world_size, const uint8_t *id);
+/* The same sharding code path with every shard in THIS process on ONE device (transfers are
+ * device-to-device copies on a shared stream): out[world_size].  Collective calls made
+ * on any member run for the whole group; destroy every member. */
+int gbp_world_create_local_shards(const gbp_config_t *cfg, int32_t device, int32_t world_size,
+                                  gbp_world_t **out);
+/* Collective; after the last gbp_world_add_robots: fixes the global ids (shard q owns
+ * [first_global_id, first_global_id + num_robots) in rank order). */
+int gbp_world_commit_shards(gbp_world_t *w);
+int64_t gbp_world_first_global_id(const gbp_world_t *w);
+int64_t gbp_world_num_robots_global(const gbp_world_t *w);
+int32_t gbp_world_num_ghosts(const gbp_world_t *w);
+
 /* ---- per-tick systems (RobotPlugin FixedUpdate chain, robot.rs:85-108) -- */
 /* update_robot_neighbours + delete_interrobot_factors + create_interrobot_factors
  * (robot.rs:1362-1586; FactorGraph::delete_interrobot_factors_connected_to
@@ -187,8 +225,8 @@ int gbp_world_read_beliefs(gbp_world_t *w, double *eta, double *lam, double *mea
                            double *cov, uint8_t *valid);
 /* Transform.translation (x, z) of every robot, f32[n*2]. */
 int gbp_world_read_positions(gbp_world_t *w, float *xy);
-/* RobotConnections.robots_connected_with as CSR: offsets[n+1], neighbours sorted
- * ascending; robot_number[e] = RobotNumberGenerator value of the FIRST (i=1)
+/* RobotConnections.robots_connected_with as CSR: offsets[n+1], neighbours (global robot
+ * ids) sorted ascending; robot_number[e] = RobotNumberGenerator value of the FIRST (i=1)
  * InterRobot factor robot r created toward neighbours[e] (robot.rs:1527).
  * Pass capacity of the neighbour arrays; returns edge count or <0. */
 int64_t gbp_world_read_connections(gbp_world_t *w, int64_t *offsets, int32_t *neighbours,
@@ -210,7 +248,8 @@ enum gbp_profile_kind {
   GBP_PROFILE_ITERATE_EXT_INT = 2, /* k_iterate<EXT=1,INT=1>, the dominant kernel */
   GBP_PROFILE_TOPOLOGY = 3,        /* whole gbp_world_update_topology */
   GBP_PROFILE_PRIORS = 4,          /* horizon + current prior kernels */
-  GBP_PROFILE_KINDS = 5
+  GBP_PROFILE_HALO = 5,            /* the send/recv part of the per-sub-step halo exchange */
+  GBP_PROFILE_KINDS = 6
 };
 int gbp_world_set_profiling(gbp_world_t *w, int32_t on);
 int gbp_world_read_profile(gbp_world_t *w, int32_t kind, int64_t *count, double *total_ms);

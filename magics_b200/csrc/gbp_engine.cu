@@ -17,8 +17,10 @@
 #include <cuda_runtime.h>
 
 #include "../../include/gbp_b200.h"
+#include "gbp_comm.cuh"
 #include "gbp_iterate.cuh"
 #include "gbp_math.cuh"
+#include "gbp_shard.cuh"
 #include "gbp_store.cuh"
 #include "gbp_topology.cuh"
 
@@ -331,9 +333,26 @@ __global__ void k_set_dsafe(Store s, double mult) {
   for (int64_t e = s.eoff[r]; e < s.eoff[r + 1]; ++e) s.e_dsafe[e] = mult * double(s.radius[s.enbr[e]]);
 }
 
+__global__ void k_iota_gid(int32_t *gid, int32_t g0, int32_t n) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) gid[r] = g0 + r;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------
+// The shards that iterate one swarm together.  A plain single-GPU world is a group of one.
+struct gbp_group {
+  int ws = 1;
+  bool nccl = false;                 // transport: NCCL send/recv (one member) or in-process copies
+  gbp::NcclApi::comm_t comm = nullptr;
+  std::vector<gbp_world *> members;  // shards living in this process, indexed by rank when !nccl
+  bool committed = false;            // global ids fixed (gbp_world_commit_shards)
+  bool halo_stale = true;            // some published record changed since the last halo exchange
+  cudaStream_t shared_stream = nullptr;
+  int refs = 0;
+};
+
 struct gbp_world {
   gbp_config_t cfg{};
   int device = 0;
@@ -351,7 +370,9 @@ struct gbp_world {
   uint8_t *sdf_dev = nullptr;
   // two edge sets: the live one and a spare the next topology change is built into
   struct EdgeSet {
-    int32_t *enbr = nullptr;
+    int32_t *enbr = nullptr;   // neighbour slot
+    int32_t *egid = nullptr;   // neighbour global id, ascending (== enbr, same allocation, when ws == 1)
+    uint64_t *e_own = nullptr; // robot_number of the receiver's OWN factor toward the neighbour (i = 1)
     double *e_dsafe = nullptr;
     uint64_t *e_rnum = nullptr;
     uint32_t *e_birth = nullptr;
@@ -385,6 +406,33 @@ struct gbp_world {
   std::vector<cudaEvent_t> ev_pool;
   double prof_ms[GBP_PROFILE_KINDS] = {0};
   int64_t prof_count[GBP_PROFILE_KINDS] = {0};
+  // ---- sharding (gbp_shard.cuh) ------------------------------------------------------
+  gbp_group *grp = nullptr;
+  bool owns_stream = true;
+  gbp::ShardInfo sh{};          // ws, rank, gfirst
+  int32_t Ntot = 0;             // robots of the whole swarm
+  int32_t nghost = 0;
+  bool force_rebuild = false;
+  float *gpos = nullptr;        // [3][Ntot] x, z, radius of every robot by global id (ws > 1)
+  int64_t gpos_cap = 0;
+  int32_t *t_gflag = nullptr, *t_gslot = nullptr, *t_sflag = nullptr, *t_soff = nullptr;
+  int64_t *t_ccnt = nullptr, *t_coff = nullptr;
+  int64_t t_cap_tot = 0, t_cap_peer = 0;
+  int32_t *t_err = nullptr;
+  int32_t *sendlist = nullptr;
+  int64_t sendlist_cap = 0;
+  uint64_t *ckeys_s = nullptr, *cvals_s = nullptr, *ckeys_r = nullptr, *cvals_r = nullptr;
+  int64_t cross_cap = 0;
+  int64_t *hdr_send = nullptr, *hdr_recv = nullptr, *hdr_host = nullptr;  // 4 int64 per shard
+  double *halo_send = nullptr, *halo_recv = nullptr;
+  int64_t halo_send_cap = 0, halo_recv_cap = 0;  // in doubles
+  gbp::PeerOffsets ghost_po{}, send_po{};        // live halo layout (records per peer block)
+  // results of the current topology pass, applied only when some shard's connectivity changed
+  struct TopoPass {
+    int64_t E1 = 0, total_new = 0, nghost = 0;
+    bool changed = false;
+    gbp::PeerOffsets ghost_po{}, send_po{}, cross_po{};
+  } tp;
 };
 
 namespace {
@@ -459,15 +507,119 @@ int drain_profile(gbp_world *w) {
   return 0;
 }
 
+using EdgeSet = gbp_world::EdgeSet;
+
+void mark_halo_stale(gbp_world *w) {
+  if (w->grp) w->grp->halo_stale = true;
+}
+
+// ---- transport ---------------------------------------------------------------------
+// Runs one exchange for every shard of the group living in this process (gbp_comm.cuh).
+int exchange(gbp_group *g, std::vector<gbp::XferPlan> &plans) {
+  if (g->ws == 1) return 0;
+  if (g->nccl) {
+    gbp::NcclApi &api = gbp::nccl_api();
+    gbp_world *w = g->members[0];
+    int rc = api.GroupStart();
+    if (rc) return fail(GBP_ERR_NCCL, std::string("ncclGroupStart: ") + api.GetErrorString(rc));
+    for (const gbp::Xfer &x : plans[0].sends)
+      if (x.bytes && (rc = api.Send(x.ptr, x.bytes, gbp::kNcclUint8, x.peer, g->comm, w->stream)))
+        return fail(GBP_ERR_NCCL, std::string("ncclSend: ") + api.GetErrorString(rc));
+    for (const gbp::Xfer &x : plans[0].recvs)
+      if (x.bytes && (rc = api.Recv(x.ptr, x.bytes, gbp::kNcclUint8, x.peer, g->comm, w->stream)))
+        return fail(GBP_ERR_NCCL, std::string("ncclRecv: ") + api.GetErrorString(rc));
+    rc = api.GroupEnd();
+    if (rc) return fail(GBP_ERR_NCCL, std::string("ncclGroupEnd: ") + api.GetErrorString(rc));
+    return 0;
+  }
+  // in-process shards on one device and one stream: the k-th send a -> b is copied into the
+  // k-th receive of b from a
+  const int ws = g->ws;
+  for (int a = 0; a < ws; ++a) {
+    std::vector<size_t> next(size_t(ws), 0);
+    for (const gbp::Xfer &sx : plans[a].sends) {
+      const int b = sx.peer;
+      const std::vector<gbp::Xfer> &rv = plans[b].recvs;
+      size_t &k = next[b];
+      while (k < rv.size() && rv[k].peer != a) ++k;
+      if (k >= rv.size() || rv[k].bytes != sx.bytes)
+        return fail(GBP_ERR_STATE, "local exchange: send/receive lists of two shards do not pair up");
+      if (sx.bytes) CK(cudaMemcpyAsync(rv[k].ptr, sx.ptr, sx.bytes, cudaMemcpyDeviceToDevice, g->shared_stream));
+      ++k;
+    }
+  }
+  return 0;
+}
+
+template <class T>
+int ensure_buf(gbp_world *w, T *&p, int64_t &cap, int64_t need) {
+  if (need <= cap) return 0;
+  CK(cudaStreamSynchronize(w->stream));
+  cudaFree(p);
+  p = nullptr;
+  cap = 0;
+  const int64_t ncap = need + need / 4 + 1024;
+  CK(dalloc(p, size_t(ncap)));
+  cap = ncap;
+  return 0;
+}
+
+// ---- per-sub-step halo: published records of border robots -> ghost slots of the peers ----
+int group_halo(gbp_group *g) {
+  // Always exchanged before an external half (never skipped on a per-shard "nothing changed"
+  // guess: every rank must post the same sequence of transfers).
+  if (g->ws == 1) return 0;
+  const int ws = g->ws;
+  std::vector<gbp::XferPlan> plans(g->members.size());
+  for (size_t m = 0; m < g->members.size(); ++m) {
+    gbp_world *w = g->members[m];
+    CK(cudaSetDevice(w->device));
+    Store &s = w->s;
+    const int64_t hd = gbp::halo_doubles_per_robot(s.V);
+    const int64_t nsend = w->send_po.start[ws];
+    if (nsend > 0) {
+      gbp::k_halo_pack<<<blocks_for(nsend * (s.V - 1), 256), 256, 0, w->stream>>>(s, w->p, ws, w->send_po, w->sendlist,
+                                                                               w->halo_send);
+      CK(cudaGetLastError());
+      w->launches += 1;
+    }
+    for (int q = 0; q < ws; ++q) {
+      if (q == w->sh.rank) continue;
+      const int64_t cs = w->send_po.start[q + 1] - w->send_po.start[q];
+      const int64_t cr = w->ghost_po.start[q + 1] - w->ghost_po.start[q];
+      if (cs) plans[m].sends.push_back({q, w->halo_send + w->send_po.start[q] * hd, size_t(cs * hd * 8)});
+      if (cr) plans[m].recvs.push_back({q, w->halo_recv + w->ghost_po.start[q] * hd, size_t(cr * hd * 8)});
+    }
+  }
+  {
+    ProfileScope ps(g->members[0], GBP_PROFILE_HALO);
+    if (int rc = exchange(g, plans)) return rc;
+  }
+  for (gbp_world *w : g->members) {
+    CK(cudaSetDevice(w->device));
+    if (w->nghost > 0) {
+      gbp::k_halo_unpack<<<blocks_for(int64_t(w->nghost) * (w->s.V - 1), 256), 256, 0, w->stream>>>(
+          w->s, w->p, ws, w->ghost_po, w->halo_recv);
+      CK(cudaGetLastError());
+      w->launches += 1;
+    }
+  }
+  g->halo_stale = false;
+  return 0;
+}
+
 template <bool EXT, bool INT>
 int launch_iterate(gbp_world *w) {
   Store &s = w->s;
-  if (s.Nloc == 0) return 0;
+  w->epoch += 1;  // every shard steps its epoch, with or without robots
+  if (s.Nloc == 0) {
+    if (INT) w->p ^= 1;
+    return 0;
+  }
   const int rpw = 32 / s.V;
   const int64_t warps = (int64_t(s.Nloc) + rpw - 1) / rpw;
   const int wpb = gbp::kIterBlock / 32;
   const unsigned grid = unsigned((warps + wpb - 1) / wpb);
-  w->epoch += 1;
   {
     ProfileScope ps(w, EXT ? (INT ? GBP_PROFILE_ITERATE_EXT_INT : GBP_PROFILE_ITERATE_EXT) : GBP_PROFILE_ITERATE_INT);
     gbp::k_iterate<EXT, INT><<<grid, gbp::kIterBlock, 0, w->stream>>>(s, w->p, w->epoch);
@@ -481,10 +633,25 @@ int launch_iterate(gbp_world *w) {
   return 0;
 }
 
+// One half-step pair for every shard of the group: the external half reads the neighbours'
+// published records, so the halo must be current before it; the internal half republishes.
+template <bool EXT, bool INT>
+int group_launch(gbp_group *g) {
+  if (EXT) {
+    if (int rc = group_halo(g)) return rc;
+  }
+  for (gbp_world *w : g->members) {
+    CK(cudaSetDevice(w->device));
+    if (int rc = launch_iterate<EXT, INT>(w)) return rc;
+  }
+  if (INT) g->halo_stale = true;
+  return 0;
+}
+
 // iterate_gbp_v2 (robot.rs:1769-1861): flatten the schedule into half-steps
 // I (internal factor+variable) and E (external factor+variable); an E directly
 // followed by an I runs as one fused launch.
-int run_schedule(gbp_world *w, int n, const uint8_t *internal, const uint8_t *external) {
+int run_schedule(gbp_group *g, int n, const uint8_t *internal, const uint8_t *external) {
   std::vector<char> ph;
   ph.reserve(size_t(n) * 2);
   for (int i = 0; i < n; ++i) {
@@ -494,21 +661,19 @@ int run_schedule(gbp_world *w, int n, const uint8_t *internal, const uint8_t *ex
   for (size_t k = 0; k < ph.size();) {
     int rc;
     if (ph[k] == 'E' && k + 1 < ph.size() && ph[k + 1] == 'I') {
-      rc = launch_iterate<true, true>(w);
+      rc = group_launch<true, true>(g);
       k += 2;
     } else if (ph[k] == 'E') {
-      rc = launch_iterate<true, false>(w);
+      rc = group_launch<true, false>(g);
       k += 1;
     } else {
-      rc = launch_iterate<false, true>(w);
+      rc = group_launch<false, true>(g);
       k += 1;
     }
     if (rc) return rc;
   }
   return 0;
 }
-
-using EdgeSet = gbp_world::EdgeSet;
 
 int ensure_scratch(gbp_world *w, size_t bytes) {
   if (bytes <= w->rb_bytes) return 0;
@@ -535,12 +700,21 @@ void bind_edge_set(gbp_world *w) {
   s.EV = e.cap * (s.V - 1);
 }
 
+void free_edge_set(gbp_world *w, EdgeSet *e) {
+  if (e->egid != e->enbr) cudaFree(e->egid);
+  cudaFree(e->enbr); cudaFree(e->e_own); cudaFree(e->e_dsafe); cudaFree(e->e_rnum); cudaFree(e->e_birth);
+  cudaFree(e->e_frozen); cudaFree(e->mir); cudaFree(e->map); cudaFree(e->mu_frozen);
+  *e = EdgeSet();
+}
+
 int grow_edge_set(gbp_world *w, EdgeSet *e, int64_t cap) {
   CK(cudaStreamSynchronize(w->stream));
-  cudaFree(e->enbr); cudaFree(e->e_dsafe); cudaFree(e->e_rnum); cudaFree(e->e_birth); cudaFree(e->e_frozen);
-  cudaFree(e->mir); cudaFree(e->map); cudaFree(e->mu_frozen);
+  free_edge_set(w, e);
   const int Vm1 = w->s.V - 1;
   CK(dalloc(e->enbr, size_t(cap)));
+  if (w->sh.ws > 1) CK(dalloc(e->egid, size_t(cap)));
+  else e->egid = e->enbr;  // one GPU: global id == slot
+  CK(dalloc(e->e_own, size_t(cap)));
   CK(dalloc(e->e_dsafe, size_t(cap)));
   CK(dalloc(e->e_rnum, size_t(cap)));
   CK(dalloc(e->e_birth, size_t(cap)));
@@ -552,27 +726,428 @@ int grow_edge_set(gbp_world *w, EdgeSet *e, int64_t cap) {
   return 0;
 }
 
-int ensure_topology_scratch(gbp_world *w, int64_t n) {
+constexpr int kResultWords = 4 + 3 * (gbp::kMaxShards + 1);
+
+int ensure_topology_scratch(gbp_world *w) {
+  const int64_t nloc = w->s.Nloc, ntot = w->Ntot, ws = w->sh.ws;
   if (!w->t_result_dev) {
-    CK(dalloc(w->t_result_dev, 2));
-    CK(cudaMallocHost(reinterpret_cast<void **>(&w->t_result_host), 2 * sizeof(int64_t)));
+    CK(dalloc(w->t_result_dev, kResultWords));
+    CK(cudaMallocHost(reinterpret_cast<void **>(&w->t_result_host), kResultWords * sizeof(int64_t)));
+    CK(dalloc(w->t_err, 1));
+    CK(cudaMemset(w->t_err, 0, sizeof(int32_t)));
+    CK(dalloc(w->hdr_send, 4));
+    CK(dalloc(w->hdr_recv, 4 * gbp::kMaxShards));
+    CK(cudaMallocHost(reinterpret_cast<void **>(&w->hdr_host), 4 * (gbp::kMaxShards + 1) * sizeof(int64_t)));
   }
-  if (n <= w->t_cap) return 0;
-  cudaFree(w->t_nlow);
-  CK(dalloc(w->t_nlow, n));
-  cudaFree(w->t_cx); cudaFree(w->t_cz); cudaFree(w->t_idx); cudaFree(w->t_idx_sorted);
-  cudaFree(w->t_keys); cudaFree(w->t_keys_sorted); cudaFree(w->t_cnt); cudaFree(w->t_off);
-  cudaFree(w->t_newcnt); cudaFree(w->t_newoff); cudaFree(w->t_cub);
-  CK(dalloc(w->t_cx, n)); CK(dalloc(w->t_cz, n)); CK(dalloc(w->t_idx, n)); CK(dalloc(w->t_idx_sorted, n));
-  CK(dalloc(w->t_keys, n)); CK(dalloc(w->t_keys_sorted, n));
-  CK(dalloc(w->t_cnt, n + 1)); CK(dalloc(w->t_off, n + 1));
-  CK(dalloc(w->t_newcnt, n + 1)); CK(dalloc(w->t_newoff, n + 1));
-  size_t b1 = 0, b2 = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, b1, w->t_keys, w->t_keys_sorted, w->t_idx, w->t_idx_sorted, int(n));
-  cub::DeviceScan::ExclusiveSum(nullptr, b2, w->t_cnt, w->t_off, int(n + 1));
-  w->t_cub_bytes = std::max(b1, b2);
-  CK(cudaMalloc(&w->t_cub, w->t_cub_bytes));
-  w->t_cap = n;
+  bool regrow_cub = false;
+  if (!w->t_cnt || nloc > w->t_cap) {
+    cudaFree(w->t_nlow); cudaFree(w->t_cnt); cudaFree(w->t_off); cudaFree(w->t_newcnt); cudaFree(w->t_newoff);
+    CK(dalloc(w->t_nlow, nloc));
+    CK(dalloc(w->t_cnt, nloc + 1)); CK(dalloc(w->t_off, nloc + 1));
+    CK(dalloc(w->t_newcnt, nloc + 1)); CK(dalloc(w->t_newoff, nloc + 1));
+    w->t_cap = nloc;
+    regrow_cub = true;
+  }
+  if (!w->t_cx || ntot > w->t_cap_tot) {
+    cudaFree(w->t_cx); cudaFree(w->t_cz); cudaFree(w->t_idx); cudaFree(w->t_idx_sorted);
+    cudaFree(w->t_keys); cudaFree(w->t_keys_sorted); cudaFree(w->t_gflag); cudaFree(w->t_gslot);
+    CK(dalloc(w->t_cx, ntot)); CK(dalloc(w->t_cz, ntot)); CK(dalloc(w->t_idx, ntot)); CK(dalloc(w->t_idx_sorted, ntot));
+    CK(dalloc(w->t_keys, ntot)); CK(dalloc(w->t_keys_sorted, ntot));
+    CK(dalloc(w->t_gflag, ntot + 1)); CK(dalloc(w->t_gslot, ntot + 1));
+    w->t_cap_tot = ntot;
+    regrow_cub = true;
+  }
+  if (ws > 1 && (!w->t_sflag || ws * nloc > w->t_cap_peer)) {
+    cudaFree(w->t_sflag); cudaFree(w->t_soff); cudaFree(w->t_ccnt); cudaFree(w->t_coff);
+    CK(dalloc(w->t_sflag, ws * nloc + 1)); CK(dalloc(w->t_soff, ws * nloc + 1));
+    CK(dalloc(w->t_ccnt, ws * nloc + 1)); CK(dalloc(w->t_coff, ws * nloc + 1));
+    w->t_cap_peer = ws * nloc;
+    regrow_cub = true;
+  }
+  if (regrow_cub || !w->t_cub) {
+    size_t b[5] = {0, 0, 0, 0, 0};
+    cub::DeviceRadixSort::SortPairs(nullptr, b[0], w->t_keys, w->t_keys_sorted, w->t_idx, w->t_idx_sorted,
+                                    int(w->t_cap_tot));
+    cub::DeviceScan::ExclusiveSum(nullptr, b[1], w->t_cnt, w->t_off, int(w->t_cap + 1));
+    cub::DeviceScan::ExclusiveSum(nullptr, b[2], w->t_gflag, w->t_gslot, int(w->t_cap_tot + 1));
+    if (ws > 1) {
+      cub::DeviceScan::ExclusiveSum(nullptr, b[3], w->t_sflag, w->t_soff, int(w->t_cap_peer + 1));
+      cub::DeviceScan::ExclusiveSum(nullptr, b[4], w->t_ccnt, w->t_coff, int(w->t_cap_peer + 1));
+    }
+    size_t need = *std::max_element(b, b + 5) + 256;
+    if (need > w->t_cub_bytes) {
+      CK(cudaStreamSynchronize(w->stream));
+      cudaFree(w->t_cub);
+      w->t_cub = nullptr;
+      CK(cudaMalloc(&w->t_cub, need));
+      w->t_cub_bytes = need;
+    }
+  }
+  return 0;
+}
+
+// Re-stride every per-variable / per-robot plane to `newcap` robot slots, keeping the own robots.
+int reserve_robots(gbp_world *w, int64_t newcap) {
+  Store &s = w->s;
+  if (newcap <= s.cap) return 0;
+  cudaStream_t st = w->stream;
+  const int V = s.V;
+  const int64_t oldNV = s.NV, newNV = newcap * V, used = int64_t(s.Nloc) * V, oldcap = s.cap, keep = s.Nloc;
+  CK(regrow(s.prior_eta, 4, oldNV, newNV, used, st));
+  CK(regrow(s.prior_lam, 1, oldNV, newNV, used, st));
+  CK(regrow(s.pub[0], gbp::kRec, oldNV, newNV, used, st));
+  CK(regrow(s.pub[1], gbp::kRec, oldNV, newNV, used, st));
+  CK(regrow(s.pub_epoch[0], 1, oldNV, newNV, used, st));
+  CK(regrow(s.pub_epoch[1], 1, oldNV, newNV, used, st));
+  CK(regrow(s.bel_ext, gbp::kRec, oldNV, newNV, used, st));
+  CK(regrow(s.mu_ext, 2, oldNV, newNV, used, st));
+  CK(regrow(s.cov, 16, oldNV, newNV, used, st));
+  CK(regrow(s.valid, 1, oldNV, newNV, used, st));
+  CK(regrow(s.m_dynL, 20, oldNV, newNV, used, st));
+  CK(regrow(s.m_dynR, 20, oldNV, newNV, used, st));
+  CK(regrow(s.m_obs, 4, oldNV, newNV, used, st));
+  CK(regrow(s.m_trk, 3, oldNV, newNV, used, st));
+  CK(regrow(s.dyn_dt, 1, oldNV, newNV, used, st));
+  CK(regrow(s.trk_record, 1, oldNV, newNV, used, st));
+  CK(regrow(s.trk_timeout, 1, oldNV, newNV, used, st));
+  CK(regrow(s.trk_last, 2, oldNV, newNV, used, st));
+  CK(regrow(s.trk_value, 1, oldNV, newNV, used, st));
+  CK(regrow(s.radius, 1, oldcap, newcap, keep, st));
+  CK(regrow(s.t0, 1, oldcap, newcap, keep, st));
+  CK(regrow(s.pos, 2, oldcap, newcap, keep, st));
+  CK(regrow(s.antenna, 1, oldcap, newcap, keep, st));
+  CK(regrow(s.idle, 1, oldcap, newcap, keep, st));
+  CK(regrow(s.finished, 1, oldcap, newcap, keep, st));
+  CK(regrow(s.latest, 1, oldcap, newcap, keep, st));
+  CK(regrow(s.iter_factor, 1, oldcap, newcap, keep, st));
+  CK(regrow(s.gid, 1, oldcap, newcap, keep, st));
+  CK(regrow(s.next_wp, 1, oldcap, newcap, keep, st));
+  CK(regrow(s.nlow, 1, oldcap, newcap, keep, st));
+  s.NV = newNV;
+  s.cap = newcap;
+  // ghost slots were dropped by the re-stride: the next topology pass rebuilds them
+  s.N = s.Nloc;
+  if (w->nghost > 0) w->force_rebuild = true;
+  mark_halo_stale(w);
+  return 0;
+}
+
+// ---- topology, phase 1 (per shard): neighbour search, diff against the live CSR, ghost and
+// send lists; one host sync reads the sizes.
+int topo_search(gbp_world *w) {
+  CK(cudaSetDevice(w->device));
+  Store &s = w->s;
+  const int32_t n = s.Nloc, ws = w->sh.ws;
+  if (ws == 1) {  // a plain world: global id == slot
+    w->sh.rank = 0;
+    w->sh.gfirst[0] = 0;
+    w->sh.gfirst[1] = n;
+    w->Ntot = n;
+  }
+  const int32_t ntot = w->Ntot, g0 = w->sh.gfirst[w->sh.rank];
+  w->tp = gbp_world::TopoPass();
+  if (ntot == 0) return 0;
+  cudaStream_t st = w->stream;
+  if (int rc = ensure_topology_scratch(w)) return rc;
+  const float *gx = ws > 1 ? w->gpos : s.pos;
+  const float *gz = ws > 1 ? w->gpos + ntot : s.pos + s.cap;
+  const int T = 128;
+  const float R = w->cfg.comms_radius;
+  const double cell = double(R) * 1.001;
+  gbp::k_cell_keys<<<blocks_for(ntot, T), T, 0, st>>>(ntot, gx, gz, cell, w->t_cx, w->t_cz, w->t_keys, w->t_idx);
+  size_t cb = w->t_cub_bytes;
+  CK(cub::DeviceRadixSort::SortPairs(w->t_cub, cb, w->t_keys, w->t_keys_sorted, w->t_idx, w->t_idx_sorted, ntot, 0, 32, st));
+  if (n > 0)
+    gbp::k_neighbours<false><<<blocks_for(n, T), T, 0, st>>>(ntot, g0, n, gx, gz, w->t_cx, w->t_cz, w->t_keys_sorted,
+                                                             w->t_idx_sorted, R, w->t_cnt, nullptr, 0);
+  CK(cudaMemsetAsync(w->t_cnt + n, 0, sizeof(int64_t), st));
+  cb = w->t_cub_bytes;
+  CK(cub::DeviceScan::ExclusiveSum(w->t_cub, cb, w->t_cnt, w->t_off, n + 1, st));
+  w->launches += 4;
+  // The new CSR is written straight into the spare edge set.  If the spare set is too small the
+  // guarded kernels did nothing: grow it and run them again.
+  EdgeSet *spare = &w->edges[1 - w->cur];
+  const EdgeSet *live = &w->edges[w->cur];
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (n > 0) {
+      gbp::k_neighbours<true><<<blocks_for(n, T), T, 0, st>>>(ntot, g0, n, gx, gz, w->t_cx, w->t_cz, w->t_keys_sorted,
+                                                              w->t_idx_sorted, R, w->t_off, spare->egid, spare->cap);
+      gbp::k_edge_diff<<<blocks_for(n, T), T, 0, st>>>(n, g0, w->t_off, spare->egid, s.eoff, live->egid, n, spare->map,
+                                                       w->t_newcnt, w->t_nlow, spare->cap);
+    }
+    CK(cudaMemsetAsync(w->t_newcnt + n, 0, sizeof(int64_t), st));
+    cb = w->t_cub_bytes;
+    CK(cub::DeviceScan::ExclusiveSum(w->t_cub, cb, w->t_newcnt, w->t_newoff, n + 1, st));
+    w->launches += 3;
+    if (ws > 1) {
+      CK(cudaMemsetAsync(w->t_gflag, 0, size_t(ntot + 1) * sizeof(int32_t), st));
+      CK(cudaMemsetAsync(w->t_sflag + int64_t(ws) * n, 0, sizeof(int32_t), st));
+      CK(cudaMemsetAsync(w->t_ccnt + int64_t(ws) * n, 0, sizeof(int64_t), st));
+      if (n > 0)
+        gbp::k_cross_mark<<<blocks_for(n, T), T, 0, st>>>(w->sh, n, w->t_off, spare->egid, spare->cap, w->t_gflag,
+                                                          w->t_sflag, w->t_ccnt);
+      cb = w->t_cub_bytes;
+      CK(cub::DeviceScan::ExclusiveSum(w->t_cub, cb, w->t_gflag, w->t_gslot, ntot + 1, st));
+      cb = w->t_cub_bytes;
+      CK(cub::DeviceScan::ExclusiveSum(w->t_cub, cb, w->t_sflag, w->t_soff, ws * n + 1, st));
+      cb = w->t_cub_bytes;
+      CK(cub::DeviceScan::ExclusiveSum(w->t_cub, cb, w->t_ccnt, w->t_coff, ws * n + 1, st));
+      w->launches += 4;
+    }
+    gbp::k_shard_result<<<1, 32, 0, st>>>(w->sh, n, w->t_off, w->t_newoff, ws > 1 ? w->t_gslot : nullptr, w->t_soff,
+                                          w->t_coff, w->t_err, w->t_result_dev);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(w->t_result_host, w->t_result_dev, kResultWords * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    w->launches += 1;
+    if (w->t_result_host[3] != 0)
+      return fail(GBP_ERR_STATE, "sharded topology: a cross-shard robot_number lookup failed in an earlier pass "
+                                 "(neighbour lists of two shards disagree)");
+    w->tp.E1 = w->t_result_host[0];
+    w->tp.total_new = w->t_result_host[1];
+    if (w->tp.E1 <= spare->cap) break;
+    if (attempt == 1) return fail(GBP_ERR_STATE, "topology: spare edge set still too small after growing");
+    if (int rc = grow_edge_set(w, spare, w->tp.E1 + w->tp.E1 / 4 + 1024)) return rc;
+  }
+  if (ws > 1) {
+    w->tp.nghost = w->t_result_host[2];
+    for (int q = 0; q <= ws; ++q) {
+      w->tp.ghost_po.start[q] = w->t_result_host[4 + q];
+      w->tp.send_po.start[q] = w->t_result_host[4 + (ws + 1) + q];
+      w->tp.cross_po.start[q] = w->t_result_host[4 + 2 * (ws + 1) + q];
+    }
+  }
+  w->tp.changed = w->tp.total_new != 0 || w->tp.E1 != s.E || w->force_rebuild;
+  return 0;
+}
+
+// ---- topology, phase 2 (per shard, ws > 1): what the other shards need from this one: the
+// header (new pair count, changed flag, epoch) and the numbers of the own cross-shard factors.
+int topo_pack(gbp_world *w, gbp::XferPlan &plan) {
+  CK(cudaSetDevice(w->device));
+  Store &s = w->s;
+  const int ws = w->sh.ws, n = s.Nloc;
+  cudaStream_t st = w->stream;
+  const int64_t ncross = w->tp.cross_po.start[ws];
+  if (ncross > w->cross_cap) {
+    CK(cudaStreamSynchronize(st));
+    cudaFree(w->ckeys_s); cudaFree(w->cvals_s); cudaFree(w->ckeys_r); cudaFree(w->cvals_r);
+    const int64_t cap = ncross + ncross / 4 + 1024;
+    CK(dalloc(w->ckeys_s, cap)); CK(dalloc(w->cvals_s, cap)); CK(dalloc(w->ckeys_r, cap)); CK(dalloc(w->cvals_r, cap));
+    w->cross_cap = cap;
+  }
+  int64_t *h = w->hdr_host + 4 * gbp::kMaxShards;  // staging row for the own header
+  h[0] = w->tp.total_new;
+  h[1] = w->tp.changed ? 1 : 0;
+  h[2] = int64_t(w->epoch);
+  h[3] = w->tp.E1;
+  CK(cudaMemcpyAsync(w->hdr_send, h, 4 * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  if (n > 0 && ncross > 0) {
+    const EdgeSet *spare = &w->edges[1 - w->cur], *live = &w->edges[w->cur];
+    gbp::k_cross_pack<<<blocks_for(n, 128), 128, 0, st>>>(w->sh, n, w->t_off, spare->egid, spare->map, w->t_newoff,
+                                                        live->e_own, w->t_coff, w->ckeys_s, w->cvals_s);
+    CK(cudaGetLastError());
+    w->launches += 1;
+  }
+  for (int q = 0; q < ws; ++q) {
+    if (q == w->sh.rank) continue;
+    const int64_t c0 = w->tp.cross_po.start[q], cnt = w->tp.cross_po.start[q + 1] - c0;
+    plan.sends.push_back({q, w->hdr_send, 4 * sizeof(int64_t)});
+    plan.recvs.push_back({q, w->hdr_recv + 4 * q, 4 * sizeof(int64_t)});
+    if (cnt) {
+      plan.sends.push_back({q, w->ckeys_s + c0, size_t(cnt) * 8});
+      plan.sends.push_back({q, w->cvals_s + c0, size_t(cnt) * 8});
+      plan.recvs.push_back({q, w->ckeys_r + c0, size_t(cnt) * 8});
+      plan.recvs.push_back({q, w->cvals_r + c0, size_t(cnt) * 8});
+    }
+  }
+  return 0;
+}
+
+// ---- topology, phase 3 (per shard): apply the new CSR.  hdr[q] = {new pairs, changed, epoch, E}
+// of every shard (own row included).
+int topo_apply(gbp_world *w, const int64_t (*hdr)[4]) {
+  CK(cudaSetDevice(w->device));
+  Store &s = w->s;
+  const int ws = w->sh.ws, n = s.Nloc, rank = w->sh.rank;
+  bool changed = false;
+  int64_t sum_new = 0, max_epoch = 0;
+  gbp::ShardBases bases{};
+  for (int q = 0; q < ws; ++q) {
+    bases.base[q] = sum_new;
+    sum_new += hdr[q][0];
+    changed = changed || hdr[q][1] != 0;
+    max_epoch = std::max(max_epoch, hdr[q][2]);
+  }
+  if (!changed) return 0;  // connectivity unchanged everywhere: keep the store as is
+  cudaStream_t st = w->stream;
+  const int T = 128;
+  const int32_t ntot = w->Ntot, g0 = w->sh.gfirst[rank];
+  const int64_t E1 = w->tp.E1;
+  // every shard moves to the same epoch, above anything any shard has written so far
+  w->epoch = uint32_t(max_epoch) + 1;
+  const int Vm1 = s.V - 1;
+  if (ws > 1) {
+    const int64_t hd = gbp::halo_doubles_per_robot(s.V);
+    if (int64_t(n) + w->tp.nghost > s.cap) {
+      if (int rc = reserve_robots(w, int64_t(n) + w->tp.nghost + w->tp.nghost / 4 + 256)) return rc;
+    }
+    if (int rc = ensure_buf(w, w->sendlist, w->sendlist_cap, w->tp.send_po.start[ws])) return rc;
+    if (int rc = ensure_buf(w, w->halo_send, w->halo_send_cap, w->tp.send_po.start[ws] * hd)) return rc;
+    if (int rc = ensure_buf(w, w->halo_recv, w->halo_recv_cap, w->tp.nghost * hd)) return rc;
+  }
+  EdgeSet *spare = &w->edges[1 - w->cur];
+  const EdgeSet *live = &w->edges[w->cur];
+  const float *gradius = ws > 1 ? w->gpos + 2 * int64_t(ntot) : s.radius;
+  if (n > 0) {
+    gbp::k_edge_assign_own<<<blocks_for(n, T), T, 0, st>>>(
+        n, s.V, w->t_off, spare->egid, spare->map, w->t_newoff, gradius, double(w->cfg.safety_distance_multiplier),
+        w->robot_number, bases.base[rank], w->epoch, live->e_own, live->e_rnum, live->e_birth, live->e_frozen,
+        spare->e_own, spare->e_dsafe, spare->e_rnum, spare->e_birth, spare->e_frozen);
+    gbp::k_edge_pull<<<blocks_for(n, T), T, 0, st>>>(w->sh, n, s.V, w->t_off, spare->egid, spare->map, spare->e_own,
+                                                     w->robot_number, bases, w->tp.cross_po, w->ckeys_r, w->cvals_r,
+                                                     spare->e_rnum, w->t_err);
+    w->launches += 2;
+  }
+  if (E1 > 0) {
+    gbp::k_mirror_move<<<blocks_for(E1 * Vm1, 256), 256, 0, st>>>(s, w->p, E1 * Vm1, Vm1, w->t_off, spare->map, s.mir,
+                                                                  s.mu_frozen, s.EV, spare->mir, spare->mu_frozen,
+                                                                  spare->cap * Vm1);
+    w->launches += 1;
+  }
+  if (ws > 1) {
+    gbp::k_ghost_fill<<<blocks_for(ntot, 256), 256, 0, st>>>(ntot, n, w->t_gflag, w->t_gslot, gradius, s.gid, s.radius);
+    if (E1 > 0)
+      gbp::k_edge_slots<<<blocks_for(E1, 256), 256, 0, st>>>(E1, g0, n, spare->egid, w->t_gslot, spare->enbr);
+    if (n > 0)
+      gbp::k_sendlist_fill<<<blocks_for(int64_t(ws) * n, 256), 256, 0, st>>>(ws, n, w->t_sflag, w->t_soff, w->sendlist);
+    w->launches += 3;
+  }
+  CK(cudaGetLastError());
+  if (n > 0) {
+    CK(cudaMemcpyAsync(s.eoff, w->t_off, size_t(n + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(s.nlow, w->t_nlow, size_t(n) * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  }
+  w->cur = 1 - w->cur;
+  bind_edge_set(w);
+  s.E = E1;
+  w->robot_number += uint64_t(Vm1) * uint64_t(sum_new);
+  w->nghost = int32_t(w->tp.nghost);
+  s.N = n + w->nghost;
+  w->ghost_po = w->tp.ghost_po;
+  w->send_po = w->tp.send_po;
+  w->force_rebuild = false;
+  mark_halo_stale(w);
+  return 0;
+}
+
+// update_robot_neighbours + delete_interrobot_factors + create_interrobot_factors for every
+// shard of the group (robot.rs:1362-1586).
+int group_update_topology(gbp_group *g) {
+  const int ws = g->ws;
+  if (ws > 1 && !g->committed) return fail(GBP_ERR_STATE, "sharded world: call gbp_world_commit_shards first");
+  ProfileScope ps(g->members[0], GBP_PROFILE_TOPOLOGY);
+  const size_t nm = g->members.size();
+  std::vector<gbp::XferPlan> plans(nm);
+  if (ws > 1) {
+    // every shard learns every robot's Transform (x, z) and radius: 12 bytes per robot per tick
+    for (size_t m = 0; m < nm; ++m) {
+      gbp_world *w = g->members[m];
+      CK(cudaSetDevice(w->device));
+      Store &s = w->s;
+      const int rank = w->sh.rank, ntot = w->Ntot, n = s.Nloc, g0 = w->sh.gfirst[rank];
+      const float *src[3] = {s.pos, s.pos + s.cap, s.radius};
+      for (int k = 0; k < 3; ++k) {
+        if (n > 0)
+          CK(cudaMemcpyAsync(w->gpos + int64_t(k) * ntot + g0, src[k], size_t(n) * 4, cudaMemcpyDeviceToDevice, w->stream));
+        for (int q = 0; q < ws; ++q) {
+          if (q == rank) continue;
+          const int nq = w->sh.gfirst[q + 1] - w->sh.gfirst[q];
+          if (n > 0) plans[m].sends.push_back({q, const_cast<float *>(src[k]), size_t(n) * 4});
+          if (nq > 0) plans[m].recvs.push_back({q, w->gpos + int64_t(k) * ntot + w->sh.gfirst[q], size_t(nq) * 4});
+        }
+      }
+    }
+    // sends are grouped by plane then peer on both sides, so the k-th send to a peer pairs with its k-th receive
+    if (int rc = exchange(g, plans)) return rc;
+  }
+  for (gbp_world *w : g->members)
+    if (int rc = topo_search(w)) return rc;
+  int64_t hdr[gbp::kMaxShards][4];
+  if (ws == 1) {
+    gbp_world *w = g->members[0];
+    hdr[0][0] = w->tp.total_new;
+    hdr[0][1] = w->tp.changed ? 1 : 0;
+    hdr[0][2] = int64_t(w->epoch);
+    hdr[0][3] = w->tp.E1;
+    return topo_apply(w, hdr);
+  }
+  for (size_t m = 0; m < nm; ++m) {
+    plans[m].clear();
+    if (int rc = topo_pack(g->members[m], plans[m])) return rc;
+  }
+  if (int rc = exchange(g, plans)) return rc;
+  for (gbp_world *w : g->members) {
+    CK(cudaSetDevice(w->device));
+    CK(cudaMemcpyAsync(w->hdr_host, w->hdr_recv, 4 * size_t(ws) * sizeof(int64_t), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+  }
+  for (gbp_world *w : g->members) {
+    for (int q = 0; q < ws; ++q)
+      for (int k = 0; k < 4; ++k)
+        hdr[q][k] = q == w->sh.rank ? w->hdr_host[4 * gbp::kMaxShards + k] : w->hdr_host[4 * q + k];
+    if (int rc = topo_apply(w, hdr)) return rc;
+  }
+  return 0;
+}
+
+// Fix the global robot ids: shard q owns [gfirst[q], gfirst[q+1]) in rank order.
+int group_commit(gbp_group *g) {
+  const int ws = g->ws;
+  const size_t nm = g->members.size();
+  std::vector<gbp::XferPlan> plans(nm);
+  for (size_t m = 0; m < nm; ++m) {
+    gbp_world *w = g->members[m];
+    CK(cudaSetDevice(w->device));
+    if (int rc = ensure_topology_scratch(w)) return rc;
+    int64_t *h = w->hdr_host + 4 * gbp::kMaxShards;
+    h[0] = w->s.Nloc;
+    h[1] = h[2] = h[3] = 0;
+    CK(cudaMemcpyAsync(w->hdr_send, h, 4 * sizeof(int64_t), cudaMemcpyHostToDevice, w->stream));
+    for (int q = 0; q < ws; ++q) {
+      if (q == w->sh.rank) continue;
+      plans[m].sends.push_back({q, w->hdr_send, 4 * sizeof(int64_t)});
+      plans[m].recvs.push_back({q, w->hdr_recv + 4 * q, 4 * sizeof(int64_t)});
+    }
+  }
+  if (int rc = exchange(g, plans)) return rc;
+  for (gbp_world *w : g->members) {
+    CK(cudaSetDevice(w->device));
+    CK(cudaMemcpyAsync(w->hdr_host, w->hdr_recv, 4 * size_t(gbp::kMaxShards) * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                       w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    int64_t tot = 0;
+    for (int q = 0; q < ws; ++q) {
+      w->sh.gfirst[q] = int32_t(tot);
+      tot += q == w->sh.rank ? int64_t(w->s.Nloc) : w->hdr_host[4 * q];
+    }
+    if (tot > INT32_MAX) return fail(GBP_ERR_BAD_ARGUMENT, "more than 2^31 robots");
+    w->sh.gfirst[ws] = int32_t(tot);
+    w->Ntot = int32_t(tot);
+    if (ws > 1 && 3 * tot > w->gpos_cap) {
+      cudaFree(w->gpos);
+      CK(dalloc(w->gpos, size_t(3 * tot)));
+      w->gpos_cap = 3 * tot;
+    }
+    if (w->s.Nloc > 0) {
+      k_iota_gid<<<blocks_for(w->s.Nloc, 256), 256, 0, w->stream>>>(w->s.gid, w->sh.gfirst[w->sh.rank], w->s.Nloc);
+      CK(cudaGetLastError());
+      w->launches += 1;
+    }
+    w->force_rebuild = true;
+  }
+  g->committed = true;
+  g->halo_stale = true;
   return 0;
 }
 
@@ -610,7 +1185,8 @@ int gbp_variable_timesteps(uint32_t h, uint32_t m, uint32_t *out, int32_t cap) {
   return cnt;
 }
 
-gbp_world_t *gbp_world_create(const gbp_config_t *cfg, int32_t device) {
+namespace {
+gbp_world *make_world(const gbp_config_t *cfg, int32_t device, cudaStream_t shared) {
   if (!cfg || cfg->num_variables < 2 || cfg->num_variables > 32) {
     fail(GBP_ERR_BAD_ARGUMENT, "gbp_world_create: num_variables must be in [2, 32]");
     return nullptr;
@@ -623,8 +1199,14 @@ gbp_world_t *gbp_world_create(const gbp_config_t *cfg, int32_t device) {
   gbp_world *w = new gbp_world();
   w->cfg = *cfg;
   w->device = device;
-  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&w->ev0) != cudaSuccess || cudaEventCreate(&w->ev1) != cudaSuccess) {
+  bool ok = cudaSetDevice(device) == cudaSuccess;
+  if (ok && shared) {
+    w->stream = shared;
+    w->owns_stream = false;
+  } else if (ok) {
+    ok = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) == cudaSuccess;
+  }
+  if (!ok || cudaEventCreate(&w->ev0) != cudaSuccess || cudaEventCreate(&w->ev1) != cudaSuccess) {
     fail(GBP_ERR_CUDA, "gbp_world_create: stream/event creation failed");
     delete w;
     return nullptr;
@@ -641,8 +1223,96 @@ gbp_world_t *gbp_world_create(const gbp_config_t *cfg, int32_t device) {
   w->s.sdf = w->sdf_dev;
   w->s.sdf_w = 1;
   w->s.sdf_h = 1;
+  w->sh.ws = 1;
+  w->sh.rank = 0;
   refresh_scalars(w);
   return w;
+}
+
+void join_group(gbp_world *w, gbp_group *g, int rank) {
+  w->grp = g;
+  w->sh.ws = g->ws;
+  w->sh.rank = rank;
+  g->members.push_back(w);
+  g->refs += 1;
+}
+}  // namespace
+
+gbp_world_t *gbp_world_create(const gbp_config_t *cfg, int32_t device) {
+  gbp_world *w = make_world(cfg, device, nullptr);
+  if (!w) return nullptr;
+  gbp_group *g = new gbp_group();
+  g->committed = true;
+  join_group(w, g, 0);
+  return w;
+}
+
+int gbp_comm_unique_id(uint8_t *id) {
+  if (!id) return fail(GBP_ERR_BAD_ARGUMENT, "gbp_comm_unique_id: null output");
+  gbp::NcclApi &api = gbp::nccl_api();
+  if (!api.load()) return fail(GBP_ERR_NCCL, api.error);
+  gbp::NcclApi::unique_id uid;
+  const int rc = api.GetUniqueId(&uid);
+  if (rc) return fail(GBP_ERR_NCCL, std::string("ncclGetUniqueId: ") + api.GetErrorString(rc));
+  static_assert(sizeof(uid) == GBP_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+  std::memcpy(id, &uid, sizeof(uid));
+  return 0;
+}
+
+gbp_world_t *gbp_world_create_shard(const gbp_config_t *cfg, int32_t device, int32_t rank, int32_t world_size,
+                                    const uint8_t *id) {
+  if (world_size < 1 || world_size > gbp::kMaxShards || rank < 0 || rank >= world_size || (world_size > 1 && !id)) {
+    fail(GBP_ERR_BAD_ARGUMENT, "gbp_world_create_shard: need 0 <= rank < world_size <= 16 and a communicator id");
+    return nullptr;
+  }
+  if (world_size == 1) return gbp_world_create(cfg, device);
+  gbp::NcclApi &api = gbp::nccl_api();
+  if (!api.load()) {
+    fail(GBP_ERR_NCCL, api.error);
+    return nullptr;
+  }
+  gbp_world *w = make_world(cfg, device, nullptr);
+  if (!w) return nullptr;
+  gbp_group *g = new gbp_group();
+  g->ws = world_size;
+  g->nccl = true;
+  join_group(w, g, rank);
+  gbp::NcclApi::unique_id uid;
+  std::memcpy(&uid, id, sizeof(uid));
+  const int rc = api.CommInitRank(&g->comm, world_size, uid, rank);
+  if (rc) {
+    fail(GBP_ERR_NCCL, std::string("ncclCommInitRank: ") + api.GetErrorString(rc));
+    gbp_world_destroy(w);
+    return nullptr;
+  }
+  return w;
+}
+
+int gbp_world_create_local_shards(const gbp_config_t *cfg, int32_t device, int32_t world_size, gbp_world_t **out) {
+  if (!out || world_size < 1 || world_size > gbp::kMaxShards)
+    return fail(GBP_ERR_BAD_ARGUMENT, "gbp_world_create_local_shards: need 1 <= world_size <= 16");
+  gbp_group *g = new gbp_group();
+  g->ws = world_size;
+  g->committed = world_size == 1;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&g->shared_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete g;
+    return fail(GBP_ERR_CUDA, "gbp_world_create_local_shards: no usable CUDA device (this engine has no CPU path)");
+  }
+  for (int r = 0; r < world_size; ++r) {
+    gbp_world *w = make_world(cfg, device, g->shared_stream);
+    if (!w) {
+      for (int k = 0; k < r; ++k) gbp_world_destroy(out[k]);
+      if (r == 0) {
+        cudaStreamDestroy(g->shared_stream);
+        delete g;
+      }
+      return GBP_ERR_CUDA;
+    }
+    join_group(w, g, r);
+    out[r] = w;
+  }
+  return 0;
 }
 
 void gbp_world_destroy(gbp_world_t *w) {
@@ -650,17 +1320,17 @@ void gbp_world_destroy(gbp_world_t *w) {
   cudaSetDevice(w->device);
   cudaStreamSynchronize(w->stream);
   Store &s = w->s;
+  free_edge_set(w, &w->edges[0]);
+  free_edge_set(w, &w->edges[1]);
   void *ptrs[] = {s.prior_eta, s.prior_lam, s.pub[0], s.pub[1], s.pub_epoch[0], s.pub_epoch[1], s.bel_ext,
                   s.mu_ext, s.cov, s.valid, s.m_dynL, s.m_dynR, s.m_obs, s.m_trk, s.dyn_dt,
                   s.trk_record, s.trk_timeout, s.trk_last, s.trk_value, s.radius, s.t0, s.pos, s.antenna,
                   s.idle, s.finished, s.latest, s.iter_factor, s.gid, s.next_wp, s.wp_off, s.wp_xy, s.eoff,
-                  s.nlow, w->edges[0].enbr, w->edges[0].e_dsafe, w->edges[0].e_rnum, w->edges[0].e_birth,
-                  w->edges[0].e_frozen, w->edges[0].mir, w->edges[0].map, w->edges[0].mu_frozen, w->edges[1].enbr,
-                  w->edges[1].e_dsafe, w->edges[1].e_rnum, w->edges[1].e_birth, w->edges[1].e_frozen,
-                  w->edges[1].mir, w->edges[1].map, w->edges[1].mu_frozen,
-                  w->t_nlow, w->t_result_dev, w->sdf_dev, w->t_cx,
+                  s.nlow, w->t_nlow, w->t_result_dev, w->sdf_dev, w->t_cx,
                   w->t_cz, w->t_idx, w->t_idx_sorted, w->t_keys, w->t_keys_sorted, w->t_cnt, w->t_off,
-                  w->t_newcnt, w->t_newoff, w->t_cub, w->rb_dev};
+                  w->t_newcnt, w->t_newoff, w->t_cub, w->rb_dev, w->gpos, w->t_gflag, w->t_gslot, w->t_sflag,
+                  w->t_soff, w->t_ccnt, w->t_coff, w->t_err, w->sendlist, w->ckeys_s, w->cvals_s, w->ckeys_r,
+                  w->cvals_r, w->hdr_send, w->hdr_recv, w->halo_send, w->halo_recv};
   for (void *q : ptrs) cudaFree(q);
   for (auto &sp : w->spans) {
     cudaEventDestroy(sp.a);
@@ -669,10 +1339,35 @@ void gbp_world_destroy(gbp_world_t *w) {
   for (cudaEvent_t e : w->ev_pool) cudaEventDestroy(e);
   cudaEventDestroy(w->ev0);
   cudaEventDestroy(w->ev1);
-  cudaStreamDestroy(w->stream);
+  if (w->owns_stream) cudaStreamDestroy(w->stream);
   if (w->t_result_host) cudaFreeHost(w->t_result_host);
+  if (w->hdr_host) cudaFreeHost(w->hdr_host);
+  if (gbp_group *g = w->grp) {
+    g->members.erase(std::remove(g->members.begin(), g->members.end(), w), g->members.end());
+    if (--g->refs == 0) {
+      if (g->comm) gbp::nccl_api().CommDestroy(g->comm);
+      if (g->shared_stream) cudaStreamDestroy(g->shared_stream);
+      delete g;
+    }
+  }
   delete w;
 }
+
+int gbp_world_commit_shards(gbp_world_t *w) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  gbp_group *g = w->grp;
+  if (g->ws == 1) return 0;
+  if (!g->nccl && int(g->members.size()) != g->ws)
+    return fail(GBP_ERR_STATE, "local shard group: a member has been destroyed");
+  return group_commit(g);
+}
+
+int64_t gbp_world_first_global_id(const gbp_world_t *w) { return w ? w->sh.gfirst[w->sh.rank] : 0; }
+int64_t gbp_world_num_robots_global(const gbp_world_t *w) {
+  if (!w) return 0;
+  return w->sh.ws == 1 ? w->s.Nloc : w->Ntot;
+}
+int32_t gbp_world_num_ghosts(const gbp_world_t *w) { return w ? w->nghost : 0; }
 
 int gbp_world_set_sdf(gbp_world_t *w, const uint8_t *rgb8, int32_t width, int32_t height) {
   if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
@@ -706,39 +1401,13 @@ int gbp_world_add_robots(gbp_world_t *w, int32_t n, const float *radii, const ui
     return fail(GBP_ERR_BAD_ARGUMENT, "gbp_world_add_robots: variable_timesteps differ from the world's");
   w->timesteps.assign(timesteps, timesteps + V);
   cudaStream_t st = w->stream;
-  const int64_t N0 = s.N, N1 = int64_t(s.N) + n, oldNV = s.NV, newNV = N1 * V, used = N0 * V;
-  const int64_t oldcap = s.cap;
-  // ---- re-stride every plane to the new capacity
-  CK(regrow(s.prior_eta, 4, oldNV, newNV, used, st));
-  CK(regrow(s.prior_lam, 1, oldNV, newNV, used, st));
-  CK(regrow(s.pub[0], gbp::kRec, oldNV, newNV, used, st));
-  CK(regrow(s.pub[1], gbp::kRec, oldNV, newNV, used, st));
-  CK(regrow(s.pub_epoch[0], 1, oldNV, newNV, used, st));
-  CK(regrow(s.pub_epoch[1], 1, oldNV, newNV, used, st));
-  CK(regrow(s.bel_ext, gbp::kRec, oldNV, newNV, used, st));
-  CK(regrow(s.mu_ext, 2, oldNV, newNV, used, st));
-  CK(regrow(s.cov, 16, oldNV, newNV, used, st));
-  CK(regrow(s.valid, 1, oldNV, newNV, used, st));
-  CK(regrow(s.m_dynL, 20, oldNV, newNV, used, st));
-  CK(regrow(s.m_dynR, 20, oldNV, newNV, used, st));
-  CK(regrow(s.m_obs, 4, oldNV, newNV, used, st));
-  CK(regrow(s.m_trk, 3, oldNV, newNV, used, st));
-  CK(regrow(s.dyn_dt, 1, oldNV, newNV, used, st));
-  CK(regrow(s.trk_record, 1, oldNV, newNV, used, st));
-  CK(regrow(s.trk_timeout, 1, oldNV, newNV, used, st));
-  CK(regrow(s.trk_last, 2, oldNV, newNV, used, st));
-  CK(regrow(s.trk_value, 1, oldNV, newNV, used, st));
-  CK(regrow(s.radius, 1, oldcap, N1, N0, st));
-  CK(regrow(s.t0, 1, oldcap, N1, N0, st));
-  CK(regrow(s.pos, 2, oldcap, N1, N0, st));
-  CK(regrow(s.antenna, 1, oldcap, N1, N0, st));
-  CK(regrow(s.idle, 1, oldcap, N1, N0, st));
-  CK(regrow(s.finished, 1, oldcap, N1, N0, st));
-  CK(regrow(s.latest, 1, oldcap, N1, N0, st));
-  CK(regrow(s.iter_factor, 1, oldcap, N1, N0, st));
-  CK(regrow(s.gid, 1, oldcap, N1, N0, st));
-  CK(regrow(s.next_wp, 1, oldcap, N1, N0, st));
-  {  // eoff / nlow: new robots start without edges
+  if (w->sh.ws > 1 && w->grp->committed)
+    return fail(GBP_ERR_STATE, "gbp_world_add_robots: a sharded world takes robots only before gbp_world_commit_shards "
+                               "(global ids are contiguous per shard)");
+  const int64_t N0 = s.Nloc, N1 = int64_t(s.Nloc) + n;
+  if (int rc = reserve_robots(w, N1)) return rc;
+  const int64_t newNV = s.NV, used = N0 * V;
+  {  // eoff: new robots start without edges
     int64_t *eoff = nullptr;
     CK(dalloc(eoff, N1 + 1));
     std::vector<int64_t> h(size_t(N1) + 1, s.E);
@@ -748,12 +1417,16 @@ int gbp_world_add_robots(gbp_world_t *w, int32_t n, const float *radii, const ui
     CK(cudaMemcpy(eoff, h.data(), h.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
     cudaFree(s.eoff);
     s.eoff = eoff;
-    CK(regrow(s.nlow, 1, oldcap, N1, N0, st));
   }
-  s.NV = newNV;
-  s.cap = N1;
+  CK(cudaMemsetAsync(s.idle + N0, 0, size_t(n), st));
+  CK(cudaMemsetAsync(s.finished + N0, 0, size_t(n), st));
+  CK(cudaMemsetAsync(s.latest + N0, 0, size_t(n), st));
+  CK(cudaMemsetAsync(s.iter_factor + N0, 0, size_t(n) * sizeof(uint32_t), st));
+  CK(cudaMemsetAsync(s.nlow + N0, 0, size_t(n) * sizeof(int32_t), st));
   s.N = int32_t(N1);
   s.Nloc = int32_t(N1);
+  const int64_t N1cap = s.cap;
+  mark_halo_stale(w);
 
   // ---- host staging of the new robots (RobotBundle::new, robot.rs:1134-1355)
   const int64_t nv = int64_t(n) * V;
@@ -777,12 +1450,12 @@ int gbp_world_add_robots(gbp_world_t *w, int32_t n, const float *radii, const ui
   CK(upload_planes(s.pub[w->p] + 20 * newNV, newNV, used, mu.data(), 4, nv, st));
   CK(upload_planes(s.prior_lam, newNV, used, pl.data(), 1, nv, st));
   CK(upload_planes(s.dyn_dt, newNV, used, dt.data(), 1, nv, st));
-  CK(upload_planes(s.radius, N1, N0, rad.data(), 1, n, st));
-  CK(upload_planes(s.t0, N1, N0, t0.data(), 1, n, st));
-  CK(upload_planes(s.pos, N1, N0, pos.data(), 2, n, st));
-  CK(upload_planes(s.antenna, N1, N0, ones.data(), 1, n, st));
-  CK(upload_planes(s.gid, N1, N0, gid.data(), 1, n, st));
-  CK(upload_planes(s.next_wp, N1, N0, nwp.data(), 1, n, st));
+  CK(upload_planes(s.radius, N1cap, N0, rad.data(), 1, n, st));
+  CK(upload_planes(s.t0, N1cap, N0, t0.data(), 1, n, st));
+  CK(upload_planes(s.pos, N1cap, N0, pos.data(), 2, n, st));
+  CK(upload_planes(s.antenna, N1cap, N0, ones.data(), 1, n, st));
+  CK(upload_planes(s.gid, N1cap, N0, gid.data(), 1, n, st));
+  CK(upload_planes(s.next_wp, N1cap, N0, nwp.data(), 1, n, st));
   // waypoint polylines (CSR, rebuilt whole)
   const int32_t base = w->wp_off.back();
   for (int r = 0; r < n; ++r) w->wp_off.push_back(base + (wp_offsets[r + 1] - wp_offsets[0]));
@@ -806,67 +1479,7 @@ int32_t gbp_world_num_robots(const gbp_world_t *w) { return w ? w->s.Nloc : 0; }
 int gbp_world_update_topology(gbp_world_t *w) {
   if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
   if (set_device(w)) return GBP_ERR_CUDA;
-  Store &s = w->s;
-  const int32_t n = s.Nloc;
-  if (n == 0) return 0;
-  cudaStream_t st = w->stream;
-  if (int rc = ensure_topology_scratch(w, n)) return rc;
-  ProfileScope ps(w, GBP_PROFILE_TOPOLOGY);
-  const int T = 128;
-  const float R = w->cfg.comms_radius;
-  const double cell = double(R) * 1.001;
-  gbp::k_cell_keys<<<blocks_for(n, T), T, 0, st>>>(n, s.pos, s.pos + s.cap, cell, w->t_cx, w->t_cz, w->t_keys, w->t_idx);
-  size_t cb = w->t_cub_bytes;
-  CK(cub::DeviceRadixSort::SortPairs(w->t_cub, cb, w->t_keys, w->t_keys_sorted, w->t_idx, w->t_idx_sorted, n, 0, 32, st));
-  gbp::k_neighbours<false><<<blocks_for(n, T), T, 0, st>>>(n, 0, n, s.pos, s.pos + s.cap, w->t_cx, w->t_cz,
-                                                           w->t_keys_sorted, w->t_idx_sorted, R, w->t_cnt, nullptr, 0);
-  CK(cudaMemsetAsync(w->t_cnt + n, 0, sizeof(int64_t), st));
-  cb = w->t_cub_bytes;
-  CK(cub::DeviceScan::ExclusiveSum(w->t_cub, cb, w->t_cnt, w->t_off, n + 1, st));
-  w->launches += 4;
-  // The new CSR is written straight into the spare edge set; one host sync per
-  // tick reads (edge count, new edge count).  If the spare set is too small the
-  // guarded kernels did nothing: grow it and run them again.
-  EdgeSet *spare = &w->edges[1 - w->cur];
-  int64_t E1 = 0, total_new = 0;
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    gbp::k_neighbours<true><<<blocks_for(n, T), T, 0, st>>>(n, 0, n, s.pos, s.pos + s.cap, w->t_cx, w->t_cz,
-                                                            w->t_keys_sorted, w->t_idx_sorted, R, w->t_off,
-                                                            spare->enbr, spare->cap);
-    gbp::k_edge_diff<<<blocks_for(n, T), T, 0, st>>>(n, w->t_off, spare->enbr, s.eoff, s.enbr, n, spare->map,
-                                                     w->t_newcnt, w->t_nlow, spare->cap);
-    CK(cudaMemsetAsync(w->t_newcnt + n, 0, sizeof(int64_t), st));
-    cb = w->t_cub_bytes;
-    CK(cub::DeviceScan::ExclusiveSum(w->t_cub, cb, w->t_newcnt, w->t_newoff, n + 1, st));
-    gbp::k_topology_result<<<1, 1, 0, st>>>(w->t_off, w->t_newoff, n, w->t_result_dev);
-    CK(cudaMemcpyAsync(w->t_result_host, w->t_result_dev, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    w->launches += 4;
-    E1 = w->t_result_host[0];
-    total_new = w->t_result_host[1];
-    if (E1 <= spare->cap) break;
-    if (int rc = grow_edge_set(w, spare, E1 + E1 / 4 + 1024)) return rc;
-  }
-  if (total_new == 0 && E1 == s.E) return 0;  // connectivity unchanged: keep the store as is
-  w->epoch += 1;
-  const int Vm1 = s.V - 1;
-  gbp::k_edge_assign<<<blocks_for(n, T), T, 0, st>>>(n, s.V, w->t_off, spare->enbr, spare->map, w->t_newoff, s.radius,
-                                                     double(w->cfg.safety_distance_multiplier), w->robot_number,
-                                                     w->epoch, s.e_dsafe, s.e_rnum, s.e_birth, s.e_frozen,
-                                                     spare->e_dsafe, spare->e_rnum, spare->e_birth, spare->e_frozen);
-  if (E1 > 0)
-    gbp::k_mirror_move<<<blocks_for(E1 * Vm1, 256), 256, 0, st>>>(s, w->p, E1 * Vm1, Vm1, w->t_off, spare->map, s.mir,
-                                                                  s.mu_frozen, s.EV, spare->mir, spare->mu_frozen,
-                                                                  spare->cap * Vm1);
-  CK(cudaGetLastError());
-  w->launches += 3;
-  CK(cudaMemcpyAsync(s.eoff, w->t_off, size_t(n + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
-  CK(cudaMemcpyAsync(s.nlow, w->t_nlow, size_t(n) * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-  w->cur = 1 - w->cur;
-  bind_edge_set(w);
-  s.E = E1;
-  w->robot_number += uint64_t(Vm1) * uint64_t(total_new);
-  return 0;
+  return group_update_topology(w->grp);
 }
 
 int gbp_world_set_comms(gbp_world_t *w, const uint8_t *antenna_active, const uint8_t *idle) {
@@ -879,6 +1492,7 @@ int gbp_world_set_comms(gbp_world_t *w, const uint8_t *antenna_active, const uin
   if (idle) CK(cudaMemcpyAsync(w->s.idle, idle, n, cudaMemcpyHostToDevice, w->stream));
   else CK(cudaMemsetAsync(w->s.idle, 0, n, w->stream));
   CK(cudaStreamSynchronize(w->stream));
+  mark_halo_stale(w);  // antenna / idle bits travel with the halo
   return 0;
 }
 
@@ -891,28 +1505,35 @@ int gbp_world_set_waypoint_index(gbp_world_t *w, const int32_t *next_index) {
   return 0;
 }
 
-int gbp_world_update_prior_of_horizon_state(gbp_world_t *w) {
-  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
-  if (set_device(w)) return GBP_ERR_CUDA;
-  if (w->s.Nloc == 0) return 0;
-  w->epoch += 1;
-  ProfileScope ps(w, GBP_PROFILE_PRIORS);
-  k_prior_horizon<<<blocks_for(w->s.Nloc, 128), 128, 0, w->stream>>>(
-      w->s, w->p, w->epoch, double(w->cfg.delta_t), double(w->cfg.target_speed), w->cfg.iterations_internal);
-  CK(cudaGetLastError());
-  w->launches += 1;
+// Both prior updates run for every shard of the group living in this process.
+int gbp_world_update_prior_of_horizon_state(gbp_world_t *w0) {
+  if (!w0) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  for (gbp_world *w : w0->grp->members) {
+    if (set_device(w)) return GBP_ERR_CUDA;
+    w->epoch += 1;
+    if (w->s.Nloc == 0) continue;
+    ProfileScope ps(w, GBP_PROFILE_PRIORS);
+    k_prior_horizon<<<blocks_for(w->s.Nloc, 128), 128, 0, w->stream>>>(
+        w->s, w->p, w->epoch, double(w->cfg.delta_t), double(w->cfg.target_speed), w->cfg.iterations_internal);
+    CK(cudaGetLastError());
+    w->launches += 1;
+  }
+  w0->grp->halo_stale = true;
   return 0;
 }
 
-int gbp_world_update_prior_of_current_state(gbp_world_t *w) {
-  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
-  if (set_device(w)) return GBP_ERR_CUDA;
-  if (w->s.Nloc == 0) return 0;
-  w->epoch += 1;
-  ProfileScope ps(w, GBP_PROFILE_PRIORS);
-  k_prior_current<<<blocks_for(w->s.Nloc, 128), 128, 0, w->stream>>>(w->s, w->p, w->epoch, w->cfg.delta_t);
-  CK(cudaGetLastError());
-  w->launches += 1;
+int gbp_world_update_prior_of_current_state(gbp_world_t *w0) {
+  if (!w0) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  for (gbp_world *w : w0->grp->members) {
+    if (set_device(w)) return GBP_ERR_CUDA;
+    w->epoch += 1;
+    if (w->s.Nloc == 0) continue;
+    ProfileScope ps(w, GBP_PROFILE_PRIORS);
+    k_prior_current<<<blocks_for(w->s.Nloc, 128), 128, 0, w->stream>>>(w->s, w->p, w->epoch, w->cfg.delta_t);
+    CK(cudaGetLastError());
+    w->launches += 1;
+  }
+  w0->grp->halo_stale = true;
   return 0;
 }
 
@@ -938,6 +1559,7 @@ int gbp_world_change_prior_of_variable(gbp_world_t *w, int32_t var, int32_t m, c
   CK(cudaStreamSynchronize(w->stream));
   cudaFree(dr);
   cudaFree(dm);
+  mark_halo_stale(w);
   return 0;
 }
 
@@ -947,7 +1569,7 @@ int gbp_world_iterate_schedule(gbp_world_t *w, int32_t n, const uint8_t *interna
   if (w->pending_internal_factor || w->pending_external_factor)
     return fail(GBP_ERR_STATE, "a half-iteration pair is open");
   if (set_device(w)) return GBP_ERR_CUDA;
-  return run_schedule(w, n, internal, external);
+  return run_schedule(w->grp, n, internal, external);
 }
 
 int gbp_world_iterate(gbp_world_t *w) {
@@ -971,7 +1593,7 @@ int gbp_world_internal_variable_iteration(gbp_world_t *w) {
   if (!w->pending_internal_factor) return fail(GBP_ERR_STATE, "internal_variable_iteration without internal_factor_iteration");
   w->pending_internal_factor = false;
   if (set_device(w)) return GBP_ERR_CUDA;
-  return launch_iterate<false, true>(w);
+  return group_launch<false, true>(w->grp);
 }
 int gbp_world_external_factor_iteration(gbp_world_t *w) {
   if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
@@ -984,7 +1606,7 @@ int gbp_world_external_variable_iteration(gbp_world_t *w) {
   if (!w->pending_external_factor) return fail(GBP_ERR_STATE, "external_variable_iteration without external_factor_iteration");
   w->pending_external_factor = false;
   if (set_device(w)) return GBP_ERR_CUDA;
-  return launch_iterate<true, false>(w);
+  return group_launch<true, false>(w->grp);
 }
 
 int gbp_world_step(gbp_world_t *w) {
@@ -1079,29 +1701,22 @@ int64_t gbp_world_read_connections(gbp_world_t *w, int64_t *offsets, int32_t *ne
   const Store &s = w->s;
   if (s.E > capacity) return fail(GBP_ERR_BAD_ARGUMENT, "capacity too small");
   CK(cudaStreamSynchronize(w->stream));
+  if (w->t_err) {
+    int32_t err = 0;
+    CK(cudaMemcpy(&err, w->t_err, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (err) return fail(GBP_ERR_STATE, "robot_number lookup failed during the last topology update");
+  }
   if (s.Nloc == 0) {
     offsets[0] = 0;
     return 0;
   }
   CK(cudaMemcpy(offsets, s.eoff, size_t(s.Nloc + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
   if (s.E > 0) {
-    if (neighbours) CK(cudaMemcpy(neighbours, s.enbr, size_t(s.E) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    const gbp_world::EdgeSet &e = w->edges[w->cur];
+    if (neighbours) CK(cudaMemcpy(neighbours, e.egid, size_t(s.E) * sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (robot_number) {
-      // the store keeps, per (receiver r <- a), the number of a's factor toward r;
-      // the ABI reports per (owner r -> a): swap through the symmetric edge
-      std::vector<int32_t> nb(s.E);
-      std::vector<uint64_t> rn(s.E);
-      std::vector<int64_t> off(size_t(s.Nloc) + 1);
-      CK(cudaMemcpy(nb.data(), s.enbr, size_t(s.E) * sizeof(int32_t), cudaMemcpyDeviceToHost));
-      CK(cudaMemcpy(rn.data(), s.e_rnum, size_t(s.E) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-      CK(cudaMemcpy(off.data(), s.eoff, off.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
-      for (int32_t r = 0; r < s.Nloc; ++r)
-        for (int64_t e = off[r]; e < off[r + 1]; ++e) {
-          const int32_t a = nb[e];
-          const int32_t *lo = nb.data() + off[a], *hi = nb.data() + off[a + 1];
-          const int32_t *it = std::lower_bound(lo, hi, r);
-          robot_number[e] = (it != hi && *it == r) ? int64_t(rn[it - nb.data()]) : -1;
-        }
+      static_assert(sizeof(int64_t) == sizeof(uint64_t), "");
+      CK(cudaMemcpy(robot_number, e.e_own, size_t(s.E) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     }
   }
   return s.E;

@@ -10,7 +10,10 @@
 //      fill; each robot's list is sorted by robot id (BTreeSet order)
 //   4. diff against the previous CSR: surviving edges keep their state, new
 //      edges get robot_number in the reference's creation order (robots in id
-//      order -> new neighbours ascending -> i = 1..V-1, robot.rs:1500-1541).
+//      order -> new neighbours ascending -> i = 1..V-1, robot.rs:1500-1541);
+//      the assignment kernels live in gbp_shard.cuh because the order is global
+//      across shards.
+// Neighbour lists hold GLOBAL robot ids; on a single GPU id == slot.
 // Connectivity, ordering and robot_number are bit-exact; nothing is approximate.
 #pragma once
 #include <cstdint>
@@ -104,12 +107,14 @@ __global__ void k_neighbours(int32_t nall, int32_t first, int32_t count, const f
   }
 }
 
-// For every robot r in [0, n): match its new neighbour list against the old one.
+// For every own robot r in [0, n) (global id g0 + r): match its new neighbour list against
+// the old one; both hold GLOBAL ids in ascending order.
 //   map[e]    old edge index of new edge e, or -1 when the edge is new
 //   newcnt[r] number of new edges of r, nlow[r] neighbours with a lower id
-__global__ void k_edge_diff(int32_t n, const int64_t *__restrict__ noff, const int32_t *__restrict__ nnbr,
-                            const int64_t *__restrict__ ooff, const int32_t *__restrict__ onbr,
-                            int32_t n_old, int64_t *map, int64_t *newcnt, int32_t *nlow, int64_t cap) {
+__global__ void k_edge_diff(int32_t n, int32_t g0, const int64_t *__restrict__ noff,
+                            const int32_t *__restrict__ nnbr, const int64_t *__restrict__ ooff,
+                            const int32_t *__restrict__ onbr, int32_t n_old, int64_t *map, int64_t *newcnt,
+                            int32_t *nlow, int64_t cap) {
   const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   if (noff[n] > cap) {
@@ -125,7 +130,7 @@ __global__ void k_edge_diff(int32_t n, const int64_t *__restrict__ noff, const i
   int32_t low = 0;
   for (int64_t e = noff[r]; e < noff[r + 1]; ++e) {
     const int32_t a = nnbr[e];
-    if (a < r) ++low;
+    if (a < g0 + r) ++low;
     int64_t lo = lo0, hi = hi0;
     while (lo < hi) {
       const int64_t mid = (lo + hi) >> 1;
@@ -138,42 +143,6 @@ __global__ void k_edge_diff(int32_t n, const int64_t *__restrict__ noff, const i
   }
   newcnt[r] = fresh;
   nlow[r] = low;
-}
-
-// Per new-CSR edge (r <- a): carry over or initialise the edge scalars.
-// robot_number of a's factor toward r at i=1 = counter0 + (V-1) * (rank of the
-// directed pair (a, r) among all new pairs ordered by (a, r)).
-__global__ void k_edge_assign(int32_t n, int32_t V, const int64_t *__restrict__ noff,
-                              const int32_t *__restrict__ nnbr, const int64_t *__restrict__ map,
-                              const int64_t *__restrict__ newoff, const float *__restrict__ radius,
-                              double safety_mult, uint64_t counter0, uint32_t epoch,
-                              const double *__restrict__ o_dsafe, const uint64_t *__restrict__ o_rnum,
-                              const uint32_t *__restrict__ o_birth, const uint8_t *__restrict__ o_frozen,
-                              double *e_dsafe, uint64_t *e_rnum, uint32_t *e_birth, uint8_t *e_frozen) {
-  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
-  for (int64_t e = noff[r]; e < noff[r + 1]; ++e) {
-    const int32_t a = nnbr[e];
-    const int64_t old = map[e];
-    e_dsafe[e] = safety_mult * double(radius[a]);
-    if (old >= 0) {
-      e_rnum[e] = o_rnum[old];
-      e_birth[e] = o_birth[old];
-      e_frozen[e] = o_frozen[old];
-    } else {
-      int64_t rank = 0;
-      for (int64_t e2 = noff[a]; e2 < noff[a + 1]; ++e2)
-        if (map[e2] < 0 && nnbr[e2] < r) ++rank;
-      e_rnum[e] = counter0 + uint64_t(V - 1) * uint64_t(newoff[a] + rank);
-      e_birth[e] = epoch;
-      e_frozen[e] = 1;  // the factor holds the receiver's belief at creation time
-    }
-  }
-}
-
-__global__ void k_topology_result(const int64_t *noff, const int64_t *newoff, int32_t n, int64_t *out) {
-  out[0] = noff[n];
-  out[1] = newoff[n];
 }
 
 // Mirror messages (and frozen means) of surviving edges move to their new slot.

@@ -156,21 +156,24 @@ def rings(n=100_000, spacing=8.0, ring_gap=44.0, r0=400.0, cfg: GbpConfig | None
 
 
 def lattice(nx=1000, ny=1000, pitch=12.0, cfg: GbpConfig | None = None, planning_horizon=5.0, lookahead_multiple=3,
-            robot_radius=1.0, goal_ahead=500.0):
+            robot_radius=1.0, goal_ahead=500.0, rows: tuple[int, int] | None = None):
     """Config 5: uniform grid, every interior robot has K = 8 at comms radius 20
     (4 at `pitch`, 4 at pitch*sqrt(2)); all head +x toward a goal 500 m ahead.
-    Robot id = row-major (iy * nx + ix) so vertical slabs / rows are contiguous."""
+    Robot id = row-major (iy * nx + ix), so a contiguous id range is a horizontal slab of rows.
+    `rows=(lo, hi)` builds only the robots of rows [lo, hi) of the same global lattice (what one
+    rank of a multi-GPU run owns), bit-identical to the corresponding slice of the whole."""
     cfg = cfg or GbpConfig(target_speed=3.6, world_width=100.0, world_height=100.0)
     ts = get_variable_timesteps(lookahead_horizon(cfg.target_speed, planning_horizon), lookahead_multiple)
     cfg = replace(cfg, num_variables=int(ts.shape[0]))
-    ix, iy = np.meshgrid(np.arange(nx), np.arange(ny))
+    r0, r1 = (0, ny) if rows is None else rows
+    ix, iy = np.meshgrid(np.arange(nx), np.arange(r0, r1))
     x = (ix.reshape(-1) - (nx - 1) / 2.0) * pitch
     y = (iy.reshape(-1) - (ny - 1) / 2.0) * pitch
     starts = np.stack([x, y], axis=1).astype(f32)
     goals = (starts + np.array([goal_ahead, 0.0], f32)).astype(f32)
-    n = nx * ny
+    n = nx * (r1 - r0)
     return _finish(cfg, np.full(n, robot_radius, f32), starts, goals, ts, planning_horizon, sdf=white_sdf(),
-                   name=f"lattice-{nx}x{ny}", meta={"nx": nx, "ny": ny, "pitch": pitch})
+                   name=f"lattice-{nx}x{ny}", meta={"nx": nx, "ny": ny, "pitch": pitch, "rows": (r0, r1)})
 
 
 def junction_twoway(per_lane=3, seed=0):

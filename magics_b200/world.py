@@ -50,6 +50,14 @@ def load_library() -> C.CDLL:
     lib.gbp_host_alloc_pinned.restype = C.c_void_p
     lib.gbp_host_alloc_pinned.argtypes = [C.c_size_t]
     lib.gbp_host_free_pinned.argtypes = [C.c_void_p]
+    lib.gbp_world_create_shard.restype = C.c_void_p
+    lib.gbp_world_create_shard.argtypes = [C.POINTER(CConfig), C.c_int32, C.c_int32, C.c_int32, C.c_char_p]
+    lib.gbp_world_create_local_shards.argtypes = [C.POINTER(CConfig), C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+    lib.gbp_world_first_global_id.restype = C.c_int64
+    lib.gbp_world_first_global_id.argtypes = [C.c_void_p]
+    lib.gbp_world_num_robots_global.restype = C.c_int64
+    lib.gbp_world_num_robots_global.argtypes = [C.c_void_p]
+    lib.gbp_world_num_ghosts.argtypes = [C.c_void_p]
     _LIB = lib
     return lib
 
@@ -95,17 +103,67 @@ def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
     return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
 
 
-class World:
-    """All robots' factor graphs on one B200 (device store + fused kernels)."""
+COMM_ID_BYTES = 128
 
-    def __init__(self, cfg: GbpConfig, device: int = 0):
+
+def comm_unique_id() -> bytes:
+    """gbp_comm_unique_id: the NCCL communicator id rank 0 hands to every rank (any transport)."""
+    lib = load_library()
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    rc = lib.gbp_comm_unique_id(buf)
+    if rc < 0:
+        raise RuntimeError("gbp_comm_unique_id failed: " + lib.gbp_last_error().decode())
+    return buf.raw
+
+
+class World:
+    """All robots' factor graphs on one B200 (device store + fused kernels), or one shard of a
+    swarm partitioned over several B200s (`World.create_shard`, one process per GPU)."""
+
+    def __init__(self, cfg: GbpConfig, device: int = 0, _handle=None):
         self._lib = load_library()
         self.cfg = cfg
         self.V = int(cfg.num_variables)
         self._c = cfg.to_c()
-        self._h = self._lib.gbp_world_create(C.byref(self._c), int(device))
+        self._h = _handle if _handle is not None else self._lib.gbp_world_create(C.byref(self._c), int(device))
         if not self._h:
             raise RuntimeError("gbp_world_create failed: " + self._lib.gbp_last_error().decode())
+
+    @classmethod
+    def create_shard(cls, cfg: GbpConfig, device: int, rank: int, world_size: int, comm_id: bytes | None):
+        """gbp_world_create_shard: this process' shard; NCCL send/recv is the transport."""
+        lib = load_library()
+        c = cfg.to_c()
+        h = lib.gbp_world_create_shard(C.byref(c), int(device), int(rank), int(world_size), comm_id)
+        if not h:
+            raise RuntimeError("gbp_world_create_shard failed: " + lib.gbp_last_error().decode())
+        return cls(cfg, device, _handle=h)
+
+    @classmethod
+    def create_local_shards(cls, cfg: GbpConfig, world_size: int, device: int = 0):
+        """gbp_world_create_local_shards: every shard in this process on one device."""
+        lib = load_library()
+        c = cfg.to_c()
+        out = (C.c_void_p * world_size)()
+        rc = lib.gbp_world_create_local_shards(C.byref(c), int(device), int(world_size), out)
+        if rc < 0:
+            raise RuntimeError("gbp_world_create_local_shards failed: " + lib.gbp_last_error().decode())
+        return [cls(cfg, device, _handle=out[r]) for r in range(world_size)]
+
+    def commit_shards(self):
+        self._call("gbp_world_commit_shards")
+
+    @property
+    def first_global_id(self) -> int:
+        return int(self._lib.gbp_world_first_global_id(C.c_void_p(self._h)))
+
+    @property
+    def num_robots_global(self) -> int:
+        return int(self._lib.gbp_world_num_robots_global(C.c_void_p(self._h)))
+
+    @property
+    def num_ghosts(self) -> int:
+        return int(self._lib.gbp_world_num_ghosts(C.c_void_p(self._h)))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -270,7 +328,7 @@ class World:
         self._call("gbp_world_node_counts", _p(out, C.c_int64))
         return out
 
-    PROFILE_KINDS = ("iterate_int", "iterate_ext", "iterate_ext_int", "topology", "priors")
+    PROFILE_KINDS = ("iterate_int", "iterate_ext", "iterate_ext_int", "topology", "priors", "halo")
 
     def set_profiling(self, on: bool):
         self._call("gbp_world_set_profiling", C.c_int32(int(on)))
