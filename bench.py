@@ -152,6 +152,16 @@ def run_cpu(sw, threads: int, ticks: int):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything else a library prints there (NCCL's version
+    # banner under NCCL_DEBUG, torchrun notices) is sent to stderr while the benchmark runs.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: dict):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -209,7 +219,7 @@ def main():
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -347,7 +357,7 @@ def main():
                             "all variable means device -> pinned host; max(CUDA events, wall clock), max over ranks"},
             "roofline": roof, "cpu_baseline": cpu, "profile_ms": prof,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
