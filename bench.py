@@ -212,7 +212,7 @@ def main():
         line = {
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": secs * 1e3 / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload}-{args.robots}: V={int(sw.cfg.num_variables)}, "
                                    "dyn+obstacle+interrobot factors, interleave-evenly 10/10; CPU arm runs the "
                                    f"bounded sample {sw.name}"},

@@ -409,6 +409,7 @@ struct gbp_world {
   // ---- sharding (gbp_shard.cuh) ------------------------------------------------------
   gbp_group *grp = nullptr;
   bool owns_stream = true;
+  bool smem_opted_in[4] = {false, false, false, false};  // k_iterate<EXT,INT> dynamic shared memory opt-in
   gbp::ShardInfo sh{};          // ws, rank, gfirst
   int32_t Ntot = 0;             // robots of the whole swarm
   int32_t nghost = 0;
@@ -611,6 +612,14 @@ int group_halo(gbp_group *g) {
 template <bool EXT, bool INT>
 int launch_iterate(gbp_world *w) {
   Store &s = w->s;
+  bool &smem_opted_in = w->smem_opted_in[(EXT ? 2 : 0) + (INT ? 1 : 0)];
+  if (!smem_opted_in && gbp::kIterSmemBytes > 0) {
+    CK(cudaFuncSetAttribute(gbp::k_iterate<EXT, INT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            int(gbp::kIterSmemBytes)));
+    CK(cudaFuncSetAttribute(gbp::k_iterate<EXT, INT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
+    smem_opted_in = true;
+  }
   w->epoch += 1;  // every shard steps its epoch, with or without robots
   if (s.Nloc == 0) {
     if (INT) w->p ^= 1;
@@ -622,7 +631,7 @@ int launch_iterate(gbp_world *w) {
   const unsigned grid = unsigned((warps + wpb - 1) / wpb);
   {
     ProfileScope ps(w, EXT ? (INT ? GBP_PROFILE_ITERATE_EXT_INT : GBP_PROFILE_ITERATE_EXT) : GBP_PROFILE_ITERATE_INT);
-    gbp::k_iterate<EXT, INT><<<grid, gbp::kIterBlock, 0, w->stream>>>(s, w->p, w->epoch);
+    gbp::k_iterate<EXT, INT><<<grid, gbp::kIterBlock, gbp::kIterSmemBytes, w->stream>>>(s, w->p, w->epoch);
   }
   CK(cudaGetLastError());
   if (w->spans.size() > 4096) {

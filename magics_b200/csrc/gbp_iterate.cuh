@@ -30,9 +30,29 @@
 namespace gbp {
 
 constexpr int kIterBlock = 128;
+constexpr size_t kIterSmemBytes = 0;
 #ifndef GBP_ITER_MIN_BLOCKS
 #define GBP_ITER_MIN_BLOCKS 3
 #endif
+
+// ---- L2 prefetch -----------------------------------------------------------------------------
+// The kernel is a chain of ~16 dependent load phases per thread at 12 warps per SM, so the
+// loaded DRAM latency of each phase is exposed.  A thread knows at entry every address it will
+// read later in its own records, so it asks L2 for them up front: prefetch.global.L2 costs no
+// register and no shared memory, and turns the later own-record phases into L2 hits.  (Measured,
+// profiles/README.md r01d: +5 %; prefetching the neighbours' records as well, staging through
+// shared memory with cp.async, or parking accumulators in shared memory for 16 warps/SM were
+// all slower than this.)
+#ifndef GBP_PREFETCH
+#define GBP_PREFETCH 1
+#endif
+
+GBP_DEV void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+template <int N>
+GBP_DEV void prefetch_planes(const double *base, int64_t stride, int64_t at) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) prefetch_l2(base + k * stride + at);
+}
 
 GBP_DEV double dot2(const double (&a)[2], const double (&b)[2]) { return (0.0 + a[0] * b[0]) + a[1] * b[1]; }
 GBP_DEV double norm2(double x, double y) { return sqrt((0.0 + x * x) + y * y); }
@@ -279,33 +299,55 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
   const int64_t NV = s.NV;
   const int64_t vi = live ? r * V + i : 0;
 
+  const double *const pubr = s.pub[p];
+  double *const pubw = s.pub[1 - p];
+  // One batch of independent loads: the robot's flags and both candidates for the running mean
+  // (VariableBelief.mean survives an update that cannot invert, variable.rs:276-297; it lives in
+  // bel_ext after an external half, else in the published record).
   bool idle = true, ant = false;
+  double mu[4] = {0.0, 0.0, 0.0, 0.0};
+  uint32_t itf = 0u;
+  int64_t eo0 = 0, eo1 = 0;
+  int32_t nlow = 0;
   if (live) {
-    idle = s.idle[r] != 0;
-    ant = s.antenna[r] != 0;
+#if GBP_PREFETCH
+    prefetch_planes<20>(s.m_dynL, NV, vi);
+    prefetch_planes<20>(s.m_dynR, NV, vi);
+    prefetch_planes<4>(s.m_obs, NV, vi);
+    prefetch_planes<3>(s.m_trk, NV, vi);
+    prefetch_planes<4>(s.prior_eta, NV, vi);
+    prefetch_l2(s.prior_lam + vi);
+    if (INT) {
+      prefetch_planes<20>(pubr, NV, vi);
+      prefetch_l2(s.dyn_dt + vi);
+    }
+#endif
+    const uint8_t f_idle = s.idle[r], f_ant = s.antenna[r], f_latest = s.latest[r];
+    itf = s.iter_factor[r];
+    eo0 = s.eoff[r];
+    eo1 = s.eoff[r + 1];
+    nlow = s.nlow[r];
+    double ma[4], mb[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ma[k] = pubr[(20 + k) * NV + vi];
+      mb[k] = s.bel_ext[(20 + k) * NV + vi];
+    }
+    idle = f_idle != 0;
+    ant = f_ant != 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mu[k] = f_latest ? mb[k] : ma[k];
   }
   const bool do_ext = EXT && live && !idle && ant;
   const bool do_int = INT && live && !idle;
-  const double *const pubr = s.pub[p];
-  double *const pubw = s.pub[1 - p];
-
-  // running mean: VariableBelief.mean survives an update that cannot invert
-  // (variable.rs:276-297)
-  double mu[4] = {0.0, 0.0, 0.0, 0.0};
-  if (do_ext || do_int) {
-    const double *rec = s.latest[r] ? s.bel_ext : pubr;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) mu[k] = rec[(20 + k) * NV + vi];
-  }
-  uint32_t itf = live ? s.iter_factor[r] : 0u;
 
   // =================== external half ====================================
   if (do_ext) {
     double ae[4], al[16];
     load_prior(s, vi, ae, al);
-    const int64_t e0 = s.eoff[r];
-    const int64_t e1 = (i >= 1) ? s.eoff[r + 1] : e0;  // variable 0 has no InterRobot factors
-    const int64_t elow = e0 + s.nlow[r];  // edges [e0, elow) have a lower robot id than r
+    const int64_t e0 = eo0;
+    const int64_t e1 = (i >= 1) ? eo1 : e0;  // variable 0 has no InterRobot factors
+    const int64_t elow = e0 + nlow;          // edges [e0, elow) have a lower robot id than r
     double mu_sent[2] = {0.0, 0.0};
     if (e1 > e0) {
       mu_sent[0] = s.mu_ext[vi];
@@ -323,13 +365,7 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
       const int64_t m = e * (V - 1) + (i - 1);
       if (x.act) {
         const bool a_ne = x.epochA > x.birth;
-        double etaA[4], lamA[16], muA[2];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) etaA[k] = a_ne ? x.rec[k] : 0.0;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) lamA[k] = a_ne ? x.rec[4 + k] : 0.0;
-        muA[0] = a_ne ? x.rec[20] : 0.0;
-        muA[1] = a_ne ? x.rec[21] : 0.0;
+        const double muA[2] = {a_ne ? x.rec[20] : 0.0, a_ne ? x.rec[21] : 0.0};
         double mb[2] = {mu_sent[0], mu_sent[1]};
         if (x.frozen) {  // rare: edge just created, or A's radio was off at the last delivery
           mb[0] = s.mu_frozen[m];
@@ -337,7 +373,7 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
         }
         const double tiny = s.tiny_scale * double(x.rnum + uint64_t(i - 1));
         double me[2], ml[4];
-        const bool ok = interrobot_message(e < elow, muA, mb, a_ne, etaA, lamA, x.dsafe, tiny, s.lm_ir, me, ml);
+        const bool ok = interrobot_message(e < elow, muA, mb, a_ne, x.rec, x.dsafe, tiny, s.lm_ir, me, ml);
         if (ok) {
           s.mir[m] = me[0];
           s.mir[s.EV + m] = me[1];
@@ -396,7 +432,7 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
     __syncwarp();
     if (do_ext && i == 1) {
       // delivered edges hold mu_ext again; undelivered ones are (stay) frozen
-      for (int64_t e = s.eoff[r]; e < s.eoff[r + 1]; ++e) {
+      for (int64_t e = eo0; e < eo1; ++e) {
         const int A = s.enbr[e];
         const uint8_t fr = (s.en_ir && s.antenna[A] != 0 && s.idle[A] == 0) ? 0 : 1;
         if (s.e_frozen[e] != fr) s.e_frozen[e] = fr;
@@ -436,12 +472,8 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
       if (s.en_dyn) {
         if (i >= 1) {  // Dynamic factor i-1 -> variable i (slot 1)
           const DynM M = dyn_potential(s.dyn_dt[vi - 1], s.qs_dyn);
-          double oe[4], ol[16], ne[4], nl[16];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) oe[k] = toR[k];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) ol[k] = toR[4 + k];
-          if (dyn_message<1>(M, fromL_ne, oe, ol, ne, nl)) {
+          double ne[4], nl[16];
+          if (dyn_message<1>(M, fromL_ne, toR, ne, nl)) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) s.m_dynL[k * NV + vi] = ne[k];
 #pragma unroll
@@ -452,12 +484,8 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
         }
         if (i <= V - 2) {  // Dynamic factor i -> variable i (slot 0)
           const DynM M = dyn_potential(s.dyn_dt[vi], s.qs_dyn);
-          double oe[4], ol[16], ne[4], nl[16];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) oe[k] = toL[k];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) ol[k] = toL[4 + k];
-          if (dyn_message<0>(M, fromR_ne, oe, ol, ne, nl)) {
+          double ne[4], nl[16];
+          if (dyn_message<0>(M, fromR_ne, toL, ne, nl)) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) s.m_dynR[k * NV + vi] = ne[k];
 #pragma unroll
@@ -485,9 +513,9 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
       // ---- belief update + new record (variable.rs:251-297)
       double ae[4], al[16];
       load_prior(s, vi, ae, al);
-      const int64_t e0 = s.eoff[r];
-      const int64_t e1 = (i >= 1) ? s.eoff[r + 1] : e0;
-      const int64_t elow = e0 + s.nlow[r];
+      const int64_t e0 = eo0;
+      const int64_t e1 = (i >= 1) ? eo1 : e0;
+      const int64_t elow = e0 + nlow;
       bool added = false;
       for (int64_t e = e0; e < e1; ++e) {
         if (!added && e >= elow) {

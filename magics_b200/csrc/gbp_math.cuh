@@ -78,7 +78,9 @@ GBP_DEV void divide_all(const double (&c)[N], double det, double (&o)[N]) {
       o[k] = (c[k] == 0.0) ? q0 : q;
     }
   } else {
-#pragma unroll 1
+    // fully unrolled (N calls of the out-of-line division): a rolled loop would index c/o
+    // dynamically and push both arrays into local memory for EVERY path through this function
+#pragma unroll
     for (int k = 0; k < N; ++k) o[k] = plain_div(c[k], det);
   }
 #endif
@@ -183,10 +185,12 @@ GBP_DEV DynM dyn_potential(double dt, double qs) {
 // KEEP = 0: message to the first variable (slot 0), marginalising slot 1;
 // KEEP = 1: message to the second.  `oe`/`ol` is the OTHER variable's message
 // (eta, Lambda) if `other_nonempty`.  Returns false for Message::empty().
+// `o` = the OTHER variable's message as one record (eta 0..3, Lambda 4..19).
 template <int KEEP>
-GBP_DEV bool dyn_message(const DynM &M, bool other_nonempty, const double (&oe)[4],
-                         const double (&ol)[16], double (&eta)[4], double (&lam)[16]) {
+GBP_DEV bool dyn_message(const DynM &M, bool other_nonempty, const double (&o)[20], double (&eta)[4],
+                         double (&lam)[16]) {
   constexpr int A = KEEP * 2, B = (1 - KEEP) * 2;  // scalar-block offsets in M
+  const double *oe = o, *ol = o + 4;
   // Lambda_bb = potential block + other message; index (kk, dim) -> kk*2 + dim
   double bb[16];
 #pragma unroll
@@ -257,10 +261,12 @@ GBP_DEV void unary_add(const double (&J)[4], double v0, double lm, double (&eta)
 //   a_nonempty whether A's variable message exists (else only the potential)
 //   dsafe      safety distance, tiny the factor's tiny_offset, lm = 1/sigma^2
 // Output: eta[0..1], lam 2x2 (rows/cols 0..1 of the 4x4; the rest is exactly 0).
+// `recA` = A's published record (eta 0..3, Lambda 4..19, position mean 20..21); only read
+// when a_nonempty.
 GBP_DEV bool interrobot_message(bool a_first, const double (&muA)[2], const double (&muB)[2],
-                                bool a_nonempty, const double (&etaA)[4],
-                                const double (&lamA)[16], double dsafe, double tiny, double lm,
-                                double (&eta)[2], double (&lam)[4]) {
+                                bool a_nonempty, const double (&recA)[22], double dsafe, double tiny,
+                                double lm, double (&eta)[2], double (&lam)[4]) {
+  const double *etaA = recA, *lamA = recA + 4;
   const double x0 = a_first ? muA[0] : muB[0], x1 = a_first ? muA[1] : muB[1];
   const double x4 = a_first ? muB[0] : muA[0], x5 = a_first ? muB[1] : muA[1];
   const double e0 = x0 - x4, e1 = x1 - x5;
