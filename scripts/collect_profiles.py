@@ -2,7 +2,7 @@
 """Copy one GPU visit (gpurun_out/<tag>/, written by scripts/gpu_round.sh) into profiles/<tag>/ as
 small text summaries: bench lines, pytest/smoke logs, the ncu launch list, selected raw metrics of the
 `--set full` capture of k_iterate and the opcode/stall summary of its source page.
-Usage: python scripts/collect_profiles.py <tag> [workload-key]"""
+Usage: python scripts/collect_profiles.py <tag>"""
 import csv
 import io
 import json
@@ -54,7 +54,8 @@ for rep in sorted(f for f in os.listdir(src) if f.endswith(".ncu-rep")):
             if m in ix:
                 f.write(f"{m},{units[ix[m]]}," + ",".join(l[ix[m]].replace(",", "") for l in launches) + "\n")
     # DRAM traffic of the first launch -> profiles/iterate_traffic.json (bench.py's roofline.traffic)
-    if len(sys.argv) > 2 and base == "prof_iterate":
+    keymap = {"prof_iterate": "lattice-1000x1000", "prof_iterate_rings": "rings-100000"}
+    if base in keymap:
         def to_bytes(col):
             v = float(launches[0][ix[col]].replace(",", ""))
             u = units[ix[col]].lower()
@@ -63,7 +64,7 @@ for rep in sorted(f for f in os.listdir(src) if f.endswith(".ncu-rep")):
         tj = os.path.join(ROOT, "profiles", "iterate_traffic.json")
         d = json.load(open(tj)) if os.path.exists(tj) else {}
         commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True, cwd=ROOT).stdout.strip()
-        d[sys.argv[2]] = {
+        d[keymap[base]] = {
             "dram_bytes_per_launch": rd + wr,
             "source": f"profiles/{tag}/ncu_{base}_full_metrics.csv (dram__bytes_read.sum {rd / 1e6:.2f} MB + "
                       f"dram__bytes_write.sum {wr / 1e6:.2f} MB, {launches[0][ix['Kernel Name']]}, after commit {commit})",

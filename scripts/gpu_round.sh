@@ -11,12 +11,14 @@ timeout 1500 python -m pytest tests -m gpu -x -q > "$OUT/pytest_gpu.log" 2>&1; e
 tail -5 "$OUT/pytest_gpu.log"
 timeout 900 python bench.py > "$OUT/bench.json" 2> "$OUT/bench.err"; echo "bench rc=$?"
 cat "$OUT/bench.json"
-timeout 600 python bench.py --workload lattice --robots 1000000 --steps 5 --no-cpu-baseline > "$OUT/bench_lattice1m.json" 2> "$OUT/bench_lattice1m.err"; echo "bench lattice rc=$?"
-cat "$OUT/bench_lattice1m.json"
+timeout 600 python bench.py --workload rings --no-cpu-baseline > "$OUT/bench_rings100k.json" 2> "$OUT/bench_rings100k.err"; echo "bench rings rc=$?"
+cat "$OUT/bench_rings100k.json"
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/bench_reference.json" 2> "$OUT/bench_reference.err"; echo "bench ref rc=$?"
 cat "$OUT/bench_reference.json"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches.csv" \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/ncu_launches.log" 2>&1; echo "ncu launches rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_iterate -s 40 -c 2 -o "$OUT/prof_iterate" -f \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/ncu_full.log" 2>&1; echo "ncu full rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_iterate -s 40 -c 1 -o "$OUT/prof_iterate_rings" -f \
+  python bench.py --workload rings --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/ncu_full_rings.log" 2>&1; echo "ncu full rings rc=$?"
 ls -la "$OUT"

@@ -87,3 +87,20 @@ def test_scenarios_are_deterministic_and_shaped():
     # initial means lie on the straight line start -> horizon (robot.rs:1187-1192)
     d = np.diff(lat.init_means[0, :, 0])
     assert (d > 0).all() and np.allclose(lat.init_means[0, :, 1], lat.init_means[0, 0, 1])
+
+
+def test_world_create_rejects_unsupported_variable_counts():
+    """V outside [2, 32] is refused with an error string before any device is touched."""
+    import ctypes as C
+
+    from magics_b200 import GbpConfig, load_library
+
+    lib = load_library()
+    for v in (0, 1, 33, 64):
+        c = GbpConfig(num_variables=v).to_c()
+        assert not lib.gbp_world_create(C.byref(c), 0)
+        assert b"num_variables" in lib.gbp_last_error()
+    out = (C.c_void_p * 2)()
+    assert lib.gbp_world_create_local_shards(C.byref(GbpConfig(num_variables=10).to_c()), 0, 0, out) < 0
+    assert lib.gbp_world_create_local_shards(C.byref(GbpConfig(num_variables=10).to_c()), 0, 17, out) < 0
+    assert not lib.gbp_world_create_shard(C.byref(GbpConfig(num_variables=10).to_c()), 0, 2, 2, None)
