@@ -177,6 +177,27 @@ int gbp_world_set_comms(gbp_world_t *w, const uint8_t *antenna_active, const uin
  * waypoint the horizon moves toward; <0 or >= len means "no more waypoints". */
 int gbp_world_set_waypoint_index(gbp_world_t *w, const int32_t *next_index);
 
+/* reached_waypoint (robot.rs:2080-2176) for every robot, single-route missions: compares the estimated
+ * position of one variable (f32 Vec2, variable.rs:127-130) with the next waypoint
+ * (glam distance_squared in f32) and advances the waypoint index (Route::advance, robot.rs:431-438).
+ * A criterion is ReachedWhenIntersects (gbp_config formation section): which variable and which distance. */
+enum gbp_intersects_with { GBP_INTERSECTS_CURRENT = 0, GBP_INTERSECTS_HORIZON = 1, GBP_INTERSECTS_VARIABLE = 2 };
+enum gbp_intersection_distance { GBP_DISTANCE_ROBOT_RADIUS = 0, GBP_DISTANCE_METER = 1 };
+typedef struct gbp_reached_when {
+  int32_t intersects_with; /* enum gbp_intersects_with */
+  int32_t variable_index;  /* for GBP_INTERSECTS_VARIABLE; out of range -> last variable */
+  int32_t distance;        /* enum gbp_intersection_distance */
+  float meter;             /* for GBP_DISTANCE_METER */
+} gbp_reached_when_t;
+/* taskpoint: criterion for every waypoint but the last (mission.taskpoint_reached_when_intersects);
+ * finished: for the last one (mission.finished_when_intersects).  out_reached[n] (may be NULL) is set
+ * to 1 for the robots that advanced — the RobotReachedWaypoint events.  Runs for the own robots of
+ * this world; in the reference it is a FixedUpdate system unordered with respect to the GBP chain. */
+int gbp_world_reached_waypoint(gbp_world_t *w, const gbp_reached_when_t *taskpoint,
+                               const gbp_reached_when_t *finished, uint8_t *out_reached);
+/* Mission/Route target_index of every robot (what gbp_world_set_waypoint_index sets). */
+int gbp_world_read_waypoint_index(gbp_world_t *w, int32_t *next_index);
+
 /* update_prior_of_horizon_state (robot.rs:2182-2283) for every robot. */
 int gbp_world_update_prior_of_horizon_state(gbp_world_t *w);
 /* update_prior_of_current_state_v3 (robot.rs:2286-2338) for every robot;

@@ -333,6 +333,35 @@ __global__ void k_set_dsafe(Store s, double mult) {
   for (int64_t e = s.eoff[r]; e < s.eoff[r + 1]; ++e) s.e_dsafe[e] = mult * double(s.radius[s.enbr[e]]);
 }
 
+// reached_waypoint (planner/robot.rs:2080-2176), one thread per robot; f32 arithmetic without
+// contraction, as glam's Vec2::distance_squared evaluates it.
+__global__ void k_reached_waypoint(Store s, int p, gbp_reached_when_t task, gbp_reached_when_t fin, uint8_t *out) {
+  const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= s.Nloc) return;
+  if (out) out[r] = 0;
+  const int32_t nwp = s.wp_off[r + 1] - s.wp_off[r], k = s.next_wp[r];
+  if (k < 0 || k >= nwp) return;  // mission.next_waypoint() is None
+  const gbp_reached_when_t c = (k == nwp - 1) ? fin : task;
+  const int V = s.V;
+  const int var = c.intersects_with == GBP_INTERSECTS_CURRENT
+                      ? 0
+                      : (c.intersects_with == GBP_INTERSECTS_HORIZON
+                             ? V - 1
+                             : (c.variable_index >= 0 && c.variable_index < V ? c.variable_index : V - 1));
+  const int64_t NV = s.NV, vi = r * V + var;
+  const double *src = s.latest[r] ? s.bel_ext : s.pub[p];
+  const float ex = float(src[20 * NV + vi]), ey = float(src[21 * NV + vi]);
+  const float rad = s.radius[r];
+  const float dsq = c.distance == GBP_DISTANCE_ROBOT_RADIUS ? __fmul_rn(rad, rad) : __fmul_rn(c.meter, c.meter);
+  const float *wp = s.wp_xy + 2 * (size_t(s.wp_off[r]) + k);
+  const float dx = __fsub_rn(ex, wp[0]), dy = __fsub_rn(ey, wp[1]);
+  const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+  if (d2 < dsq) {
+    s.next_wp[r] = k + 1;
+    if (out) out[r] = 1;
+  }
+}
+
 __global__ void k_iota_gid(int32_t *gid, int32_t g0, int32_t n) {
   const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < n) gid[r] = g0 + r;
@@ -1510,6 +1539,41 @@ int gbp_world_set_waypoint_index(gbp_world_t *w, const int32_t *next_index) {
   if (!next_index) return fail(GBP_ERR_BAD_ARGUMENT, "null index array");
   if (set_device(w)) return GBP_ERR_CUDA;
   CK(cudaMemcpyAsync(w->s.next_wp, next_index, size_t(w->s.Nloc) * sizeof(int32_t), cudaMemcpyHostToDevice, w->stream));
+  CK(cudaStreamSynchronize(w->stream));
+  return 0;
+}
+
+int gbp_world_reached_waypoint(gbp_world_t *w, const gbp_reached_when_t *taskpoint, const gbp_reached_when_t *finished,
+                               uint8_t *out_reached) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (!taskpoint || !finished) return fail(GBP_ERR_BAD_ARGUMENT, "gbp_world_reached_waypoint: null criterion");
+  for (const gbp_reached_when_t *c : {taskpoint, finished})
+    if (c->intersects_with < 0 || c->intersects_with > 2 || c->distance < 0 || c->distance > 1)
+      return fail(GBP_ERR_BAD_ARGUMENT, "gbp_world_reached_waypoint: bad criterion");
+  if (set_device(w)) return GBP_ERR_CUDA;
+  const int n = w->s.Nloc;
+  if (n == 0) return 0;
+  uint8_t *d_out = nullptr;
+  if (out_reached) {
+    if (int rc = ensure_scratch(w, size_t(n))) return rc;
+    d_out = static_cast<uint8_t *>(w->rb_dev);
+  }
+  k_reached_waypoint<<<blocks_for(n, 128), 128, 0, w->stream>>>(w->s, w->p, *taskpoint, *finished, d_out);
+  CK(cudaGetLastError());
+  w->launches += 1;
+  if (out_reached) {
+    CK(cudaMemcpyAsync(out_reached, d_out, size_t(n), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+  }
+  return 0;
+}
+
+int gbp_world_read_waypoint_index(gbp_world_t *w, int32_t *next_index) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (!next_index) return fail(GBP_ERR_BAD_ARGUMENT, "null output");
+  if (set_device(w)) return GBP_ERR_CUDA;
+  if (w->s.Nloc == 0) return 0;
+  CK(cudaMemcpyAsync(next_index, w->s.next_wp, size_t(w->s.Nloc) * sizeof(int32_t), cudaMemcpyDeviceToHost, w->stream));
   CK(cudaStreamSynchronize(w->stream));
   return 0;
 }

@@ -89,6 +89,12 @@ class LocalShards:
             if w.num_robots:
                 w.set_waypoint_index(a)
 
+    def reached_waypoint(self, taskpoint=(0, 0, 0, 0.0), finished=(0, 0, 0, 0.0)):
+        return np.concatenate([w.reached_waypoint(taskpoint, finished) for w in self.shards])
+
+    def read_waypoint_index(self):
+        return np.concatenate([w.read_waypoint_index() for w in self.shards])
+
     def update_prior_of_horizon_state(self):
         self.shards[0].update_prior_of_horizon_state()
 

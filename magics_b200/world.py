@@ -106,6 +106,12 @@ def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
 COMM_ID_BYTES = 128
 
 
+class ReachedWhen(C.Structure):
+    """gbp_reached_when_t"""
+    _fields_ = [("intersects_with", C.c_int32), ("variable_index", C.c_int32), ("distance", C.c_int32),
+                ("meter", C.c_float)]
+
+
 def comm_unique_id() -> bytes:
     """gbp_comm_unique_id: the NCCL communicator id rank 0 hands to every rank (any transport)."""
     lib = load_library()
@@ -222,6 +228,19 @@ class World:
     def set_waypoint_index(self, idx):
         idx = np.ascontiguousarray(idx, np.int32)
         self._call("gbp_world_set_waypoint_index", _p(idx, C.c_int32))
+
+    def reached_waypoint(self, taskpoint=(0, 0, 0, 0.0), finished=(0, 0, 0, 0.0)):
+        """reached_waypoint (robot.rs:2080-2176): criteria are (intersects_with, variable_index,
+        distance_kind, meter) for ordinary waypoints and for the last one; returns who advanced."""
+        t, f = ReachedWhen(*taskpoint), ReachedWhen(*finished)
+        out = np.zeros(self.num_robots, np.uint8)
+        self._call("gbp_world_reached_waypoint", C.byref(t), C.byref(f), _p(out, C.c_uint8))
+        return out.astype(bool)
+
+    def read_waypoint_index(self):
+        out = np.zeros(self.num_robots, np.int32)
+        self._call("gbp_world_read_waypoint_index", _p(out, C.c_int32))
+        return out
 
     def update_prior_of_horizon_state(self):
         self._call("gbp_world_update_prior_of_horizon_state")

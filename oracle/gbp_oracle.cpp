@@ -1204,6 +1204,42 @@ int gbpo_update_prior_of_horizon_state(void *p) {
   deliver_to_factors(*w, deferred);
   return 0;
 }
+// reached_waypoint (planner/robot.rs:2080-2176) for single-route missions: the chosen variable's
+// estimated position as an f32 Vec2 (variable.rs:127-130) against the next waypoint, glam
+// Vec2::distance_squared in f32; Route::advance (robot.rs:431-438) on success.
+// crit = {intersects_with (0 Current, 1 Horizon, 2 Variable(ix)), ix, distance kind (0 RobotRadius, 1 Meter)},
+// crit[0..2] for ordinary waypoints (taskpoint_reached_when_intersects), crit[3..5] for the last one
+// (finished_when_intersects); meters[0..1] likewise.  out_reached[n] (optional) flags the robots that advanced.
+int gbpo_reached_waypoint(void *p, const int32_t *crit, const float *meters, uint8_t *out_reached) {
+  World *w = static_cast<World *>(p);
+  for (size_t k = 0; k < w->robots.size(); ++k) {
+    Robot &r = w->robots[k];
+    if (out_reached) out_reached[k] = 0;
+    const int nwp = int(r.waypoints.size());
+    if (r.next_wp < 0 || r.next_wp >= nwp) continue;  // mission.next_waypoint() is None
+    const bool last = r.next_wp == nwp - 1;
+    const int32_t *c = crit + (last ? 3 : 0);
+    const float meter = meters[last ? 1 : 0];
+    const int V = int(r.g.vars.size());
+    int var = c[0] == 0 ? 0 : (c[0] == 1 ? V - 1 : (c[1] >= 0 && c[1] < V ? c[1] : V - 1));
+    const Variable &v = r.g.vars[var];
+    const float ex = float(v.mu[0]), ey = float(v.mu[1]);
+    const float dsq = c[2] == 0 ? r.radius * r.radius : meter * meter;
+    const float dx = ex - r.waypoints[r.next_wp].first, dy = ey - r.waypoints[r.next_wp].second;
+    const float d2 = dx * dx + dy * dy;
+    if (d2 < dsq) {
+      r.next_wp += 1;
+      if (out_reached) out_reached[k] = 1;
+    }
+  }
+  return 0;
+}
+int gbpo_read_waypoint_index(void *p, int32_t *out) {
+  World *w = static_cast<World *>(p);
+  for (size_t k = 0; k < w->robots.size(); ++k) out[k] = w->robots[k].next_wp;
+  return 0;
+}
+
 // update_prior_of_current_state_v3 (planner/robot.rs:2286-2338).
 int gbpo_update_prior_of_current_state(void *p) {
   World *w = static_cast<World *>(p);

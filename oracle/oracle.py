@@ -175,6 +175,19 @@ class OracleWorld:
         idx = np.ascontiguousarray(idx, np.int32)
         self._call("gbpo_set_waypoint_index", _p(idx, C.c_int32))
 
+    def reached_waypoint(self, taskpoint=(0, 0, 0, 0.0), finished=(0, 0, 0, 0.0)):
+        """(intersects_with, variable_index, distance_kind, meter) for ordinary / last waypoints."""
+        crit = np.array([taskpoint[0], taskpoint[1], taskpoint[2], finished[0], finished[1], finished[2]], np.int32)
+        meters = np.array([taskpoint[3], finished[3]], np.float32)
+        out = np.zeros(self.num_robots, np.uint8)
+        self._call("gbpo_reached_waypoint", _p(crit, C.c_int32), _p(meters, C.c_float), _p(out, C.c_uint8))
+        return out.astype(bool)
+
+    def read_waypoint_index(self):
+        out = np.zeros(self.num_robots, np.int32)
+        self._call("gbpo_read_waypoint_index", _p(out, C.c_int32))
+        return out
+
     def update_prior_of_horizon_state(self):
         self._call("gbpo_update_prior_of_horizon_state")
 

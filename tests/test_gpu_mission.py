@@ -1,0 +1,57 @@
+"""whole scenarios stepped on the device with the mission logic there too —
+`reached_waypoint` (robot.rs:2080-2176) advances each robot's waypoint index from the estimated position
+of the configured variable, the horizon prior then heads for the next waypoint and a robot that has passed
+its last waypoint stops moving its horizon (FinishedPath).  Compared tick by tick with the oracle."""
+import numpy as np
+import pytest
+
+from magics_b200 import World, scenarios
+from magics_b200.sharded import LocalShards
+from oracle.oracle import OracleWorld
+from tests.test_gpu_parity import check
+
+pytestmark = pytest.mark.gpu
+
+CURRENT, HORIZON, VARIABLE = 0, 1, 2
+RADIUS, METER = 0, 1
+
+
+@pytest.mark.parametrize("make", [lambda cfg: World(cfg), lambda cfg: LocalShards(cfg, 3)], ids=["single", "ws3"])
+def test_circle_runs_to_completion_on_device(make):
+    sw = scenarios.circle(8, circle_radius=8.0)
+    g, o = make(sw.cfg), OracleWorld(sw.cfg)
+    sw.add_to(g)
+    sw.add_to(o)
+    task, fin = (HORIZON, 0, RADIUS, 0.0), (CURRENT, 0, RADIUS, 0.0)
+    reached_total = np.zeros(sw.n, int)
+    for tick in range(90):
+        rg, ro = g.reached_waypoint(task, fin), o.reached_waypoint(task, fin)
+        assert np.array_equal(rg, ro), f"tick {tick}: different robots reached a waypoint"
+        reached_total += rg
+        g.step()
+        o.step()
+        if tick % 15 == 0:
+            check(g, o, f"mission tick {tick}")
+    check(g, o, "mission end")
+    assert np.array_equal(g.read_waypoint_index(), o.read_waypoint_index())
+    assert (reached_total == 1).all() and (g.read_waypoint_index() == 2).all(), "every robot reaches its goal once"
+
+
+def test_junction_three_waypoints_variable_and_meter_criteria():
+    sw = scenarios.junction_twoway(per_lane=1)
+    g, o = World(sw.cfg), OracleWorld(sw.cfg)
+    sw.add_to(g)
+    sw.add_to(o)
+    task, fin = (VARIABLE, 4, METER, 6.0), (VARIABLE, 99, METER, 3.0)  # index 99 -> last variable
+    seen = set()
+    for tick in range(120):
+        rg, ro = g.reached_waypoint(task, fin), o.reached_waypoint(task, fin)
+        assert np.array_equal(rg, ro), f"tick {tick}"
+        g.step()
+        o.step()
+        seen.update(g.read_waypoint_index().tolist())
+        if tick % 20 == 0:
+            check(g, o, f"junction mission tick {tick}")
+    check(g, o, "junction mission end")
+    assert np.array_equal(g.read_waypoint_index(), o.read_waypoint_index())
+    assert {1, 2} <= seen, seen  # robots passed the junction-centre waypoint and headed for the exit
