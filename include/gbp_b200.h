@@ -244,6 +244,13 @@ int gbp_world_set_schedule(gbp_world_t *w, int32_t kind, int32_t internal, int32
  *   eta[n*V*4], lam[n*V*16] row-major, mean[n*V*4], cov[n*V*16], valid[n*V] */
 int gbp_world_read_beliefs(gbp_world_t *w, double *eta, double *lam, double *mean,
                            double *cov, uint8_t *valid);
+/* The same read-back without stalling the engine: the gather runs on the engine's stream, the
+ * device->host copies on a second stream, so the kernels of the next tick overlap the PCIe
+ * transfer (host buffers should be page-locked, gbp_host_alloc_pinned).  The buffers are valid
+ * after gbp_world_readback_wait; at most one read-back is in flight (a second call waits for the first). */
+int gbp_world_read_beliefs_async(gbp_world_t *w, double *eta, double *lam, double *mean,
+                                 double *cov, uint8_t *valid);
+int gbp_world_readback_wait(gbp_world_t *w);
 /* Transform.translation (x, z) of every robot, f32[n*2]. */
 int gbp_world_read_positions(gbp_world_t *w, float *xy);
 /* RobotConnections.robots_connected_with as CSR: offsets[n+1], neighbours (global robot

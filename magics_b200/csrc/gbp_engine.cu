@@ -246,15 +246,58 @@ __device__ void change_prior_dev(const Store &s, int p, uint32_t epoch, int64_t 
     }
 }
 
-// update_prior_of_horizon_state (planner/robot.rs:2182-2283), one thread per robot.
+// change_prior_dev spread over the 32 lanes of a warp (one robot per warp): a prior change touches
+// ~70 scattered sectors of one robot, so one thread per robot is pure latency; every lane must
+// hold the same `nm`, computed from reads that happened before the __syncwarp below.
+__device__ void change_prior_warp(const Store &s, int p, uint32_t epoch, int64_t r, int var, const double (&nm)[4],
+                                  unsigned lane) {
+  const int64_t NV = s.NV, vi = r * s.V + var;
+  const double *src = s.latest[r] ? s.bel_ext : s.pub[p];
+  double keep = 0.0;
+  if (lane < 20) keep = src[lane * NV + vi];
+  const double pl = s.prior_lam[vi];
+  __syncwarp();
+  if (lane < 20) {
+    s.pub[p][lane * NV + vi] = keep;
+    s.bel_ext[lane * NV + vi] = keep;
+  } else if (lane < 24) {
+    const int k = int(lane) - 20;
+    s.pub[p][(20 + k) * NV + vi] = nm[k];
+    s.bel_ext[(20 + k) * NV + vi] = nm[k];
+    s.prior_eta[k * NV + vi] = pl * nm[k];
+  } else if (lane == 24) {
+    s.pub_epoch[p][vi] = epoch;
+    s.mu_ext[vi] = nm[0];
+    s.mu_ext[NV + vi] = nm[1];
+  } else if (lane == 25) {
+    s.m_dynL[vi] = gbp::empty_marker();
+  } else if (lane == 26) {
+    s.m_dynR[vi] = gbp::empty_marker();
+  } else if (lane == 27) {
+    s.m_obs[vi] = gbp::empty_marker();
+  } else if (lane == 28) {
+    s.m_trk[vi] = gbp::empty_marker();
+  }
+  if (var >= 1 && s.eoff)
+    for (int64_t e = s.eoff[r] + lane; e < s.eoff[r + 1]; e += 32) {
+      const int64_t m = e * (s.V - 1) + (var - 1);
+      s.mir[m] = gbp::empty_marker();
+      // external factors receive the new mean whatever the antenna state (robot.rs:2272-2282)
+      s.mu_frozen[m] = nm[0];
+      s.mu_frozen[s.EV + m] = nm[1];
+    }
+}
+
+// update_prior_of_horizon_state (planner/robot.rs:2182-2283), one warp per robot.
 __global__ void k_prior_horizon(Store s, int p, uint32_t epoch, double delta_t, double max_speed,
                                 int iterations_internal) {
-  const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31u;
   if (r >= s.Nloc) return;
   if (s.finished[r] || s.idle[r]) return;
   const int32_t nwp = s.wp_off[r + 1] - s.wp_off[r], k = s.next_wp[r];
   if (k < 0 || k >= nwp) {
-    s.finished[r] = 1;
+    if (lane == 0) s.finished[r] = 1;
     return;
   }
   if (iterations_internal == 0) return;
@@ -272,12 +315,13 @@ __global__ void k_prior_horizon(Store s, int p, uint32_t epoch, double delta_t, 
   const double sp = fmin(max_speed, dist);
   const double vx = sp * nx, vy = sp * ny;
   const double nm[4] = {ex + vx * delta_t, ey + vy * delta_t, vx, vy};
-  change_prior_dev(s, p, epoch, r, s.V - 1, nm);
+  change_prior_warp(s, p, epoch, r, s.V - 1, nm, lane);
 }
 
-// update_prior_of_current_state_v3 (planner/robot.rs:2286-2338).
+// update_prior_of_current_state_v3 (planner/robot.rs:2286-2338), one warp per robot.
 __global__ void k_prior_current(Store s, int p, uint32_t epoch, float delta_t) {
-  const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31u;
   if (r >= s.Nloc) return;
   if (s.idle[r]) return;
   const int64_t NV = s.NV, v0 = r * s.V, v1 = v0 + 1;
@@ -290,9 +334,12 @@ __global__ void k_prior_current(Store s, int p, uint32_t epoch, float delta_t) {
     ch[k] = double(time_scale) * (src[(20 + k) * NV + v1] - c);
     nm[k] = c + ch[k];
   }
-  change_prior_dev(s, p, epoch, r, 0, nm);
-  s.pos[r] = __fadd_rn(s.pos[r], float(ch[0]));
-  s.pos[s.cap + r] = __fadd_rn(s.pos[s.cap + r], float(ch[1]));
+  const float px = s.pos[r], pz = s.pos[s.cap + r];
+  change_prior_warp(s, p, epoch, r, 0, nm, lane);
+  if (lane == 0) {
+    s.pos[r] = __fadd_rn(px, float(ch[0]));
+    s.pos[s.cap + r] = __fadd_rn(pz, float(ch[1]));
+  }
 }
 
 __global__ void k_change_prior_list(Store s, int p, uint32_t epoch, int var, int m,
@@ -425,6 +472,11 @@ struct gbp_world {
   // grow-only device scratch for read-backs / small uploads (no cudaMalloc per call)
   void *rb_dev = nullptr;
   size_t rb_bytes = 0;
+  // asynchronous read-back: the AoS gather runs on the engine's stream, the device->host copies on
+  // a second stream, so the next tick's kernels overlap the PCIe transfer
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_gathered = nullptr, ev_copied = nullptr;
+  bool copy_pending = false;
   // optional per-launch CUDA-event timing (bench.py roofline leg)
   struct Span {
     int kind;
@@ -714,6 +766,10 @@ int run_schedule(gbp_group *g, int n, const uint8_t *internal, const uint8_t *ex
 }
 
 int ensure_scratch(gbp_world *w, size_t bytes) {
+  if (w->copy_pending) {  // an asynchronous read-back is still copying out of the scratch
+    CK(cudaEventSynchronize(w->ev_copied));
+    w->copy_pending = false;
+  }
   if (bytes <= w->rb_bytes) return 0;
   CK(cudaStreamSynchronize(w->stream));
   cudaFree(w->rb_dev);
@@ -1377,6 +1433,12 @@ void gbp_world_destroy(gbp_world_t *w) {
   for (cudaEvent_t e : w->ev_pool) cudaEventDestroy(e);
   cudaEventDestroy(w->ev0);
   cudaEventDestroy(w->ev1);
+  if (w->copy_stream) {
+    cudaStreamSynchronize(w->copy_stream);
+    cudaStreamDestroy(w->copy_stream);
+    cudaEventDestroy(w->ev_gathered);
+    cudaEventDestroy(w->ev_copied);
+  }
   if (w->owns_stream) cudaStreamDestroy(w->stream);
   if (w->t_result_host) cudaFreeHost(w->t_result_host);
   if (w->hdr_host) cudaFreeHost(w->hdr_host);
@@ -1586,7 +1648,7 @@ int gbp_world_update_prior_of_horizon_state(gbp_world_t *w0) {
     w->epoch += 1;
     if (w->s.Nloc == 0) continue;
     ProfileScope ps(w, GBP_PROFILE_PRIORS);
-    k_prior_horizon<<<blocks_for(w->s.Nloc, 128), 128, 0, w->stream>>>(
+    k_prior_horizon<<<blocks_for(int64_t(w->s.Nloc) * 32, 128), 128, 0, w->stream>>>(
         w->s, w->p, w->epoch, double(w->cfg.delta_t), double(w->cfg.target_speed), w->cfg.iterations_internal);
     CK(cudaGetLastError());
     w->launches += 1;
@@ -1602,7 +1664,7 @@ int gbp_world_update_prior_of_current_state(gbp_world_t *w0) {
     w->epoch += 1;
     if (w->s.Nloc == 0) continue;
     ProfileScope ps(w, GBP_PROFILE_PRIORS);
-    k_prior_current<<<blocks_for(w->s.Nloc, 128), 128, 0, w->stream>>>(w->s, w->p, w->epoch, w->cfg.delta_t);
+    k_prior_current<<<blocks_for(int64_t(w->s.Nloc) * 32, 128), 128, 0, w->stream>>>(w->s, w->p, w->epoch, w->cfg.delta_t);
     CK(cudaGetLastError());
     w->launches += 1;
   }
@@ -1722,9 +1784,17 @@ int gbp_world_set_schedule(gbp_world_t *w, int32_t kind, int32_t internal, int32
   return 0;
 }
 
-int gbp_world_read_beliefs(gbp_world_t *w, double *eta, double *lam, double *mean, double *cov, uint8_t *valid) {
-  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+namespace {
+int wait_readback(gbp_world *w) {
+  if (w->copy_pending) {
+    CK(cudaEventSynchronize(w->ev_copied));
+    w->copy_pending = false;
+  }
+  return 0;
+}
+int read_beliefs_impl(gbp_world *w, double *eta, double *lam, double *mean, double *cov, uint8_t *valid, bool async) {
   if (set_device(w)) return GBP_ERR_CUDA;
+  if (int rc = wait_readback(w)) return rc;  // the scratch of a pending copy is about to be reused
   const int64_t nv = int64_t(w->s.Nloc) * w->s.V;
   if (nv == 0) return 0;
   // one grow-only device scratch, carved into the requested AoS arrays
@@ -1741,13 +1811,46 @@ int gbp_world_read_beliefs(gbp_world_t *w, double *eta, double *lam, double *mea
   k_gather_beliefs<<<blocks_for(nv, 256), 256, 0, w->stream>>>(w->s, w->p, d_eta, d_lam, d_mean, d_cov, d_valid);
   CK(cudaGetLastError());
   w->launches += 1;
-  if (eta) CK(cudaMemcpyAsync(eta, d_eta, b_eta, cudaMemcpyDeviceToHost, w->stream));
-  if (lam) CK(cudaMemcpyAsync(lam, d_lam, b_lam, cudaMemcpyDeviceToHost, w->stream));
-  if (mean) CK(cudaMemcpyAsync(mean, d_mean, b_mean, cudaMemcpyDeviceToHost, w->stream));
-  if (cov) CK(cudaMemcpyAsync(cov, d_cov, b_cov, cudaMemcpyDeviceToHost, w->stream));
-  if (valid) CK(cudaMemcpyAsync(valid, d_valid, b_valid, cudaMemcpyDeviceToHost, w->stream));
-  CK(cudaStreamSynchronize(w->stream));
+  cudaStream_t cs = w->stream;
+  if (async) {
+    if (!w->copy_stream) {
+      CK(cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&w->ev_gathered, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&w->ev_copied, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(w->ev_gathered, w->stream));
+    CK(cudaStreamWaitEvent(w->copy_stream, w->ev_gathered, 0));
+    cs = w->copy_stream;
+  }
+  if (eta) CK(cudaMemcpyAsync(eta, d_eta, b_eta, cudaMemcpyDeviceToHost, cs));
+  if (lam) CK(cudaMemcpyAsync(lam, d_lam, b_lam, cudaMemcpyDeviceToHost, cs));
+  if (mean) CK(cudaMemcpyAsync(mean, d_mean, b_mean, cudaMemcpyDeviceToHost, cs));
+  if (cov) CK(cudaMemcpyAsync(cov, d_cov, b_cov, cudaMemcpyDeviceToHost, cs));
+  if (valid) CK(cudaMemcpyAsync(valid, d_valid, b_valid, cudaMemcpyDeviceToHost, cs));
+  if (async) {
+    CK(cudaEventRecord(w->ev_copied, cs));
+    w->copy_pending = true;
+  } else {
+    CK(cudaStreamSynchronize(w->stream));
+  }
   return 0;
+}
+}  // namespace
+
+int gbp_world_read_beliefs(gbp_world_t *w, double *eta, double *lam, double *mean, double *cov, uint8_t *valid) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  return read_beliefs_impl(w, eta, lam, mean, cov, valid, false);
+}
+
+int gbp_world_read_beliefs_async(gbp_world_t *w, double *eta, double *lam, double *mean, double *cov, uint8_t *valid) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  return read_beliefs_impl(w, eta, lam, mean, cov, valid, true);
+}
+
+int gbp_world_readback_wait(gbp_world_t *w) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (set_device(w)) return GBP_ERR_CUDA;
+  return wait_readback(w);
 }
 
 int gbp_world_read_positions(gbp_world_t *w, float *xy) {

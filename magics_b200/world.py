@@ -294,6 +294,17 @@ class World:
         self._call("gbp_world_read_beliefs", None, None, _p(out, C.c_double), None, None)
         return out
 
+    def read_means_into_async(self, out: np.ndarray):
+        """Start the read-back of every variable mean into a pinned (n, V, 4) buffer; the next tick may be
+        launched right away, `readback_wait()` makes the buffer valid."""
+        if out.dtype != np.float64 or not out.flags.c_contiguous or out.size != self.num_robots * self.V * 4:
+            raise ValueError("read_means_into_async: need a C-contiguous f64 buffer of n*V*4 elements")
+        self._call("gbp_world_read_beliefs_async", None, None, _p(out, C.c_double), None, None)
+        return out
+
+    def readback_wait(self):
+        self._call("gbp_world_readback_wait")
+
     def read_beliefs(self, eta=True, lam=True, mean=True, cov=True, valid=True):
         n, V = self.num_robots, self.V
         out = {}

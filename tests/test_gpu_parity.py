@@ -235,3 +235,28 @@ def test_rings_2000_full_iteration_parity():
         o.step()
     errs = check(g, o, "rings-2000")
     assert np.diff(g.read_connections()[0]).mean() > 3.5
+
+
+def test_async_readback_overlaps_the_next_tick_without_tearing():
+    """gbp_world_read_beliefs_async: the means copied out while the next tick runs are the means of the
+    tick they were requested after, bit for bit."""
+    from magics_b200 import pinned_empty
+
+    sw = scenarios.rings(20000)
+    g = World(sw.cfg)
+    sw.add_to(g)
+    bufs = [pinned_empty((sw.n, sw.cfg.num_variables, 4)) for _ in range(2)]
+    expect = []
+    for k in range(4):
+        g.step()
+        expect.append(g.read_beliefs(eta=False, lam=False, cov=False, valid=False)["mean"].copy())
+    h = World(sw.cfg)
+    sw.add_to(h)
+    for k in range(4):
+        h.step()
+        h.read_means_into_async(bufs[k % 2])
+        if k > 0:
+            assert np.array_equal(bufs[(k - 1) % 2], expect[k - 1]), f"tick {k - 1}"
+        h.reached_waypoint()  # uses the same device scratch: must not disturb the copy in flight
+    h.readback_wait()
+    assert np.array_equal(bufs[3 % 2], expect[3])
