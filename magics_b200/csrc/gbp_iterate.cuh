@@ -46,6 +46,9 @@ constexpr size_t kIterSmemBytes = 0;
 #ifndef GBP_PREFETCH
 #define GBP_PREFETCH 1
 #endif
+#ifndef GBP_MIRROR_MASK
+#define GBP_MIRROR_MASK 1
+#endif
 
 GBP_DEV void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 template <int N>
@@ -124,17 +127,19 @@ GBP_DEV void add_internal(const Store &s, int64_t vi, int i, double (&ae)[4], do
   }
 }
 
-GBP_DEV void add_mirror(const Store &s, int64_t m, double (&ae)[4], double (&al)[16]) {
+// Adds the stored mirror message m if there is one; returns whether there was.
+GBP_DEV bool add_mirror(const Store &s, int64_t m, double (&ae)[4], double (&al)[16]) {
   double v[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) v[k] = s.mir[k * s.EV + m];
-  if (is_empty_marker(v[0])) return;
+  if (is_empty_marker(v[0])) return false;
   ae[0] = ae[0] + v[0];
   ae[1] = ae[1] + v[1];
   al[0] = al[0] + v[2];
   al[1] = al[1] + v[3];
   al[4] = al[4] + v[4];
   al[5] = al[5] + v[5];
+  return true;
 }
 
 GBP_DEV void load_prior(const Store &s, int64_t vi, double (&ae)[4], double (&al)[16]) {
@@ -262,27 +267,32 @@ GBP_DEV void obstacle_update(const Store &s, int64_t vi, const double (&x)[4]) {
   s.m_obs[3 * NV + vi] = v0;
 }
 
-// Inputs of one InterRobot edge (receiver r <- neighbour A) for variable i, loaded as one batch
-// with a single dependent level (A = enbr[e] -> everything else), before any arithmetic.
-struct EdgeIn {
-  double rec[22];  // A's published record: eta4, Lambda16, position mean
-  double dsafe;
+// Head of one InterRobot edge (receiver r <- neighbour A) for variable i: everything needed to
+// decide whether A's factor sends a message at all — A's position mean, the record's epoch, A's
+// radio/idle bits and the edge scalars: 10 small loads with one dependent level (A = enbr[e]).
+// A's (eta, Lambda) — 20 doubles — is fetched only when the factor is not skipped
+// (InterRobotFactor::skip, interrobot.rs:213-226): in a swarm most robots within comms range
+// are outside safety range.  (Loading the head one edge ahead was measured slower: registers.)
+struct EdgeHead {
+  double mu0, mu1, dsafe;
   uint64_t rnum;
   uint32_t epochA, birth;
+  int A;
   bool act, frozen;
 };
-GBP_DEV void load_edge(const Store &s, const double *__restrict__ pubr, int p, int64_t e, int A, int V, int i,
-                       EdgeIn &x) {
+GBP_DEV void load_head(const Store &s, const double *__restrict__ pubr, int p, int64_t e, int A, int V, int i,
+                       EdgeHead &h) {
   const int64_t NV = s.NV;
   const int64_t va = int64_t(A) * V + i;
-#pragma unroll
-  for (int k = 0; k < 22; ++k) x.rec[k] = pubr[k * NV + va];
-  x.epochA = s.pub_epoch[p][va];
-  x.act = s.en_ir && s.antenna[A] != 0 && s.idle[A] == 0;
-  x.birth = s.e_birth[e];
-  x.frozen = s.e_frozen[e] != 0;
-  x.rnum = s.e_rnum[e];
-  x.dsafe = s.e_dsafe[e];
+  h.A = A;
+  h.mu0 = pubr[20 * NV + va];
+  h.mu1 = pubr[21 * NV + va];
+  h.epochA = s.pub_epoch[p][va];
+  h.act = s.en_ir && s.antenna[A] != 0 && s.idle[A] == 0;
+  h.birth = s.e_birth[e];
+  h.frozen = s.e_frozen[e] != 0;
+  h.rnum = s.e_rnum[e];
+  h.dsafe = s.e_dsafe[e];
 }
 
 template <bool EXT, bool INT>
@@ -341,6 +351,10 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
   const bool do_ext = EXT && live && !idle && ant;
   const bool do_int = INT && live && !idle;
 
+  // bit (e - e0): the mirror message of edge e is non-empty after the external half, so the
+  // internal half of the same launch need not read the Empty ones back (edges beyond 64: it reads)
+  uint64_t mir_ne = 0;
+
   // =================== external half ====================================
   if (do_ext) {
     double ae[4], al[16];
@@ -354,26 +368,34 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
       mu_sent[1] = s.mu_ext[NV + vi];
     }
     bool added = false;
-    // Everything an edge needs is loaded up front, unconditionally (one dependent level:
-    // enbr[e] -> the rest), and the loads of edge e+1 are issued before the arithmetic of
-    // edge e so their latency hides behind it.
-    auto process = [&](int64_t e, const EdgeIn &x) {
+    int A_next = (e0 < e1) ? s.enbr[e0] : 0;
+    for (int64_t e = e0; e < e1; ++e) {
+      EdgeHead h;
+      load_head(s, pubr, p, e, A_next, V, i, h);
+      if (e + 1 < e1) A_next = s.enbr[e + 1];
       if (!added && e >= elow) {
         add_internal(s, vi, i, ae, al);
         added = true;
       }
       const int64_t m = e * (V - 1) + (i - 1);
-      if (x.act) {
-        const bool a_ne = x.epochA > x.birth;
-        const double muA[2] = {a_ne ? x.rec[20] : 0.0, a_ne ? x.rec[21] : 0.0};
+      if (h.act) {
+        const bool a_ne = h.epochA > h.birth;
+        const double muA[2] = {a_ne ? h.mu0 : 0.0, a_ne ? h.mu1 : 0.0};
         double mb[2] = {mu_sent[0], mu_sent[1]};
-        if (x.frozen) {  // rare: edge just created, or A's radio was off at the last delivery
+        if (h.frozen) {  // rare: edge just created, or A's radio was off at the last delivery
           mb[0] = s.mu_frozen[m];
           mb[1] = s.mu_frozen[s.EV + m];
         }
-        const double tiny = s.tiny_scale * double(x.rnum + uint64_t(i - 1));
+        bool ok = false;
         double me[2], ml[4];
-        const bool ok = interrobot_message(e < elow, muA, mb, a_ne, x.rec, x.dsafe, tiny, s.lm_ir, me, ml);
+        if (!interrobot_skip(e < elow, muA, mb, h.dsafe)) {
+          double rec[20];
+          const int64_t va = int64_t(h.A) * V + i;
+#pragma unroll
+          for (int k = 0; k < 20; ++k) rec[k] = pubr[k * NV + va];
+          const double tiny = s.tiny_scale * double(h.rnum + uint64_t(i - 1));
+          ok = interrobot_message(e < elow, muA, mb, a_ne, rec, h.dsafe, tiny, s.lm_ir, me, ml);
+        }
         if (ok) {
           s.mir[m] = me[0];
           s.mir[s.EV + m] = me[1];
@@ -387,25 +409,20 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
           al[1] = al[1] + ml[1];
           al[4] = al[4] + ml[2];
           al[5] = al[5] + ml[3];
+          if (e - e0 < 64) mir_ne |= 1ull << (e - e0);
         } else {
           s.mir[m] = empty_marker();
         }
       } else {
-        add_mirror(s, m, ae, al);  // undelivered: the variable keeps the old message
+        // undelivered: the variable keeps the old message
+        if (add_mirror(s, m, ae, al) && e - e0 < 64) mir_ne |= 1ull << (e - e0);
         // ... and A's factor keeps the mean it already holds from this variable
         // while this variable's belief moves on (robot.rs:1851): freeze it
-        if (!x.frozen) {
+        if (!h.frozen) {
           s.mu_frozen[m] = mu_sent[0];
           s.mu_frozen[s.EV + m] = mu_sent[1];
         }
       }
-    };
-    int A_next = (e0 < e1) ? s.enbr[e0] : 0;
-    for (int64_t e = e0; e < e1; ++e) {
-      EdgeIn x;
-      load_edge(s, pubr, p, e, A_next, V, i, x);
-      if (e + 1 < e1) A_next = s.enbr[e + 1];
-      process(e, x);
     }
     if (!added) add_internal(s, vi, i, ae, al);
     double cov[16];
@@ -522,6 +539,9 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
           add_internal(s, vi, i, ae, al);
           added = true;
         }
+#if GBP_MIRROR_MASK
+        if (EXT && do_ext && e - e0 < 64 && !((mir_ne >> (e - e0)) & 1ull)) continue;  // known Empty
+#endif
         add_mirror(s, e * (V - 1) + (i - 1), ae, al);
       }
       if (!added) add_internal(s, vi, i, ae, al);

@@ -261,10 +261,20 @@ GBP_DEV void unary_add(const double (&J)[4], double v0, double lm, double (&eta)
 //   a_nonempty whether A's variable message exists (else only the potential)
 //   dsafe      safety distance, tiny the factor's tiny_offset, lm = 1/sigma^2
 // Output: eta[0..1], lam 2x2 (rows/cols 0..1 of the 4x4; the rest is exactly 0).
-// `recA` = A's published record (eta 0..3, Lambda 4..19, position mean 20..21); only read
-// when a_nonempty.
+// InterRobotFactor::skip (interrobot.rs:213-226) on the linearisation point: the squared distance
+// of the two position means (no tiny_offset) against the safety distance.  Exactly the first
+// test of interrobot_message, exposed so that the caller can decide BEFORE fetching A's 20-double
+// (eta, Lambda) record: in a swarm most robots within comms range are outside safety range.
+GBP_DEV bool interrobot_skip(bool a_first, const double (&muA)[2], const double (&muB)[2], double dsafe) {
+  const double x0 = a_first ? muA[0] : muB[0], x1 = a_first ? muA[1] : muB[1];
+  const double x4 = a_first ? muB[0] : muA[0], x5 = a_first ? muB[1] : muA[1];
+  const double e0 = x0 - x4, e1 = x1 - x5;
+  return (0.0 + e0 * e0) + e1 * e1 >= dsafe * dsafe;
+}
+
+// `recA` = A's published record (eta 0..3, Lambda 4..19); only read when a_nonempty.
 GBP_DEV bool interrobot_message(bool a_first, const double (&muA)[2], const double (&muB)[2],
-                                bool a_nonempty, const double (&recA)[22], double dsafe, double tiny,
+                                bool a_nonempty, const double (&recA)[20], double dsafe, double tiny,
                                 double lm, double (&eta)[2], double (&lam)[4]) {
   const double *etaA = recA, *lamA = recA + 4;
   const double x0 = a_first ? muA[0] : muB[0], x1 = a_first ? muA[1] : muB[1];
