@@ -198,6 +198,20 @@ int gbp_world_reached_waypoint(gbp_world_t *w, const gbp_reached_when_t *taskpoi
 /* Mission/Route target_index of every robot (what gbp_world_set_waypoint_index sets). */
 int gbp_world_read_waypoint_index(gbp_world_t *w, int32_t *next_index);
 
+/* update_robot_robot_collisions + RobotRobotCollisions bookkeeping (planner/collisions.rs:72-143,
+ * :146-200, :455-493): bounding-sphere test of every connected pair (parry2d
+ * BoundingSphere::intersects, f32) and the Free/Colliding state machine; a Free -> Colliding
+ * transition is one collision.  Pairs are taken from the comms-radius connectivity, so
+ * radius_a + radius_b <= comms radius is required (true for every shipped scenario).  Collective
+ * for a sharded world; the counts are this shard's share (a pair counts on the shard of its
+ * lower robot id): num_collisions = RobotRobotCollisions::num_collisions, colliding_now = pairs in
+ * state Colliding.  Either pointer may be NULL (no host sync then). */
+int gbp_world_update_robot_collisions(gbp_world_t *w, int64_t *num_collisions, int64_t *colliding_now);
+/* The two counters of this shard as of the last update (no kernel runs). */
+int gbp_world_read_collision_totals(gbp_world_t *w, int64_t *num_collisions, int64_t *colliding_now);
+/* RobotRobotCollisions::get(entity) for every own robot: per_robot[n]. */
+int gbp_world_read_robot_collisions(gbp_world_t *w, uint32_t *per_robot);
+
 /* update_prior_of_horizon_state (robot.rs:2182-2283) for every robot. */
 int gbp_world_update_prior_of_horizon_state(gbp_world_t *w);
 /* update_prior_of_current_state_v3 (robot.rs:2286-2338) for every robot;

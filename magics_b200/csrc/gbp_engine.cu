@@ -491,6 +491,7 @@ struct gbp_world {
   gbp_group *grp = nullptr;
   bool owns_stream = true;
   bool smem_opted_in[4] = {false, false, false, false};  // k_iterate<EXT,INT> dynamic shared memory opt-in
+  unsigned long long *coll_totals = nullptr;              // [0] Hit events so far, [1] pairs colliding now
   gbp::ShardInfo sh{};          // ws, rank, gfirst
   int32_t Ntot = 0;             // robots of the whole swarm
   int32_t nghost = 0;
@@ -916,6 +917,7 @@ int reserve_robots(gbp_world *w, int64_t newcap) {
   CK(regrow(s.iter_factor, 1, oldcap, newcap, keep, st));
   CK(regrow(s.gid, 1, oldcap, newcap, keep, st));
   CK(regrow(s.next_wp, 1, oldcap, newcap, keep, st));
+  CK(regrow(s.coll_hits, 1, oldcap, newcap, keep, st));
   CK(regrow(s.nlow, 1, oldcap, newcap, keep, st));
   s.NV = newNV;
   s.cap = newcap;
@@ -1419,7 +1421,7 @@ void gbp_world_destroy(gbp_world_t *w) {
   void *ptrs[] = {s.prior_eta, s.prior_lam, s.pub[0], s.pub[1], s.pub_epoch[0], s.pub_epoch[1], s.bel_ext,
                   s.mu_ext, s.cov, s.valid, s.m_dynL, s.m_dynR, s.m_obs, s.m_trk, s.dyn_dt,
                   s.trk_record, s.trk_timeout, s.trk_last, s.trk_value, s.radius, s.t0, s.pos, s.antenna,
-                  s.idle, s.finished, s.latest, s.iter_factor, s.gid, s.next_wp, s.wp_off, s.wp_xy, s.eoff,
+                  s.idle, s.finished, s.latest, s.iter_factor, s.gid, s.next_wp, s.coll_hits, w->coll_totals, s.wp_off, s.wp_xy, s.eoff,
                   s.nlow, w->t_nlow, w->t_result_dev, w->sdf_dev, w->t_cx,
                   w->t_cz, w->t_idx, w->t_idx_sorted, w->t_keys, w->t_keys_sorted, w->t_cnt, w->t_off,
                   w->t_newcnt, w->t_newoff, w->t_cub, w->rb_dev, w->gpos, w->t_gflag, w->t_gslot, w->t_sflag,
@@ -1523,6 +1525,7 @@ int gbp_world_add_robots(gbp_world_t *w, int32_t n, const float *radii, const ui
   CK(cudaMemsetAsync(s.latest + N0, 0, size_t(n), st));
   CK(cudaMemsetAsync(s.iter_factor + N0, 0, size_t(n) * sizeof(uint32_t), st));
   CK(cudaMemsetAsync(s.nlow + N0, 0, size_t(n) * sizeof(int32_t), st));
+  CK(cudaMemsetAsync(s.coll_hits + N0, 0, size_t(n) * sizeof(uint32_t), st));
   s.N = int32_t(N1);
   s.Nloc = int32_t(N1);
   const int64_t N1cap = s.cap;
@@ -1627,6 +1630,53 @@ int gbp_world_reached_waypoint(gbp_world_t *w, const gbp_reached_when_t *taskpoi
     CK(cudaMemcpyAsync(out_reached, d_out, size_t(n), cudaMemcpyDeviceToHost, w->stream));
     CK(cudaStreamSynchronize(w->stream));
   }
+  return 0;
+}
+
+int gbp_world_update_robot_collisions(gbp_world_t *w0, int64_t *num_collisions, int64_t *colliding_now) {
+  if (!w0) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  gbp_group *g = w0->grp;
+  // ghosts must sit at their current Transform: the halo carries it
+  if (g->ws > 1 && g->halo_stale) {
+    if (int rc = group_halo(g)) return rc;
+  }
+  for (gbp_world *w : g->members) {
+    if (set_device(w)) return GBP_ERR_CUDA;
+    if (!w->coll_totals) {
+      CK(dalloc(w->coll_totals, 2));
+      CK(cudaMemsetAsync(w->coll_totals, 0, 2 * sizeof(unsigned long long), w->stream));
+    }
+    CK(cudaMemsetAsync(w->coll_totals + 1, 0, sizeof(unsigned long long), w->stream));
+    if (w->s.Nloc == 0 || w->s.E == 0) continue;
+    gbp::k_robot_collisions<<<blocks_for(w->s.Nloc, 128), 128, 0, w->stream>>>(
+        w->s, w->edges[w->cur].egid, w->sh.gfirst[w->sh.rank], w->coll_totals);
+    CK(cudaGetLastError());
+    w->launches += 1;
+  }
+  if (num_collisions || colliding_now) return gbp_world_read_collision_totals(w0, num_collisions, colliding_now);
+  return 0;
+}
+
+int gbp_world_read_collision_totals(gbp_world_t *w, int64_t *num_collisions, int64_t *colliding_now) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (set_device(w)) return GBP_ERR_CUDA;
+  unsigned long long h[2] = {0, 0};
+  if (w->coll_totals) {
+    CK(cudaMemcpyAsync(h, w->coll_totals, sizeof(h), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+  }
+  if (num_collisions) *num_collisions = int64_t(h[0]);
+  if (colliding_now) *colliding_now = int64_t(h[1]);
+  return 0;
+}
+
+int gbp_world_read_robot_collisions(gbp_world_t *w, uint32_t *per_robot) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (!per_robot) return fail(GBP_ERR_BAD_ARGUMENT, "null output");
+  if (set_device(w)) return GBP_ERR_CUDA;
+  if (w->s.Nloc == 0) return 0;
+  CK(cudaMemcpyAsync(per_robot, w->s.coll_hits, size_t(w->s.Nloc) * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+  CK(cudaStreamSynchronize(w->stream));
   return 0;
 }
 

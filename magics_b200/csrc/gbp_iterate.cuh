@@ -290,7 +290,7 @@ GBP_DEV void load_head(const Store &s, const double *__restrict__ pubr, int p, i
   h.epochA = s.pub_epoch[p][va];
   h.act = s.en_ir && s.antenna[A] != 0 && s.idle[A] == 0;
   h.birth = s.e_birth[e];
-  h.frozen = s.e_frozen[e] != 0;
+  h.frozen = (s.e_frozen[e] & 1) != 0;
   h.rnum = s.e_rnum[e];
   h.dsafe = s.e_dsafe[e];
 }
@@ -452,7 +452,8 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
       for (int64_t e = eo0; e < eo1; ++e) {
         const int A = s.enbr[e];
         const uint8_t fr = (s.en_ir && s.antenna[A] != 0 && s.idle[A] == 0) ? 0 : 1;
-        if (s.e_frozen[e] != fr) s.e_frozen[e] = fr;
+        const uint8_t cur = s.e_frozen[e];
+        if ((cur & 1) != fr) s.e_frozen[e] = uint8_t((cur & 2) | fr);  // bit 1 belongs to the collision monitor
       }
     }
   }

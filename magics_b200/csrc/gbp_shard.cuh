@@ -234,10 +234,11 @@ __global__ void k_edge_pull(ShardInfo sh, int32_t nloc, int32_t V, const int64_t
 
 // ---- per-sub-step halo ----------------------------------------------------------
 // One record per (robot, variable i >= 1): eta4, Lambda16, position mean (22 doubles)
-// + the record's epoch; one double of antenna/idle bits per robot.  Inside a peer
-// block the layout is plane-major so that consecutive threads touch consecutive doubles.
+// + the record's epoch; per robot two more doubles: antenna/idle bits, and the f32 Transform
+// (x, z) packed into one double (the collision monitor tests ghosts at their current position).
+// Inside a peer block the layout is plane-major so that consecutive threads touch consecutive doubles.
 constexpr int kHaloPlanes = 23;
-__host__ __device__ inline int64_t halo_doubles_per_robot(int V) { return int64_t(kHaloPlanes) * (V - 1) + 1; }
+__host__ __device__ inline int64_t halo_doubles_per_robot(int V) { return int64_t(kHaloPlanes) * (V - 1) + 2; }
 
 __global__ void k_halo_pack(Store s, int p, int ws, PeerOffsets po, const int32_t *__restrict__ sendlist,
                             double *__restrict__ buf) {
@@ -256,7 +257,12 @@ __global__ void k_halo_pack(Store s, int p, int ws, PeerOffsets po, const int32_
 #pragma unroll
   for (int k = 0; k < 22; ++k) blk[k * ps + at] = rec[k * NV + vi];
   blk[22 * ps + at] = double(s.pub_epoch[p][vi]);
-  if (i == 1) blk[kHaloPlanes * ps + jj] = double(int(s.antenna[r] != 0) | (int(s.idle[r] != 0) << 1));
+  if (i == 1) {
+    blk[kHaloPlanes * ps + jj] = double(int(s.antenna[r] != 0) | (int(s.idle[r] != 0) << 1));
+    const unsigned long long xz = (unsigned long long)__float_as_uint(s.pos[r]) |
+                                  ((unsigned long long)__float_as_uint(s.pos[s.cap + r]) << 32);
+    blk[kHaloPlanes * ps + cnt + jj] = __longlong_as_double((long long)xz);
+  }
 }
 
 __global__ void k_halo_unpack(Store s, int p, int ws, PeerOffsets po, const double *__restrict__ buf) {
@@ -279,7 +285,43 @@ __global__ void k_halo_unpack(Store s, int p, int ws, PeerOffsets po, const doub
     const int bits = int(blk[kHaloPlanes * ps + jj]);
     s.antenna[slot] = uint8_t(bits & 1);
     s.idle[slot] = uint8_t((bits >> 1) & 1);
+    const unsigned long long xz = (unsigned long long)__double_as_longlong(blk[kHaloPlanes * ps + cnt + jj]);
+    s.pos[slot] = __uint_as_float(unsigned(xz & 0xffffffffull));
+    s.pos[s.cap + slot] = __uint_as_float(unsigned(xz >> 32));
   }
+}
+
+// update_robot_robot_collisions (planner/collisions.rs:72-143) restricted to connected pairs (every
+// colliding pair is connected as long as radius_a + radius_b <= comms radius, which the host checks):
+// parry2d BoundingSphere::intersects in f32 — |c_b - c_a|^2 <= (r_a + r_b)^2 — and the Free/Colliding
+// state machine of CollisionHistory::update (:472-488).  Every directed edge carries the pair's state
+// (both directions evolve identically, so a pair split over two shards needs no message); a Hit
+// increments the own robot's counter, and the global counter once per pair (lower id's side).
+__global__ void k_robot_collisions(Store s, const int32_t *__restrict__ egid, int32_t g0,
+                                   unsigned long long *totals /* [0] hits, [1] colliding pairs now */) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= s.Nloc) return;
+  const float ax = s.pos[r], az = s.pos[s.cap + r], ar = s.radius[r];
+  unsigned hits = 0, pair_hits = 0, pair_now = 0;
+  for (int64_t e = s.eoff[r]; e < s.eoff[r + 1]; ++e) {
+    const int32_t a = s.enbr[e];
+    const float dx = __fsub_rn(s.pos[a], ax), dz = __fsub_rn(s.pos[s.cap + a], az);
+    const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dz, dz));
+    const float sr = __fadd_rn(ar, s.radius[a]);
+    const bool now = d2 <= __fmul_rn(sr, sr);
+    const uint8_t cur = s.e_frozen[e];
+    const bool was = (cur & 2) != 0;
+    if (now != was) s.e_frozen[e] = uint8_t((cur & 1) | (now ? 2 : 0));
+    const bool lower = g0 + r < egid[e];
+    if (now && !was) {  // CollisionStatus::Hit
+      hits += 1;
+      if (lower) pair_hits += 1;
+    }
+    if (now && lower) pair_now += 1;
+  }
+  if (hits) s.coll_hits[r] += hits;
+  if (pair_hits) atomicAdd(&totals[0], (unsigned long long)pair_hits);
+  if (pair_now) atomicAdd(&totals[1], (unsigned long long)pair_now);
 }
 
 }  // namespace gbp

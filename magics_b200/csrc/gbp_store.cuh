@@ -74,7 +74,9 @@ struct Store {
   double *e_dsafe;     // [E]   safety distance of A's factor: multiplier * radius_A
   uint64_t *e_rnum;    // [E]   robot_number of A's factor toward B at i = 1
   uint32_t *e_birth;   // [E]   epoch at which the edge was created
-  uint8_t *e_frozen;   // [E]   1 while A's factor holds an older mean of B than mu_ext (see mu_frozen)
+  uint8_t *e_frozen;   // [E]   bit 0: A's factor holds an older mean of B than mu_ext (see mu_frozen);
+                       //       bit 1: CollisionState::Colliding of the pair (planner/collisions.rs:455-493)
+  uint32_t *coll_hits; // [cap] per robot: collisions it has been part of (RobotRobotCollisions::get)
   double *mu_frozen;   // [2][E*(V-1)] position mean of B's variable that A's factor holds while the
                        //   edge is frozen: B's belief at edge creation (robot.rs:1557-1585), or the
                        //   last mean delivered before A's antenna went off (robot.rs:1851)

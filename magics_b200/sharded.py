@@ -9,6 +9,8 @@ against a plain `World`, a `LocalShards` and the oracle and compare all three.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 
 from .config import GbpConfig
@@ -94,6 +96,20 @@ class LocalShards:
 
     def read_waypoint_index(self):
         return np.concatenate([w.read_waypoint_index() for w in self.shards])
+
+    def update_robot_collisions(self):
+        self.shards[0]._call("gbp_world_update_robot_collisions", None, None)  # collective, no sync
+        total = now = 0
+        for w in self.shards:
+            t, n = C.c_int64(0), C.c_int64(0)
+            # per-shard totals: read without re-running the monitor
+            w._call("gbp_world_read_collision_totals", C.byref(t), C.byref(n))
+            total += int(t.value)
+            now += int(n.value)
+        return total, now
+
+    def read_robot_collisions(self):
+        return np.concatenate([w.read_robot_collisions() for w in self.shards])
 
     def update_prior_of_horizon_state(self):
         self.shards[0].update_prior_of_horizon_state()

@@ -242,6 +242,17 @@ class World:
         self._call("gbp_world_read_waypoint_index", _p(out, C.c_int32))
         return out
 
+    def update_robot_collisions(self):
+        """update_robot_robot_collisions (planner/collisions.rs:72-143): (collisions so far, pairs colliding now)."""
+        total, now = C.c_int64(0), C.c_int64(0)
+        self._call("gbp_world_update_robot_collisions", C.byref(total), C.byref(now))
+        return int(total.value), int(now.value)
+
+    def read_robot_collisions(self):
+        out = np.zeros(self.num_robots, np.uint32)
+        self._call("gbp_world_read_robot_collisions", _p(out, C.c_uint32))
+        return out
+
     def update_prior_of_horizon_state(self):
         self._call("gbp_world_update_prior_of_horizon_state")
 

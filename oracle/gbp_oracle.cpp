@@ -689,6 +689,10 @@ struct Robot {
 };
 
 struct World {
+  // RobotRobotCollisions (planner/collisions.rs:146-200): state per unordered pair, total Hit count
+  std::map<std::pair<int, int>, bool> coll_state;
+  std::vector<uint32_t> coll_hits;
+  int64_t collisions = 0;
   Cfg cfg;
   Sdf sdf;
   std::vector<uint32_t> timesteps;
@@ -1232,6 +1236,36 @@ int gbpo_reached_waypoint(void *p, const int32_t *crit, const float *meters, uin
       if (out_reached) out_reached[k] = 1;
     }
   }
+  return 0;
+}
+// update_robot_robot_collisions (planner/collisions.rs:72-143): ALL pairs (r < c) in robot order;
+// parry2d BoundingSphere::intersects (un-vendored crate, restated: |c_b - c_a|^2 <= (r_a + r_b)^2 in
+// f32); CollisionHistory::update (:472-488): Free -> Colliding is a Hit.
+int gbpo_update_robot_collisions(void *p, int64_t *num_collisions, int64_t *colliding_now, uint32_t *per_robot) {
+  World *w = static_cast<World *>(p);
+  const int n = int(w->robots.size());
+  w->coll_hits.resize(size_t(n), 0u);
+  int64_t now_count = 0;
+  for (int r = 0; r < n; ++r)
+    for (int c = r + 1; c < n; ++c) {
+      const Robot &a = w->robots[r], &b = w->robots[c];
+      const float dx = b.pos[0] - a.pos[0], dz = b.pos[1] - a.pos[1];
+      const float d2 = dx * dx + dz * dz;
+      const float sr = a.radius + b.radius;
+      const bool now = d2 <= sr * sr;
+      bool &state = w->coll_state[{r, c}];
+      if (now && !state) {
+        w->collisions += 1;
+        w->coll_hits[r] += 1;
+        w->coll_hits[c] += 1;
+      }
+      state = now;
+      if (now) ++now_count;
+    }
+  if (num_collisions) *num_collisions = w->collisions;
+  if (colliding_now) *colliding_now = now_count;
+  if (per_robot)
+    for (int r = 0; r < n; ++r) per_robot[r] = w->coll_hits[r];
   return 0;
 }
 int gbpo_read_waypoint_index(void *p, int32_t *out) {

@@ -183,6 +183,15 @@ class OracleWorld:
         self._call("gbpo_reached_waypoint", _p(crit, C.c_int32), _p(meters, C.c_float), _p(out, C.c_uint8))
         return out.astype(bool)
 
+    def update_robot_collisions(self):
+        total, now = C.c_int64(0), C.c_int64(0)
+        self._hits = np.zeros(self.num_robots, np.uint32)
+        self._call("gbpo_update_robot_collisions", C.byref(total), C.byref(now), _p(self._hits, C.c_uint32))
+        return int(total.value), int(now.value)
+
+    def read_robot_collisions(self):
+        return self._hits.copy()
+
     def read_waypoint_index(self):
         out = np.zeros(self.num_robots, np.int32)
         self._call("gbpo_read_waypoint_index", _p(out, C.c_int32))

@@ -55,3 +55,31 @@ def test_junction_three_waypoints_variable_and_meter_criteria():
     check(g, o, "junction mission end")
     assert np.array_equal(g.read_waypoint_index(), o.read_waypoint_index())
     assert {1, 2} <= seen, seen  # robots passed the junction-centre waypoint and headed for the exit
+
+
+@pytest.mark.parametrize("make", [lambda cfg: World(cfg), lambda cfg: LocalShards(cfg, 3)], ids=["single", "ws3"])
+@pytest.mark.parametrize("interrobot", [0, 1])
+def test_robot_robot_collision_monitor(make, interrobot):
+    """update_robot_robot_collisions (planner/collisions.rs:72-143).  With InterRobot
+    factors disabled the circle swarm drives straight through its centre and collides; with them enabled
+    it (mostly) does not.  Hit counts, currently-colliding pairs and per-robot counts against the oracle's
+    all-pairs version, every tick."""
+    sw = scenarios.circle(8, circle_radius=8.0, robot_radius=1.0)
+    sw.cfg.enable_interrobot = interrobot
+    g, o = make(sw.cfg), OracleWorld(sw.cfg)
+    sw.add_to(g)
+    sw.add_to(o)
+    seen_now = 0
+    for tick in range(60):
+        g.step()
+        o.step()
+        cg, co = g.update_robot_collisions(), o.update_robot_collisions()
+        assert cg == co, f"tick {tick}: (collisions, colliding now) {cg} vs {co}"
+        seen_now = max(seen_now, cg[1])
+        if tick % 10 == 9:
+            assert np.array_equal(g.read_robot_collisions(), o.read_robot_collisions()), f"tick {tick}"
+    check(g, o, "collision run")
+    total, _ = g.update_robot_collisions()
+    if not interrobot:
+        assert total >= 4 and seen_now >= 2, (total, seen_now)
+        assert g.read_robot_collisions().sum() == 2 * total
