@@ -50,18 +50,25 @@ cudaError_t dalloc(T *&p, size_t n) {
 }
 
 // Re-stride a [planes][old_stride] array to [planes][new_stride], keeping the
-// first `used` entries of each plane.
+// first `used` entries of each plane.  `tiled`: a per-variable array in the tiled layout of
+// gbp_store.cuh (tiles of 32 slots x planes, back to back) — growing it appends tiles, the used
+// ones move as one block.
 template <class T>
 cudaError_t regrow(T *&p, int planes, int64_t old_stride, int64_t new_stride, int64_t used,
-                   cudaStream_t st) {
+                   cudaStream_t st, bool tiled = false) {
   T *q = nullptr;
   cudaError_t e = dalloc(q, size_t(planes) * size_t(new_stride));
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(q, 0, size_t(planes) * size_t(new_stride) * sizeof(T), st);
   if (e != cudaSuccess) return e;
   if (p && used > 0) {
-    e = cudaMemcpy2DAsync(q, size_t(new_stride) * sizeof(T), p, size_t(old_stride) * sizeof(T),
-                          size_t(used) * sizeof(T), size_t(planes), cudaMemcpyDeviceToDevice, st);
+    if (tiled && GBP_TILED && planes > 1) {
+      const size_t tiles = size_t((used + gbp::kTile - 1) / gbp::kTile);
+      e = cudaMemcpyAsync(q, p, tiles * size_t(planes) * gbp::kTile * sizeof(T), cudaMemcpyDeviceToDevice, st);
+    } else {
+      e = cudaMemcpy2DAsync(q, size_t(new_stride) * sizeof(T), p, size_t(old_stride) * sizeof(T),
+                            size_t(used) * sizeof(T), size_t(planes), cudaMemcpyDeviceToDevice, st);
+    }
     if (e != cudaSuccess) return e;
   }
   if (p) {
@@ -155,15 +162,15 @@ void schedule_half(int kind, int n, int max, uint8_t *out) {
 // ---- small kernels -------------------------------------------------------------
 
 // VariableNode::new (variable.rs:140-166) for the variables [first, first+count):
-// expects mu (rows 20..23 of pub[p]) and prior_lam already uploaded.
-__global__ void k_init_vars(Store s, int p, int64_t first, int64_t count) {
+// expects prior_lam already uploaded; `mu0` = the initial means as [4][count] planes.
+__global__ void k_init_vars(Store s, int64_t first, int64_t count, const double *__restrict__ mu0) {
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= count) return;
-  const int64_t vi = first + t, NV = s.NV;
+  const int64_t vi = first + t;
   double mu[4], lam[16], cov[16];
   const double pl = s.prior_lam[vi];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) mu[k] = s.pub[p][(20 + k) * NV + vi];
+  for (int k = 0; k < 4; ++k) mu[k] = mu0[k * count + t];
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
     lam[k] = (k % 5 == 0) ? pl : 0.0;
@@ -176,35 +183,35 @@ __global__ void k_init_vars(Store s, int p, int64_t first, int64_t count) {
   for (int b = 0; b < 2; ++b) {
     double *rec = s.pub[b];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) rec[k * NV + vi] = pl * mu[k];
+    for (int k = 0; k < 4; ++k) rec[s.at<gbp::kRec>(k, vi)] = pl * mu[k];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) rec[(4 + k) * NV + vi] = lam[k];
+    for (int k = 0; k < 16; ++k) rec[s.at<gbp::kRec>(4 + k, vi)] = lam[k];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) rec[(20 + k) * NV + vi] = mu[k];
+    for (int k = 0; k < 4; ++k) rec[s.at<gbp::kRec>(20 + k, vi)] = mu[k];
     s.pub_epoch[b][vi] = 0u;
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    s.prior_eta[k * NV + vi] = pl * mu[k];
-    s.bel_ext[k * NV + vi] = pl * mu[k];
-    s.bel_ext[(20 + k) * NV + vi] = mu[k];
+    s.prior_eta[s.at<4>(k, vi)] = pl * mu[k];
+    s.bel_ext[s.at<gbp::kRec>(k, vi)] = pl * mu[k];
+    s.bel_ext[s.at<gbp::kRec>(20 + k, vi)] = mu[k];
   }
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    s.bel_ext[(4 + k) * NV + vi] = lam[k];
-    s.cov[k * NV + vi] = cov[k];
+    s.bel_ext[s.at<gbp::kRec>(4 + k, vi)] = lam[k];
+    s.cov[s.at<16>(k, vi)] = cov[k];
   }
   s.valid[vi] = fin ? 1 : 0;
-  s.mu_ext[vi] = mu[0];
-  s.mu_ext[NV + vi] = mu[1];
-  s.m_dynL[vi] = gbp::empty_marker();
-  s.m_dynR[vi] = gbp::empty_marker();
-  s.m_obs[vi] = gbp::empty_marker();
-  s.m_trk[vi] = gbp::empty_marker();
+  s.mu_ext[s.at<2>(0, vi)] = mu[0];
+  s.mu_ext[s.at<2>(1, vi)] = mu[1];
+  s.m_dynL[s.at<20>(0, vi)] = gbp::empty_marker();
+  s.m_dynR[s.at<20>(0, vi)] = gbp::empty_marker();
+  s.m_obs[s.at<4>(0, vi)] = gbp::empty_marker();
+  s.m_trk[s.at<3>(0, vi)] = gbp::empty_marker();
   s.trk_record[vi] = 0u;
   s.trk_timeout[vi] = -1;
-  s.trk_last[vi] = float(mu[0]);  // with_last_measurement (factor/mod.rs:279-283)
-  s.trk_last[NV + vi] = float(mu[1]);
+  s.trk_last[s.at<2>(0, vi)] = float(mu[0]);  // with_last_measurement (factor/mod.rs:279-283)
+  s.trk_last[s.at<2>(1, vi)] = float(mu[1]);
   s.trk_value[vi] = 0.0;
 }
 
@@ -214,28 +221,28 @@ __global__ void k_init_vars(Store s, int p, int64_t first, int64_t count) {
 // (eta_belief, Lambda_belief, new mean); the variable's inbox is emptied.
 __device__ void change_prior_dev(const Store &s, int p, uint32_t epoch, int64_t r, int var,
                                  const double (&nm)[4]) {
-  const int64_t NV = s.NV, vi = r * s.V + var;
+  const int64_t vi = r * s.V + var;
   const double *src = s.latest[r] ? s.bel_ext : s.pub[p];
   const double pl = s.prior_lam[vi];
   double rec[20];
 #pragma unroll
-  for (int k = 0; k < 20; ++k) rec[k] = src[k * NV + vi];
+  for (int k = 0; k < 20; ++k) rec[k] = src[s.at<gbp::kRec>(k, vi)];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) s.prior_eta[k * NV + vi] = pl * nm[k];
+  for (int k = 0; k < 4; ++k) s.prior_eta[s.at<4>(k, vi)] = pl * nm[k];
   double *dst[2] = {s.pub[p], s.bel_ext};
   for (int b = 0; b < 2; ++b) {
 #pragma unroll
-    for (int k = 0; k < 20; ++k) dst[b][k * NV + vi] = rec[k];
+    for (int k = 0; k < 20; ++k) dst[b][s.at<gbp::kRec>(k, vi)] = rec[k];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) dst[b][(20 + k) * NV + vi] = nm[k];
+    for (int k = 0; k < 4; ++k) dst[b][s.at<gbp::kRec>(20 + k, vi)] = nm[k];
   }
   s.pub_epoch[p][vi] = epoch;
-  s.mu_ext[vi] = nm[0];
-  s.mu_ext[NV + vi] = nm[1];
-  s.m_dynL[vi] = gbp::empty_marker();
-  s.m_dynR[vi] = gbp::empty_marker();
-  s.m_obs[vi] = gbp::empty_marker();
-  s.m_trk[vi] = gbp::empty_marker();
+  s.mu_ext[s.at<2>(0, vi)] = nm[0];
+  s.mu_ext[s.at<2>(1, vi)] = nm[1];
+  s.m_dynL[s.at<20>(0, vi)] = gbp::empty_marker();
+  s.m_dynR[s.at<20>(0, vi)] = gbp::empty_marker();
+  s.m_obs[s.at<4>(0, vi)] = gbp::empty_marker();
+  s.m_trk[s.at<3>(0, vi)] = gbp::empty_marker();
   if (var >= 1 && s.eoff)
     for (int64_t e = s.eoff[r]; e < s.eoff[r + 1]; ++e) {
       const int64_t m = e * (s.V - 1) + (var - 1);
@@ -251,32 +258,32 @@ __device__ void change_prior_dev(const Store &s, int p, uint32_t epoch, int64_t 
 // hold the same `nm`, computed from reads that happened before the __syncwarp below.
 __device__ void change_prior_warp(const Store &s, int p, uint32_t epoch, int64_t r, int var, const double (&nm)[4],
                                   unsigned lane) {
-  const int64_t NV = s.NV, vi = r * s.V + var;
+  const int64_t vi = r * s.V + var;
   const double *src = s.latest[r] ? s.bel_ext : s.pub[p];
   double keep = 0.0;
-  if (lane < 20) keep = src[lane * NV + vi];
+  if (lane < 20) keep = src[s.at<gbp::kRec>(lane, vi)];
   const double pl = s.prior_lam[vi];
   __syncwarp();
   if (lane < 20) {
-    s.pub[p][lane * NV + vi] = keep;
-    s.bel_ext[lane * NV + vi] = keep;
+    s.pub[p][s.at<gbp::kRec>(lane, vi)] = keep;
+    s.bel_ext[s.at<gbp::kRec>(lane, vi)] = keep;
   } else if (lane < 24) {
     const int k = int(lane) - 20;
-    s.pub[p][(20 + k) * NV + vi] = nm[k];
-    s.bel_ext[(20 + k) * NV + vi] = nm[k];
-    s.prior_eta[k * NV + vi] = pl * nm[k];
+    s.pub[p][s.at<gbp::kRec>(20 + k, vi)] = nm[k];
+    s.bel_ext[s.at<gbp::kRec>(20 + k, vi)] = nm[k];
+    s.prior_eta[s.at<4>(k, vi)] = pl * nm[k];
   } else if (lane == 24) {
     s.pub_epoch[p][vi] = epoch;
-    s.mu_ext[vi] = nm[0];
-    s.mu_ext[NV + vi] = nm[1];
+    s.mu_ext[s.at<2>(0, vi)] = nm[0];
+    s.mu_ext[s.at<2>(1, vi)] = nm[1];
   } else if (lane == 25) {
-    s.m_dynL[vi] = gbp::empty_marker();
+    s.m_dynL[s.at<20>(0, vi)] = gbp::empty_marker();
   } else if (lane == 26) {
-    s.m_dynR[vi] = gbp::empty_marker();
+    s.m_dynR[s.at<20>(0, vi)] = gbp::empty_marker();
   } else if (lane == 27) {
-    s.m_obs[vi] = gbp::empty_marker();
+    s.m_obs[s.at<4>(0, vi)] = gbp::empty_marker();
   } else if (lane == 28) {
-    s.m_trk[vi] = gbp::empty_marker();
+    s.m_trk[s.at<3>(0, vi)] = gbp::empty_marker();
   }
   if (var >= 1 && s.eoff)
     for (int64_t e = s.eoff[r] + lane; e < s.eoff[r + 1]; e += 32) {
@@ -301,9 +308,9 @@ __global__ void k_prior_horizon(Store s, int p, uint32_t epoch, double delta_t, 
     return;
   }
   if (iterations_internal == 0) return;
-  const int64_t NV = s.NV, vi = r * s.V + (s.V - 1);
+  const int64_t vi = r * s.V + (s.V - 1);
   const double *src = s.latest[r] ? s.bel_ext : s.pub[p];
-  const double ex = src[20 * NV + vi], ey = src[21 * NV + vi];
+  const double ex = src[s.at<gbp::kRec>(20, vi)], ey = src[s.at<gbp::kRec>(21, vi)];
   const float *wp = s.wp_xy + 2 * (size_t(s.wp_off[r]) + k);
   const double hx = double(wp[0]) - ex, hy = double(wp[1]) - ey;
   const double dist = gbp::norm2(hx, hy);
@@ -324,14 +331,14 @@ __global__ void k_prior_current(Store s, int p, uint32_t epoch, float delta_t) {
   const unsigned lane = threadIdx.x & 31u;
   if (r >= s.Nloc) return;
   if (s.idle[r]) return;
-  const int64_t NV = s.NV, v0 = r * s.V, v1 = v0 + 1;
+  const int64_t v0 = r * s.V, v1 = v0 + 1;
   const double *src = s.latest[r] ? s.bel_ext : s.pub[p];
   const float time_scale = __fdiv_rn(delta_t, s.t0[r]);
   double ch[4], nm[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const double c = src[(20 + k) * NV + v0];
-    ch[k] = double(time_scale) * (src[(20 + k) * NV + v1] - c);
+    const double c = src[s.at<gbp::kRec>(20 + k, v0)];
+    ch[k] = double(time_scale) * (src[s.at<gbp::kRec>(20 + k, v1)] - c);
     nm[k] = c + ch[k];
   }
   const float px = s.pos[r], pz = s.pos[s.cap + r];
@@ -355,16 +362,16 @@ __global__ void k_gather_beliefs(Store s, int p, double *eta, double *lam, doubl
                                  uint8_t *valid) {
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= int64_t(s.Nloc) * s.V) return;
-  const int64_t r = t / s.V, NV = s.NV;
+  const int64_t r = t / s.V;
   const double *src = s.latest[r] ? s.bel_ext : s.pub[p];
   if (eta)
-    for (int k = 0; k < 4; ++k) eta[4 * t + k] = src[k * NV + t];
+    for (int k = 0; k < 4; ++k) eta[4 * t + k] = src[s.at<gbp::kRec>(k, t)];
   if (lam)
-    for (int k = 0; k < 16; ++k) lam[16 * t + k] = src[(4 + k) * NV + t];
+    for (int k = 0; k < 16; ++k) lam[16 * t + k] = src[s.at<gbp::kRec>(4 + k, t)];
   if (mean)
-    for (int k = 0; k < 4; ++k) mean[4 * t + k] = src[(20 + k) * NV + t];
+    for (int k = 0; k < 4; ++k) mean[4 * t + k] = src[s.at<gbp::kRec>(20 + k, t)];
   if (cov)
-    for (int k = 0; k < 16; ++k) cov[16 * t + k] = s.cov[k * NV + t];
+    for (int k = 0; k < 16; ++k) cov[16 * t + k] = s.cov[s.at<16>(k, t)];
   if (valid) valid[t] = s.valid[t];
 }
 
@@ -395,9 +402,9 @@ __global__ void k_reached_waypoint(Store s, int p, gbp_reached_when_t task, gbp_
                       : (c.intersects_with == GBP_INTERSECTS_HORIZON
                              ? V - 1
                              : (c.variable_index >= 0 && c.variable_index < V ? c.variable_index : V - 1));
-  const int64_t NV = s.NV, vi = r * V + var;
+  const int64_t vi = r * V + var;
   const double *src = s.latest[r] ? s.bel_ext : s.pub[p];
-  const float ex = float(src[20 * NV + vi]), ey = float(src[21 * NV + vi]);
+  const float ex = float(src[s.at<gbp::kRec>(20, vi)]), ey = float(src[s.at<gbp::kRec>(21, vi)]);
   const float rad = s.radius[r];
   const float dsq = c.distance == GBP_DISTANCE_ROBOT_RADIUS ? __fmul_rn(rad, rad) : __fmul_rn(c.meter, c.meter);
   const float *wp = s.wp_xy + 2 * (size_t(s.wp_off[r]) + k);
@@ -887,25 +894,26 @@ int reserve_robots(gbp_world *w, int64_t newcap) {
   if (newcap <= s.cap) return 0;
   cudaStream_t st = w->stream;
   const int V = s.V;
-  const int64_t oldNV = s.NV, newNV = newcap * V, used = int64_t(s.Nloc) * V, oldcap = s.cap, keep = s.Nloc;
-  CK(regrow(s.prior_eta, 4, oldNV, newNV, used, st));
+  // whole tiles (gbp_store.cuh)
+  const int64_t oldNV = s.NV, newNV = (newcap * V + gbp::kTile - 1) / gbp::kTile * gbp::kTile, used = int64_t(s.Nloc) * V, oldcap = s.cap, keep = s.Nloc;
+  CK(regrow(s.prior_eta, 4, oldNV, newNV, used, st, true));
   CK(regrow(s.prior_lam, 1, oldNV, newNV, used, st));
-  CK(regrow(s.pub[0], gbp::kRec, oldNV, newNV, used, st));
-  CK(regrow(s.pub[1], gbp::kRec, oldNV, newNV, used, st));
+  CK(regrow(s.pub[0], gbp::kRec, oldNV, newNV, used, st, true));
+  CK(regrow(s.pub[1], gbp::kRec, oldNV, newNV, used, st, true));
   CK(regrow(s.pub_epoch[0], 1, oldNV, newNV, used, st));
   CK(regrow(s.pub_epoch[1], 1, oldNV, newNV, used, st));
-  CK(regrow(s.bel_ext, gbp::kRec, oldNV, newNV, used, st));
-  CK(regrow(s.mu_ext, 2, oldNV, newNV, used, st));
-  CK(regrow(s.cov, 16, oldNV, newNV, used, st));
+  CK(regrow(s.bel_ext, gbp::kRec, oldNV, newNV, used, st, true));
+  CK(regrow(s.mu_ext, 2, oldNV, newNV, used, st, true));
+  CK(regrow(s.cov, 16, oldNV, newNV, used, st, true));
   CK(regrow(s.valid, 1, oldNV, newNV, used, st));
-  CK(regrow(s.m_dynL, 20, oldNV, newNV, used, st));
-  CK(regrow(s.m_dynR, 20, oldNV, newNV, used, st));
-  CK(regrow(s.m_obs, 4, oldNV, newNV, used, st));
-  CK(regrow(s.m_trk, 3, oldNV, newNV, used, st));
+  CK(regrow(s.m_dynL, 20, oldNV, newNV, used, st, true));
+  CK(regrow(s.m_dynR, 20, oldNV, newNV, used, st, true));
+  CK(regrow(s.m_obs, 4, oldNV, newNV, used, st, true));
+  CK(regrow(s.m_trk, 3, oldNV, newNV, used, st, true));
   CK(regrow(s.dyn_dt, 1, oldNV, newNV, used, st));
   CK(regrow(s.trk_record, 1, oldNV, newNV, used, st));
   CK(regrow(s.trk_timeout, 1, oldNV, newNV, used, st));
-  CK(regrow(s.trk_last, 2, oldNV, newNV, used, st));
+  CK(regrow(s.trk_last, 2, oldNV, newNV, used, st, true));
   CK(regrow(s.trk_value, 1, oldNV, newNV, used, st));
   CK(regrow(s.radius, 1, oldcap, newcap, keep, st));
   CK(regrow(s.t0, 1, oldcap, newcap, keep, st));
@@ -1550,7 +1558,9 @@ int gbp_world_add_robots(gbp_world_t *w, int32_t n, const float *radii, const ui
       if (i < V - 1) dt[t] = double(t0[r] * float(timesteps[i + 1] - timesteps[i]));  // :1232
     }
   }
-  CK(upload_planes(s.pub[w->p] + 20 * newNV, newNV, used, mu.data(), 4, nv, st));
+  double *d_mu = nullptr;  // [4][nv] staging; k_init_vars reads the means from it
+  CK(dalloc(d_mu, size_t(4) * size_t(nv)));
+  CK(cudaMemcpyAsync(d_mu, mu.data(), size_t(4) * size_t(nv) * sizeof(double), cudaMemcpyHostToDevice, st));
   CK(upload_planes(s.prior_lam, newNV, used, pl.data(), 1, nv, st));
   CK(upload_planes(s.dyn_dt, newNV, used, dt.data(), 1, nv, st));
   CK(upload_planes(s.radius, N1cap, N0, rad.data(), 1, n, st));
@@ -1570,10 +1580,11 @@ int gbp_world_add_robots(gbp_world_t *w, int32_t n, const float *radii, const ui
   CK(dalloc(s.wp_xy, w->wp_xy.size()));
   CK(cudaMemcpyAsync(s.wp_off, w->wp_off.data(), w->wp_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(s.wp_xy, w->wp_xy.data(), w->wp_xy.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-  k_init_vars<<<blocks_for(nv, 256), 256, 0, st>>>(s, w->p, used, nv);
+  k_init_vars<<<blocks_for(nv, 256), 256, 0, st>>>(s, used, nv, d_mu);
   CK(cudaGetLastError());
   w->launches += 1;
   CK(cudaStreamSynchronize(st));  // staging vectors go out of scope
+  cudaFree(d_mu);
   return 0;
 }
 

@@ -29,11 +29,14 @@
 
 namespace gbp {
 
-constexpr int kIterBlock = 128;
-constexpr size_t kIterSmemBytes = 0;
+#ifndef GBP_ITER_BLOCK
+#define GBP_ITER_BLOCK 128
+#endif
 #ifndef GBP_ITER_MIN_BLOCKS
 #define GBP_ITER_MIN_BLOCKS 3
 #endif
+constexpr int kIterBlock = GBP_ITER_BLOCK;
+constexpr size_t kIterSmemBytes = 0;
 
 // ---- L2 prefetch -----------------------------------------------------------------------------
 // The kernel is a chain of ~16 dependent load phases per thread at 12 warps per SM, so the
@@ -42,7 +45,8 @@ constexpr size_t kIterSmemBytes = 0;
 // register and no shared memory, and turns the later own-record phases into L2 hits.  (Measured,
 // profiles/README.md r01d: +5 %; prefetching the neighbours' records as well, staging through
 // shared memory with cp.async, or parking accumulators in shared memory for 16 warps/SM were
-// all slower than this.)
+// all slower than this; so was, r01f, letting a robot's lanes split its edges and pull each
+// neighbour's position means / epoch / radio bits into L1 ahead of the edge loop: +-0.)
 #ifndef GBP_PREFETCH
 #define GBP_PREFETCH 1
 #endif
@@ -51,10 +55,11 @@ constexpr size_t kIterSmemBytes = 0;
 #endif
 
 GBP_DEV void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-template <int N>
-GBP_DEV void prefetch_planes(const double *base, int64_t stride, int64_t at) {
+// first N components of a P-component per-variable record
+template <int P, int N>
+GBP_DEV void prefetch_planes(const Store &s, const double *base, int64_t vi) {
 #pragma unroll
-  for (int k = 0; k < N; ++k) prefetch_l2(base + k * stride + at);
+  for (int k = 0; k < N; ++k) prefetch_l2(base + s.at<P>(k, vi));
 }
 
 GBP_DEV double dot2(const double (&a)[2], const double (&b)[2]) { return (0.0 + a[0] * b[0]) + a[1] * b[1]; }
@@ -79,14 +84,13 @@ GBP_DEV double sdf_measure(const Store &s, double x_pos, double y_pos, uint32_t 
 // FactorId order dyn(i-1) < dyn(i) < obs(i) < trk(i) (id.rs:25-61; creation order
 // robot.rs:1228-1334), added onto (ae, al) (variable.rs:263-271).
 GBP_DEV void add_internal(const Store &s, int64_t vi, int i, double (&ae)[4], double (&al)[16]) {
-  const int64_t NV = s.NV;
   // Every record is loaded whole before its Empty marker is looked at: the slots of
   // factors a variable does not have (dyn(i-1) of variable 0, ...) hold the marker for
   // ever, so no index test is needed and no load waits on another load.
   {
     double m[20];
 #pragma unroll
-    for (int k = 0; k < 20; ++k) m[k] = s.m_dynL[k * NV + vi];
+    for (int k = 0; k < 20; ++k) m[k] = s.m_dynL[s.at<20>(k, vi)];
     if (!is_empty_marker(m[0])) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) ae[k] = ae[k] + m[k];
@@ -97,7 +101,7 @@ GBP_DEV void add_internal(const Store &s, int64_t vi, int i, double (&ae)[4], do
   {
     double m[20];
 #pragma unroll
-    for (int k = 0; k < 20; ++k) m[k] = s.m_dynR[k * NV + vi];
+    for (int k = 0; k < 20; ++k) m[k] = s.m_dynR[s.at<20>(k, vi)];
     if (!is_empty_marker(m[0])) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) ae[k] = ae[k] + m[k];
@@ -108,9 +112,9 @@ GBP_DEV void add_internal(const Store &s, int64_t vi, int i, double (&ae)[4], do
   {
     double o[4], t[3];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) o[k] = s.m_obs[k * NV + vi];
+    for (int k = 0; k < 4; ++k) o[k] = s.m_obs[s.at<4>(k, vi)];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) t[k] = s.m_trk[k * NV + vi];
+    for (int k = 0; k < 3; ++k) t[k] = s.m_trk[s.at<3>(k, vi)];
     if (!is_empty_marker(o[0])) {
       const double J[4] = {o[0], o[1], o[2], o[2]};
       unary_add(J, o[3], s.lm_obs, ae, al);
@@ -144,7 +148,7 @@ GBP_DEV bool add_mirror(const Store &s, int64_t m, double (&ae)[4], double (&al)
 
 GBP_DEV void load_prior(const Store &s, int64_t vi, double (&ae)[4], double (&al)[16]) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) ae[k] = s.prior_eta[k * s.NV + vi];
+  for (int k = 0; k < 4; ++k) ae[k] = s.prior_eta[s.at<4>(k, vi)];
   const double pl = s.prior_lam[vi];
 #pragma unroll
   for (int k = 0; k < 16; ++k) al[k] = (k % 5 == 0) ? pl : 0.0;
@@ -164,7 +168,6 @@ GBP_DEV void shfl_vec(double (&v)[20], bool &flag, int delta_up, unsigned lane) 
 // TrackingFactor::skip + measure + jacobian (factor/tracking.rs:171-381) for
 // variable vi of robot r at linearisation point x.  Writes the message record.
 GBP_DEV void tracking_update(const Store &s, int64_t r, int64_t vi, const double (&x)[4]) {
-  const int64_t NV = s.NV;
   bool skip = false;
   int32_t timeout = s.trk_timeout[vi];
   if (timeout >= 0) {
@@ -181,7 +184,7 @@ GBP_DEV void tracking_update(const Store &s, int64_t r, int64_t vi, const double
   uint32_t rec = s.trk_record[vi];
   if (!skip && (npath < 2 || rec >= npath - 1)) skip = true;
   if (skip) {
-    s.m_trk[vi] = empty_marker();
+    s.m_trk[s.at<3>(0, vi)] = empty_marker();
     return;
   }
   const float *wp = s.wp_xy + 2 * size_t(w0);
@@ -231,23 +234,22 @@ GBP_DEV void tracking_update(const Store &s, int64_t r, int64_t vi, const double
   const double ad = s.trk_attraction;
   const double meas = dist < ad ? dist / ad : 1.0;
   const float lx = float(mp[0]), ly = float(mp[1]);
-  s.trk_last[vi] = lx;
-  s.trk_last[NV + vi] = ly;
+  s.trk_last[s.at<2>(0, vi)] = lx;
+  s.trk_last[s.at<2>(1, vi)] = ly;
   s.trk_value[vi] = meas;
   // jacobian (tracking.rs:171-194) from the measurement just stored
   const double j0 = (1.0 / meas) * (x_pos[0] - double(lx));
   const double j1 = (1.0 / meas) * (x_pos[1] - double(ly));
   const double v0 = ((0.0 + j0 * x[0]) + j1 * x[1]) + (0.0 - meas);
-  s.m_trk[vi] = j0;
-  s.m_trk[NV + vi] = j1;
-  s.m_trk[2 * NV + vi] = v0;
+  s.m_trk[s.at<3>(0, vi)] = j0;
+  s.m_trk[s.at<3>(1, vi)] = j1;
+  s.m_trk[s.at<3>(2, vi)] = v0;
 }
 
 // ObstacleFactor update: measure + first_order_jacobian (factor/mod.rs:102-128,
 // obstacle.rs:129-188) at linearisation point x; six SDF lookups, perturb and
 // restore sequence kept so that x+d-d rounding reaches the same pixels.
 GBP_DEV void obstacle_update(const Store &s, int64_t vi, const double (&x)[4]) {
-  const int64_t NV = s.NV;
   const double h = sdf_measure(s, x[0], x[1]);
   const double h0 = sdf_measure(s, x[0], x[1]);
   const double delta = s.jac_delta;
@@ -261,10 +263,10 @@ GBP_DEV void obstacle_update(const Store &s, int64_t vi, const double (&x)[4]) {
   const double h3 = sdf_measure(s, px, py);  // columns 2 and 3 perturb the velocity only
   const double j0 = (h1 - h0) / delta, j1 = (h2 - h0) / delta, j2 = (h3 - h0) / delta;
   const double v0 = ((((0.0 + j0 * x[0]) + j1 * x[1]) + j2 * x[2]) + j2 * x[3]) + (0.0 - h);
-  s.m_obs[vi] = j0;
-  s.m_obs[NV + vi] = j1;
-  s.m_obs[2 * NV + vi] = j2;
-  s.m_obs[3 * NV + vi] = v0;
+  s.m_obs[s.at<4>(0, vi)] = j0;
+  s.m_obs[s.at<4>(1, vi)] = j1;
+  s.m_obs[s.at<4>(2, vi)] = j2;
+  s.m_obs[s.at<4>(3, vi)] = v0;
 }
 
 // Head of one InterRobot edge (receiver r <- neighbour A) for variable i: everything needed to
@@ -282,11 +284,10 @@ struct EdgeHead {
 };
 GBP_DEV void load_head(const Store &s, const double *__restrict__ pubr, int p, int64_t e, int A, int V, int i,
                        EdgeHead &h) {
-  const int64_t NV = s.NV;
   const int64_t va = int64_t(A) * V + i;
   h.A = A;
-  h.mu0 = pubr[20 * NV + va];
-  h.mu1 = pubr[21 * NV + va];
+  h.mu0 = pubr[s.at<kRec>(20, va)];
+  h.mu1 = pubr[s.at<kRec>(21, va)];
   h.epochA = s.pub_epoch[p][va];
   h.act = s.en_ir && s.antenna[A] != 0 && s.idle[A] == 0;
   h.birth = s.e_birth[e];
@@ -295,8 +296,13 @@ GBP_DEV void load_head(const Store &s, const double *__restrict__ pubr, int p, i
   h.dsafe = s.e_dsafe[e];
 }
 
+#ifdef GBP_ITER_MAXREG  // experiments: exact register cap instead of a CTAs-per-SM target
+#define GBP_ITER_BOUNDS __maxnreg__(GBP_ITER_MAXREG)
+#else
+#define GBP_ITER_BOUNDS __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
+#endif
 template <bool EXT, bool INT>
-__global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
+__global__ void GBP_ITER_BOUNDS
     k_iterate(const __grid_constant__ Store s, const int p, const uint32_t epoch) {
   const int V = s.V;
   const int rpw = 32 / V;
@@ -306,7 +312,6 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
   const int i = int(lane) - rl * V;
   const int64_t r = warp * rpw + rl;
   const bool live = rl < rpw && r < s.Nloc;
-  const int64_t NV = s.NV;
   const int64_t vi = live ? r * V + i : 0;
 
   const double *const pubr = s.pub[p];
@@ -321,14 +326,14 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
   int32_t nlow = 0;
   if (live) {
 #if GBP_PREFETCH
-    prefetch_planes<20>(s.m_dynL, NV, vi);
-    prefetch_planes<20>(s.m_dynR, NV, vi);
-    prefetch_planes<4>(s.m_obs, NV, vi);
-    prefetch_planes<3>(s.m_trk, NV, vi);
-    prefetch_planes<4>(s.prior_eta, NV, vi);
+    prefetch_planes<20, 20>(s, s.m_dynL, vi);
+    prefetch_planes<20, 20>(s, s.m_dynR, vi);
+    prefetch_planes<4, 4>(s, s.m_obs, vi);
+    prefetch_planes<3, 3>(s, s.m_trk, vi);
+    prefetch_planes<4, 4>(s, s.prior_eta, vi);
     prefetch_l2(s.prior_lam + vi);
     if (INT) {
-      prefetch_planes<20>(pubr, NV, vi);
+      prefetch_planes<kRec, 20>(s, pubr, vi);
       prefetch_l2(s.dyn_dt + vi);
     }
 #endif
@@ -340,8 +345,8 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
     double ma[4], mb[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      ma[k] = pubr[(20 + k) * NV + vi];
-      mb[k] = s.bel_ext[(20 + k) * NV + vi];
+      ma[k] = pubr[s.at<kRec>(20 + k, vi)];
+      mb[k] = s.bel_ext[s.at<24>(20 + k, vi)];
     }
     idle = f_idle != 0;
     ant = f_ant != 0;
@@ -362,21 +367,21 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
     const int64_t e0 = eo0;
     const int64_t e1 = (i >= 1) ? eo1 : e0;  // variable 0 has no InterRobot factors
     const int64_t elow = e0 + nlow;          // edges [e0, elow) have a lower robot id than r
+    // where the own factors' messages sit in the inbox order (id.rs:25-61): after the mirror
+    // factors of lower-id robots, before those of higher-id robots
+    const int64_t eadd = elow < e1 ? elow : e1;
     double mu_sent[2] = {0.0, 0.0};
     if (e1 > e0) {
-      mu_sent[0] = s.mu_ext[vi];
-      mu_sent[1] = s.mu_ext[NV + vi];
+      mu_sent[0] = s.mu_ext[s.at<2>(0, vi)];
+      mu_sent[1] = s.mu_ext[s.at<2>(1, vi)];
     }
-    bool added = false;
     int A_next = (e0 < e1) ? s.enbr[e0] : 0;
-    for (int64_t e = e0; e < e1; ++e) {
+    for (int64_t e = e0;; ++e) {
+      if (e == eadd) add_internal(s, vi, i, ae, al);
+      if (e >= e1) break;
       EdgeHead h;
       load_head(s, pubr, p, e, A_next, V, i, h);
       if (e + 1 < e1) A_next = s.enbr[e + 1];
-      if (!added && e >= elow) {
-        add_internal(s, vi, i, ae, al);
-        added = true;
-      }
       const int64_t m = e * (V - 1) + (i - 1);
       if (h.act) {
         const bool a_ne = h.epochA > h.birth;
@@ -392,7 +397,7 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
           double rec[20];
           const int64_t va = int64_t(h.A) * V + i;
 #pragma unroll
-          for (int k = 0; k < 20; ++k) rec[k] = pubr[k * NV + va];
+          for (int k = 0; k < 20; ++k) rec[k] = pubr[s.at<kRec>(k, va)];
           const double tiny = s.tiny_scale * double(h.rnum + uint64_t(i - 1));
           ok = interrobot_message(e < elow, muA, mb, a_ne, rec, h.dsafe, tiny, s.lm_ir, me, ml);
         }
@@ -424,32 +429,32 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
         }
       }
     }
-    if (!added) add_internal(s, vi, i, ae, al);
     double cov[16];
     bool valid = false;
     const bool taken = belief_moments(ae, al, mu, cov, valid);
     if (taken) {
 #pragma unroll
-      for (int k = 0; k < 16; ++k) s.cov[k * NV + vi] = cov[k];
+      for (int k = 0; k < 16; ++k) s.cov[s.at<16>(k, vi)] = cov[k];
       s.valid[vi] = valid ? 1 : 0;
     }
-    s.mu_ext[vi] = mu[0];
-    s.mu_ext[NV + vi] = mu[1];
+    s.mu_ext[s.at<2>(0, vi)] = mu[0];
+    s.mu_ext[s.at<2>(1, vi)] = mu[1];
     if (!INT || !do_int) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) s.bel_ext[k * NV + vi] = ae[k];
+      for (int k = 0; k < 4; ++k) s.bel_ext[s.at<24>(k, vi)] = ae[k];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) s.bel_ext[(4 + k) * NV + vi] = al[k];
+      for (int k = 0; k < 16; ++k) s.bel_ext[s.at<24>(4 + k, vi)] = al[k];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) s.bel_ext[(20 + k) * NV + vi] = mu[k];
+      for (int k = 0; k < 4; ++k) s.bel_ext[s.at<24>(20 + k, vi)] = mu[k];
     }
     itf += 1;
   }
   if (EXT) {
     __syncwarp();
-    if (do_ext && i == 1) {
-      // delivered edges hold mu_ext again; undelivered ones are (stay) frozen
-      for (int64_t e = eo0; e < eo1; ++e) {
+    if (do_ext) {
+      // delivered edges hold mu_ext again; undelivered ones are (stay) frozen; the robot's lanes
+      // share the edges (every lane has finished reading e_frozen: __syncwarp above)
+      for (int64_t e = eo0 + i; e < eo1; e += V) {
         const int A = s.enbr[e];
         const uint8_t fr = (s.en_ir && s.antenna[A] != 0 && s.idle[A] == 0) ? 0 : 1;
         const uint8_t cur = s.e_frozen[e];
@@ -468,11 +473,11 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
       own_ne = s.pub_epoch[p][vi] > 0u;
       double R[20];
 #pragma unroll
-      for (int k = 0; k < 20; ++k) R[k] = pubr[k * NV + vi];
+      for (int k = 0; k < 20; ++k) R[k] = pubr[s.at<kRec>(k, vi)];
 #pragma unroll
-      for (int k = 0; k < 20; ++k) toR[k] = s.m_dynR[k * NV + vi];
+      for (int k = 0; k < 20; ++k) toR[k] = s.m_dynR[s.at<20>(k, vi)];
 #pragma unroll
-      for (int k = 0; k < 20; ++k) toL[k] = s.m_dynL[k * NV + vi];
+      for (int k = 0; k < 20; ++k) toL[k] = s.m_dynL[s.at<20>(k, vi)];
       const bool hasR = !is_empty_marker(toR[0]), hasL = !is_empty_marker(toL[0]);
 #pragma unroll
       for (int k = 0; k < 20; ++k) {
@@ -493,11 +498,11 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
           double ne[4], nl[16];
           if (dyn_message<1>(M, fromL_ne, toR, ne, nl)) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) s.m_dynL[k * NV + vi] = ne[k];
+            for (int k = 0; k < 4; ++k) s.m_dynL[s.at<20>(k, vi)] = ne[k];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) s.m_dynL[(4 + k) * NV + vi] = nl[k];
+            for (int k = 0; k < 16; ++k) s.m_dynL[s.at<20>(4 + k, vi)] = nl[k];
           } else {
-            s.m_dynL[vi] = empty_marker();
+            s.m_dynL[s.at<20>(0, vi)] = empty_marker();
           }
         }
         if (i <= V - 2) {  // Dynamic factor i -> variable i (slot 0)
@@ -505,11 +510,11 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
           double ne[4], nl[16];
           if (dyn_message<0>(M, fromR_ne, toL, ne, nl)) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) s.m_dynR[k * NV + vi] = ne[k];
+            for (int k = 0; k < 4; ++k) s.m_dynR[s.at<20>(k, vi)] = ne[k];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) s.m_dynR[(4 + k) * NV + vi] = nl[k];
+            for (int k = 0; k < 16; ++k) s.m_dynR[s.at<20>(4 + k, vi)] = nl[k];
           } else {
-            s.m_dynR[vi] = empty_marker();
+            s.m_dynR[s.at<20>(0, vi)] = empty_marker();
           }
         }
       }
@@ -518,7 +523,7 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
         double x[4], x0[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          x[k] = pubr[(20 + k) * NV + vi];
+          x[k] = pubr[s.at<kRec>(20 + k, vi)];
           x0[k] = own_ne ? x[k] : 0.0;  // Obstacle inbox starts Empty (factorgraph.rs:310-322)
         }
         if (s.en_obs) obstacle_update(s, vi, x0);
@@ -534,37 +539,34 @@ __global__ void __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
       const int64_t e0 = eo0;
       const int64_t e1 = (i >= 1) ? eo1 : e0;
       const int64_t elow = e0 + nlow;
-      bool added = false;
-      for (int64_t e = e0; e < e1; ++e) {
-        if (!added && e >= elow) {
-          add_internal(s, vi, i, ae, al);
-          added = true;
-        }
+      const int64_t eadd = elow < e1 ? elow : e1;
+      for (int64_t e = e0;; ++e) {
+        if (e == eadd) add_internal(s, vi, i, ae, al);
+        if (e >= e1) break;
 #if GBP_MIRROR_MASK
         if (EXT && do_ext && e - e0 < 64 && !((mir_ne >> (e - e0)) & 1ull)) continue;  // known Empty
 #endif
         add_mirror(s, e * (V - 1) + (i - 1), ae, al);
       }
-      if (!added) add_internal(s, vi, i, ae, al);
       double cov[16];
       bool valid = false;
       const bool taken = belief_moments(ae, al, mu, cov, valid);
       if (taken) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) s.cov[k * NV + vi] = cov[k];
+        for (int k = 0; k < 16; ++k) s.cov[s.at<16>(k, vi)] = cov[k];
         s.valid[vi] = valid ? 1 : 0;
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) pubw[k * NV + vi] = ae[k];
+      for (int k = 0; k < 4; ++k) pubw[s.at<kRec>(k, vi)] = ae[k];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) pubw[(4 + k) * NV + vi] = al[k];
+      for (int k = 0; k < 16; ++k) pubw[s.at<kRec>(4 + k, vi)] = al[k];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) pubw[(20 + k) * NV + vi] = mu[k];
+      for (int k = 0; k < 4; ++k) pubw[s.at<kRec>(20 + k, vi)] = mu[k];
       s.pub_epoch[1 - p][vi] = epoch;
     } else if (live) {
       // idle robot: its record is carried over to the other buffer unchanged
 #pragma unroll
-      for (int k = 0; k < kRec; ++k) pubw[k * NV + vi] = pubr[k * NV + vi];
+      for (int k = 0; k < kRec; ++k) pubw[s.at<kRec>(k, vi)] = pubr[s.at<kRec>(k, vi)];
       s.pub_epoch[1 - p][vi] = s.pub_epoch[p][vi];
     }
   }

@@ -252,10 +252,10 @@ __global__ void k_halo_pack(Store s, int p, int ws, PeerOffsets po, const int32_
   const int64_t ps = cnt * Vm1, at = jj * Vm1 + (i - 1);
   double *blk = buf + po.start[q] * halo_doubles_per_robot(s.V);
   const int32_t r = sendlist[j];
-  const int64_t vi = int64_t(r) * s.V + i, NV = s.NV;
+  const int64_t vi = int64_t(r) * s.V + i;
   const double *rec = s.pub[p];
 #pragma unroll
-  for (int k = 0; k < 22; ++k) blk[k * ps + at] = rec[k * NV + vi];
+  for (int k = 0; k < 22; ++k) blk[k * ps + at] = rec[s.at<kRec>(k, vi)];
   blk[22 * ps + at] = double(s.pub_epoch[p][vi]);
   if (i == 1) {
     blk[kHaloPlanes * ps + jj] = double(int(s.antenna[r] != 0) | (int(s.idle[r] != 0) << 1));
@@ -276,10 +276,10 @@ __global__ void k_halo_unpack(Store s, int p, int ws, PeerOffsets po, const doub
   const int64_t ps = cnt * Vm1, at = jj * Vm1 + (i - 1);
   const double *blk = buf + po.start[q] * halo_doubles_per_robot(s.V);
   const int64_t slot = int64_t(s.Nloc) + j;
-  const int64_t vi = slot * s.V + i, NV = s.NV;
+  const int64_t vi = slot * s.V + i;
   double *rec = s.pub[p];
 #pragma unroll
-  for (int k = 0; k < 22; ++k) rec[k * NV + vi] = blk[k * ps + at];
+  for (int k = 0; k < 22; ++k) rec[s.at<kRec>(k, vi)] = blk[k * ps + at];
   s.pub_epoch[p][vi] = uint32_t(blk[22 * ps + at]);
   if (i == 1) {
     const int bits = int(blk[kHaloPlanes * ps + jj]);

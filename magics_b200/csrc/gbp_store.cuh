@@ -6,6 +6,14 @@
 // for every variable of every robot, index vi = robot*V + i, so a warp reading
 // one component touches consecutive doubles.
 //
+// Per-variable arrays with P > 1 components are TILED (GBP_TILED, the default): 32
+// consecutive variable slots form a tile, a tile holds its P component rows of 32
+// doubles (256 B) back to back, element (k, vi) sits at ((vi >> 5) * P + k) * 32 + (vi & 31).
+// A thread computes one base address per array and reaches every component of its
+// record with an immediate offset (k * 256 B) instead of a 64-bit multiply-add per
+// load; a record tile is one contiguous block (pub: 6 KiB), which is also the unit a
+// bulk copy can move.  -DGBP_TILED=0 keeps whole planes of stride NV (k * NV + vi).
+//
 // What is stored is the minimum from which every inbox of the reference can be
 // rebuilt bit-for-bit:
 //   pub[p]   belief record (eta4, Lambda16, mu4) of each variable as of its last
@@ -22,16 +30,32 @@
 // while writing its own new record to pub[1-p].
 #pragma once
 #include <cstdint>
+#include <cuda_runtime.h>
 
 namespace gbp {
 
 constexpr int kRec = 24;  // eta 0..3, lambda 4..19 (row major), mu 20..23
 
+#ifndef GBP_TILED
+#define GBP_TILED 1
+#endif
+constexpr int kTile = 32;  // variable slots per tile; NV is kept a multiple of it
+
 struct Store {
   int32_t N;     // robots resident on this device (local + ghost slots)
   int32_t Nloc;  // robots this device iterates (slots [0, Nloc))
   int32_t V;     // variables per robot
-  int64_t NV;    // plane stride = capacity * V
+  int64_t NV;    // variable-slot capacity: capacity * V rounded up to a whole tile
+
+  // Index of component k of variable slot vi in a per-variable array of P components.
+  template <int P>
+  __host__ __device__ __forceinline__ int64_t at(int k, int64_t vi) const {
+#if GBP_TILED
+    return (vi >> 5) * int64_t(P * kTile) + (vi & 31) + int64_t(k) * kTile;
+#else
+    return int64_t(k) * NV + vi;
+#endif
+  }
 
   // ---- per variable -------------------------------------------------------
   double *prior_eta;     // [4][NV]   VariablePrior.information_vector

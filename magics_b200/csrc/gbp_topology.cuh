@@ -168,8 +168,8 @@ __global__ void k_mirror_move(Store s, int p, int64_t total, int32_t Vm1, const 
     }
     const int64_t vi = int64_t(lo) * s.V + (i + 1);
     const double *rec = s.latest[lo] ? s.bel_ext : s.pub[p];
-    nfrozen[t] = rec[20 * s.NV + vi];
-    nfrozen[nEV + t] = rec[21 * s.NV + vi];
+    nfrozen[t] = rec[s.at<kRec>(20, vi)];
+    nfrozen[nEV + t] = rec[s.at<kRec>(21, vi)];
     return;
   }
   const int64_t o = old * Vm1 + i;
