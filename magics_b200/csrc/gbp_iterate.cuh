@@ -46,9 +46,13 @@ constexpr size_t kIterSmemBytes = 0;
 // profiles/README.md r01d: +5 %; prefetching the neighbours' records as well, staging through
 // shared memory with cp.async, or parking accumulators in shared memory for 16 warps/SM were
 // all slower than this; so was, r01f, letting a robot's lanes split its edges and pull each
-// neighbour's position means / epoch / radio bits into L1 ahead of the edge loop: +-0.)
+// neighbour's position means / epoch / radio bits into L1 ahead of the edge loop: +-0; and sending
+// the read-once records around L1 with ld.global.cg: -10 %.)
 #ifndef GBP_PREFETCH
 #define GBP_PREFETCH 1
+#endif
+#ifndef GBP_INT_ACC
+#define GBP_INT_ACC 1
 #endif
 #ifndef GBP_MIRROR_MASK
 #define GBP_MIRROR_MASK 1
@@ -83,52 +87,47 @@ GBP_DEV double sdf_measure(const Store &s, double x_pos, double y_pos, uint32_t 
 // Sum of the messages variable i holds from its own non-InterRobot factors, in
 // FactorId order dyn(i-1) < dyn(i) < obs(i) < trk(i) (id.rs:25-61; creation order
 // robot.rs:1228-1334), added onto (ae, al) (variable.rs:263-271).
+// One stored Dynamic-factor message (eta4, Lambda16) added onto (ae, al) unless it is Empty.
+// The record is loaded whole before its Empty marker is looked at: the slots of factors a variable
+// does not have (dyn(i-1) of variable 0, ...) hold the marker for ever, so no index test is needed
+// and no load waits on another load.
+GBP_DEV void add_dyn_stored(const Store &s, const double *__restrict__ arr, int64_t vi, double (&ae)[4],
+                            double (&al)[16]) {
+  double m[20];
+#pragma unroll
+  for (int k = 0; k < 20; ++k) m[k] = arr[s.at<20>(k, vi)];
+  if (!is_empty_marker(m[0])) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ae[k] = ae[k] + m[k];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) al[k] = al[k] + m[4 + k];
+  }
+}
+// The stored Obstacle and Tracking messages (factored form, expanded on use).
+GBP_DEV void add_unary_stored(const Store &s, int64_t vi, double (&ae)[4], double (&al)[16]) {
+  double o[4], t[3];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o[k] = s.m_obs[s.at<4>(k, vi)];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) t[k] = s.m_trk[s.at<3>(k, vi)];
+  if (!is_empty_marker(o[0])) {
+    const double J[4] = {o[0], o[1], o[2], o[2]};
+    unary_add(J, o[3], s.lm_obs, ae, al);
+  }
+  if (!is_empty_marker(t[0])) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const double g = t[k] * s.lm_trk;
+      ae[k] = ae[k] + g * t[2];
+#pragma unroll
+      for (int l = 0; l < 2; ++l) al[k * 4 + l] = al[k * 4 + l] + g * t[l];
+    }
+  }
+}
 GBP_DEV void add_internal(const Store &s, int64_t vi, int i, double (&ae)[4], double (&al)[16]) {
-  // Every record is loaded whole before its Empty marker is looked at: the slots of
-  // factors a variable does not have (dyn(i-1) of variable 0, ...) hold the marker for
-  // ever, so no index test is needed and no load waits on another load.
-  {
-    double m[20];
-#pragma unroll
-    for (int k = 0; k < 20; ++k) m[k] = s.m_dynL[s.at<20>(k, vi)];
-    if (!is_empty_marker(m[0])) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) ae[k] = ae[k] + m[k];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) al[k] = al[k] + m[4 + k];
-    }
-  }
-  {
-    double m[20];
-#pragma unroll
-    for (int k = 0; k < 20; ++k) m[k] = s.m_dynR[s.at<20>(k, vi)];
-    if (!is_empty_marker(m[0])) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) ae[k] = ae[k] + m[k];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) al[k] = al[k] + m[4 + k];
-    }
-  }
-  {
-    double o[4], t[3];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) o[k] = s.m_obs[s.at<4>(k, vi)];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) t[k] = s.m_trk[s.at<3>(k, vi)];
-    if (!is_empty_marker(o[0])) {
-      const double J[4] = {o[0], o[1], o[2], o[2]};
-      unary_add(J, o[3], s.lm_obs, ae, al);
-    }
-    if (!is_empty_marker(t[0])) {
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const double g = t[k] * s.lm_trk;
-        ae[k] = ae[k] + g * t[2];
-#pragma unroll
-        for (int l = 0; l < 2; ++l) al[k * 4 + l] = al[k * 4 + l] + g * t[l];
-      }
-    }
-  }
+  add_dyn_stored(s, s.m_dynL, vi, ae, al);
+  add_dyn_stored(s, s.m_dynR, vi, ae, al);
+  add_unary_stored(s, vi, ae, al);
 }
 
 // Adds the stored mirror message m if there is one; returns whether there was.
@@ -261,7 +260,13 @@ GBP_DEV void obstacle_update(const Store &s, int64_t vi, const double (&x)[4]) {
   const double h2 = sdf_measure(s, px, py);
   py -= delta;
   const double h3 = sdf_measure(s, px, py);  // columns 2 and 3 perturb the velocity only
-  const double j0 = (h1 - h0) / delta, j1 = (h2 - h0) / delta, j2 = (h3 - h0) / delta;
+  // three quotients by the same delta; bit-identical to the three divisions.  (A plain `0.0 / delta`
+  // — every robot away from obstacles — takes the division's slow path: 2.5 % of the kernel's
+  // instructions in the r01f profile.)
+  const double num[3] = {h1 - h0, h2 - h0, h3 - h0};
+  double quo[3];
+  divide_all(num, delta, quo);
+  const double j0 = quo[0], j1 = quo[1], j2 = quo[2];
   const double v0 = ((((0.0 + j0 * x[0]) + j1 * x[1]) + j2 * x[2]) + j2 * x[3]) + (0.0 - h);
   s.m_obs[s.at<4>(0, vi)] = j0;
   s.m_obs[s.at<4>(1, vi)] = j1;
@@ -274,7 +279,8 @@ GBP_DEV void obstacle_update(const Store &s, int64_t vi, const double (&x)[4]) {
 // radio/idle bits and the edge scalars: 10 small loads with one dependent level (A = enbr[e]).
 // A's (eta, Lambda) — 20 doubles — is fetched only when the factor is not skipped
 // (InterRobotFactor::skip, interrobot.rs:213-226): in a swarm most robots within comms range
-// are outside safety range.  (Loading the head one edge ahead was measured slower: registers.)
+// are outside safety range.  (Loading the head one edge ahead, or two heads at once in front of one
+// non-unrolled edge body, was measured slower: registers / spills.)
 struct EdgeHead {
   double mu0, mu1, dsafe;
   uint64_t rnum;
@@ -294,6 +300,60 @@ GBP_DEV void load_head(const Store &s, const double *__restrict__ pubr, int p, i
   h.frozen = (s.e_frozen[e] & 1) != 0;
   h.rnum = s.e_rnum[e];
   h.dsafe = s.e_dsafe[e];
+}
+
+// External half, one edge (receiver r <- neighbour A) for variable i: evaluates A's InterRobot
+// factor from A's published record (or keeps the stored mirror message when nothing is delivered)
+// and adds the message to the running inbox sum (ae, al).
+GBP_DEV void ext_edge(const Store &s, const double *__restrict__ pubr, const EdgeHead &h, int64_t e, int64_t e0,
+                      int64_t elow, int V, int i, const double (&mu_sent)[2], double (&ae)[4], double (&al)[16],
+                      uint64_t &mir_ne) {
+  const int64_t m = e * (V - 1) + (i - 1);
+  if (h.act) {
+    const bool a_ne = h.epochA > h.birth;
+    const double muA[2] = {a_ne ? h.mu0 : 0.0, a_ne ? h.mu1 : 0.0};
+    double mb[2] = {mu_sent[0], mu_sent[1]};
+    if (h.frozen) {  // rare: edge just created, or A's radio was off at the last delivery
+      mb[0] = s.mu_frozen[m];
+      mb[1] = s.mu_frozen[s.EV + m];
+    }
+    bool ok = false;
+    double me[2], ml[4];
+    if (!interrobot_skip(e < elow, muA, mb, h.dsafe)) {
+      double rec[20];
+      const int64_t va = int64_t(h.A) * V + i;
+#pragma unroll
+      for (int k = 0; k < 20; ++k) rec[k] = pubr[s.at<kRec>(k, va)];
+      const double tiny = s.tiny_scale * double(h.rnum + uint64_t(i - 1));
+      ok = interrobot_message(e < elow, muA, mb, a_ne, rec, h.dsafe, tiny, s.lm_ir, me, ml);
+    }
+    if (ok) {
+      s.mir[m] = me[0];
+      s.mir[s.EV + m] = me[1];
+      s.mir[2 * s.EV + m] = ml[0];
+      s.mir[3 * s.EV + m] = ml[1];
+      s.mir[4 * s.EV + m] = ml[2];
+      s.mir[5 * s.EV + m] = ml[3];
+      ae[0] = ae[0] + me[0];
+      ae[1] = ae[1] + me[1];
+      al[0] = al[0] + ml[0];
+      al[1] = al[1] + ml[1];
+      al[4] = al[4] + ml[2];
+      al[5] = al[5] + ml[3];
+      if (e - e0 < 64) mir_ne |= 1ull << (e - e0);
+    } else {
+      s.mir[m] = empty_marker();
+    }
+  } else {
+    // undelivered: the variable keeps the old message
+    if (add_mirror(s, m, ae, al) && e - e0 < 64) mir_ne |= 1ull << (e - e0);
+    // ... and A's factor keeps the mean it already holds from this variable
+    // while this variable's belief moves on (robot.rs:1851): freeze it
+    if (!h.frozen) {
+      s.mu_frozen[m] = mu_sent[0];
+      s.mu_frozen[s.EV + m] = mu_sent[1];
+    }
+  }
 }
 
 #ifdef GBP_ITER_MAXREG  // experiments: exact register cap instead of a CTAs-per-SM target
@@ -382,52 +442,7 @@ __global__ void GBP_ITER_BOUNDS
       EdgeHead h;
       load_head(s, pubr, p, e, A_next, V, i, h);
       if (e + 1 < e1) A_next = s.enbr[e + 1];
-      const int64_t m = e * (V - 1) + (i - 1);
-      if (h.act) {
-        const bool a_ne = h.epochA > h.birth;
-        const double muA[2] = {a_ne ? h.mu0 : 0.0, a_ne ? h.mu1 : 0.0};
-        double mb[2] = {mu_sent[0], mu_sent[1]};
-        if (h.frozen) {  // rare: edge just created, or A's radio was off at the last delivery
-          mb[0] = s.mu_frozen[m];
-          mb[1] = s.mu_frozen[s.EV + m];
-        }
-        bool ok = false;
-        double me[2], ml[4];
-        if (!interrobot_skip(e < elow, muA, mb, h.dsafe)) {
-          double rec[20];
-          const int64_t va = int64_t(h.A) * V + i;
-#pragma unroll
-          for (int k = 0; k < 20; ++k) rec[k] = pubr[s.at<kRec>(k, va)];
-          const double tiny = s.tiny_scale * double(h.rnum + uint64_t(i - 1));
-          ok = interrobot_message(e < elow, muA, mb, a_ne, rec, h.dsafe, tiny, s.lm_ir, me, ml);
-        }
-        if (ok) {
-          s.mir[m] = me[0];
-          s.mir[s.EV + m] = me[1];
-          s.mir[2 * s.EV + m] = ml[0];
-          s.mir[3 * s.EV + m] = ml[1];
-          s.mir[4 * s.EV + m] = ml[2];
-          s.mir[5 * s.EV + m] = ml[3];
-          ae[0] = ae[0] + me[0];
-          ae[1] = ae[1] + me[1];
-          al[0] = al[0] + ml[0];
-          al[1] = al[1] + ml[1];
-          al[4] = al[4] + ml[2];
-          al[5] = al[5] + ml[3];
-          if (e - e0 < 64) mir_ne |= 1ull << (e - e0);
-        } else {
-          s.mir[m] = empty_marker();
-        }
-      } else {
-        // undelivered: the variable keeps the old message
-        if (add_mirror(s, m, ae, al) && e - e0 < 64) mir_ne |= 1ull << (e - e0);
-        // ... and A's factor keeps the mean it already holds from this variable
-        // while this variable's belief moves on (robot.rs:1851): freeze it
-        if (!h.frozen) {
-          s.mu_frozen[m] = mu_sent[0];
-          s.mu_frozen[s.EV + m] = mu_sent[1];
-        }
-      }
+      ext_edge(s, pubr, h, e, e0, elow, V, i, mu_sent, ae, al, mir_ne);
     }
     double cov[16];
     bool valid = false;
@@ -492,6 +507,24 @@ __global__ void GBP_ITER_BOUNDS
     shfl_vec(toR, fromL_ne, 1, lane);    // lane i receives var i-1 -> dyn(i-1)
     shfl_vec(toL, fromR_ne, -1, lane);   // lane i receives var i+1 -> dyn(i)
     if (do_int) {
+      // Inbox sum of the variable iteration that follows (variable.rs:263-271), in FactorId order:
+      // prior, mirror messages of lower-id robots, dyn(i-1), dyn(i), obstacle, tracking, mirror
+      // messages of higher-id robots.  GBP_INT_ACC: the two Dynamic messages are added straight from
+      // the registers they were computed in instead of being read back after the store.
+      double ae[4], al[16];
+      const int64_t e0 = eo0;
+      const int64_t e1 = (i >= 1) ? eo1 : e0;
+      const int64_t elow = e0 + nlow;
+      const int64_t eadd = elow < e1 ? elow : e1;
+#if GBP_INT_ACC
+      load_prior(s, vi, ae, al);
+      for (int64_t e = e0; e < eadd; ++e) {
+#if GBP_MIRROR_MASK
+        if (EXT && do_ext && e - e0 < 64 && !((mir_ne >> (e - e0)) & 1ull)) continue;  // known Empty
+#endif
+        add_mirror(s, e * (V - 1) + (i - 1), ae, al);
+      }
+#endif
       if (s.en_dyn) {
         if (i >= 1) {  // Dynamic factor i-1 -> variable i (slot 1)
           const DynM M = dyn_potential(s.dyn_dt[vi - 1], s.qs_dyn);
@@ -501,10 +534,16 @@ __global__ void GBP_ITER_BOUNDS
             for (int k = 0; k < 4; ++k) s.m_dynL[s.at<20>(k, vi)] = ne[k];
 #pragma unroll
             for (int k = 0; k < 16; ++k) s.m_dynL[s.at<20>(4 + k, vi)] = nl[k];
+#if GBP_INT_ACC
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ae[k] = ae[k] + ne[k];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) al[k] = al[k] + nl[k];
+#endif
           } else {
             s.m_dynL[s.at<20>(0, vi)] = empty_marker();
           }
-        }
+        }  // variable 0 has no dyn(i-1): its slot holds the Empty marker for ever
         if (i <= V - 2) {  // Dynamic factor i -> variable i (slot 0)
           const DynM M = dyn_potential(s.dyn_dt[vi], s.qs_dyn);
           double ne[4], nl[16];
@@ -513,11 +552,23 @@ __global__ void GBP_ITER_BOUNDS
             for (int k = 0; k < 4; ++k) s.m_dynR[s.at<20>(k, vi)] = ne[k];
 #pragma unroll
             for (int k = 0; k < 16; ++k) s.m_dynR[s.at<20>(4 + k, vi)] = nl[k];
+#if GBP_INT_ACC
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ae[k] = ae[k] + ne[k];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) al[k] = al[k] + nl[k];
+#endif
           } else {
             s.m_dynR[s.at<20>(0, vi)] = empty_marker();
           }
-        }
+        }  // likewise the last variable and dyn(i)
       }
+#if GBP_INT_ACC
+      else {  // Dynamic factors disabled: whatever they sent while enabled is still in the inbox
+        add_dyn_stored(s, s.m_dynL, vi, ae, al);
+        add_dyn_stored(s, s.m_dynR, vi, ae, al);
+      }
+#endif
       if (i >= 1 && i <= V - 2 && (s.en_obs || s.en_trk)) {
         // linearisation point = mean of the variable's last message (factor/mod.rs:336-349)
         double x[4], x0[4];
@@ -534,12 +585,16 @@ __global__ void GBP_ITER_BOUNDS
       itf += 1;
 
       // ---- belief update + new record (variable.rs:251-297)
-      double ae[4], al[16];
+#if GBP_INT_ACC
+      add_unary_stored(s, vi, ae, al);
+      for (int64_t e = eadd; e < e1; ++e) {
+#if GBP_MIRROR_MASK
+        if (EXT && do_ext && e - e0 < 64 && !((mir_ne >> (e - e0)) & 1ull)) continue;  // known Empty
+#endif
+        add_mirror(s, e * (V - 1) + (i - 1), ae, al);
+      }
+#else
       load_prior(s, vi, ae, al);
-      const int64_t e0 = eo0;
-      const int64_t e1 = (i >= 1) ? eo1 : e0;
-      const int64_t elow = e0 + nlow;
-      const int64_t eadd = elow < e1 ? elow : e1;
       for (int64_t e = e0;; ++e) {
         if (e == eadd) add_internal(s, vi, i, ae, al);
         if (e >= e1) break;
@@ -548,6 +603,7 @@ __global__ void GBP_ITER_BOUNDS
 #endif
         add_mirror(s, e * (V - 1) + (i - 1), ae, al);
       }
+#endif
       double cov[16];
       bool valid = false;
       const bool taken = belief_moments(ae, al, mu, cov, valid);

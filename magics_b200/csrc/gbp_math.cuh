@@ -60,10 +60,11 @@ GBP_DEV void divide_all(const double (&c)[N], double det, double (&o)[N]) {
 #pragma unroll
   for (int k = 0; k < N; ++k) o[k] = c[k] / det;
 #else
-  bool ok = exp_in_safe_range(det);
+  // no short-circuit: N independent tests OR-ed together instead of N branches
+  bool bad = !exp_in_safe_range(det);
 #pragma unroll
-  for (int k = 0; k < N; ++k) ok = ok && (c[k] == 0.0 || exp_in_safe_range(c[k]));
-  if (ok) {
+  for (int k = 0; k < N; ++k) bad |= (c[k] != 0.0) & !exp_in_safe_range(c[k]);
+  if (!bad) {
     const double y = 1.0 / det;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
@@ -139,14 +140,16 @@ GBP_DEV bool inv4_rows01(const double (&m)[16], double (&r0)[4], double (&r1)[4]
 // when the new covariance is finite.
 GBP_DEV bool belief_moments(const double (&eta)[4], const double (&lam)[16], double (&mu)[4],
                             double (&cov)[16], bool &valid) {
+  // `any(|x| *x - 1e-6 > 0.0)` (variable.rs:276): x - 1e-6 > 0 exactly when x > 1e-6 (the
+  // difference of two doubles never rounds across zero), for NaN and infinities too
   bool nz = false;
 #pragma unroll
-  for (int k = 0; k < 16; ++k) nz = nz || (lam[k] - 1e-6 > 0.0);
+  for (int k = 0; k < 16; ++k) nz |= lam[k] > 1e-6;
   if (!nz) return false;
   if (!inv4(lam, cov)) return false;
   bool fin = true;
 #pragma unroll
-  for (int k = 0; k < 16; ++k) fin = fin && isfinite(cov[k]);
+  for (int k = 0; k < 16; ++k) fin &= isfinite(cov[k]);
   valid = fin;
   if (fin) {
 #pragma unroll
@@ -233,7 +236,7 @@ GBP_DEV bool dyn_message(const DynM &M, bool other_nonempty, const double (&o)[2
       const double aa = ((r & 1) == dc) ? M.m[A + (r >> 1)][A + cc] : 0.0;
       const double v = aa - tl;
       lam[r * 4 + c] = v;
-      inf = inf || isinf(v);
+      inf |= isinf(v);
     }
   }
   return !inf;
