@@ -9,9 +9,15 @@
 // a literal evaluation as long as the file is compiled with -fmad=false.
 #pragma once
 #include <cstdint>
+#ifdef GBP_HOST_MATH_TEST
+// tests/host_math/: the same header compiled by g++ (-ffp-contract=off) so that the device
+// arithmetic can be compared with the oracle bit for bit without a GPU
+#include "host_math_shim.h"
+#else
 #include <cuda_runtime.h>
-
 #define GBP_DEV __device__ __forceinline__
+#define GBP_NOINLINE_DEV __device__ __noinline__
+#endif
 
 namespace gbp {
 
@@ -51,7 +57,7 @@ GBP_DEV bool exp_in_safe_range(double v) {
   return e - 523u < 1001u;  // 2^-500 <= |v| < 2^501
 }
 // out-of-line: the rare operands share one copy of the IEEE division sequence
-__device__ __noinline__ double plain_div(double x, double det) { return x / det; }
+GBP_NOINLINE_DEV double plain_div(double x, double det) { return x / det; }
 
 // o[k] = c[k] / det for N numerators, bit-identical to the N divisions.
 template <int N>
@@ -87,7 +93,55 @@ GBP_DEV void divide_all(const double (&c)[N], double det, double (&o)[N]) {
 #endif
 }
 
+#ifndef GBP_INV4_DECOUPLED
+#define GBP_INV4_DECOUPLED 1
+#endif
 GBP_DEV bool inv4(const double (&m)[16], double (&o)[16]) {
+#if GBP_INV4_DECOUPLED
+  // State order is (x, y, vx, vy).  Unless an Obstacle, Tracking or InterRobot message is present the
+  // x and y chains never mix: every entry m[r][c] with r + c odd is an exact zero.  Each cofactor of
+  // the general expansion below then keeps two of its six triple products (the other four have an
+  // exact-zero factor and add +-0), eight cofactors vanish altogether, and det = m00*C00 + m02*C02.
+  // Same products, same association, same order: every non-zero of the result has the bits of the
+  // general formula (the sign of an exact zero is not tracked).  A non-finite entry reaches det
+  // (all eight entries feed it) and sends the matrix down the general path, where 0 * inf matters.
+  if ((m[1] == 0.0) & (m[3] == 0.0) & (m[4] == 0.0) & (m[6] == 0.0) & (m[9] == 0.0) & (m[11] == 0.0) &
+      (m[12] == 0.0) & (m[14] == 0.0)) {
+    double c[8];
+    c[0] = (m[5] * m[10]) * m[15] - (m[7] * m[10]) * m[13];  // minor<0,0>
+    c[1] = (m[7] * m[8]) * m[13] - (m[5] * m[8]) * m[15];    // minor<0,2>
+    const double det = m[0] * c[0] + m[2] * c[1];
+    if (isfinite(det)) {
+      if (det == 0.0) return false;
+      c[2] = (m[0] * m[10]) * m[15] - (m[2] * m[8]) * m[15];  // minor<1,1>
+      c[3] = (m[2] * m[8]) * m[13] - (m[0] * m[10]) * m[13];  // minor<1,3>
+      c[4] = (m[2] * m[7]) * m[13] - (m[2] * m[5]) * m[15];   // minor<2,0>
+      c[5] = (m[0] * m[5]) * m[15] - (m[0] * m[7]) * m[13];   // minor<2,2>
+      c[6] = (m[2] * m[7]) * m[8] - (m[0] * m[7]) * m[10];    // minor<3,1>
+      c[7] = (m[0] * m[5]) * m[10] - (m[2] * m[5]) * m[8];    // minor<3,3>
+      double q[8];
+      divide_all(c, det, q);
+      // adjugate placement: cofactor <SR,SC> lands at [SC][SR]
+      o[0] = q[0];
+      o[1] = 0.0;
+      o[2] = q[4];
+      o[3] = 0.0;
+      o[4] = 0.0;
+      o[5] = q[2];
+      o[6] = 0.0;
+      o[7] = q[6];
+      o[8] = q[1];
+      o[9] = 0.0;
+      o[10] = q[5];
+      o[11] = 0.0;
+      o[12] = 0.0;
+      o[13] = q[3];
+      o[14] = 0.0;
+      o[15] = q[7];
+      return true;
+    }
+  }
+#endif
   double c[16];
   c[0] = minor3<0, 0>(m);
   c[4] = -minor3<0, 1>(m);

@@ -1,0 +1,43 @@
+// host_math.cpp — C entry points over the DEVICE math header compiled for the host, so the
+// per-node arithmetic of the CUDA engine can be checked against the oracle without a GPU.
+#define GBP_HOST_MATH_TEST 1
+#include "../../magics_b200/csrc/gbp_math.cuh"
+
+extern "C" {
+int hm_inv4(const double *m, double *out) {
+  double a[16], o[16] = {0};
+  for (int k = 0; k < 16; ++k) a[k] = m[k];
+  const bool ok = gbp::inv4(a, o);
+  for (int k = 0; k < 16; ++k) out[k] = o[k];
+  return ok ? 1 : 0;
+}
+int hm_divide_all16(const double *c, double det, double *out) {
+  double a[16], o[16];
+  for (int k = 0; k < 16; ++k) a[k] = c[k];
+  gbp::divide_all(a, det, o);
+  for (int k = 0; k < 16; ++k) out[k] = o[k];
+  return 0;
+}
+// returns 0: not taken, 1: taken (cov, valid written; mu only if valid)
+int hm_belief_moments(const double *eta, const double *lam, double *mu, double *cov, int *valid) {
+  double e[4], l[16], m[4], c[16];
+  for (int k = 0; k < 4; ++k) e[k] = eta[k], m[k] = mu[k];
+  for (int k = 0; k < 16; ++k) l[k] = lam[k], c[k] = cov[k];
+  bool v = false;
+  const bool t = gbp::belief_moments(e, l, m, c, v);
+  for (int k = 0; k < 4; ++k) mu[k] = m[k];
+  for (int k = 0; k < 16; ++k) cov[k] = c[k];
+  *valid = v ? 1 : 0;
+  return t ? 1 : 0;
+}
+// Dynamic factor message to slot `keep` given the other variable's message (eta4, Lambda16) or none.
+int hm_dyn_message(int keep, double dt, double qs, int other_nonempty, const double *other, double *eta, double *lam) {
+  const gbp::DynM M = gbp::dyn_potential(dt, qs);
+  double o[20], e[4], l[16];
+  for (int k = 0; k < 20; ++k) o[k] = other ? other[k] : 0.0;
+  const bool ok = keep ? gbp::dyn_message<1>(M, other_nonempty != 0, o, e, l) : gbp::dyn_message<0>(M, other_nonempty != 0, o, e, l);
+  for (int k = 0; k < 4; ++k) eta[k] = e[k];
+  for (int k = 0; k < 16; ++k) lam[k] = l[k];
+  return ok ? 1 : 0;
+}
+}
