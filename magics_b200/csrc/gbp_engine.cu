@@ -162,7 +162,7 @@ void schedule_half(int kind, int n, int max, uint8_t *out) {
 // ---- small kernels -------------------------------------------------------------
 
 // VariableNode::new (variable.rs:140-166) for the variables [first, first+count):
-// expects prior_lam already uploaded; `mu0` = the initial means as [4][count] planes.
+// expects prior_lam already uploaded; `mu0` = the initial means and delta_t as [5][count] planes.
 __global__ void k_init_vars(Store s, int64_t first, int64_t count, const double *__restrict__ mu0) {
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= count) return;
@@ -213,6 +213,14 @@ __global__ void k_init_vars(Store s, int64_t first, int64_t count, const double 
   s.trk_last[s.at<2>(0, vi)] = float(mu[0]);  // with_last_measurement (factor/mod.rs:279-283)
   s.trk_last[s.at<2>(1, vi)] = float(mu[1]);
   s.trk_value[vi] = 0.0;
+  // DynamicFactor i between variables i and i+1 (robot.rs:1228-1255); the last variable has none
+  const double dt = mu0[4 * count + t];
+  double q11, q12, q22;
+  gbp::dyn_q(dt, s.qs_dyn, q11, q12, q22);
+  s.dyn_c[s.at<4>(0, vi)] = dt;
+  s.dyn_c[s.at<4>(1, vi)] = q11;
+  s.dyn_c[s.at<4>(2, vi)] = q12;
+  s.dyn_c[s.at<4>(3, vi)] = q22;
 }
 
 // VariableNode::change_prior + FactorGraph::change_prior_of_variable for variable
@@ -910,7 +918,7 @@ int reserve_robots(gbp_world *w, int64_t newcap) {
   CK(regrow(s.m_dynR, 20, oldNV, newNV, used, st, true));
   CK(regrow(s.m_obs, 4, oldNV, newNV, used, st, true));
   CK(regrow(s.m_trk, 3, oldNV, newNV, used, st, true));
-  CK(regrow(s.dyn_dt, 1, oldNV, newNV, used, st));
+  CK(regrow(s.dyn_c, 4, oldNV, newNV, used, st, true));
   CK(regrow(s.trk_record, 1, oldNV, newNV, used, st));
   CK(regrow(s.trk_timeout, 1, oldNV, newNV, used, st));
   CK(regrow(s.trk_last, 2, oldNV, newNV, used, st, true));
@@ -1427,7 +1435,7 @@ void gbp_world_destroy(gbp_world_t *w) {
   free_edge_set(w, &w->edges[0]);
   free_edge_set(w, &w->edges[1]);
   void *ptrs[] = {s.prior_eta, s.prior_lam, s.pub[0], s.pub[1], s.pub_epoch[0], s.pub_epoch[1], s.bel_ext,
-                  s.mu_ext, s.cov, s.valid, s.m_dynL, s.m_dynR, s.m_obs, s.m_trk, s.dyn_dt,
+                  s.mu_ext, s.cov, s.valid, s.m_dynL, s.m_dynR, s.m_obs, s.m_trk, s.dyn_c,
                   s.trk_record, s.trk_timeout, s.trk_last, s.trk_value, s.radius, s.t0, s.pos, s.antenna,
                   s.idle, s.finished, s.latest, s.iter_factor, s.gid, s.next_wp, s.coll_hits, w->coll_totals, s.wp_off, s.wp_xy, s.eoff,
                   s.nlow, w->t_nlow, w->t_result_dev, w->sdf_dev, w->t_cx,
@@ -1558,11 +1566,11 @@ int gbp_world_add_robots(gbp_world_t *w, int32_t n, const float *radii, const ui
       if (i < V - 1) dt[t] = double(t0[r] * float(timesteps[i + 1] - timesteps[i]));  // :1232
     }
   }
-  double *d_mu = nullptr;  // [4][nv] staging; k_init_vars reads the means from it
-  CK(dalloc(d_mu, size_t(4) * size_t(nv)));
+  double *d_mu = nullptr;  // [5][nv] staging: the four mean planes and delta_t; k_init_vars reads them
+  CK(dalloc(d_mu, size_t(5) * size_t(nv)));
   CK(cudaMemcpyAsync(d_mu, mu.data(), size_t(4) * size_t(nv) * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_mu + size_t(4) * size_t(nv), dt.data(), size_t(nv) * sizeof(double), cudaMemcpyHostToDevice, st));
   CK(upload_planes(s.prior_lam, newNV, used, pl.data(), 1, nv, st));
-  CK(upload_planes(s.dyn_dt, newNV, used, dt.data(), 1, nv, st));
   CK(upload_planes(s.radius, N1cap, N0, rad.data(), 1, n, st));
   CK(upload_planes(s.t0, N1cap, N0, t0.data(), 1, n, st));
   CK(upload_planes(s.pos, N1cap, N0, pos.data(), 2, n, st));

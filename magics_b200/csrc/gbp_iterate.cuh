@@ -47,7 +47,9 @@ constexpr size_t kIterSmemBytes = 0;
 // shared memory with cp.async, or parking accumulators in shared memory for 16 warps/SM were
 // all slower than this; so was, r01f, letting a robot's lanes split its edges and pull each
 // neighbour's position means / epoch / radio bits into L1 ahead of the edge loop: +-0; and sending
-// the read-once records around L1 with ld.global.cg: -10 %.)
+// the read-once records around L1 with ld.global.cg: -10 %; staging the heads of 8 edges at once in
+// per-thread shared-memory slots (two dependent round trips per robot instead of K): -9 %; loading
+// the Dynamic-factor constants and the linearisation mean with the first internal batch: -1.5 %.)
 #ifndef GBP_PREFETCH
 #define GBP_PREFETCH 1
 #endif
@@ -322,9 +324,10 @@ GBP_DEV void ext_edge(const Store &s, const double *__restrict__ pubr, const Edg
     if (!interrobot_skip(e < elow, muA, mb, h.dsafe)) {
       double rec[20];
       const int64_t va = int64_t(h.A) * V + i;
+      const uint64_t rnum = h.rnum;
 #pragma unroll
       for (int k = 0; k < 20; ++k) rec[k] = pubr[s.at<kRec>(k, va)];
-      const double tiny = s.tiny_scale * double(h.rnum + uint64_t(i - 1));
+      const double tiny = s.tiny_scale * double(rnum + uint64_t(i - 1));
       ok = interrobot_message(e < elow, muA, mb, a_ne, rec, h.dsafe, tiny, s.lm_ir, me, ml);
     }
     if (ok) {
@@ -394,7 +397,7 @@ __global__ void GBP_ITER_BOUNDS
     prefetch_l2(s.prior_lam + vi);
     if (INT) {
       prefetch_planes<kRec, 20>(s, pubr, vi);
-      prefetch_l2(s.dyn_dt + vi);
+      prefetch_planes<4, 4>(s, s.dyn_c, vi);
     }
 #endif
     const uint8_t f_idle = s.idle[r], f_ant = s.antenna[r], f_latest = s.latest[r];
@@ -527,7 +530,10 @@ __global__ void GBP_ITER_BOUNDS
 #endif
       if (s.en_dyn) {
         if (i >= 1) {  // Dynamic factor i-1 -> variable i (slot 1)
-          const DynM M = dyn_potential(s.dyn_dt[vi - 1], s.qs_dyn);
+          double dcL[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) dcL[k] = s.dyn_c[s.at<4>(k, vi - 1)];
+          const DynM M = dyn_potential_q(dcL[0], dcL[1], dcL[2], dcL[3]);
           double ne[4], nl[16];
           if (dyn_message<1>(M, fromL_ne, toR, ne, nl)) {
 #pragma unroll
@@ -545,7 +551,10 @@ __global__ void GBP_ITER_BOUNDS
           }
         }  // variable 0 has no dyn(i-1): its slot holds the Empty marker for ever
         if (i <= V - 2) {  // Dynamic factor i -> variable i (slot 0)
-          const DynM M = dyn_potential(s.dyn_dt[vi], s.qs_dyn);
+          double dcR[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) dcR[k] = s.dyn_c[s.at<4>(k, vi)];
+          const DynM M = dyn_potential_q(dcR[0], dcR[1], dcR[2], dcR[3]);
           double ne[4], nl[16];
           if (dyn_message<0>(M, fromR_ne, toL, ne, nl)) {
 #pragma unroll

@@ -220,10 +220,17 @@ GBP_DEV bool belief_moments(const double (&eta)[4], const double (&lam)[16], dou
 struct DynM {
   double m[4][4];
 };
-GBP_DEV DynM dyn_potential(double dt, double qs) {
+// The three distinct entries of Qi^-1 / sigma^2 (dynamic.rs:22-52): they depend on the factor's
+// delta_t and sigma only, so the engine evaluates them once per factor (k_init_vars) and keeps them
+// next to delta_t in Store::dyn_c — six divisions per thread and launch less, same bits.
+GBP_DEV void dyn_q(double dt, double qs, double &q11, double &q12, double &q22) {
   const double p3 = 1.0 / ((dt * dt) * dt);
   const double p2 = 1.0 / (dt * dt);
-  const double q11 = (12.0 * p3) * qs, q12 = (-6.0 * p2) * qs, q22 = (4.0 / dt) * qs;
+  q11 = (12.0 * p3) * qs;
+  q12 = (-6.0 * p2) * qs;
+  q22 = (4.0 / dt) * qs;
+}
+GBP_DEV DynM dyn_potential_q(double dt, double q11, double q12, double q22) {
   const double a[4] = {q11, dt * q11 + q12, -q11, -q12};
   const double b[4] = {q12, dt * q12 + q22, -q12, -q22};
   DynM r;
@@ -235,6 +242,11 @@ GBP_DEV DynM dyn_potential(double dt, double qs) {
     r.m[k][3] = -b[k];
   }
   return r;
+}
+GBP_DEV DynM dyn_potential(double dt, double qs) {
+  double q11, q12, q22;
+  dyn_q(dt, qs, q11, q12, q22);
+  return dyn_potential_q(dt, q11, q12, q22);
 }
 
 // FactorNode::update for a DynamicFactor, one outgoing message

@@ -70,7 +70,7 @@ struct Store {
   double *m_dynR;        // [20][NV]  message from Dynamic factor i
   double *m_obs;         // [4][NV]   Obstacle message as (J0, J1, J2=J3, v0)
   double *m_trk;         // [3][NV]   Tracking message as (J0, J1, v0)
-  double *dyn_dt;        // [NV]      delta_t of Dynamic factor i (f32 widened)
+  double *dyn_c;         // [4][NV]   Dynamic factor i: delta_t (f32 widened) and q11, q12, q22 (gbp_math.cuh dyn_q)
   uint32_t *trk_record;  // [NV]      Tracking.record
   int32_t *trk_timeout;  // [NV]      TrackingFactor.timeout (-1 = None)
   float *trk_last;       // [2][NV]   LastMeasurement.pos (f32)
