@@ -106,6 +106,26 @@ void gbp_world_destroy(gbp_world_t *w);
  * (simulation_loader.rs:52, robot.rs:1274): RGB8, row 0 = top, uploaded once. */
 int gbp_world_set_sdf(gbp_world_t *w, const uint8_t *rgb8, int32_t width, int32_t height);
 
+/* `gbp_environment::Environment` as far as SDF generation reads it
+ * (crates/gbp_environment/src/lib.rs:40-75,940-971; settings.sdf: resolution, expansion, blur). */
+typedef struct gbp_environment {
+  int32_t nrows, ncols;      /* tiles.grid: rows of box-drawing characters */
+  const uint32_t *tiles;     /* [nrows*ncols] Unicode code points, row-major (TileGrid::get_tile) */
+  float tile_size;           /* tiles.settings.tile-size */
+  float path_width;          /* tiles.settings.path-width, a fraction of the tile */
+  uint32_t resolution;       /* tiles.settings.sdf.resolution: pixels per tile */
+  float expansion;           /* tiles.settings.sdf.expansion */
+  float blur;                /* tiles.settings.sdf.blur (sigma = blur * resolution pixels) */
+  int32_t n_obstacles;       /* placeable obstacles: must be 0 (is_placeable_obstacle is not built yet) */
+} gbp_environment_t;
+
+/* Replaces env_to_png::env_to_sdf_image (crates/env_to_png/src/lib.rs:149-163: env_to_image :166-207 +
+ * image::imageops::blur), called at scenario load (simulation_loader.rs:153-161): rasterises the tile grid
+ * and blurs it on the device.  rgb8: [nrows*resolution][ncols*resolution][3], R = G = B, row 0 = top. */
+int gbp_env_to_sdf_image(const gbp_environment_t *env, int32_t device, uint8_t *rgb8);
+/* Same, but the image never leaves the device: it becomes the world's SDF (gbp_world_set_sdf). */
+int gbp_world_set_sdf_from_environment(gbp_world_t *w, const gbp_environment_t *env);
+
 /* Replaces RobotBundle::new for n robots (robot.rs:1134-1355): V variables
  * (prior 1e30*I on first/last, non-finite -> 0 on the rest, variable.rs:146-148),
  * V-1 Dynamic, V-2 Obstacle, V-2 Tracking factors.

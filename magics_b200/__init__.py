@@ -19,5 +19,6 @@ from .config import (  # noqa: F401
     SCHEDULE_SOON_AS_POSSIBLE,
     GbpConfig,
 )
-from .world import (World, gbp_schedule, get_variable_timesteps, library_path, load_library,  # noqa: F401
-                    pinned_empty)
+from .environment import Environment  # noqa: F401
+from .world import (World, env_to_sdf_image, gbp_schedule, get_variable_timesteps, library_path,  # noqa: F401
+                    load_library, pinned_empty)

@@ -22,6 +22,7 @@
 #include "gbp_math.cuh"
 #include "gbp_shard.cuh"
 #include "gbp_store.cuh"
+#include "gbp_sdf.cuh"
 #include "gbp_topology.cuh"
 
 using gbp::Store;
@@ -1501,6 +1502,101 @@ int gbp_world_set_sdf(gbp_world_t *w, const uint8_t *rgb8, int32_t width, int32_
   w->s.sdf = w->sdf_dev;
   w->s.sdf_w = width;
   w->s.sdf_h = height;
+  refresh_scalars(w);
+  return 0;
+}
+
+namespace {
+// image 0.25.1 `imageops::sample::gaussian` in f32 (host side: the tap weights depend on sigma and the
+// integer tap offset only; the kernels normalise them per window)
+float env_gaussian(float x, float r) {
+  return (1.0f / (std::sqrt(2.0f * 3.14159265358979323846f) * r)) * std::exp(-(x * x) / (2.0f * (r * r)));
+}
+
+// env_to_png::env_to_sdf_image (crates/env_to_png/src/lib.rs:149-163) on the current device: leaves the
+// single-channel image in *d_gray (cudaMalloc'ed, caller owns it).
+int env_to_sdf_device(const gbp_environment_t *env, cudaStream_t st, uint8_t **d_gray, uint32_t *Wo, uint32_t *Ho,
+                      int64_t *launches) {
+  if (!env || !env->tiles || env->nrows <= 0 || env->ncols <= 0 || env->resolution == 0)
+    return fail(GBP_ERR_BAD_ARGUMENT, "environment: empty tile grid or zero resolution");
+  // Percentage::new asserts (env_to_png/src/lib.rs:53-57, Sub/Add :126-142)
+  const float pw = env->path_width - env->expansion;
+  if (!(env->path_width >= 0.0f && env->path_width <= 1.0f && env->expansion >= 0.0f && env->expansion <= 1.0f &&
+        env->blur >= 0.0f && env->blur <= 1.0f && pw >= 0.0f))
+    return fail(GBP_ERR_BAD_ARGUMENT, "environment: path-width, expansion and blur are percentages in [0, 1], "
+                                      "path-width >= expansion");
+  if (env->n_obstacles != 0)
+    return fail(GBP_ERR_BAD_ARGUMENT, "environment: placeable obstacles are not rasterised by this build");
+  gbp::EnvParams e{env->nrows, env->ncols, env->resolution, env->tile_size, env->path_width, env->expansion};
+  const uint64_t W64 = uint64_t(env->ncols) * env->resolution, H64 = uint64_t(env->nrows) * env->resolution;
+  if (W64 > 65535u * 64u || H64 > 65535u) return fail(GBP_ERR_BAD_ARGUMENT, "environment: image too large");
+  const uint32_t W = uint32_t(W64), H = uint32_t(H64);
+  const size_t npx = size_t(W) * H, ntile = size_t(env->nrows) * env->ncols;
+  uint32_t *d_tiles = nullptr;
+  uint8_t *d_img = nullptr;
+  CK(dalloc(d_tiles, ntile));
+  CK(dalloc(d_img, npx));
+  CK(cudaMemcpyAsync(d_tiles, env->tiles, ntile * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  const dim3 grid((W + 255) / 256, H);
+  gbp::k_env_raster<<<grid, 256, 0, st>>>(e, d_tiles, d_img);
+  CK(cudaGetLastError());
+  *launches += 1;
+  const float blur_pixels = env->blur * float(env->resolution);
+  if (!(blur_pixels < 1.0f)) {
+    const float sigma = blur_pixels <= 0.0f ? 1.0f : blur_pixels;
+    const float support = 2.0f * sigma;
+    const int D = int(std::ceil(support)) + 2;
+    std::vector<float> wt(size_t(2 * D + 1));
+    for (int d = -D; d <= D; ++d) wt[size_t(d + D)] = env_gaussian(float(d), sigma);
+    float *d_w = nullptr, *d_tmp = nullptr;
+    CK(dalloc(d_w, wt.size()));
+    CK(dalloc(d_tmp, npx));
+    CK(cudaMemcpyAsync(d_w, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    gbp::k_blur_rows<<<grid, 256, 0, st>>>(d_img, d_tmp, W, H, support, d_w, D);
+    gbp::k_blur_cols<<<grid, 256, 0, st>>>(d_tmp, d_img, W, H, support, d_w, D);
+    CK(cudaGetLastError());
+    *launches += 2;
+    CK(cudaStreamSynchronize(st));  // wt goes out of scope
+    cudaFree(d_w);
+    cudaFree(d_tmp);
+  }
+  CK(cudaStreamSynchronize(st));
+  cudaFree(d_tiles);
+  *d_gray = d_img;
+  *Wo = W;
+  *Ho = H;
+  return 0;
+}
+}  // namespace
+
+int gbp_env_to_sdf_image(const gbp_environment_t *env, int32_t device, uint8_t *rgb8) {
+  if (!rgb8) return fail(GBP_ERR_BAD_ARGUMENT, "gbp_env_to_sdf_image: null output");
+  CK(cudaSetDevice(device));
+  uint8_t *d_gray = nullptr, *d_rgb = nullptr;
+  uint32_t W = 0, H = 0;
+  int64_t launches = 0;
+  if (int rc = env_to_sdf_device(env, nullptr, &d_gray, &W, &H, &launches)) return rc;
+  const size_t npx = size_t(W) * H;
+  CK(dalloc(d_rgb, 3 * npx));
+  gbp::k_gray_to_rgb<<<blocks_for(int64_t(npx), 256), 256>>>(d_gray, d_rgb, npx);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(rgb8, d_rgb, 3 * npx, cudaMemcpyDeviceToHost));
+  cudaFree(d_gray);
+  cudaFree(d_rgb);
+  return 0;
+}
+
+int gbp_world_set_sdf_from_environment(gbp_world_t *w, const gbp_environment_t *env) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (set_device(w)) return GBP_ERR_CUDA;
+  uint8_t *d_gray = nullptr;
+  uint32_t W = 0, H = 0;
+  if (int rc = env_to_sdf_device(env, w->stream, &d_gray, &W, &H, &w->launches)) return rc;
+  cudaFree(w->sdf_dev);
+  w->sdf_dev = d_gray;
+  w->s.sdf = w->sdf_dev;
+  w->s.sdf_w = int32_t(W);
+  w->s.sdf_h = int32_t(H);
   refresh_scalars(w);
   return 0;
 }

@@ -87,6 +87,19 @@ def get_variable_timesteps(lookahead_horizon: int, lookahead_multiple: int) -> n
     return out[:n].copy()
 
 
+def env_to_sdf_image(env, device: int = 0) -> np.ndarray:
+    """`env_to_png::env_to_sdf_image` (crates/env_to_png/src/lib.rs:149-163) on the device -> (h, w, 3) u8."""
+    lib = load_library()
+    h, w = env.image_shape
+    out = np.empty((h, w, 3), np.uint8)
+    ce, keep = env.c_struct()
+    rc = lib.gbp_env_to_sdf_image(C.byref(ce), C.c_int32(device), _p(out, C.c_uint8))
+    del keep
+    if rc != 0:
+        raise RuntimeError(f"gbp_env_to_sdf_image failed ({rc}): {lib.gbp_last_error().decode()}")
+    return out
+
+
 def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
     """numpy array backed by page-locked host memory (gbp_host_alloc_pinned): host buffers handed to
     the upload / read-back calls DMA at PCIe speed instead of being staged by the driver.
@@ -201,6 +214,12 @@ class World:
         rgb8 = np.ascontiguousarray(rgb8, np.uint8)
         h, w = rgb8.shape[:2]
         self._call("gbp_world_set_sdf", _p(rgb8, C.c_uint8), C.c_int32(w), C.c_int32(h))
+
+    def set_sdf_from_environment(self, env):
+        """env_to_sdf_image on the device; the image stays there as the world's SDF."""
+        ce, keep = env.c_struct()
+        self._call("gbp_world_set_sdf_from_environment", C.byref(ce))
+        del keep
 
     def add_robots(self, radii, timesteps, init_means, positions, wp_offsets, wp_xy):
         radii = np.ascontiguousarray(radii, np.float32)

@@ -1044,6 +1044,68 @@ void expand(int kind, int n, int max, uint8_t *out) {
 // ---------------------------------------------------------------------------
 // C entry points for ctypes (tests / bench only)
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// crates/env_to_png/src/lib.rs — Environment -> SDF image: rasterise the tile
+// grid (env_to_image :166-207, is_tile_obstacle :340-479), then `image::imageops::blur`.
+// Placeable obstacles (`is_placeable_obstacle` :283-336) are not restated: the BASELINE scenarios
+// (circle, junction twoway, complex) have `obstacles: []`.
+// Third party, absent from /root/reference: image 0.25.1 `imageops::blur` (Cargo.lock) — restated
+// from its published source: sigma <= 0 -> 1; separable Gaussian with support 2*sigma, vertical pass
+// into an f32 image, horizontal pass clamped to [0, 255] and rounded half away from zero; per output
+// row/column the window is [floor(c - support), ceil(c + support)) around c = index + 0.5, clamped
+// to the image, weights gaussian(i - index, sigma) in f32 normalised by their in-order sum, taps
+// accumulated in order as t += v * w.  PARITY UNPINNED: no reference test covers the blur.
+// ---------------------------------------------------------------------------
+namespace envpng {
+// image_to_tile_units (:213-223)
+inline void image_to_tile_units(uint32_t px, uint32_t py, uint32_t res, float tile_size, float &ox, float &oy) {
+  const float x = float(px) + 0.5f, y = float(py) + 0.5f;
+  ox = x / float(res) * tile_size;
+  oy = y / float(res) * tile_size;
+}
+// offset_modulus (:241-243)
+inline float offset_modulus(float value, float modulus) {
+  return -(std::ceil(value / modulus) * modulus - value) / modulus + 1.0f;
+}
+// image_to_tile_coords (:249-258)
+inline void image_to_tile_coords(uint32_t px, uint32_t py, uint32_t res, uint64_t &tx, uint64_t &ty) {
+  tx = uint64_t(std::floor(float(px) / float(res)));
+  ty = uint64_t(std::floor(float(py) / float(res)));
+}
+// is_tile_obstacle (:340-479); tile = Unicode code point
+inline bool is_tile_obstacle(uint32_t tile, float path_width_in, float px, float py, float expansion) {
+  const float path_width = path_width_in - expansion;
+  const float almost_full = 1.0f - path_width;
+  const float ow = almost_full / 2.0f;       // obstacle_width
+  const float opw = ow + path_width;         // obstacle_and_path_width
+  const float half_lo = 0.5f - expansion / 2.0f, half_hi = 0.5f + expansion / 2.0f;
+  switch (tile) {
+    case 0x2500: return py < ow || py > opw;                                        // ─
+    case 0x2502: return px < ow || px > opw;                                        // │
+    case 0x2574: return py < ow || py > opw || px > half_lo;                        // ╴
+    case 0x2576: return py < ow || py > opw || px < half_hi;                        // ╶
+    case 0x2577: return px < ow || px > opw || py < half_hi;                        // ╷
+    case 0x2575: return px < ow || px > opw || py > half_lo;                        // ╵
+    case 0x250C: return px < ow || py < ow || (px > opw && py > opw);               // ┌
+    case 0x2510: return px > opw || py < ow || (px < ow && py > opw);               // ┐
+    case 0x2514: return px < ow || py > opw || (px > opw && py < ow);               // └
+    case 0x2518: return px > opw || py > opw || (px < ow && py < ow);               // ┘
+    case 0x252C: return py < ow || (py > opw && (px < ow || px > opw));             // ┬
+    case 0x2534: return py > opw || (py < ow && (px < ow || px > opw));             // ┴
+    case 0x251C: return px < ow || (px > opw && (py < ow || py > opw));             // ├
+    case 0x2524: return px > opw || (px < ow && (py < ow || py > opw));             // ┤
+    case 0x253C: return (px < ow || px > opw) && (py < ow || py > opw);             // ┼
+    case 0x20: return true;                                                         // ' '
+    default: return false;
+  }
+}
+// image 0.25.1 imageops::sample::gaussian
+inline float gaussian(float x, float r) {
+  return (1.0f / (std::sqrt(2.0f * 3.14159265358979323846f) * r)) * std::exp(-(x * x) / (2.0f * (r * r)));
+}
+inline int64_t clampi(int64_t v, int64_t lo, int64_t hi) { return v < lo ? lo : (v > hi ? hi : v); }
+}  // namespace envpng
+
 extern "C" {
 
 int gbpo_schedule(int32_t kind, uint8_t internal, uint8_t external, uint8_t *oi, uint8_t *oe) {
@@ -1101,6 +1163,88 @@ int gbpo_inv4(const double *m, double *out) {
   if (!r) return 0;
   std::copy(r->a.begin(), r->a.end(), out);
   return 1;
+}
+
+
+void gbpo_image_to_tile_units(uint32_t px, uint32_t py, uint32_t res, float tile_size, float *out2) {
+  envpng::image_to_tile_units(px, py, res, tile_size, out2[0], out2[1]);
+}
+void gbpo_tile_units_to_percentage(float x, float y, float tile_size, float *out2) {  // :230-238
+  out2[0] = envpng::offset_modulus(x, tile_size);
+  out2[1] = envpng::offset_modulus(y, tile_size);
+}
+void gbpo_image_to_tile_coords(uint32_t px, uint32_t py, uint32_t res, uint64_t *out2) {
+  envpng::image_to_tile_coords(px, py, res, out2[0], out2[1]);
+}
+int gbpo_is_tile_obstacle(uint32_t tile, float path_width, float px, float py, float expansion) {
+  return envpng::is_tile_obstacle(tile, path_width, px, py, expansion) ? 1 : 0;
+}
+// env_to_sdf_image (:149-163): out_rgb is [nrows*res][ncols*res][3]
+int gbpo_env_to_sdf_image(int nrows, int ncols, const uint32_t *tiles, float tile_size, float path_width,
+                          uint32_t res, float expansion, float blur_percent, uint8_t *out_rgb) {
+  using namespace envpng;
+  const uint32_t W = uint32_t(ncols) * res, H = uint32_t(nrows) * res;
+  std::vector<uint8_t> img(size_t(W) * H);
+  for (uint32_t y = 0; y < H; ++y)
+    for (uint32_t x = 0; x < W; ++x) {
+      uint64_t tx, ty;
+      image_to_tile_coords(x, y, res, tx, ty);
+      float ux, uy;
+      image_to_tile_units(x, y, res, tile_size, ux, uy);
+      const float fx = offset_modulus(ux, tile_size), fy = offset_modulus(uy, tile_size);
+      if (ty >= uint64_t(nrows) || tx >= uint64_t(ncols)) return -1;  // "Tile not found"
+      img[size_t(y) * W + x] = is_tile_obstacle(tiles[ty * ncols + tx], path_width, fx, fy, expansion) ? 0 : 255;
+    }
+  const float blur_pixels = blur_percent * float(res);
+  if (!(blur_pixels < 1.0f)) {
+    const float sigma = blur_pixels <= 0.0f ? 1.0f : blur_pixels;
+    const float support = 2.0f * sigma;
+    // vertical_sample -> f32 image
+    std::vector<float> tmp(size_t(W) * H);
+    std::vector<float> ws;
+    for (uint32_t oy = 0; oy < H; ++oy) {
+      float c = (float(oy) + 0.5f) * 1.0f;
+      const int64_t left = clampi(int64_t(std::floor(c - support)), 0, int64_t(H) - 1);
+      const int64_t right = clampi(int64_t(std::ceil(c + support)), left + 1, int64_t(H));
+      c = c - 0.5f;
+      ws.clear();
+      float sum = 0.0f;
+      for (int64_t i = left; i < right; ++i) {
+        const float w = gaussian((float(i) - c) / 1.0f, sigma);
+        ws.push_back(w);
+        sum += w;
+      }
+      for (float &w : ws) w /= sum;
+      for (uint32_t x = 0; x < W; ++x) {
+        float t = 0.0f;
+        for (size_t k = 0; k < ws.size(); ++k) t += float(img[size_t(left + int64_t(k)) * W + x]) * ws[k];
+        tmp[size_t(oy) * W + x] = t;
+      }
+    }
+    // horizontal_sample -> u8, clamp + round half away from zero (FloatNearest)
+    for (uint32_t ox = 0; ox < W; ++ox) {
+      float c = (float(ox) + 0.5f) * 1.0f;
+      const int64_t left = clampi(int64_t(std::floor(c - support)), 0, int64_t(W) - 1);
+      const int64_t right = clampi(int64_t(std::ceil(c + support)), left + 1, int64_t(W));
+      c = c - 0.5f;
+      ws.clear();
+      float sum = 0.0f;
+      for (int64_t i = left; i < right; ++i) {
+        const float w = gaussian((float(i) - c) / 1.0f, sigma);
+        ws.push_back(w);
+        sum += w;
+      }
+      for (float &w : ws) w /= sum;
+      for (uint32_t y = 0; y < H; ++y) {
+        float t = 0.0f;
+        for (size_t k = 0; k < ws.size(); ++k) t += tmp[size_t(y) * W + size_t(left + int64_t(k))] * ws[k];
+        const float cl = t < 0.0f ? 0.0f : (t > 255.0f ? 255.0f : t);
+        img[size_t(y) * W + ox] = uint8_t(std::round(cl));
+      }
+    }
+  }
+  for (size_t k = 0; k < img.size(); ++k) out_rgb[3 * k] = out_rgb[3 * k + 1] = out_rgb[3 * k + 2] = img[k];
+  return 0;
 }
 
 void *gbpo_create(const void *cfg) {

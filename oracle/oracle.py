@@ -114,6 +114,20 @@ def inv4(m: np.ndarray):
     return out if ok else None
 
 
+def env_to_sdf_image(env) -> np.ndarray:
+    """CPU restatement of env_to_png::env_to_sdf_image (crates/env_to_png/src/lib.rs:149-163) -> (h, w, 3) u8.
+    `env` is a magics_b200.environment.Environment (plain data)."""
+    h, w = env.image_shape
+    out = np.empty((h, w, 3), np.uint8)
+    codes = env.tile_codes()
+    rc = lib().gbpo_env_to_sdf_image(env.nrows, env.ncols, _p(codes, C.c_uint32), C.c_float(env.tile_size),
+                                     C.c_float(env.path_width), C.c_uint32(env.resolution), C.c_float(env.expansion),
+                                     C.c_float(env.blur), _p(out, C.c_uint8))
+    if rc != 0:
+        raise RuntimeError(f"gbpo_env_to_sdf_image failed ({rc})")
+    return out
+
+
 class OracleWorld:
     """Same surface as magics_b200.World, executed by the CPU restatement."""
 

@@ -9,6 +9,8 @@ Sources (all `#[cfg(test)]` blocks of the reference):
   crates/magics/src/utils.rs:95-133           -> variable_timesteps.json
   crates/magics/src/factorgraph/factor/marginalise_factor_distance.rs:182-233
                                               -> marginalise.json
+  crates/env_to_png/src/lib.rs:482-533 (tests) and config/scenarios/*/environment.yaml
+                                              -> env_to_png.json
 """
 import json
 import os
@@ -77,7 +79,42 @@ def marginalise():
     }
 
 
+def env_to_png():
+    # crates/env_to_png/src/lib.rs:482-533: four #[test]s.  Read against the crate's own code, three of
+    # their assertions are stale (image_to_tile_units adds 0.5 to the pixel index since :218;
+    # tile_units_to_percentage returns the fraction INTO the tile, 0.23 not 0.3; a '─' tile only looks
+    # at y, so (0.1, 0.6) is free): they are recorded as written, flagged `consistent_with_code`.
+    src = open(f"{REF}/env_to_png/src/lib.rs").read()
+    assert "fn test_image_to_tile_coords" in src and "assert_eq!(tile_coords.x, 1);" in src
+    kats = [
+        {"fn": "image_to_tile_units", "args": {"px": 23, "py": 56, "resolution": 100, "tile_size": 10.0},
+         "expected": [2.3, 5.6], "consistent_with_code": False, "code_gives": "(px + 0.5) / res * tile = [2.35, 5.65]"},
+        {"fn": "tile_units_to_percentage", "args": {"x": 2.3, "y": 5.6, "tile_size": 10.0},
+         "expected": [0.3, 0.6], "consistent_with_code": False, "code_gives": "offset_modulus = [0.23, 0.56]"},
+        {"fn": "image_to_tile_coords", "args": {"px": 134, "py": 240, "resolution": 100}, "expected": [1, 2],
+         "consistent_with_code": True},
+        {"fn": "is_tile_obstacle", "args": {"tile": "─", "path_width": 0.5, "x": 0.3, "y": 0.6, "expansion": 0.0},
+         "expected": False, "consistent_with_code": True},
+        {"fn": "is_tile_obstacle", "args": {"tile": "─", "path_width": 0.5, "x": 0.1, "y": 0.6, "expansion": 0.0},
+         "expected": True, "consistent_with_code": False, "code_gives": "False: a horizontal tile only tests y"},
+    ]
+    # the tile-only environments of the BASELINE scenarios (obstacles: [])
+    import yaml
+
+    envs = {}
+    for name in ("Structured Junction Twoway", "Collaborative Complex", "Junction Twoway", "Structured Junction"):
+        path = f"/root/reference/config/scenarios/{name}/environment.yaml"
+        d = yaml.safe_load(open(path))
+        if d.get("obstacles"):
+            continue
+        s = d["tiles"]["settings"]
+        envs[name] = {"grid": d["tiles"]["grid"], "tile_size": s["tile-size"], "path_width": s["path-width"],
+                      "resolution": s["sdf"]["resolution"], "expansion": s["sdf"]["expansion"], "blur": s["sdf"]["blur"]}
+    return {"kats": kats, "environments": envs}
+
+
 if __name__ == "__main__":
+    json.dump(env_to_png(), open(os.path.join(HERE, "env_to_png.json"), "w"), indent=1, ensure_ascii=False)
     s = schedules()
     json.dump(s, open(os.path.join(HERE, "schedules.json"), "w"), indent=1)
     json.dump(timesteps(), open(os.path.join(HERE, "variable_timesteps.json"), "w"), indent=1)
