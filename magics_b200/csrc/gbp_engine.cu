@@ -492,6 +492,15 @@ struct gbp_world {
   // a second stream, so the next tick's kernels overlap the PCIe transfer
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_gathered = nullptr, ev_copied = nullptr;
+  // host -> device inputs of a tick (gbp_world_set_comms, gbp_world_set_waypoint_index): staged through
+  // double-buffered device slots on their own stream so that the call returns when the HOST buffer is
+  // free again, not when the previous tick's kernels have drained (staged_upload)
+  static constexpr int kUpKinds = 3;  // antenna, idle, next_wp
+  cudaStream_t up_stream = nullptr;
+  void *up_stage[kUpKinds][2] = {};
+  size_t up_bytes[kUpKinds] = {};
+  cudaEvent_t ev_up_done[kUpKinds][2] = {}, ev_up_used[kUpKinds][2] = {};
+  int up_gen[kUpKinds] = {};
   bool copy_pending = false;
   // optional per-launch CUDA-event timing (bench.py roofline leg)
   struct Span {
@@ -1452,6 +1461,16 @@ void gbp_world_destroy(gbp_world_t *w) {
   for (cudaEvent_t e : w->ev_pool) cudaEventDestroy(e);
   cudaEventDestroy(w->ev0);
   cudaEventDestroy(w->ev1);
+  if (w->up_stream) {
+    cudaStreamSynchronize(w->up_stream);
+    cudaStreamDestroy(w->up_stream);
+    for (int q = 0; q < gbp_world::kUpKinds; ++q)
+      for (int g = 0; g < 2; ++g) {
+        cudaFree(w->up_stage[q][g]);
+        if (w->ev_up_done[q][g]) cudaEventDestroy(w->ev_up_done[q][g]);
+        if (w->ev_up_used[q][g]) cudaEventDestroy(w->ev_up_used[q][g]);
+      }
+  }
   if (w->copy_stream) {
     cudaStreamSynchronize(w->copy_stream);
     cudaStreamDestroy(w->copy_stream);
@@ -1700,16 +1719,59 @@ int gbp_world_update_topology(gbp_world_t *w) {
   return group_update_topology(w->grp);
 }
 
+namespace {
+// Copies `bytes` from a borrowed host buffer into the device array `dst`, ordered on the world's stream
+// like any other operation, but WITHOUT waiting for the work already queued there: host -> staging slot on
+// the upload stream (the call returns once that copy is done, so the caller may reuse its buffer), then
+// staging -> dst on the world's stream.  Two slots per kind: a slot is rewritten only after the
+// staging -> dst copy of the call before last, which ran a tick ago.
+int staged_upload(gbp_world *w, int kind, void *dst, const void *src, size_t bytes) {
+  if (bytes == 0) return 0;
+  if (!w->up_stream) {
+    CK(cudaStreamCreateWithFlags(&w->up_stream, cudaStreamNonBlocking));
+    for (int q = 0; q < gbp_world::kUpKinds; ++q)
+      for (int g = 0; g < 2; ++g) {
+        CK(cudaEventCreateWithFlags(&w->ev_up_done[q][g], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&w->ev_up_used[q][g], cudaEventDisableTiming));
+      }
+  }
+  if (bytes > w->up_bytes[kind]) {  // grow-only; rare (robots were added)
+    CK(cudaStreamSynchronize(w->stream));
+    CK(cudaStreamSynchronize(w->up_stream));
+    for (int g = 0; g < 2; ++g) {
+      cudaFree(w->up_stage[kind][g]);
+      w->up_stage[kind][g] = nullptr;
+      CK(cudaMalloc(&w->up_stage[kind][g], bytes));
+    }
+    w->up_bytes[kind] = bytes;
+  }
+  const int g = (w->up_gen[kind] ^= 1);
+  CK(cudaStreamWaitEvent(w->up_stream, w->ev_up_used[kind][g], 0));
+  CK(cudaMemcpyAsync(w->up_stage[kind][g], src, bytes, cudaMemcpyHostToDevice, w->up_stream));
+  CK(cudaEventRecord(w->ev_up_done[kind][g], w->up_stream));
+  CK(cudaStreamWaitEvent(w->stream, w->ev_up_done[kind][g], 0));
+  CK(cudaMemcpyAsync(dst, w->up_stage[kind][g], bytes, cudaMemcpyDeviceToDevice, w->stream));
+  CK(cudaEventRecord(w->ev_up_used[kind][g], w->stream));
+  CK(cudaStreamSynchronize(w->up_stream));  // the host buffer is free again
+  return 0;
+}
+}  // namespace
+
 int gbp_world_set_comms(gbp_world_t *w, const uint8_t *antenna_active, const uint8_t *idle) {
   if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
   if (set_device(w)) return GBP_ERR_CUDA;
   const int n = w->s.Nloc;
   if (n == 0) return 0;
-  if (antenna_active) CK(cudaMemcpyAsync(w->s.antenna, antenna_active, n, cudaMemcpyHostToDevice, w->stream));
-  else CK(cudaMemsetAsync(w->s.antenna, 1, n, w->stream));
-  if (idle) CK(cudaMemcpyAsync(w->s.idle, idle, n, cudaMemcpyHostToDevice, w->stream));
-  else CK(cudaMemsetAsync(w->s.idle, 0, n, w->stream));
-  CK(cudaStreamSynchronize(w->stream));
+  if (antenna_active) {
+    if (int rc = staged_upload(w, 0, w->s.antenna, antenna_active, size_t(n))) return rc;
+  } else {
+    CK(cudaMemsetAsync(w->s.antenna, 1, n, w->stream));
+  }
+  if (idle) {
+    if (int rc = staged_upload(w, 1, w->s.idle, idle, size_t(n))) return rc;
+  } else {
+    CK(cudaMemsetAsync(w->s.idle, 0, n, w->stream));
+  }
   mark_halo_stale(w);  // antenna / idle bits travel with the halo
   return 0;
 }
@@ -1718,9 +1780,7 @@ int gbp_world_set_waypoint_index(gbp_world_t *w, const int32_t *next_index) {
   if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
   if (!next_index) return fail(GBP_ERR_BAD_ARGUMENT, "null index array");
   if (set_device(w)) return GBP_ERR_CUDA;
-  CK(cudaMemcpyAsync(w->s.next_wp, next_index, size_t(w->s.Nloc) * sizeof(int32_t), cudaMemcpyHostToDevice, w->stream));
-  CK(cudaStreamSynchronize(w->stream));
-  return 0;
+  return staged_upload(w, 2, w->s.next_wp, next_index, size_t(w->s.Nloc) * sizeof(int32_t));
 }
 
 int gbp_world_reached_waypoint(gbp_world_t *w, const gbp_reached_when_t *taskpoint, const gbp_reached_when_t *finished,
