@@ -106,6 +106,29 @@ void gbp_world_destroy(gbp_world_t *w);
  * (simulation_loader.rs:52, robot.rs:1274): RGB8, row 0 = top, uploaded once. */
 int gbp_world_set_sdf(gbp_world_t *w, const uint8_t *rgb8, int32_t width, int32_t height);
 
+/* `gbp_environment::Obstacle` (crates/gbp_environment/src/lib.rs:532-572) with its `PlaceableShape`
+ * (:437-443: Circle :118-142, Triangle :154-227, RegularPolygon :233-314, Rectangle :316-361, Polygon
+ * :363-435).  Angles in radians as the YAML holds them (`Angle(f64)`). */
+enum {
+  GBP_SHAPE_CIRCLE = 0,
+  GBP_SHAPE_TRIANGLE = 1,
+  GBP_SHAPE_REGULAR_POLYGON = 2,
+  GBP_SHAPE_POLYGON = 3,
+  GBP_SHAPE_RECTANGLE = 4
+};
+typedef struct gbp_obstacle {
+  int32_t kind;               /* GBP_SHAPE_* */
+  int32_t tile_row, tile_col; /* tile-coordinates */
+  double rotation;            /* rotation.as_radians() */
+  double tx, ty;              /* translation (RelativePoint) */
+  double radius;              /* circle, triangle (inscribed circle), regular polygon */
+  double angle_a, angle_b;    /* triangle: angles.A, angles.B */
+  int32_t sides;              /* regular polygon */
+  int32_t n_points;           /* polygon */
+  int64_t point_offset;       /* polygon: first point in gbp_environment_t::polygon_points */
+  double width, height;       /* rectangle */
+} gbp_obstacle_t;
+
 /* `gbp_environment::Environment` as far as SDF generation reads it
  * (crates/gbp_environment/src/lib.rs:40-75,940-971; settings.sdf: resolution, expansion, blur). */
 typedef struct gbp_environment {
@@ -116,12 +139,14 @@ typedef struct gbp_environment {
   uint32_t resolution;       /* tiles.settings.sdf.resolution: pixels per tile */
   float expansion;           /* tiles.settings.sdf.expansion */
   float blur;                /* tiles.settings.sdf.blur (sigma = blur * resolution pixels) */
-  int32_t n_obstacles;       /* placeable obstacles: must be 0 (is_placeable_obstacle is not built yet) */
+  int32_t n_obstacles;       /* env.obstacles.len() */
+  const gbp_obstacle_t *obstacles;  /* [n_obstacles] in file order (first hit wins, lib.rs:293-333) */
+  const double *polygon_points;     /* (x, y) pairs of every polygon obstacle */
 } gbp_environment_t;
 
 /* Replaces env_to_png::env_to_sdf_image (crates/env_to_png/src/lib.rs:149-163: env_to_image :166-207 +
  * image::imageops::blur), called at scenario load (simulation_loader.rs:153-161): rasterises the tile grid
- * and blurs it on the device.  rgb8: [nrows*resolution][ncols*resolution][3], R = G = B, row 0 = top. */
+ * and the placeable obstacles and blurs the image on the device.  rgb8: [nrows*resolution][ncols*resolution][3], R = G = B, row 0 = top. */
 int gbp_env_to_sdf_image(const gbp_environment_t *env, int32_t device, uint8_t *rgb8);
 /* Same, but the image never leaves the device: it becomes the world's SDF (gbp_world_set_sdf). */
 int gbp_world_set_sdf_from_environment(gbp_world_t *w, const gbp_environment_t *env);

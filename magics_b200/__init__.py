@@ -19,6 +19,6 @@ from .config import (  # noqa: F401
     SCHEDULE_SOON_AS_POSSIBLE,
     GbpConfig,
 )
-from .environment import Environment  # noqa: F401
+from .environment import Environment, Obstacle  # noqa: F401
 from .world import (World, env_to_sdf_image, gbp_schedule, get_variable_timesteps, library_path,  # noqa: F401
                     load_library, pinned_empty)

@@ -1532,6 +1532,89 @@ float env_gaussian(float x, float r) {
   return (1.0f / (std::sqrt(2.0f * 3.14159265358979323846f) * r)) * std::exp(-(x * x) / (2.0f * (r * r)));
 }
 
+// Host-side preparation of the placeable obstacles: `shape.expanded(expansion as f64)`, the vertices each
+// shape's `inside()` would recompute per point, and the rotation quaternion of is_placeable_obstacle
+// (env_to_png/src/lib.rs:303-324).  libm sinf / cosf / sin / cos, as the reference process calls them.
+int env_prepare_shapes(const gbp_environment_t *env, std::vector<gbp::EnvShape> &shapes, std::vector<double> &verts) {
+  const float kPi = 3.14159265358979323846f, kHalfPi = 1.57079632679489661923f;
+  const double expansion = double(env->expansion);
+  for (int k = 0; k < env->n_obstacles; ++k) {
+    const gbp_obstacle_t &o = env->obstacles[k];
+    gbp::EnvShape s{};
+    s.kind = o.kind;
+    s.tile_row = o.tile_row;
+    s.tile_col = o.tile_col;
+    s.tx = float(o.tx);
+    s.ty = float(o.ty);
+    float rotation_offset = kHalfPi;
+    switch (o.kind) {
+      case GBP_SHAPE_CIRCLE: {  // Circle::expanded / inside (gbp_environment/src/lib.rs:128-141)
+        const double r = o.radius + expansion;
+        s.r2 = float(r * r);
+        break;
+      }
+      case GBP_SHAPE_TRIANGLE: {  // Triangle::expanded / points (:171-210), f32
+        const float radius = float(o.radius + expansion);
+        const float a = float(o.angle_a), b = float(o.angle_b);
+        const float c = kPi - (a + b);
+        const float ah = radius / std::sin(a), bh = radius / std::sin(b), ch = radius / std::sin(c);
+        const float aa = kPi + a / 2.0f, ba = -b / 2.0f, ca = kPi - b - c / 2.0f;
+        s.tri[0] = std::cos(aa) * ah;
+        s.tri[1] = std::sin(aa) * ah;
+        s.tri[2] = std::cos(ba) * bh;
+        s.tri[3] = std::sin(ba) * bh;
+        s.tri[4] = std::cos(ca) * ch;
+        s.tri[5] = std::sin(ca) * ch;
+        break;
+      }
+      case GBP_SHAPE_REGULAR_POLYGON: {  // RegularPolygon::expanded / point_at (:250-287), f64
+        if (o.sides < 1) return fail(GBP_ERR_BAD_ARGUMENT, "environment: regular polygon without sides");
+        const double radius = o.radius + expansion * 2.0;
+        s.n = o.sides;
+        s.poff = int64_t(verts.size() / 2);
+        for (int i = 0; i < o.sides; ++i) {
+          const double angle = 2.0 * 3.14159265358979323846 / double(o.sides) * double(i) + 0.78539816339744830962;
+          verts.push_back(std::cos(angle) * radius);
+          verts.push_back(std::sin(angle) * radius);
+        }
+        rotation_offset = kHalfPi + kHalfPi + ((o.sides % 2 != 0) ? kPi / float(o.sides) : 0.0f);
+        break;
+      }
+      case GBP_SHAPE_POLYGON: {  // Polygon::expanded (:374-401)
+        if (o.n_points < 1 || !env->polygon_points)
+          return fail(GBP_ERR_BAD_ARGUMENT, "environment: polygon without points");
+        const double *p = env->polygon_points + 2 * o.point_offset;
+        double ax = 0.0, ay = 0.0;
+        for (int i = 0; i < o.n_points; ++i) {
+          ax = ax + p[2 * i];
+          ay = ay + p[2 * i + 1];
+        }
+        const double cx = ax / double(o.n_points), cy = ay / double(o.n_points);
+        s.n = o.n_points;
+        s.poff = int64_t(verts.size() / 2);
+        for (int i = 0; i < o.n_points; ++i) {
+          const double dx = p[2 * i] - cx, dy = p[2 * i + 1] - cy;
+          verts.push_back(p[2 * i] + dx * 4.0 * expansion);
+          verts.push_back(p[2 * i + 1] + dy * 4.0 * expansion);
+        }
+        rotation_offset = 0.0f;
+        break;
+      }
+      case GBP_SHAPE_RECTANGLE: {  // Rectangle::expanded / inside (:335-359)
+        s.hw = (o.width + expansion * 2.0) / 4.0;
+        s.hh = (o.height + expansion * 2.0) / 4.0;
+        break;
+      }
+      default: return fail(GBP_ERR_BAD_ARGUMENT, "environment: unknown obstacle shape");
+    }
+    const float angle = float(o.rotation) + rotation_offset;
+    s.qs = std::sin(angle * 0.5f);
+    s.qw = std::cos(angle * 0.5f);
+    shapes.push_back(s);
+  }
+  return 0;
+}
+
 // env_to_png::env_to_sdf_image (crates/env_to_png/src/lib.rs:149-163) on the current device: leaves the
 // single-channel image in *d_gray (cudaMalloc'ed, caller owns it).
 int env_to_sdf_device(const gbp_environment_t *env, cudaStream_t st, uint8_t **d_gray, uint32_t *Wo, uint32_t *Ho,
@@ -1544,8 +1627,11 @@ int env_to_sdf_device(const gbp_environment_t *env, cudaStream_t st, uint8_t **d
         env->blur >= 0.0f && env->blur <= 1.0f && pw >= 0.0f))
     return fail(GBP_ERR_BAD_ARGUMENT, "environment: path-width, expansion and blur are percentages in [0, 1], "
                                       "path-width >= expansion");
-  if (env->n_obstacles != 0)
-    return fail(GBP_ERR_BAD_ARGUMENT, "environment: placeable obstacles are not rasterised by this build");
+  if (env->n_obstacles < 0 || (env->n_obstacles > 0 && !env->obstacles))
+    return fail(GBP_ERR_BAD_ARGUMENT, "environment: bad obstacle list");
+  std::vector<gbp::EnvShape> shapes;
+  std::vector<double> verts;
+  if (int rc = env_prepare_shapes(env, shapes, verts)) return rc;
   gbp::EnvParams e{env->nrows, env->ncols, env->resolution, env->tile_size, env->path_width, env->expansion};
   const uint64_t W64 = uint64_t(env->ncols) * env->resolution, H64 = uint64_t(env->nrows) * env->resolution;
   if (W64 > 65535u * 64u || H64 > 65535u) return fail(GBP_ERR_BAD_ARGUMENT, "environment: image too large");
@@ -1556,8 +1642,16 @@ int env_to_sdf_device(const gbp_environment_t *env, cudaStream_t st, uint8_t **d
   CK(dalloc(d_tiles, ntile));
   CK(dalloc(d_img, npx));
   CK(cudaMemcpyAsync(d_tiles, env->tiles, ntile * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  gbp::EnvShape *d_shapes = nullptr;
+  double *d_verts = nullptr;
+  CK(dalloc(d_shapes, shapes.size()));
+  CK(dalloc(d_verts, verts.size()));
+  if (!shapes.empty())
+    CK(cudaMemcpyAsync(d_shapes, shapes.data(), shapes.size() * sizeof(gbp::EnvShape), cudaMemcpyHostToDevice, st));
+  if (!verts.empty())
+    CK(cudaMemcpyAsync(d_verts, verts.data(), verts.size() * sizeof(double), cudaMemcpyHostToDevice, st));
   const dim3 grid((W + 255) / 256, H);
-  gbp::k_env_raster<<<grid, 256, 0, st>>>(e, d_tiles, d_img);
+  gbp::k_env_raster<<<grid, 256, 0, st>>>(e, d_tiles, d_shapes, int(shapes.size()), d_verts, d_img);
   CK(cudaGetLastError());
   *launches += 1;
   const float blur_pixels = env->blur * float(env->resolution);
@@ -1581,6 +1675,8 @@ int env_to_sdf_device(const gbp_environment_t *env, cudaStream_t st, uint8_t **d
   }
   CK(cudaStreamSynchronize(st));
   cudaFree(d_tiles);
+  cudaFree(d_shapes);
+  cudaFree(d_verts);
   *d_gray = d_img;
   *Wo = W;
   *Ho = H;

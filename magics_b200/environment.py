@@ -12,11 +12,39 @@ from dataclasses import dataclass, field
 import numpy as np
 
 
+SHAPE_KINDS = {"circle": 0, "triangle": 1, "regular-polygon": 2, "polygon": 3, "rectangle": 4}
+
+
+class CObstacle(C.Structure):
+    """include/gbp_b200.h gbp_obstacle_t"""
+    _fields_ = [("kind", C.c_int32), ("tile_row", C.c_int32), ("tile_col", C.c_int32), ("rotation", C.c_double),
+                ("tx", C.c_double), ("ty", C.c_double), ("radius", C.c_double), ("angle_a", C.c_double),
+                ("angle_b", C.c_double), ("sides", C.c_int32), ("n_points", C.c_int32), ("point_offset", C.c_int64),
+                ("width", C.c_double), ("height", C.c_double)]
+
+
 class CEnvironment(C.Structure):
     """include/gbp_b200.h gbp_environment_t"""
     _fields_ = [("nrows", C.c_int32), ("ncols", C.c_int32), ("tiles", C.POINTER(C.c_uint32)),
                 ("tile_size", C.c_float), ("path_width", C.c_float), ("resolution", C.c_uint32),
-                ("expansion", C.c_float), ("blur", C.c_float), ("n_obstacles", C.c_int32)]
+                ("expansion", C.c_float), ("blur", C.c_float), ("n_obstacles", C.c_int32),
+                ("obstacles", C.POINTER(CObstacle)), ("polygon_points", C.POINTER(C.c_double))]
+
+
+@dataclass
+class Obstacle:
+    """`gbp_environment::Obstacle` (crates/gbp_environment/src/lib.rs:532-572); angles in radians as in the YAML."""
+    shape: str                     # one of SHAPE_KINDS
+    row: int = 0
+    col: int = 0
+    translation: tuple = (0.5, 0.5)
+    rotation: float = 0.0
+    radius: float = 0.0            # circle, triangle, regular-polygon
+    angles: tuple = (0.0, 0.0)     # triangle (A, B)
+    sides: int = 0                 # regular-polygon
+    points: tuple = ()             # polygon ((x, y), ...)
+    width: float = 0.0             # rectangle
+    height: float = 0.0
 
 
 @dataclass
@@ -32,14 +60,32 @@ class Environment:
 
     @classmethod
     def from_yaml(cls, text: str) -> "Environment":
+        """Parses an `environment.yaml` (serde's externally tagged shapes: `shape: !circle {radius: ..}`)."""
         import yaml
 
-        d = yaml.safe_load(text)
+        class Loader(yaml.SafeLoader):
+            pass
+
+        def tagged(loader, suffix, node):
+            return {"kind": suffix, **loader.construct_mapping(node, deep=True)}
+
+        Loader.add_multi_constructor("!", tagged)
+        d = yaml.load(text, Loader=Loader)
         s = d["tiles"]["settings"]
         sdf = s.get("sdf", {})
+        obstacles = []
+        for o in d.get("obstacles") or []:
+            sh = o["shape"]
+            ang = sh.get("angles", {})
+            obstacles.append(Obstacle(
+                shape=sh["kind"], row=int(o["tile-coordinates"]["row"]), col=int(o["tile-coordinates"]["col"]),
+                translation=(float(o["translation"]["x"]), float(o["translation"]["y"])), rotation=float(o["rotation"]),
+                radius=float(sh.get("radius", 0.0)), angles=(float(ang.get("A", 0.0)), float(ang.get("B", 0.0))),
+                sides=int(sh.get("sides", 0)), points=tuple((float(p["x"]), float(p["y"])) for p in sh.get("points", [])),
+                width=float(sh.get("width", 0.0)), height=float(sh.get("height", 0.0))))
         return cls(grid=list(d["tiles"]["grid"]), tile_size=float(s["tile-size"]), path_width=float(s["path-width"]),
                    resolution=int(sdf.get("resolution", 200)), expansion=float(sdf.get("expansion", 0.0)),
-                   blur=float(sdf.get("blur", 0.0)), obstacles=list(d.get("obstacles") or []))
+                   blur=float(sdf.get("blur", 0.0)), obstacles=obstacles)
 
     @property
     def nrows(self) -> int:
@@ -66,9 +112,23 @@ class Environment:
             raise ValueError("tile grid rows differ in length (env_to_image: 'Tile not found')")
         return np.ascontiguousarray(rows, dtype=np.uint32).reshape(-1)
 
+    def c_obstacles(self):
+        """(CObstacle array, polygon points (m, 2) f64)"""
+        arr = (CObstacle * max(1, len(self.obstacles)))()
+        pts: list[tuple[float, float]] = []
+        for k, o in enumerate(self.obstacles):
+            if isinstance(o, dict):
+                o = Obstacle(**o)
+            arr[k] = CObstacle(SHAPE_KINDS[o.shape], o.row, o.col, o.rotation, o.translation[0], o.translation[1],
+                               o.radius, o.angles[0], o.angles[1], o.sides, len(o.points), len(pts), o.width, o.height)
+            pts.extend(o.points)
+        return arr, np.ascontiguousarray(pts if pts else [(0.0, 0.0)], dtype=np.float64)
+
     def c_struct(self):
-        """(CEnvironment, keep-alive array)"""
+        """(CEnvironment, keep-alive objects)"""
         codes = self.tile_codes()
+        obs, pts = self.c_obstacles()
         ce = CEnvironment(self.nrows, self.ncols, codes.ctypes.data_as(C.POINTER(C.c_uint32)), self.tile_size,
-                          self.path_width, self.resolution, self.expansion, self.blur, len(self.obstacles))
-        return ce, codes
+                          self.path_width, self.resolution, self.expansion, self.blur, len(self.obstacles),
+                          C.cast(obs, C.POINTER(CObstacle)), pts.ctypes.data_as(C.POINTER(C.c_double)))
+        return ce, (codes, obs, pts)

@@ -1047,8 +1047,8 @@ void expand(int kind, int n, int max, uint8_t *out) {
 // ---------------------------------------------------------------------------
 // crates/env_to_png/src/lib.rs — Environment -> SDF image: rasterise the tile
 // grid (env_to_image :166-207, is_tile_obstacle :340-479), then `image::imageops::blur`.
-// Placeable obstacles (`is_placeable_obstacle` :283-336) are not restated: the BASELINE scenarios
-// (circle, junction twoway, complex) have `obstacles: []`.
+// and the placeable obstacles (is_placeable_obstacle :283-336, shapes of gbp_environment/src/lib.rs:118-435;
+// glam 0.25 `Quat::from_rotation_z(..).mul_vec3` is third party and restated from its formula).
 // Third party, absent from /root/reference: image 0.25.1 `imageops::blur` (Cargo.lock) — restated
 // from its published source: sigma <= 0 -> 1; separable Gaussian with support 2*sigma, vertical pass
 // into an f32 image, horizontal pass clamped to [0, 255] and rounded half away from zero; per output
@@ -1099,6 +1099,129 @@ inline bool is_tile_obstacle(uint32_t tile, float path_width_in, float px, float
     default: return false;
   }
 }
+// ---- placeable obstacles (crates/gbp_environment/src/lib.rs:118-435, env_to_png/src/lib.rs:283-336),
+// restated literally: every `inside()` recomputes its vertices, as the reference does per pixel.
+struct Obstacle {  // same layout as gbp_obstacle_t of the product header (plain data from the caller)
+  int32_t kind, tile_row, tile_col;
+  double rotation, tx, ty, radius, angle_a, angle_b;
+  int32_t sides, n_points;
+  int64_t point_offset;
+  double width, height;
+};
+struct V2 {
+  float x, y;
+};
+constexpr float kPiF = 3.14159265358979323846f, kHalfPiF = 1.57079632679489661923f;
+constexpr double kPiD = 3.14159265358979323846, kQuarterPiD = 0.78539816339744830962;
+inline V2 from_angle(float a) { return V2{std::cos(a), std::sin(a)}; }  // glam Vec2::from_angle
+inline float tri_sign(V2 p1, V2 p2, V2 p3) {                             // :229-231
+  return (p1.x - p3.x) * (p2.y - p3.y) - (p2.x - p3.x) * (p1.y - p3.y);
+}
+inline bool circle_inside(double radius, V2 p) {  // :138-141
+  const float sq = p.x * p.x + p.y * p.y;
+  return sq <= float(radius * radius);
+}
+inline bool triangle_inside(double angle_a, double angle_b, double radius_d, V2 p) {  // :192-226
+  const float a = float(angle_a), b = float(angle_b);
+  const float c = kPiF - (a + b);
+  const float radius = float(radius_d);
+  const float ah = radius / std::sin(a), bh = radius / std::sin(b), ch = radius / std::sin(c);
+  const V2 ad = from_angle(kPiF + a / 2.0f), bd = from_angle(-b / 2.0f), cd = from_angle(kPiF - b - c / 2.0f);
+  const V2 A{ad.x * ah, ad.y * ah}, B{bd.x * bh, bd.y * bh}, C{cd.x * ch, cd.y * ch};
+  const float d1 = tri_sign(p, A, B), d2 = tri_sign(p, B, C), d3 = tri_sign(p, C, A);
+  const bool has_neg = d1 < 0.0f || d2 < 0.0f || d3 < 0.0f;
+  const bool has_pos = d1 > 0.0f || d2 > 0.0f || d3 > 0.0f;
+  return !(has_neg && has_pos);
+}
+inline void regular_point_at(int sides, double radius, int i, double &x, double &y) {  // :271-287
+  const double angle = 2.0 * kPiD / double(sides) * double(i) + kQuarterPiD;
+  x = std::cos(angle) * radius;
+  y = std::sin(angle) * radius;
+}
+inline bool regular_polygon_inside(int sides, double radius, V2 p) {  // :298-313
+  bool inside = false;
+  const double x = double(p.x) * 2.0, y = double(p.y) * 2.0;
+  int j = sides - 1;
+  for (int i = 0; i < sides; ++i) {
+    double xi, yi, xj, yj;
+    regular_point_at(sides, radius, i, xi, yi);
+    regular_point_at(sides, radius, j, xj, yj);
+    if ((yi < y && yj >= y) || (yj < y && yi >= y)) {
+      if (xi + (y - yi) / (yj - yi) * (xj - xi) < x) inside = !inside;
+    }
+    j = i;
+  }
+  return inside;
+}
+inline bool rectangle_inside(double width, double height, V2 p) {  // :347-359
+  const double x = double(p.x), y = double(p.y);
+  const double half_width = width / 4.0, half_height = height / 4.0;
+  return x >= -half_height && x <= half_height && y >= -half_width && y <= half_width;
+}
+inline bool polygon_inside(const std::vector<double> &pts, V2 p) {  // is_point_in_polygon :412-428
+  const double px = double(p.x), py = double(p.y);
+  bool inside = false;
+  const size_t n = pts.size() / 2;
+  size_t j = n - 1;
+  for (size_t i = 0; i < n; ++i) {
+    const double ix = pts[2 * i], iy = pts[2 * i + 1], jx = pts[2 * j], jy = pts[2 * j + 1];
+    if ((iy > py) != (jy > py) && px < (jx - ix) * (py - iy) / (jy - iy) + ix) inside = !inside;
+    j = i;
+  }
+  return inside;
+}
+// glam 0.25 Quat::from_rotation_z(angle).mul_vec3((x, y, 0)).xy() (third party, restated):
+// rhs * (w*w - b.b) + b * (rhs.b * 2) + (b x rhs) * (w * 2) with b = (0, 0, sin(angle/2)), w = cos(angle/2)
+inline V2 rotate_z(float angle, V2 v) {
+  const float s = std::sin(angle * 0.5f), w = std::cos(angle * 0.5f);
+  const float b2 = (0.0f * 0.0f + 0.0f * 0.0f) + s * s;
+  const float k = w * w - b2;
+  const float d2 = ((v.x * 0.0f + v.y * 0.0f) + 0.0f * s) * 2.0f;
+  const float cx = 0.0f * 0.0f - s * v.y, cy = s * v.x - 0.0f * 0.0f;
+  return V2{(v.x * k + 0.0f * d2) + cx * (w * 2.0f), (v.y * k + 0.0f * d2) + cy * (w * 2.0f)};
+}
+// is_placeable_obstacle (env_to_png/src/lib.rs:283-336)
+inline bool is_placeable_obstacle(const Obstacle *obs, int n_obs, const double *poly_pts, uint64_t tile_x,
+                                  uint64_t tile_y, float px, float py, float expansion_f) {
+  const double expansion = double(expansion_f);
+  for (int k = 0; k < n_obs; ++k) {
+    const Obstacle &o = obs[k];
+    if (uint64_t(o.tile_col) != tile_x || uint64_t(o.tile_row) != tile_y) continue;
+    const V2 translated{px - float(o.tx), py - float(o.ty)};
+    float rotation_offset = kHalfPiF;
+    if (o.kind == 2) rotation_offset = kHalfPiF + kHalfPiF + ((o.sides % 2 != 0) ? kPiF / float(o.sides) : 0.0f);
+    else if (o.kind == 3) rotation_offset = 0.0f;
+    const V2 r = rotate_z(float(o.rotation) + rotation_offset, translated);
+    bool inside = false;
+    switch (o.kind) {
+      case 0: inside = circle_inside(o.radius + expansion, r); break;                               // :128-134
+      case 1: inside = triangle_inside(o.angle_a, o.angle_b, o.radius + expansion, r); break;       // :171-190
+      case 2: inside = regular_polygon_inside(o.sides, o.radius + expansion * 2.0, r); break;       // :250-267
+      case 3: {                                                                                     // :374-401
+        const double *p = poly_pts + 2 * o.point_offset;
+        double ax = 0.0, ay = 0.0;
+        for (int i = 0; i < o.n_points; ++i) {
+          ax = ax + p[2 * i];
+          ay = ay + p[2 * i + 1];
+        }
+        const double cx = ax / double(o.n_points), cy = ay / double(o.n_points);
+        std::vector<double> e;
+        for (int i = 0; i < o.n_points; ++i) {
+          const double dx = p[2 * i] - cx, dy = p[2 * i + 1] - cy;
+          e.push_back(p[2 * i] + dx * 4.0 * expansion);
+          e.push_back(p[2 * i + 1] + dy * 4.0 * expansion);
+        }
+        inside = polygon_inside(e, r);
+        break;
+      }
+      case 4: inside = rectangle_inside(o.width + expansion * 2.0, o.height + expansion * 2.0, r); break;  // :335-344
+      default: break;
+    }
+    if (inside) return true;
+  }
+  return false;
+}
+
 // image 0.25.1 imageops::sample::gaussian
 inline float gaussian(float x, float r) {
   return (1.0f / (std::sqrt(2.0f * 3.14159265358979323846f) * r)) * std::exp(-(x * x) / (2.0f * (r * r)));
@@ -1181,7 +1304,8 @@ int gbpo_is_tile_obstacle(uint32_t tile, float path_width, float px, float py, f
 }
 // env_to_sdf_image (:149-163): out_rgb is [nrows*res][ncols*res][3]
 int gbpo_env_to_sdf_image(int nrows, int ncols, const uint32_t *tiles, float tile_size, float path_width,
-                          uint32_t res, float expansion, float blur_percent, uint8_t *out_rgb) {
+                          uint32_t res, float expansion, float blur_percent, int n_obstacles, const void *obstacles,
+                          const double *polygon_points, uint8_t *out_rgb) {
   using namespace envpng;
   const uint32_t W = uint32_t(ncols) * res, H = uint32_t(nrows) * res;
   std::vector<uint8_t> img(size_t(W) * H);
@@ -1193,7 +1317,10 @@ int gbpo_env_to_sdf_image(int nrows, int ncols, const uint32_t *tiles, float til
       image_to_tile_units(x, y, res, tile_size, ux, uy);
       const float fx = offset_modulus(ux, tile_size), fy = offset_modulus(uy, tile_size);
       if (ty >= uint64_t(nrows) || tx >= uint64_t(ncols)) return -1;  // "Tile not found"
-      img[size_t(y) * W + x] = is_tile_obstacle(tiles[ty * ncols + tx], path_width, fx, fy, expansion) ? 0 : 255;
+      const bool obstacle = is_tile_obstacle(tiles[ty * ncols + tx], path_width, fx, fy, expansion) ||
+                            is_placeable_obstacle(static_cast<const Obstacle *>(obstacles), n_obstacles, polygon_points,
+                                                  tx, ty, fx, fy, expansion);
+      img[size_t(y) * W + x] = obstacle ? 0 : 255;
     }
   const float blur_pixels = blur_percent * float(res);
   if (!(blur_pixels < 1.0f)) {

@@ -120,9 +120,11 @@ def env_to_sdf_image(env) -> np.ndarray:
     h, w = env.image_shape
     out = np.empty((h, w, 3), np.uint8)
     codes = env.tile_codes()
+    obs, pts = env.c_obstacles()  # plain input data, same struct layout as the oracle's `envpng::Obstacle`
     rc = lib().gbpo_env_to_sdf_image(env.nrows, env.ncols, _p(codes, C.c_uint32), C.c_float(env.tile_size),
                                      C.c_float(env.path_width), C.c_uint32(env.resolution), C.c_float(env.expansion),
-                                     C.c_float(env.blur), _p(out, C.c_uint8))
+                                     C.c_float(env.blur), len(env.obstacles), C.cast(obs, C.c_void_p),
+                                     _p(pts, C.c_double), _p(out, C.c_uint8))
     if rc != 0:
         raise RuntimeError(f"gbpo_env_to_sdf_image failed ({rc})")
     return out

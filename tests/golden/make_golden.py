@@ -110,7 +110,20 @@ def env_to_png():
         s = d["tiles"]["settings"]
         envs[name] = {"grid": d["tiles"]["grid"], "tile_size": s["tile-size"], "path_width": s["path-width"],
                       "resolution": s["sdf"]["resolution"], "expansion": s["sdf"]["expansion"], "blur": s["sdf"]["blur"]}
-    return {"kats": kats, "environments": envs}
+    # environments with placeable obstacles (all five PlaceableShape variants occur), parsed with the
+    # product's own YAML reader and stored as plain data
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from dataclasses import asdict
+
+    from magics_b200.environment import Environment
+
+    placed = {}
+    for name in ("Obstacle Shapes Showcase", "Merge", "Environment Obstacles Experiment",
+                 "Communications Failure Experiment", "Varying Network Connectivity Experiment"):
+        env = Environment.from_yaml(open(f"/root/reference/config/scenarios/{name}/environment.yaml").read())
+        placed[name] = asdict(env)
+    return {"kats": kats, "environments": envs, "environments_with_obstacles": placed}
 
 
 if __name__ == "__main__":

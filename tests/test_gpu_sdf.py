@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from magics_b200 import Environment, GbpConfig, World, env_to_sdf_image
+from magics_b200 import Environment, GbpConfig, Obstacle, World, env_to_sdf_image
 from oracle import oracle as oo
 from oracle.oracle import OracleWorld
 
@@ -67,7 +67,7 @@ def test_bad_environments_are_rejected():
     with pytest.raises(RuntimeError):
         env_to_sdf_image(Environment(grid=["┼"], blur=1.5))
     with pytest.raises(RuntimeError):
-        env_to_sdf_image(Environment(grid=["┼"], obstacles=[{"shape": "circle"}]))
+        env_to_sdf_image(Environment(grid=["█"], obstacles=[Obstacle("regular-polygon", sides=0, radius=0.1)]))
     with pytest.raises(ValueError):
         env_to_sdf_image(Environment(grid=["┼─", "┼"]))
 
@@ -90,3 +90,43 @@ def test_junction_scenario_on_the_generated_sdf():
         g.step()
         o.step()
     assert_beliefs_match(g.read_beliefs(), o.read_beliefs(), what="junction on generated SDF")
+
+
+@pytest.mark.parametrize("name", sorted(GOLD["environments_with_obstacles"]))
+def test_scenario_environments_with_placeable_obstacles_bit_exact(name):
+    e = GOLD["environments_with_obstacles"][name]
+    env = Environment(**{**e, "obstacles": [Obstacle(**o) for o in e["obstacles"]]})
+    got, ref = env_to_sdf_image(env), oo.env_to_sdf_image(env)
+    assert np.array_equal(got, ref), f"{name}: {int((got != ref).sum())} bytes differ"
+
+
+def test_random_placeable_obstacles_bit_exact():
+    rng = np.random.default_rng(5)
+    kinds = ["circle", "triangle", "regular-polygon", "polygon", "rectangle"]
+    for trial in range(6):
+        obstacles = []
+        for k in range(40):
+            kind = kinds[k % 5]
+            kw = dict(row=int(rng.integers(0, 2)), col=int(rng.integers(0, 3)),
+                      translation=(float(rng.uniform(0, 1)), float(rng.uniform(0, 1))),
+                      rotation=float(rng.uniform(0, 2 * np.pi)))
+            if kind == "circle":
+                kw["radius"] = float(rng.uniform(0.01, 0.2))
+            elif kind == "triangle":
+                a = float(rng.uniform(0.3, 1.3))
+                kw.update(radius=float(rng.uniform(0.01, 0.08)), angles=(a, float(rng.uniform(0.3, np.pi - a - 0.3))))
+            elif kind == "regular-polygon":
+                kw.update(sides=int(rng.integers(3, 9)), radius=float(rng.uniform(0.05, 0.4)))
+            elif kind == "polygon":
+                m = int(rng.integers(3, 8))
+                ang = np.sort(rng.uniform(0, 2 * np.pi, m))
+                rad = rng.uniform(0.05, 0.3, m)
+                kw["points"] = tuple((float(r * np.cos(a)), float(r * np.sin(a))) for r, a in zip(rad, ang))
+            else:
+                kw.update(width=float(rng.uniform(0.05, 0.8)), height=float(rng.uniform(0.05, 0.8)))
+            obstacles.append(Obstacle(kind, **kw))
+        env = Environment(grid=["█─┼", "│█ "], tile_size=20.0, path_width=0.3, resolution=int(rng.integers(30, 90)),
+                          expansion=float(rng.choice([0.0, 0.025, 0.1])), blur=float(rng.choice([0.0, 0.03])),
+                          obstacles=obstacles)
+        got, ref = env_to_sdf_image(env), oo.env_to_sdf_image(env)
+        assert np.array_equal(got, ref), f"trial {trial}: {int((got != ref).sum())} bytes differ"

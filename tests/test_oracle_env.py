@@ -98,3 +98,67 @@ def test_blur_matches_a_gaussian_filter_in_the_interior():
 def test_blur_below_one_pixel_is_skipped():
     env = Environment(grid=["┼"], resolution=50, path_width=0.3, blur=0.019)  # 0.95 px
     assert set(np.unique(oo.env_to_sdf_image(env))) == {0, 255}
+
+
+# ---- placeable obstacles (is_placeable_obstacle, env_to_png/src/lib.rs:283-336) -----------------------------
+def _blank(res=400, **kw):
+    return Environment(grid=["█"], resolution=res, **kw)  # unknown glyph: no tile obstacle anywhere
+
+
+def _dark_fraction(env):
+    return float((oo.env_to_sdf_image(env)[..., 0] == 0).mean())
+
+
+def test_obstacle_environments_parse_and_render():
+    from magics_b200.environment import Obstacle
+
+    for name, e in GOLD["environments_with_obstacles"].items():
+        env = Environment(**{**e, "obstacles": [Obstacle(**o) for o in e["obstacles"]]})
+        img = oo.env_to_sdf_image(env)
+        bare = oo.env_to_sdf_image(Environment(**{**e, "obstacles": []}))
+        assert img.shape == bare.shape and (img.astype(int) <= bare.astype(int)).all(), name  # obstacles only darken
+        assert (img != bare).any(), name
+
+
+def test_shape_areas_match_their_geometry():
+    from magics_b200.environment import Obstacle
+
+    e = 0.02
+    # circle: radius + expansion (gbp_environment/src/lib.rs:128-141)
+    f = _dark_fraction(_blank(expansion=e, obstacles=[Obstacle("circle", radius=0.2)]))
+    assert abs(f - np.pi * (0.2 + e) ** 2) < 2e-3
+    # rectangle: the test is against width / 4 and height / 4 after + 2 * expansion (:335-359)
+    f = _dark_fraction(_blank(expansion=e, obstacles=[Obstacle("rectangle", width=0.8, height=0.4, rotation=0.3)]))
+    assert abs(f - ((0.8 + 2 * e) / 2) * ((0.4 + 2 * e) / 2)) < 2e-3
+    # regular polygon: the point is doubled, so the circumradius is (radius + 2 * expansion) / 2 (:250-313)
+    for n in (3, 4, 5, 8):
+        f = _dark_fraction(_blank(expansion=e, obstacles=[Obstacle("regular-polygon", sides=n, radius=0.5, rotation=1.0)]))
+        rho = (0.5 + 2 * e) / 2
+        assert abs(f - n / 2 * rho * rho * np.sin(2 * np.pi / n)) < 2e-3, n
+    # polygon: vertices pushed away from their mean by 4 * expansion of the offset (:374-401), shoelace area
+    pts = np.array([(-0.3, -0.2), (0.25, -0.25), (0.3, 0.1), (0.0, 0.3), (-0.35, 0.15)])
+    grown = pts + (pts - pts.mean(0)) * 4 * e
+    area = 0.5 * abs(np.dot(grown[:, 0], np.roll(grown[:, 1], -1)) - np.dot(grown[:, 1], np.roll(grown[:, 0], -1)))
+    f = _dark_fraction(_blank(expansion=e, obstacles=[Obstacle("polygon", points=tuple(map(tuple, pts)), rotation=0.7)]))
+    assert abs(f - area) < 2e-3
+    # triangle: vertices at radius / sin(angle) along the directions of Triangle::points (:192-210; not the
+    # incircle construction its doc comment promises), area by the shoelace formula in float64
+    A, B = 1.0, 0.9
+    Cc = np.pi - (A + B)
+    r = 0.1 + e
+    dirs = (np.pi + A / 2, -B / 2, np.pi - B - Cc / 2)
+    v = np.array([[np.cos(d) * r / np.sin(a), np.sin(d) * r / np.sin(a)] for d, a in zip(dirs, (A, B, Cc))])
+    area = 0.5 * abs(np.dot(v[:, 0], np.roll(v[:, 1], -1)) - np.dot(v[:, 1], np.roll(v[:, 0], -1)))
+    f = _dark_fraction(_blank(expansion=e, obstacles=[Obstacle("triangle", radius=0.1, angles=(A, B), rotation=2.0)]))
+    assert abs(f - area) < 2e-3
+
+
+def test_obstacles_only_apply_to_their_tile_and_first_hit_wins():
+    from magics_b200.environment import Obstacle
+
+    env = Environment(grid=["██", "██"], resolution=50,
+                      obstacles=[Obstacle("circle", row=1, col=0, radius=0.3), Obstacle("circle", row=0, col=1, radius=0.1)])
+    g = oo.env_to_sdf_image(env)[..., 0]
+    assert g[:50, :50].min() == 255 and g[50:, 50:].min() == 255  # tiles (0,0) and (1,1) untouched
+    assert g[75, 25] == 0 and g[25, 75] == 0                      # centres of tiles (1,0) and (0,1)
+    assert (g[50:, :50] == 0).sum() > (g[:50, 50:] == 0).sum()
