@@ -425,6 +425,16 @@ __global__ void k_reached_waypoint(Store s, int p, gbp_reached_when_t task, gbp_
   }
 }
 
+// A few result words from device memory straight into page-locked host memory (device-accessible
+// under unified addressing).  The per-tick size read-back of the topology pass used to be a small
+// cudaMemcpyAsync D2H; DMA transfers of one direction are served in order, so it queued behind the
+// 320 MB read-back of the previous tick's means and the host — and with it the next launches — waited
+// 5 ms for it (scripts/e2e_probe.py).  Stores from a kernel do not pass through that queue.
+__global__ void k_words_to_host(int64_t *__restrict__ host_dst, const int64_t *__restrict__ src, int n) {
+  for (int k = threadIdx.x; k < n; k += blockDim.x) host_dst[k] = src[k];
+  __threadfence_system();
+}
+
 __global__ void k_iota_gid(int32_t *gid, int32_t g0, int32_t n) {
   const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < n) gid[r] = g0 + r;
@@ -1019,7 +1029,9 @@ int topo_search(gbp_world *w) {
     gbp::k_shard_result<<<1, 32, 0, st>>>(w->sh, n, w->t_off, w->t_newoff, ws > 1 ? w->t_gslot : nullptr, w->t_soff,
                                           w->t_coff, w->t_err, w->t_result_dev);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(w->t_result_host, w->t_result_dev, kResultWords * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    k_words_to_host<<<1, 64, 0, st>>>(w->t_result_host, w->t_result_dev, int(kResultWords));
+    CK(cudaGetLastError());
+    w->launches += 1;
     CK(cudaStreamSynchronize(st));
     w->launches += 1;
     if (w->t_result_host[3] != 0)
@@ -1211,7 +1223,9 @@ int group_update_topology(gbp_group *g) {
   if (int rc = exchange(g, plans)) return rc;
   for (gbp_world *w : g->members) {
     CK(cudaSetDevice(w->device));
-    CK(cudaMemcpyAsync(w->hdr_host, w->hdr_recv, 4 * size_t(ws) * sizeof(int64_t), cudaMemcpyDeviceToHost, w->stream));
+    k_words_to_host<<<1, 64, 0, w->stream>>>(w->hdr_host, w->hdr_recv, 4 * ws);
+    CK(cudaGetLastError());
+    w->launches += 1;
     CK(cudaStreamSynchronize(w->stream));
   }
   for (gbp_world *w : g->members) {

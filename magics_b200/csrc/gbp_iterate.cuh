@@ -112,7 +112,9 @@ GBP_DEV void add_unary_stored(const Store &s, int64_t vi, double (&ae)[4], doubl
   for (int k = 0; k < 4; ++k) o[k] = s.m_obs[s.at<4>(k, vi)];
 #pragma unroll
   for (int k = 0; k < 3; ++k) t[k] = s.m_trk[s.at<3>(k, vi)];
-  if (!is_empty_marker(o[0])) {
+  // A zero Jacobian (every variable away from obstacle edges) with a finite v0 adds exact zeros to all
+  // 20 sums: skipped — also keeps x and y decoupled for the inverse that follows.
+  if (!is_empty_marker(o[0]) && !((o[0] == 0.0) & (o[1] == 0.0) & (o[2] == 0.0) & isfinite(o[3]))) {
     const double J[4] = {o[0], o[1], o[2], o[2]};
     unary_add(J, o[3], s.lm_obs, ae, al);
   }
