@@ -268,6 +268,23 @@ int gbp_world_update_prior_of_current_state(gbp_world_t *w);
 int gbp_world_change_prior_of_variable(gbp_world_t *w, int32_t variable_index, int32_t m,
                                        const int32_t *robots, const double *new_means);
 
+/* Global-planner hand-off (planner/robot.rs:655-776: an RRT* path has arrived for a robot).
+ * set_tracking_path: FactorGraph::modify_tracking_factors(|t| t.set_tracking_path(..)) (factorgraph.rs:1467-1477,
+ *   factor/tracking.rs:134-136) + Route::update_waypoints (robot.rs:389-392): the polyline of each listed
+ *   robot is replaced (wp_offsets[m+1], wp_xy as in gbp_world_add_robots; two or more points) and its next
+ *   waypoint index becomes 1.
+ * reset_variables: FactorGraph::reset_variables(means, first_last_sigma, inbetween_sigma) (factorgraph.rs:1541-1564):
+ *   means[m*V*4]; belief mean and precision (sigma on the diagonal) replaced, information vector kept, every
+ *   inbox of the robot's variables AND of its factors emptied.  The reference passes (1e30, INFINITY).
+ * reset_tracking_factors: FactorGraph::reset_tracking_factors (factorgraph.rs:1566-1590): timeout of 10
+ *   iterations on every tracking factor.
+ * Single-GPU worlds only for reset_variables (GBP_ERR_STATE on a sharded world). */
+int gbp_world_set_tracking_path(gbp_world_t *w, int32_t m, const int32_t *robots, const int32_t *wp_offsets,
+                                const float *wp_xy);
+int gbp_world_reset_variables(gbp_world_t *w, int32_t m, const int32_t *robots, const double *means,
+                              double first_last_sigma, double inbetween_sigma);
+int gbp_world_reset_tracking_factors(gbp_world_t *w, int32_t m, const int32_t *robots);
+
 /* iterate_gbp_v2 (robot.rs:1769-1861) with the config's schedule. */
 int gbp_world_iterate(gbp_world_t *w);
 /* Same with an explicit schedule: n sub-steps of (internal[i], external[i]). */

@@ -211,6 +211,7 @@ __global__ void k_init_vars(Store s, int64_t first, int64_t count, const double 
   s.m_trk[s.at<3>(0, vi)] = gbp::empty_marker();
   s.trk_record[vi] = 0u;
   s.trk_timeout[vi] = -1;
+  s.trk_seed[vi] = 1;
   s.trk_last[s.at<2>(0, vi)] = float(mu[0]);  // with_last_measurement (factor/mod.rs:279-283)
   s.trk_last[s.at<2>(1, vi)] = float(mu[1]);
   s.trk_value[vi] = 0.0;
@@ -364,6 +365,83 @@ __global__ void k_change_prior_list(Store s, int p, uint32_t epoch, int var, int
   if (t >= m) return;
   const double nm[4] = {means[4 * t], means[4 * t + 1], means[4 * t + 2], means[4 * t + 3]};
   change_prior_dev(s, p, epoch, robots[t], var, nm);
+}
+
+// FactorGraph::reset_variables (factorgraph.rs:1541-1564) for the listed robots, one thread per
+// (robot, variable): VariableNode::reset (variable.rs:350-360) — belief mean and precision replaced, the
+// information vector kept, every inbox entry emptied — and FactorNode::empty_inbox (factor/mod.rs:480-483)
+// for the own factors, whose messages FROM this variable are the published record: epoch 0 = "none".
+__global__ void k_reset_variables(Store s, int p, int m, const int32_t *__restrict__ robots,
+                                  const double *__restrict__ means, double first_last_sigma, double inbetween_sigma) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int V = s.V;
+  if (t >= int64_t(m) * V) return;
+  const int k = int(t / V), i = int(t - int64_t(k) * V);
+  const int64_t r = robots[k], vi = r * V + i;
+  const double sigma = (i == 0 || i == V - 1) ? first_last_sigma : inbetween_sigma;
+  const double *src = s.latest[r] ? s.bel_ext : s.pub[p];
+  double eta[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) eta[a] = src[s.at<gbp::kRec>(a, vi)];
+  double *dst[2] = {s.pub[p], s.bel_ext};
+  for (int b = 0; b < 2; ++b) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) dst[b][s.at<gbp::kRec>(a, vi)] = eta[a];
+#pragma unroll
+    for (int a = 0; a < 16; ++a) dst[b][s.at<gbp::kRec>(4 + a, vi)] = (a % 5 == 0) ? sigma : 0.0;  // from_diag_elem
+#pragma unroll
+    for (int a = 0; a < 4; ++a) dst[b][s.at<gbp::kRec>(20 + a, vi)] = means[4 * t + a];
+  }
+  s.pub_epoch[p][vi] = 0u;
+  s.m_dynL[s.at<20>(0, vi)] = gbp::empty_marker();
+  s.m_dynR[s.at<20>(0, vi)] = gbp::empty_marker();
+  s.m_obs[s.at<4>(0, vi)] = gbp::empty_marker();
+  s.m_trk[s.at<3>(0, vi)] = gbp::empty_marker();
+  s.trk_seed[vi] = 0;
+  if (i >= 1 && s.eoff)
+    for (int64_t e = s.eoff[r]; e < s.eoff[r + 1]; ++e) s.mir[e * (V - 1) + (i - 1)] = gbp::empty_marker();
+}
+
+// ... and the robot's own InterRobot factors lose the message they held from the NEIGHBOUR's variable.
+// The neighbour A evaluates that factor itself (gbp_iterate.cuh) with the mean it last sent: until A
+// delivers again the factor linearises A's side at zeros, i.e. the edge (A <- r) is frozen at (0, 0).
+// One thread per edge of a reset robot; A's list is sorted by id.
+__global__ void k_reset_reverse_edges(Store s, int m, const int32_t *__restrict__ robots) {
+  const int k = blockIdx.x;
+  if (k >= m) return;
+  const int32_t r = robots[k];
+  const int Vm1 = s.V - 1;
+  for (int64_t e = s.eoff[r] + threadIdx.x; e < s.eoff[r + 1]; e += blockDim.x) {
+    const int32_t A = s.enbr[e];
+    if (A >= s.Nloc) continue;
+    int64_t lo = s.eoff[A], hi = s.eoff[A + 1];
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (s.enbr[mid] < r) lo = mid + 1;
+      else hi = mid;
+    }
+    if (lo >= s.eoff[A + 1] || s.enbr[lo] != r) continue;
+    s.e_frozen[lo] = uint8_t(s.e_frozen[lo] | 1);
+    for (int i = 0; i < Vm1; ++i) {
+      s.mu_frozen[lo * Vm1 + i] = 0.0;
+      s.mu_frozen[s.EV + lo * Vm1 + i] = 0.0;
+    }
+  }
+}
+
+// FactorGraph::reset_tracking_factors (factorgraph.rs:1566-1590): set_timeout(10) on the tracking factor
+// of every variable but the first and the last.
+__global__ void k_reset_tracking(Store s, int m, const int32_t *__restrict__ robots) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int V = s.V;
+  if (t >= int64_t(m) * V) return;
+  const int k = int(t / V), i = int(t - int64_t(k) * V);
+  if (i >= 1 && i <= V - 2) s.trk_timeout[int64_t(robots[k]) * V + i] = 10;
+}
+
+__global__ void k_set_next_wp(Store s, int m, const int32_t *__restrict__ robots, int32_t value) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < m) s.next_wp[robots[t]] = value;
 }
 
 // Gather VariableBelief of every variable into the ABI's array-of-structs layout.
@@ -941,6 +1019,7 @@ int reserve_robots(gbp_world *w, int64_t newcap) {
   CK(regrow(s.dyn_c, 4, oldNV, newNV, used, st, true));
   CK(regrow(s.trk_record, 1, oldNV, newNV, used, st));
   CK(regrow(s.trk_timeout, 1, oldNV, newNV, used, st));
+  CK(regrow(s.trk_seed, 1, oldNV, newNV, used, st));
   CK(regrow(s.trk_last, 2, oldNV, newNV, used, st, true));
   CK(regrow(s.trk_value, 1, oldNV, newNV, used, st));
   CK(regrow(s.radius, 1, oldcap, newcap, keep, st));
@@ -1460,7 +1539,7 @@ void gbp_world_destroy(gbp_world_t *w) {
   free_edge_set(w, &w->edges[1]);
   void *ptrs[] = {s.prior_eta, s.prior_lam, s.pub[0], s.pub[1], s.pub_epoch[0], s.pub_epoch[1], s.bel_ext,
                   s.mu_ext, s.cov, s.valid, s.m_dynL, s.m_dynR, s.m_obs, s.m_trk, s.dyn_c,
-                  s.trk_record, s.trk_timeout, s.trk_last, s.trk_value, s.radius, s.t0, s.pos, s.antenna,
+                  s.trk_record, s.trk_timeout, s.trk_seed, s.trk_last, s.trk_value, s.radius, s.t0, s.pos, s.antenna,
                   s.idle, s.finished, s.latest, s.iter_factor, s.gid, s.next_wp, s.coll_hits, w->coll_totals, s.wp_off, s.wp_xy, s.eoff,
                   s.nlow, w->t_nlow, w->t_result_dev, w->sdf_dev, w->t_cx,
                   w->t_cz, w->t_idx, w->t_idx_sorted, w->t_keys, w->t_keys_sorted, w->t_cnt, w->t_off,
@@ -2030,6 +2109,103 @@ int gbp_world_change_prior_of_variable(gbp_world_t *w, int32_t var, int32_t m, c
   cudaFree(dr);
   cudaFree(dm);
   mark_halo_stale(w);
+  return 0;
+}
+
+namespace {
+int check_robot_list(const gbp_world *w, int32_t m, const int32_t *robots, const char *what) {
+  if (m < 0 || (m > 0 && !robots)) return fail(GBP_ERR_BAD_ARGUMENT, std::string(what) + ": bad robot list");
+  for (int k = 0; k < m; ++k)
+    if (robots[k] < 0 || robots[k] >= w->s.Nloc) return fail(GBP_ERR_BAD_ARGUMENT, std::string(what) + ": robot index out of range");
+  return 0;
+}
+}  // namespace
+
+int gbp_world_set_tracking_path(gbp_world_t *w, int32_t m, const int32_t *robots, const int32_t *wp_offsets,
+                                const float *wp_xy) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (int rc = check_robot_list(w, m, robots, "gbp_world_set_tracking_path")) return rc;
+  if (m == 0) return 0;
+  if (!wp_offsets || !wp_xy) return fail(GBP_ERR_BAD_ARGUMENT, "gbp_world_set_tracking_path: null path");
+  for (int k = 0; k < m; ++k)
+    if (wp_offsets[k + 1] - wp_offsets[k] < 2)
+      return fail(GBP_ERR_BAD_ARGUMENT, "gbp_world_set_tracking_path: a path needs two or more points");
+  if (set_device(w)) return GBP_ERR_CUDA;
+  // the waypoint CSR is rebuilt whole on the host (a path change is a per-mission event, not per tick)
+  const int n = w->s.Nloc;
+  std::vector<std::vector<float>> poly(static_cast<size_t>(n));
+  for (int r = 0; r < n; ++r)
+    poly[r].assign(w->wp_xy.begin() + 2 * size_t(w->wp_off[r]), w->wp_xy.begin() + 2 * size_t(w->wp_off[r + 1]));
+  for (int k = 0; k < m; ++k)
+    poly[robots[k]].assign(wp_xy + 2 * size_t(wp_offsets[k]), wp_xy + 2 * size_t(wp_offsets[k + 1]));
+  w->wp_off.assign(1, 0);
+  w->wp_xy.clear();
+  for (int r = 0; r < n; ++r) {
+    w->wp_xy.insert(w->wp_xy.end(), poly[r].begin(), poly[r].end());
+    w->wp_off.push_back(int32_t(w->wp_xy.size() / 2));
+  }
+  cudaStream_t st = w->stream;
+  CK(cudaStreamSynchronize(st));
+  cudaFree(w->s.wp_off);
+  cudaFree(w->s.wp_xy);
+  CK(dalloc(w->s.wp_off, w->wp_off.size()));
+  CK(dalloc(w->s.wp_xy, w->wp_xy.size()));
+  CK(cudaMemcpyAsync(w->s.wp_off, w->wp_off.data(), w->wp_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(w->s.wp_xy, w->wp_xy.data(), w->wp_xy.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  int32_t *dr = nullptr;
+  CK(dalloc(dr, m));
+  CK(cudaMemcpyAsync(dr, robots, size_t(m) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  k_set_next_wp<<<blocks_for(m, 128), 128, 0, st>>>(w->s, m, dr, 1);  // Route::update_waypoints: target_index = 1
+  CK(cudaGetLastError());
+  w->launches += 1;
+  CK(cudaStreamSynchronize(st));
+  cudaFree(dr);
+  return 0;
+}
+
+int gbp_world_reset_variables(gbp_world_t *w, int32_t m, const int32_t *robots, const double *means,
+                              double first_last_sigma, double inbetween_sigma) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (int rc = check_robot_list(w, m, robots, "gbp_world_reset_variables")) return rc;
+  if (m == 0) return 0;
+  if (!means) return fail(GBP_ERR_BAD_ARGUMENT, "gbp_world_reset_variables: null means");
+  if (w->sh.ws > 1)
+    return fail(GBP_ERR_STATE, "gbp_world_reset_variables: not available on a sharded world yet (the emptied "
+                               "InterRobot inboxes of cross-shard factors would have to travel)");
+  if (set_device(w)) return GBP_ERR_CUDA;
+  const int V = w->s.V;
+  cudaStream_t st = w->stream;
+  int32_t *dr = nullptr;
+  double *dm = nullptr;
+  CK(dalloc(dr, m));
+  CK(dalloc(dm, size_t(4) * V * m));
+  CK(cudaMemcpyAsync(dr, robots, size_t(m) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dm, means, size_t(4) * V * m * sizeof(double), cudaMemcpyHostToDevice, st));
+  k_reset_variables<<<blocks_for(int64_t(m) * V, 128), 128, 0, st>>>(w->s, w->p, m, dr, dm, first_last_sigma,
+                                                                     inbetween_sigma);
+  if (w->s.eoff && w->s.E > 0) k_reset_reverse_edges<<<m, 64, 0, st>>>(w->s, m, dr);
+  CK(cudaGetLastError());
+  w->launches += 2;
+  CK(cudaStreamSynchronize(st));
+  cudaFree(dr);
+  cudaFree(dm);
+  mark_halo_stale(w);
+  return 0;
+}
+
+int gbp_world_reset_tracking_factors(gbp_world_t *w, int32_t m, const int32_t *robots) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (int rc = check_robot_list(w, m, robots, "gbp_world_reset_tracking_factors")) return rc;
+  if (m == 0) return 0;
+  if (set_device(w)) return GBP_ERR_CUDA;
+  int32_t *dr = nullptr;
+  CK(dalloc(dr, m));
+  CK(cudaMemcpyAsync(dr, robots, size_t(m) * sizeof(int32_t), cudaMemcpyHostToDevice, w->stream));
+  k_reset_tracking<<<blocks_for(int64_t(m) * w->s.V, 128), 128, 0, w->stream>>>(w->s, m, dr);
+  CK(cudaGetLastError());
+  w->launches += 1;
+  CK(cudaStreamSynchronize(w->stream));
+  cudaFree(dr);
   return 0;
 }
 

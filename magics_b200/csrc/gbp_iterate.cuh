@@ -591,7 +591,13 @@ __global__ void GBP_ITER_BOUNDS
         if (s.en_obs) obstacle_update(s, vi, x0);
         // Tracking factors are skipped until iteration_count.factor >= 10
         // (factorgraph.rs:701); their inbox starts with the variable's belief
-        if (s.en_trk && itf >= 10u) tracking_update(s, r, vi, x);
+        if (s.en_trk && itf >= 10u) {
+          double xt[4];
+          const bool has = own_ne || s.trk_seed[vi] != 0;  // emptied by reset_variables: linearise at zeros
+#pragma unroll
+          for (int k = 0; k < 4; ++k) xt[k] = has ? x[k] : 0.0;
+          tracking_update(s, r, vi, xt);
+        }
       }
       itf += 1;
 

@@ -73,6 +73,8 @@ struct Store {
   double *dyn_c;         // [4][NV]   Dynamic factor i: delta_t (f32 widened) and q11, q12, q22 (gbp_math.cuh dyn_q)
   uint32_t *trk_record;  // [NV]      Tracking.record
   int32_t *trk_timeout;  // [NV]      TrackingFactor.timeout (-1 = None)
+  uint8_t *trk_seed;     // [NV]      1: the Tracking factor's inbox still holds the belief it was created with
+                         //           (factorgraph.rs:310-322); 0 after FactorGraph::reset_variables emptied it
   float *trk_last;       // [2][NV]   LastMeasurement.pos (f32)
   double *trk_value;     // [NV]      LastMeasurement.value
 

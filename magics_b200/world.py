@@ -284,6 +284,28 @@ class World:
         self._call("gbp_world_change_prior_of_variable", C.c_int32(variable_index), C.c_int32(robots.shape[0]),
                    _p(robots, C.c_int32), _p(new_means, C.c_double))
 
+    # ---- global-planner hand-off (planner/robot.rs:655-776) ----------------
+    def set_tracking_path(self, robots, paths):
+        """New polyline (>= 2 points each) for the listed robots: tracking path + mission waypoints, next index 1."""
+        robots = np.ascontiguousarray(robots, np.int32)
+        off = np.zeros(len(paths) + 1, np.int32)
+        off[1:] = np.cumsum([len(p) for p in paths])
+        xy = np.ascontiguousarray(np.concatenate([np.asarray(p, np.float32).reshape(-1, 2) for p in paths]), np.float32)
+        self._call("gbp_world_set_tracking_path", C.c_int32(robots.size), _p(robots, C.c_int32), _p(off, C.c_int32),
+                   _p(xy, C.c_float))
+
+    def reset_variables(self, robots, means, first_last_sigma=1e30, inbetween_sigma=float("inf")):
+        """FactorGraph::reset_variables for the listed robots; means (m, V, 4) f64."""
+        robots = np.ascontiguousarray(robots, np.int32)
+        means = np.ascontiguousarray(means, np.float64)
+        assert means.size == robots.size * self.V * 4
+        self._call("gbp_world_reset_variables", C.c_int32(robots.size), _p(robots, C.c_int32), _p(means, C.c_double),
+                   C.c_double(first_last_sigma), C.c_double(inbetween_sigma))
+
+    def reset_tracking_factors(self, robots):
+        robots = np.ascontiguousarray(robots, np.int32)
+        self._call("gbp_world_reset_tracking_factors", C.c_int32(robots.size), _p(robots, C.c_int32))
+
     def iterate(self):
         self._call("gbp_world_iterate")
 

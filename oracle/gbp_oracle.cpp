@@ -1573,6 +1573,62 @@ int gbpo_change_prior_of_variable(void *p, int var, int m, const int32_t *robots
   return 0;
 }
 
+// ---- global-planner hand-off: what `update_robot_mission` does to the factor graph
+// when an RRT* path arrives (planner/robot.rs:655-776).
+// FactorGraph::modify_tracking_factors(|t| t.set_tracking_path(..)) (factorgraph.rs:1467-1477,
+// factor/tracking.rs:134-136) + Route::update_waypoints (robot.rs:389-392): the tracking path of every
+// tracking factor and the mission's waypoints become the new polyline, target_index = 1.
+int gbpo_set_tracking_path(void *p, int m, const int32_t *robots, const int32_t *wp_offsets, const float *wp_xy) {
+  World *w = static_cast<World *>(p);
+  for (int k = 0; k < m; ++k) {
+    Robot &r = w->robots[robots[k]];
+    std::vector<std::pair<float, float>> path;
+    for (int q = wp_offsets[k]; q < wp_offsets[k + 1]; ++q) path.emplace_back(wp_xy[2 * q], wp_xy[2 * q + 1]);
+    if (path.size() < 2) return -2;  // min_len_vec::TwoOrMore
+    for (auto &kv : r.g.factors)
+      if (kv.second.kind == TRACKING) kv.second.path = path;
+    r.waypoints = path;
+    r.next_wp = 1;
+  }
+  return 0;
+}
+// FactorGraph::reset_variables (factorgraph.rs:1541-1564): VariableNode::reset (variable.rs:350-360) for
+// every variable — mean and belief precision replaced, every inbox entry emptied — then
+// FactorNode::empty_inbox (factor/mod.rs:480-483) for every factor of the graph.
+int gbpo_reset_variables(void *p, int m, const int32_t *robots, const double *means, double first_last_sigma,
+                         double inbetween_sigma) {
+  World *w = static_cast<World *>(p);
+  for (int k = 0; k < m; ++k) {
+    Graph &g = w->robots[robots[k]].g;
+    const int V = int(g.vars.size());
+    for (int i = 0; i < V; ++i) {
+      Variable &v = g.vars[i];
+      const double sigma = (i == 0 || i == V - 1) ? first_last_sigma : inbetween_sigma;
+      for (int a = 0; a < DOFS; ++a) v.mu[a] = means[(size_t(k) * V + i) * DOFS + a];
+      for (int a = 0; a < DOFS; ++a)
+        for (int b = 0; b < DOFS; ++b) v.lam(a, b) = (a == b) ? sigma : 0.0;  // Matrix::from_diag_elem
+      for (auto &kv : v.inbox) kv.second = Message::empty();
+    }
+    for (auto &kv : g.factors)
+      for (auto &in : kv.second.inbox) in.second = Message::empty();
+  }
+  return 0;
+}
+// FactorGraph::reset_tracking_factors (factorgraph.rs:1566-1590): set_timeout(10) on the tracking factor of
+// every variable but the first and the last.
+int gbpo_reset_tracking_factors(void *p, int m, const int32_t *robots) {
+  World *w = static_cast<World *>(p);
+  for (int k = 0; k < m; ++k) {
+    Graph &g = w->robots[robots[k]].g;
+    const int V = int(g.vars.size());
+    for (auto &kv : g.factors) {
+      Factor &f = kv.second;
+      if (f.kind == TRACKING && f.own_var >= 1 && f.own_var <= V - 2) f.timeout = 10;
+    }
+  }
+  return 0;
+}
+
 int gbpo_internal_factor_iteration(void *p) { world_internal(*static_cast<World *>(p), true, false); return 0; }
 int gbpo_internal_variable_iteration(void *p) { world_internal(*static_cast<World *>(p), false, true); return 0; }
 int gbpo_external_factor_iteration(void *p) { world_external_factor(*static_cast<World *>(p)); return 0; }

@@ -225,6 +225,24 @@ class OracleWorld:
         self._call("gbpo_change_prior_of_variable", int(variable_index), robots.shape[0],
                    _p(robots, C.c_int32), _p(new_means, C.c_double))
 
+    def set_tracking_path(self, robots, paths):
+        robots = np.ascontiguousarray(robots, np.int32)
+        off = np.zeros(len(paths) + 1, np.int32)
+        off[1:] = np.cumsum([len(p) for p in paths])
+        xy = np.ascontiguousarray(np.concatenate([np.asarray(p, np.float32).reshape(-1, 2) for p in paths]), np.float32)
+        self._call("gbpo_set_tracking_path", int(robots.size), _p(robots, C.c_int32), _p(off, C.c_int32),
+                   _p(xy, C.c_float))
+
+    def reset_variables(self, robots, means, first_last_sigma=1e30, inbetween_sigma=float("inf")):
+        robots = np.ascontiguousarray(robots, np.int32)
+        means = np.ascontiguousarray(means, np.float64)
+        self._call("gbpo_reset_variables", int(robots.size), _p(robots, C.c_int32), _p(means, C.c_double),
+                   C.c_double(first_last_sigma), C.c_double(inbetween_sigma))
+
+    def reset_tracking_factors(self, robots):
+        robots = np.ascontiguousarray(robots, np.int32)
+        self._call("gbpo_reset_tracking_factors", int(robots.size), _p(robots, C.c_int32))
+
     def iterate(self):
         self._call("gbpo_iterate")
 
