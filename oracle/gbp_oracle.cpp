@@ -26,6 +26,13 @@
 // `unrolled_dot` (ndarray numeric_util.rs: eight partial sums combined
 // (p0+p4)+(p1+p5)+(p2+p6)+(p3+p7), then the tail sequentially).
 //
+// SDF generation (crates/env_to_png): image_to_tile_coords and one is_tile_obstacle case
+// are pinned by the crate's #[test]s (the other three assertions there are stale against the crate's own
+// code, tests/golden/make_golden.py records which); the placeable shapes and `image::imageops::blur`
+// (image 0.25.1, third party) are PARITY UNPINNED and checked against independent geometry / a scipy
+// Gaussian instead (tests/test_oracle_env.py).  The RRT* hand-off functions (next-4) restate
+// factorgraph.rs:1467-1590 literally; the reference has no test for them.
+//
 // Build: g++ -O3 -std=c++17 -ffp-contract=off -pthread -shared -fPIC (see Makefile).
 
 #include <algorithm>
