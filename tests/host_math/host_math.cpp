@@ -40,4 +40,19 @@ int hm_dyn_message(int keep, double dt, double qs, int other_nonempty, const dou
   for (int k = 0; k < 16; ++k) lam[k] = l[k];
   return ok ? 1 : 0;
 }
+// InterRobot factor of robot A toward robot B, message to B's variable (the one the engine pulls).
+// rec_a = A's published record (eta4, Lambda16); returns 0 for Message::empty() (skip / singular / inf).
+int hm_interrobot_message(int a_first, const double *mu_a, const double *mu_b, int a_nonempty, const double *rec_a,
+                          double dsafe, double tiny, double lm, double *eta2, double *lam4) {
+  double ma[2] = {mu_a[0], mu_a[1]}, mb[2] = {mu_b[0], mu_b[1]}, rec[20], e[2], l[4];
+  for (int k = 0; k < 20; ++k) rec[k] = rec_a[k];
+  const bool ok = gbp::interrobot_message(a_first != 0, ma, mb, a_nonempty != 0, rec, dsafe, tiny, lm, e, l);
+  for (int k = 0; k < 2; ++k) eta2[k] = e[k];
+  for (int k = 0; k < 4; ++k) lam4[k] = l[k];
+  return ok ? 1 : 0;
+}
+int hm_interrobot_skip(int a_first, const double *mu_a, const double *mu_b, double dsafe) {
+  double ma[2] = {mu_a[0], mu_a[1]}, mb[2] = {mu_b[0], mu_b[1]};
+  return gbp::interrobot_skip(a_first != 0, ma, mb, dsafe) ? 1 : 0;
+}
 }

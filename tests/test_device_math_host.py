@@ -121,3 +121,133 @@ def test_divide_all_is_bit_identical_to_plain_division(libs):
             ref = c / det
         same = (o.view(np.uint64) == ref.view(np.uint64)) | (np.isnan(o) & np.isnan(ref))
         assert same.all(), (c, det, o, ref)
+
+
+# ---- the device factor / belief arithmetic against independent float64 linear algebra -------------------
+def _spd(rng, scale):
+    a = rng.standard_normal((4, 4))
+    return (a @ a.T + 4 * np.eye(4)) * scale
+
+
+def _schur(eta, lam, keep):
+    """Marginalise the other 4-block out of an 8-dim information form (marginalise_factor_distance.rs:55-127)."""
+    a = slice(0, 4) if keep == 0 else slice(4, 8)
+    b = slice(4, 8) if keep == 0 else slice(0, 4)
+    lbb_inv = np.linalg.inv(lam[b, b])
+    return eta[a] - lam[a, b] @ lbb_inv @ eta[b], lam[a, a] - lam[a, b] @ lbb_inv @ lam[b, a]
+
+
+def _rel(got, ref):
+    return float(np.max(np.abs(got - ref)) / max(1e-300, np.max(np.abs(ref))))
+
+
+def test_dynamic_factor_message_matches_the_schur_complement(libs):
+    dev, _, _ = libs
+    rng = np.random.default_rng(7)
+    I2, Z2 = np.eye(2), np.zeros((2, 2))
+    for trial in range(300):
+        dt, sigma = float(rng.uniform(0.05, 2.0)), float(rng.choice([0.1, 1.0]))
+        qs = 1.0 / sigma ** 2
+        # DynamicFactor (factor/dynamic.rs:22-52): h = J x, z = 0, so eta_p = 0 and Lambda_p = J^T Qi^-1 J
+        J = np.block([[I2, dt * I2, -I2, Z2], [Z2, I2, Z2, -I2]])
+        Qi_inv = qs * np.block([[12 / dt ** 3 * I2, -6 / dt ** 2 * I2], [-6 / dt ** 2 * I2, 4 / dt * I2]])
+        lam_p = J.T @ Qi_inv @ J
+        for keep in (0, 1):
+            for nonempty in (0, 1):
+                oe, ol = rng.standard_normal(4) * 10, _spd(rng, float(10.0 ** rng.integers(-1, 4)))
+                other = np.concatenate([oe, ol.reshape(-1)])
+                eta, lam = np.zeros(4), np.zeros(16)
+                ok = dev.hm_dyn_message(keep, C.c_double(dt), C.c_double(qs), nonempty, other.ctypes.data_as(P),
+                                        eta.ctypes.data_as(P), lam.ctypes.data_as(P))
+                assert ok == 1
+                e8, l8 = np.zeros(8), lam_p.copy()
+                o = slice(4, 8) if keep == 0 else slice(0, 4)  # the OTHER variable's block
+                if nonempty:
+                    e8[o] += oe
+                    l8[o, o] += ol
+                re, rl = _schur(e8, l8, keep)
+                # against the size of the unreduced block: the potential alone marginalises to (almost) nothing,
+                # a difference of two equal matrices, so the result's own size is round-off
+                k = slice(0, 4) if keep == 0 else slice(4, 8)
+                scale = np.abs(l8[k, k]).max()
+                assert np.max(np.abs(lam.reshape(4, 4) - rl)) <= 1e-9 * scale
+                assert np.max(np.abs(eta - re)) <= 1e-9 * max(1.0, np.abs(re).max(), np.abs(e8).max())
+
+
+def test_belief_moments_match_a_dense_solve(libs):
+    dev, _, _ = libs
+    rng = np.random.default_rng(8)
+    for trial in range(500):
+        lam = _spd(rng, float(10.0 ** rng.integers(-2, 6)))
+        if trial % 3 == 0:  # x and y decoupled, a 1e30 prior
+            lam[np.add.outer(np.arange(4), np.arange(4)) % 2 == 1] = 0.0
+            lam[0, 0] += 1e30
+        eta = rng.standard_normal(4) * np.abs(lam).max()
+        mu, cov, valid = np.zeros(4), np.zeros(16), C.c_int(0)
+        taken = dev.hm_belief_moments(eta.ctypes.data_as(P), lam.reshape(-1).copy().ctypes.data_as(P),
+                                      mu.ctypes.data_as(P), cov.ctypes.data_as(P), C.byref(valid))
+        assert taken == 1 and valid.value == 1
+        ref = np.linalg.inv(lam)
+        assert _rel(cov.reshape(4, 4), ref) < 1e-9
+        assert np.max(np.abs(mu - ref @ eta)) <= 1e-9 * max(1.0, np.abs(ref @ eta).max())
+    # all-zero precision (an interior variable before any message): nothing is taken, mean untouched
+    mu = np.array([1.0, 2.0, 3.0, 4.0])
+    z = np.zeros(16)
+    assert dev.hm_belief_moments(np.zeros(4).ctypes.data_as(P), z.ctypes.data_as(P), mu.ctypes.data_as(P),
+                                 np.zeros(16).ctypes.data_as(P), C.byref(C.c_int(0))) == 0
+    assert np.array_equal(mu, [1.0, 2.0, 3.0, 4.0])
+
+
+def test_interrobot_message_matches_the_linearised_factor(libs):
+    dev, _, _ = libs
+    rng = np.random.default_rng(9)
+    n_msg = n_skip = 0
+    for trial in range(2000):
+        a_first = int(rng.integers(0, 2))
+        dsafe, sigma = float(rng.uniform(1.0, 4.0)), 0.01
+        lm = 1.0 / sigma ** 2
+        mu_a = rng.uniform(-3, 3, 2)
+        mu_b = mu_a + rng.uniform(-1, 1, 2) * dsafe * 1.2
+        tiny = 9.999999974752427e-7 * float(rng.integers(1, 50))
+        a_nonempty = int(rng.integers(0, 2))
+        ea, la = rng.standard_normal(4) * 5, _spd(rng, float(10.0 ** rng.integers(0, 4)))
+        rec = np.concatenate([ea, la.reshape(-1)])
+        eta2, lam4 = np.zeros(2), np.zeros(4)
+        ok = dev.hm_interrobot_message(a_first, mu_a.ctypes.data_as(P), mu_b.ctypes.data_as(P), a_nonempty,
+                                       rec.ctypes.data_as(P), C.c_double(dsafe), C.c_double(tiny), C.c_double(lm),
+                                       eta2.ctypes.data_as(P), lam4.ctypes.data_as(P))
+        skip = dev.hm_interrobot_skip(a_first, mu_a.ctypes.data_as(P), mu_b.ctypes.data_as(P), C.c_double(dsafe))
+        x0, x1 = (mu_a, mu_b) if a_first else (mu_b, mu_a)  # slot order by robot id (id.rs:83-118)
+        # InterRobotFactor::skip (interrobot.rs:213-226): squared distance without the tiny offset
+        assert skip == int(float(np.sum((x0 - x1) ** 2)) >= dsafe * dsafe)
+        if skip:
+            assert ok == 0
+            n_skip += 1
+            continue
+        # measure / jacobian (interrobot.rs:121-204) at x = (x0, 0, 0, x1, 0, 0)
+        d = x0 - x1 + tiny
+        r = float(np.linalg.norm(d))
+        J = np.zeros(8)
+        h = 0.0
+        if r <= dsafe:
+            h = 1.0 - r / dsafe
+            J[0:2] = -d / (dsafe * r)
+            J[4:6] = d / (dsafe * r)
+        x = np.concatenate([x0, [0, 0], x1, [0, 0]])
+        v0 = J @ x + (0.0 - h)
+        eta8, lam8 = J * lm * v0, np.outer(J, J) * lm
+        sa = slice(0, 4) if a_first else slice(4, 8)  # A's (the factor owner's) variable
+        if a_nonempty:
+            eta8[sa] += ea
+            lam8[sa, sa] += la
+        if not a_nonempty:
+            # the potential alone is rank one: Lambda of A's block is singular, the reference returns Empty
+            assert ok == 0
+            continue
+        re, rl = _schur(eta8, lam8, keep=1 if a_first else 0)
+        assert ok == 1
+        n_msg += 1
+        assert np.max(np.abs(eta2 - re[:2])) <= 1e-9 * max(1.0, np.abs(re).max())
+        assert np.max(np.abs(lam4.reshape(2, 2) - rl[:2, :2])) <= 1e-9 * max(1.0, np.abs(rl).max())
+        assert np.max(np.abs(rl[2:, :])) <= 1e-9 * max(1.0, np.abs(rl).max())  # the rest of the message is zero
+    assert n_msg > 200 and n_skip > 200
