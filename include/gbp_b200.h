@@ -342,18 +342,26 @@ int gbp_world_sdf_lookup(gbp_world_t *w, int32_t m, const double *xy, uint32_t *
 /* FactorGraph::factor_count / node_count style totals (factorgraph.rs:247-276):
  * out[0]=variables out[1]=dynamic out[2]=obstacle out[3]=tracking out[4]=interrobot. */
 int gbp_world_node_counts(gbp_world_t *w, int64_t out[5]);
+/* Which iterate kernel runs a robot is decided on the device per launch: k_iterate_axis (two lanes per
+ * variable) while the robot's x and y chains are decoupled — no InterRobot factor inside its safety
+ * distance, flat SDF, no Tracking message — and k_iterate otherwise; both produce the bits of the
+ * reference's update order.  general_only != 0 sends every robot through k_iterate
+ * (A/B tests).  read: robots of this shard currently assigned to each kernel. */
+int gbp_world_set_iterate_path(gbp_world_t *w, int32_t general_only);
+int gbp_world_read_iterate_path(gbp_world_t *w, int64_t *robots_axis, int64_t *robots_general);
 /* number of GPU kernels this handle has launched so far (bench `gpu_launches`) */
 int64_t gbp_world_kernel_launches(const gbp_world_t *w);
 /* Optional per-launch CUDA-event timing on the engine's stream (bench.py's
  * roofline leg): accumulated count / device milliseconds per kernel family. */
 enum gbp_profile_kind {
-  GBP_PROFILE_ITERATE_INT = 0,     /* k_iterate<EXT=0,INT=1> */
-  GBP_PROFILE_ITERATE_EXT = 1,     /* k_iterate<EXT=1,INT=0> */
-  GBP_PROFILE_ITERATE_EXT_INT = 2, /* k_iterate<EXT=1,INT=1>, the dominant kernel */
+  GBP_PROFILE_ITERATE_INT = 0,     /* k_iterate_axis<EXT=0,INT=1> (k_iterate when general_only) */
+  GBP_PROFILE_ITERATE_EXT = 1,     /* k_iterate_axis<EXT=1,INT=0> */
+  GBP_PROFILE_ITERATE_EXT_INT = 2, /* k_iterate_axis<EXT=1,INT=1>, the dominant kernel */
   GBP_PROFILE_TOPOLOGY = 3,        /* whole gbp_world_update_topology */
   GBP_PROFILE_PRIORS = 4,          /* horizon + current prior kernels */
   GBP_PROFILE_HALO = 5,            /* the send/recv part of the per-sub-step halo exchange */
-  GBP_PROFILE_KINDS = 6
+  GBP_PROFILE_ITERATE_GENERAL = 6, /* k_iterate over the robots k_iterate_axis handed over (any EXT/INT) */
+  GBP_PROFILE_KINDS = 7
 };
 int gbp_world_set_profiling(gbp_world_t *w, int32_t on);
 int gbp_world_read_profile(gbp_world_t *w, int32_t kind, int64_t *count, double *total_ms);

@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -19,6 +20,7 @@
 #include "../../include/gbp_b200.h"
 #include "gbp_comm.cuh"
 #include "gbp_iterate.cuh"
+#include "gbp_iterate_axis.cuh"
 #include "gbp_math.cuh"
 #include "gbp_shard.cuh"
 #include "gbp_store.cuh"
@@ -203,10 +205,13 @@ __global__ void k_init_vars(Store s, int64_t first, int64_t count, const double 
     s.cov[s.at<16>(k, vi)] = cov[k];
   }
   s.valid[vi] = fin ? 1 : 0;
+  s.cov_lazy[vi] = 0;
   s.mu_ext[s.at<2>(0, vi)] = mu[0];
   s.mu_ext[s.at<2>(1, vi)] = mu[1];
-  s.m_dynL[s.at<20>(0, vi)] = gbp::empty_marker();
-  s.m_dynR[s.at<20>(0, vi)] = gbp::empty_marker();
+  for (int b = 0; b < 2; ++b) {
+    s.m_dynL[b][s.at<20>(0, vi)] = gbp::empty_marker();
+    s.m_dynR[b][s.at<20>(0, vi)] = gbp::empty_marker();
+  }
   s.m_obs[s.at<4>(0, vi)] = gbp::empty_marker();
   s.m_trk[s.at<3>(0, vi)] = gbp::empty_marker();
   s.trk_record[vi] = 0u;
@@ -249,8 +254,8 @@ __device__ void change_prior_dev(const Store &s, int p, uint32_t epoch, int64_t 
   s.pub_epoch[p][vi] = epoch;
   s.mu_ext[s.at<2>(0, vi)] = nm[0];
   s.mu_ext[s.at<2>(1, vi)] = nm[1];
-  s.m_dynL[s.at<20>(0, vi)] = gbp::empty_marker();
-  s.m_dynR[s.at<20>(0, vi)] = gbp::empty_marker();
+  s.m_dynL[p][s.at<20>(0, vi)] = gbp::empty_marker();
+  s.m_dynR[p][s.at<20>(0, vi)] = gbp::empty_marker();
   s.m_obs[s.at<4>(0, vi)] = gbp::empty_marker();
   s.m_trk[s.at<3>(0, vi)] = gbp::empty_marker();
   if (var >= 1 && s.eoff)
@@ -287,9 +292,9 @@ __device__ void change_prior_warp(const Store &s, int p, uint32_t epoch, int64_t
     s.mu_ext[s.at<2>(0, vi)] = nm[0];
     s.mu_ext[s.at<2>(1, vi)] = nm[1];
   } else if (lane == 25) {
-    s.m_dynL[s.at<20>(0, vi)] = gbp::empty_marker();
+    s.m_dynL[p][s.at<20>(0, vi)] = gbp::empty_marker();
   } else if (lane == 26) {
-    s.m_dynR[s.at<20>(0, vi)] = gbp::empty_marker();
+    s.m_dynR[p][s.at<20>(0, vi)] = gbp::empty_marker();
   } else if (lane == 27) {
     s.m_obs[s.at<4>(0, vi)] = gbp::empty_marker();
   } else if (lane == 28) {
@@ -379,6 +384,8 @@ __global__ void k_reset_variables(Store s, int p, int m, const int32_t *__restri
   const int k = int(t / V), i = int(t - int64_t(k) * V);
   const int64_t r = robots[k], vi = r * V + i;
   const double sigma = (i == 0 || i == V - 1) ? first_last_sigma : inbetween_sigma;
+  // VariableNode::reset leaves the covariance alone: resolve a lazy one before the precision it derives from changes
+  if (s.cov_lazy[vi]) gbp::materialise_cov(s, p, r, vi);
   const double *src = s.latest[r] ? s.bel_ext : s.pub[p];
   double eta[4];
 #pragma unroll
@@ -393,8 +400,8 @@ __global__ void k_reset_variables(Store s, int p, int m, const int32_t *__restri
     for (int a = 0; a < 4; ++a) dst[b][s.at<gbp::kRec>(20 + a, vi)] = means[4 * t + a];
   }
   s.pub_epoch[p][vi] = 0u;
-  s.m_dynL[s.at<20>(0, vi)] = gbp::empty_marker();
-  s.m_dynR[s.at<20>(0, vi)] = gbp::empty_marker();
+  s.m_dynL[p][s.at<20>(0, vi)] = gbp::empty_marker();
+  s.m_dynR[p][s.at<20>(0, vi)] = gbp::empty_marker();
   s.m_obs[s.at<4>(0, vi)] = gbp::empty_marker();
   s.m_trk[s.at<3>(0, vi)] = gbp::empty_marker();
   s.trk_seed[vi] = 0;
@@ -457,6 +464,20 @@ __global__ void k_gather_beliefs(Store s, int p, double *eta, double *lam, doubl
     for (int k = 0; k < 16; ++k) lam[16 * t + k] = src[s.at<gbp::kRec>(4 + k, t)];
   if (mean)
     for (int k = 0; k < 4; ++k) mean[4 * t + k] = src[s.at<gbp::kRec>(20 + k, t)];
+  if (s.cov_lazy[t]) {
+    // not stored: the covariance is inv4 of the current precision, taken and finite (gbp_iterate_axis.cuh)
+    if (cov) {
+      double l[16], c[16];
+      for (int k = 0; k < 16; ++k) {
+        l[k] = src[s.at<gbp::kRec>(4 + k, t)];
+        c[k] = 0.0;
+      }
+      gbp::inv4(l, c);
+      for (int k = 0; k < 16; ++k) cov[16 * t + k] = c[k];
+    }
+    if (valid) valid[t] = 1;
+    return;
+  }
   if (cov)
     for (int k = 0; k < 16; ++k) cov[16 * t + k] = s.cov[s.at<16>(k, t)];
   if (valid) valid[t] = s.valid[t];
@@ -604,6 +625,10 @@ struct gbp_world {
   gbp_group *grp = nullptr;
   bool owns_stream = true;
   bool smem_opted_in[4] = {false, false, false, false};  // k_iterate<EXT,INT> dynamic shared memory opt-in
+  bool axis_opted_in[4] = {false, false, false, false};  // k_iterate_axis<EXT,INT> likewise
+  bool general_only = false;  // gbp_world_set_iterate_path: every robot through k_iterate
+  int sm_count = 148;
+  int par = 0;                // launch parity: which Store::gen_count the current launch appends to
   unsigned long long *coll_totals = nullptr;              // [0] Hit events so far, [1] pairs colliding now
   gbp::ShardInfo sh{};          // ws, rank, gfirst
   int32_t Ntot = 0;             // robots of the whole swarm
@@ -807,32 +832,47 @@ int group_halo(gbp_group *g) {
 template <bool EXT, bool INT>
 int launch_iterate(gbp_world *w) {
   Store &s = w->s;
-  bool &smem_opted_in = w->smem_opted_in[(EXT ? 2 : 0) + (INT ? 1 : 0)];
-  if (!smem_opted_in && gbp::kIterSmemBytes > 0) {
-    CK(cudaFuncSetAttribute(gbp::k_iterate<EXT, INT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            int(gbp::kIterSmemBytes)));
-    CK(cudaFuncSetAttribute(gbp::k_iterate<EXT, INT>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                            cudaSharedmemCarveoutMaxShared));
-    smem_opted_in = true;
-  }
+  const int which = (EXT ? 2 : 0) + (INT ? 1 : 0);
   w->epoch += 1;  // every shard steps its epoch, with or without robots
   if (s.Nloc == 0) {
     if (INT) w->p ^= 1;
     return 0;
   }
   const int rpw = 32 / s.V;
-  const int64_t warps = (int64_t(s.Nloc) + rpw - 1) / rpw;
   const int wpb = gbp::kIterBlock / 32;
-  const unsigned grid = unsigned((warps + wpb - 1) / wpb);
-  {
-    ProfileScope ps(w, EXT ? (INT ? GBP_PROFILE_ITERATE_EXT_INT : GBP_PROFILE_ITERATE_EXT) : GBP_PROFILE_ITERATE_INT);
-    gbp::k_iterate<EXT, INT><<<grid, gbp::kIterBlock, gbp::kIterSmemBytes, w->stream>>>(s, w->p, w->epoch);
+  const int kind = EXT ? (INT ? GBP_PROFILE_ITERATE_EXT_INT : GBP_PROFILE_ITERATE_EXT) : GBP_PROFILE_ITERATE_INT;
+  if (w->general_only) {
+    const int64_t warps = (int64_t(s.Nloc) + rpw - 1) / rpw;
+    const unsigned grid = unsigned((warps + wpb - 1) / wpb);
+    ProfileScope ps(w, kind);
+    gbp::k_iterate<EXT, INT><<<grid, gbp::kIterBlock, 0, w->stream>>>(s, w->p, w->epoch, -1);
+    w->launches += 1;
+  } else {
+    // the decoupled robots (two lanes per variable), then whatever that kernel handed over
+    const gbp::AxisGeom q = gbp::axis_geom(s.V);
+    if (!w->axis_opted_in[which]) {
+      CK(cudaFuncSetAttribute(gbp::k_iterate_axis<EXT, INT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(q.smem)));
+      w->axis_opted_in[which] = true;
+    }
+    {
+      ProfileScope ps(w, kind);
+      gbp::k_iterate_axis<EXT, INT><<<blocks_for(s.Nloc, q.rpc), q.threads, q.smem, w->stream>>>(s, w->p, w->epoch, q.rpc,
+                                                                                              w->par);
+    }
+    CK(cudaGetLastError());
+    {
+      const int64_t warps = (int64_t(s.Nloc) + rpw - 1) / rpw;
+      const unsigned grid = unsigned(std::min<int64_t>((warps + wpb - 1) / wpb, int64_t(w->sm_count) * 4));
+      ProfileScope ps(w, GBP_PROFILE_ITERATE_GENERAL);
+      gbp::k_iterate<EXT, INT><<<grid, gbp::kIterBlock, 0, w->stream>>>(s, w->p, w->epoch, w->par);
+    }
+    w->par ^= 1;
+    w->launches += 2;
   }
   CK(cudaGetLastError());
   if (w->spans.size() > 4096) {
     if (int rc = drain_profile(w)) return rc;
   }
-  w->launches += 1;
   if (INT) w->p ^= 1;
   return 0;
 }
@@ -1012,8 +1052,11 @@ int reserve_robots(gbp_world *w, int64_t newcap) {
   CK(regrow(s.mu_ext, 2, oldNV, newNV, used, st, true));
   CK(regrow(s.cov, 16, oldNV, newNV, used, st, true));
   CK(regrow(s.valid, 1, oldNV, newNV, used, st));
-  CK(regrow(s.m_dynL, 20, oldNV, newNV, used, st, true));
-  CK(regrow(s.m_dynR, 20, oldNV, newNV, used, st, true));
+  CK(regrow(s.cov_lazy, 1, oldNV, newNV, used, st));
+  for (int b = 0; b < 2; ++b) {
+    CK(regrow(s.m_dynL[b], 20, oldNV, newNV, used, st, true));
+    CK(regrow(s.m_dynR[b], 20, oldNV, newNV, used, st, true));
+  }
   CK(regrow(s.m_obs, 4, oldNV, newNV, used, st, true));
   CK(regrow(s.m_trk, 3, oldNV, newNV, used, st, true));
   CK(regrow(s.dyn_c, 4, oldNV, newNV, used, st, true));
@@ -1030,6 +1073,12 @@ int reserve_robots(gbp_world *w, int64_t newcap) {
   CK(regrow(s.finished, 1, oldcap, newcap, keep, st));
   CK(regrow(s.latest, 1, oldcap, newcap, keep, st));
   CK(regrow(s.iter_factor, 1, oldcap, newcap, keep, st));
+  CK(regrow(s.mode, 1, oldcap, newcap, keep, st));
+  CK(regrow(s.gen_list, 1, oldcap, newcap, 0, st));
+  if (!s.gen_count) {
+    CK(dalloc(s.gen_count, 2));
+    CK(cudaMemsetAsync(s.gen_count, 0, 2 * sizeof(int32_t), st));
+  }
   CK(regrow(s.gid, 1, oldcap, newcap, keep, st));
   CK(regrow(s.next_wp, 1, oldcap, newcap, keep, st));
   CK(regrow(s.coll_hits, 1, oldcap, newcap, keep, st));
@@ -1427,6 +1476,8 @@ gbp_world *make_world(const gbp_config_t *cfg, int32_t device, cudaStream_t shar
     return nullptr;
   }
   w->s.V = cfg->num_variables;
+  cudaDeviceGetAttribute(&w->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (const char *e = std::getenv("GBP_GENERAL_ONLY")) w->general_only = e[0] == '1';
   // default SDF: a single white pixel (empty environment)
   const uint8_t white = 255;
   if (cudaMalloc(&w->sdf_dev, 1) != cudaSuccess ||
@@ -1538,7 +1589,7 @@ void gbp_world_destroy(gbp_world_t *w) {
   free_edge_set(w, &w->edges[0]);
   free_edge_set(w, &w->edges[1]);
   void *ptrs[] = {s.prior_eta, s.prior_lam, s.pub[0], s.pub[1], s.pub_epoch[0], s.pub_epoch[1], s.bel_ext,
-                  s.mu_ext, s.cov, s.valid, s.m_dynL, s.m_dynR, s.m_obs, s.m_trk, s.dyn_c,
+                  s.mu_ext, s.cov, s.valid, s.cov_lazy, s.mode, s.gen_list, s.gen_count, s.m_dynL[0], s.m_dynL[1], s.m_dynR[0], s.m_dynR[1], s.m_obs, s.m_trk, s.dyn_c,
                   s.trk_record, s.trk_timeout, s.trk_seed, s.trk_last, s.trk_value, s.radius, s.t0, s.pos, s.antenna,
                   s.idle, s.finished, s.latest, s.iter_factor, s.gid, s.next_wp, s.coll_hits, w->coll_totals, s.wp_off, s.wp_xy, s.eoff,
                   s.nlow, w->t_nlow, w->t_result_dev, w->sdf_dev, w->t_cx,
@@ -1844,6 +1895,7 @@ int gbp_world_add_robots(gbp_world_t *w, int32_t n, const float *radii, const ui
   CK(cudaMemsetAsync(s.finished + N0, 0, size_t(n), st));
   CK(cudaMemsetAsync(s.latest + N0, 0, size_t(n), st));
   CK(cudaMemsetAsync(s.iter_factor + N0, 0, size_t(n) * sizeof(uint32_t), st));
+  CK(cudaMemsetAsync(s.mode + N0, 1, size_t(n), st));  // k_iterate hands a robot to k_iterate_axis once it qualifies
   CK(cudaMemsetAsync(s.nlow + N0, 0, size_t(n) * sizeof(int32_t), st));
   CK(cudaMemsetAsync(s.coll_hits + N0, 0, size_t(n) * sizeof(uint32_t), st));
   s.N = int32_t(N1);
@@ -2426,6 +2478,35 @@ int gbp_world_sdf_lookup(gbp_world_t *w, int32_t m, const double *xy, uint32_t *
   CK(cudaMemcpyAsync(value, dv, size_t(m) * 8, cudaMemcpyDeviceToHost, w->stream));
   CK(cudaStreamSynchronize(w->stream));
   cudaFree(dxy); cudaFree(dv); cudaFree(dpx); cudaFree(dpy);
+  return 0;
+}
+
+int gbp_world_set_iterate_path(gbp_world_t *w0, int32_t general_only) {
+  if (!w0) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  for (gbp_world *w : w0->grp->members) {
+    w->general_only = general_only != 0;
+    // k_iterate does not maintain Store::mode while it runs alone: every robot re-qualifies from scratch
+    if (w->s.Nloc > 0) {
+      CK(cudaSetDevice(w->device));
+      CK(cudaMemsetAsync(w->s.mode, 1, size_t(w->s.Nloc), w->stream));
+    }
+  }
+  return 0;
+}
+
+int gbp_world_read_iterate_path(gbp_world_t *w, int64_t *robots_axis, int64_t *robots_general) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (set_device(w)) return GBP_ERR_CUDA;
+  const int n = w->s.Nloc;
+  std::vector<uint8_t> h(size_t(n), 1);
+  if (n > 0) {
+    CK(cudaMemcpyAsync(h.data(), w->s.mode, size_t(n), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+  }
+  int64_t gen = 0;
+  for (uint8_t m : h) gen += m != 0;
+  if (robots_axis) *robots_axis = w->general_only ? 0 : n - gen;
+  if (robots_general) *robots_general = w->general_only ? n : gen;
   return 0;
 }
 

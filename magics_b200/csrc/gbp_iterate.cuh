@@ -53,9 +53,6 @@ constexpr size_t kIterSmemBytes = 0;
 #ifndef GBP_PREFETCH
 #define GBP_PREFETCH 1
 #endif
-#ifndef GBP_INT_ACC
-#define GBP_INT_ACC 1
-#endif
 #ifndef GBP_MIRROR_MASK
 #define GBP_MIRROR_MASK 1
 #endif
@@ -106,8 +103,11 @@ GBP_DEV void add_dyn_stored(const Store &s, const double *__restrict__ arr, int6
   }
 }
 // The stored Obstacle and Tracking messages (factored form, expanded on use).
-GBP_DEV void add_unary_stored(const Store &s, int64_t vi, double (&ae)[4], double (&al)[16]) {
+// Returns bit 0: the Obstacle message contributed (non-zero Jacobian or non-finite v0), bit 1: a Tracking
+// message is stored — either one couples the variable's x and y chains (k_iterate_axis must not run it).
+GBP_DEV unsigned add_unary_stored(const Store &s, int64_t vi, double (&ae)[4], double (&al)[16]) {
   double o[4], t[3];
+  unsigned contributed = 0u;
 #pragma unroll
   for (int k = 0; k < 4; ++k) o[k] = s.m_obs[s.at<4>(k, vi)];
 #pragma unroll
@@ -117,6 +117,7 @@ GBP_DEV void add_unary_stored(const Store &s, int64_t vi, double (&ae)[4], doubl
   if (!is_empty_marker(o[0]) && !((o[0] == 0.0) & (o[1] == 0.0) & (o[2] == 0.0) & isfinite(o[3]))) {
     const double J[4] = {o[0], o[1], o[2], o[2]};
     unary_add(J, o[3], s.lm_obs, ae, al);
+    contributed |= 1u;
   }
   if (!is_empty_marker(t[0])) {
 #pragma unroll
@@ -126,12 +127,32 @@ GBP_DEV void add_unary_stored(const Store &s, int64_t vi, double (&ae)[4], doubl
 #pragma unroll
       for (int l = 0; l < 2; ++l) al[k * 4 + l] = al[k * 4 + l] + g * t[l];
     }
+    contributed |= 2u;
   }
+  return contributed;
 }
-GBP_DEV void add_internal(const Store &s, int64_t vi, int i, double (&ae)[4], double (&al)[16]) {
-  add_dyn_stored(s, s.m_dynL, vi, ae, al);
-  add_dyn_stored(s, s.m_dynR, vi, ae, al);
-  add_unary_stored(s, vi, ae, al);
+GBP_DEV unsigned add_internal(const Store &s, int p, int64_t vi, double (&ae)[4], double (&al)[16]) {
+  add_dyn_stored(s, s.m_dynL[p], vi, ae, al);
+  add_dyn_stored(s, s.m_dynR[p], vi, ae, al);
+  return add_unary_stored(s, vi, ae, al);
+}
+
+// Store::cov_lazy resolved: VariableBelief.covariance_matrix = inv4 of the variable's current precision, which
+// k_iterate_axis took and found finite (belief_axis) but did not store.  Out of line: rare (a robot's first
+// launch after it left k_iterate_axis, FactorGraph::reset_variables).
+__device__ __noinline__ void materialise_cov(const Store &s, int p, int64_t r, int64_t vi) {
+  const double *src = s.latest[r] ? s.bel_ext : s.pub[p];
+  double lam[16], cov[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    lam[k] = src[s.at<kRec>(4 + k, vi)];
+    cov[k] = 0.0;
+  }
+  inv4(lam, cov);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s.cov[s.at<16>(k, vi)] = cov[k];
+  s.valid[vi] = 1;
+  s.cov_lazy[vi] = 0;
 }
 
 // Adds the stored mirror message m if there is one; returns whether there was.
@@ -147,6 +168,17 @@ GBP_DEV bool add_mirror(const Store &s, int64_t m, double (&ae)[4], double (&al)
   al[4] = al[4] + v[4];
   al[5] = al[5] + v[5];
   return true;
+}
+
+// The Dynamic messages are double buffered like the published records (an internal half reads [p] and
+// writes [1 - p], so that a robot k_iterate_axis gives up on is still untouched); a variable that does not
+// renew them — idle robot, Dynamic factors disabled — carries them over.
+GBP_DEV void copy_dyn_messages(const Store &s, int p, int64_t vi) {
+#pragma unroll 4
+  for (int k = 0; k < 20; ++k) {
+    s.m_dynL[1 - p][s.at<20>(k, vi)] = s.m_dynL[p][s.at<20>(k, vi)];
+    s.m_dynR[1 - p][s.at<20>(k, vi)] = s.m_dynR[p][s.at<20>(k, vi)];
+  }
 }
 
 GBP_DEV void load_prior(const Store &s, int64_t vi, double (&ae)[4], double (&al)[16]) {
@@ -366,18 +398,17 @@ GBP_DEV void ext_edge(const Store &s, const double *__restrict__ pubr, const Edg
 #else
 #define GBP_ITER_BOUNDS __launch_bounds__(kIterBlock, GBP_ITER_MIN_BLOCKS)
 #endif
+// One warp's robots (32/V of them, lane = rl * V + i) through one launch.  `requalify`: the robots come
+// from Store::gen_list; a robot whose state satisfies the invariant of Store::mode 0 again after this
+// launch is handed back to k_iterate_axis.
 template <bool EXT, bool INT>
-__global__ void GBP_ITER_BOUNDS
-    k_iterate(const __grid_constant__ Store s, const int p, const uint32_t epoch) {
+GBP_DEV void iterate_warp(const Store &s, const int p, const uint32_t epoch, const int64_t r, const bool live,
+                          const int rl, const int i, const unsigned lane, const bool requalify) {
   const int V = s.V;
-  const int rpw = 32 / V;
-  const unsigned lane = threadIdx.x & 31u;
-  const int64_t warp = (int64_t(blockIdx.x) * kIterBlock + threadIdx.x) >> 5;
-  const int rl = int(lane) / V;
-  const int i = int(lane) - rl * V;
-  const int64_t r = warp * rpw + rl;
-  const bool live = rl < rpw && r < s.Nloc;
   const int64_t vi = live ? r * V + i : 0;
+  if (live && s.cov_lazy[vi]) materialise_cov(s, p, r, vi);
+  // light: this lane's variable ends the launch in the decoupled regime (gbp_iterate_axis.cuh)
+  bool light = INT && s.en_dyn;
 
   const double *const pubr = s.pub[p];
   double *const pubw = s.pub[1 - p];
@@ -391,8 +422,8 @@ __global__ void GBP_ITER_BOUNDS
   int32_t nlow = 0;
   if (live) {
 #if GBP_PREFETCH
-    prefetch_planes<20, 20>(s, s.m_dynL, vi);
-    prefetch_planes<20, 20>(s, s.m_dynR, vi);
+    prefetch_planes<20, 20>(s, s.m_dynL[p], vi);
+    prefetch_planes<20, 20>(s, s.m_dynR[p], vi);
     prefetch_planes<4, 4>(s, s.m_obs, vi);
     prefetch_planes<3, 3>(s, s.m_trk, vi);
     prefetch_planes<4, 4>(s, s.prior_eta, vi);
@@ -442,7 +473,7 @@ __global__ void GBP_ITER_BOUNDS
     }
     int A_next = (e0 < e1) ? s.enbr[e0] : 0;
     for (int64_t e = e0;; ++e) {
-      if (e == eadd) add_internal(s, vi, i, ae, al);
+      if (e == eadd) add_internal(s, p, vi, ae, al);
       if (e >= e1) break;
       EdgeHead h;
       load_head(s, pubr, p, e, A_next, V, i, h);
@@ -457,6 +488,7 @@ __global__ void GBP_ITER_BOUNDS
       for (int k = 0; k < 16; ++k) s.cov[s.at<16>(k, vi)] = cov[k];
       s.valid[vi] = valid ? 1 : 0;
     }
+    light = light && taken && valid && mir_ne == 0ull && e1 - e0 <= 64;
     s.mu_ext[s.at<2>(0, vi)] = mu[0];
     s.mu_ext[s.at<2>(1, vi)] = mu[1];
     if (!INT || !do_int) {
@@ -495,9 +527,9 @@ __global__ void GBP_ITER_BOUNDS
 #pragma unroll
       for (int k = 0; k < 20; ++k) R[k] = pubr[s.at<kRec>(k, vi)];
 #pragma unroll
-      for (int k = 0; k < 20; ++k) toR[k] = s.m_dynR[s.at<20>(k, vi)];
+      for (int k = 0; k < 20; ++k) toR[k] = s.m_dynR[p][s.at<20>(k, vi)];
 #pragma unroll
-      for (int k = 0; k < 20; ++k) toL[k] = s.m_dynL[s.at<20>(k, vi)];
+      for (int k = 0; k < 20; ++k) toL[k] = s.m_dynL[p][s.at<20>(k, vi)];
       const bool hasR = !is_empty_marker(toR[0]), hasL = !is_empty_marker(toL[0]);
 #pragma unroll
       for (int k = 0; k < 20; ++k) {
@@ -514,22 +546,21 @@ __global__ void GBP_ITER_BOUNDS
     if (do_int) {
       // Inbox sum of the variable iteration that follows (variable.rs:263-271), in FactorId order:
       // prior, mirror messages of lower-id robots, dyn(i-1), dyn(i), obstacle, tracking, mirror
-      // messages of higher-id robots.  GBP_INT_ACC: the two Dynamic messages are added straight from
-      // the registers they were computed in instead of being read back after the store.
+      // messages of higher-id robots.  The two Dynamic messages are added straight from the registers
+      // they were computed in.
       double ae[4], al[16];
       const int64_t e0 = eo0;
       const int64_t e1 = (i >= 1) ? eo1 : e0;
       const int64_t elow = e0 + nlow;
       const int64_t eadd = elow < e1 ? elow : e1;
-#if GBP_INT_ACC
+      bool any_mir = false;
       load_prior(s, vi, ae, al);
       for (int64_t e = e0; e < eadd; ++e) {
 #if GBP_MIRROR_MASK
         if (EXT && do_ext && e - e0 < 64 && !((mir_ne >> (e - e0)) & 1ull)) continue;  // known Empty
 #endif
-        add_mirror(s, e * (V - 1) + (i - 1), ae, al);
+        any_mir |= add_mirror(s, e * (V - 1) + (i - 1), ae, al);
       }
-#endif
       if (s.en_dyn) {
         if (i >= 1) {  // Dynamic factor i-1 -> variable i (slot 1)
           double dcL[4];
@@ -539,17 +570,18 @@ __global__ void GBP_ITER_BOUNDS
           double ne[4], nl[16];
           if (dyn_message<1>(M, fromL_ne, toR, ne, nl)) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) s.m_dynL[s.at<20>(k, vi)] = ne[k];
+            for (int k = 0; k < 4; ++k) s.m_dynL[1 - p][s.at<20>(k, vi)] = ne[k];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) s.m_dynL[s.at<20>(4 + k, vi)] = nl[k];
-#if GBP_INT_ACC
+            for (int k = 0; k < 16; ++k) s.m_dynL[1 - p][s.at<20>(4 + k, vi)] = nl[k];
 #pragma unroll
             for (int k = 0; k < 4; ++k) ae[k] = ae[k] + ne[k];
 #pragma unroll
             for (int k = 0; k < 16; ++k) al[k] = al[k] + nl[k];
-#endif
+            light = light && (nl[1] == 0.0) & (nl[3] == 0.0) & (nl[4] == 0.0) & (nl[6] == 0.0) & (nl[9] == 0.0) &
+                             (nl[11] == 0.0) & (nl[12] == 0.0) & (nl[14] == 0.0);
           } else {
-            s.m_dynL[s.at<20>(0, vi)] = empty_marker();
+            s.m_dynL[1 - p][s.at<20>(0, vi)] = empty_marker();
+            light = false;
           }
         }  // variable 0 has no dyn(i-1): its slot holds the Empty marker for ever
         if (i <= V - 2) {  // Dynamic factor i -> variable i (slot 0)
@@ -560,26 +592,26 @@ __global__ void GBP_ITER_BOUNDS
           double ne[4], nl[16];
           if (dyn_message<0>(M, fromR_ne, toL, ne, nl)) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) s.m_dynR[s.at<20>(k, vi)] = ne[k];
+            for (int k = 0; k < 4; ++k) s.m_dynR[1 - p][s.at<20>(k, vi)] = ne[k];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) s.m_dynR[s.at<20>(4 + k, vi)] = nl[k];
-#if GBP_INT_ACC
+            for (int k = 0; k < 16; ++k) s.m_dynR[1 - p][s.at<20>(4 + k, vi)] = nl[k];
 #pragma unroll
             for (int k = 0; k < 4; ++k) ae[k] = ae[k] + ne[k];
 #pragma unroll
             for (int k = 0; k < 16; ++k) al[k] = al[k] + nl[k];
-#endif
+            light = light && (nl[1] == 0.0) & (nl[3] == 0.0) & (nl[4] == 0.0) & (nl[6] == 0.0) & (nl[9] == 0.0) &
+                             (nl[11] == 0.0) & (nl[12] == 0.0) & (nl[14] == 0.0);
           } else {
-            s.m_dynR[s.at<20>(0, vi)] = empty_marker();
+            s.m_dynR[1 - p][s.at<20>(0, vi)] = empty_marker();
+            light = false;
           }
         }  // likewise the last variable and dyn(i)
       }
-#if GBP_INT_ACC
       else {  // Dynamic factors disabled: whatever they sent while enabled is still in the inbox
-        add_dyn_stored(s, s.m_dynL, vi, ae, al);
-        add_dyn_stored(s, s.m_dynR, vi, ae, al);
+        add_dyn_stored(s, s.m_dynL[p], vi, ae, al);
+        add_dyn_stored(s, s.m_dynR[p], vi, ae, al);
+        copy_dyn_messages(s, p, vi);
       }
-#endif
       if (i >= 1 && i <= V - 2 && (s.en_obs || s.en_trk)) {
         // linearisation point = mean of the variable's last message (factor/mod.rs:336-349)
         double x[4], x0[4];
@@ -592,6 +624,7 @@ __global__ void GBP_ITER_BOUNDS
         // Tracking factors are skipped until iteration_count.factor >= 10
         // (factorgraph.rs:701); their inbox starts with the variable's belief
         if (s.en_trk && itf >= 10u) {
+          light = false;
           double xt[4];
           const bool has = own_ne || s.trk_seed[vi] != 0;  // emptied by reset_variables: linearise at zeros
 #pragma unroll
@@ -602,25 +635,13 @@ __global__ void GBP_ITER_BOUNDS
       itf += 1;
 
       // ---- belief update + new record (variable.rs:251-297)
-#if GBP_INT_ACC
-      add_unary_stored(s, vi, ae, al);
+      const unsigned unary = add_unary_stored(s, vi, ae, al);
       for (int64_t e = eadd; e < e1; ++e) {
 #if GBP_MIRROR_MASK
         if (EXT && do_ext && e - e0 < 64 && !((mir_ne >> (e - e0)) & 1ull)) continue;  // known Empty
 #endif
-        add_mirror(s, e * (V - 1) + (i - 1), ae, al);
+        any_mir |= add_mirror(s, e * (V - 1) + (i - 1), ae, al);
       }
-#else
-      load_prior(s, vi, ae, al);
-      for (int64_t e = e0;; ++e) {
-        if (e == eadd) add_internal(s, vi, i, ae, al);
-        if (e >= e1) break;
-#if GBP_MIRROR_MASK
-        if (EXT && do_ext && e - e0 < 64 && !((mir_ne >> (e - e0)) & 1ull)) continue;  // known Empty
-#endif
-        add_mirror(s, e * (V - 1) + (i - 1), ae, al);
-      }
-#endif
       double cov[16];
       bool valid = false;
       const bool taken = belief_moments(ae, al, mu, cov, valid);
@@ -629,6 +650,9 @@ __global__ void GBP_ITER_BOUNDS
         for (int k = 0; k < 16; ++k) s.cov[s.at<16>(k, vi)] = cov[k];
         s.valid[vi] = valid ? 1 : 0;
       }
+      light = light && taken && valid && unary == 0u && !any_mir && (al[1] == 0.0) & (al[3] == 0.0) & (al[4] == 0.0) &
+                           (al[6] == 0.0) & (al[9] == 0.0) & (al[11] == 0.0) & (al[12] == 0.0) & (al[14] == 0.0) &
+                           isfinite(ae[0]) & isfinite(ae[1]) & isfinite(ae[2]) & isfinite(ae[3]);
 #pragma unroll
       for (int k = 0; k < 4; ++k) pubw[s.at<kRec>(k, vi)] = ae[k];
 #pragma unroll
@@ -641,12 +665,46 @@ __global__ void GBP_ITER_BOUNDS
 #pragma unroll
       for (int k = 0; k < kRec; ++k) pubw[s.at<kRec>(k, vi)] = pubr[s.at<kRec>(k, vi)];
       s.pub_epoch[1 - p][vi] = s.pub_epoch[p][vi];
+      copy_dyn_messages(s, p, vi);
     }
   }
   if (live && i == 0) {
     s.iter_factor[r] = itf;
     if (do_int) s.latest[r] = 0;
     else if (do_ext) s.latest[r] = 1;
+  }
+  if (INT && requalify) {
+    // every variable of the robot must qualify; idle robots keep their mode
+    const unsigned all = ((V == 32) ? 0xffffffffu : ((1u << V) - 1u)) << (rl * V);
+    const unsigned votes = __ballot_sync(0xffffffffu, live && do_int && light);
+    // Two qualifying internal halves in a row: both buffers of the double-buffered records and messages
+    // then hold this robot's decoupled state (k_iterate_axis never touches the cross rows).
+    if (live && do_int && i == 0) s.mode[r] = (votes & all) == all ? (s.mode[r] == 2 ? 0 : 2) : 1;
+  }
+}
+
+// par >= 0: the robots of Store::gen_list (length gen_count[par]; the counter of the next launch is
+// cleared here) through a grid-stride loop; par < 0: every robot of the shard, no hand-back.
+template <bool EXT, bool INT>
+__global__ void GBP_ITER_BOUNDS
+    k_iterate(const __grid_constant__ Store s, const int p, const uint32_t epoch, const int par) {
+  const int V = s.V;
+  const int rpw = 32 / V;
+  const unsigned lane = threadIdx.x & 31u;
+  const int rl = int(lane) / V;
+  const int i = int(lane) - rl * V;
+  int64_t nrob = s.Nloc;
+  if (par >= 0) {
+    nrob = s.gen_count[par];
+    if (blockIdx.x == 0 && threadIdx.x == 0) s.gen_count[par ^ 1] = 0;
+  }
+  const int64_t nwarps = (nrob + rpw - 1) / rpw;
+  const int64_t wstride = (int64_t(gridDim.x) * kIterBlock) >> 5;
+  for (int64_t warp = (int64_t(blockIdx.x) * kIterBlock + threadIdx.x) >> 5; warp < nwarps; warp += wstride) {
+    const int64_t k = warp * rpw + rl;
+    const bool live = rl < rpw && k < nrob;
+    const int64_t r = live ? (par >= 0 ? int64_t(s.gen_list[k]) : k) : 0;
+    iterate_warp<EXT, INT>(s, p, epoch, r, live, rl, i, lane, par >= 0);
   }
 }
 

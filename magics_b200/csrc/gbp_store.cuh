@@ -66,8 +66,11 @@ struct Store {
   double *mu_ext;        // [2][NV]   position mean last delivered to external factors
   double *cov;           // [16][NV]  VariableBelief.covariance_matrix
   uint8_t *valid;        // [NV]      VariableBelief.valid
-  double *m_dynL;        // [20][NV]  message from Dynamic factor i-1 (eta4, Lambda16)
-  double *m_dynR;        // [20][NV]  message from Dynamic factor i
+  uint8_t *cov_lazy;     // [NV]      1: cov / valid are not stored — the covariance is inv4 of the variable's current
+                         //           precision (bel_ext if latest[r], else pub[p]) and valid is 1; set by k_iterate_axis,
+                         //           resolved by materialise_cov (gbp_iterate.cuh) and k_gather_beliefs
+  double *m_dynL[2];     // [20][NV]  message from Dynamic factor i-1 (eta4, Lambda16); double buffered with pub:
+  double *m_dynR[2];     // [20][NV]  message from Dynamic factor i         an internal half reads [p], writes [1-p]
   double *m_obs;         // [4][NV]   Obstacle message as (J0, J1, J2=J3, v0)
   double *m_trk;         // [3][NV]   Tracking message as (J0, J1, v0)
   double *dyn_c;         // [4][NV]   Dynamic factor i: delta_t (f32 widened) and q11, q12, q22 (gbp_math.cuh dyn_q)
@@ -87,6 +90,11 @@ struct Store {
   uint8_t *finished;      // [cap]     FinishedPath
   uint8_t *latest;        // [cap]     0: pub[p] holds the current belief, 1: bel_ext
   uint32_t *iter_factor;  // [cap]     FactorGraph.iteration_count.factor
+  uint8_t *mode;          // [cap]     0: the robot's x and y chains are decoupled, k_iterate_axis iterates it;
+                          //           1: k_iterate does; 2: k_iterate does and found it decoupled once
+                          //           (invariant of mode 0 and the hand-back rule: gbp_iterate_axis.cuh)
+  int32_t *gen_list;      // [cap]     robots k_iterate has to run in the current launch (filled by k_iterate_axis)
+  int32_t *gen_count;     // [2]       length of gen_list, indexed by launch parity
   int32_t *gid;           // [cap]     global robot id of the slot (== slot on one GPU)
   int32_t *next_wp;       // [cap]
   int32_t *wp_off;        // [cap+1]

@@ -410,7 +410,18 @@ class World:
         self._call("gbp_world_node_counts", _p(out, C.c_int64))
         return out
 
-    PROFILE_KINDS = ("iterate_int", "iterate_ext", "iterate_ext_int", "topology", "priors", "halo")
+    def set_iterate_path(self, general_only: bool):
+        """general_only: every robot through k_iterate (A/B tests); default: k_iterate_axis for the robots
+        whose x and y chains are decoupled, decided on the device per launch."""
+        self._call("gbp_world_set_iterate_path", C.c_int32(int(bool(general_only))))
+
+    def read_iterate_path(self):
+        """(robots currently iterated by k_iterate_axis, robots iterated by k_iterate) on this shard."""
+        ax, gen = C.c_int64(0), C.c_int64(0)
+        self._call("gbp_world_read_iterate_path", C.byref(ax), C.byref(gen))
+        return int(ax.value), int(gen.value)
+
+    PROFILE_KINDS = ("iterate_int", "iterate_ext", "iterate_ext_int", "topology", "priors", "halo", "iterate_general")
 
     def set_profiling(self, on: bool):
         self._call("gbp_world_set_profiling", C.c_int32(int(on)))

@@ -2,6 +2,7 @@
 // per-node arithmetic of the CUDA engine can be checked against the oracle without a GPU.
 #define GBP_HOST_MATH_TEST 1
 #include "../../magics_b200/csrc/gbp_math.cuh"
+#include "../../magics_b200/csrc/gbp_math_axis.cuh"
 
 extern "C" {
 int hm_inv4(const double *m, double *out) {
@@ -54,5 +55,33 @@ int hm_interrobot_message(int a_first, const double *mu_a, const double *mu_b, i
 int hm_interrobot_skip(int a_first, const double *mu_a, const double *mu_b, double dsafe) {
   double ma[2] = {mu_a[0], mu_a[1]}, mb[2] = {mu_b[0], mu_b[1]};
   return gbp::interrobot_skip(a_first != 0, ma, mb, dsafe) ? 1 : 0;
+}
+
+// ---- gbp_math_axis.cuh: one axis of the decoupled regime (block = (m[a][a], m[a][a+2], m[a+2][a], m[a+2][a+2])) ----
+int hm_inv_axis(int a, const double *P, const double *Q, double *O) {
+  double p[4], q[4], o[4] = {0, 0, 0, 0};
+  for (int k = 0; k < 4; ++k) p[k] = P[k], q[k] = Q[k];
+  const bool ok = gbp::inv_axis(a, p, q, o);
+  for (int k = 0; k < 4; ++k) O[k] = o[k];
+  return ok ? 1 : 0;
+}
+int hm_belief_axis(int a, const double *e, const double *P, const double *Q, double *mu) {
+  double ee[2] = {e[0], e[1]}, p[4], q[4], m[2] = {mu[0], mu[1]};
+  for (int k = 0; k < 4; ++k) p[k] = P[k], q[k] = Q[k];
+  const bool ok = gbp::belief_axis(a, ee, p, q, m);
+  mu[0] = m[0];
+  mu[1] = m[1];
+  return ok ? 1 : 0;
+}
+int hm_dyn_message_axis(int keep, int a, double dt, double qs, int other_nonempty, const double *oe, const double *oP,
+                        const double *oQ, double *eta, double *lam) {
+  const gbp::DynM M = gbp::dyn_potential(dt, qs);
+  double e[2] = {oe[0], oe[1]}, p[4], q[4], re[2] = {0, 0}, rl[4] = {0, 0, 0, 0};
+  for (int k = 0; k < 4; ++k) p[k] = oP[k], q[k] = oQ[k];
+  const bool ok = keep ? gbp::dyn_message_axis<1>(a, M, other_nonempty != 0, e, p, q, re, rl)
+                       : gbp::dyn_message_axis<0>(a, M, other_nonempty != 0, e, p, q, re, rl);
+  for (int k = 0; k < 2; ++k) eta[k] = re[k];
+  for (int k = 0; k < 4; ++k) lam[k] = rl[k];
+  return ok ? 1 : 0;
 }
 }

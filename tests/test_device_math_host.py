@@ -25,7 +25,8 @@ def _build(tag: str, flags: list[str]) -> C.CDLL:
     os.makedirs(out_dir, exist_ok=True)
     out = os.path.join(out_dir, f"libhost_math_{tag}.so")
     deps = [SRC, os.path.join(HERE, "host_math", "host_math_shim.h"),
-            os.path.join(HERE, "..", "magics_b200", "csrc", "gbp_math.cuh")]
+            os.path.join(HERE, "..", "magics_b200", "csrc", "gbp_math.cuh"),
+            os.path.join(HERE, "..", "magics_b200", "csrc", "gbp_math_axis.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(out) < os.path.getmtime(d) for d in deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
                         "-I", os.path.join(HERE, "host_math")] + flags + ["-o", out, SRC], check=True)
@@ -251,3 +252,123 @@ def test_interrobot_message_matches_the_linearised_factor(libs):
         assert np.max(np.abs(lam4.reshape(2, 2) - rl[:2, :2])) <= 1e-9 * max(1.0, np.abs(rl).max())
         assert np.max(np.abs(rl[2:, :])) <= 1e-9 * max(1.0, np.abs(rl).max())  # the rest of the message is zero
     assert n_msg > 200 and n_skip > 200
+
+
+# ---- gbp_math_axis.cuh: the two-lanes-per-variable arithmetic of the decoupled regime, bit for bit against
+# ---- the general 4x4 routines of gbp_math.cuh (which the tests above tie to the oracle) -------------------------
+AX = [np.array([0, 2, 8, 10]), np.array([5, 7, 13, 15])]   # row-major 4x4 indices of each axis' block
+AXV = [np.array([0, 2]), np.array([1, 3])]                  # vector components of each axis
+
+
+def _bits_equal(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return bool(np.all((a.view(np.uint64) == b.view(np.uint64)) | (np.isnan(a) & np.isnan(b))))
+
+
+def _decoupled(rng, kind):
+    """A 4x4 with exact zeros wherever row + column is odd."""
+    vals = rng.standard_normal((4, 4)) * 10.0 ** rng.integers(-6, 12, size=(4, 4))
+    m = np.where((np.add.outer(np.arange(4), np.arange(4)) % 2) == 0, vals, 0.0)
+    if kind == 1:
+        m = (m + m.T) / 2 + 2 * np.diag(np.abs(np.diag(m)))
+    elif kind == 2:
+        m[0, 0] = 1e30
+        m[1, 1] = 1e30
+    elif kind == 3 and rng.random() < 0.5:
+        m[2, :] = m[0, :]  # singular x block
+    return m
+
+
+def test_inv_axis_has_the_bits_of_inv4(libs):
+    dev, _, _ = libs
+    rng = np.random.default_rng(21)
+    taken = 0
+    for t in range(20000):
+        m = _decoupled(rng, t % 4).reshape(16)
+        if t % 97 == 0:
+            m[rng.choice(np.concatenate(AX))] = rng.choice([np.inf, -np.inf, np.nan])
+        r0, o0 = _inv(dev, "hm_inv4", m)
+        det_fin = True
+        outs = []
+        for a in (0, 1):
+            P_, Q_ = m[AX[a]].copy(), m[AX[1 - a]].copy()
+            O = np.zeros(4)
+            ok = dev.hm_inv_axis(a, P_.ctypes.data_as(P), Q_.ctypes.data_as(P), O.ctypes.data_as(P))
+            outs.append((ok, O))
+        assert outs[0][0] == outs[1][0]
+        if outs[0][0]:
+            # the lane pair took the update: inv4 must have taken it too, with the same bits in both blocks
+            assert r0 == 1
+            for a in (0, 1):
+                assert _bits_equal(outs[a][1], o0[AX[a]]), (m, outs[a][1], o0[AX[a]])
+            taken += 1
+        else:
+            # refused: singular, or a non-finite determinant (inv4's general path)
+            assert r0 == 0 or not np.all(np.isfinite(m))
+    assert taken > 10000
+
+
+def test_belief_axis_has_the_bits_of_belief_moments(libs):
+    dev, _, _ = libs
+    rng = np.random.default_rng(22)
+    taken = 0
+    for t in range(5000):
+        lam = _decoupled(rng, 1 if t % 3 else 2).reshape(16)
+        if t % 11 == 0:
+            lam *= 1e-9  # nothing above the 1e-6 threshold of variable.rs:276
+        eta = rng.standard_normal(4) * 10.0 ** rng.integers(-3, 8, size=4)
+        mu0 = rng.standard_normal(4)
+        mu, cov, valid = mu0.copy(), np.zeros(16), C.c_int(0)
+        tk = dev.hm_belief_moments(eta.ctypes.data_as(P), lam.copy().ctypes.data_as(P), mu.ctypes.data_as(P),
+                                   cov.ctypes.data_as(P), C.byref(valid))
+        oks = []
+        for a in (0, 1):
+            e2, m2 = eta[AXV[a]].copy(), mu0[AXV[a]].copy()
+            P_, Q_ = lam[AX[a]].copy(), lam[AX[1 - a]].copy()
+            ok = dev.hm_belief_axis(a, e2.ctypes.data_as(P), P_.ctypes.data_as(P), Q_.ctypes.data_as(P), m2.ctypes.data_as(P))
+            oks.append(ok)
+            if ok:
+                assert tk == 1 and valid.value == 1
+                assert _bits_equal(m2, mu[AXV[a]]), (lam, eta, m2, mu)
+        if tk == 1 and valid.value == 1:
+            assert oks == [1, 1]
+            taken += 1
+        else:
+            assert oks == [0, 0]
+    assert taken > 3000
+
+
+def test_dyn_message_axis_has_the_bits_of_dyn_message(libs):
+    dev, _, _ = libs
+    rng = np.random.default_rng(23)
+    n_ok = 0
+    for t in range(6000):
+        dt = float(np.float32(rng.uniform(0.02, 2.5)))
+        qs = 1.0 / float(rng.choice([0.1, 1.0, 0.5])) ** 2
+        keep, nonempty = int(rng.integers(0, 2)), int(t % 5 != 0)
+        ol = _decoupled(rng, 1 if t % 7 else 0).reshape(16)
+        oe = rng.standard_normal(4) * 10.0 ** rng.integers(-3, 6, size=4)
+        other = np.concatenate([oe, ol])
+        eta, lam = np.zeros(4), np.zeros(16)
+        ok = dev.hm_dyn_message(keep, C.c_double(dt), C.c_double(qs), nonempty, other.ctypes.data_as(P),
+                                eta.ctypes.data_as(P), lam.ctypes.data_as(P))
+        oks = []
+        for a in (0, 1):
+            e2, P_, Q_ = oe[AXV[a]].copy(), ol[AX[a]].copy(), ol[AX[1 - a]].copy()
+            re, rl = np.zeros(2), np.zeros(4)
+            oka = dev.hm_dyn_message_axis(keep, a, C.c_double(dt), C.c_double(qs), nonempty, e2.ctypes.data_as(P),
+                                          P_.ctypes.data_as(P), Q_.ctypes.data_as(P), re.ctypes.data_as(P),
+                                          rl.ctypes.data_as(P))
+            oks.append(oka)
+            if oka:
+                assert ok == 1
+                assert _bits_equal(re, eta[AXV[a]]), (t, a, re, eta)
+                assert _bits_equal(rl, lam[AX[a]]), (t, a, rl, lam)
+        if ok and oks == [1, 1]:
+            # the entries outside the two blocks are exact zeros in the general result
+            rest = np.setdiff1d(np.arange(16), np.concatenate(AX))
+            assert np.all(lam[rest] == 0.0)
+            n_ok += 1
+        else:
+            assert oks[0] == oks[1] or ok == 0
+    assert n_ok > 4000
