@@ -191,9 +191,15 @@ def main():
         # sample of the same workload: W warm-up ticks, then exactly K timed ticks.
         if rank != 0:
             return
+        from magics_b200 import scenarios
+        from oracle import oracle as _oracle
         from oracle.oracle import OracleWorld, schedule
 
+        # this arm must not map the product library: the generators take their variable timesteps from the
+        # oracle's restatement of utils.rs:95-133 instead of the engine's gbp_variable_timesteps
+        scenarios.get_variable_timesteps = _oracle.variable_timesteps
         sw, _ = build_workload(args.workload, args.cpu_robots)
+        assert "libgbp_b200" not in open("/proc/self/maps").read(), "reference arm loaded the product library"
         o = OracleWorld(sw.cfg, threads=cores)
         sw.add_to(o)
         oi, oe = schedule(sw.cfg.schedule_kind, sw.cfg.iterations_internal, sw.cfg.iterations_external)
@@ -232,7 +238,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from magics_b200 import gbp_schedule, pinned_empty
-    from magics_b200.dist import broadcast_comm_id, max_over_ranks, sum_over_ranks
+    from magics_b200.dist import broadcast_comm_id, max_over_ranks, sum_over_ranks, sum_u64_over_ranks
+    from magics_b200.sharded import state_hash
 
     # One swarm, spatially partitioned: rank q owns a contiguous id range (a slab of lattice rows /
     # an arc of rings) and exchanges the published records of its border robots with its
@@ -309,7 +316,16 @@ def main():
     e2e_ms = max(ms_e2e, wall_e2e)
     e2e_ms = max_over_ranks(e2e_ms) if world > 1 else e2e_ms
     e2e_value = n_total * substeps * args.steps / (e2e_ms * 1e-3)
-    edges_local = float(g.read_connections()[0][-1])
+    # after the timed ticks: digests of every variable mean and of the whole InterRobot edge set with its
+    # robot_numbers — identical for N = 1, 2, 4, 8 by design (the sharded run reproduces the single-GPU bits)
+    conn = g.read_connections()
+    g.read_means_into(means[0])
+    h_means, h_conn = state_hash(g.first_global_id, means[0], *conn)
+    if world > 1:
+        h_means, h_conn = sum_u64_over_ranks(h_means), sum_u64_over_ranks(h_conn)
+    rn_max_local = float(conn[2].max()) if conn[2].size else -1.0
+    rn_max = max_over_ranks(rn_max_local) if world > 1 else rn_max_local
+    edges_local = float(conn[0][-1])
     edges_total = sum_over_ranks(edges_local) if world > 1 else edges_local
     ghosts_total = sum_over_ranks(g.num_ghosts) if world > 1 else 0.0
     h2d_total = sum_over_ranks(ant.nbytes + wpi.nbytes) if world > 1 else float(ant.nbytes + wpi.nbytes)
@@ -362,6 +378,11 @@ def main():
                     "what": "per step: set_comms + set_waypoint_index (pinned host -> device), gbp_world_step, "
                             "all variable means device -> pinned host (copy of tick t overlaps tick t+1, consumed one tick "
                             "later; the last copy is inside the timed region); max(CUDA events, wall clock), max over ranks"},
+            "state_hash": {"means": f"{h_means:016x}", "connectivity": f"{h_conn:016x}", "edges": int(edges_total),
+                           "last_robot_number": int(rn_max), "ticks": args.warmup + 2 * args.steps,
+                           "what": "sum mod 2^64 over all robots of a 64-bit digest of every variable mean "
+                                   "(keyed by global robot id) / of every directed InterRobot pair with its "
+                                   "robot_number, after all ticks of this run; the same for every N"},
             "roofline": roof, "cpu_baseline": cpu, "profile_ms": prof,
         }
         emit(line)

@@ -230,6 +230,15 @@ __global__ void k_init_vars(Store s, int64_t first, int64_t count, const double 
   s.dyn_c[s.at<4>(3, vi)] = q22;
 }
 
+// Store::dyn_tab: the Dynamic-factor constants of one robot, by variable index (valid for every robot while
+// all of them share one radius, i.e. one delta_t per factor).
+__global__ void k_dyn_table(Store s, int64_t robot, double *tab) {
+  const int i = threadIdx.x + blockIdx.x * blockDim.x;
+  if (i >= s.V) return;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) tab[4 * i + k] = s.dyn_c[s.at<4>(k, robot * s.V + i)];
+}
+
 // VariableNode::change_prior + FactorGraph::change_prior_of_variable for variable
 // `var` of robot r with new mean nm (variable.rs:203-230, factorgraph.rs:494-528):
 // every factor that holds a message from this variable now holds
@@ -273,40 +282,48 @@ __device__ void change_prior_dev(const Store &s, int p, uint32_t epoch, int64_t 
 // hold the same `nm`, computed from reads that happened before the __syncwarp below.
 __device__ void change_prior_warp(const Store &s, int p, uint32_t epoch, int64_t r, int var, const double (&nm)[4],
                                   unsigned lane) {
+  // Every store below lands in a 32-byte sector of which it fills 8 bytes (a read-modify-write in DRAM), so
+  // nothing is written that already holds the value: the (eta, Lambda) rows move only when the current belief
+  // lives in bel_ext, bel_ext is left alone while nothing reads it (latest == 0: every reader takes
+  // `latest ? bel_ext : pub[p]`), an Empty marker is not stored over an Empty marker, and mu_frozen is
+  // only meaningful while the edge's frozen bit is set (otherwise A's factor holds mu_ext).
   const int64_t vi = r * s.V + var;
-  const double *src = s.latest[r] ? s.bel_ext : s.pub[p];
+  const bool latest = s.latest[r] != 0;
   double keep = 0.0;
-  if (lane < 20) keep = src[s.at<gbp::kRec>(lane, vi)];
+  if (latest && lane < 20) keep = s.bel_ext[s.at<gbp::kRec>(lane, vi)];
   const double pl = s.prior_lam[vi];
+  double mark = 0.0;
+  if (lane == 25) mark = s.m_dynL[p][s.at<20>(0, vi)];
+  else if (lane == 26) mark = s.m_dynR[p][s.at<20>(0, vi)];
+  else if (lane == 27) mark = s.m_obs[s.at<4>(0, vi)];
+  else if (lane == 28) mark = s.m_trk[s.at<3>(0, vi)];
   __syncwarp();
   if (lane < 20) {
-    s.pub[p][s.at<gbp::kRec>(lane, vi)] = keep;
-    s.bel_ext[s.at<gbp::kRec>(lane, vi)] = keep;
+    if (latest) s.pub[p][s.at<gbp::kRec>(lane, vi)] = keep;
   } else if (lane < 24) {
     const int k = int(lane) - 20;
     s.pub[p][s.at<gbp::kRec>(20 + k, vi)] = nm[k];
-    s.bel_ext[s.at<gbp::kRec>(20 + k, vi)] = nm[k];
+    if (latest) s.bel_ext[s.at<gbp::kRec>(20 + k, vi)] = nm[k];
     s.prior_eta[s.at<4>(k, vi)] = pl * nm[k];
   } else if (lane == 24) {
     s.pub_epoch[p][vi] = epoch;
     s.mu_ext[s.at<2>(0, vi)] = nm[0];
     s.mu_ext[s.at<2>(1, vi)] = nm[1];
-  } else if (lane == 25) {
-    s.m_dynL[p][s.at<20>(0, vi)] = gbp::empty_marker();
-  } else if (lane == 26) {
-    s.m_dynR[p][s.at<20>(0, vi)] = gbp::empty_marker();
-  } else if (lane == 27) {
-    s.m_obs[s.at<4>(0, vi)] = gbp::empty_marker();
-  } else if (lane == 28) {
-    s.m_trk[s.at<3>(0, vi)] = gbp::empty_marker();
+  } else if (lane <= 28 && !gbp::is_empty_marker(mark)) {
+    if (lane == 25) s.m_dynL[p][s.at<20>(0, vi)] = gbp::empty_marker();
+    else if (lane == 26) s.m_dynR[p][s.at<20>(0, vi)] = gbp::empty_marker();
+    else if (lane == 27) s.m_obs[s.at<4>(0, vi)] = gbp::empty_marker();
+    else s.m_trk[s.at<3>(0, vi)] = gbp::empty_marker();
   }
   if (var >= 1 && s.eoff)
     for (int64_t e = s.eoff[r] + lane; e < s.eoff[r + 1]; e += 32) {
       const int64_t m = e * (s.V - 1) + (var - 1);
-      s.mir[m] = gbp::empty_marker();
+      if (!gbp::is_empty_marker(s.mir[m])) s.mir[m] = gbp::empty_marker();
       // external factors receive the new mean whatever the antenna state (robot.rs:2272-2282)
-      s.mu_frozen[m] = nm[0];
-      s.mu_frozen[s.EV + m] = nm[1];
+      if (s.e_frozen[e] & 1) {
+        s.mu_frozen[m] = nm[0];
+        s.mu_frozen[s.EV + m] = nm[1];
+      }
     }
 }
 
@@ -627,6 +644,9 @@ struct gbp_world {
   bool smem_opted_in[4] = {false, false, false, false};  // k_iterate<EXT,INT> dynamic shared memory opt-in
   bool axis_opted_in[4] = {false, false, false, false};  // k_iterate_axis<EXT,INT> likewise
   bool general_only = false;  // gbp_world_set_iterate_path: every robot through k_iterate
+  double *dyn_tab_dev = nullptr;  // Store::dyn_tab while every robot added so far has the same t0 (radius)
+  bool t0_seen = false, t0_uniform = true;
+  float t0_first = 0.0f;
   int sm_count = 148;
   int par = 0;                // launch parity: which Store::gen_count the current launch appends to
   unsigned long long *coll_totals = nullptr;              // [0] Hit events so far, [1] pairs colliding now
@@ -684,6 +704,11 @@ void refresh_scalars(gbp_world *w) {
   s.world_w = c.world_width;
   s.world_h = c.world_height;
   s.jac_delta = (c.world_width / double(uint32_t(s.sdf_w)) + c.world_height / double(uint32_t(s.sdf_h))) / 2.0;
+  // ObstacleFactor::measure (obstacle.rs:141-160): offsets and scales are functions of the world and image size only
+  s.sdf_xo = s.world_w / 2.0;
+  s.sdf_yo = s.world_h / 2.0;
+  s.sdf_xs = double(uint32_t(s.sdf_w)) / s.world_w;
+  s.sdf_ys = double(uint32_t(s.sdf_h)) / s.world_h;
 }
 
 cudaEvent_t take_event(gbp_world *w) {
@@ -1588,6 +1613,7 @@ void gbp_world_destroy(gbp_world_t *w) {
   Store &s = w->s;
   free_edge_set(w, &w->edges[0]);
   free_edge_set(w, &w->edges[1]);
+  cudaFree(w->dyn_tab_dev);
   void *ptrs[] = {s.prior_eta, s.prior_lam, s.pub[0], s.pub[1], s.pub_epoch[0], s.pub_epoch[1], s.bel_ext,
                   s.mu_ext, s.cov, s.valid, s.cov_lazy, s.mode, s.gen_list, s.gen_count, s.m_dynL[0], s.m_dynL[1], s.m_dynR[0], s.m_dynR[1], s.m_obs, s.m_trk, s.dyn_c,
                   s.trk_record, s.trk_timeout, s.trk_seed, s.trk_last, s.trk_value, s.radius, s.t0, s.pos, s.antenna,
@@ -1947,6 +1973,23 @@ int gbp_world_add_robots(gbp_world_t *w, int32_t n, const float *radii, const ui
   k_init_vars<<<blocks_for(nv, 256), 256, 0, st>>>(s, used, nv, d_mu);
   CK(cudaGetLastError());
   w->launches += 1;
+  // one delta_t per Dynamic factor for the whole world? (t0 = radius / 2 / target_speed, robot.rs:1225)
+  for (int r = 0; r < n && w->t0_uniform; ++r) {
+    if (!w->t0_seen) {
+      w->t0_first = t0[r];
+      w->t0_seen = true;
+    }
+    w->t0_uniform = std::memcmp(&t0[r], &w->t0_first, sizeof(float)) == 0;
+  }
+  if (!w->t0_uniform) {
+    s.dyn_tab = nullptr;
+  } else if (!s.dyn_tab) {
+    if (!w->dyn_tab_dev) CK(dalloc(w->dyn_tab_dev, size_t(4) * size_t(V)));
+    k_dyn_table<<<blocks_for(V, 64), 64, 0, st>>>(s, N0, w->dyn_tab_dev);
+    CK(cudaGetLastError());
+    w->launches += 1;
+    s.dyn_tab = w->dyn_tab_dev;
+  }
   CK(cudaStreamSynchronize(st));  // staging vectors go out of scope
   cudaFree(d_mu);
   return 0;

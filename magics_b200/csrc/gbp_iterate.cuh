@@ -71,9 +71,10 @@ GBP_DEV double norm2(double x, double y) { return sqrt((0.0 + x * x) + y * y); }
 // ObstacleFactor::measure (factor/obstacle.rs:141-188).
 GBP_DEV double sdf_measure(const Store &s, double x_pos, double y_pos, uint32_t *opx = nullptr,
                            uint32_t *opy = nullptr) {
-  const double x_offset = s.world_w / 2.0, y_offset = s.world_h / 2.0;
-  const double x_scale = double(uint32_t(s.sdf_w)) / s.world_w;
-  const double y_scale = double(uint32_t(s.sdf_h)) / s.world_h;
+  // offsets world / 2.0 and scales f64::from(image dimension) / world, evaluated once on the host
+  // (refresh_scalars: one IEEE division each, the same bits as evaluating them here per call)
+  const double x_offset = s.sdf_xo, y_offset = s.sdf_yo;
+  const double x_scale = s.sdf_xs, y_scale = s.sdf_ys;
   const uint32_t xp = sat_u32((x_pos + x_offset) * x_scale);
   const uint32_t yp = sat_u32((-y_pos + y_offset) * y_scale);
   if (opx) *opx = xp;

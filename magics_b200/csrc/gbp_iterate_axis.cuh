@@ -37,10 +37,18 @@
 namespace gbp {
 
 #ifndef GBP_AXIS_MAXREG
-#define GBP_AXIS_MAXREG 80
+#define GBP_AXIS_MAXREG 96  // 5 warps per scheduler either way from 80 to 96 registers (16384 / (32 * 96) = 5.3)
 #endif
 
 static_assert(GBP_TILED == 1, "k_iterate_axis addresses the tiled store");
+
+// Edge heads (neighbour slot, birth epoch, frozen bit, safety distance) a robot's lanes stage in shared
+// memory for one another; a robot with more neighbours than this goes to the general kernel.
+constexpr int kAxisEdges = 32;
+#ifndef GBP_AXIS_BATCH
+#define GBP_AXIS_BATCH 2  // edges whose neighbour loads a lane has in flight at once (4: spills, 10 % slower)
+#endif
+constexpr int kAxisBatch = GBP_AXIS_BATCH;
 
 struct AxisGeom {
   int rpc;      // robots per CTA
@@ -58,11 +66,18 @@ inline AxisGeom axis_geom(int V) {
   }
   int rpc = 16 / g;
   while (2 * V * rpc < 128) rpc *= 2;
-  if (2 * V * rpc > 1024) rpc = 512 / V > 0 ? 512 / V : 1;  // V > 32: whole warps given up
+  // at most 512 threads (96 registers each): odd V gives up the 128-byte alignment of a warp's variable slots
+  if (2 * V * rpc > 512) rpc = 256 / V > 0 ? 256 / V : 1;
+#ifdef GBP_AXIS_RPC
+  rpc = GBP_AXIS_RPC;  // tuning builds
+#endif
   AxisGeom q;
   q.rpc = rpc;
   q.threads = (2 * V * rpc + 31) / 32 * 32;
-  q.smem = size_t(12) * q.threads * sizeof(double) + size_t(q.threads + 2 * rpc) * sizeof(int);
+  // doubles: xr, xl [6][T], Dynamic-factor constants [4][V], staged safety distances; then ints: xne [T],
+  // xbail, xflip [rpc], staged neighbour slots and birth epochs; then bytes: staged frozen bits
+  q.smem = (size_t(12) * q.threads + size_t(4) * V + size_t(rpc) * kAxisEdges) * sizeof(double) +
+           (size_t(q.threads) + 2 * size_t(rpc) + 2 * size_t(rpc) * kAxisEdges) * sizeof(int) + size_t(rpc) * kAxisEdges;
   return q;
 }
 
@@ -93,6 +108,13 @@ GBP_DEV void st_axis(double *__restrict__ arr, AxisRows q, const double (&e)[2],
   arr[q.m + 10 * kTile] = L[3];
 }
 
+// The loads of a launch come in three dependent waves instead of one per use (the kernel is bound by
+// load latency, not by bytes: profiles/README.md r02a):
+//   1. everything addressed by (robot, variable) alone — flags, edge range, prior, record, stored Dynamic
+//      messages, last delivered mean — issued back to back for every live lane, used or not;
+//   2. the robot's edge heads, one edge per lane, into shared memory (one __syncthreads);
+//   3. per lane, for kAxisBatch of its edges at once, what hangs off the neighbour slot: radio / idle
+//      bits, the neighbour variable's position mean and record epoch.
 template <bool EXT, bool INT>
 __global__ void __maxnreg__(GBP_AXIS_MAXREG)
     k_iterate_axis(const __grid_constant__ Store s, const int p, const uint32_t epoch, const int rpc, const int par) {
@@ -103,137 +125,190 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
   const int64_t r = int64_t(blockIdx.x) * rpc + rl;
   const bool live = rl < rpc && r < s.Nloc;
   const int64_t vi = live ? r * V + i : 0;
-  double *const xr = sh;          // [6][T] variable -> Dynamic factor i   (its right-hand factor)
-  double *const xl = sh + 6 * T;  // [6][T] variable -> Dynamic factor i-1 (its left-hand factor)
-  int *const xne = reinterpret_cast<int *>(sh + 12 * T);  // [T] the variable has sent a message at all
-  int *const xbail = xne + T;                             // [rpc] some lane of the robot needs the general kernel
-  int *const xflip = xbail + rpc;                         // [rpc] some e_frozen bit of the robot has to change
+  double *const xr = sh;                             // [6][T] variable -> Dynamic factor i   (its right-hand factor)
+  double *const xl = sh + 6 * T;                     // [6][T] variable -> Dynamic factor i-1 (its left-hand factor)
+  double *const dtab = sh + 12 * T;                  // [V][4] Store::dyn_tab
+  double *const hd_dsafe = dtab + 4 * V;             // [rpc][kAxisEdges]
+  int *const xne = reinterpret_cast<int *>(hd_dsafe + rpc * kAxisEdges);  // [T] the variable has sent a message at all
+  int *const xbail = xne + T;                        // [rpc] some lane of the robot needs the general kernel
+  int *const xflip = xbail + rpc;                    // [rpc] some e_frozen bit of the robot has to change
+  int *const hd_nbr = xflip + rpc;                   // [rpc][kAxisEdges]
+  uint32_t *const hd_birth = reinterpret_cast<uint32_t *>(hd_nbr + rpc * kAxisEdges);
+  uint8_t *const hd_frozen = reinterpret_cast<uint8_t *>(hd_birth + rpc * kAxisEdges);
   if (t < 2 * rpc) xbail[t] = 0;
-  __syncthreads();
 
   const double *const pubr = s.pub[p];
   double *const pubw = s.pub[1 - p];
   const AxisRows qp = axis_rows<kRec>(s, a, vi), qm = axis_rows<20>(s, a, vi);
 
-  // ---- the robot's flags, this lane's prior and running mean ------------------------------------
-  bool was_general = false, idle = true, ant = false;
+  // ---- wave 1 ---------------------------------------------------------------------------------
+  bool was_general = false, idle = true, ant = false, latest = false;
   uint32_t itf = 0u;
   int64_t eo0 = 0, eo1 = 0;
   int32_t nlow = 0;
   bool own_ne = false;
   double pe[2] = {0.0, 0.0}, pl = 0.0, mu[2] = {0.0, 0.0}, pos = 0.0, vel = 0.0;
+  double mu_sent[2] = {0.0, 0.0};
+  double eRec[2] = {0.0, 0.0}, LRec[4] = {0.0, 0.0, 0.0, 0.0};
+  double eL[2] = {0.0, 0.0}, LL[4] = {0.0, 0.0, 0.0, 0.0}, eR[2] = {0.0, 0.0}, LR[4] = {0.0, 0.0, 0.0, 0.0};
+  double markL = 0.0, markR = 0.0;  // row 0 of the stored Dynamic messages: the Empty marker sits there
   if (live) {
+    eo0 = s.eoff[r];
+    eo1 = s.eoff[r + 1];
     was_general = s.mode[r] != 0;
     idle = s.idle[r] != 0;
     ant = s.antenna[r] != 0;
-    const bool latest = s.latest[r] != 0;
+    latest = s.latest[r] != 0;
     itf = s.iter_factor[r];
-    eo0 = s.eoff[r];
-    eo1 = s.eoff[r + 1];
     nlow = s.nlow[r];
     own_ne = s.pub_epoch[p][vi] > 0u;
+    ld_axis(s.m_dynL[p], qm, eL, LL);
+    ld_axis(s.m_dynR[p], qm, eR, LR);
+    markL = a ? s.m_dynL[p][qm.v - kTile] : eL[0];
+    markR = a ? s.m_dynR[p][qm.v - kTile] : eR[0];
+    if (INT) ld_axis(pubr, qp, eRec, LRec);
+    pos = pubr[qp.v + 20 * kTile];
+    vel = pubr[qp.v + 22 * kTile];
     pe[0] = s.prior_eta[s.at<4>(a, vi)];
     pe[1] = s.prior_eta[s.at<4>(a + 2, vi)];
     pl = s.prior_lam[vi];
-    pos = pubr[qp.v + 20 * kTile];
-    vel = pubr[qp.v + 22 * kTile];
-    // VariableBelief.mean survives in bel_ext after an external half, else in the published record
-    mu[0] = pos;
-    mu[1] = vel;
-    if (latest) {
-      mu[0] = s.bel_ext[qp.v + 20 * kTile];
-      mu[1] = s.bel_ext[qp.v + 22 * kTile];
+    if (EXT) {
+      mu_sent[0] = s.mu_ext[s.at<2>(0, vi)];
+      mu_sent[1] = s.mu_ext[s.at<2>(1, vi)];
     }
   }
+  // ---- wave 2: edge heads, Dynamic-factor constants ------------------------------------------------
+  const int ne_all = int(eo1 - eo0);
+  const int ne = ne_all < kAxisEdges ? ne_all : kAxisEdges;
+  if (EXT && live) {
+    for (int k = 2 * i + a; k < ne; k += 2 * V) {
+      const int64_t e = eo0 + k;
+      hd_nbr[rl * kAxisEdges + k] = s.enbr[e];
+      hd_birth[rl * kAxisEdges + k] = s.e_birth[e];
+      hd_frozen[rl * kAxisEdges + k] = s.e_frozen[e];
+      hd_dsafe[rl * kAxisEdges + k] = s.e_dsafe[e];
+    }
+  }
+  if (INT && s.dyn_tab)
+    for (int k = t; k < 4 * V; k += T) dtab[k] = s.dyn_tab[k];
+  // VariableBelief.mean survives in bel_ext after an external half, else in the published record
+  mu[0] = pos;
+  mu[1] = vel;
+  if (live && latest) {
+    mu[0] = s.bel_ext[qp.v + 20 * kTile];
+    mu[1] = s.bel_ext[qp.v + 22 * kTile];
+  }
+  __syncthreads();
+
   const bool work = live && !was_general;
   const bool do_ext = EXT && work && !idle && ant;
   const bool do_int = INT && work && !idle;
   // Dynamic factors disabled: whatever they sent while enabled stays in the inbox — general kernel
-  bool bad = work && !s.en_dyn;
+  bool bad = work && (!s.en_dyn || ne_all > kAxisEdges);
 
-  // ---- stored Dynamic messages: external inbox sum (variable.rs:263-271; FactorId order prior, dyn(i-1),
-  // dyn(i) — mirror, Obstacle and Tracking messages contribute nothing in this regime) and the variable ->
-  // factor messages of the previous variable iteration, (record - the factor's own last message)
-  // (variable.rs:301-330), handed to the neighbouring variables through shared memory
+  // ---- wave 3 issued, then the stored Dynamic messages are consumed while it is in flight ----------
+  // The pair shares the robot's edges (lane a takes edges a, a + 2, ...): every InterRobot factor must
+  // take `skip`; its head is the neighbour's position mean, the record's epoch, radio / idle bits and
+  // the staged edge scalars.
+  const bool edges = EXT && do_ext && i >= 1 && ne > a;
+  const int nmine = edges ? (ne - a + 1) >> 1 : 0;
+  double m0[kAxisBatch] = {}, m1[kAxisBatch] = {};
+  uint32_t epA[kAxisBatch] = {};
+  unsigned onA = 0u;  // bit q: neighbour q of the batch has its radio on and is not idle
+  auto fetch = [&](int b0) {
+    onA = 0u;
+#pragma unroll
+    for (int q = 0; q < kAxisBatch; ++q) {
+      const int k = (b0 + q < nmine) ? a + 2 * (b0 + q) : a;  // past the end: a valid edge again, result unused
+      const int A = hd_nbr[rl * kAxisEdges + k];
+      const int64_t va = int64_t(A) * V + i;
+      m0[q] = pubr[s.at<kRec>(20, va)];
+      m1[q] = pubr[s.at<kRec>(21, va)];
+      epA[q] = s.pub_epoch[p][va];
+      onA |= ((s.antenna[A] != 0) & (s.idle[A] == 0)) ? (1u << q) : 0u;
+    }
+  };
+  if (edges) fetch(0);
+
+  // external inbox sum (variable.rs:263-271; FactorId order prior, dyn(i-1), dyn(i) — mirror, Obstacle and
+  // Tracking messages contribute nothing in this regime) and the variable -> factor messages of the previous
+  // variable iteration, (record - the factor's own last message) (variable.rs:301-330), handed to the
+  // neighbouring variables through shared memory
   double ae[2] = {pe[0], pe[1]}, al[4] = {pl, 0.0, 0.0, pl}, Q[4];
   {
-    double eRec[2] = {0.0, 0.0}, LRec[4] = {0.0, 0.0, 0.0, 0.0};
-    if (INT && work) ld_axis(pubr, qp, eRec, LRec);
+    const bool hasL = work && !is_empty_marker(markL), hasR = work && !is_empty_marker(markR);
     if (INT && work && idle) {
       // idle robot: its record and messages are carried over to the other buffers unchanged
       st_axis(pubw, qp, eRec, LRec);
       pubw[qp.v + 20 * kTile] = pos;
       pubw[qp.v + 22 * kTile] = vel;
       if (a == 0) s.pub_epoch[1 - p][vi] = s.pub_epoch[p][vi];
-    }
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-      const double *const src = side ? s.m_dynR[p] : s.m_dynL[p];
-      double *const x = side ? xr : xl;
-      double e[2] = {0.0, 0.0}, L[4] = {0.0, 0.0, 0.0, 0.0};
-      bool has = false;
-      if (work) {
-        ld_axis(src, qm, e, L);
-        has = !is_empty_marker(src[qm.v - a * kTile]);  // the Empty marker sits in row 0
-        if (INT && idle) {
-          double *const dst = side ? s.m_dynR[1 - p] : s.m_dynL[1 - p];
-          st_axis(dst, qm, e, L);
-          if (a == 1) dst[qm.v - kTile] = src[qm.v - kTile];
-        }
-      }
-      if (EXT && do_ext && has) {
-#pragma unroll
-        for (int k = 0; k < 2; ++k) ae[k] = ae[k] + e[k];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) al[k] = al[k] + L[k];
-      }
-      if (INT) {
-#pragma unroll
-        for (int k = 0; k < 2; ++k) x[k * T + t] = has ? eRec[k] - e[k] : eRec[k];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) x[(2 + k) * T + t] = has ? LRec[k] - L[k] : LRec[k];
+      st_axis(s.m_dynL[1 - p], qm, eL, LL);
+      st_axis(s.m_dynR[1 - p], qm, eR, LR);
+      if (a == 1) {
+        s.m_dynL[1 - p][qm.v - kTile] = markL;
+        s.m_dynR[1 - p][qm.v - kTile] = markR;
       }
     }
-    if (INT) xne[t] = own_ne ? 1 : 0;
+    if (EXT && do_ext) {
+      if (hasL) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) ae[k] = ae[k] + eL[k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) al[k] = al[k] + LL[k];
+      }
+      if (hasR) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) ae[k] = ae[k] + eR[k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) al[k] = al[k] + LR[k];
+      }
+    }
+    if (INT) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        xl[k * T + t] = hasL ? eRec[k] - eL[k] : eRec[k];
+        xr[k * T + t] = hasR ? eRec[k] - eR[k] : eRec[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        xl[(2 + k) * T + t] = hasL ? LRec[k] - LL[k] : LRec[k];
+        xr[(2 + k) * T + t] = hasR ? LRec[k] - LR[k] : LRec[k];
+      }
+      xne[t] = own_ne ? 1 : 0;
+    }
   }
 
-  double mu_sent[2] = {0.0, 0.0}, mu_ext_new = 0.0;
+  double mu_ext_new = 0.0;
   uint32_t frz = 0u;
   bool flip = false;
 
   // =================== external half ====================================
   if (EXT) {
-    if (do_ext && i >= 1 && eo1 > eo0) {
-      // The pair shares the robot's edges: every InterRobot factor must take `skip`; its head is
-      // the neighbour's position mean, the record's epoch, radio/idle bits and the edge scalars.
-      mu_sent[0] = s.mu_ext[s.at<2>(0, vi)];
-      mu_sent[1] = s.mu_ext[s.at<2>(1, vi)];
-      const int64_t elow = eo0 + nlow;
-      for (int64_t e = eo0 + a; e < eo1; e += 2) {
-        const int A = s.enbr[e];
-        const int64_t va = int64_t(A) * V + i;
-        const double m0 = pubr[s.at<kRec>(20, va)], m1 = pubr[s.at<kRec>(21, va)];
-        const uint32_t epochA = s.pub_epoch[p][va];
-        const bool act = s.en_ir && s.antenna[A] != 0 && s.idle[A] == 0;
-        const uint32_t birth = s.e_birth[e];
-        const bool frozen = (s.e_frozen[e] & 1) != 0;
-        const double dsafe = s.e_dsafe[e];
+    for (int b0 = 0; b0 < nmine; b0 += kAxisBatch) {
+      if (b0) fetch(b0);
+#pragma unroll
+      for (int q = 0; q < kAxisBatch; ++q) {
+        if (b0 + q >= nmine) break;
+        const int k = a + 2 * (b0 + q);
+        const bool act = s.en_ir && ((onA >> q) & 1u);
+        const uint32_t birth = hd_birth[rl * kAxisEdges + k];
+        const bool frozen = (hd_frozen[rl * kAxisEdges + k] & 1) != 0;
+        const double dsafe = hd_dsafe[rl * kAxisEdges + k];
         flip |= frozen == act;  // bit 0 has to end up as !act
         if (act) {
-          const bool a_ne = epochA > birth;
-          const double muA[2] = {a_ne ? m0 : 0.0, a_ne ? m1 : 0.0};
+          const bool a_ne = epA[q] > birth;
+          const double muA[2] = {a_ne ? m0[q] : 0.0, a_ne ? m1[q] : 0.0};
           double mb[2] = {mu_sent[0], mu_sent[1]};
           if (frozen) {
-            const int64_t m = e * (V - 1) + (i - 1);
+            const int64_t m = (eo0 + k) * (V - 1) + (i - 1);
             mb[0] = s.mu_frozen[m];
             mb[1] = s.mu_frozen[s.EV + m];
           }
-          if (!interrobot_skip(e < elow, muA, mb, dsafe)) bad = true;
+          if (!interrobot_skip(k < nlow, muA, mb, dsafe)) bad = true;
         } else if (!frozen) {
           // undelivered: A's factor keeps the mean it holds while this belief moves on (robot.rs:1851)
-          const int64_t k = (e - eo0) >> 1;
-          if (k < 32) frz |= 1u << k;
-          else bad = true;
+          frz |= 1u << (b0 + q);
         }
       }
     }
@@ -250,6 +325,31 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
   if (INT) {
     // linearisation point of the Obstacle factor: the record's position mean, both axes
     const double other_pos = __shfl_xor_sync(0xffffffffu, pos, 1);
+    // ObstacleFactor (obstacle.rs:129-188, factor/mod.rs:102-128): the Jacobian must come out zero.  Same
+    // perturb-and-restore sequence as obstacle_update; the pair splits the four lookups — the x lane takes
+    // h(x, y) and h(x + d, y), the y lane h(x', y + d) and h(x', y') with x' = (x + d) - d, y' = (y + d) - d.
+    bool obs_here = false;
+    double h_first = 0.0, h_second = 0.0;
+    if (s.en_obs && do_int && i >= 1 && i <= V - 2) {
+      obs_here = true;
+      const double x = own_ne ? (a ? other_pos : pos) : 0.0, y = own_ne ? (a ? pos : other_pos) : 0.0;
+      const double delta = s.jac_delta;
+      double px = x + delta, py = y;
+      double x1 = x, y1 = y, x2 = px, y2 = y;
+      if (a) {
+        px -= delta;
+        py += delta;
+        x1 = px;
+        y1 = py;
+        py -= delta;
+        x2 = px;
+        y2 = py;
+      }
+      h_first = sdf_measure(s, x1, y1);
+      h_second = sdf_measure(s, x2, y2);
+    }
+    // h(x, y) is the x lane's first lookup; J0 = (h(x + d, y) - h0) / d, J1 and J2 = J3 likewise
+    const double h0 = __shfl_sync(0xffffffffu, h_first, (threadIdx.x & 31u) & ~1u);
     __syncthreads();
     ae[0] = pe[0];
     ae[1] = pe[1];
@@ -267,13 +367,13 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
         const double oQ[4] = {xr[2 * T + tq], xr[3 * T + tq], xr[4 * T + tq], xr[5 * T + tq]};
         double dc[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) dc[k] = s.dyn_c[s.at<4>(k, vi - 1)];
+        for (int k = 0; k < 4; ++k) dc[k] = s.dyn_tab ? dtab[4 * (i - 1) + k] : s.dyn_c[s.at<4>(k, vi - 1)];
         const DynM M = dyn_potential_q(dc[0], dc[1], dc[2], dc[3]);
-        double ne[2], nl[4];
-        if (dyn_message_axis<1>(a, M, xne[tn] != 0, oe, oP, oQ, ne, nl)) {
-          st_axis(s.m_dynL[1 - p], qm, ne, nl);
+        double ne_[2], nl[4];
+        if (dyn_message_axis<1>(a, M, xne[tn] != 0, oe, oP, oQ, ne_, nl)) {
+          st_axis(s.m_dynL[1 - p], qm, ne_, nl);
 #pragma unroll
-          for (int k = 0; k < 2; ++k) ae[k] = ae[k] + ne[k];
+          for (int k = 0; k < 2; ++k) ae[k] = ae[k] + ne_[k];
 #pragma unroll
           for (int k = 0; k < 4; ++k) al[k] = al[k] + nl[k];
         } else {
@@ -287,13 +387,13 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
         const double oQ[4] = {xl[2 * T + tq], xl[3 * T + tq], xl[4 * T + tq], xl[5 * T + tq]};
         double dc[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) dc[k] = s.dyn_c[s.at<4>(k, vi)];
+        for (int k = 0; k < 4; ++k) dc[k] = s.dyn_tab ? dtab[4 * i + k] : s.dyn_c[s.at<4>(k, vi)];
         const DynM M = dyn_potential_q(dc[0], dc[1], dc[2], dc[3]);
-        double ne[2], nl[4];
-        if (dyn_message_axis<0>(a, M, xne[tn] != 0, oe, oP, oQ, ne, nl)) {
-          st_axis(s.m_dynR[1 - p], qm, ne, nl);
+        double ne_[2], nl[4];
+        if (dyn_message_axis<0>(a, M, xne[tn] != 0, oe, oP, oQ, ne_, nl)) {
+          st_axis(s.m_dynR[1 - p], qm, ne_, nl);
 #pragma unroll
-          for (int k = 0; k < 2; ++k) ae[k] = ae[k] + ne[k];
+          for (int k = 0; k < 2; ++k) ae[k] = ae[k] + ne_[k];
 #pragma unroll
           for (int k = 0; k < 4; ++k) al[k] = al[k] + nl[k];
         } else {
@@ -303,25 +403,9 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
       if (i >= 1 && i <= V - 2) {
         // Tracking factors run from iteration_count.factor >= 10 on (factorgraph.rs:701): general kernel
         if (s.en_trk && itf >= 10u) bad = true;
-        if (s.en_obs) {
-          // ObstacleFactor (obstacle.rs:129-188, factor/mod.rs:102-128): the Jacobian must come out zero.
-          // Same perturb-and-restore sequence as obstacle_update; the pair splits the lookups.
+        if (obs_here) {
           if (!(isfinite(pos) & isfinite(vel))) bad = true;  // v0 = J.x - h has to be finite
-          const double x = own_ne ? (a ? other_pos : pos) : 0.0, y = own_ne ? (a ? pos : other_pos) : 0.0;
-          const double delta = s.jac_delta;
-          const double h0 = sdf_measure(s, x, y);
-          double px = x, py = y;
-          px += delta;
-          if (a == 0) {
-            if (!(sdf_measure(s, px, py) - h0 == 0.0)) bad = true;
-          } else {
-            px -= delta;
-            py += delta;
-            const double h2 = sdf_measure(s, px, py);
-            py -= delta;
-            const double h3 = sdf_measure(s, px, py);
-            if (!((h2 - h0 == 0.0) & (h3 - h0 == 0.0))) bad = true;
-          }
+          if (!((a ? h_first - h0 == 0.0 : true) & (h_second - h0 == 0.0))) bad = true;
         }
       }
       itf += 1;

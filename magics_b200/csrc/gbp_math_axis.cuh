@@ -54,9 +54,16 @@ GBP_DEV bool inv_axis(int a, const double (&P)[4], const double (&Q)[4], double 
 // (the other outcomes — precision below 1e-6 everywhere, singular, non-finite covariance — keep an
 // older mean / covariance and belong to the general kernel).  mu = own two components.
 GBP_DEV bool belief_axis(int a, const double (&e)[2], const double (&P)[4], const double (&Q)[4], double (&mu)[2]) {
-  bool nz = false;
+  // `precision_matrix.iter().any(|x| *x > 1e-6)` (variable.rs:276): the first diagonal entry settles it for every
+  // variable that has a prior or a Dynamic message; the other seven are looked at only if it does not (nvcc turns
+  // the eight-way OR into emulated 64-bit max operations, ~50 instructions)
+  bool nz = P[0] > 1e-6;
+  if (!nz) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) nz |= (P[k] > 1e-6) | (Q[k] > 1e-6);
+    for (int k = 1; k < 4; ++k) nz |= P[k] > 1e-6;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) nz |= Q[k] > 1e-6;
+  }
   double O[4];
   if (!nz || !inv_axis(a, P, Q, O)) return false;
   bool fin = isfinite(e[0]) & isfinite(e[1]);

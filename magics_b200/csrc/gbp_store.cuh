@@ -74,6 +74,8 @@ struct Store {
   double *m_obs;         // [4][NV]   Obstacle message as (J0, J1, J2=J3, v0)
   double *m_trk;         // [3][NV]   Tracking message as (J0, J1, v0)
   double *dyn_c;         // [4][NV]   Dynamic factor i: delta_t (f32 widened) and q11, q12, q22 (gbp_math.cuh dyn_q)
+  const double *dyn_tab; // [V][4]    the same four constants by variable index while every robot of the world has
+                         //           the same delta_t per factor (one radius: robot.rs:1225,1232), else null
   uint32_t *trk_record;  // [NV]      Tracking.record
   int32_t *trk_timeout;  // [NV]      TrackingFactor.timeout (-1 = None)
   uint8_t *trk_seed;     // [NV]      1: the Tracking factor's inbox still holds the belief it was created with
@@ -122,6 +124,7 @@ struct Store {
   const uint8_t *sdf;  // red channel, row 0 = top
   int32_t sdf_w, sdf_h;
   double world_w, world_h, jac_delta;
+  double sdf_xo, sdf_yo, sdf_xs, sdf_ys;  // ObstacleFactor::measure's offsets (world / 2) and scales (pixels / world)
 
   // ---- scalars widened once (robot.rs:1238-1240,1272,1318,1517-1522) ------
   double qs_dyn;   // 1/sigma_dynamics^2

@@ -57,6 +57,20 @@ def sum_over_ranks(value: float) -> float:
     return float(t.item())
 
 
+def sum_u64_over_ranks(value: int) -> int:
+    """Sum modulo 2**64 of one unsigned 64-bit integer per rank, exact on every backend (four 16-bit limbs
+    summed as int64)."""
+    import torch
+    import torch.distributed as dist
+
+    v = int(value) & 0xFFFFFFFFFFFFFFFF
+    t = torch.tensor([(v >> (16 * k)) & 0xFFFF for k in range(4)], dtype=torch.int64, device=_device())
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    limbs = [int(x) for x in t.cpu().tolist()]
+    return sum(l << (16 * k) for k, l in enumerate(limbs)) & 0xFFFFFFFFFFFFFFFF
+
+
 def gather_arrays(arrays: dict, rank: int, world_size: int, dst: int = 0):
     """Dict of numpy arrays from every rank to `dst` (list indexed by rank; None elsewhere).
     Arrays may differ in length per rank: each rank's dict travels as one npz byte string."""

@@ -25,6 +25,42 @@ def partition(n: int, world_size: int) -> np.ndarray:
     return np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
 
 
+_M1 = np.uint64(0x9E3779B97F4A7C15)
+_M2 = np.uint64(0xBF58476D1CE4E5B9)
+_M3 = np.uint64(0x94D049BB133111EB)
+
+
+def _mix64(x: np.ndarray) -> np.ndarray:
+    """splitmix64 finaliser, element-wise on uint64 (wrapping arithmetic)."""
+    with np.errstate(over="ignore"):
+        x = (x ^ (x >> np.uint64(30))) * _M2
+        x = (x ^ (x >> np.uint64(27))) * _M3
+        return x ^ (x >> np.uint64(31))
+
+
+def state_hash(first_global_id: int, means: np.ndarray, offsets: np.ndarray, neighbours: np.ndarray,
+               robot_number: np.ndarray) -> tuple[int, int]:
+    """Partition-independent 64-bit digests of a shard's state, to be SUMMED modulo 2**64 over the shards:
+    (means, connectivity).  `means`: (n, V, 4) f64 — every bit of every variable mean enters, keyed by the
+    robot's global id and the component index; connectivity: every directed pair (robot, neighbour,
+    robot_number) in global ids.  A swarm partitioned over 1, 2, 4 or 8 GPUs gives the same two sums
+    iff all means, the whole InterRobot edge set and every robot_number are bit-identical."""
+    with np.errstate(over="ignore"):
+        m = np.ascontiguousarray(means, np.float64)
+        n = m.shape[0]
+        bits = m.reshape(n, m.size // n if n else 0).view(np.uint64)
+        gid = (np.arange(n, dtype=np.uint64) + np.uint64(first_global_id))[:, None]
+        comp = np.arange(bits.shape[1], dtype=np.uint64)[None, :]
+        h_means = int(np.sum(_mix64(bits ^ _mix64(gid * _M1 + comp)), dtype=np.uint64)) if n else 0
+        off = np.asarray(offsets, np.int64)
+        deg = np.diff(off)
+        src = np.repeat(np.arange(n, dtype=np.uint64) + np.uint64(first_global_id), deg)
+        nb = np.asarray(neighbours).astype(np.uint64)
+        rn = np.asarray(robot_number).astype(np.uint64)
+        h_conn = int(np.sum(_mix64(_mix64(src * _M1 + nb) ^ (rn * _M2)), dtype=np.uint64)) if src.size else 0
+    return h_means, h_conn
+
+
 class LocalShards:
     """`world_size` shards of one swarm in this process on one device (gbp_world_create_local_shards)."""
 

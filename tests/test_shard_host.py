@@ -39,6 +39,39 @@ def test_lattice_rank_slices_tile_the_global_swarm():
             lo += p.n
 
 
+def test_state_hash_does_not_depend_on_the_partition():
+    """bench.py prints the digests at N = 1, 2, 4, 8: shard sums must equal the single-shard value, and one
+    changed bit of a mean, one changed neighbour or robot_number must change them."""
+    from magics_b200.sharded import state_hash
+
+    rng = np.random.default_rng(3)
+    n, V = 61, 7
+    means = rng.normal(size=(n, V, 4))
+    deg = rng.integers(0, 5, n)
+    off = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+    nb = rng.integers(0, n, off[-1]).astype(np.int32)
+    rn = rng.integers(0, 10_000, off[-1]).astype(np.int64)
+    whole = state_hash(0, means, off, nb, rn)
+    for ws in (2, 4, 8):
+        b = partition(n, ws)
+        tot = [0, 0]
+        for q in range(ws):
+            lo, hi = int(b[q]), int(b[q + 1])
+            h = state_hash(lo, means[lo:hi], off[lo:hi + 1] - off[lo], nb[off[lo]:off[hi]], rn[off[lo]:off[hi]])
+            tot = [(tot[k] + h[k]) % 2 ** 64 for k in range(2)]
+        assert tuple(tot) == whole, ws
+    m2 = means.copy()
+    m2[17, 3, 2] = np.nextafter(m2[17, 3, 2], np.inf)
+    assert state_hash(0, m2, off, nb, rn)[0] != whole[0]
+    m3 = means.copy()
+    m3[[4, 5]] = m3[[5, 4]]  # two robots swapped: the digest is keyed by robot id
+    assert state_hash(0, m3, off, nb, rn)[0] != whole[0]
+    rn2 = rn.copy()
+    rn2[0] += 1
+    assert state_hash(0, means, off, nb, rn2)[1] != whole[1]
+    assert state_hash(0, means[:0], off[:1], nb[:0], rn[:0]) == (0, 0)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -48,7 +81,7 @@ def _free_port():
 def _gloo_worker(rank, ws, port, q):
     import torch.distributed as dist
 
-    from magics_b200.dist import broadcast_bytes, gather_arrays, max_over_ranks, sum_over_ranks
+    from magics_b200.dist import broadcast_bytes, gather_arrays, max_over_ranks, sum_over_ranks, sum_u64_over_ranks
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=ws)
@@ -58,6 +91,9 @@ def _gloo_worker(rank, ws, port, q):
         assert got == bytes(range(128))
         assert max_over_ranks(10.0 + rank) == 10.0 + ws - 1
         assert sum_over_ranks(1.5) == 1.5 * ws
+        # exact modulo-2**64 sum (bench.py's cross-N state hash): wraps, keeps every bit
+        big = 0xFFFFFFFFFFFFFFF0 + rank
+        assert sum_u64_over_ranks(big) == sum(0xFFFFFFFFFFFFFFF0 + r for r in range(ws)) % 2 ** 64
         # ragged per-rank arrays (a rank may own no robots)
         mine = {"mean": np.full((rank * 3, 2, 4), float(rank)), "nb": np.arange(rank * 5, dtype=np.int32)}
         parts = gather_arrays(mine, rank, ws)
