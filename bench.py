@@ -9,9 +9,9 @@ interleave-evenly => 10 sub-steps, each one robot-GBP-iteration per robot).
   value  robots x sub-steps x steps / device time, swarm resident in HBM
   e2e    same through the C ABI with HOST buffers each step (comms mask and
          waypoint indices in, every variable's mean out)
-  roofline  dominant kernel k_iterate<EXT,INT>: algorithmic bytes per launch
-            (192*(5E+7F) + 704*V per robot-iteration) / its
-            average CUDA-event duration, against MEASURED_PEAKS.json
+  roofline  dominant kernel k_iterate_axis<EXT,INT>: compulsory bytes of the
+            store layout per launch / its average CUDA-event
+            duration, against MEASURED_PEAKS.json; `traffic` = ncu DRAM bytes
   cpu_baseline  the oracle (C++ restatement of the reference algorithm) timed
             on the host cores on a bounded sample of the same workload
 
@@ -37,11 +37,28 @@ METRIC = "robot_gbp_iterations_per_sec"
 UNIT = "robot-GBP-iterations/s"
 
 
-def algorithmic_bytes_per_robot_iteration(V: int, K: float, e_obs: int, e_trk: int) -> float:
-    """messages counted as the reference's 192-byte payloads."""
+def reference_message_bytes_per_robot_iteration(V: int, K: float, e_obs: int, e_trk: int) -> float:
+    """what the REFERENCE's formulation moves — every message a 192-byte payload in an inbox.
+    Reported for context only; the engine never materialises these messages."""
     E = 2 * (V - 1) + e_obs * (V - 2) + e_trk * (V - 2)
     F = K * (V - 1)
     return 192.0 * (5 * E + 7 * F) + 704.0 * V
+
+
+def compulsory_bytes_per_robot_iteration(V: int, K: float) -> float:
+    """Bytes one fused external+internal half-step of k_iterate_axis has to move for one robot with the store of
+    DESIGN.md section 3 (decoupled regime, both lanes of every variable; derivation in DESIGN.md section 4):
+      read   per variable: record rows of both axes 12 + mean 4, stored Dynamic messages 2 x 12, prior 5 doubles,
+             record epoch 4 B; variables >= 1: last delivered mean 2 doubles
+      write  per variable: new record 16 doubles + epoch 4 B + lazy-covariance flag 1 B; new Dynamic messages
+             12 doubles for each of the 2 (V - 1) factor slots; variables >= 1: delivered mean 2 doubles
+      per robot: mode / idle / antenna / latest bytes, iteration count, edge range, nlow (25 B)
+      per edge:  neighbour slot 4, birth epoch 4, frozen bit 1, safety distance 8 B; the neighbours' position
+             means are rows of records the launch reads anyway (L2 serves the K re-reads).
+    """
+    reads = V * (16 + 24 + 5) * 8 + V * 4 + (V - 1) * 2 * 8
+    writes = V * 16 * 8 + V * 5 + 2 * (V - 1) * 12 * 8 + (V - 1) * 2 * 8
+    return float(reads + writes + 25 + 17.0 * K)
 
 
 class ClockSampler:
@@ -334,23 +351,32 @@ def main():
     if rank == 0:
         deg = float(np.diff(g.read_connections()[0]).mean()) if n else 0.0
         peak, peak_kind = measured_peak_gbs()
-        bytes_iter = algorithmic_bytes_per_robot_iteration(cfg.num_variables, deg, int(cfg.enable_obstacle),
-                                                           int(cfg.enable_tracking))
+        bytes_iter = compulsory_bytes_per_robot_iteration(cfg.num_variables, deg)
         dom = prof.get("iterate_ext_int", {"count": 0, "ms": 0.0})
         roof = None
         if dom["count"]:
-            avg_s = dom["ms"] * 1e-3 / dom["count"]
+            # device time of one fused external+internal half-step pair; a sharded run launches the kernel twice per
+            # pair (border robots, then the rest), so the total is divided by the pairs of the schedule
+            ph = [c for a, b in zip(oi, oe) for c in (("I",) if a else ()) + (("E",) if b else ())]
+            fused_per_tick = sum(1 for k in range(len(ph) - 1) if ph[k] == "E" and ph[k + 1] == "I")
+            avg_s = dom["ms"] * 1e-3 / max(1, fused_per_tick * args.steps)
             achieved = bytes_iter * n / avg_s / 1e9
             traffic, traffic_src = ncu_traffic(sw.name)
-            roof = {"bound": "hbm", "kernel": "k_iterate<EXT,INT>", "achieved": achieved, "peak": peak,
+            if traffic is not None and n_total != n:
+                traffic *= n / n_total  # the ncu capture is of the whole swarm on one GPU; this shard iterates n robots
+            roof = {"bound": "hbm", "kernel": "k_iterate_axis<EXT,INT>", "achieved": achieved, "peak": peak,
                     "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "traffic_source": traffic_src,
                     "traffic_frac": (traffic / avg_s / 1e9 / peak) if traffic else None,
                     "avg_launch_ms": avg_s * 1e3, "launches_timed": dom["count"],
-                    "algorithmic_bytes_per_robot_iteration": bytes_iter, "mean_neighbours": deg,
-                    "note": "achieved counts the reference's 192-byte messages (SURVEY 8d); the engine's "
-                            "compressed store moves `traffic` bytes per launch instead, so frac can exceed 1; "
-                            "traffic_frac = real DRAM bytes / launch time / peak"}
+                    "compulsory_bytes_per_robot_iteration": bytes_iter, "mean_neighbours": deg,
+                    "reference_message_bytes_per_robot_iteration": reference_message_bytes_per_robot_iteration(
+                        cfg.num_variables, deg, int(cfg.enable_obstacle), int(cfg.enable_tracking)),
+                    "note": "achieved = compulsory bytes of this store layout (DESIGN.md section 4) x robots of "
+                            "rank 0 / average device time of the fused external+internal launch (CUDA events "
+                            "on the engine's stream); traffic = dram__bytes_read + dram__bytes_write of the same "
+                            "launch from the committed ncu capture (scaled to this rank's robots when sharded); "
+                            "traffic_frac = traffic / time / peak"}
         cpu = None
         if not args.no_cpu_baseline:
             swc, _ = build_workload(args.workload, args.cpu_robots)

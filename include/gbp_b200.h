@@ -329,6 +329,19 @@ int gbp_world_read_beliefs_async(gbp_world_t *w, double *eta, double *lam, doubl
 int gbp_world_readback_wait(gbp_world_t *w);
 /* Transform.translation (x, z) of every robot, f32[n*2]. */
 int gbp_world_read_positions(gbp_world_t *w, float *xy);
+/* RobotDespawned (planner/robot.rs:2171-2172, despawn_entity_after): the listed robots (LOCAL indices) leave the
+ * simulation.  From the next gbp_world_update_topology on they are in nobody's comms range, so every InterRobot
+ * factor to or from them is deleted by the regular path (robot.rs:1386-1439); they are never iterated again and
+ * gbp_world_reached_waypoint reports nothing for them.  Indices are stable: the slot stays, frozen in its last
+ * state, and still counts in gbp_world_num_robots; gbp_world_read_removed tells which slots are dead.  On a
+ * sharded world each rank removes its own robots; the peers learn it with the positions of the next topology pass. */
+int gbp_world_remove_robots(gbp_world_t *w, int32_t m, const int32_t *robots);
+int gbp_world_read_removed(gbp_world_t *w, uint8_t *removed);
+/* State of every Tracking factor, as the visualisers and the RRT* hand-off read it (factor/tracking.rs:62-90,
+ * `Tracking.record`, `LastMeasurement { pos: Vec2, value }`), one entry per (robot,
+ * variable): record[n*V], last_pos f32[n*V*2], last_value[n*V].  Variables 0 and V-1 have no Tracking factor;
+ * their entries keep the initial values (record 0, the initial mean, 0.0). */
+int gbp_world_read_tracking(gbp_world_t *w, int64_t *record, float *last_pos, double *last_value);
 /* RobotConnections.robots_connected_with as CSR: offsets[n+1], neighbours (global robot
  * ids) sorted ascending; robot_number[e] = RobotNumberGenerator value of the FIRST (i=1)
  * InterRobot factor robot r created toward neighbours[e] (robot.rs:1527).

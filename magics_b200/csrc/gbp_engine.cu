@@ -230,6 +230,16 @@ __global__ void k_init_vars(Store s, int64_t first, int64_t count, const double 
   s.dyn_c[s.at<4>(3, vi)] = q22;
 }
 
+// TrackingFactor state read-back (tracking.rs:62-90 `Tracking.record`, `LastMeasurement`): AoS rows per variable.
+__global__ void k_gather_tracking(Store s, int64_t nv, int64_t *record, float *pos, double *value) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= nv) return;
+  record[t] = int64_t(s.trk_record[t]);
+  pos[2 * t] = s.trk_last[s.at<2>(0, t)];
+  pos[2 * t + 1] = s.trk_last[s.at<2>(1, t)];
+  value[t] = s.trk_value[t];
+}
+
 // Store::dyn_tab: the Dynamic-factor constants of one robot, by variable index (valid for every robot while
 // all of them share one radius, i.e. one delta_t per factor).
 __global__ void k_dyn_table(Store s, int64_t robot, double *tab) {
@@ -518,6 +528,7 @@ __global__ void k_reached_waypoint(Store s, int p, gbp_reached_when_t task, gbp_
   const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (r >= s.Nloc) return;
   if (out) out[r] = 0;
+  if (s.gone[r] != 0.0f) return;  // despawned: the system's query no longer yields the entity
   const int32_t nwp = s.wp_off[r + 1] - s.wp_off[r], k = s.next_wp[r];
   if (k < 0 || k >= nwp) return;  // mission.next_waypoint() is None
   const gbp_reached_when_t c = (k == nwp - 1) ? fin : task;
@@ -551,6 +562,19 @@ __global__ void k_words_to_host(int64_t *__restrict__ host_dst, const int64_t *_
   __threadfence_system();
 }
 
+// gbp_world_remove_robots: the entity is despawned (robot.rs:2171-2172 RobotDespawned, despawn_entity_after).
+__global__ void k_remove_robots(Store s, int m, const int32_t *__restrict__ robots) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m) return;
+  const int32_t r = robots[k];
+  s.gone[r] = 1.0f;
+  s.idle[r] = 1;  // never iterated again; k_keep_gone_idle re-applies it after every gbp_world_set_comms
+}
+__global__ void k_keep_gone_idle(Store s) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < s.Nloc && s.gone[r] != 0.0f) s.idle[r] = 1;
+}
+
 __global__ void k_iota_gid(int32_t *gid, int32_t g0, int32_t n) {
   const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < n) gid[r] = g0 + r;
@@ -567,6 +591,8 @@ struct gbp_group {
   std::vector<gbp_world *> members;  // shards living in this process, indexed by rank when !nccl
   bool committed = false;            // global ids fixed (gbp_world_commit_shards)
   bool halo_stale = true;            // some published record changed since the last halo exchange
+  bool halo_pending = false;         // an exchange started right after the border robots' internal half is in flight
+                                     // on the comm streams (group_launch); the next external half waits for it
   cudaStream_t shared_stream = nullptr;
   int refs = 0;
 };
@@ -642,7 +668,7 @@ struct gbp_world {
   gbp_group *grp = nullptr;
   bool owns_stream = true;
   bool smem_opted_in[4] = {false, false, false, false};  // k_iterate<EXT,INT> dynamic shared memory opt-in
-  bool axis_opted_in[4] = {false, false, false, false};  // k_iterate_axis<EXT,INT> likewise
+  bool axis_opted_in[12] = {};  // k_iterate_axis<EXT,INT,PART> likewise
   bool general_only = false;  // gbp_world_set_iterate_path: every robot through k_iterate
   double *dyn_tab_dev = nullptr;  // Store::dyn_tab while every robot added so far has the same t0 (radius)
   bool t0_seen = false, t0_uniform = true;
@@ -654,7 +680,10 @@ struct gbp_world {
   int32_t Ntot = 0;             // robots of the whole swarm
   int32_t nghost = 0;
   bool force_rebuild = false;
-  float *gpos = nullptr;        // [3][Ntot] x, z, radius of every robot by global id (ws > 1)
+  float *gpos = nullptr;        // [4][Ntot] x, z, radius, despawned flag of every robot by global id (ws > 1)
+  bool any_gone = false;        // some own robot has been removed: set_comms keeps it idle
+  std::vector<uint8_t> gone_host;  // host mirror of Store::gone
+  int64_t n_gone = 0;
   int64_t gpos_cap = 0;
   int32_t *t_gflag = nullptr, *t_gslot = nullptr, *t_sflag = nullptr, *t_soff = nullptr;
   int64_t *t_ccnt = nullptr, *t_coff = nullptr;
@@ -666,6 +695,14 @@ struct gbp_world {
   int64_t cross_cap = 0;
   int64_t *hdr_send = nullptr, *hdr_recv = nullptr, *hdr_host = nullptr;  // 4 int64 per shard
   double *halo_send = nullptr, *halo_recv = nullptr;
+  // halo / compute overlap: the robots of the send lists ("border") run first, their records travel on
+  // comm_stream while the interior robots run on `stream`
+  cudaStream_t comm_stream = nullptr;  // == stream for in-process shards (one device, one stream)
+  cudaEvent_t ev_border = nullptr, ev_halo = nullptr, ev_fence = nullptr;
+  uint32_t *border_words = nullptr;    // Store-side flags, one byte per own robot, as words for atomicOr
+  int32_t *border_list = nullptr, *border_count = nullptr;
+  int64_t border_cap = 0, border_words_cap = 0;
+  int64_t n_border_max = 0;            // length of the send lists = upper bound of *border_count
   int64_t halo_send_cap = 0, halo_recv_cap = 0;  // in doubles
   gbp::PeerOffsets ghost_po{}, send_po{};        // live halo layout (records per peer block)
   // results of the current topology pass, applied only when some shard's connectivity changed
@@ -761,21 +798,32 @@ void mark_halo_stale(gbp_world *w) {
 
 // ---- transport ---------------------------------------------------------------------
 // Runs one exchange for every shard of the group living in this process (gbp_comm.cuh).
-int exchange(gbp_group *g, std::vector<gbp::XferPlan> &plans) {
+int exchange(gbp_group *g, std::vector<gbp::XferPlan> &plans, bool on_comm_stream = false) {
   if (g->ws == 1) return 0;
   if (g->nccl) {
     gbp::NcclApi &api = gbp::nccl_api();
     gbp_world *w = g->members[0];
+    // Every NCCL call of the communicator is enqueued on ONE stream (comm_stream), so the order of its
+    // operations is the order of the calls on every rank; a caller working on w->stream is fenced in and out.
+    cudaStream_t nst = w->comm_stream;
+    if (!on_comm_stream) {
+      CK(cudaEventRecord(w->ev_fence, w->stream));
+      CK(cudaStreamWaitEvent(nst, w->ev_fence, 0));
+    }
     int rc = api.GroupStart();
     if (rc) return fail(GBP_ERR_NCCL, std::string("ncclGroupStart: ") + api.GetErrorString(rc));
     for (const gbp::Xfer &x : plans[0].sends)
-      if (x.bytes && (rc = api.Send(x.ptr, x.bytes, gbp::kNcclUint8, x.peer, g->comm, w->stream)))
+      if (x.bytes && (rc = api.Send(x.ptr, x.bytes, gbp::kNcclUint8, x.peer, g->comm, nst)))
         return fail(GBP_ERR_NCCL, std::string("ncclSend: ") + api.GetErrorString(rc));
     for (const gbp::Xfer &x : plans[0].recvs)
-      if (x.bytes && (rc = api.Recv(x.ptr, x.bytes, gbp::kNcclUint8, x.peer, g->comm, w->stream)))
+      if (x.bytes && (rc = api.Recv(x.ptr, x.bytes, gbp::kNcclUint8, x.peer, g->comm, nst)))
         return fail(GBP_ERR_NCCL, std::string("ncclRecv: ") + api.GetErrorString(rc));
     rc = api.GroupEnd();
     if (rc) return fail(GBP_ERR_NCCL, std::string("ncclGroupEnd: ") + api.GetErrorString(rc));
+    if (!on_comm_stream) {
+      CK(cudaEventRecord(w->ev_fence, nst));
+      CK(cudaStreamWaitEvent(w->stream, w->ev_fence, 0));
+    }
     return 0;
   }
   // in-process shards on one device and one stream: the k-th send a -> b is copied into the
@@ -811,9 +859,12 @@ int ensure_buf(gbp_world *w, T *&p, int64_t &cap, int64_t need) {
 }
 
 // ---- per-sub-step halo: published records of border robots -> ghost slots of the peers ----
-int group_halo(gbp_group *g) {
-  // Always exchanged before an external half (never skipped on a per-shard "nothing changed"
-  // guess: every rank must post the same sequence of transfers).
+// ahead == false: the exchange an external half needs, on the shards' own streams, from / into pub[p].
+// ahead == true: started by group_launch right after the border robots' internal half, while the interior
+// robots are still running: from / into pub[1 - p] (the buffer that half writes and the NEXT external half
+// reads), on the comm streams, between the events ev_border (border records written) and ev_halo
+// (ghost slots filled).  Every rank posts the same sequence of exchanges either way.
+int group_halo(gbp_group *g, bool ahead = false) {
   if (g->ws == 1) return 0;
   const int ws = g->ws;
   std::vector<gbp::XferPlan> plans(g->members.size());
@@ -821,11 +872,17 @@ int group_halo(gbp_group *g) {
     gbp_world *w = g->members[m];
     CK(cudaSetDevice(w->device));
     Store &s = w->s;
+    cudaStream_t st = ahead ? w->comm_stream : w->stream;
+    const int pb = ahead ? 1 - w->p : w->p;
+    if (ahead && w->comm_stream != w->stream) {
+      CK(cudaEventRecord(w->ev_border, w->stream));
+      CK(cudaStreamWaitEvent(w->comm_stream, w->ev_border, 0));
+    }
     const int64_t hd = gbp::halo_doubles_per_robot(s.V);
     const int64_t nsend = w->send_po.start[ws];
     if (nsend > 0) {
-      gbp::k_halo_pack<<<blocks_for(nsend * (s.V - 1), 256), 256, 0, w->stream>>>(s, w->p, ws, w->send_po, w->sendlist,
-                                                                               w->halo_send);
+      gbp::k_halo_pack<<<blocks_for(nsend * (s.V - 1), 256), 256, 0, st>>>(s, pb, ws, w->send_po, w->sendlist,
+                                                                        w->halo_send);
       CK(cudaGetLastError());
       w->launches += 1;
     }
@@ -838,31 +895,68 @@ int group_halo(gbp_group *g) {
     }
   }
   {
-    ProfileScope ps(g->members[0], GBP_PROFILE_HALO);
-    if (int rc = exchange(g, plans)) return rc;
+    gbp_world *w0 = g->members[0];
+    gbp_world::Span sp{};
+    if (w0->profiling) {  // the exchange alone, timed on the stream it runs on
+      sp.kind = GBP_PROFILE_HALO;
+      sp.a = take_event(w0);
+      sp.b = take_event(w0);
+      cudaEventRecord(sp.a, ahead ? w0->comm_stream : w0->stream);
+    }
+    if (int rc = exchange(g, plans, ahead)) return rc;
+    if (w0->profiling) {
+      cudaEventRecord(sp.b, ahead ? w0->comm_stream : w0->stream);
+      w0->spans.push_back(sp);
+    }
   }
   for (gbp_world *w : g->members) {
     CK(cudaSetDevice(w->device));
+    cudaStream_t st = ahead ? w->comm_stream : w->stream;
+    const int pb = ahead ? 1 - w->p : w->p;
     if (w->nghost > 0) {
-      gbp::k_halo_unpack<<<blocks_for(int64_t(w->nghost) * (w->s.V - 1), 256), 256, 0, w->stream>>>(
-          w->s, w->p, ws, w->ghost_po, w->halo_recv);
+      gbp::k_halo_unpack<<<blocks_for(int64_t(w->nghost) * (w->s.V - 1), 256), 256, 0, st>>>(w->s, pb, ws, w->ghost_po,
+                                                                                           w->halo_recv);
       CK(cudaGetLastError());
       w->launches += 1;
     }
+    if (ahead && w->comm_stream != w->stream) CK(cudaEventRecord(w->ev_halo, w->comm_stream));
   }
   g->halo_stale = false;
+  g->halo_pending = ahead;
   return 0;
 }
 
+// Work queued on the shards' own streams from here on sees the exchange that was started ahead (if any) finished:
+// called before anything that reads ghost slots or rebuilds what the exchange uses (send lists, buffers).
+int group_halo_join(gbp_group *g) {
+  if (!g->halo_pending) return 0;
+  for (gbp_world *w : g->members)
+    if (w->comm_stream != w->stream) {
+      CK(cudaSetDevice(w->device));
+      CK(cudaStreamWaitEvent(w->stream, w->ev_halo, 0));
+    }
+  g->halo_pending = false;
+  return 0;
+}
+
+// The external half that follows needs current ghost records: an exchange started ahead is waited for; one is
+// made now if records changed since (or none was started).
+int group_halo_ready(gbp_group *g) {
+  if (g->ws == 1) return 0;
+  if (int rc = group_halo_join(g)) return rc;
+  // Always exchanged before an external half otherwise (never skipped on a per-shard "nothing changed"
+  // guess: every rank must post the same sequence of transfers).
+  if (g->halo_stale) return group_halo(g, false);
+  return 0;
+}
+
+// One iterate launch pair (k_iterate_axis, then k_iterate over what it handed over) for one part of a shard:
+// part 0 = every own robot, 1 = the border robots (send lists), 2 = the others.
 template <bool EXT, bool INT>
-int launch_iterate(gbp_world *w) {
+int launch_iterate(gbp_world *w, int part) {
   Store &s = w->s;
   const int which = (EXT ? 2 : 0) + (INT ? 1 : 0);
-  w->epoch += 1;  // every shard steps its epoch, with or without robots
-  if (s.Nloc == 0) {
-    if (INT) w->p ^= 1;
-    return 0;
-  }
+  if (s.Nloc == 0) return 0;
   const int rpw = 32 / s.V;
   const int wpb = gbp::kIterBlock / 32;
   const int kind = EXT ? (INT ? GBP_PROFILE_ITERATE_EXT_INT : GBP_PROFILE_ITERATE_EXT) : GBP_PROFILE_ITERATE_INT;
@@ -875,45 +969,70 @@ int launch_iterate(gbp_world *w) {
   } else {
     // the decoupled robots (two lanes per variable), then whatever that kernel handed over
     const gbp::AxisGeom q = gbp::axis_geom(s.V);
-    if (!w->axis_opted_in[which]) {
-      CK(cudaFuncSetAttribute(gbp::k_iterate_axis<EXT, INT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(q.smem)));
-      w->axis_opted_in[which] = true;
+    if (part == 2 && !w->border_words) part = 0;  // no topology pass has flagged anything yet
+    auto kernel = part == 0 ? gbp::k_iterate_axis<EXT, INT, 0>
+                            : (part == 1 ? gbp::k_iterate_axis<EXT, INT, 1> : gbp::k_iterate_axis<EXT, INT, 2>);
+    bool &opted = w->axis_opted_in[which * 3 + part];
+    if (!opted) {
+      CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(q.smem)));
+      opted = true;
     }
-    {
+    const int64_t nrob = part == 1 ? w->n_border_max : int64_t(s.Nloc);
+    if (nrob > 0) {
       ProfileScope ps(w, kind);
-      gbp::k_iterate_axis<EXT, INT><<<blocks_for(s.Nloc, q.rpc), q.threads, q.smem, w->stream>>>(s, w->p, w->epoch, q.rpc,
-                                                                                              w->par);
-    }
-    CK(cudaGetLastError());
-    {
-      const int64_t warps = (int64_t(s.Nloc) + rpw - 1) / rpw;
+      kernel<<<blocks_for(nrob, q.rpc), q.threads, q.smem, w->stream>>>(
+          s, w->p, w->epoch, q.rpc, w->par, w->border_list, w->border_count,
+          reinterpret_cast<const uint8_t *>(w->border_words));
+      CK(cudaGetLastError());
+      const int64_t warps = (nrob + rpw - 1) / rpw;
       const unsigned grid = unsigned(std::min<int64_t>((warps + wpb - 1) / wpb, int64_t(w->sm_count) * 4));
-      ProfileScope ps(w, GBP_PROFILE_ITERATE_GENERAL);
+      ProfileScope pg(w, GBP_PROFILE_ITERATE_GENERAL);
       gbp::k_iterate<EXT, INT><<<grid, gbp::kIterBlock, 0, w->stream>>>(s, w->p, w->epoch, w->par);
+      w->par ^= 1;
+      w->launches += 2;
     }
-    w->par ^= 1;
-    w->launches += 2;
   }
   CK(cudaGetLastError());
   if (w->spans.size() > 4096) {
     if (int rc = drain_profile(w)) return rc;
   }
-  if (INT) w->p ^= 1;
   return 0;
 }
 
 // One half-step pair for every shard of the group: the external half reads the neighbours'
 // published records, so the halo must be current before it; the internal half republishes.
+// Sharded worlds run an internal half in two parts — border robots, then the rest — and start the
+// exchange of the new border records in between, so that it overlaps the interior launch
+// (the two delivery loops robot.rs:1814-1831, :1843-1858 for pairs split over two GPUs).
 template <bool EXT, bool INT>
 int group_launch(gbp_group *g) {
   if (EXT) {
-    if (int rc = group_halo(g)) return rc;
+    if (int rc = group_halo_ready(g)) return rc;
   }
+  bool split = INT && g->ws > 1;
   for (gbp_world *w : g->members) {
-    CK(cudaSetDevice(w->device));
-    if (int rc = launch_iterate<EXT, INT>(w)) return rc;
+    w->epoch += 1;  // every shard steps its epoch, with or without robots
+    split = split && !w->general_only;
   }
-  if (INT) g->halo_stale = true;
+  if (!split) {
+    for (gbp_world *w : g->members) {
+      CK(cudaSetDevice(w->device));
+      if (int rc = launch_iterate<EXT, INT>(w, 0)) return rc;
+    }
+    if (INT) g->halo_stale = true;
+  } else {
+    for (gbp_world *w : g->members) {
+      CK(cudaSetDevice(w->device));
+      if (int rc = launch_iterate<EXT, INT>(w, 1)) return rc;
+    }
+    if (int rc = group_halo(g, true)) return rc;
+    for (gbp_world *w : g->members) {
+      CK(cudaSetDevice(w->device));
+      if (int rc = launch_iterate<EXT, INT>(w, 2)) return rc;
+    }
+  }
+  if (INT)
+    for (gbp_world *w : g->members) w->p ^= 1;
   return 0;
 }
 
@@ -1096,6 +1215,7 @@ int reserve_robots(gbp_world *w, int64_t newcap) {
   CK(regrow(s.antenna, 1, oldcap, newcap, keep, st));
   CK(regrow(s.idle, 1, oldcap, newcap, keep, st));
   CK(regrow(s.finished, 1, oldcap, newcap, keep, st));
+  CK(regrow(s.gone, 1, oldcap, newcap, keep, st));
   CK(regrow(s.latest, 1, oldcap, newcap, keep, st));
   CK(regrow(s.iter_factor, 1, oldcap, newcap, keep, st));
   CK(regrow(s.mode, 1, oldcap, newcap, keep, st));
@@ -1136,10 +1256,11 @@ int topo_search(gbp_world *w) {
   if (int rc = ensure_topology_scratch(w)) return rc;
   const float *gx = ws > 1 ? w->gpos : s.pos;
   const float *gz = ws > 1 ? w->gpos + ntot : s.pos + s.cap;
+  const float *ggone = ws > 1 ? w->gpos + 3 * int64_t(ntot) : s.gone;
   const int T = 128;
   const float R = w->cfg.comms_radius;
   const double cell = double(R) * 1.001;
-  gbp::k_cell_keys<<<blocks_for(ntot, T), T, 0, st>>>(ntot, gx, gz, cell, w->t_cx, w->t_cz, w->t_keys, w->t_idx);
+  gbp::k_cell_keys<<<blocks_for(ntot, T), T, 0, st>>>(ntot, gx, gz, ggone, cell, w->t_cx, w->t_cz, w->t_keys, w->t_idx);
   size_t cb = w->t_cub_bytes;
   CK(cub::DeviceRadixSort::SortPairs(w->t_cub, cb, w->t_keys, w->t_keys_sorted, w->t_idx, w->t_idx_sorted, ntot, 0, 32, st));
   if (n > 0)
@@ -1309,6 +1430,19 @@ int topo_apply(gbp_world *w, const int64_t (*hdr)[4]) {
     if (n > 0)
       gbp::k_sendlist_fill<<<blocks_for(int64_t(ws) * n, 256), 256, 0, st>>>(ws, n, w->t_sflag, w->t_soff, w->sendlist);
     w->launches += 3;
+    // border robots = the union of the send lists (a robot next to two peers is listed twice)
+    const int64_t nsend = w->tp.send_po.start[ws];
+    if (int rc = ensure_buf(w, w->border_list, w->border_cap, std::max<int64_t>(nsend, 1))) return rc;
+    if (int rc = ensure_buf(w, w->border_words, w->border_words_cap, (int64_t(s.cap) + 3) / 4 + 1)) return rc;
+    if (!w->border_count) CK(dalloc(w->border_count, 1));
+    CK(cudaMemsetAsync(w->border_words, 0, size_t(w->border_words_cap) * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(w->border_count, 0, sizeof(int32_t), st));
+    if (nsend > 0) {
+      gbp::k_border_list<<<blocks_for(nsend, 256), 256, 0, st>>>(nsend, w->sendlist, w->border_words, w->border_list,
+                                                               w->border_count);
+      w->launches += 1;
+    }
+    w->n_border_max = nsend;
   }
   CK(cudaGetLastError());
   if (n > 0) {
@@ -1333,18 +1467,19 @@ int topo_apply(gbp_world *w, const int64_t (*hdr)[4]) {
 int group_update_topology(gbp_group *g) {
   const int ws = g->ws;
   if (ws > 1 && !g->committed) return fail(GBP_ERR_STATE, "sharded world: call gbp_world_commit_shards first");
+  if (int rc = group_halo_join(g)) return rc;
   ProfileScope ps(g->members[0], GBP_PROFILE_TOPOLOGY);
   const size_t nm = g->members.size();
   std::vector<gbp::XferPlan> plans(nm);
   if (ws > 1) {
-    // every shard learns every robot's Transform (x, z) and radius: 12 bytes per robot per tick
+    // every shard learns every robot's Transform (x, z), radius and despawned flag: 16 bytes per robot per tick
     for (size_t m = 0; m < nm; ++m) {
       gbp_world *w = g->members[m];
       CK(cudaSetDevice(w->device));
       Store &s = w->s;
       const int rank = w->sh.rank, ntot = w->Ntot, n = s.Nloc, g0 = w->sh.gfirst[rank];
-      const float *src[3] = {s.pos, s.pos + s.cap, s.radius};
-      for (int k = 0; k < 3; ++k) {
+      const float *src[4] = {s.pos, s.pos + s.cap, s.radius, s.gone};
+      for (int k = 0; k < 4; ++k) {
         if (n > 0)
           CK(cudaMemcpyAsync(w->gpos + int64_t(k) * ntot + g0, src[k], size_t(n) * 4, cudaMemcpyDeviceToDevice, w->stream));
         for (int q = 0; q < ws; ++q) {
@@ -1423,10 +1558,10 @@ int group_commit(gbp_group *g) {
     if (tot > INT32_MAX) return fail(GBP_ERR_BAD_ARGUMENT, "more than 2^31 robots");
     w->sh.gfirst[ws] = int32_t(tot);
     w->Ntot = int32_t(tot);
-    if (ws > 1 && 3 * tot > w->gpos_cap) {
+    if (ws > 1 && 4 * tot > w->gpos_cap) {
       cudaFree(w->gpos);
-      CK(dalloc(w->gpos, size_t(3 * tot)));
-      w->gpos_cap = 3 * tot;
+      CK(dalloc(w->gpos, size_t(4 * tot)));
+      w->gpos_cap = 4 * tot;
     }
     if (w->s.Nloc > 0) {
       k_iota_gid<<<blocks_for(w->s.Nloc, 256), 256, 0, w->stream>>>(w->s.gid, w->sh.gfirst[w->sh.rank], w->s.Nloc);
@@ -1521,6 +1656,15 @@ gbp_world *make_world(const gbp_config_t *cfg, int32_t device, cudaStream_t shar
 }
 
 void join_group(gbp_world *w, gbp_group *g, int rank) {
+  // NCCL groups: a second stream carries every transfer; in-process shards share one stream for everything
+  w->comm_stream = w->stream;
+  if (g->nccl) {
+    cudaSetDevice(w->device);
+    cudaStreamCreateWithFlags(&w->comm_stream, cudaStreamNonBlocking);
+  }
+  cudaEventCreateWithFlags(&w->ev_border, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&w->ev_halo, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&w->ev_fence, cudaEventDisableTiming);
   w->grp = g;
   w->sh.ws = g->ws;
   w->sh.rank = rank;
@@ -1614,10 +1758,19 @@ void gbp_world_destroy(gbp_world_t *w) {
   free_edge_set(w, &w->edges[0]);
   free_edge_set(w, &w->edges[1]);
   cudaFree(w->dyn_tab_dev);
+  if (w->comm_stream && w->comm_stream != w->stream) {
+    cudaStreamSynchronize(w->comm_stream);
+    cudaStreamDestroy(w->comm_stream);
+  }
+  for (cudaEvent_t e : {w->ev_border, w->ev_halo, w->ev_fence})
+    if (e) cudaEventDestroy(e);
+  cudaFree(w->border_list);
+  cudaFree(w->border_words);
+  cudaFree(w->border_count);
   void *ptrs[] = {s.prior_eta, s.prior_lam, s.pub[0], s.pub[1], s.pub_epoch[0], s.pub_epoch[1], s.bel_ext,
                   s.mu_ext, s.cov, s.valid, s.cov_lazy, s.mode, s.gen_list, s.gen_count, s.m_dynL[0], s.m_dynL[1], s.m_dynR[0], s.m_dynR[1], s.m_obs, s.m_trk, s.dyn_c,
                   s.trk_record, s.trk_timeout, s.trk_seed, s.trk_last, s.trk_value, s.radius, s.t0, s.pos, s.antenna,
-                  s.idle, s.finished, s.latest, s.iter_factor, s.gid, s.next_wp, s.coll_hits, w->coll_totals, s.wp_off, s.wp_xy, s.eoff,
+                  s.idle, s.finished, s.gone, s.latest, s.iter_factor, s.gid, s.next_wp, s.coll_hits, w->coll_totals, s.wp_off, s.wp_xy, s.eoff,
                   s.nlow, w->t_nlow, w->t_result_dev, w->sdf_dev, w->t_cx,
                   w->t_cz, w->t_idx, w->t_idx_sorted, w->t_keys, w->t_keys_sorted, w->t_cnt, w->t_off,
                   w->t_newcnt, w->t_newoff, w->t_cub, w->rb_dev, w->gpos, w->t_gflag, w->t_gslot, w->t_sflag,
@@ -1919,6 +2072,7 @@ int gbp_world_add_robots(gbp_world_t *w, int32_t n, const float *radii, const ui
   }
   CK(cudaMemsetAsync(s.idle + N0, 0, size_t(n), st));
   CK(cudaMemsetAsync(s.finished + N0, 0, size_t(n), st));
+  CK(cudaMemsetAsync(s.gone + N0, 0, size_t(n) * sizeof(float), st));
   CK(cudaMemsetAsync(s.latest + N0, 0, size_t(n), st));
   CK(cudaMemsetAsync(s.iter_factor + N0, 0, size_t(n) * sizeof(uint32_t), st));
   CK(cudaMemsetAsync(s.mode + N0, 1, size_t(n), st));  // k_iterate hands a robot to k_iterate_axis once it qualifies
@@ -2056,7 +2210,51 @@ int gbp_world_set_comms(gbp_world_t *w, const uint8_t *antenna_active, const uin
   } else {
     CK(cudaMemsetAsync(w->s.idle, 0, n, w->stream));
   }
+  if (w->any_gone) {
+    k_keep_gone_idle<<<blocks_for(n, 256), 256, 0, w->stream>>>(w->s);
+    CK(cudaGetLastError());
+    w->launches += 1;
+  }
   mark_halo_stale(w);  // antenna / idle bits travel with the halo
+  return 0;
+}
+
+int gbp_world_remove_robots(gbp_world_t *w, int32_t m, const int32_t *robots) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (m < 0 || (m > 0 && !robots)) return fail(GBP_ERR_BAD_ARGUMENT, "gbp_world_remove_robots: null list");
+  if (set_device(w)) return GBP_ERR_CUDA;
+  for (int k = 0; k < m; ++k)
+    if (robots[k] < 0 || robots[k] >= w->s.Nloc)
+      return fail(GBP_ERR_BAD_ARGUMENT, "gbp_world_remove_robots: robot index out of range");
+  if (m == 0) return 0;
+  w->gone_host.resize(size_t(w->s.Nloc), 0);
+  for (int k = 0; k < m; ++k)
+    if (!w->gone_host[robots[k]]) {
+      w->gone_host[robots[k]] = 1;
+      w->n_gone += 1;
+    }
+  if (int rc = ensure_scratch(w, size_t(m) * sizeof(int32_t))) return rc;
+  CK(cudaMemcpyAsync(w->rb_dev, robots, size_t(m) * sizeof(int32_t), cudaMemcpyHostToDevice, w->stream));
+  k_remove_robots<<<blocks_for(m, 256), 256, 0, w->stream>>>(w->s, m, static_cast<const int32_t *>(w->rb_dev));
+  CK(cudaGetLastError());
+  w->launches += 1;
+  CK(cudaStreamSynchronize(w->stream));  // the caller's list may go away
+  w->any_gone = true;
+  mark_halo_stale(w);
+  return 0;
+}
+
+int gbp_world_read_removed(gbp_world_t *w, uint8_t *removed) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (!removed) return fail(GBP_ERR_BAD_ARGUMENT, "null output");
+  if (set_device(w)) return GBP_ERR_CUDA;
+  const int n = w->s.Nloc;
+  std::vector<float> h(size_t(n), 0.0f);
+  if (n > 0) {
+    CK(cudaMemcpyAsync(h.data(), w->s.gone, size_t(n) * sizeof(float), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+  }
+  for (int r = 0; r < n; ++r) removed[r] = h[r] != 0.0f ? 1 : 0;
   return 0;
 }
 
@@ -2096,6 +2294,7 @@ int gbp_world_update_robot_collisions(gbp_world_t *w0, int64_t *num_collisions, 
   if (!w0) return fail(GBP_ERR_BAD_HANDLE, "null world");
   gbp_group *g = w0->grp;
   // ghosts must sit at their current Transform: the halo carries it
+  if (int rc = group_halo_join(g)) return rc;
   if (g->ws > 1 && g->halo_stale) {
     if (int rc = group_halo(g)) return rc;
   }
@@ -2504,6 +2703,27 @@ int64_t gbp_world_read_connections(gbp_world_t *w, int64_t *offsets, int32_t *ne
   return s.E;
 }
 
+int gbp_world_read_tracking(gbp_world_t *w, int64_t *record, float *last_pos, double *last_value) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (!record || !last_pos || !last_value) return fail(GBP_ERR_BAD_ARGUMENT, "null output");
+  if (set_device(w)) return GBP_ERR_CUDA;
+  const int64_t nv = int64_t(w->s.Nloc) * w->s.V;
+  if (nv == 0) return 0;
+  const size_t bytes = size_t(nv) * (sizeof(int64_t) + sizeof(double) + 2 * sizeof(float));
+  if (int rc = ensure_scratch(w, bytes)) return rc;
+  int64_t *d_rec = static_cast<int64_t *>(w->rb_dev);
+  double *d_val = reinterpret_cast<double *>(d_rec + nv);
+  float *d_pos = reinterpret_cast<float *>(d_val + nv);
+  k_gather_tracking<<<blocks_for(nv, 256), 256, 0, w->stream>>>(w->s, nv, d_rec, d_pos, d_val);
+  CK(cudaGetLastError());
+  w->launches += 1;
+  CK(cudaMemcpyAsync(record, d_rec, size_t(nv) * sizeof(int64_t), cudaMemcpyDeviceToHost, w->stream));
+  CK(cudaMemcpyAsync(last_value, d_val, size_t(nv) * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+  CK(cudaMemcpyAsync(last_pos, d_pos, size_t(nv) * 2 * sizeof(float), cudaMemcpyDeviceToHost, w->stream));
+  CK(cudaStreamSynchronize(w->stream));
+  return 0;
+}
+
 int gbp_world_sdf_lookup(gbp_world_t *w, int32_t m, const double *xy, uint32_t *px, uint32_t *py, double *value) {
   if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
   if (m < 0 || (m > 0 && (!xy || !px || !py || !value))) return fail(GBP_ERR_BAD_ARGUMENT, "null argument");
@@ -2555,7 +2775,7 @@ int gbp_world_read_iterate_path(gbp_world_t *w, int64_t *robots_axis, int64_t *r
 
 int gbp_world_node_counts(gbp_world_t *w, int64_t out[5]) {
   if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
-  const int64_t n = w->s.Nloc, V = w->s.V;
+  const int64_t n = int64_t(w->s.Nloc) - w->n_gone, V = w->s.V;  // despawned robots took their graphs with them
   out[0] = n * V;
   out[1] = n * (V - 1);
   out[2] = n * (V - 2);

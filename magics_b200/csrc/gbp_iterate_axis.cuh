@@ -49,6 +49,10 @@ constexpr int kAxisEdges = 32;
 #define GBP_AXIS_BATCH 2  // edges whose neighbour loads a lane has in flight at once (4: spills, 10 % slower)
 #endif
 constexpr int kAxisBatch = GBP_AXIS_BATCH;
+#ifndef GBP_AXIS_PREFETCH
+#define GBP_AXIS_PREFETCH 0  // CTAs ahead whose wave-1 rows this CTA pulls into L2 (592 = 148 SMs x 4 resident CTAs:
+                             // +1.5 % DRAM bytes, no time gained — profiles/README.md r02e/r02f; off)
+#endif
 
 struct AxisGeom {
   int rpc;      // robots per CTA
@@ -115,15 +119,24 @@ GBP_DEV void st_axis(double *__restrict__ arr, AxisRows q, const double (&e)[2],
 //   2. the robot's edge heads, one edge per lane, into shared memory (one __syncthreads);
 //   3. per lane, for kAxisBatch of its edges at once, what hangs off the neighbour slot: radio / idle
 //      bits, the neighbour variable's position mean and record epoch.
-template <bool EXT, bool INT>
+//
+// Which robots a launch covers (multi-GPU): PART 0: slots [0, Nloc); PART 2: the same except
+// those flagged in `skip` (the interior robots of a shard); PART 1: the *nlist robots of `list` (the border robots,
+// whose records the peers wait for: they run first and their halo travels while the interior launch runs).
+// PART is a template parameter: the single-GPU launch (PART 0) must not pay for the other two (measured: 4 %).
+template <bool EXT, bool INT, int PART>
 __global__ void __maxnreg__(GBP_AXIS_MAXREG)
-    k_iterate_axis(const __grid_constant__ Store s, const int p, const uint32_t epoch, const int rpc, const int par) {
+    k_iterate_axis(const __grid_constant__ Store s, const int p, const uint32_t epoch, const int rpc, const int par,
+                   const int32_t *__restrict__ list, const int32_t *__restrict__ nlist,
+                   const uint8_t *__restrict__ skip) {
   extern __shared__ double sh[];
   const int T = blockDim.x, V = s.V;
   const int t = threadIdx.x, a = t & 1, slot = t >> 1;
   const int rl = slot / V, i = slot - rl * V;
-  const int64_t r = int64_t(blockIdx.x) * rpc + rl;
-  const bool live = rl < rpc && r < s.Nloc;
+  const int64_t ridx = int64_t(blockIdx.x) * rpc + rl;
+  bool live = rl < rpc && ridx < (PART == 1 ? int64_t(*nlist) : int64_t(s.Nloc));
+  const int64_t r = live ? (PART == 1 ? int64_t(list[ridx]) : ridx) : 0;
+  if (PART == 2 && live && skip[r]) live = false;
   const int64_t vi = live ? r * V + i : 0;
   double *const xr = sh;                             // [6][T] variable -> Dynamic factor i   (its right-hand factor)
   double *const xl = sh + 6 * T;                     // [6][T] variable -> Dynamic factor i-1 (its left-hand factor)
@@ -141,6 +154,42 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
   double *const pubw = s.pub[1 - p];
   const AxisRows qp = axis_rows<kRec>(s, a, vi), qm = axis_rows<20>(s, a, vi);
 
+#if GBP_AXIS_PREFETCH > 0
+  // The CTA that will take this one's place on the SM finds its wave-1 rows in L2 (contiguous launches only: CTAs
+  // are dispatched in blockIdx order, GBP_AXIS_PREFETCH of them are resident at a time).
+  if (PART != 1 && rl < rpc) {
+    const int64_t rn = ridx + int64_t(GBP_AXIS_PREFETCH) * rpc;
+    if (rn < s.Nloc) {
+      const int64_t vn = rn * V + i;
+      const AxisRows pp = axis_rows<kRec>(s, a, vn), pm = axis_rows<20>(s, a, vn);
+      const double *const rec = s.pub[p];
+      if (INT) {
+        prefetch_l2(rec + pp.v);
+        prefetch_l2(rec + pp.v + 2 * kTile);
+        prefetch_l2(rec + pp.m);
+        prefetch_l2(rec + pp.m + 2 * kTile);
+        prefetch_l2(rec + pp.m + 8 * kTile);
+        prefetch_l2(rec + pp.m + 10 * kTile);
+      }
+      prefetch_l2(rec + pp.v + 20 * kTile);
+      prefetch_l2(rec + pp.v + 22 * kTile);
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        const double *const m = side ? s.m_dynR[p] : s.m_dynL[p];
+        prefetch_l2(m + pm.v);
+        prefetch_l2(m + pm.v + 2 * kTile);
+        prefetch_l2(m + pm.m);
+        prefetch_l2(m + pm.m + 2 * kTile);
+        prefetch_l2(m + pm.m + 8 * kTile);
+        prefetch_l2(m + pm.m + 10 * kTile);
+      }
+      prefetch_l2(s.prior_eta + s.at<4>(a, vn));
+      prefetch_l2(s.prior_eta + s.at<4>(a + 2, vn));
+      if (a == 0) prefetch_l2(s.prior_lam + vn);
+      if (EXT) prefetch_l2(s.mu_ext + s.at<2>(a, vn));
+    }
+  }
+#endif
   // ---- wave 1 ---------------------------------------------------------------------------------
   bool was_general = false, idle = true, ant = false, latest = false;
   uint32_t itf = 0u;

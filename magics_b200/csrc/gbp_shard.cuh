@@ -114,6 +114,18 @@ __global__ void k_sendlist_fill(int32_t ws, int32_t nloc, const int32_t *__restr
   if (sflag[t]) sendlist[soff[t]] = int32_t(t % nloc);
 }
 
+// Union of the per-peer send lists: flags (one byte per own robot, set through its word) and a list without
+// duplicates (any order) — the robots whose internal half runs first so that their records can travel while
+// the other robots are iterated (group_launch).
+__global__ void k_border_list(int64_t nsend, const int32_t *__restrict__ sendlist, uint32_t *words, int32_t *list,
+                              int32_t *count) {
+  const int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j >= nsend) return;
+  const int32_t r = sendlist[j];
+  const uint32_t bit = 1u << (8 * (r & 3));
+  if (!(atomicOr(&words[r >> 2], bit) & bit)) list[atomicAdd(count, 1)] = r;
+}
+
 // Neighbour global id -> slot (own: gid - g0; ghost: Nloc + rank among ghosts).
 __global__ void k_edge_slots(int64_t E, int32_t g0, int32_t nloc, const int32_t *__restrict__ ngid,
                              const int32_t *__restrict__ gslot, int32_t *enbr) {

@@ -90,6 +90,8 @@ struct Store {
   uint8_t *antenna;       // [cap]     RadioAntenna.active
   uint8_t *idle;          // [cap]     mission.state.idle()
   uint8_t *finished;      // [cap]     FinishedPath
+  float *gone;            // [cap]     1.0f: the robot's entity has been despawned (gbp_world_remove_robots): it no longer
+                          //           appears in the neighbour search and is never iterated; its slot keeps its last state
   uint8_t *latest;        // [cap]     0: pub[p] holds the current belief, 1: bel_ext
   uint32_t *iter_factor;  // [cap]     FactorGraph.iteration_count.factor
   uint8_t *mode;          // [cap]     0: the robot's x and y chains are decoupled, k_iterate_axis iterates it;

@@ -40,11 +40,17 @@ __device__ __forceinline__ bool within_comms(float ax, float az, float bx, float
   return !(R < d);
 }
 
+// Cell of a despawned robot (gone[r] != 0): no query ever visits it, and its own query is skipped — the
+// reference's update_robot_neighbours only iterates entities that still exist (robot.rs:1362-1384).
+constexpr int32_t kNoCell = INT32_MIN;
+
 __global__ void k_cell_keys(int32_t n, const float *__restrict__ px, const float *__restrict__ pz,
-                            double cell, int32_t *cx, int32_t *cz, uint32_t *keys, int32_t *idx) {
+                            const float *__restrict__ gone, double cell, int32_t *cx, int32_t *cz, uint32_t *keys,
+                            int32_t *idx) {
   const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
-  const int32_t x = int32_t(floor(double(px[r]) / cell)), z = int32_t(floor(double(pz[r]) / cell));
+  int32_t x = int32_t(floor(double(px[r]) / cell)), z = int32_t(floor(double(pz[r]) / cell));
+  if (gone && gone[r] != 0.0f) x = z = kNoCell;
   cx[r] = x;
   cz[r] = z;
   keys[r] = cell_hash(x, z);
@@ -78,7 +84,7 @@ __global__ void k_neighbours(int32_t nall, int32_t first, int32_t count, const f
   const int32_t mx = cx[r], mz = cz[r];
   int64_t n = 0;
   const int64_t base = FILL ? cnt_or_off[t] : 0;
-  for (int dz = -1; dz <= 1; ++dz)
+  for (int dz = -1; dz <= 1 && mx != kNoCell; ++dz)
     for (int dx = -1; dx <= 1; ++dx) {
       const int32_t qx = mx + dx, qz = mz + dz;
       const uint32_t key = cell_hash(qx, qz);

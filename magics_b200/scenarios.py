@@ -230,3 +230,88 @@ def complex_environment(n=19, seed=0):
     goals = np.stack([-side * 118.0, y[::-1]], axis=1).astype(f32)
     sdf = synthetic_sdf(2000, 1400, seed=seed, n_rect=40, blur_px=4.0)
     return _finish(cfg, np.full(n, 1.0, f32), starts, goals, ts, 5.0, sdf=sdf, name=f"complex-{n}")
+
+
+# ---- the reference's own scenario inputs (BASELINE configs 1-3) -------------------------------------------
+_SCHEDULES = {"centered": 0, "interleave-evenly": 1, "soon-as-possible": 2, "late-as-possible": 3,
+              "half-beginning-half-end": 4}
+
+
+class ReferenceScenario:
+    """One of the reference's `config/scenarios/<name>/` directories, as extracted into tests/golden/scenarios.json by
+    tests/golden/make_golden.py: the formation group (`formation.yaml`), the environment (`environment.yaml`) and the
+    [gbp] / [robot] scalars of `config.toml`.  It plays the roles of `spawn_formation` (spawner.rs:415-600) and of the
+    FormationSpawner clock for a run at the scenario's fixed rate: `spawn_events` says which formation spawns at
+    which tick, `spawn` turns one formation into the arrays `World.add_robots` / the oracle take.
+
+    Inputs the reference draws from its PRNG (robot radii in [radius.min, radius.max], random placement along a line
+    segment) come from the numpy Generator passed to `spawn`."""
+
+    def __init__(self, name: str, golden_path: str | None = None):
+        import json
+        import os
+
+        from .environment import Environment, Obstacle
+        from .formation import formation_from_dict
+
+        path = golden_path or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                                           "scenarios.json")
+        d = json.load(open(path))[name]
+        self.name = name
+        e = dict(d["environment"])
+        e["obstacles"] = [Obstacle(**{k: (tuple(map(tuple, v)) if k == "points" else tuple(v) if isinstance(v, list) else v)
+                                      for k, v in o.items()}) for o in e.get("obstacles") or []]
+        self.env = Environment(**e)
+        self.formations = [formation_from_dict(f) for f in d["formations"]]
+        g, r = d["gbp"], d["robot"]
+        en = g.get("factors-enabled", {})
+        it = g.get("iteration-schedule", {})
+        self.world_w, self.world_h = self.env.world_size
+        self.hz = float(d["simulation"]["hz"])
+        self.despawn = bool(d["simulation"]["despawn-robot-when-final-waypoint-reached"])
+        self.planning_horizon = float(r["planning-horizon"])
+        self.lookahead_multiple = int(g.get("lookahead-multiple", 3))
+        self.radius_range = (float(r["radius"]["min"]), float(r["radius"]["max"]))
+        trk = g.get("tracking", {})
+        cfg = GbpConfig(
+            sigma_factor_dynamics=float(g["sigma-factor-dynamics"]), sigma_factor_interrobot=float(g["sigma-factor-interrobot"]),
+            sigma_factor_obstacle=float(g["sigma-factor-obstacle"]), sigma_factor_tracking=float(g["sigma-factor-tracking"]),
+            safety_distance_multiplier=float(r["inter-robot-safety-distance-multiplier"]),
+            comms_radius=float(r["communication"]["radius"]), target_speed=float(r["target-speed"]),
+            delta_t=1.0 / self.hz, tracking_switch_padding=float(trk.get("switch-padding", 1.0)),
+            tracking_attraction_distance=float(trk.get("attraction-distance", 2.0)),
+            enable_dynamic=int(en.get("dynamic", True)), enable_interrobot=int(en.get("interrobot", True)),
+            enable_obstacle=int(en.get("obstacle", True)), enable_tracking=int(en.get("tracking", False)),
+            schedule_kind=_SCHEDULES[it.get("schedule", "interleave-evenly")], iterations_internal=int(it.get("internal", 10)),
+            iterations_external=int(it.get("external", 10)), world_width=self.world_w, world_height=self.world_h)
+        self.timesteps = get_variable_timesteps(lookahead_horizon(cfg.target_speed, self.planning_horizon),
+                                                self.lookahead_multiple)
+        self.cfg = replace(cfg, num_variables=int(self.timesteps.shape[0]))
+        crit = {(f.reached_when, f.finished_when) for f in self.formations}
+        # gbp_world_reached_waypoint takes one criterion pair per call; the shipped scenarios use one per group
+        self.reached_when, self.finished_when = next(iter(crit)) if len(crit) == 1 else (None, None)
+
+    def spawn_events(self, ticks: int) -> list[tuple[int, int]]:
+        """(tick, formation index) of every spawn in the first `ticks` fixed steps, in time then formation order."""
+        ev = []
+        for k, f in enumerate(self.formations):
+            for t in f.spawn_times(ticks / self.hz):
+                tick = int(np.ceil(t * self.hz - 1e-9))
+                if tick < ticks:
+                    ev.append((tick, k))
+        return sorted(ev)
+
+    def spawn(self, formation_index: int, rng) -> Swarm | None:
+        """spawn_formation for one event: radii, Formation::as_positions, the route of every robot."""
+        from .formation import as_positions, routes
+
+        f = self.formations[formation_index]
+        lo, hi = self.radius_range
+        radii = np.asarray([f32(lo) if lo == hi else f32(rng.uniform(lo, hi)) for _ in range(f.robots)], f32)
+        placed = as_positions(f, self.world_w, self.world_h, radii, rng)
+        if placed is None:
+            return None  # "failed to spawn formation ..., skipping" (spawner.rs:460-468)
+        init, wps = placed
+        r = routes(init, wps)
+        return _finish(self.cfg, radii, init, np.stack([w[1] for w in r]).astype(f32), self.timesteps,
+                       self.planning_horizon, sdf=None, name=f"{self.name}[{formation_index}]", waypoints=r)

@@ -161,6 +161,20 @@ class LocalShards:
             m = (robots >= lo) & (robots < hi)
             w.change_prior_of_variable(variable_index, (robots[m] - lo).astype(np.int32), new_means[m])
 
+    def remove_robots(self, robots):
+        robots = np.asarray(robots, np.int64)
+        for q, w in enumerate(self.shards):
+            lo, hi = self.bounds[q], self.bounds[q + 1]
+            m = (robots >= lo) & (robots < hi)
+            w.remove_robots((robots[m] - lo).astype(np.int32))
+
+    def read_removed(self):
+        return np.concatenate([w.read_removed() for w in self.shards])
+
+    def read_tracking(self):
+        parts = [w.read_tracking() for w in self.shards]
+        return tuple(np.concatenate([p[k] for p in parts], axis=0) for k in range(3))
+
     def iterate(self):
         self.shards[0].iterate()
 

@@ -384,6 +384,25 @@ class World:
         self._call("gbp_world_read_positions", _p(xy, C.c_float))
         return xy
 
+    def remove_robots(self, robots):
+        """RobotDespawned: the robots leave the simulation (their slots stay, frozen)."""
+        robots = np.ascontiguousarray(robots, np.int32)
+        self._call("gbp_world_remove_robots", C.c_int32(robots.shape[0]), _p(robots, C.c_int32))
+
+    def read_removed(self):
+        out = np.zeros(self.num_robots, np.uint8)
+        self._call("gbp_world_read_removed", _p(out, C.c_uint8))
+        return out
+
+    def read_tracking(self):
+        """(record (n, V) i64, last_pos (n, V, 2) f32, last_value (n, V) f64) of every Tracking factor."""
+        n, V = self.num_robots, self.V
+        rec = np.zeros((n, V), np.int64)
+        pos = np.zeros((n, V, 2), np.float32)
+        val = np.zeros((n, V), np.float64)
+        self._call("gbp_world_read_tracking", _p(rec, C.c_int64), _p(pos, C.c_float), _p(val, C.c_double))
+        return rec, pos, val
+
     def read_connections(self):
         n = self.num_robots
         counts = self.node_counts()

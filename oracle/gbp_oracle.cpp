@@ -690,6 +690,7 @@ struct Robot {
   float radius, t0;
   float pos[2];  // Transform.translation.x / .z
   bool antenna = true, idle = false, finished = false;
+  bool gone = false;  // the entity has been despawned (RobotDespawned, robot.rs:2171-2172): no query yields it any more
   std::set<int> within, connected;  // RobotConnections
   std::vector<std::pair<float, float>> waypoints;
   int next_wp = 1;
@@ -800,8 +801,9 @@ void update_neighbours(World &w) {
   parallel_for(n, w.threads, 64, [&](int a) {
     Robot &ra = w.robots[a];
     ra.within.clear();
+    if (ra.gone) return;  // not in the query
     for (int b = 0; b < n; ++b) {
-      if (b == a) continue;
+      if (b == a || w.robots[b].gone) continue;
       float dx = ra.pos[0] - w.robots[b].pos[0];
       float dy = 0.0f;
       float dz = ra.pos[1] - w.robots[b].pos[1];
@@ -836,6 +838,10 @@ void delete_ir_connected_to(Graph &g, int other) {
 void delete_interrobot_factors(World &w) {
   std::vector<std::pair<int, int>> pairs;
   for (auto &r : w.robots) {
+    if (r.gone) {  // despawned with its RobotConnections; its graph is never looked at again
+      r.connected.clear();
+      continue;
+    }
     std::vector<int> lost;
     for (int c : r.connected)
       if (!r.within.count(c)) lost.push_back(c);
@@ -846,7 +852,8 @@ void delete_interrobot_factors(World &w) {
   }
   for (auto &p : pairs) {
     delete_ir_connected_to(w.robots[p.first].g, p.second);
-    delete_ir_connected_to(w.robots[p.second].g, p.first);
+    // query.get_mut(robot2) fails for a despawned robot (robot.rs:1428-1437: error!, nothing deleted)
+    if (!w.robots[p.second].gone) delete_ir_connected_to(w.robots[p.second].g, p.first);
   }
 }
 
@@ -949,7 +956,7 @@ void world_internal(World &w, bool factors, bool variables) {
   // query.par_iter_mut() (robot.rs:1789-1800): threads over robots
   parallel_for(n, w.threads, 16, [&](int i) {
     Robot &r = w.robots[i];
-    if (r.idle) return;
+    if (r.idle || r.gone) return;
     if (factors) internal_factor_iteration(r.g);
     if (variables) internal_variable_iteration(r.g);
   });
@@ -957,24 +964,24 @@ void world_internal(World &w, bool factors, bool variables) {
 void world_external_factor(World &w) {  // robot.rs:1803-1831 (single thread)
   std::vector<Routed> msgs;
   for (auto &r : w.robots) {
-    if (!r.antenna || r.idle) continue;
+    if (!r.antenna || r.idle || r.gone) continue;
     external_factor_iteration(r.g, msgs);
   }
   for (auto &m : msgs) {
     Robot &t = w.robots[m.to.first];
-    if (!t.antenna || t.idle) continue;
+    if (!t.antenna || t.idle || t.gone) continue;  // gone: query.get_mut fails (robot.rs:1815-1819, 1844-1848)
     t.g.vars[m.to.second].inbox[m.from] = m.m;
   }
 }
 void world_external_variable(World &w) {  // robot.rs:1833-1858 (single thread)
   std::vector<Routed> msgs;
   for (auto &r : w.robots) {
-    if (!r.antenna || r.idle) continue;
+    if (!r.antenna || r.idle || r.gone) continue;
     external_variable_iteration(r.g, msgs);
   }
   for (auto &m : msgs) {
     Robot &t = w.robots[m.to.first];
-    if (!t.antenna || t.idle) continue;
+    if (!t.antenna || t.idle || t.gone) continue;  // gone: query.get_mut fails (robot.rs:1815-1819, 1844-1848)
     auto it = t.g.factors.find(m.to.second);
     if (it != t.g.factors.end()) factor_receive(it->second, m.from, m.m);
   }
@@ -1430,6 +1437,16 @@ int gbpo_set_comms(void *p, const uint8_t *antenna, const uint8_t *idle) {
   }
   return 0;
 }
+// RobotDespawned: the entity (FactorGraph, RobotConnections, Transform) is gone.
+int gbpo_remove_robots(void *p, int m, const int32_t *robots) {
+  World *w = static_cast<World *>(p);
+  for (int k = 0; k < m; ++k) {
+    if (robots[k] < 0 || size_t(robots[k]) >= w->robots.size()) return -1;
+    w->robots[robots[k]].gone = true;
+  }
+  return 0;
+}
+
 int gbpo_set_waypoint_index(void *p, const int32_t *idx) {
   World *w = static_cast<World *>(p);
   for (size_t i = 0; i < w->robots.size(); ++i) w->robots[i].next_wp = idx[i];
@@ -1466,7 +1483,7 @@ int gbpo_update_prior_of_horizon_state(void *p) {
   double max_speed = double(w->cfg.target_speed);
   std::vector<Routed> deferred;
   for (auto &r : w->robots) {
-    if (r.finished || r.idle) continue;
+    if (r.finished || r.idle || r.gone) continue;
     if (r.next_wp < 0 || r.next_wp >= int(r.waypoints.size())) {
       r.finished = true;
       continue;
@@ -1497,6 +1514,7 @@ int gbpo_reached_waypoint(void *p, const int32_t *crit, const float *meters, uin
   for (size_t k = 0; k < w->robots.size(); ++k) {
     Robot &r = w->robots[k];
     if (out_reached) out_reached[k] = 0;
+    if (r.gone) continue;
     const int nwp = int(r.waypoints.size());
     if (r.next_wp < 0 || r.next_wp >= nwp) continue;  // mission.next_waypoint() is None
     const bool last = r.next_wp == nwp - 1;
@@ -1527,6 +1545,7 @@ int gbpo_update_robot_collisions(void *p, int64_t *num_collisions, int64_t *coll
   for (int r = 0; r < n; ++r)
     for (int c = r + 1; c < n; ++c) {
       const Robot &a = w->robots[r], &b = w->robots[c];
+      if (a.gone || b.gone) continue;  // the query iterates living entities only
       const float dx = b.pos[0] - a.pos[0], dz = b.pos[1] - a.pos[1];
       const float d2 = dx * dx + dz * dz;
       const float sr = a.radius + b.radius;
@@ -1557,7 +1576,7 @@ int gbpo_update_prior_of_current_state(void *p) {
   World *w = static_cast<World *>(p);
   std::vector<Routed> deferred;
   for (auto &r : w->robots) {
-    if (r.idle) continue;
+    if (r.idle || r.gone) continue;
     float time_scale = w->cfg.delta_t / r.t0;
     Variable &c = r.g.vars[0];
     Variable &nx = r.g.vars[1];
@@ -1750,6 +1769,7 @@ int gbpo_node_counts(void *p, int64_t out[5]) {
   World *w = static_cast<World *>(p);
   for (int i = 0; i < 5; ++i) out[i] = 0;
   for (auto &r : w->robots) {
+    if (r.gone) continue;  // despawned with its FactorGraph component
     out[0] += int64_t(r.g.vars.size());
     for (auto &kv : r.g.factors) {
       switch (kv.second.kind) {

@@ -187,6 +187,10 @@ class OracleWorld:
         i = None if idle is None else np.ascontiguousarray(idle, np.uint8)
         self._call("gbpo_set_comms", _p(a, C.c_uint8), _p(i, C.c_uint8))
 
+    def remove_robots(self, robots):
+        robots = np.ascontiguousarray(robots, np.int32)
+        self._call("gbpo_remove_robots", int(robots.shape[0]), _p(robots, C.c_int32))
+
     def set_waypoint_index(self, idx):
         idx = np.ascontiguousarray(idx, np.int32)
         self._call("gbpo_set_waypoint_index", _p(idx, C.c_int32))

@@ -11,6 +11,9 @@ Sources (all `#[cfg(test)]` blocks of the reference):
                                               -> marginalise.json
   crates/env_to_png/src/lib.rs:482-533 (tests) and config/scenarios/*/environment.yaml
                                               -> env_to_png.json
+  config/scenarios/{Circle Experiment, Structured Junction Twoway, Collaborative Complex}/
+      {formation.yaml, environment.yaml, config.toml}   (BASELINE configs 1-3: the scenario INPUT data)
+                                              -> scenarios.json
 """
 import json
 import os
@@ -126,7 +129,44 @@ def env_to_png():
     return {"kats": kats, "environments": envs, "environments_with_obstacles": placed}
 
 
+def scenarios():
+    """The input files of the three BASELINE scenarios, as plain data: the formation group (parsed YAML with serde's
+    tags kept as {"kind": tag, ...}), the environment (same form as env_to_png.json) and the scalars of config.toml
+    the hot path reads ([gbp], [robot], [simulation].hz / despawn flag)."""
+    import sys
+    import tomllib
+    from dataclasses import asdict
+
+    import yaml
+
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from magics_b200.environment import Environment
+
+    class Loader(yaml.SafeLoader):
+        pass
+
+    def tagged(loader, suffix, node):
+        if isinstance(node, yaml.MappingNode):
+            return {"kind": suffix, **loader.construct_mapping(node, deep=True)}
+        if isinstance(node, yaml.SequenceNode):
+            return {"kind": suffix, "value": loader.construct_sequence(node, deep=True)}
+        return {"kind": suffix, "value": loader.construct_scalar(node)}
+
+    Loader.add_multi_constructor("!", tagged)
+    out = {}
+    for name in ("Circle Experiment", "Structured Junction Twoway", "Collaborative Complex"):
+        base = f"/root/reference/config/scenarios/{name}"
+        cfg = tomllib.load(open(f"{base}/config.toml", "rb"))
+        form = yaml.load(open(f"{base}/formation.yaml").read(), Loader=Loader)
+        env = Environment.from_yaml(open(f"{base}/environment.yaml").read())
+        out[name] = {"source": f"config/scenarios/{name}/", "formations": form["formations"], "environment": asdict(env),
+                     "gbp": cfg["gbp"], "robot": cfg["robot"],
+                     "simulation": {k: cfg["simulation"][k] for k in ("hz", "despawn-robot-when-final-waypoint-reached")}}
+    return out
+
+
 if __name__ == "__main__":
+    json.dump(scenarios(), open(os.path.join(HERE, "scenarios.json"), "w"), indent=1, ensure_ascii=False)
     json.dump(env_to_png(), open(os.path.join(HERE, "env_to_png.json"), "w"), indent=1, ensure_ascii=False)
     s = schedules()
     json.dump(s, open(os.path.join(HERE, "schedules.json"), "w"), indent=1)

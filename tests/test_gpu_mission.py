@@ -83,3 +83,38 @@ def test_robot_robot_collision_monitor(make, interrobot):
     if not interrobot:
         assert total >= 4 and seen_now >= 2, (total, seen_now)
         assert g.read_robot_collisions().sum() == 2 * total
+
+
+@pytest.mark.parametrize("make", [lambda cfg: World(cfg), lambda cfg: LocalShards(cfg, 3)], ids=["single", "ws3"])
+def test_despawn_on_final_waypoint_and_mid_run_removal(make):
+    """RobotDespawned (robot.rs:2171-2172, despawn_entity_after): a robot that completes its mission leaves the
+    simulation; the next topology pass deletes every InterRobot factor to or from it (robot.rs:1386-1439, the
+    failed `query.get_mut` branch) and nobody iterates or sees it again.  Two robots are also removed mid-run, while
+    their InterRobot factors are active."""
+    sw = scenarios.circle(10, circle_radius=9.0)
+    g, o = make(sw.cfg), OracleWorld(sw.cfg)
+    sw.add_to(g)
+    sw.add_to(o)
+    task, fin = (HORIZON, 0, RADIUS, 0.0), (CURRENT, 0, RADIUS, 0.0)
+    gone = np.zeros(sw.n, bool)
+    for tick in range(80):
+        rg, ro = g.reached_waypoint(task, fin), o.reached_waypoint(task, fin)
+        assert np.array_equal(rg, ro), f"tick {tick}: different robots reached a waypoint"
+        done = (g.read_waypoint_index() >= 2) & ~gone  # mission.is_completed()
+        if tick == 6:
+            done[[2, 7]] = True
+        if done.any():
+            ids = np.flatnonzero(done).astype(np.int32)
+            g.remove_robots(ids)
+            o.remove_robots(ids)
+            gone |= done
+        g.step()
+        o.step()
+        if tick % 8 == 0 or done.any():
+            check(g, o, f"despawn tick {tick}")
+            off = g.read_connections()[0]
+            assert (np.diff(off)[gone] == 0).all(), "a despawned robot keeps no connection"
+            assert not np.isin(g.read_connections()[1], np.flatnonzero(gone)).any(), "nobody is connected to one"
+    check(g, o, "despawn end")
+    assert np.array_equal(g.read_removed().astype(bool), gone)
+    assert gone.sum() >= 6, gone  # the two removed by hand and the robots that reached their goal

@@ -101,9 +101,18 @@ def test_junction_twoway_all_factor_kinds():
         o.step()
         if tick % 3 == 0 or tick == 15:
             check(g, o, f"junction tick {tick}")
-    for r in (0, 5):
-        for i in (1, 6, 10):
-            assert o.read_tracking(r, i) is not None
+    # Tracking factor state (tracking.rs:62-90): record counter, LastMeasurement.pos (f32) and .value, bit for bit
+    rec, pos, val = g.read_tracking()
+    moved = 0
+    for r in range(sw.n):
+        for i in range(1, sw.cfg.num_variables - 1):
+            t = o.read_tracking(r, i)
+            assert t is not None
+            assert int(rec[r, i]) == t[0], (r, i, rec[r, i], t[0])
+            assert pos[r, i].tobytes() == np.asarray(t[1], np.float32).tobytes(), (r, i, pos[r, i], t[1])
+            assert np.float64(val[r, i]).tobytes() == np.float64(t[2]).tobytes(), (r, i, val[r, i], t[2])
+            moved += int(t[2] != 0.0)
+    assert moved > 0  # the factors have run (iteration_count.factor >= 10) and measured something
 
 
 def test_complex_environment_obstacle_factors():
