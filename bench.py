@@ -147,6 +147,12 @@ def build_workload(name: str, robots: int, rank: int = 0, world: int = 1):
         ny = max(1, robots // side)
         b = partition(ny, world)
         return scenarios.lattice(side, ny, rows=(int(b[rank]), int(b[rank + 1]))), side * ny
+    if name == "dense":
+        # stress workload (scenarios.dense_lattice): active InterRobot factors, edges churning; slabs of rows like lattice
+        side = int(round(robots ** 0.5))
+        sw = scenarios.dense_lattice(side, max(1, robots // side))
+        b = partition(sw.n // side, world)
+        return (sw if world == 1 else sw.slice(int(b[rank]) * side, int(b[rank + 1]) * side)), sw.n
     raise ValueError(name)
 
 
@@ -168,6 +174,77 @@ def run_cpu(sw, threads: int, ticks: int):
     return sw.n * substeps / best, best, substeps
 
 
+def extra_point(sw, steps: int, warmup: int = 3) -> dict:
+    """One more workload on one GPU, device-timed like the headline: robots x sub-steps x steps / CUDA-event time."""
+    from magics_b200 import World, gbp_schedule
+
+    g = World(sw.cfg, device=0)
+    sw.add_to(g)
+    oi, oe = gbp_schedule(sw.cfg.schedule_kind, sw.cfg.iterations_internal, sw.cfg.iterations_external)
+    substeps = int(np.sum(oi & oe)) or int(max(oi.sum(), oe.sum()))
+    for _ in range(warmup):
+        g.step()
+    g.sync()
+    g.set_profiling(True)
+    e0 = int(g.read_connections()[0][-1])
+    g.timer_start()
+    for _ in range(steps):
+        g.step()
+    ms = g.timer_stop_ms()
+    prof = g.read_profile()
+    off, nbr, rn = g.read_connections()
+    ax, gen = g.read_iterate_path()
+    out = {"workload": sw.name, "robots": sw.n, "variables": int(sw.cfg.num_variables), "steps": steps,
+           "value": sw.n * substeps * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+           "mean_neighbours": float(off[-1]) / max(1, sw.n), "edges_before": e0, "edges_after": int(off[-1]),
+           "robots_in_k_iterate_axis": ax, "robots_in_k_iterate": gen,
+           "profile_ms_per_step": {k: round(v["ms"] / steps, 4) for k, v in prof.items() if v["count"]}}
+    g.close()
+    return out
+
+
+def scenario_point(name: str, ticks: int, cores: int) -> dict:
+    """A BASELINE scenario (configs 1-3) at its real size on the reference's own inputs (tests/golden/scenarios.json):
+    robots spawned by the scenario's formation clock, ms per sim step of the engine (wall clock around every
+    gbp_world_step incl. a device sync: these swarms are launch-latency bound) and of the CPU restatement."""
+    from magics_b200 import World, scenarios
+    from oracle import oracle as _oracle
+    from oracle.oracle import OracleWorld
+
+    sc = scenarios.ReferenceScenario(name)
+    g, o = World(sc.cfg, device=0), OracleWorld(sc.cfg, threads=cores)
+    g.set_sdf_from_environment(sc.env)
+    o.set_sdf(_oracle.env_to_sdf_image(sc.env))
+    rng = np.random.default_rng(0)
+    events = sc.spawn_events(ticks)
+    t_gpu = t_cpu = 0.0
+    timed = 0
+    for tick in range(ticks):
+        for _, k in [e for e in events if e[0] == tick]:
+            sw = sc.spawn(k, rng)
+            if sw is not None:
+                sw.add_to(g, set_sdf=False)
+                sw.add_to(o, set_sdf=False)
+        if g.num_robots == 0:
+            continue
+        g.sync()
+        t = time.perf_counter()
+        g.step()
+        g.sync()
+        t_gpu += time.perf_counter() - t
+        t = time.perf_counter()
+        o.step()
+        t_cpu += time.perf_counter() - t
+        timed += 1
+    n = g.num_robots
+    edges = int(g.read_connections()[0][-1])
+    g.close()
+    o.close()
+    return {"scenario": name, "robots_at_end": n, "variables": int(sc.cfg.num_variables), "ticks_timed": timed,
+            "edges_at_end": edges, "ms_per_step_gpu": t_gpu * 1e3 / max(1, timed),
+            "ms_per_step_cpu_port": t_cpu * 1e3 / max(1, timed), "cpu_threads": cores}
+
+
 def main():
     # stdout carries exactly ONE JSON line: everything else a library prints there (NCCL's version
     # banner under NCCL_DEBUG, torchrun notices) is sent to stderr while the benchmark runs.
@@ -184,7 +261,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="lattice", choices=["rings", "lattice"])
+    ap.add_argument("--workload", default="lattice", choices=["rings", "lattice", "dense"])
     ap.add_argument("--robots", type=int, default=None,
                     help="robots of the whole swarm (default: lattice 1 000 000, rings 100 000)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
@@ -192,10 +269,13 @@ def main():
                          "1/2/4/8 GPUs); weak: --robots per GPU")
     ap.add_argument("--cpu-robots", type=int, default=3000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra workloads reported next to the headline at N = 1 (config 4 rings-100k, a 10 k "
+                         "lattice, the dense stress lattice, BASELINE scenarios 1-3 at their real sizes)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.robots is None:
-        args.robots = 1_000_000 if args.workload == "lattice" else 100_000
+        args.robots = {"lattice": 1_000_000, "rings": 100_000, "dense": 250_000}[args.workload]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -411,6 +491,28 @@ def main():
                                    "robot_number, after all ticks of this run; the same for every N"},
             "roofline": roof, "cpu_baseline": cpu, "profile_ms": prof,
         }
+        if world == 1 and not args.no_extras and args.workload == "lattice":
+            # the other sizes the metric names (10 k / 100 k), the regime the headline never enters (active
+            # InterRobot factors, edges created and deleted every tick) and configs 1-3 on the reference's inputs
+            from magics_b200 import scenarios
+
+            g.close()
+            extras = []
+            for make, steps in ((lambda: scenarios.rings(100_000), 10), (lambda: scenarios.lattice(100, 100), 20),
+                                (lambda: scenarios.dense_lattice(500, 500), 5)):
+                try:
+                    extras.append(extra_point(make(), steps))
+                except Exception as e:  # an extra never takes the headline down
+                    extras.append({"error": repr(e)})
+            line["points"] = extras
+            scen = []
+            for name, ticks in (("Circle Experiment", 30), ("Structured Junction Twoway", 70),
+                                ("Collaborative Complex", 50)):
+                try:
+                    scen.append(scenario_point(name, ticks, cores))
+                except Exception as e:
+                    scen.append({"scenario": name, "error": repr(e)})
+            line["scenarios"] = scen
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -278,7 +278,9 @@ int gbp_world_change_prior_of_variable(gbp_world_t *w, int32_t variable_index, i
  *   inbox of the robot's variables AND of its factors emptied.  The reference passes (1e30, INFINITY).
  * reset_tracking_factors: FactorGraph::reset_tracking_factors (factorgraph.rs:1566-1590): timeout of 10
  *   iterations on every tracking factor.
- * Single-GPU worlds only for reset_variables (GBP_ERR_STATE on a sharded world). */
+ * On a sharded world reset_variables is collective: every rank calls it in the same tick with its own robots
+ * (m = 0 if it has none); the ids of the reset robots travel to the other shards, which freeze their own InterRobot
+ * factors toward them at the zero linearisation point the emptied inbox gives (factor/mod.rs:336-349). */
 int gbp_world_set_tracking_path(gbp_world_t *w, int32_t m, const int32_t *robots, const int32_t *wp_offsets,
                                 const float *wp_xy);
 int gbp_world_reset_variables(gbp_world_t *w, int32_t m, const int32_t *robots, const double *means,
@@ -299,7 +301,13 @@ int gbp_world_iterate_schedule(gbp_world_t *w, int32_t n, const uint8_t *interna
  *   external_variable_iteration factorgraph.rs:794-826 + delivery robot.rs:1843-1858
  * The internal pair and the external pair must each be called in this order
  * (as iterate_gbp_v2 does); the engine executes a pair as one fused pass when
- * the second half is requested and returns GBP_ERR_STATE on any other order. */
+ * the second half is requested and returns GBP_ERR_STATE on any other order.
+ * The state "after the factor half, before the variable half" is therefore never
+ * materialised: while a pair is open (state kept per swarm, so any shard of a group
+ * may close what another opened) every read-back and every state-changing call —
+ * read_beliefs, set_comms, change_prior_of_variable, reset_variables, remove_robots,
+ * update_topology, iterate* — returns GBP_ERR_STATE instead of showing or changing
+ * something the reference would not. */
 int gbp_world_internal_factor_iteration(gbp_world_t *w);
 int gbp_world_internal_variable_iteration(gbp_world_t *w);
 int gbp_world_external_factor_iteration(gbp_world_t *w);

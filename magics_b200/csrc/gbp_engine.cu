@@ -230,6 +230,29 @@ __global__ void k_init_vars(Store s, int64_t first, int64_t count, const double 
   s.dyn_c[s.at<4>(3, vi)] = q22;
 }
 
+// FactorGraph::reset_variables on another shard's robot (global ids `ids`, ascending): the own robots' InterRobot
+// factors toward it have lost its message (they will linearise at zeros), i.e. every own edge whose neighbour is in
+// the list is frozen at (0, 0) — the remote half of k_reset_reverse_edges.
+__global__ void k_freeze_edges_toward(Store s, const int32_t *__restrict__ egid, int n_ids,
+                                      const int32_t *__restrict__ ids) {
+  const int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= s.E) return;
+  const int32_t a = egid[e];
+  int lo = 0, hi = n_ids;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (ids[mid] < a) lo = mid + 1;
+    else hi = mid;
+  }
+  if (lo >= n_ids || ids[lo] != a) return;
+  const int Vm1 = s.V - 1;
+  s.e_frozen[e] = uint8_t(s.e_frozen[e] | 1);
+  for (int i = 0; i < Vm1; ++i) {
+    s.mu_frozen[e * Vm1 + i] = 0.0;
+    s.mu_frozen[s.EV + e * Vm1 + i] = 0.0;
+  }
+}
+
 // TrackingFactor state read-back (tracking.rs:62-90 `Tracking.record`, `LastMeasurement`): AoS rows per variable.
 __global__ void k_gather_tracking(Store s, int64_t nv, int64_t *record, float *pos, double *value) {
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -448,10 +471,12 @@ __global__ void k_reset_reverse_edges(Store s, int m, const int32_t *__restrict_
   for (int64_t e = s.eoff[r] + threadIdx.x; e < s.eoff[r + 1]; e += blockDim.x) {
     const int32_t A = s.enbr[e];
     if (A >= s.Nloc) continue;
+    // rows are ordered by GLOBAL id (on a shard the ghost slots of lower-id robots come first)
+    const int32_t gr = s.gid[r];
     int64_t lo = s.eoff[A], hi = s.eoff[A + 1];
     while (lo < hi) {
       const int64_t mid = (lo + hi) >> 1;
-      if (s.enbr[mid] < r) lo = mid + 1;
+      if (s.gid[s.enbr[mid]] < gr) lo = mid + 1;
       else hi = mid;
     }
     if (lo >= s.eoff[A + 1] || s.enbr[lo] != r) continue;
@@ -575,6 +600,16 @@ __global__ void k_keep_gone_idle(Store s) {
   if (r < s.Nloc && s.gone[r] != 0.0f) s.idle[r] = 1;
 }
 
+// bounding box of nothing, candidate counter 0, and the cell-less dummy robot the padded candidate list points at
+__global__ void k_box_init(int32_t *box, int32_t *cx_dummy, int32_t *cz_dummy) {
+  if (threadIdx.x == 0) {
+    box[0] = box[1] = INT32_MAX;
+    box[2] = box[3] = INT32_MIN;
+    box[4] = 0;
+    *cx_dummy = *cz_dummy = gbp::kNoCell;
+  }
+}
+
 __global__ void k_iota_gid(int32_t *gid, int32_t g0, int32_t n) {
   const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < n) gid[r] = g0 + r;
@@ -591,6 +626,10 @@ struct gbp_group {
   std::vector<gbp_world *> members;  // shards living in this process, indexed by rank when !nccl
   bool committed = false;            // global ids fixed (gbp_world_commit_shards)
   bool halo_stale = true;            // some published record changed since the last halo exchange
+  // gbp_world_{internal,external}_factor_iteration has been called and the matching *_variable_iteration has not:
+  // the factor half runs fused with the variable half, so the state "after factors, before variables" is never
+  // materialised; reads and state-changing calls are refused while a pair is open (pair_open)
+  bool pending_internal_factor = false, pending_external_factor = false;
   bool halo_pending = false;         // an exchange started right after the border robots' internal half is in flight
                                      // on the comm streams (group_launch); the next external half waits for it
   cudaStream_t shared_stream = nullptr;
@@ -629,9 +668,10 @@ struct gbp_world {
   int cur = 0;
   int32_t *t_nlow = nullptr;
   int64_t *t_result_dev = nullptr, *t_result_host = nullptr;
-  bool pending_internal_factor = false, pending_external_factor = false;
   // topology scratch
   int32_t *t_cx = nullptr, *t_cz = nullptr, *t_idx = nullptr, *t_idx_sorted = nullptr;
+  int32_t *t_box = nullptr;      // sharded neighbour search: own bounding box [0..3], candidates found [4]
+  int64_t cand_cap = 0;          // entries the hash of a sharded world sorts (grows when a pass finds more)
   uint32_t *t_keys = nullptr, *t_keys_sorted = nullptr;
   int64_t *t_cnt = nullptr, *t_off = nullptr, *t_newcnt = nullptr, *t_newoff = nullptr;
   void *t_cub = nullptr;
@@ -682,6 +722,7 @@ struct gbp_world {
   bool force_rebuild = false;
   float *gpos = nullptr;        // [4][Ntot] x, z, radius, despawned flag of every robot by global id (ws > 1)
   bool any_gone = false;        // some own robot has been removed: set_comms keeps it idle
+  float max_radius = 0.0f;         // over the own robots: the collision monitor only tests connected pairs
   std::vector<uint8_t> gone_host;  // host mirror of Store::gone
   int64_t n_gone = 0;
   int64_t gpos_cap = 0;
@@ -717,6 +758,16 @@ namespace {
 
 int set_device(gbp_world *w) {
   CK(cudaSetDevice(w->device));
+  return 0;
+}
+
+// State-changing and reading entry points call this first: between a *_factor_iteration call and its
+// *_variable_iteration the reference has already run the factor half (factorgraph.rs:688-714, 719-760); the engine
+// has not (it fuses the two), so it refuses to show or change that state rather than return something else.
+int pair_open(const gbp_world *w, const char *what) {
+  if (w->grp && (w->grp->pending_internal_factor || w->grp->pending_external_factor))
+    return fail(GBP_ERR_STATE, std::string(what) + ": a factor half-iteration is open on this world (call the matching "
+                                                   "*_variable_iteration first)");
   return 0;
 }
 
@@ -1118,11 +1169,12 @@ int grow_edge_set(gbp_world *w, EdgeSet *e, int64_t cap) {
   return 0;
 }
 
-constexpr int kResultWords = 4 + 3 * (gbp::kMaxShards + 1);
+constexpr int kResultWords = 4 + 3 * (gbp::kMaxShards + 1) + 1;
 
 int ensure_topology_scratch(gbp_world *w) {
   const int64_t nloc = w->s.Nloc, ntot = w->Ntot, ws = w->sh.ws;
   if (!w->t_result_dev) {
+    CK(dalloc(w->t_box, 5));  // bounding box of the own robots (4 ordered ints) + candidate count
     CK(dalloc(w->t_result_dev, kResultWords));
     CK(cudaMallocHost(reinterpret_cast<void **>(&w->t_result_host), kResultWords * sizeof(int64_t)));
     CK(dalloc(w->t_err, 1));
@@ -1143,7 +1195,8 @@ int ensure_topology_scratch(gbp_world *w) {
   if (!w->t_cx || ntot > w->t_cap_tot) {
     cudaFree(w->t_cx); cudaFree(w->t_cz); cudaFree(w->t_idx); cudaFree(w->t_idx_sorted);
     cudaFree(w->t_keys); cudaFree(w->t_keys_sorted); cudaFree(w->t_gflag); cudaFree(w->t_gslot);
-    CK(dalloc(w->t_cx, ntot)); CK(dalloc(w->t_cz, ntot)); CK(dalloc(w->t_idx, ntot)); CK(dalloc(w->t_idx_sorted, ntot));
+    CK(dalloc(w->t_cx, ntot + 1)); CK(dalloc(w->t_cz, ntot + 1));  // slot ntot: the dummy of the padded candidate list
+    CK(dalloc(w->t_idx, ntot)); CK(dalloc(w->t_idx_sorted, ntot));
     CK(dalloc(w->t_keys, ntot)); CK(dalloc(w->t_keys_sorted, ntot));
     CK(dalloc(w->t_gflag, ntot + 1)); CK(dalloc(w->t_gslot, ntot + 1));
     w->t_cap_tot = ntot;
@@ -1260,11 +1313,25 @@ int topo_search(gbp_world *w) {
   const int T = 128;
   const float R = w->cfg.comms_radius;
   const double cell = double(R) * 1.001;
-  gbp::k_cell_keys<<<blocks_for(ntot, T), T, 0, st>>>(ntot, gx, gz, ggone, cell, w->t_cx, w->t_cz, w->t_keys, w->t_idx);
+  // entries in the hash: every robot on one GPU; on a shard only the robots near its own ones (k_cell_keys_near),
+  // padded to cand_cap with a sentinel key pointing at a cell-less dummy
+  int32_t nall = ntot;
+  if (ws == 1) {
+    gbp::k_cell_keys<<<blocks_for(ntot, T), T, 0, st>>>(ntot, gx, gz, ggone, cell, w->t_cx, w->t_cz, w->t_keys, w->t_idx);
+  } else {
+    if (w->cand_cap <= 0 || w->cand_cap > ntot) w->cand_cap = ntot;
+    nall = int32_t(w->cand_cap);
+    k_box_init<<<1, 32, 0, st>>>(w->t_box, w->t_cx + ntot, w->t_cz + ntot);
+    if (n > 0) gbp::k_own_bbox<<<blocks_for(n, 256), 256, 0, st>>>(g0, n, gx, gz, ggone, w->t_box);
+    gbp::k_fill_u32<<<blocks_for(nall, 256), 256, 0, st>>>(w->t_keys, w->t_idx, nall, 0xFFFFFFFFu, ntot);
+    gbp::k_cell_keys_near<<<blocks_for(ntot, T), T, 0, st>>>(ntot, gx, gz, ggone, cell, R * 1.01f, w->t_box, w->t_cx,
+                                                            w->t_cz, w->t_keys, w->t_idx, nall, w->t_box + 4);
+    w->launches += 3;
+  }
   size_t cb = w->t_cub_bytes;
-  CK(cub::DeviceRadixSort::SortPairs(w->t_cub, cb, w->t_keys, w->t_keys_sorted, w->t_idx, w->t_idx_sorted, ntot, 0, 32, st));
+  CK(cub::DeviceRadixSort::SortPairs(w->t_cub, cb, w->t_keys, w->t_keys_sorted, w->t_idx, w->t_idx_sorted, nall, 0, 32, st));
   if (n > 0)
-    gbp::k_neighbours<false><<<blocks_for(n, T), T, 0, st>>>(ntot, g0, n, gx, gz, w->t_cx, w->t_cz, w->t_keys_sorted,
+    gbp::k_neighbours<false><<<blocks_for(n, T), T, 0, st>>>(nall, g0, n, gx, gz, w->t_cx, w->t_cz, w->t_keys_sorted,
                                                              w->t_idx_sorted, R, w->t_cnt, nullptr, 0);
   CK(cudaMemsetAsync(w->t_cnt + n, 0, sizeof(int64_t), st));
   cb = w->t_cub_bytes;
@@ -1276,7 +1343,7 @@ int topo_search(gbp_world *w) {
   const EdgeSet *live = &w->edges[w->cur];
   for (int attempt = 0; attempt < 2; ++attempt) {
     if (n > 0) {
-      gbp::k_neighbours<true><<<blocks_for(n, T), T, 0, st>>>(ntot, g0, n, gx, gz, w->t_cx, w->t_cz, w->t_keys_sorted,
+      gbp::k_neighbours<true><<<blocks_for(n, T), T, 0, st>>>(nall, g0, n, gx, gz, w->t_cx, w->t_cz, w->t_keys_sorted,
                                                               w->t_idx_sorted, R, w->t_off, spare->egid, spare->cap);
       gbp::k_edge_diff<<<blocks_for(n, T), T, 0, st>>>(n, g0, w->t_off, spare->egid, s.eoff, live->egid, n, spare->map,
                                                        w->t_newcnt, w->t_nlow, spare->cap);
@@ -1301,7 +1368,7 @@ int topo_search(gbp_world *w) {
       w->launches += 4;
     }
     gbp::k_shard_result<<<1, 32, 0, st>>>(w->sh, n, w->t_off, w->t_newoff, ws > 1 ? w->t_gslot : nullptr, w->t_soff,
-                                          w->t_coff, w->t_err, w->t_result_dev);
+                                          w->t_coff, w->t_err, ws > 1 ? w->t_box + 4 : nullptr, w->t_result_dev);
     CK(cudaGetLastError());
     k_words_to_host<<<1, 64, 0, st>>>(w->t_result_host, w->t_result_dev, int(kResultWords));
     CK(cudaGetLastError());
@@ -1311,6 +1378,17 @@ int topo_search(gbp_world *w) {
     if (w->t_result_host[3] != 0)
       return fail(GBP_ERR_STATE, "sharded topology: a cross-shard robot_number lookup failed in an earlier pass "
                                  "(neighbour lists of two shards disagree)");
+    if (ws > 1) {
+      const int64_t ncand = w->t_result_host[4 + 3 * (gbp::kMaxShards + 1)];
+      if (ncand > nall) {
+        // more robots near this shard than the padded list holds: the lists just built miss some — size the list
+        // for what was found and run the whole search again
+        w->cand_cap = std::min<int64_t>(ntot, ncand + ncand / 4 + 1024);
+        return topo_search(w);
+      }
+      // shrink toward the need (with slack) so that the sort stays proportional to the shard, not to the swarm
+      w->cand_cap = std::min<int64_t>(ntot, std::max<int64_t>(ncand + ncand / 4 + 1024, 4096));
+    }
     w->tp.E1 = w->t_result_host[0];
     w->tp.total_new = w->t_result_host[1];
     if (w->tp.E1 <= spare->cap) break;
@@ -1772,7 +1850,7 @@ void gbp_world_destroy(gbp_world_t *w) {
                   s.trk_record, s.trk_timeout, s.trk_seed, s.trk_last, s.trk_value, s.radius, s.t0, s.pos, s.antenna,
                   s.idle, s.finished, s.gone, s.latest, s.iter_factor, s.gid, s.next_wp, s.coll_hits, w->coll_totals, s.wp_off, s.wp_xy, s.eoff,
                   s.nlow, w->t_nlow, w->t_result_dev, w->sdf_dev, w->t_cx,
-                  w->t_cz, w->t_idx, w->t_idx_sorted, w->t_keys, w->t_keys_sorted, w->t_cnt, w->t_off,
+                  w->t_cz, w->t_box, w->t_idx, w->t_idx_sorted, w->t_keys, w->t_keys_sorted, w->t_cnt, w->t_off,
                   w->t_newcnt, w->t_newoff, w->t_cub, w->rb_dev, w->gpos, w->t_gflag, w->t_gslot, w->t_sflag,
                   w->t_soff, w->t_ccnt, w->t_coff, w->t_err, w->sendlist, w->ckeys_s, w->cvals_s, w->ckeys_r,
                   w->cvals_r, w->hdr_send, w->hdr_recv, w->halo_send, w->halo_recv};
@@ -2090,6 +2168,7 @@ int gbp_world_add_robots(gbp_world_t *w, int32_t n, const float *radii, const ui
   std::vector<uint8_t> ones(n, 1);
   std::vector<int32_t> gid(n), nwp(n, 1);
   for (int r = 0; r < n; ++r) {
+    w->max_radius = std::max(w->max_radius, radii[r]);
     t0[r] = radii[r] / 2.0f / w->cfg.target_speed;  // :1225 (f32)
     pos[r] = positions[2 * r];
     pos[size_t(n) + r] = positions[2 * r + 1];
@@ -2153,6 +2232,7 @@ int32_t gbp_world_num_robots(const gbp_world_t *w) { return w ? w->s.Nloc : 0; }
 
 int gbp_world_update_topology(gbp_world_t *w) {
   if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (int rc = pair_open(w, "gbp_world_update_topology")) return rc;
   if (set_device(w)) return GBP_ERR_CUDA;
   return group_update_topology(w->grp);
 }
@@ -2197,6 +2277,7 @@ int staged_upload(gbp_world *w, int kind, void *dst, const void *src, size_t byt
 
 int gbp_world_set_comms(gbp_world_t *w, const uint8_t *antenna_active, const uint8_t *idle) {
   if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (int rc = pair_open(w, "gbp_world_set_comms")) return rc;
   if (set_device(w)) return GBP_ERR_CUDA;
   const int n = w->s.Nloc;
   if (n == 0) return 0;
@@ -2221,6 +2302,7 @@ int gbp_world_set_comms(gbp_world_t *w, const uint8_t *antenna_active, const uin
 
 int gbp_world_remove_robots(gbp_world_t *w, int32_t m, const int32_t *robots) {
   if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (int rc = pair_open(w, "gbp_world_remove_robots")) return rc;
   if (m < 0 || (m > 0 && !robots)) return fail(GBP_ERR_BAD_ARGUMENT, "gbp_world_remove_robots: null list");
   if (set_device(w)) return GBP_ERR_CUDA;
   for (int k = 0; k < m; ++k)
@@ -2294,6 +2376,13 @@ int gbp_world_update_robot_collisions(gbp_world_t *w0, int64_t *num_collisions, 
   if (!w0) return fail(GBP_ERR_BAD_HANDLE, "null world");
   gbp_group *g = w0->grp;
   // ghosts must sit at their current Transform: the halo carries it
+  // The monitor walks the InterRobot edges instead of all pairs (planner/collisions.rs:72-143 tests every pair):
+  // exact as long as two touching robots are always connected, i.e. r_a + r_b <= comms radius.  Every shard checks
+  // its own robots against half the radius, which bounds every pair.
+  for (gbp_world *w : g->members)
+    if (2.0f * w->max_radius > w->cfg.comms_radius)
+      return fail(GBP_ERR_STATE, "gbp_world_update_robot_collisions: a robot diameter exceeds the communication radius; "
+                                 "colliding pairs could be out of comms range and would be missed");
   if (int rc = group_halo_join(g)) return rc;
   if (g->ws > 1 && g->halo_stale) {
     if (int rc = group_halo(g)) return rc;
@@ -2383,6 +2472,7 @@ int gbp_world_update_prior_of_current_state(gbp_world_t *w0) {
 int gbp_world_change_prior_of_variable(gbp_world_t *w, int32_t var, int32_t m, const int32_t *robots,
                                        const double *new_means) {
   if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (int rc = pair_open(w, "gbp_world_change_prior_of_variable")) return rc;
   if (var < 0 || var >= w->s.V || m < 0 || (m > 0 && (!robots || !new_means)))
     return fail(GBP_ERR_BAD_ARGUMENT, "gbp_world_change_prior_of_variable: bad argument");
   if (m == 0) return 0;
@@ -2457,32 +2547,93 @@ int gbp_world_set_tracking_path(gbp_world_t *w, int32_t m, const int32_t *robots
   return 0;
 }
 
+namespace {
+// The shards that hold InterRobot factors toward the robots `gids` (ascending global ids) freeze them.
+int freeze_on_shard(gbp_world *v, const int32_t *d_ids, int n_ids) {
+  if (n_ids == 0 || v->s.E == 0) return 0;
+  CK(cudaSetDevice(v->device));
+  k_freeze_edges_toward<<<blocks_for(v->s.E, 256), 256, 0, v->stream>>>(v->s, v->edges[v->cur].egid, n_ids, d_ids);
+  CK(cudaGetLastError());
+  v->launches += 1;
+  return 0;
+}
+}  // namespace
+
 int gbp_world_reset_variables(gbp_world_t *w, int32_t m, const int32_t *robots, const double *means,
                               double first_last_sigma, double inbetween_sigma) {
   if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (int rc = pair_open(w, "gbp_world_reset_variables")) return rc;
   if (int rc = check_robot_list(w, m, robots, "gbp_world_reset_variables")) return rc;
-  if (m == 0) return 0;
-  if (!means) return fail(GBP_ERR_BAD_ARGUMENT, "gbp_world_reset_variables: null means");
-  if (w->sh.ws > 1)
-    return fail(GBP_ERR_STATE, "gbp_world_reset_variables: not available on a sharded world yet (the emptied "
-                               "InterRobot inboxes of cross-shard factors would have to travel)");
+  gbp_group *g = w->grp;
+  const bool collective = g->ws > 1 && g->nccl;  // every rank calls, possibly with m == 0
+  if (m == 0 && !collective) return 0;
+  if (m > 0 && !means) return fail(GBP_ERR_BAD_ARGUMENT, "gbp_world_reset_variables: null means");
   if (set_device(w)) return GBP_ERR_CUDA;
+  if (int rc = group_halo_join(g)) return rc;
   const int V = w->s.V;
   cudaStream_t st = w->stream;
-  int32_t *dr = nullptr;
+  int32_t *dr = nullptr, *dg = nullptr;
   double *dm = nullptr;
-  CK(dalloc(dr, m));
-  CK(dalloc(dm, size_t(4) * V * m));
-  CK(cudaMemcpyAsync(dr, robots, size_t(m) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(dm, means, size_t(4) * V * m * sizeof(double), cudaMemcpyHostToDevice, st));
-  k_reset_variables<<<blocks_for(int64_t(m) * V, 128), 128, 0, st>>>(w->s, w->p, m, dr, dm, first_last_sigma,
-                                                                     inbetween_sigma);
-  if (w->s.eoff && w->s.E > 0) k_reset_reverse_edges<<<m, 64, 0, st>>>(w->s, m, dr);
-  CK(cudaGetLastError());
-  w->launches += 2;
+  // the robots' global ids, ascending: what the other shards look for among their neighbours
+  std::vector<int32_t> gids(robots, robots + m);
+  for (int32_t &x : gids) x += w->sh.gfirst[w->sh.rank];
+  std::sort(gids.begin(), gids.end());
+  if (m > 0) {
+    CK(dalloc(dr, m));
+    CK(dalloc(dg, m));
+    CK(dalloc(dm, size_t(4) * V * m));
+    CK(cudaMemcpyAsync(dr, robots, size_t(m) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dg, gids.data(), size_t(m) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dm, means, size_t(4) * V * m * sizeof(double), cudaMemcpyHostToDevice, st));
+    k_reset_variables<<<blocks_for(int64_t(m) * V, 128), 128, 0, st>>>(w->s, w->p, m, dr, dm, first_last_sigma,
+                                                                       inbetween_sigma);
+    if (w->s.eoff && w->s.E > 0) k_reset_reverse_edges<<<m, 64, 0, st>>>(w->s, m, dr);
+    CK(cudaGetLastError());
+    w->launches += 2;
+  }
+  int rc = 0;
+  int32_t *d_all = nullptr;
+  if (g->ws > 1 && !g->nccl) {
+    // in-process shards: one device, one stream — the other members' edges are frozen directly
+    for (gbp_world *v : g->members)
+      if (v != w && (rc = freeze_on_shard(v, dg, m))) break;
+  } else if (collective) {
+    // 1. how many robots every shard resets; 2. their global ids; 3. freeze the own edges toward them
+    const int ws = g->ws, rank = w->sh.rank;
+    std::vector<gbp::XferPlan> plans(1);
+    int64_t *h = w->hdr_host + 4 * gbp::kMaxShards;
+    h[0] = m;
+    h[1] = h[2] = h[3] = 0;
+    CK(cudaMemcpyAsync(w->hdr_send, h, 4 * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    for (int q = 0; q < ws; ++q) {
+      if (q == rank) continue;
+      plans[0].sends.push_back({q, w->hdr_send, 4 * sizeof(int64_t)});
+      plans[0].recvs.push_back({q, w->hdr_recv + 4 * q, 4 * sizeof(int64_t)});
+    }
+    if ((rc = exchange(g, plans)) == 0) {
+      CK(cudaMemcpyAsync(w->hdr_host, w->hdr_recv, 4 * size_t(gbp::kMaxShards) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      std::vector<int64_t> off(size_t(ws) + 1, 0);
+      for (int q = 0; q < ws; ++q) off[q + 1] = off[q] + (q == rank ? 0 : w->hdr_host[4 * q]);
+      const int64_t total = off[ws];
+      if (total > 0) CK(dalloc(d_all, size_t(total)));
+      plans[0].clear();
+      for (int q = 0; q < ws; ++q) {
+        if (q == rank) continue;
+        if (m > 0) plans[0].sends.push_back({q, dg, size_t(m) * sizeof(int32_t)});
+        if (off[q + 1] > off[q])
+          plans[0].recvs.push_back({q, d_all + off[q], size_t(off[q + 1] - off[q]) * sizeof(int32_t)});
+      }
+      // peers' id ranges ascend with the rank and every list is sorted: the concatenation is sorted
+      if ((rc = exchange(g, plans)) == 0) rc = freeze_on_shard(w, d_all, int(total));
+    }
+  }
   CK(cudaStreamSynchronize(st));
   cudaFree(dr);
+  cudaFree(dg);
   cudaFree(dm);
+  cudaFree(d_all);
+  if (rc) return rc;
   mark_halo_stale(w);
   return 0;
 }
@@ -2506,7 +2657,7 @@ int gbp_world_reset_tracking_factors(gbp_world_t *w, int32_t m, const int32_t *r
 int gbp_world_iterate_schedule(gbp_world_t *w, int32_t n, const uint8_t *internal, const uint8_t *external) {
   if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
   if (n < 0 || (n > 0 && (!internal || !external))) return fail(GBP_ERR_BAD_ARGUMENT, "bad schedule");
-  if (w->pending_internal_factor || w->pending_external_factor)
+  if (w->grp->pending_internal_factor || w->grp->pending_external_factor)
     return fail(GBP_ERR_STATE, "a half-iteration pair is open");
   if (set_device(w)) return GBP_ERR_CUDA;
   return run_schedule(w->grp, n, internal, external);
@@ -2524,27 +2675,27 @@ int gbp_world_iterate(gbp_world_t *w) {
 
 int gbp_world_internal_factor_iteration(gbp_world_t *w) {
   if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
-  if (w->pending_internal_factor || w->pending_external_factor) return fail(GBP_ERR_STATE, "half-iteration order");
-  w->pending_internal_factor = true;
+  if (w->grp->pending_internal_factor || w->grp->pending_external_factor) return fail(GBP_ERR_STATE, "half-iteration order");
+  w->grp->pending_internal_factor = true;
   return 0;
 }
 int gbp_world_internal_variable_iteration(gbp_world_t *w) {
   if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
-  if (!w->pending_internal_factor) return fail(GBP_ERR_STATE, "internal_variable_iteration without internal_factor_iteration");
-  w->pending_internal_factor = false;
+  if (!w->grp->pending_internal_factor) return fail(GBP_ERR_STATE, "internal_variable_iteration without internal_factor_iteration");
+  w->grp->pending_internal_factor = false;
   if (set_device(w)) return GBP_ERR_CUDA;
   return group_launch<false, true>(w->grp);
 }
 int gbp_world_external_factor_iteration(gbp_world_t *w) {
   if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
-  if (w->pending_internal_factor || w->pending_external_factor) return fail(GBP_ERR_STATE, "half-iteration order");
-  w->pending_external_factor = true;
+  if (w->grp->pending_internal_factor || w->grp->pending_external_factor) return fail(GBP_ERR_STATE, "half-iteration order");
+  w->grp->pending_external_factor = true;
   return 0;
 }
 int gbp_world_external_variable_iteration(gbp_world_t *w) {
   if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
-  if (!w->pending_external_factor) return fail(GBP_ERR_STATE, "external_variable_iteration without external_factor_iteration");
-  w->pending_external_factor = false;
+  if (!w->grp->pending_external_factor) return fail(GBP_ERR_STATE, "external_variable_iteration without external_factor_iteration");
+  w->grp->pending_external_factor = false;
   if (set_device(w)) return GBP_ERR_CUDA;
   return group_launch<true, false>(w->grp);
 }
@@ -2644,6 +2795,7 @@ int read_beliefs_impl(gbp_world *w, double *eta, double *lam, double *mean, doub
 
 int gbp_world_read_beliefs(gbp_world_t *w, double *eta, double *lam, double *mean, double *cov, uint8_t *valid) {
   if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (int rc = pair_open(w, "gbp_world_read_beliefs")) return rc;
   return read_beliefs_impl(w, eta, lam, mean, cov, valid, false);
 }
 

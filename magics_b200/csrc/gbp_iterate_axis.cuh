@@ -49,6 +49,14 @@ constexpr int kAxisEdges = 32;
 #define GBP_AXIS_BATCH 2  // edges whose neighbour loads a lane has in flight at once (4: spills, 10 % slower)
 #endif
 constexpr int kAxisBatch = GBP_AXIS_BATCH;
+#ifndef GBP_AXIS_MARK_SHFL
+#define GBP_AXIS_MARK_SHFL 0   // 1: the y lane gets "message is Empty" from the x lane instead of loading row 0 itself
+                               // (4 registers fewer, but +1 % time: profiles/README.md r02j)
+#endif
+#ifndef GBP_AXIS_RELOAD_SENT
+#define GBP_AXIS_RELOAD_SENT 0 // 1: the last delivered mean is read again in the rare freeze path instead of being kept
+                               // (4 registers fewer, +3 % time: r02j)
+#endif
 #ifndef GBP_AXIS_PREFETCH
 #define GBP_AXIS_PREFETCH 0  // CTAs ahead whose wave-1 rows this CTA pulls into L2 (592 = 148 SMs x 4 resident CTAs:
                              // +1.5 % DRAM bytes, no time gained — profiles/README.md r02e/r02f; off)
@@ -134,9 +142,14 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
   const int t = threadIdx.x, a = t & 1, slot = t >> 1;
   const int rl = slot / V, i = slot - rl * V;
   const int64_t ridx = int64_t(blockIdx.x) * rpc + rl;
-  bool live = rl < rpc && ridx < (PART == 1 ? int64_t(*nlist) : int64_t(s.Nloc));
-  const int64_t r = live ? (PART == 1 ? int64_t(list[ridx]) : ridx) : 0;
-  if (PART == 2 && live && skip[r]) live = false;
+  int64_t r = ridx;
+  bool live = rl < rpc && ridx < int64_t(s.Nloc);
+  if (PART == 1) {
+    live = rl < rpc && ridx < int64_t(*nlist);
+    r = live ? int64_t(list[ridx]) : 0;
+  } else if (PART == 2) {
+    live = live && !skip[r];
+  }
   const int64_t vi = live ? r * V + i : 0;
   double *const xr = sh;                             // [6][T] variable -> Dynamic factor i   (its right-hand factor)
   double *const xl = sh + 6 * T;                     // [6][T] variable -> Dynamic factor i-1 (its left-hand factor)
@@ -200,7 +213,9 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
   double mu_sent[2] = {0.0, 0.0};
   double eRec[2] = {0.0, 0.0}, LRec[4] = {0.0, 0.0, 0.0, 0.0};
   double eL[2] = {0.0, 0.0}, LL[4] = {0.0, 0.0, 0.0, 0.0}, eR[2] = {0.0, 0.0}, LR[4] = {0.0, 0.0, 0.0, 0.0};
+#if !GBP_AXIS_MARK_SHFL
   double markL = 0.0, markR = 0.0;  // row 0 of the stored Dynamic messages: the Empty marker sits there
+#endif
   if (live) {
     eo0 = s.eoff[r];
     eo1 = s.eoff[r + 1];
@@ -213,8 +228,10 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
     own_ne = s.pub_epoch[p][vi] > 0u;
     ld_axis(s.m_dynL[p], qm, eL, LL);
     ld_axis(s.m_dynR[p], qm, eR, LR);
+#if !GBP_AXIS_MARK_SHFL
     markL = a ? s.m_dynL[p][qm.v - kTile] : eL[0];
     markR = a ? s.m_dynR[p][qm.v - kTile] : eR[0];
+#endif
     if (INT) ld_axis(pubr, qp, eRec, LRec);
     pos = pubr[qp.v + 20 * kTile];
     vel = pubr[qp.v + 22 * kTile];
@@ -285,19 +302,23 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
   // neighbouring variables through shared memory
   double ae[2] = {pe[0], pe[1]}, al[4] = {pl, 0.0, 0.0, pl}, Q[4];
   {
+#if GBP_AXIS_MARK_SHFL
+    // the Empty marker sits in row 0 of a stored message, which the x lane holds as eL[0] / eR[0]; the y lane asks it
+    const unsigned even = (threadIdx.x & 31u) & ~1u;
+    const unsigned ne_bits = (is_empty_marker(eL[0]) ? 0u : 1u) | (is_empty_marker(eR[0]) ? 0u : 2u);
+    const unsigned pair_bits = __shfl_sync(0xffffffffu, ne_bits, even);
+    const bool hasL = work && (pair_bits & 1u), hasR = work && (pair_bits & 2u);
+#else
     const bool hasL = work && !is_empty_marker(markL), hasR = work && !is_empty_marker(markR);
+#endif
     if (INT && work && idle) {
       // idle robot: its record and messages are carried over to the other buffers unchanged
       st_axis(pubw, qp, eRec, LRec);
       pubw[qp.v + 20 * kTile] = pos;
       pubw[qp.v + 22 * kTile] = vel;
       if (a == 0) s.pub_epoch[1 - p][vi] = s.pub_epoch[p][vi];
-      st_axis(s.m_dynL[1 - p], qm, eL, LL);
+      st_axis(s.m_dynL[1 - p], qm, eL, LL);  // row 0 (the marker, if Empty) travels with the x lane
       st_axis(s.m_dynR[1 - p], qm, eR, LR);
-      if (a == 1) {
-        s.m_dynL[1 - p][qm.v - kTile] = markL;
-        s.m_dynR[1 - p][qm.v - kTile] = markR;
-      }
     }
     if (EXT && do_ext) {
       if (hasL) {
@@ -483,14 +504,27 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
   if (!work || bail) return;
 
   if (do_ext) {
-    s.mu_ext[s.at<2>(a, vi)] = mu_ext_new;
-    while (frz) {
-      const int k = __ffs(int(frz)) - 1;
-      frz &= frz - 1u;
-      const int64_t m = (eo0 + a + 2 * int64_t(k)) * (V - 1) + (i - 1);
-      s.mu_frozen[m] = mu_sent[0];
-      s.mu_frozen[s.EV + m] = mu_sent[1];
+    if (frz) {
+      // the mean these factors keep is the one delivered last (still in mu_ext: read again, rare path)
+#if GBP_AXIS_RELOAD_SENT
+      const double sent0 = s.mu_ext[s.at<2>(0, vi)], sent1 = s.mu_ext[s.at<2>(1, vi)];
+#else
+      const double sent0 = mu_sent[0], sent1 = mu_sent[1];
+#endif
+      while (frz) {
+        const int k = __ffs(int(frz)) - 1;
+        frz &= frz - 1u;
+        const int64_t m = (eo0 + a + 2 * int64_t(k)) * (V - 1) + (i - 1);
+        s.mu_frozen[m] = sent0;
+        s.mu_frozen[s.EV + m] = sent1;
+      }
     }
+    // both lanes of the pair (same branch: do_ext is per robot) must have read mu_ext before either overwrites its
+    // component
+#if GBP_AXIS_RELOAD_SENT
+    __syncwarp(3u << ((threadIdx.x & 31u) & ~1u));
+#endif
+    s.mu_ext[s.at<2>(a, vi)] = mu_ext_new;
     if (xflip[rl]) {
       // delivered edges hold mu_ext again; undelivered ones are (stay) frozen; the robot's lanes share the edges
       for (int64_t e = eo0 + 2 * i + a; e < eo1; e += 2 * V) {

@@ -79,11 +79,13 @@ __global__ void k_cross_mark(ShardInfo sh, int32_t nloc, const int64_t *__restri
 // out[0] = E1, out[1] = new directed pairs of this shard, out[2] = ghosts, out[3] = error flag,
 // out[4 + q] = ghost block start of shard q, out[4 + (ws+1) + q] = send block start,
 // out[4 + 2(ws+1) + q] = cross-edge block start   (q = 0..ws)
+// out[4 + 3(ws+1)] = robots that passed the candidate filter of the neighbour search (k_cell_keys_near)
 __global__ void k_shard_result(ShardInfo sh, int32_t nloc, const int64_t *noff, const int64_t *newoff,
                                const int32_t *gslot, const int32_t *soff, const int64_t *coff,
-                               const int32_t *err, int64_t *out) {
+                               const int32_t *err, const int32_t *ncand, int64_t *out) {
   const int q = threadIdx.x;
   if (q == 0) {
+    out[4 + 3 * (kMaxShards + 1)] = ncand ? *ncand : 0;
     out[0] = noff[nloc];
     out[1] = newoff[nloc];
     out[2] = gslot ? gslot[sh.gfirst[sh.ws]] : 0;

@@ -57,6 +57,59 @@ __global__ void k_cell_keys(int32_t n, const float *__restrict__ px, const float
   idx[r] = r;
 }
 
+// ---- sharded worlds: only robots near this shard's own robots enter the hash -------------------------
+// A shard receives every robot's position (16 bytes each) but only those inside the bounding box of its own
+// robots, grown by one comms radius, can be a neighbour of one of them.  k_own_bbox reduces the box (floats
+// ordered as integers), k_cell_keys_near appends the candidates — own robots included — to a compact
+// (key, index) list; the slots past the candidates keep the sentinel key / dummy index the host pre-filled.
+__device__ __forceinline__ int32_t float_order(float f) {
+  const int32_t b = __float_as_int(f);
+  return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__global__ void k_own_bbox(int32_t first, int32_t count, const float *__restrict__ px, const float *__restrict__ pz,
+                           const float *__restrict__ gone, int32_t *box /* min x, min z, max x, max z (ordered ints) */) {
+  const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const int32_t r = first + t;
+  if (gone && gone[r] != 0.0f) return;
+  const float x = px[r], z = pz[r];
+  if (!(x == x) || !(z == z)) return;  // NaN: no cell either way (the spatial hash never reproduced `!(R < NaN)`)
+  atomicMin(&box[0], float_order(x));
+  atomicMin(&box[1], float_order(z));
+  atomicMax(&box[2], float_order(x));
+  atomicMax(&box[3], float_order(z));
+}
+__global__ void k_cell_keys_near(int32_t n, const float *__restrict__ px, const float *__restrict__ pz,
+                                 const float *__restrict__ gone, double cell, float margin,
+                                 const int32_t *__restrict__ box, int32_t *cx, int32_t *cz, uint32_t *keys,
+                                 int32_t *idx, int32_t cap, int32_t *count) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float fx = px[r], fz = pz[r];
+  int32_t x = int32_t(floor(double(fx) / cell)), z = int32_t(floor(double(fz) / cell));
+  const bool dead = gone && gone[r] != 0.0f;
+  if (dead) x = z = kNoCell;
+  cx[r] = x;
+  cz[r] = z;
+  if (dead) return;
+  // compare in the ordered-integer domain of the box, with the margin applied in float (a superset is fine)
+  const bool near = float_order(fx + margin) >= box[0] && float_order(fz + margin) >= box[1] &&
+                    float_order(fx - margin) <= box[2] && float_order(fz - margin) <= box[3];
+  if (!near) return;
+  const int32_t j = atomicAdd(count, 1);
+  if (j < cap) {
+    keys[j] = cell_hash(x, z);
+    idx[j] = r;
+  }
+}
+__global__ void k_fill_u32(uint32_t *a, int32_t *b, int32_t n, uint32_t va, int32_t vb) {
+  const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) {
+    a[t] = va;
+    b[t] = vb;
+  }
+}
+
 __device__ __forceinline__ int32_t lower_bound_u32(const uint32_t *a, int32_t n, uint32_t key) {
   int32_t lo = 0, hi = n;
   while (lo < hi) {

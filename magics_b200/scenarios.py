@@ -176,6 +176,26 @@ def lattice(nx=1000, ny=1000, pitch=12.0, cfg: GbpConfig | None = None, planning
                    name=f"lattice-{nx}x{ny}", meta={"nx": nx, "ny": ny, "pitch": pitch, "rows": (r0, r1)})
 
 
+def dense_lattice(nx=500, ny=500, pitch=2.0, comms_radius=4.5, cfg: GbpConfig | None = None, planning_horizon=5.0,
+                  lookahead_multiple=3, robot_radius=1.0, goal_ahead=500.0):
+    """Stress workload (not a BASELINE config): a lattice tighter than the safety distance 2.2 * radius, so the
+    InterRobot factors of the four nearest neighbours are ACTIVE (no `skip` exit), with K = 20 neighbours inside the
+    comms radius, and rows alternately heading +x / -x so that neighbouring rows shear past each other: InterRobot
+    factors are created and deleted every tick.  Everything the lattice-1M benchmark never exercises."""
+    cfg = cfg or GbpConfig(target_speed=3.6, comms_radius=comms_radius, world_width=100.0, world_height=100.0)
+    ts = get_variable_timesteps(lookahead_horizon(cfg.target_speed, planning_horizon), lookahead_multiple)
+    cfg = replace(cfg, num_variables=int(ts.shape[0]))
+    ix, iy = np.meshgrid(np.arange(nx), np.arange(ny))
+    x = (ix.reshape(-1) - (nx - 1) / 2.0) * pitch
+    y = (iy.reshape(-1) - (ny - 1) / 2.0) * pitch
+    starts = np.stack([x, y], axis=1).astype(f32)
+    sign = np.where(iy.reshape(-1) % 2 == 0, 1.0, -1.0)
+    goals = (starts + np.stack([sign * goal_ahead, np.zeros_like(sign)], axis=1)).astype(f32)
+    n = nx * ny
+    return _finish(cfg, np.full(n, robot_radius, f32), starts, goals, ts, planning_horizon, sdf=white_sdf(),
+                   name=f"dense-{nx}x{ny}", meta={"nx": nx, "ny": ny, "pitch": pitch})
+
+
 def junction_twoway(per_lane=3, seed=0):
     """Config 2: `Structured Junction Twoway` scalars (all four factor kinds, V=12),
     12 lanes (4 arms x {left, straight, right}) through a '+' junction with a

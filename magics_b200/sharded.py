@@ -161,6 +161,30 @@ class LocalShards:
             m = (robots >= lo) & (robots < hi)
             w.change_prior_of_variable(variable_index, (robots[m] - lo).astype(np.int32), new_means[m])
 
+    def _by_shard(self, robots):
+        robots = np.asarray(robots, np.int64)
+        for q, w in enumerate(self.shards):
+            lo, hi = self.bounds[q], self.bounds[q + 1]
+            yield w, (robots >= lo) & (robots < hi), lo
+
+    def reset_variables(self, robots, means, first_last_sigma=1e30, inbetween_sigma=float("inf")):
+        robots = np.asarray(robots, np.int64)
+        means = np.asarray(means, np.float64).reshape(robots.size, self.V, 4)
+        for w, m, lo in self._by_shard(robots):
+            w.reset_variables((robots[m] - lo).astype(np.int32), means[m], first_last_sigma, inbetween_sigma)
+
+    def set_tracking_path(self, robots, paths):
+        robots = np.asarray(robots, np.int64)
+        for w, m, lo in self._by_shard(robots):
+            if m.any():
+                w.set_tracking_path((robots[m] - lo).astype(np.int32), [p for p, k in zip(paths, m) if k])
+
+    def reset_tracking_factors(self, robots):
+        robots = np.asarray(robots, np.int64)
+        for w, m, lo in self._by_shard(robots):
+            if m.any():
+                w.reset_tracking_factors((robots[m] - lo).astype(np.int32))
+
     def remove_robots(self, robots):
         robots = np.asarray(robots, np.int64)
         for q, w in enumerate(self.shards):

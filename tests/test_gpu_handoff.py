@@ -55,11 +55,18 @@ def test_rrt_path_arrives_for_some_robots_of_the_junction():
         check(g, o, f"tick {tick} after hand-off")
 
 
-def test_reset_of_robots_with_active_interrobot_factors():
+@pytest.mark.parametrize("ws", [1, 3])
+def test_reset_of_robots_with_active_interrobot_factors(ws):
     """Both ends of an edge reset, one end reset, and a reset while the neighbour's radio is off: the robot's own
-    InterRobot factors lose the neighbour's message until the neighbour delivers again."""
+    InterRobot factors lose the neighbour's message until the neighbour delivers again.  ws = 3: the swarm is split
+    over three shards, so most reset robots have neighbours whose factors live on another shard."""
     sw = scenarios.circle(12, circle_radius=14.0)
-    g, o = make_pair(sw)
+    if ws == 1:
+        g, o = make_pair(sw)
+    else:
+        g, o = LocalShards(sw.cfg, ws), OracleWorld(sw.cfg)
+        sw.add_to(g)
+        sw.add_to(o)
     V = sw.cfg.num_variables
     for _ in range(4):
         g.step()
@@ -124,8 +131,3 @@ def test_tracking_path_only_and_errors():
         g.set_tracking_path([1], [path[:1]])
     with pytest.raises(RuntimeError):
         g.reset_variables([99], np.zeros((1, sw.cfg.num_variables, 4)))
-    sh = LocalShards(sw.cfg, 2)
-    sw.add_to(sh)
-    with pytest.raises(RuntimeError):
-        sh.shards[0].reset_variables([0], np.zeros((1, sw.cfg.num_variables, 4)))
-    sh.close()

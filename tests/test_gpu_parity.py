@@ -91,6 +91,22 @@ def test_all_schedules(kind, internal, external):
         check(g, o, f"schedule {kind} {internal}/{external} tick {tick}")
 
 
+def test_open_half_iteration_pair_refuses_reads_and_changes():
+    """internal_factor_iteration alone only opens a pair (the factor half runs fused with the variable half): until it
+    is closed the engine refuses to show or change state the reference would already have advanced."""
+    sw = scenarios.circle(4, circle_radius=6.0)
+    g, o = make_pair(sw)
+    g.internal_factor_iteration()
+    for call in (g.read_beliefs, lambda: g.set_comms(np.ones(4, np.uint8), None), g.update_topology, g.iterate,
+                 g.external_factor_iteration, lambda: g.remove_robots([0])):
+        with pytest.raises(RuntimeError, match="half-iteration|order|pair"):
+            call()
+    g.internal_variable_iteration()
+    o.internal_factor_iteration()
+    o.internal_variable_iteration()
+    check(g, o, "pair closed")
+
+
 def test_junction_twoway_all_factor_kinds():
     """BASELINE config 2: tracking + obstacle + interrobot + dynamic, V=12."""
     sw = scenarios.junction_twoway(per_lane=2)
