@@ -76,6 +76,13 @@ typedef struct gbp_config {
   int32_t iterations_external;
   double world_width;               /* obstacle::WorldSize (robot.rs:1258-1263) */
   double world_height;
+  /* 0 (default): every InterRobot factor between two robots that have left each other's comms range is deleted.
+   * 1: delete_interrobot_factors exactly as written (robot.rs:1386-1439): the (robot, lost
+   *    neighbour) pairs go through a HashMap keyed by robot, so a robot that loses several neighbours in one tick
+   *    keeps only its LAST (largest id) pair; a lost pair (a, b) is deleted iff b is a's last lost neighbour or a is
+   *    b's.  The others stay as factor sets nobody lists in `robots_connected_with` any more; they keep being
+   *    iterated, and when the pair meets again a second set is created next to them.  Single-GPU worlds only. */
+  int32_t strict_reference_quirks;
 } gbp_config_t;
 
 typedef struct gbp_world gbp_world_t; /* opaque */
@@ -382,7 +389,11 @@ enum gbp_profile_kind {
   GBP_PROFILE_PRIORS = 4,          /* horizon + current prior kernels */
   GBP_PROFILE_HALO = 5,            /* the send/recv part of the per-sub-step halo exchange */
   GBP_PROFILE_ITERATE_GENERAL = 6, /* k_iterate over the robots k_iterate_axis handed over (any EXT/INT) */
-  GBP_PROFILE_KINDS = 7
+  GBP_PROFILE_TOPO_POSITIONS = 7,  /* sharded worlds: the exchange of every robot's position / radius / despawned flag */
+  GBP_PROFILE_TOPO_SEARCH = 8,     /* neighbour search + diff against the live edges, up to the size read-back */
+  GBP_PROFILE_TOPO_APPLY = 9,      /* sharded: header / cross-shard robot_number exchange; then the new edge set */
+  GBP_PROFILE_ITERATE_BORDER = 10, /* sharded: k_iterate_axis over the border robots (any EXT/INT), launched before the rest */
+  GBP_PROFILE_KINDS = 11
 };
 int gbp_world_set_profiling(gbp_world_t *w, int32_t on);
 int gbp_world_read_profile(gbp_world_t *w, int32_t kind, int64_t *count, double *total_ms);

@@ -40,6 +40,7 @@ class CConfig(C.Structure):
         ("iterations_external", C.c_int32),
         ("world_width", C.c_double),
         ("world_height", C.c_double),
+        ("strict_reference_quirks", C.c_int32),
     ]
 
 
@@ -68,6 +69,7 @@ class GbpConfig:
     iterations_external: int = 10
     world_width: float = 100.0
     world_height: float = 100.0
+    strict_reference_quirks: int = 0  # 1: delete_interrobot_factors as written (lossy HashMap)
 
     def to_c(self) -> CConfig:
         return CConfig(**{f.name: getattr(self, f.name) for f in fields(self)})

@@ -479,11 +479,13 @@ __global__ void k_reset_reverse_edges(Store s, int m, const int32_t *__restrict_
       if (s.gid[s.enbr[mid]] < gr) lo = mid + 1;
       else hi = mid;
     }
-    if (lo >= s.eoff[A + 1] || s.enbr[lo] != r) continue;
-    s.e_frozen[lo] = uint8_t(s.e_frozen[lo] | 1);
-    for (int i = 0; i < Vm1; ++i) {
-      s.mu_frozen[lo * Vm1 + i] = 0.0;
-      s.mu_frozen[s.EV + lo * Vm1 + i] = 0.0;
+    // every factor set toward r (strict_reference_quirks can leave more than one)
+    for (; lo < s.eoff[A + 1] && s.enbr[lo] == r; ++lo) {
+      s.e_frozen[lo] = uint8_t(s.e_frozen[lo] | 1);
+      for (int i = 0; i < Vm1; ++i) {
+        s.mu_frozen[lo * Vm1 + i] = 0.0;
+        s.mu_frozen[s.EV + lo * Vm1 + i] = 0.0;
+      }
     }
   }
 }
@@ -670,6 +672,12 @@ struct gbp_world {
   int64_t *t_result_dev = nullptr, *t_result_host = nullptr;
   // topology scratch
   int32_t *t_cx = nullptr, *t_cz = nullptr, *t_idx = nullptr, *t_idx_sorted = nullptr;
+  // strict_reference_quirks (single GPU): robots within range as their own CSR, largest lost neighbour, zombie flags
+  int32_t *q_wnbr = nullptr, *q_maxlost = nullptr;
+  int64_t *q_woff = nullptr;
+  uint8_t *q_zombie = nullptr;
+  int64_t q_wcap = 0, q_zcap = 0, q_ncap = 0;
+  int32_t *t_park = nullptr;     // neighbour ids found by the counting pass, kNbrPark per own robot
   int32_t *t_box = nullptr;      // sharded neighbour search: own bounding box [0..3], candidates found [4]
   int64_t cand_cap = 0;          // entries the hash of a sharded world sorts (grows when a pass finds more)
   uint32_t *t_keys = nullptr, *t_keys_sorted = nullptr;
@@ -739,10 +747,15 @@ struct gbp_world {
   // halo / compute overlap: the robots of the send lists ("border") run first, their records travel on
   // comm_stream while the interior robots run on `stream`
   cudaStream_t comm_stream = nullptr;  // == stream for in-process shards (one device, one stream)
+  cudaStream_t border_stream = nullptr;  // highest priority: the border robots' launches run CONCURRENTLY with the
+                                         // interior launch and finish first (== stream for in-process shards)
+  cudaEvent_t ev_start = nullptr;        // everything before this half-step pair is done (border_stream waits for it)
+  int32_t *border_gen_list = nullptr, *border_gen_count = nullptr;  // the border launches' own hand-over list
+  int border_par = 0;
   cudaEvent_t ev_border = nullptr, ev_halo = nullptr, ev_fence = nullptr;
   uint32_t *border_words = nullptr;    // Store-side flags, one byte per own robot, as words for atomicOr
   int32_t *border_list = nullptr, *border_count = nullptr;
-  int64_t border_cap = 0, border_words_cap = 0;
+  int64_t border_cap = 0, border_words_cap = 0, border_gen_cap = 0;
   int64_t n_border_max = 0;            // length of the send lists = upper bound of *border_count
   int64_t halo_send_cap = 0, halo_recv_cap = 0;  // in doubles
   gbp::PeerOffsets ghost_po{}, send_po{};        // live halo layout (records per peer block)
@@ -811,17 +824,18 @@ cudaEvent_t take_event(gbp_world *w) {
 }
 struct ProfileScope {
   gbp_world *w;
+  cudaStream_t st;
   gbp_world::Span sp{};
-  ProfileScope(gbp_world *w_, int kind) : w(w_) {
+  ProfileScope(gbp_world *w_, int kind, cudaStream_t st_ = nullptr) : w(w_), st(st_ ? st_ : w_->stream) {
     if (!w->profiling) return;
     sp.kind = kind;
     sp.a = take_event(w);
     sp.b = take_event(w);
-    cudaEventRecord(sp.a, w->stream);
+    cudaEventRecord(sp.a, st);
   }
   ~ProfileScope() {
     if (!w->profiling) return;
-    cudaEventRecord(sp.b, w->stream);
+    cudaEventRecord(sp.b, st);
     w->spans.push_back(sp);
   }
 };
@@ -926,7 +940,7 @@ int group_halo(gbp_group *g, bool ahead = false) {
     cudaStream_t st = ahead ? w->comm_stream : w->stream;
     const int pb = ahead ? 1 - w->p : w->p;
     if (ahead && w->comm_stream != w->stream) {
-      CK(cudaEventRecord(w->ev_border, w->stream));
+      CK(cudaEventRecord(w->ev_border, w->border_stream));
       CK(cudaStreamWaitEvent(w->comm_stream, w->ev_border, 0));
     }
     const int64_t hd = gbp::halo_doubles_per_robot(s.V);
@@ -1005,7 +1019,17 @@ int group_halo_ready(gbp_group *g) {
 // part 0 = every own robot, 1 = the border robots (send lists), 2 = the others.
 template <bool EXT, bool INT>
 int launch_iterate(gbp_world *w, int part) {
-  Store &s = w->s;
+  // The border part runs on its own high-priority stream with its own hand-over list, concurrently with the
+  // interior part on w->stream (group_launch orders them with events).
+  Store s = w->s;
+  cudaStream_t st = w->stream;
+  int *par = &w->par;
+  if (part == 1) {
+    st = w->border_stream;
+    s.gen_list = w->border_gen_list;
+    s.gen_count = w->border_gen_count;
+    par = &w->border_par;
+  }
   const int which = (EXT ? 2 : 0) + (INT ? 1 : 0);
   if (s.Nloc == 0) return 0;
   const int rpw = 32 / s.V;
@@ -1015,7 +1039,7 @@ int launch_iterate(gbp_world *w, int part) {
     const int64_t warps = (int64_t(s.Nloc) + rpw - 1) / rpw;
     const unsigned grid = unsigned((warps + wpb - 1) / wpb);
     ProfileScope ps(w, kind);
-    gbp::k_iterate<EXT, INT><<<grid, gbp::kIterBlock, 0, w->stream>>>(s, w->p, w->epoch, -1);
+    gbp::k_iterate<EXT, INT><<<grid, gbp::kIterBlock, 0, st>>>(s, w->p, w->epoch, -1);
     w->launches += 1;
   } else {
     // the decoupled robots (two lanes per variable), then whatever that kernel handed over
@@ -1030,16 +1054,18 @@ int launch_iterate(gbp_world *w, int part) {
     }
     const int64_t nrob = part == 1 ? w->n_border_max : int64_t(s.Nloc);
     if (nrob > 0) {
-      ProfileScope ps(w, kind);
-      kernel<<<blocks_for(nrob, q.rpc), q.threads, q.smem, w->stream>>>(
-          s, w->p, w->epoch, q.rpc, w->par, w->border_list, w->border_count,
-          reinterpret_cast<const uint8_t *>(w->border_words));
+      {
+        ProfileScope ps(w, part == 1 ? int(GBP_PROFILE_ITERATE_BORDER) : kind, st);
+        kernel<<<blocks_for(nrob, q.rpc), q.threads, q.smem, st>>>(s, w->p, w->epoch, q.rpc, *par, w->border_list,
+                                                                  w->border_count,
+                                                                  reinterpret_cast<const uint8_t *>(w->border_words));
+      }
       CK(cudaGetLastError());
       const int64_t warps = (nrob + rpw - 1) / rpw;
       const unsigned grid = unsigned(std::min<int64_t>((warps + wpb - 1) / wpb, int64_t(w->sm_count) * 4));
-      ProfileScope pg(w, GBP_PROFILE_ITERATE_GENERAL);
-      gbp::k_iterate<EXT, INT><<<grid, gbp::kIterBlock, 0, w->stream>>>(s, w->p, w->epoch, w->par);
-      w->par ^= 1;
+      ProfileScope pg(w, GBP_PROFILE_ITERATE_GENERAL, st);
+      gbp::k_iterate<EXT, INT><<<grid, gbp::kIterBlock, 0, st>>>(s, w->p, w->epoch, *par);
+      *par ^= 1;
       w->launches += 2;
     }
   }
@@ -1072,14 +1098,22 @@ int group_launch(gbp_group *g) {
     }
     if (INT) g->halo_stale = true;
   } else {
+    // border robots on the high-priority stream (behind everything queued so far), the halo of their new records
+    // on the comm stream behind them, the other robots on the shard's own stream at the same time
     for (gbp_world *w : g->members) {
       CK(cudaSetDevice(w->device));
+      if (w->border_stream != w->stream) {
+        CK(cudaEventRecord(w->ev_start, w->stream));
+        CK(cudaStreamWaitEvent(w->border_stream, w->ev_start, 0));
+      }
       if (int rc = launch_iterate<EXT, INT>(w, 1)) return rc;
     }
     if (int rc = group_halo(g, true)) return rc;
     for (gbp_world *w : g->members) {
       CK(cudaSetDevice(w->device));
       if (int rc = launch_iterate<EXT, INT>(w, 2)) return rc;
+      // what follows on the shard's own stream sees the border robots' results too
+      if (w->border_stream != w->stream) CK(cudaStreamWaitEvent(w->stream, w->ev_border, 0));
     }
   }
   if (INT)
@@ -1186,6 +1220,8 @@ int ensure_topology_scratch(gbp_world *w) {
   bool regrow_cub = false;
   if (!w->t_cnt || nloc > w->t_cap) {
     cudaFree(w->t_nlow); cudaFree(w->t_cnt); cudaFree(w->t_off); cudaFree(w->t_newcnt); cudaFree(w->t_newoff);
+    cudaFree(w->t_park);
+    CK(dalloc(w->t_park, size_t(nloc) * gbp::kNbrPark + 1));
     CK(dalloc(w->t_nlow, nloc));
     CK(dalloc(w->t_cnt, nloc + 1)); CK(dalloc(w->t_off, nloc + 1));
     CK(dalloc(w->t_newcnt, nloc + 1)); CK(dalloc(w->t_newoff, nloc + 1));
@@ -1331,8 +1367,8 @@ int topo_search(gbp_world *w) {
   size_t cb = w->t_cub_bytes;
   CK(cub::DeviceRadixSort::SortPairs(w->t_cub, cb, w->t_keys, w->t_keys_sorted, w->t_idx, w->t_idx_sorted, nall, 0, 32, st));
   if (n > 0)
-    gbp::k_neighbours<false><<<blocks_for(n, T), T, 0, st>>>(nall, g0, n, gx, gz, w->t_cx, w->t_cz, w->t_keys_sorted,
-                                                             w->t_idx_sorted, R, w->t_cnt, nullptr, 0);
+    gbp::k_neighbours_find<<<blocks_for(n, T), T, 0, st>>>(nall, g0, n, gx, gz, w->t_cx, w->t_cz, w->t_keys_sorted,
+                                                           w->t_idx_sorted, R, w->t_cnt, w->t_park);
   CK(cudaMemsetAsync(w->t_cnt + n, 0, sizeof(int64_t), st));
   cb = w->t_cub_bytes;
   CK(cub::DeviceScan::ExclusiveSum(w->t_cub, cb, w->t_cnt, w->t_off, n + 1, st));
@@ -1341,10 +1377,51 @@ int topo_search(gbp_world *w) {
   // guarded kernels did nothing: grow it and run them again.
   EdgeSet *spare = &w->edges[1 - w->cur];
   const EdgeSet *live = &w->edges[w->cur];
+  const bool quirk = w->cfg.strict_reference_quirks != 0;
+  if (quirk && n > 0) {
+    // delete_interrobot_factors as written: the robots within range become their own CSR (q_woff, q_wnbr); the new
+    // rows are the old edges that survive the lossy deletion merged with fresh edges (k_quirk_rows).  A test mode:
+    // two extra size read-backs per tick instead of the guarded relaunch scheme.
+    int64_t nw = 0;
+    CK(cudaMemcpyAsync(&nw, w->t_off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (int rc = ensure_buf(w, w->q_wnbr, w->q_wcap, std::max<int64_t>(nw, 1))) return rc;
+    if (n > w->q_ncap) {
+      cudaFree(w->q_maxlost);
+      cudaFree(w->q_woff);
+      CK(dalloc(w->q_maxlost, size_t(n)));
+      CK(dalloc(w->q_woff, size_t(n) + 1));
+      w->q_ncap = n;
+    }
+    gbp::k_neighbours_fill<<<blocks_for(n, T), T, 0, st>>>(nall, g0, n, gx, gz, w->t_cx, w->t_cz, w->t_keys_sorted,
+                                                           w->t_idx_sorted, R, w->t_off, w->t_park, w->q_wnbr, w->q_wcap);
+    CK(cudaMemcpyAsync(w->q_woff, w->t_off, size_t(n + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    const int64_t *ooff = s.E > 0 ? s.eoff : nullptr;
+    gbp::k_quirk_lost_max<<<blocks_for(n, T), T, 0, st>>>(n, ooff, live->egid, live->e_frozen, s.gone, w->q_woff,
+                                                          w->q_wnbr, w->q_maxlost);
+    gbp::k_quirk_rows<false><<<blocks_for(n, T), T, 0, st>>>(n, ooff, live->egid, live->e_frozen, s.gone, w->q_woff,
+                                                             w->q_wnbr, w->q_maxlost, w->t_cnt, nullptr, nullptr, nullptr,
+                                                             nullptr, nullptr);
+    CK(cudaMemsetAsync(w->t_cnt + n, 0, sizeof(int64_t), st));
+    cb = w->t_cub_bytes;
+    CK(cub::DeviceScan::ExclusiveSum(w->t_cub, cb, w->t_cnt, w->t_off, n + 1, st));
+    int64_t e1 = 0;
+    CK(cudaMemcpyAsync(&e1, w->t_off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (e1 > spare->cap)
+      if (int rc = grow_edge_set(w, spare, e1 + e1 / 4 + 1024)) return rc;
+    if (int rc = ensure_buf(w, w->q_zombie, w->q_zcap, std::max<int64_t>(e1, 1))) return rc;
+    gbp::k_quirk_rows<true><<<blocks_for(n, T), T, 0, st>>>(n, ooff, live->egid, live->e_frozen, s.gone, w->q_woff,
+                                                            w->q_wnbr, w->q_maxlost, w->t_off, spare->egid, spare->map,
+                                                            w->q_zombie, w->t_newcnt, w->t_nlow);
+    CK(cudaGetLastError());
+    w->launches += 6;
+  }
   for (int attempt = 0; attempt < 2; ++attempt) {
-    if (n > 0) {
-      gbp::k_neighbours<true><<<blocks_for(n, T), T, 0, st>>>(nall, g0, n, gx, gz, w->t_cx, w->t_cz, w->t_keys_sorted,
-                                                              w->t_idx_sorted, R, w->t_off, spare->egid, spare->cap);
+    if (n > 0 && !quirk) {
+      gbp::k_neighbours_fill<<<blocks_for(n, T), T, 0, st>>>(nall, g0, n, gx, gz, w->t_cx, w->t_cz, w->t_keys_sorted,
+                                                             w->t_idx_sorted, R, w->t_off, w->t_park, spare->egid,
+                                                             spare->cap);
       gbp::k_edge_diff<<<blocks_for(n, T), T, 0, st>>>(n, g0, w->t_off, spare->egid, s.eoff, live->egid, n, spare->map,
                                                        w->t_newcnt, w->t_nlow, spare->cap);
     }
@@ -1403,7 +1480,8 @@ int topo_search(gbp_world *w) {
       w->tp.cross_po.start[q] = w->t_result_host[4 + 2 * (ws + 1) + q];
     }
   }
-  w->tp.changed = w->tp.total_new != 0 || w->tp.E1 != s.E || w->force_rebuild;
+  // quirk mode: an edge can turn into a zombie without any edge appearing or disappearing — always rebuild
+  w->tp.changed = w->tp.total_new != 0 || w->tp.E1 != s.E || w->force_rebuild || quirk;
   return 0;
 }
 
@@ -1489,7 +1567,8 @@ int topo_apply(gbp_world *w, const int64_t (*hdr)[4]) {
     gbp::k_edge_assign_own<<<blocks_for(n, T), T, 0, st>>>(
         n, s.V, w->t_off, spare->egid, spare->map, w->t_newoff, gradius, double(w->cfg.safety_distance_multiplier),
         w->robot_number, bases.base[rank], w->epoch, live->e_own, live->e_rnum, live->e_birth, live->e_frozen,
-        spare->e_own, spare->e_dsafe, spare->e_rnum, spare->e_birth, spare->e_frozen);
+        spare->e_own, spare->e_dsafe, spare->e_rnum, spare->e_birth, spare->e_frozen,
+        w->cfg.strict_reference_quirks ? w->q_zombie : nullptr);
     gbp::k_edge_pull<<<blocks_for(n, T), T, 0, st>>>(w->sh, n, s.V, w->t_off, spare->egid, spare->map, spare->e_own,
                                                      w->robot_number, bases, w->tp.cross_po, w->ckeys_r, w->cvals_r,
                                                      spare->e_rnum, w->t_err);
@@ -1513,6 +1592,11 @@ int topo_apply(gbp_world *w, const int64_t (*hdr)[4]) {
     if (int rc = ensure_buf(w, w->border_list, w->border_cap, std::max<int64_t>(nsend, 1))) return rc;
     if (int rc = ensure_buf(w, w->border_words, w->border_words_cap, (int64_t(s.cap) + 3) / 4 + 1)) return rc;
     if (!w->border_count) CK(dalloc(w->border_count, 1));
+    if (!w->border_gen_count) {
+      CK(dalloc(w->border_gen_count, 2));
+      CK(cudaMemsetAsync(w->border_gen_count, 0, 2 * sizeof(int32_t), st));
+    }
+    if (int rc = ensure_buf(w, w->border_gen_list, w->border_gen_cap, std::max<int64_t>(nsend, 1))) return rc;
     CK(cudaMemsetAsync(w->border_words, 0, size_t(w->border_words_cap) * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(w->border_count, 0, sizeof(int32_t), st));
     if (nsend > 0) {
@@ -1550,6 +1634,7 @@ int group_update_topology(gbp_group *g) {
   const size_t nm = g->members.size();
   std::vector<gbp::XferPlan> plans(nm);
   if (ws > 1) {
+    ProfileScope pp(g->members[0], GBP_PROFILE_TOPO_POSITIONS);
     // every shard learns every robot's Transform (x, z), radius and despawned flag: 16 bytes per robot per tick
     for (size_t m = 0; m < nm; ++m) {
       gbp_world *w = g->members[m];
@@ -1571,8 +1656,12 @@ int group_update_topology(gbp_group *g) {
     // sends are grouped by plane then peer on both sides, so the k-th send to a peer pairs with its k-th receive
     if (int rc = exchange(g, plans)) return rc;
   }
-  for (gbp_world *w : g->members)
-    if (int rc = topo_search(w)) return rc;
+  {
+    ProfileScope pq(g->members[0], GBP_PROFILE_TOPO_SEARCH);
+    for (gbp_world *w : g->members)
+      if (int rc = topo_search(w)) return rc;
+  }
+  ProfileScope pa(g->members[0], GBP_PROFILE_TOPO_APPLY);
   int64_t hdr[gbp::kMaxShards][4];
   if (ws == 1) {
     gbp_world *w = g->members[0];
@@ -1743,6 +1832,13 @@ void join_group(gbp_world *w, gbp_group *g, int rank) {
   cudaEventCreateWithFlags(&w->ev_border, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&w->ev_halo, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&w->ev_fence, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&w->ev_start, cudaEventDisableTiming);
+  w->border_stream = w->stream;
+  if (g->nccl) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = highest priority
+    cudaStreamCreateWithPriority(&w->border_stream, cudaStreamNonBlocking, hi);
+  }
   w->grp = g;
   w->sh.ws = g->ws;
   w->sh.rank = rank;
@@ -1779,6 +1875,11 @@ gbp_world_t *gbp_world_create_shard(const gbp_config_t *cfg, int32_t device, int
     return nullptr;
   }
   if (world_size == 1) return gbp_world_create(cfg, device);
+  if (cfg && cfg->strict_reference_quirks) {
+    fail(GBP_ERR_BAD_ARGUMENT, "strict_reference_quirks is available on single-GPU worlds only (a pair is deleted or kept "
+                               "depending on the lost neighbours of BOTH robots)");
+    return nullptr;
+  }
   gbp::NcclApi &api = gbp::nccl_api();
   if (!api.load()) {
     fail(GBP_ERR_NCCL, api.error);
@@ -1804,6 +1905,8 @@ gbp_world_t *gbp_world_create_shard(const gbp_config_t *cfg, int32_t device, int
 int gbp_world_create_local_shards(const gbp_config_t *cfg, int32_t device, int32_t world_size, gbp_world_t **out) {
   if (!out || world_size < 1 || world_size > gbp::kMaxShards)
     return fail(GBP_ERR_BAD_ARGUMENT, "gbp_world_create_local_shards: need 1 <= world_size <= 16");
+  if (cfg && cfg->strict_reference_quirks && world_size > 1)
+    return fail(GBP_ERR_BAD_ARGUMENT, "strict_reference_quirks is available on single-GPU worlds only");
   gbp_group *g = new gbp_group();
   g->ws = world_size;
   g->committed = world_size == 1;
@@ -1840,7 +1943,13 @@ void gbp_world_destroy(gbp_world_t *w) {
     cudaStreamSynchronize(w->comm_stream);
     cudaStreamDestroy(w->comm_stream);
   }
-  for (cudaEvent_t e : {w->ev_border, w->ev_halo, w->ev_fence})
+  if (w->border_stream && w->border_stream != w->stream) {
+    cudaStreamSynchronize(w->border_stream);
+    cudaStreamDestroy(w->border_stream);
+  }
+  cudaFree(w->border_gen_list);
+  cudaFree(w->border_gen_count);
+  for (cudaEvent_t e : {w->ev_border, w->ev_halo, w->ev_fence, w->ev_start})
     if (e) cudaEventDestroy(e);
   cudaFree(w->border_list);
   cudaFree(w->border_words);
@@ -1850,7 +1959,7 @@ void gbp_world_destroy(gbp_world_t *w) {
                   s.trk_record, s.trk_timeout, s.trk_seed, s.trk_last, s.trk_value, s.radius, s.t0, s.pos, s.antenna,
                   s.idle, s.finished, s.gone, s.latest, s.iter_factor, s.gid, s.next_wp, s.coll_hits, w->coll_totals, s.wp_off, s.wp_xy, s.eoff,
                   s.nlow, w->t_nlow, w->t_result_dev, w->sdf_dev, w->t_cx,
-                  w->t_cz, w->t_box, w->t_idx, w->t_idx_sorted, w->t_keys, w->t_keys_sorted, w->t_cnt, w->t_off,
+                  w->t_cz, w->t_box, w->t_park, w->q_wnbr, w->q_maxlost, w->q_woff, w->q_zombie, w->t_idx, w->t_idx_sorted, w->t_keys, w->t_keys_sorted, w->t_cnt, w->t_off,
                   w->t_newcnt, w->t_newoff, w->t_cub, w->rb_dev, w->gpos, w->t_gflag, w->t_gslot, w->t_sflag,
                   w->t_soff, w->t_ccnt, w->t_coff, w->t_err, w->sendlist, w->ckeys_s, w->cvals_s, w->ckeys_r,
                   w->cvals_r, w->hdr_send, w->hdr_recv, w->halo_send, w->halo_recv};
@@ -2850,6 +2959,25 @@ int64_t gbp_world_read_connections(gbp_world_t *w, int64_t *offsets, int32_t *ne
     if (robot_number) {
       static_assert(sizeof(int64_t) == sizeof(uint64_t), "");
       CK(cudaMemcpy(robot_number, e.e_own, size_t(s.E) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    }
+    if (w->cfg.strict_reference_quirks) {
+      // robots_connected_with lists live connections only: the factor sets the lossy deletion left behind
+      // (e_frozen bit 2) are dropped from the answer, the lists closed up
+      std::vector<uint8_t> fl(size_t(s.E));
+      CK(cudaMemcpy(fl.data(), e.e_frozen, size_t(s.E), cudaMemcpyDeviceToHost));
+      const std::vector<int64_t> orig(offsets, offsets + s.Nloc + 1);
+      int64_t out = 0;
+      for (int32_t r = 0; r < s.Nloc; ++r) {
+        offsets[r] = out;
+        for (int64_t k = orig[size_t(r)]; k < orig[size_t(r) + 1]; ++k) {
+          if (fl[size_t(k)] & gbp::kEdgeZombie) continue;
+          if (neighbours) neighbours[out] = neighbours[k];
+          if (robot_number) robot_number[out] = robot_number[k];
+          ++out;
+        }
+      }
+      offsets[s.Nloc] = out;
+      return out;
     }
   }
   return s.E;

@@ -103,21 +103,38 @@ GBP_DEV AxisRows axis_rows(const Store &s, int a, int64_t vi) {
   const int64_t b = s.at<P>(0, vi);
   return {b + a * kTile, b + (4 + 5 * a) * kTile};
 }
+#ifndef GBP_AXIS_STREAM
+#define GBP_AXIS_STREAM 0  // 1: evict-first loads / stores for rows nobody else reads in this launch
+#endif
+GBP_DEV double ld_row(const double *p) {
+#if GBP_AXIS_STREAM
+  return __ldcs(p);
+#else
+  return *p;
+#endif
+}
+GBP_DEV void st_row(double *p, double v) {
+#if GBP_AXIS_STREAM
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
 GBP_DEV void ld_axis(const double *__restrict__ arr, AxisRows q, double (&e)[2], double (&L)[4]) {
-  e[0] = arr[q.v];
-  e[1] = arr[q.v + 2 * kTile];
-  L[0] = arr[q.m];
-  L[1] = arr[q.m + 2 * kTile];
-  L[2] = arr[q.m + 8 * kTile];
-  L[3] = arr[q.m + 10 * kTile];
+  e[0] = ld_row(arr + q.v);
+  e[1] = ld_row(arr + q.v + 2 * kTile);
+  L[0] = ld_row(arr + q.m);
+  L[1] = ld_row(arr + q.m + 2 * kTile);
+  L[2] = ld_row(arr + q.m + 8 * kTile);
+  L[3] = ld_row(arr + q.m + 10 * kTile);
 }
 GBP_DEV void st_axis(double *__restrict__ arr, AxisRows q, const double (&e)[2], const double (&L)[4]) {
-  arr[q.v] = e[0];
-  arr[q.v + 2 * kTile] = e[1];
-  arr[q.m] = L[0];
-  arr[q.m + 2 * kTile] = L[1];
-  arr[q.m + 8 * kTile] = L[2];
-  arr[q.m + 10 * kTile] = L[3];
+  st_row(arr + q.v, e[0]);
+  st_row(arr + q.v + 2 * kTile, e[1]);
+  st_row(arr + q.m, L[0]);
+  st_row(arr + q.m + 2 * kTile, L[1]);
+  st_row(arr + q.m + 8 * kTile, L[2]);
+  st_row(arr + q.m + 10 * kTile, L[3]);
 }
 
 // The loads of a launch come in three dependent waves instead of one per use (the kernel is bound by
@@ -147,9 +164,9 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
   if (PART == 1) {
     live = rl < rpc && ridx < int64_t(*nlist);
     r = live ? int64_t(list[ridx]) : 0;
-  } else if (PART == 2) {
-    live = live && !skip[r];
   }
+  // PART 2: a flagged (border) robot is skipped, but nothing waits for its flag: it is read with the other
+  // per-robot flags of wave 1 and only decides `work` (gating the first loads on it cost 5 % of the launch)
   const int64_t vi = live ? r * V + i : 0;
   double *const xr = sh;                             // [6][T] variable -> Dynamic factor i   (its right-hand factor)
   double *const xl = sh + 6 * T;                     // [6][T] variable -> Dynamic factor i-1 (its left-hand factor)
@@ -204,7 +221,7 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
   }
 #endif
   // ---- wave 1 ---------------------------------------------------------------------------------
-  bool was_general = false, idle = true, ant = false, latest = false;
+  bool was_general = false, idle = true, ant = false, latest = false, skipped = false;
   uint32_t itf = 0u;
   int64_t eo0 = 0, eo1 = 0;
   int32_t nlow = 0;
@@ -220,6 +237,7 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
     eo0 = s.eoff[r];
     eo1 = s.eoff[r + 1];
     was_general = s.mode[r] != 0;
+    if (PART == 2) skipped = skip[r] != 0;
     idle = s.idle[r] != 0;
     ant = s.antenna[r] != 0;
     latest = s.latest[r] != 0;
@@ -266,7 +284,7 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
   }
   __syncthreads();
 
-  const bool work = live && !was_general;
+  const bool work = live && !was_general && !skipped;
   const bool do_ext = EXT && work && !idle && ant;
   const bool do_int = INT && work && !idle;
   // Dynamic factors disabled: whatever they sent while enabled stays in the inbox — general kernel
@@ -497,7 +515,7 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
   if (flip) xflip[rl] = 1;
   __syncthreads();
   const bool bail = live && xbail[rl] != 0;
-  if (live && i == 0 && a == 0 && (was_general || bail)) {
+  if (live && !skipped && i == 0 && a == 0 && (was_general || bail)) {
     s.gen_list[atomicAdd(&s.gen_count[par], 1)] = int32_t(r);
     if (!was_general) s.mode[r] = 1;
   }

@@ -177,7 +177,7 @@ __global__ void k_edge_assign_own(int32_t nloc, int32_t V, const int64_t *__rest
                                   const uint64_t *__restrict__ o_own, const uint64_t *__restrict__ o_rnum,
                                   const uint32_t *__restrict__ o_birth, const uint8_t *__restrict__ o_frozen,
                                   uint64_t *e_own, double *e_dsafe, uint64_t *e_rnum, uint32_t *e_birth,
-                                  uint8_t *e_frozen) {
+                                  uint8_t *e_frozen, const uint8_t *__restrict__ zombie = nullptr) {
   const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nloc) return;
   int64_t fresh = 0;
@@ -188,7 +188,8 @@ __global__ void k_edge_assign_own(int32_t nloc, int32_t V, const int64_t *__rest
       e_own[e] = o_own[old];
       e_rnum[e] = o_rnum[old];
       e_birth[e] = o_birth[old];
-      e_frozen[e] = o_frozen[old];
+      // strict_reference_quirks: bit 2 marks a factor set its robots no longer list as a connection
+      e_frozen[e] = uint8_t((o_frozen[old] & ~4) | ((zombie && zombie[e]) ? 4 : 0));
     } else {
       e_own[e] = counter0 + uint64_t(V - 1) * uint64_t(base + newoff[r] + fresh);
       ++fresh;
@@ -224,6 +225,8 @@ __global__ void k_edge_pull(ShardInfo sh, int32_t nloc, int32_t V, const int64_t
         if (ngid[mid] < g0 + r) lo = mid + 1;
         else hi = mid;
       }
+      // strict_reference_quirks: older sets of the same pair come first; the new edge pairs with the new one
+      while (lo < end && ngid[lo] == g0 + r && map[lo] >= 0) ++lo;
       if (lo < end && ngid[lo] == g0 + r) e_rnum[e] = e_own[lo];
       else atomicExch(err, 1);
     } else {
@@ -319,6 +322,7 @@ __global__ void k_robot_collisions(Store s, const int32_t *__restrict__ egid, in
   unsigned hits = 0, pair_hits = 0, pair_now = 0;
   for (int64_t e = s.eoff[r]; e < s.eoff[r + 1]; ++e) {
     const int32_t a = s.enbr[e];
+    if (s.e_frozen[e] & 4) continue;  // not a connection (strict_reference_quirks); a touching pair has a live edge too
     const float dx = __fsub_rn(s.pos[a], ax), dz = __fsub_rn(s.pos[s.cap + a], az);
     const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dz, dz));
     const float sr = __fadd_rn(ar, s.radius[a]);

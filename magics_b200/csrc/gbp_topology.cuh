@@ -120,23 +120,18 @@ __device__ __forceinline__ int32_t lower_bound_u32(const uint32_t *a, int32_t n,
   return lo;
 }
 
-// Pass 1 (FILL = false): count robots within comms range of each of the robots
-// [first, first+count).  Pass 2 (FILL = true): write them and sort ascending.
-// `gid` maps a slot to its global robot id (the reference's Entity order).
-template <bool FILL>
-__global__ void k_neighbours(int32_t nall, int32_t first, int32_t count, const float *__restrict__ px,
-                             const float *__restrict__ pz, const int32_t *__restrict__ cx,
-                             const int32_t *__restrict__ cz, const uint32_t *__restrict__ keys_sorted,
-                             const int32_t *__restrict__ idx_sorted, float R, int64_t *cnt_or_off,
-                             int32_t *nbr, int64_t nbr_cap) {
-  const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= count) return;
-  if (FILL && cnt_or_off[count] > nbr_cap) return;  // host regrows and relaunches
-  const int32_t r = first + t;
+// Robots within comms range of robot r (index into the position arrays): the 3x3 cells around r's cell, each
+// located by binary search in the sorted keys, the reference's exact f32 predicate on every occupant.
+// Up to `cap` of them are written to `dst` in discovery order; returns how many there are.
+__device__ __forceinline__ int32_t search_neighbours(int32_t nall, int32_t r, const float *__restrict__ px,
+                                                     const float *__restrict__ pz, const int32_t *__restrict__ cx,
+                                                     const int32_t *__restrict__ cz,
+                                                     const uint32_t *__restrict__ keys_sorted,
+                                                     const int32_t *__restrict__ idx_sorted, float R, int32_t *dst,
+                                                     int32_t cap) {
   const float ax = px[r], az = pz[r];
   const int32_t mx = cx[r], mz = cz[r];
-  int64_t n = 0;
-  const int64_t base = FILL ? cnt_or_off[t] : 0;
+  int32_t n = 0;
   for (int dz = -1; dz <= 1 && mx != kNoCell; ++dz)
     for (int dx = -1; dx <= 1; ++dx) {
       const int32_t qx = mx + dx, qz = mz + dz;
@@ -145,24 +140,52 @@ __global__ void k_neighbours(int32_t nall, int32_t first, int32_t count, const f
         const int32_t o = idx_sorted[j];
         if (o == r || cx[o] != qx || cz[o] != qz) continue;
         if (!within_comms(ax, az, px[o], pz[o], R)) continue;
-        if (FILL) nbr[base + n] = o;
+        if (n < cap) dst[n] = o;
         ++n;
       }
     }
-  if (!FILL) {
-    cnt_or_off[t] = n;
+  return n;
+}
+
+// Neighbour lists in two kernels with ONE search per robot: k_neighbours_find counts the neighbours of each of the
+// robots [first, first+count) and parks up to kNbrPark of them per robot; after the exclusive scan of the counts
+// k_neighbours_fill moves the parked ids into the CSR (searching again only for a robot with more than kNbrPark
+// neighbours) and sorts each list by robot id (BTreeSet<Entity> order, robot.rs:1369-1382).
+constexpr int kNbrPark = 24;
+__global__ void k_neighbours_find(int32_t nall, int32_t first, int32_t count, const float *__restrict__ px,
+                                  const float *__restrict__ pz, const int32_t *__restrict__ cx,
+                                  const int32_t *__restrict__ cz, const uint32_t *__restrict__ keys_sorted,
+                                  const int32_t *__restrict__ idx_sorted, float R, int64_t *cnt, int32_t *park) {
+  const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  cnt[t] = search_neighbours(nall, first + t, px, pz, cx, cz, keys_sorted, idx_sorted, R,
+                             park + int64_t(t) * kNbrPark, kNbrPark);
+}
+__global__ void k_neighbours_fill(int32_t nall, int32_t first, int32_t count, const float *__restrict__ px,
+                                  const float *__restrict__ pz, const int32_t *__restrict__ cx,
+                                  const int32_t *__restrict__ cz, const uint32_t *__restrict__ keys_sorted,
+                                  const int32_t *__restrict__ idx_sorted, float R, const int64_t *__restrict__ off,
+                                  const int32_t *__restrict__ park, int32_t *nbr, int64_t nbr_cap) {
+  const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  if (off[count] > nbr_cap) return;  // host regrows and relaunches
+  const int64_t base = off[t];
+  const int32_t n = int32_t(off[t + 1] - base);
+  int32_t *a = nbr + base;
+  if (n <= kNbrPark) {
+    for (int32_t u = 0; u < n; ++u) a[u] = park[int64_t(t) * kNbrPark + u];
   } else {
-    // insertion sort by robot id (BTreeSet<Entity> order, robot.rs:1369-1382)
-    int32_t *a = nbr + base;
-    for (int64_t u = 1; u < n; ++u) {
-      const int32_t v = a[u];
-      int64_t w = u - 1;
-      while (w >= 0 && a[w] > v) {
-        a[w + 1] = a[w];
-        --w;
-      }
-      a[w + 1] = v;
+    search_neighbours(nall, first + t, px, pz, cx, cz, keys_sorted, idx_sorted, R, a, n);
+  }
+  // insertion sort by robot id
+  for (int32_t u = 1; u < n; ++u) {
+    const int32_t v = a[u];
+    int32_t w = u - 1;
+    while (w >= 0 && a[w] > v) {
+      a[w + 1] = a[w];
+      --w;
     }
+    a[w + 1] = v;
   }
 }
 
@@ -202,6 +225,101 @@ __global__ void k_edge_diff(int32_t n, int32_t g0, const int64_t *__restrict__ n
   }
   newcnt[r] = fresh;
   nlow[r] = low;
+}
+
+// ---- strict_reference_quirks: delete_interrobot_factors exactly as written --------------
+// The reference collects (robot, lost neighbour) pairs into a HashMap keyed by robot (robot.rs:1391-1404): only the
+// LAST lost neighbour of a robot — the largest id, lost neighbours are inserted in ascending order — survives, and a
+// lost pair (r, a) is deleted (both directions, every factor set between the two: factorgraph.rs:380-436) iff
+// a == maxlost[r] or r == maxlost[a].  Every robot drops all its lost neighbours from `robots_connected_with` either
+// way, so an undeleted pair stays behind as a "zombie" factor set (e_frozen bit 2): still iterated, no longer listed
+// as a connection, and joined by a second set when the two robots meet again.
+constexpr uint8_t kEdgeZombie = 4;
+
+__device__ __forceinline__ bool in_sorted(const int32_t *a, int64_t lo, int64_t hi, int32_t v) {
+  const int64_t end = hi;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo < end && a[lo] == v;
+}
+// maxlost[r]: largest neighbour r is connected with (old non-zombie edge) that is not within range any more; -1: none.
+__global__ void k_quirk_lost_max(int32_t n, const int64_t *__restrict__ ooff, const int32_t *__restrict__ onbr,
+                                 const uint8_t *__restrict__ oflags, const float *__restrict__ gone,
+                                 const int64_t *__restrict__ woff, const int32_t *__restrict__ wnbr, int32_t *maxlost) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  int32_t ml = -1;
+  if (ooff && !(gone && gone[r] != 0.0f))  // a despawned robot is not in the query: it contributes no pair
+    for (int64_t e = ooff[r]; e < ooff[r + 1]; ++e) {
+      if (oflags[e] & kEdgeZombie) continue;
+      const int32_t a = onbr[e];
+      if (!in_sorted(wnbr, woff[r], woff[r + 1], a)) ml = a > ml ? a : ml;
+    }
+  maxlost[r] = ml;
+}
+// The new row of robot r: its old edges that are not deleted (in their old order: neighbour id, then creation)
+// merged with a fresh edge for every robot within range it is not connected with.  FILL = false: row length,
+// new-edge count and nlow; FILL = true: neighbour ids, map (old edge index or -1) and zombie flags.
+template <bool FILL>
+__global__ void k_quirk_rows(int32_t n, const int64_t *__restrict__ ooff, const int32_t *__restrict__ onbr,
+                             const uint8_t *__restrict__ oflags, const float *__restrict__ gone,
+                             const int64_t *__restrict__ woff, const int32_t *__restrict__ wnbr,
+                             const int32_t *__restrict__ maxlost, int64_t *cnt_or_off, int32_t *nnbr, int64_t *map,
+                             uint8_t *zombie, int64_t *newcnt, int32_t *nlow) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  int64_t i = 0, oe = 0;
+  if (ooff && !(gone && gone[r] != 0.0f)) {  // a despawned robot's graph went with it: its row empties
+    i = ooff[r];
+    oe = ooff[r + 1];
+  }
+  int64_t j = woff[r];
+  const int64_t we = woff[r + 1];
+  int64_t out = FILL ? cnt_or_off[r] : 0, fresh = 0;
+  const int64_t out0 = out;
+  int32_t low = 0;
+  const int32_t mlr = maxlost[r];
+  while (i < oe || j < we) {
+    const int32_t ao = i < oe ? onbr[i] : INT32_MAX, aw = j < we ? wnbr[j] : INT32_MAX;
+    const int32_t a = ao < aw ? ao : aw;
+    const bool in_w = aw == a;
+    const bool covered = mlr == a || maxlost[a] == r;
+    bool had_normal = false;
+    for (; i < oe && onbr[i] == a; ++i) {
+      const bool zomb = (oflags[i] & kEdgeZombie) != 0;
+      had_normal |= !zomb;
+      if (covered) continue;  // every factor set between the two robots goes
+      if (FILL) {
+        nnbr[out] = a;
+        map[out] = i;
+        zombie[out] = (zomb || !in_w) ? 1 : 0;
+      }
+      ++out;
+      low += a < r;
+    }
+    if (in_w) {
+      if (!had_normal) {  // within range and not connected: create_interrobot_factors makes a new set
+        if (FILL) {
+          nnbr[out] = a;
+          map[out] = -1;
+          zombie[out] = 0;
+        }
+        ++out;
+        ++fresh;
+        low += a < r;
+      }
+      ++j;
+    }
+  }
+  if (!FILL) {
+    cnt_or_off[r] = out - out0;
+  } else {
+    newcnt[r] = fresh;
+    nlow[r] = low;
+  }
 }
 
 // Mirror messages (and frozen means) of surviving edges move to their new slot.

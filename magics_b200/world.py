@@ -440,7 +440,8 @@ class World:
         self._call("gbp_world_read_iterate_path", C.byref(ax), C.byref(gen))
         return int(ax.value), int(gen.value)
 
-    PROFILE_KINDS = ("iterate_int", "iterate_ext", "iterate_ext_int", "topology", "priors", "halo", "iterate_general")
+    PROFILE_KINDS = ("iterate_int", "iterate_ext", "iterate_ext_int", "topology", "priors", "halo", "iterate_general",
+                     "topo_positions", "topo_search", "topo_apply", "iterate_border")
 
     def set_profiling(self, on: bool):
         self._call("gbp_world_set_profiling", C.c_int32(int(on)))
@@ -449,7 +450,10 @@ class World:
         out = {}
         for k, name in enumerate(self.PROFILE_KINDS):
             cnt, ms = C.c_int64(0), C.c_double(0)
-            self._call("gbp_world_read_profile", C.c_int32(k), C.byref(cnt), C.byref(ms))
+            try:
+                self._call("gbp_world_read_profile", C.c_int32(k), C.byref(cnt), C.byref(ms))
+            except RuntimeError:
+                break  # an older build of the library (tuning variants) knows fewer kinds
             out[name] = {"count": int(cnt.value), "ms": float(ms.value)}
         return out
 

@@ -218,6 +218,7 @@ struct Cfg {  // mirror of gbp_config_t (include/gbp_b200.h), same field order
   uint8_t enable_dynamic, enable_interrobot, enable_obstacle, enable_tracking;
   int32_t schedule_kind, iterations_internal, iterations_external;
   double world_width, world_height;
+  int32_t strict_reference_quirks;  // 1: delete_interrobot_factors through the lossy per-robot map (robot.rs:1391-1404)
 };
 
 struct Sdf {
@@ -832,9 +833,12 @@ void delete_ir_connected_to(Graph &g, int other) {
 
 // delete_interrobot_factors (planner/robot.rs:1386-1439).  The reference funnels
 // the (robot, lost neighbour) pairs through a HashMap<RobotId, RobotId>, which
-// drops pairs when one robot loses several neighbours in a tick;
-// every lost pair is deleted here (the symmetric pair covers it in the reference
-// whenever the quirk does not trigger).
+// drops pairs when one robot loses several neighbours in a tick.
+// cfg.strict_reference_quirks = 1 reproduces that; 0 deletes every lost pair (the
+// symmetric pair covers it in the reference whenever the quirk does not trigger).
+// B.2 (stale interrobot_factor_indices, factorgraph.rs:409-415) needs nothing here:
+// a stale entry can only make an InterRobot factor update twice in one half, which
+// is idempotent (same inbox, same messages); factor indices are never reused here.
 void delete_interrobot_factors(World &w) {
   std::vector<std::pair<int, int>> pairs;
   for (auto &r : w.robots) {
@@ -849,6 +853,14 @@ void delete_interrobot_factors(World &w) {
       pairs.emplace_back(r.g.id, c);
       r.connected.erase(c);
     }
+  }
+  if (w.cfg.strict_reference_quirks) {
+    // `HashMap<RobotId, RobotId>::extend`: one entry per robot, the last inserted pair wins — the lost neighbours are
+    // inserted in BTreeSet (ascending) order, so it is the largest id.  Which pairs are processed does not depend on
+    // the map's iteration order, and deleting is idempotent.
+    std::map<int, int> last;
+    for (auto &p : pairs) last[p.first] = p.second;
+    pairs.assign(last.begin(), last.end());
   }
   for (auto &p : pairs) {
     delete_ir_connected_to(w.robots[p.first].g, p.second);
@@ -1794,6 +1806,12 @@ int gbpo_read_mirror_message(void *p, int robot, int var, int from_robot, double
     std::copy(kv.second.payload->lam.a.begin(), kv.second.payload->lam.a.end(), lam);
     return 1;
   }
+  return 0;
+}
+int gbpo_has_mirror_slot(void *p, int robot, int var, int from_robot) {
+  World *w = static_cast<World *>(p);
+  for (auto &kv : w->robots[robot].g.vars[var].inbox)
+    if (kv.first.first == from_robot) return 1;
   return 0;
 }
 // Tracking factor state of robot r, variable i: record, last_pos (f32), last_value.

@@ -39,6 +39,7 @@ class OracleConfig(C.Structure):
         ("iterations_external", C.c_int32),
         ("world_width", C.c_double),
         ("world_height", C.c_double),
+        ("strict_reference_quirks", C.c_int32),
     ]
 
 
@@ -320,6 +321,18 @@ class OracleWorld:
         out = np.zeros(5, np.int64)
         self._call("gbpo_node_counts", _p(out, C.c_int64))
         return out
+
+    def read_mirror_message(self, robot, var, from_robot):
+        """(eta (4,), lam (4, 4)) of the message variable `var` of `robot` holds from the InterRobot factor owned by
+        `from_robot`; None when the slot is absent or holds Message::empty()."""
+        eta, lam = np.zeros(4), np.zeros((4, 4))
+        ok = self._call("gbpo_read_mirror_message", int(robot), int(var), int(from_robot), _p(eta, C.c_double),
+                        _p(lam, C.c_double))
+        return (eta, lam) if ok else None
+
+    def has_mirror_slot(self, robot, var, from_robot) -> bool:
+        """whether the variable's inbox has an entry keyed by a factor of `from_robot` at all (Empty or not)."""
+        return bool(self._call("gbpo_has_mirror_slot", int(robot), int(var), int(from_robot)))
 
     def read_tracking(self, robot, var):
         rec = C.c_int64(0)

@@ -54,7 +54,8 @@ for rep in sorted(f for f in os.listdir(src) if f.endswith(".ncu-rep")):
             if m in ix:
                 f.write(f"{m},{units[ix[m]]}," + ",".join(l[ix[m]].replace(",", "") for l in launches) + "\n")
     # DRAM traffic of the first launch -> profiles/iterate_traffic.json (bench.py's roofline.traffic)
-    keymap = {"prof_iterate": "lattice-1000x1000", "prof_iterate_rings": "rings-100000"}
+    keymap = {"prof_iterate": "lattice-1000x1000", "prof_iterate_rings": "rings-100000",
+              "prof_axis": "lattice-1000x1000", "prof_axis_rings": "rings-100000"}
     if base in keymap:
         def to_bytes(col):
             v = float(launches[0][ix[col]].replace(",", ""))
@@ -76,4 +77,8 @@ for rep in sorted(f for f in os.listdir(src) if f.endswith(".ncu-rep")):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_source_summary.py"), tmp, "30"],
                          capture_output=True, text=True)
     open(os.path.join(dst, f"ncu_{base}_source_summary.txt"), "w").write(out.stdout + out.stderr[-2000:])
+    # stall samples by CUDA source line (needs -lineinfo and --import-source on)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_lines.py"), path, "60"],
+                         capture_output=True, text=True)
+    open(os.path.join(dst, f"ncu_{base}_source_lines.txt"), "w").write(out.stdout + out.stderr[-2000:])
 print(sorted(os.listdir(dst)))

@@ -31,8 +31,9 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_config_struct_layout_matches_header():
-    # 11 x 4-byte scalars, 4 x u8, 3 x i32, 2 x f64 with natural alignment
-    assert ctypes.sizeof(CConfig) == 80
+    # 11 x 4-byte scalars, 4 x u8, 3 x i32, 2 x f64, 1 x i32 (+ tail padding) with natural alignment
+    assert ctypes.sizeof(CConfig) == 88
+    assert CConfig.strict_reference_quirks.offset == 80 and CConfig.world_width.offset == 64
     c = GbpConfig().to_c()
     assert c.num_variables == 10 and abs(c.sigma_factor_interrobot - 0.01) < 1e-9 and c.world_width == 100.0
 

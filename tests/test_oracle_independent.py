@@ -9,6 +9,7 @@ a dense solve written independently of the oracle's code path.
 import numpy as np
 
 from magics_b200 import GbpConfig, scenarios
+from oracle import oracle
 from oracle.oracle import OracleWorld
 
 
@@ -87,3 +88,34 @@ def test_two_robots_head_on_are_pushed_apart_symmetrically():
     assert np.isfinite(b["mean"]).all()
     # InterRobot factors act: the planned paths leave the straight line y = 0
     assert np.abs(b["mean"][:, :, 1]).max() > 1e-3
+
+
+def test_strict_reference_quirks_keeps_exactly_the_uncovered_pair():
+    """SURVEY appendix B.1 in the oracle: four robots, {0, 3} and {1, 2} part; every robot loses two neighbours in one
+    tick.  HashMap<RobotId, RobotId> keeps (0,2), (1,3), (2,3), (3,2): the pairs (0,2), (1,3), (2,3) are deleted in both
+    directions and nobody deletes (0,1).  Without the quirk all four cross pairs go."""
+    from dataclasses import replace
+
+    from magics_b200 import scenarios
+    from magics_b200.config import GbpConfig
+
+    f32 = np.float32
+    for strict in (0, 1):
+        cfg = GbpConfig(target_speed=4.0, strict_reference_quirks=strict)
+        ts = oracle.variable_timesteps(scenarios.lookahead_horizon(cfg.target_speed, 5.0), 3)
+        cfg = replace(cfg, num_variables=int(ts.shape[0]))
+        starts = np.array([[0, 0.75], [12, 0.75], [12, -0.75], [0, -0.75]], f32)
+        far = np.array([[-14, 0.75], [26, 0.75], [26, -0.75], [-14, -0.75]], f32)
+        sw = scenarios._finish(cfg, np.full(4, 0.3, f32), starts, far, ts, 5.0, sdf=scenarios.white_sdf())
+        o = OracleWorld(sw.cfg)
+        sw.add_to(o)
+        for _ in range(12):
+            o.step()
+        off, nb, _ = o.read_connections()
+        assert [sorted(nb[off[r]:off[r + 1]].tolist()) for r in range(4)] == [[3], [2], [1], [0]]
+        sets = int(o.node_counts()[4]) // (cfg.num_variables - 1)
+        assert sets == (6 if strict else 4)
+        # robot 0 still holds the mirror message slot of robot 1's factor, and not of robot 2's
+        has = lambda r, frm: o.has_mirror_slot(r, 1, frm)  # noqa: E731
+        assert has(0, 1) == bool(strict) and has(1, 0) == bool(strict)
+        assert not has(0, 2) and not has(2, 0) and not has(1, 3) and not has(3, 2)
