@@ -324,7 +324,11 @@ int gbp_world_external_variable_iteration(gbp_world_t *w);
 int gbp_world_step(gbp_world_t *w);
 
 /* ---- setters used by the UI hooks (ui/settings.rs:437,495,590) ---------- */
-/* FactorGraph::change_factor_enabled (factorgraph.rs:1529-1539); kind: 0 dyn 1 ir 2 obs 3 trk */
+/* FactorGraph::change_factor_enabled (factorgraph.rs:1529-1539); kind: 0 dyn 1 ir 2 obs 3 trk.
+ * Disabling is exact (the factors stop updating and stop receiving; what they sent stays in the variables' inboxes).
+ * RE-enabling differs for one factor update: the reference's factor resumes with the inbox it held when it was
+ * switched off (a disabled factor drops what it is sent, factor/mod.rs:308-310), the engine rebuilds every factor
+ * inbox from the current records. */
 int gbp_world_change_factor_enabled(gbp_world_t *w, int32_t kind, uint8_t enabled);
 /* FactorGraph::update_inter_robot_safety_distance_multiplier (factorgraph.rs:892) */
 int gbp_world_set_safety_distance_multiplier(gbp_world_t *w, float multiplier);
@@ -352,6 +356,16 @@ int gbp_world_read_positions(gbp_world_t *w, float *xy);
  * sharded world each rank removes its own robots; the peers learn it with the positions of the next topology pass. */
 int gbp_world_remove_robots(gbp_world_t *w, int32_t m, const int32_t *robots);
 int gbp_world_read_removed(gbp_world_t *w, uint8_t *removed);
+/* MessageCount (factorgraph/mod.rs:103-137; FactorGraph::messages_sent / messages_received, factorgraph.rs:876-890,
+ * read by export.rs:434-439 and the robot diagnostics).  Off by default; turn it on right after gbp_world_create,
+ * before robots are added (the reference counts from graph creation on).  The counts are kept by small accounting
+ * kernels next to every half-step, prior update and topology change - from who takes part, with the reference's
+ * rules: a message counts as sent per inbox key of the updating node (not in change_prior), as received in
+ * receive_message_from (a disabled factor swallows it uncounted), the counters of a deleted InterRobot factor go
+ * with it.  counts[4 * r + k]: sent.internal, sent.external, received.internal, received.external of robot r.
+ * Single-GPU worlds only. */
+int gbp_world_set_message_counting(gbp_world_t *w, int32_t on);
+int gbp_world_read_message_counts(gbp_world_t *w, int64_t *counts);
 /* State of every Tracking factor, as the visualisers and the RRT* hand-off read it (factor/tracking.rs:62-90,
  * `Tracking.record`, `LastMeasurement { pos: Vec2, value }`), one entry per (robot,
  * variable): record[n*V], last_pos f32[n*V*2], last_value[n*V].  Variables 0 and V-1 have no Tracking factor;

@@ -589,6 +589,189 @@ __global__ void k_words_to_host(int64_t *__restrict__ host_dst, const int64_t *_
   __threadfence_system();
 }
 
+// ---- MessageCount accounting (factorgraph/mod.rs:103-137; read by export.rs:434-439) ---------------------------
+// The reference counts a message as SENT per inbox key of the node that updates (factor/mod.rs:353-367, 410-452;
+// variable.rs:299-332; NOT in change_prior, variable.rs:208-229) and as RECEIVED in receive_message_from
+// (variable.rs:176-190; factor/mod.rs:307-318, after the `enabled` test), internal / external by graph id.  These
+// kernels reproduce the counts from who takes part in a half-step — no message is looked at.  One thread per robot,
+// launched BEFORE the work they account for (they read iteration counts and mission flags as that work finds them).
+// cnt[k * cap + r], k = sent internal, sent external, received internal, received external: the robot's variables
+// and non-InterRobot factors; emsg[k * ecap + e]: its own InterRobot factors toward neighbour e (see EdgeSet::e_msg).
+struct MsgShape {
+  int V;
+  unsigned long long keys_own;  // same-graph non-InterRobot inbox keys of a robot's variables: 2(V-1) + 2(V-2)
+  __host__ __device__ explicit MsgShape(int v) : V(v), keys_own(2ull * (v - 1) + 2ull * (v - 2)) {}
+  // edges variable <-> enabled factor of each kind (factor_receive is a no-op for a disabled factor)
+  __device__ unsigned long long enabled_edges(const Store &s, bool tracking_runs) const {
+    return (s.en_dyn ? 2ull * (V - 1) : 0ull) + (s.en_obs ? 1ull * (V - 2) : 0ull) + (tracking_runs ? 1ull * (V - 2) : 0ull);
+  }
+};
+__global__ void k_msg_init_robots(Store s, int64_t first, int64_t count, int64_t cap, unsigned long long *cnt) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const int64_t r = first + t;
+  const MsgShape sh(s.V);
+  // add_internal_edge (factorgraph.rs:304-330) for every own factor: the variable receives Empty, the factor - if
+  // enabled - the variable's message
+  cnt[0 * cap + r] = 0;
+  cnt[1 * cap + r] = 0;
+  cnt[2 * cap + r] = sh.keys_own + sh.enabled_edges(s, s.en_trk != 0);
+  cnt[3 * cap + r] = 0;
+}
+template <bool EXT, bool INT>
+__global__ void k_msg_half(Store s, int64_t cap, unsigned long long *cnt, int64_t ecap, uint32_t *emsg) {
+  const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= s.Nloc) return;
+  const bool idle = s.idle[r] != 0, ant = s.antenna[r] != 0;
+  const bool do_ext = EXT && !idle && ant, do_int = INT && !idle;
+  if (!do_ext && !do_int) return;
+  const MsgShape sh(s.V);
+  const unsigned long long Vm1 = sh.V - 1;
+  const int64_t e0 = s.eoff ? s.eoff[r] : 0, e1 = s.eoff ? s.eoff[r + 1] : 0;
+  const unsigned long long K = (unsigned long long)(e1 - e0);
+  unsigned long long si = 0, se = 0, ri = 0, re = 0;
+  uint32_t itf = s.iter_factor[r];
+  if (do_ext) {
+    // external_factor_iteration (factorgraph.rs:719-760): every enabled own InterRobot factor sends one internal and
+    // one external message; the neighbours' factors do the same and theirs reach my variables if they ran
+    // (robot.rs:1814-1831).  external_variable_iteration (factorgraph.rs:794-826): one response per inbox key; the
+    // neighbours' responses reach my InterRobot factors if the neighbour ran (robot.rs:1843-1858).
+    si += sh.keys_own + K * Vm1;
+    se += K * Vm1;
+    for (int64_t e = e0; e < e1; ++e) {
+      const int A = s.enbr[e];
+      const bool a_runs = s.antenna[A] != 0 && s.idle[A] == 0;
+      if (s.en_ir) {
+        emsg[0 * ecap + e] += uint32_t(Vm1);
+        if (a_runs) {
+          re += Vm1;
+          emsg[2 * ecap + e] += uint32_t(Vm1);
+        }
+      }
+    }
+    itf += 1;
+  }
+  if (do_int) {
+    // internal_factor_iteration (factorgraph.rs:688-714): enabled non-InterRobot factors, Tracking from
+    // iteration_count.factor >= 10 on; internal_variable_iteration (:762-790): responses to same-graph factors are
+    // delivered (to the enabled ones), the others only counted as sent.
+    const unsigned long long f = sh.enabled_edges(s, s.en_trk && itf >= 10u);
+    si += f;
+    ri += f;
+    si += sh.keys_own + K * Vm1;
+    se += K * Vm1;
+    ri += sh.enabled_edges(s, s.en_trk != 0);
+    if (s.en_ir)
+      for (int64_t e = e0; e < e1; ++e) emsg[1 * ecap + e] += uint32_t(Vm1);
+  }
+  cnt[0 * cap + r] += si;
+  cnt[1 * cap + r] += se;
+  cnt[2 * cap + r] += ri;
+  cnt[3 * cap + r] += re;
+}
+// Will update_prior_of_horizon_state change robot r's horizon prior in the call that follows? (robot.rs:2190-2215)
+__device__ __forceinline__ bool horizon_update_runs(const Store &s, int64_t r, int iterations_internal) {
+  if (s.finished[r] || s.idle[r]) return false;
+  const int32_t nwp = s.wp_off[r + 1] - s.wp_off[r], k = s.next_wp[r];
+  return k >= 0 && k < nwp && iterations_internal != 0;
+}
+// update_prior_of_horizon_state: change_prior_of_variable(V-1) delivers to dyn(V-2), to the own InterRobot factors of
+// variable V-1 and to the neighbours' (factorgraph.rs:494-528, robot.rs:2266-2282: no antenna test); nothing is
+// counted as sent.
+__global__ void k_msg_prior_horizon(Store s, int iterations_internal, int64_t cap, unsigned long long *cnt, int64_t ecap,
+                                    uint32_t *emsg) {
+  const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= s.Nloc) return;
+  const bool mine = horizon_update_runs(s, r, iterations_internal);
+  if (mine && s.en_dyn) cnt[2 * cap + r] += 1;
+  if (!s.en_ir || !s.eoff) return;
+  for (int64_t e = s.eoff[r]; e < s.eoff[r + 1]; ++e) {
+    if (mine) emsg[1 * ecap + e] += 1u;
+    const int A = s.enbr[e];
+    if (A < s.Nloc && s.gone[r] == 0.0f && horizon_update_runs(s, A, iterations_internal)) emsg[2 * ecap + e] += 1u;
+  }
+}
+__global__ void k_msg_prior_current(Store s, int64_t cap, unsigned long long *cnt) {
+  const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= s.Nloc) return;
+  if (!s.idle[r] && s.en_dyn) cnt[2 * cap + r] += 1;  // dyn(0) receives (robot.rs:2286-2338)
+}
+// FactorGraph::change_prior_of_variable for variable `var` of the listed robots (gbp_world_change_prior_of_variable):
+// the same-graph factors of the variable receive (dyn(var-1), dyn(var), obs, trk as they exist and are enabled; the own
+// InterRobot factors for var >= 1), and so does every neighbour's InterRobot factor toward it — counted on the
+// neighbour's edge, found by its global id.
+__global__ void k_msg_change_prior(Store s, int var, int m, const int32_t *__restrict__ robots, int64_t cap,
+                                   unsigned long long *cnt, int64_t ecap, uint32_t *emsg) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  const int32_t r = robots[t];
+  const int V = s.V;
+  unsigned long long ri = 0;
+  if (s.en_dyn) ri += (var >= 1) + (var <= V - 2);
+  if (var >= 1 && var <= V - 2) ri += (s.en_obs ? 1 : 0) + (s.en_trk ? 1 : 0);
+  atomicAdd(&cnt[2 * cap + r], ri);
+  if (var < 1 || !s.en_ir || !s.eoff) return;
+  const int32_t gr = s.gid[r];
+  for (int64_t e = s.eoff[r]; e < s.eoff[r + 1]; ++e) {
+    atomicAdd(&emsg[1 * ecap + e], 1u);
+    const int32_t A = s.enbr[e];
+    if (A >= s.Nloc || s.gone[A] != 0.0f) continue;
+    int64_t lo = s.eoff[A], hi = s.eoff[A + 1];
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (s.gid[s.enbr[mid]] < gr) lo = mid + 1;
+      else hi = mid;
+    }
+    // one delivery per factor set the neighbour holds toward r; with several sets (strict_reference_quirks) the
+    // k-th set of r's row pairs with the k-th of the neighbour's: count on the matching position
+    int64_t k = 0;
+    for (int64_t q = s.eoff[r]; q < e; ++q) k += s.enbr[q] == A;
+    if (lo + k < s.eoff[A + 1] && s.enbr[lo + k] == r) atomicAdd(&emsg[2 * ecap + lo + k], 1u);
+  }
+}
+// Topology change: counters of surviving edges move with them; a new connection is a handshake — per factor the own
+// variable and (if enabled) the factor receive internally (add_internal_edge), the neighbour's variable and (if
+// enabled) the factor receive externally (add_external_edge factorgraph.rs:340-353, robot.rs:1557-1585).
+__global__ void k_msg_edges(Store s, int32_t n, const int64_t *__restrict__ noff, const int64_t *__restrict__ map,
+                            int64_t ocap, const uint32_t *__restrict__ omsg, int64_t ncap, uint32_t *nmsg, int64_t cap,
+                            unsigned long long *cnt) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint32_t Vm1 = uint32_t(s.V - 1);
+  unsigned long long fresh = 0;
+  for (int64_t e = noff[r]; e < noff[r + 1]; ++e) {
+    const int64_t old = map[e];
+    if (old >= 0) {
+      for (int k = 0; k < 3; ++k) nmsg[k * ncap + e] = omsg[k * ocap + old];
+    } else {
+      nmsg[0 * ncap + e] = 0u;
+      nmsg[1 * ncap + e] = s.en_ir ? Vm1 : 0u;
+      nmsg[2 * ncap + e] = s.en_ir ? Vm1 : 0u;
+      ++fresh;
+    }
+  }
+  cnt[2 * cap + r] += fresh * Vm1;
+  cnt[3 * cap + r] += fresh * Vm1;
+}
+// FactorGraph::messages_sent / messages_received (factorgraph.rs:876-890): out[4 r + k]; zeros for a despawned robot.
+__global__ void k_msg_gather(Store s, int64_t cap, const unsigned long long *__restrict__ cnt, int64_t ecap,
+                             const uint32_t *__restrict__ emsg, int64_t *out) {
+  const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= s.Nloc) return;
+  unsigned long long v[4] = {0, 0, 0, 0};
+  if (s.gone[r] == 0.0f) {
+    for (int k = 0; k < 4; ++k) v[k] = cnt[k * cap + r];
+    if (s.eoff)
+      for (int64_t e = s.eoff[r]; e < s.eoff[r + 1]; ++e) {
+        v[0] += emsg[0 * ecap + e];
+        v[1] += emsg[0 * ecap + e];
+        v[2] += emsg[1 * ecap + e];
+        v[3] += emsg[2 * ecap + e];
+      }
+  }
+  for (int k = 0; k < 4; ++k) out[4 * r + k] = int64_t(v[k]);
+}
+
 // gbp_world_remove_robots: the entity is despawned (robot.rs:2171-2172 RobotDespawned, despawn_entity_after).
 __global__ void k_remove_robots(Store s, int m, const int32_t *__restrict__ robots) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -665,6 +848,10 @@ struct gbp_world {
     double *mir = nullptr;
     double *mu_frozen = nullptr;
     int64_t *map = nullptr;
+    // MessageCount of the receiver's OWN InterRobot factors toward the neighbour, summed over the V-1 factors of the
+    // edge: [0] sent (internal == external: every update sends one of each), [1] received internal, [2] received
+    // external.  They go when the edge goes, like the counters of a deleted factor node.
+    uint32_t *e_msg = nullptr;  // [3][cap]
     int64_t cap = 0;
   } edges[2];
   int cur = 0;
@@ -730,6 +917,11 @@ struct gbp_world {
   bool force_rebuild = false;
   float *gpos = nullptr;        // [4][Ntot] x, z, radius, despawned flag of every robot by global id (ws > 1)
   bool any_gone = false;        // some own robot has been removed: set_comms keeps it idle
+  // gbp_world_set_message_counting: MessageCount (factorgraph/mod.rs:103-137) kept by small accounting kernels
+  // next to every half-step / prior update / topology change; off by default (the hot kernels never see it)
+  bool count_messages = false;
+  unsigned long long *msg_cnt = nullptr;  // [4][cap]: variables + non-InterRobot factors of each robot
+  int64_t msg_cap = 0;
   float max_radius = 0.0f;         // over the own robots: the collision monitor only tests connected pairs
   std::vector<uint8_t> gone_host;  // host mirror of Store::gone
   int64_t n_gone = 0;
@@ -1086,6 +1278,14 @@ int group_launch(gbp_group *g) {
   if (EXT) {
     if (int rc = group_halo_ready(g)) return rc;
   }
+  for (gbp_world *w : g->members)
+    if (w->count_messages && w->s.Nloc > 0) {
+      CK(cudaSetDevice(w->device));
+      k_msg_half<EXT, INT><<<blocks_for(w->s.Nloc, 128), 128, 0, w->stream>>>(w->s, w->msg_cap, w->msg_cnt,
+                                                                             w->edges[w->cur].cap, w->edges[w->cur].e_msg);
+      CK(cudaGetLastError());
+      w->launches += 1;
+    }
   bool split = INT && g->ws > 1;
   for (gbp_world *w : g->members) {
     w->epoch += 1;  // every shard steps its epoch, with or without robots
@@ -1180,7 +1380,7 @@ void bind_edge_set(gbp_world *w) {
 void free_edge_set(gbp_world *w, EdgeSet *e) {
   if (e->egid != e->enbr) cudaFree(e->egid);
   cudaFree(e->enbr); cudaFree(e->e_own); cudaFree(e->e_dsafe); cudaFree(e->e_rnum); cudaFree(e->e_birth);
-  cudaFree(e->e_frozen); cudaFree(e->mir); cudaFree(e->map); cudaFree(e->mu_frozen);
+  cudaFree(e->e_frozen); cudaFree(e->mir); cudaFree(e->map); cudaFree(e->mu_frozen); cudaFree(e->e_msg);
   *e = EdgeSet();
 }
 
@@ -1199,6 +1399,7 @@ int grow_edge_set(gbp_world *w, EdgeSet *e, int64_t cap) {
   CK(dalloc(e->mu_frozen, size_t(2) * size_t(cap) * Vm1));
   CK(dalloc(e->map, size_t(cap)));
   CK(dalloc(e->mir, size_t(6) * size_t(cap) * Vm1));
+  CK(dalloc(e->e_msg, size_t(3) * size_t(cap)));
   e->cap = cap;
   return 0;
 }
@@ -1305,6 +1506,10 @@ int reserve_robots(gbp_world *w, int64_t newcap) {
   CK(regrow(s.idle, 1, oldcap, newcap, keep, st));
   CK(regrow(s.finished, 1, oldcap, newcap, keep, st));
   CK(regrow(s.gone, 1, oldcap, newcap, keep, st));
+  if (w->count_messages) {
+    CK(regrow(w->msg_cnt, 4, w->msg_cap, newcap, keep, st));
+    w->msg_cap = newcap;
+  }
   CK(regrow(s.latest, 1, oldcap, newcap, keep, st));
   CK(regrow(s.iter_factor, 1, oldcap, newcap, keep, st));
   CK(regrow(s.mode, 1, oldcap, newcap, keep, st));
@@ -1573,6 +1778,11 @@ int topo_apply(gbp_world *w, const int64_t (*hdr)[4]) {
                                                      w->robot_number, bases, w->tp.cross_po, w->ckeys_r, w->cvals_r,
                                                      spare->e_rnum, w->t_err);
     w->launches += 2;
+  }
+  if (w->count_messages && n > 0) {
+    k_msg_edges<<<blocks_for(n, T), T, 0, st>>>(s, n, w->t_off, spare->map, live->cap, live->e_msg, spare->cap,
+                                                spare->e_msg, w->msg_cap, w->msg_cnt);
+    w->launches += 1;
   }
   if (E1 > 0) {
     gbp::k_mirror_move<<<blocks_for(E1 * Vm1, 256), 256, 0, st>>>(s, w->p, E1 * Vm1, Vm1, w->t_off, spare->map, s.mir,
@@ -1947,6 +2157,7 @@ void gbp_world_destroy(gbp_world_t *w) {
     cudaStreamSynchronize(w->border_stream);
     cudaStreamDestroy(w->border_stream);
   }
+  cudaFree(w->msg_cnt);
   cudaFree(w->border_gen_list);
   cudaFree(w->border_gen_count);
   for (cudaEvent_t e : {w->ev_border, w->ev_halo, w->ev_fence, w->ev_start})
@@ -2315,6 +2526,11 @@ int gbp_world_add_robots(gbp_world_t *w, int32_t n, const float *radii, const ui
   k_init_vars<<<blocks_for(nv, 256), 256, 0, st>>>(s, used, nv, d_mu);
   CK(cudaGetLastError());
   w->launches += 1;
+  if (w->count_messages) {
+    k_msg_init_robots<<<blocks_for(n, 256), 256, 0, st>>>(s, N0, n, w->msg_cap, w->msg_cnt);
+    CK(cudaGetLastError());
+    w->launches += 1;
+  }
   // one delta_t per Dynamic factor for the whole world? (t0 = radius / 2 / target_speed, robot.rs:1225)
   for (int r = 0; r < n && w->t0_uniform; ++r) {
     if (!w->t0_seen) {
@@ -2553,6 +2769,11 @@ int gbp_world_update_prior_of_horizon_state(gbp_world_t *w0) {
     if (set_device(w)) return GBP_ERR_CUDA;
     w->epoch += 1;
     if (w->s.Nloc == 0) continue;
+    if (w->count_messages) {
+      k_msg_prior_horizon<<<blocks_for(w->s.Nloc, 128), 128, 0, w->stream>>>(
+          w->s, w->cfg.iterations_internal, w->msg_cap, w->msg_cnt, w->edges[w->cur].cap, w->edges[w->cur].e_msg);
+      w->launches += 1;
+    }
     ProfileScope ps(w, GBP_PROFILE_PRIORS);
     k_prior_horizon<<<blocks_for(int64_t(w->s.Nloc) * 32, 128), 128, 0, w->stream>>>(
         w->s, w->p, w->epoch, double(w->cfg.delta_t), double(w->cfg.target_speed), w->cfg.iterations_internal);
@@ -2569,6 +2790,10 @@ int gbp_world_update_prior_of_current_state(gbp_world_t *w0) {
     if (set_device(w)) return GBP_ERR_CUDA;
     w->epoch += 1;
     if (w->s.Nloc == 0) continue;
+    if (w->count_messages) {
+      k_msg_prior_current<<<blocks_for(w->s.Nloc, 128), 128, 0, w->stream>>>(w->s, w->msg_cap, w->msg_cnt);
+      w->launches += 1;
+    }
     ProfileScope ps(w, GBP_PROFILE_PRIORS);
     k_prior_current<<<blocks_for(int64_t(w->s.Nloc) * 32, 128), 128, 0, w->stream>>>(w->s, w->p, w->epoch, w->cfg.delta_t);
     CK(cudaGetLastError());
@@ -2595,6 +2820,11 @@ int gbp_world_change_prior_of_variable(gbp_world_t *w, int32_t var, int32_t m, c
   CK(cudaMemcpyAsync(dr, robots, size_t(m) * sizeof(int32_t), cudaMemcpyHostToDevice, w->stream));
   CK(cudaMemcpyAsync(dm, new_means, size_t(4) * m * sizeof(double), cudaMemcpyHostToDevice, w->stream));
   w->epoch += 1;
+  if (w->count_messages) {
+    k_msg_change_prior<<<blocks_for(m, 128), 128, 0, w->stream>>>(w->s, var, m, dr, w->msg_cap, w->msg_cnt,
+                                                                 w->edges[w->cur].cap, w->edges[w->cur].e_msg);
+    w->launches += 1;
+  }
   k_change_prior_list<<<blocks_for(m, 128), 128, 0, w->stream>>>(w->s, w->p, w->epoch, var, m, dr, dm);
   CK(cudaGetLastError());
   w->launches += 1;
@@ -2981,6 +3211,37 @@ int64_t gbp_world_read_connections(gbp_world_t *w, int64_t *offsets, int32_t *ne
     }
   }
   return s.E;
+}
+
+int gbp_world_set_message_counting(gbp_world_t *w, int32_t on) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (on && w->sh.ws > 1)
+    return fail(GBP_ERR_STATE, "gbp_world_set_message_counting: single-GPU worlds only (what a ghost robot's prior update "
+                               "delivers to the own factors is not visible to the shard)");
+  if (on && !w->count_messages && w->s.Nloc > 0)
+    return fail(GBP_ERR_STATE, "gbp_world_set_message_counting: turn the counters on before the first robot is added "
+                               "(the reference counts from the creation of the graph on)");
+  w->count_messages = on != 0;
+  return 0;
+}
+
+int gbp_world_read_message_counts(gbp_world_t *w, int64_t *counts) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (!counts) return fail(GBP_ERR_BAD_ARGUMENT, "null output");
+  if (int rc = pair_open(w, "gbp_world_read_message_counts")) return rc;
+  if (!w->count_messages) return fail(GBP_ERR_STATE, "message counting is off (gbp_world_set_message_counting)");
+  if (set_device(w)) return GBP_ERR_CUDA;
+  const int64_t n = w->s.Nloc;
+  if (n == 0) return 0;
+  if (int rc = ensure_scratch(w, size_t(4) * size_t(n) * sizeof(int64_t))) return rc;
+  int64_t *d = static_cast<int64_t *>(w->rb_dev);
+  k_msg_gather<<<blocks_for(n, 128), 128, 0, w->stream>>>(w->s, w->msg_cap, w->msg_cnt, w->edges[w->cur].cap,
+                                                         w->edges[w->cur].e_msg, d);
+  CK(cudaGetLastError());
+  w->launches += 1;
+  CK(cudaMemcpyAsync(counts, d, size_t(4) * size_t(n) * sizeof(int64_t), cudaMemcpyDeviceToHost, w->stream));
+  CK(cudaStreamSynchronize(w->stream));
+  return 0;
 }
 
 int gbp_world_read_tracking(gbp_world_t *w, int64_t *record, float *last_pos, double *last_value) {

@@ -57,6 +57,9 @@ constexpr int kAxisBatch = GBP_AXIS_BATCH;
 #define GBP_AXIS_RELOAD_SENT 0 // 1: the last delivered mean is read again in the rare freeze path instead of being kept
                                // (4 registers fewer, +3 % time: r02j)
 #endif
+#ifndef GBP_AXIS_DYN_PAIR
+#define GBP_AXIS_DYN_PAIR 0  // 1: the two Dynamic messages of a variable as one straight-line block (two inverses in flight)
+#endif
 #ifndef GBP_AXIS_PREFETCH
 #define GBP_AXIS_PREFETCH 0  // CTAs ahead whose wave-1 rows this CTA pulls into L2 (592 = 148 SMs x 4 resident CTAs:
                              // +1.5 % DRAM bytes, no time gained — profiles/README.md r02e/r02f; off)
@@ -448,6 +451,65 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
     if (do_int) {
       // inbox sum of the variable iteration in FactorId order: prior, dyn(i-1), dyn(i); each new message is
       // stored at once (the buffers written here are not read in this launch)
+#if GBP_AXIS_DYN_PAIR
+      {
+        // Dynamic factor i-1 -> variable i (slot 1, "L": the other message comes from variable i-1) and Dynamic
+        // factor i -> variable i (slot 0, "R": from variable i+1), evaluated together (dyn_message_axis_pair).  The
+        // first / last variable has only one of them and evaluates it twice.
+        const bool doL = i >= 1, doR = i <= V - 2;
+        const double *const x1 = doL ? xr : xl, *const x2 = doR ? xl : xr;
+        const int d1 = doL ? -2 : 2, d2 = doR ? 2 : -2;
+        const int tn1 = t + d1, tq1 = (t ^ 1) + d1, tn2 = t + d2, tq2 = (t ^ 1) + d2;
+        const int f1 = doL ? i - 1 : i, f2 = doR ? i : i - 1;  // factor index of the constants
+        const double oe1[2] = {x1[tn1], x1[T + tn1]}, oe2[2] = {x2[tn2], x2[T + tn2]};
+        const double oP1[4] = {x1[2 * T + tn1], x1[3 * T + tn1], x1[4 * T + tn1], x1[5 * T + tn1]};
+        const double oQ1[4] = {x1[2 * T + tq1], x1[3 * T + tq1], x1[4 * T + tq1], x1[5 * T + tq1]};
+        const double oP2[4] = {x2[2 * T + tn2], x2[3 * T + tn2], x2[4 * T + tn2], x2[5 * T + tn2]};
+        const double oQ2[4] = {x2[2 * T + tq2], x2[3 * T + tq2], x2[4 * T + tq2], x2[5 * T + tq2]};
+        double dc1[4], dc2[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          dc1[k] = s.dyn_tab ? dtab[4 * f1 + k] : s.dyn_c[s.at<4>(k, vi - i + f1)];
+          dc2[k] = s.dyn_tab ? dtab[4 * f2 + k] : s.dyn_c[s.at<4>(k, vi - i + f2)];
+        }
+        const DynM M1 = dyn_potential_q(dc1[0], dc1[1], dc1[2], dc1[3]);
+        const DynM M2 = dyn_potential_q(dc2[0], dc2[1], dc2[2], dc2[3]);
+        double e1[2], l1[4], e2[2], l2[4];
+        bool ok1, ok2;
+        if (doL && doR) {
+          dyn_message_axis_pair(a, M1, xne[tn1] != 0, oe1, oP1, oQ1, M2, xne[tn2] != 0, oe2, oP2, oQ2, e1, l1, e2, l2, ok1,
+                                ok2);
+        } else if (doL) {
+          ok1 = dyn_message_axis<1>(a, M1, xne[tn1] != 0, oe1, oP1, oQ1, e1, l1);
+          ok2 = true;
+        } else {
+          ok2 = dyn_message_axis<0>(a, M2, xne[tn2] != 0, oe2, oP2, oQ2, e2, l2);
+          ok1 = true;
+        }
+        if (doL) {
+          if (ok1) {
+            st_axis(s.m_dynL[1 - p], qm, e1, l1);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) ae[k] = ae[k] + e1[k];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) al[k] = al[k] + l1[k];
+          } else {
+            bad = true;
+          }
+        }
+        if (doR) {
+          if (ok2) {
+            st_axis(s.m_dynR[1 - p], qm, e2, l2);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) ae[k] = ae[k] + e2[k];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) al[k] = al[k] + l2[k];
+          } else {
+            bad = true;
+          }
+        }
+      }
+#else
       if (i >= 1) {  // Dynamic factor i-1 -> variable i (slot 1); the other message comes from variable i-1
         const int tn = t - 2, tq = (t ^ 1) - 2;
         const double oe[2] = {xr[tn], xr[T + tn]};
@@ -488,6 +550,7 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
           bad = true;
         }
       }
+#endif
       if (i >= 1 && i <= V - 2) {
         // Tracking factors run from iteration_count.factor >= 10 on (factorgraph.rs:701): general kernel
         if (s.en_trk && itf >= 10u) bad = true;

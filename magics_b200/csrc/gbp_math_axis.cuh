@@ -113,4 +113,118 @@ GBP_DEV bool dyn_message_axis(int a, const DynM &M, bool other_nonempty, const d
   return !inf;
 }
 
+// ---- both Dynamic messages of a variable at once ------------------------------------------------------------
+// The two 4x4 cofactor inverses (and the two reciprocals inside them) are independent dependency chains; written
+// as one straight-line block they overlap in the FP64 pipe instead of running one after the other (the kernel
+// spends a quarter of its issue interval on fixed-latency dependencies).  Same operations per message as
+// inv_axis / divide_all / dyn_message_axis, so the same bits.
+GBP_DEV void cof_axis_pair(int a, const double (&P1)[4], const double (&Q1)[4], const double (&P2)[4],
+                           const double (&Q2)[4], double (&c1)[4], double &det1, double (&c2)[4], double &det2) {
+  const bool y = a != 0;
+#define GBP_ENTRIES(P, Q, m)                                                                          \
+  const double m##0 = y ? Q[0] : P[0], m##2 = y ? Q[1] : P[1], m##8 = y ? Q[2] : P[2], m##10 = y ? Q[3] : P[3]; \
+  const double m##5 = y ? P[0] : Q[0], m##7 = y ? P[1] : Q[1], m##13 = y ? P[2] : Q[2], m##15 = y ? P[3] : Q[3];
+  GBP_ENTRIES(P1, Q1, u)
+  GBP_ENTRIES(P2, Q2, v)
+#undef GBP_ENTRIES
+  const double u_c0 = (u5 * u10) * u15 - (u7 * u10) * u13, v_c0 = (v5 * v10) * v15 - (v7 * v10) * v13;
+  const double u_c1 = (u7 * u8) * u13 - (u5 * u8) * u15, v_c1 = (v7 * v8) * v13 - (v5 * v8) * v15;
+  det1 = u0 * u_c0 + u2 * u_c1;
+  det2 = v0 * v_c0 + v2 * v_c1;
+  if (!y) {
+    c1[0] = u_c0;
+    c2[0] = v_c0;
+    c1[1] = (u2 * u7) * u13 - (u2 * u5) * u15;
+    c2[1] = (v2 * v7) * v13 - (v2 * v5) * v15;
+    c1[2] = u_c1;
+    c2[2] = v_c1;
+    c1[3] = (u0 * u5) * u15 - (u0 * u7) * u13;
+    c2[3] = (v0 * v5) * v15 - (v0 * v7) * v13;
+  } else {
+    c1[0] = (u0 * u10) * u15 - (u2 * u8) * u15;
+    c2[0] = (v0 * v10) * v15 - (v2 * v8) * v15;
+    c1[1] = (u2 * u7) * u8 - (u0 * u7) * u10;
+    c2[1] = (v2 * v7) * v8 - (v0 * v7) * v10;
+    c1[2] = (u2 * u8) * u13 - (u0 * u10) * u13;
+    c2[2] = (v2 * v8) * v13 - (v0 * v10) * v13;
+    c1[3] = (u0 * u5) * u10 - (u2 * u5) * u8;
+    c2[3] = (v0 * v5) * v10 - (v2 * v5) * v8;
+  }
+}
+// o1 = c1 / det1, o2 = c2 / det2, bit-identical to the divisions (divide_all's scheme, both reciprocals in flight)
+GBP_DEV void divide_pair(const double (&c1)[4], double det1, const double (&c2)[4], double det2, double (&o1)[4],
+                         double (&o2)[4]) {
+  bool bad = !exp_in_safe_range(det1) | !exp_in_safe_range(det2);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    bad |= ((c1[k] != 0.0) & !exp_in_safe_range(c1[k])) | ((c2[k] != 0.0) & !exp_in_safe_range(c2[k]));
+  if (!bad) {
+    const double y1 = 1.0 / det1, y2 = 1.0 / det2;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double p0 = c1[k] * y1, q0 = c2[k] * y2;
+      double r1 = fma(-p0, det1, c1[k]), r2 = fma(-q0, det2, c2[k]);
+      double p = fma(r1, y1, p0), q = fma(r2, y2, q0);
+      r1 = fma(-p, det1, c1[k]);
+      r2 = fma(-q, det2, c2[k]);
+      p = fma(r1, y1, p);
+      q = fma(r2, y2, q);
+      o1[k] = (c1[k] == 0.0) ? p0 : p;
+      o2[k] = (c2[k] == 0.0) ? q0 : q;
+    }
+  } else {
+    divide_all(c1, det1, o1);
+    divide_all(c2, det2, o2);
+  }
+}
+// dyn_message_axis<1> (message to the second variable of Dynamic factor i-1: "L") and dyn_message_axis<0> (to the first
+// variable of factor i: "R") together.  ok1 / ok2 = what the single functions return.
+GBP_DEV void dyn_message_axis_pair(int a, const DynM &M1, bool ne1, const double (&oe1)[2], const double (&oP1)[4],
+                                   const double (&oQ1)[4], const DynM &M2, bool ne2, const double (&oe2)[2],
+                                   const double (&oP2)[4], const double (&oQ2)[4], double (&eta1)[2],
+                                   double (&lam1)[4], double (&eta2)[2], double (&lam2)[4], bool &ok1, bool &ok2) {
+  // message 1: KEEP = 1 -> A = 2, B = 0; message 2: KEEP = 0 -> A = 0, B = 2
+  double bP1[4], bQ1[4], bP2[4], bQ2[4];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const double p1 = M1.m[0 + r][0 + c], p2 = M2.m[2 + r][2 + c];
+      bP1[r * 2 + c] = ne1 ? p1 + oP1[r * 2 + c] : p1;
+      bQ1[r * 2 + c] = ne1 ? p1 + oQ1[r * 2 + c] : p1;
+      bP2[r * 2 + c] = ne2 ? p2 + oP2[r * 2 + c] : p2;
+      bQ2[r * 2 + c] = ne2 ? p2 + oQ2[r * 2 + c] : p2;
+    }
+  double c1[4], c2[4], det1, det2, I1[4], I2[4];
+  cof_axis_pair(a, bP1, bQ1, bP2, bQ2, c1, det1, c2, det2);
+  ok1 = isfinite(det1) && det1 != 0.0;
+  ok2 = isfinite(det2) && det2 != 0.0;
+  divide_pair(c1, det1, c2, det2, I1, I2);
+  const double eb1[2] = {ne1 ? 0.0 + oe1[0] : 0.0, ne1 ? 0.0 + oe1[1] : 0.0};
+  const double eb2[2] = {ne2 ? 0.0 + oe2[0] : 0.0, ne2 ? 0.0 + oe2[1] : 0.0};
+  ok1 = ok1 && (isfinite(eb1[0]) & isfinite(eb1[1]));
+  ok2 = ok2 && (isfinite(eb2[0]) & isfinite(eb2[1]));
+  bool inf1 = false, inf2 = false;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const double s0 = M1.m[2 + r][0] * I1[0] + M1.m[2 + r][1] * I1[2];
+    const double s1 = M1.m[2 + r][0] * I1[1] + M1.m[2 + r][1] * I1[3];
+    const double t0 = M2.m[0 + r][2] * I2[0] + M2.m[0 + r][3] * I2[2];
+    const double t1 = M2.m[0 + r][2] * I2[1] + M2.m[0 + r][3] * I2[3];
+    eta1[r] = 0.0 - ((0.0 + s0 * eb1[0]) + s1 * eb1[1]);
+    eta2[r] = 0.0 - ((0.0 + t0 * eb2[0]) + t1 * eb2[1]);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const double v1 = M1.m[2 + r][2 + c] - (s0 * M1.m[0][2 + c] + s1 * M1.m[1][2 + c]);
+      const double v2 = M2.m[0 + r][0 + c] - (t0 * M2.m[2][0 + c] + t1 * M2.m[3][0 + c]);
+      lam1[r * 2 + c] = v1;
+      lam2[r * 2 + c] = v2;
+      inf1 |= isinf(v1);
+      inf2 |= isinf(v2);
+    }
+  }
+  ok1 = ok1 && !inf1;
+  ok2 = ok2 && !inf2;
+}
+
 }  // namespace gbp

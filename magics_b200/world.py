@@ -394,6 +394,31 @@ class World:
         self._call("gbp_world_read_removed", _p(out, C.c_uint8))
         return out
 
+    def set_message_counting(self, on: bool = True):
+        """MessageCount accounting (off by default); call before add_robots."""
+        self._call("gbp_world_set_message_counting", C.c_int32(int(bool(on))))
+
+    def read_message_counts(self):
+        """(n, 4) i64: sent internal / external, received internal / external per robot."""
+        out = np.zeros((self.num_robots, 4), np.int64)
+        self._call("gbp_world_read_message_counts", _p(out, C.c_int64))
+        return out
+
+    def export_totals(self) -> dict:
+        """The per-robot totals `export.rs` writes (RobotData, export.rs:112-277) as far as the engine keeps them:
+        radius, collisions.robots (planner/collisions.rs RobotRobotCollisions::get), messages sent / received
+        (internal, external) when the counters are on, the mission's next waypoint index.  collisions.environment and
+        the position / velocity histories are not kept by the engine."""
+        out = {"collisions_robots": self.read_robot_collisions(), "next_waypoint": self.read_waypoint_index(),
+               "removed": self.read_removed().astype(bool)}
+        try:
+            c = self.read_message_counts()
+            out["messages"] = {"sent": {"internal": c[:, 0], "external": c[:, 1]},
+                               "received": {"internal": c[:, 2], "external": c[:, 3]}}
+        except RuntimeError:
+            out["messages"] = None
+        return out
+
     def read_tracking(self):
         """(record (n, V) i64, last_pos (n, V, 2) f32, last_value (n, V) f64) of every Tracking factor."""
         n, V = self.num_robots, self.V

@@ -230,7 +230,13 @@ enum Kind { DYNAMIC = 0, INTERROBOT = 1, OBSTACLE = 2, TRACKING = 3 };
 
 // factor/mod.rs:597-650 FactorState + the kind-specific fields of the four
 // live factor kinds (dynamic.rs, interrobot.rs, obstacle.rs, tracking.rs).
+// MessageCount (factorgraph/mod.rs:103-137): per node, never reset (reset_message_count has no caller).
+struct MsgCount {
+  uint64_t sent_int = 0, sent_ext = 0, recv_int = 0, recv_ext = 0;
+};
+
 struct Factor {
+  MsgCount cnt;
   Kind kind;
   int graph;       // factorgraph_id
   int index;       // node index
@@ -552,6 +558,8 @@ std::vector<std::pair<NodeId, Message>> factor_update(Factor &f) {
     ++i;
   }
   std::vector<std::pair<NodeId, Message>> out;
+  // messages_sent, per inbox key, in both the skip branch and the regular one (factor/mod.rs:353-367, 410-452)
+  for (auto &kv : f.inbox) (kv.first.first == f.graph ? f.cnt.sent_int : f.cnt.sent_ext) += 1;
   if (skip(f)) {
     for (auto &kv : f.inbox) out.emplace_back(kv.first, Message::empty());
     return out;
@@ -590,6 +598,7 @@ std::vector<std::pair<NodeId, Message>> factor_update(Factor &f) {
 
 // variable.rs:15-54,86-106
 struct Variable {
+  MsgCount cnt;
   int graph, index;
   Vec prior_eta;
   Mat prior_lam;
@@ -652,6 +661,9 @@ std::vector<std::pair<NodeId, Message>> variable_update(Variable &v) {
     }
   }
   std::vector<std::pair<NodeId, Message>> out;
+  // one response per inbox key, counted whether or not the caller delivers it (variable.rs:299-332);
+  // change_prior's messages are NOT counted as sent (variable.rs:208-229 drops its local counter)
+  for (auto &kv : v.inbox) (kv.first.first == v.graph ? v.cnt.sent_int : v.cnt.sent_ext) += 1;
   for (auto &kv : v.inbox) {
     if (kv.second.is_empty()) {
       out.emplace_back(kv.first, prepare_message(v));
@@ -684,6 +696,12 @@ struct Graph {
 void factor_receive(Factor &f, NodeId from, const Message &m) {
   if (!f.enabled) return;
   f.inbox[from] = m;
+  (from.first == f.graph ? f.cnt.recv_int : f.cnt.recv_ext) += 1;
+}
+// VariableNode::receive_message_from (variable.rs:176-190).
+void variable_receive(Variable &v, NodeId from, const Message &m) {
+  v.inbox[from] = m;
+  (from.first == v.graph ? v.cnt.recv_int : v.cnt.recv_ext) += 1;
 }
 
 struct Robot {
@@ -713,7 +731,7 @@ struct World {
 // FactorGraph::add_internal_edge (factorgraph.rs:304-330).
 void add_internal_edge(Graph &g, int var, int fidx) {
   Variable &v = g.vars[var];
-  v.inbox[{g.id, fidx}] = Message::empty();
+  variable_receive(v, {g.id, fidx}, Message::empty());
   Message vm = prepare_message(v);
   Factor &f = g.factors.at(fidx);
   if (f.kind == TRACKING) factor_receive(f, {g.id, var}, vm);
@@ -906,7 +924,7 @@ void create_interrobot_factors(World &w) {
   std::vector<Tmp> tmp;
   for (auto &e : ext) {  // add_external_edge (factorgraph.rs:340-353)
     Graph &og = w.robots[e.other].g;
-    og.vars[e.i].inbox[{e.robot, e.fidx}] = Message::empty();
+    variable_receive(og.vars[e.i], {e.robot, e.fidx}, Message::empty());
     tmp.push_back({e.robot, e.fidx, prepare_message(og.vars[e.i]), {e.other, e.i}});
   }
   for (auto &t : tmp) {
@@ -923,7 +941,7 @@ void internal_factor_iteration(Graph &g) {
     if (f.kind == INTERROBOT) continue;
     if (f.kind == TRACKING && g.iter_factor < 10) continue;
     auto msgs = factor_update(f);
-    for (auto &m : msgs) g.vars[m.first.second].inbox[{g.id, f.index}] = m.second;
+    for (auto &m : msgs) variable_receive(g.vars[m.first.second], {g.id, f.index}, m.second);
   }
   g.iter_factor += 1;
 }
@@ -982,7 +1000,7 @@ void world_external_factor(World &w) {  // robot.rs:1803-1831 (single thread)
   for (auto &m : msgs) {
     Robot &t = w.robots[m.to.first];
     if (!t.antenna || t.idle || t.gone) continue;  // gone: query.get_mut fails (robot.rs:1815-1819, 1844-1848)
-    t.g.vars[m.to.second].inbox[m.from] = m.m;
+    variable_receive(t.g.vars[m.to.second], m.from, m.m);
   }
 }
 void world_external_variable(World &w) {  // robot.rs:1833-1858 (single thread)
@@ -1482,6 +1500,7 @@ static void change_prior_of_variable(World &w, int robot, int var, const Vec &me
 }
 static void deliver_to_factors(World &w, std::vector<Routed> &msgs) {
   for (auto &m : msgs) {
+    if (w.robots[m.to.first].gone) continue;  // query.get_mut fails for a despawned robot (robot.rs:2273-2277)
     auto &fs = w.robots[m.to.first].g.factors;
     auto it = fs.find(m.to.second);
     if (it != fs.end()) factor_receive(it->second, m.from, m.m);
@@ -1805,6 +1824,30 @@ int gbpo_read_mirror_message(void *p, int robot, int var, int from_robot, double
     std::copy(kv.second.payload->eta.begin(), kv.second.payload->eta.end(), eta);
     std::copy(kv.second.payload->lam.a.begin(), kv.second.payload->lam.a.end(), lam);
     return 1;
+  }
+  return 0;
+}
+// FactorGraph::messages_sent / messages_received (factorgraph.rs:876-890): sums over the nodes the graph holds NOW
+// (a deleted InterRobot factor takes its counters with it).  out[4 * r + k]: sent.internal, sent.external,
+// received.internal, received.external of robot r; zeros for a despawned robot.
+int gbpo_read_message_counts(void *p, int64_t *out) {
+  World *w = static_cast<World *>(p);
+  for (size_t r = 0; r < w->robots.size(); ++r) {
+    MsgCount t;
+    if (!w->robots[r].gone) {
+      for (auto &v : w->robots[r].g.vars) {
+        t.sent_int += v.cnt.sent_int; t.sent_ext += v.cnt.sent_ext;
+        t.recv_int += v.cnt.recv_int; t.recv_ext += v.cnt.recv_ext;
+      }
+      for (auto &kv : w->robots[r].g.factors) {
+        const MsgCount &c = kv.second.cnt;
+        t.sent_int += c.sent_int; t.sent_ext += c.sent_ext; t.recv_int += c.recv_int; t.recv_ext += c.recv_ext;
+      }
+    }
+    out[4 * r + 0] = int64_t(t.sent_int);
+    out[4 * r + 1] = int64_t(t.sent_ext);
+    out[4 * r + 2] = int64_t(t.recv_int);
+    out[4 * r + 3] = int64_t(t.recv_ext);
   }
   return 0;
 }

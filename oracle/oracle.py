@@ -322,6 +322,13 @@ class OracleWorld:
         self._call("gbpo_node_counts", _p(out, C.c_int64))
         return out
 
+    def read_message_counts(self):
+        """(n, 4) i64: messages sent internal / external, received internal / external per robot (FactorGraph::
+        messages_sent / messages_received)."""
+        out = np.zeros((self.num_robots, 4), np.int64)
+        self._call("gbpo_read_message_counts", _p(out, C.c_int64))
+        return out
+
     def read_mirror_message(self, robot, var, from_robot):
         """(eta (4,), lam (4, 4)) of the message variable `var` of `robot` holds from the InterRobot factor owned by
         `from_robot`; None when the slot is absent or holds Message::empty()."""
