@@ -365,7 +365,6 @@ def main():
     # ---- device-resident timing ------------------------------------------
     for _ in range(args.warmup):
         g.step()
-    g.set_profiling(True)
     launches0 = g.kernel_launches
     sampler = ClockSampler(local_rank)
     barrier()
@@ -378,6 +377,12 @@ def main():
     clocks = sampler.stop()
     launches = g.kernel_launches - launches0
     launches = sum_over_ranks(launches) if world > 1 else launches
+    # per-kernel device times for the roofline leg: a separate, untimed pass — the CUDA events around every launch
+    # would sit between kernels that otherwise overlap their launch with the previous kernel's tail
+    prof_steps = min(args.steps, 5)
+    g.set_profiling(True)
+    for _ in range(prof_steps):
+        g.step()
     prof = g.read_profile()
     g.set_profiling(False)
     ms = max_over_ranks(ms) if world > 1 else ms
@@ -439,7 +444,7 @@ def main():
             # pair (border robots, then the rest), so the total is divided by the pairs of the schedule
             ph = [c for a, b in zip(oi, oe) for c in (("I",) if a else ()) + (("E",) if b else ())]
             fused_per_tick = sum(1 for k in range(len(ph) - 1) if ph[k] == "E" and ph[k + 1] == "I")
-            avg_s = dom["ms"] * 1e-3 / max(1, fused_per_tick * args.steps)
+            avg_s = dom["ms"] * 1e-3 / max(1, fused_per_tick * prof_steps)
             achieved = bytes_iter * n / avg_s / 1e9
             traffic, traffic_src = ncu_traffic(sw.name)
             if traffic is not None and n_total != n:
@@ -485,11 +490,11 @@ def main():
                             "all variable means device -> pinned host (copy of tick t overlaps tick t+1, consumed one tick "
                             "later; the last copy is inside the timed region); max(CUDA events, wall clock), max over ranks"},
             "state_hash": {"means": f"{h_means:016x}", "connectivity": f"{h_conn:016x}", "edges": int(edges_total),
-                           "last_robot_number": int(rn_max), "ticks": args.warmup + 2 * args.steps,
+                           "last_robot_number": int(rn_max), "ticks": args.warmup + 2 * args.steps + prof_steps,
                            "what": "sum mod 2^64 over all robots of a 64-bit digest of every variable mean "
                                    "(keyed by global robot id) / of every directed InterRobot pair with its "
                                    "robot_number, after all ticks of this run; the same for every N"},
-            "roofline": roof, "cpu_baseline": cpu, "profile_ms": prof,
+            "roofline": roof, "cpu_baseline": cpu, "profile_ms": prof, "profile_steps": prof_steps,
         }
         if world == 1 and not args.no_extras and args.workload == "lattice":
             # the other sizes the metric names (10 k / 100 k), the regime the headline never enters (active

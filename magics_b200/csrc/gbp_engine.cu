@@ -905,6 +905,7 @@ struct gbp_world {
   bool smem_opted_in[4] = {false, false, false, false};  // k_iterate<EXT,INT> dynamic shared memory opt-in
   bool axis_opted_in[12] = {};  // k_iterate_axis<EXT,INT,PART> likewise
   bool general_only = false;  // gbp_world_set_iterate_path: every robot through k_iterate
+  bool use_pdl = true;        // iterate kernels launched with programmatic stream serialization (GBP_PDL=0: off)
   double *dyn_tab_dev = nullptr;  // Store::dyn_tab while every robot added so far has the same t0 (radius)
   bool t0_seen = false, t0_uniform = true;
   float t0_first = 0.0f;
@@ -1207,6 +1208,24 @@ int group_halo_ready(gbp_group *g) {
   return 0;
 }
 
+// Kernel launch with programmatic stream serialization (PDL): the kernel may begin while the previous kernel of the
+// stream is draining; it orders itself with griddepcontrol.wait (gbp_iterate.cuh pdl_wait).
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+                       Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // One iterate launch pair (k_iterate_axis, then k_iterate over what it handed over) for one part of a shard:
 // part 0 = every own robot, 1 = the border robots (send lists), 2 = the others.
 template <bool EXT, bool INT>
@@ -1248,15 +1267,17 @@ int launch_iterate(gbp_world *w, int part) {
     if (nrob > 0) {
       {
         ProfileScope ps(w, part == 1 ? int(GBP_PROFILE_ITERATE_BORDER) : kind, st);
-        kernel<<<blocks_for(nrob, q.rpc), q.threads, q.smem, st>>>(s, w->p, w->epoch, q.rpc, *par, w->border_list,
-                                                                  w->border_count,
-                                                                  reinterpret_cast<const uint8_t *>(w->border_words));
+        CK(launch_pdl(w->use_pdl, kernel, blocks_for(nrob, q.rpc), unsigned(q.threads), q.smem, st, s, w->p, w->epoch,
+                      q.rpc, *par, static_cast<const int32_t *>(w->border_list),
+                      static_cast<const int32_t *>(w->border_count),
+                      reinterpret_cast<const uint8_t *>(w->border_words)));
       }
       CK(cudaGetLastError());
       const int64_t warps = (nrob + rpw - 1) / rpw;
       const unsigned grid = unsigned(std::min<int64_t>((warps + wpb - 1) / wpb, int64_t(w->sm_count) * 4));
       ProfileScope pg(w, GBP_PROFILE_ITERATE_GENERAL, st);
-      gbp::k_iterate<EXT, INT><<<grid, gbp::kIterBlock, 0, st>>>(s, w->p, w->epoch, *par);
+      CK(launch_pdl(w->use_pdl, gbp::k_iterate<EXT, INT>, grid, unsigned(gbp::kIterBlock), size_t(0), st, s, w->p,
+                    w->epoch, *par));
       *par ^= 1;
       w->launches += 2;
     }
@@ -2015,6 +2036,7 @@ gbp_world *make_world(const gbp_config_t *cfg, int32_t device, cudaStream_t shar
   w->s.V = cfg->num_variables;
   cudaDeviceGetAttribute(&w->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (const char *e = std::getenv("GBP_GENERAL_ONLY")) w->general_only = e[0] == '1';
+  if (const char *e = std::getenv("GBP_PDL")) w->use_pdl = e[0] != '0';
   // default SDF: a single white pixel (empty environment)
   const uint8_t white = 255;
   if (cudaMalloc(&w->sdf_dev, 1) != cudaSuccess ||

@@ -57,6 +57,10 @@ constexpr size_t kIterSmemBytes = 0;
 #define GBP_MIRROR_MASK 1
 #endif
 
+// Programmatic dependent launch (sm_90+): wait for the grids this one depends on / let the next grid of the stream start.
+GBP_DEV void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+GBP_DEV void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 GBP_DEV void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // first N components of a P-component per-variable record
 template <int P, int N>
@@ -694,6 +698,8 @@ __global__ void GBP_ITER_BOUNDS
   const unsigned lane = threadIdx.x & 31u;
   const int rl = int(lane) / V;
   const int i = int(lane) - rl * V;
+  pdl_wait();
+  pdl_launch_dependents();
   int64_t nrob = s.Nloc;
   if (par >= 0) {
     nrob = s.gen_count[par];

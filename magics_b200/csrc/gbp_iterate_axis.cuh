@@ -182,6 +182,11 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
   uint32_t *const hd_birth = reinterpret_cast<uint32_t *>(hd_nbr + rpc * kAxisEdges);
   uint8_t *const hd_frozen = reinterpret_cast<uint8_t *>(hd_birth + rpc * kAxisEdges);
   if (t < 2 * rpc) xbail[t] = 0;
+  // Programmatic dependent launch: everything above overlapped the tail of the kernel before this one in the
+  // stream; nothing it wrote is touched before this point.  The kernel after this one may start launching at once
+  // (it waits for this grid's completion at its own griddepcontrol.wait).  No-ops without the launch attribute.
+  pdl_wait();
+  pdl_launch_dependents();
 
   const double *const pubr = s.pub[p];
   double *const pubw = s.pub[1 - p];

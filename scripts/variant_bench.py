@@ -55,11 +55,13 @@ def main():
     for _ in range(a.warmup):
         g.step()
     g.sync()
-    g.set_profiling(True)
     g.timer_start()
     for _ in range(a.steps):
         g.step()
     ms = g.timer_stop_ms()
+    g.set_profiling(True)  # per-kernel times from a separate pass (events between kernels defeat launch overlap)
+    for _ in range(a.steps):
+        g.step()
     prof = g.read_profile()
     out.update(robots=sw.n, ms_per_tick=ms / a.steps, M_per_s=sw.n * substeps * a.steps / ms / 1e3,
                profile={k: [v["count"], round(v["ms"], 2)] for k, v in prof.items()} if isinstance(prof, dict) else None)
