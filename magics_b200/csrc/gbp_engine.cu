@@ -905,6 +905,8 @@ struct gbp_world {
   bool smem_opted_in[4] = {false, false, false, false};  // k_iterate<EXT,INT> dynamic shared memory opt-in
   bool axis_opted_in[12] = {};  // k_iterate_axis<EXT,INT,PART> likewise
   bool general_only = false;  // gbp_world_set_iterate_path: every robot through k_iterate
+  bool halo_overlap = true;   // sharded: border robots first, their halo behind the interior launch (GBP_HALO_OVERLAP=0:
+                              // one launch for all robots, the exchange before the next external half)
   bool use_pdl = true;        // iterate kernels launched with programmatic stream serialization (GBP_PDL=0: off)
   double *dyn_tab_dev = nullptr;  // Store::dyn_tab while every robot added so far has the same t0 (radius)
   bool t0_seen = false, t0_uniform = true;
@@ -1222,7 +1224,7 @@ cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), unsigned grid, unsign
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = (pdl && GBP_PDL) ? 1 : 0;  // without the kernels' griddepcontrol.wait the attribute would be unsafe
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
@@ -1307,7 +1309,7 @@ int group_launch(gbp_group *g) {
       CK(cudaGetLastError());
       w->launches += 1;
     }
-  bool split = INT && g->ws > 1;
+  bool split = INT && g->ws > 1 && g->members[0]->halo_overlap;
   for (gbp_world *w : g->members) {
     w->epoch += 1;  // every shard steps its epoch, with or without robots
     split = split && !w->general_only;
@@ -2037,6 +2039,7 @@ gbp_world *make_world(const gbp_config_t *cfg, int32_t device, cudaStream_t shar
   cudaDeviceGetAttribute(&w->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (const char *e = std::getenv("GBP_GENERAL_ONLY")) w->general_only = e[0] == '1';
   if (const char *e = std::getenv("GBP_PDL")) w->use_pdl = e[0] != '0';
+  if (const char *e = std::getenv("GBP_HALO_OVERLAP")) w->halo_overlap = e[0] != '0';
   // default SDF: a single white pixel (empty environment)
   const uint8_t white = 255;
   if (cudaMalloc(&w->sdf_dev, 1) != cudaSuccess ||

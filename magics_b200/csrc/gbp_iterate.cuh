@@ -57,9 +57,23 @@ constexpr size_t kIterSmemBytes = 0;
 #define GBP_MIRROR_MASK 1
 #endif
 
-// Programmatic dependent launch (sm_90+): wait for the grids this one depends on / let the next grid of the stream start.
-GBP_DEV void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-GBP_DEV void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+// Programmatic dependent launch (sm_90+): wait for the grids this one depends on / let the next grid of the stream
+// start.  Compiled in with -DGBP_PDL=1 only: measured (profiles/README.md r02q, r02r) it hides 0.7 % of a tick on a
+// 125 k-robot shard and nothing on 1 M robots, while the barrier the asm puts into k_iterate_axis' prologue costs
+// that kernel 1.5 %.
+#ifndef GBP_PDL
+#define GBP_PDL 0
+#endif
+GBP_DEV void pdl_wait() {
+#if GBP_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+GBP_DEV void pdl_launch_dependents() {
+#if GBP_PDL
+  asm volatile("griddepcontrol.launch_dependents;");
+#endif
+}
 
 GBP_DEV void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // first N components of a P-component per-variable record
