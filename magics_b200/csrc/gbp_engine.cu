@@ -815,6 +815,12 @@ struct gbp_group {
   // the factor half runs fused with the variable half, so the state "after factors, before variables" is never
   // materialised; reads and state-changing calls are refused while a pair is open (pair_open)
   bool pending_internal_factor = false, pending_external_factor = false;
+  // The topology pass of the NEXT tick depends on positions only, and those are final once
+  // update_prior_of_current_state has run: the search is started right there on a side stream (group_topology_early)
+  // and runs next to iterate_gbp; gbp_world_update_topology then only reads its sizes and applies it.
+  bool early_pending = false;        // a search is in flight / done on the topo streams
+  uint64_t topo_version = 0;         // bumped by whatever changes the search's inputs (positions, robots added / removed)
+  uint64_t early_version = 0;        // topo_version the pending search was started from
   bool halo_pending = false;         // an exchange started right after the border robots' internal half is in flight
                                      // on the comm streams (group_launch); the next external half waits for it
   cudaStream_t shared_stream = nullptr;
@@ -942,6 +948,9 @@ struct gbp_world {
   // halo / compute overlap: the robots of the send lists ("border") run first, their records travel on
   // comm_stream while the interior robots run on `stream`
   cudaStream_t comm_stream = nullptr;  // == stream for in-process shards (one device, one stream)
+  cudaStream_t topo_stream = nullptr;    // the early topology search (== stream for in-process shards)
+  cudaEvent_t ev_prior = nullptr, ev_topo = nullptr;
+  bool topo_early = true;                // GBP_TOPO_EARLY=0: search inside gbp_world_update_topology as in round 1
   cudaStream_t border_stream = nullptr;  // highest priority: the border robots' launches run CONCURRENTLY with the
                                          // interior launch and finish first (== stream for in-process shards)
   cudaEvent_t ev_start = nullptr;        // everything before this half-step pair is done (border_stream waits for it)
@@ -1058,7 +1067,7 @@ void mark_halo_stale(gbp_world *w) {
 
 // ---- transport ---------------------------------------------------------------------
 // Runs one exchange for every shard of the group living in this process (gbp_comm.cuh).
-int exchange(gbp_group *g, std::vector<gbp::XferPlan> &plans, bool on_comm_stream = false) {
+int exchange(gbp_group *g, std::vector<gbp::XferPlan> &plans, bool on_comm_stream = false, bool home_is_topo = false) {
   if (g->ws == 1) return 0;
   if (g->nccl) {
     gbp::NcclApi &api = gbp::nccl_api();
@@ -1066,8 +1075,9 @@ int exchange(gbp_group *g, std::vector<gbp::XferPlan> &plans, bool on_comm_strea
     // Every NCCL call of the communicator is enqueued on ONE stream (comm_stream), so the order of its
     // operations is the order of the calls on every rank; a caller working on w->stream is fenced in and out.
     cudaStream_t nst = w->comm_stream;
+    cudaStream_t home = home_is_topo ? w->topo_stream : w->stream;
     if (!on_comm_stream) {
-      CK(cudaEventRecord(w->ev_fence, w->stream));
+      CK(cudaEventRecord(w->ev_fence, home));
       CK(cudaStreamWaitEvent(nst, w->ev_fence, 0));
     }
     int rc = api.GroupStart();
@@ -1082,7 +1092,7 @@ int exchange(gbp_group *g, std::vector<gbp::XferPlan> &plans, bool on_comm_strea
     if (rc) return fail(GBP_ERR_NCCL, std::string("ncclGroupEnd: ") + api.GetErrorString(rc));
     if (!on_comm_stream) {
       CK(cudaEventRecord(w->ev_fence, nst));
-      CK(cudaStreamWaitEvent(w->stream, w->ev_fence, 0));
+      CK(cudaStreamWaitEvent(home, w->ev_fence, 0));
     }
     return 0;
   }
@@ -1134,10 +1144,7 @@ int group_halo(gbp_group *g, bool ahead = false) {
     Store &s = w->s;
     cudaStream_t st = ahead ? w->comm_stream : w->stream;
     const int pb = ahead ? 1 - w->p : w->p;
-    if (ahead && w->comm_stream != w->stream) {
-      CK(cudaEventRecord(w->ev_border, w->border_stream));
-      CK(cudaStreamWaitEvent(w->comm_stream, w->ev_border, 0));
-    }
+    if (ahead && w->comm_stream != w->stream) CK(cudaStreamWaitEvent(w->comm_stream, w->ev_border, 0));
     const int64_t hd = gbp::halo_doubles_per_robot(s.V);
     const int64_t nsend = w->send_po.start[ws];
     if (nsend > 0) {
@@ -1321,8 +1328,10 @@ int group_launch(gbp_group *g) {
     }
     if (INT) g->halo_stale = true;
   } else {
-    // border robots on the high-priority stream (behind everything queued so far), the halo of their new records
-    // on the comm stream behind them, the other robots on the shard's own stream at the same time
+    // border robots on the high-priority stream (behind everything queued so far), the other robots on the shard's own
+    // stream at the same time, the halo of the new border records on the comm stream behind the border launches.
+    // The interior launch is enqueued BEFORE the host builds the exchange (NCCL group calls take tens of
+    // microseconds of host time, during which the shard's own stream would otherwise sit empty: r02t8).
     for (gbp_world *w : g->members) {
       CK(cudaSetDevice(w->device));
       if (w->border_stream != w->stream) {
@@ -1330,14 +1339,12 @@ int group_launch(gbp_group *g) {
         CK(cudaStreamWaitEvent(w->border_stream, w->ev_start, 0));
       }
       if (int rc = launch_iterate<EXT, INT>(w, 1)) return rc;
-    }
-    if (int rc = group_halo(g, true)) return rc;
-    for (gbp_world *w : g->members) {
-      CK(cudaSetDevice(w->device));
+      if (w->border_stream != w->stream) CK(cudaEventRecord(w->ev_border, w->border_stream));
       if (int rc = launch_iterate<EXT, INT>(w, 2)) return rc;
       // what follows on the shard's own stream sees the border robots' results too
       if (w->border_stream != w->stream) CK(cudaStreamWaitEvent(w->stream, w->ev_border, 0));
     }
+    if (int rc = group_halo(g, true)) return rc;
   }
   if (INT)
     for (gbp_world *w : g->members) w->p ^= 1;
@@ -1492,9 +1499,18 @@ int ensure_topology_scratch(gbp_world *w) {
 }
 
 // Re-stride every per-variable / per-robot plane to `newcap` robot slots, keeping the own robots.
+int group_topology_early_wait(gbp_group *g);
+// Whatever changes what a neighbour search reads (positions, despawned flags, the robot count, the arrays
+// themselves) calls this first: a search in flight is waited for and its result is not used.
+int topology_inputs_change(gbp_world *w) {
+  w->grp->topo_version += 1;
+  return group_topology_early_wait(w->grp);
+}
+
 int reserve_robots(gbp_world *w, int64_t newcap) {
   Store &s = w->s;
   if (newcap <= s.cap) return 0;
+  if (int rc = topology_inputs_change(w)) return rc;  // the arrays move
   cudaStream_t st = w->stream;
   const int V = s.V;
   // whole tiles (gbp_store.cuh)
@@ -1556,7 +1572,11 @@ int reserve_robots(gbp_world *w, int64_t newcap) {
 
 // ---- topology, phase 1 (per shard): neighbour search, diff against the live CSR, ghost and
 // send lists; one host sync reads the sizes.
-int topo_search(gbp_world *w) {
+// mode 0: the whole pass on the shard's own stream, sizes read back before returning.
+// mode 1: enqueue only, on the topo stream (group_topology_early); mode 2: the pass enqueued by mode 1 has
+// completed (the caller waited for ev_topo) — read its sizes; if a buffer turns out too small the affected part
+// runs again on the shard's own stream.
+int topo_search(gbp_world *w, int mode = 0) {
   CK(cudaSetDevice(w->device));
   Store &s = w->s;
   const int32_t n = s.Nloc, ws = w->sh.ws;
@@ -1567,10 +1587,11 @@ int topo_search(gbp_world *w) {
     w->Ntot = n;
   }
   const int32_t ntot = w->Ntot, g0 = w->sh.gfirst[w->sh.rank];
-  w->tp = gbp_world::TopoPass();
+  if (mode != 2) w->tp = gbp_world::TopoPass();
   if (ntot == 0) return 0;
-  cudaStream_t st = w->stream;
-  if (int rc = ensure_topology_scratch(w)) return rc;
+  cudaStream_t st = mode == 1 ? w->topo_stream : w->stream;
+  if (mode != 2)
+    if (int rc = ensure_topology_scratch(w)) return rc;
   const float *gx = ws > 1 ? w->gpos : s.pos;
   const float *gz = ws > 1 ? w->gpos + ntot : s.pos + s.cap;
   const float *ggone = ws > 1 ? w->gpos + 3 * int64_t(ntot) : s.gone;
@@ -1580,11 +1601,15 @@ int topo_search(gbp_world *w) {
   // entries in the hash: every robot on one GPU; on a shard only the robots near its own ones (k_cell_keys_near),
   // padded to cand_cap with a sentinel key pointing at a cell-less dummy
   int32_t nall = ntot;
+  if (ws > 1) {
+    if (w->cand_cap <= 0 || w->cand_cap > ntot) w->cand_cap = ntot;
+    nall = int32_t(w->cand_cap);
+  }
+  size_t cb = w->t_cub_bytes;
+  if (mode != 2) {
   if (ws == 1) {
     gbp::k_cell_keys<<<blocks_for(ntot, T), T, 0, st>>>(ntot, gx, gz, ggone, cell, w->t_cx, w->t_cz, w->t_keys, w->t_idx);
   } else {
-    if (w->cand_cap <= 0 || w->cand_cap > ntot) w->cand_cap = ntot;
-    nall = int32_t(w->cand_cap);
     k_box_init<<<1, 32, 0, st>>>(w->t_box, w->t_cx + ntot, w->t_cz + ntot);
     if (n > 0) gbp::k_own_bbox<<<blocks_for(n, 256), 256, 0, st>>>(g0, n, gx, gz, ggone, w->t_box);
     gbp::k_fill_u32<<<blocks_for(nall, 256), 256, 0, st>>>(w->t_keys, w->t_idx, nall, 0xFFFFFFFFu, ntot);
@@ -1592,7 +1617,7 @@ int topo_search(gbp_world *w) {
                                                             w->t_cz, w->t_keys, w->t_idx, nall, w->t_box + 4);
     w->launches += 3;
   }
-  size_t cb = w->t_cub_bytes;
+  cb = w->t_cub_bytes;
   CK(cub::DeviceRadixSort::SortPairs(w->t_cub, cb, w->t_keys, w->t_keys_sorted, w->t_idx, w->t_idx_sorted, nall, 0, 32, st));
   if (n > 0)
     gbp::k_neighbours_find<<<blocks_for(n, T), T, 0, st>>>(nall, g0, n, gx, gz, w->t_cx, w->t_cz, w->t_keys_sorted,
@@ -1601,11 +1626,13 @@ int topo_search(gbp_world *w) {
   cb = w->t_cub_bytes;
   CK(cub::DeviceScan::ExclusiveSum(w->t_cub, cb, w->t_cnt, w->t_off, n + 1, st));
   w->launches += 4;
+  }  // mode != 2
   // The new CSR is written straight into the spare edge set.  If the spare set is too small the
   // guarded kernels did nothing: grow it and run them again.
   EdgeSet *spare = &w->edges[1 - w->cur];
   const EdgeSet *live = &w->edges[w->cur];
   const bool quirk = w->cfg.strict_reference_quirks != 0;
+  if (quirk && mode != 0) return fail(GBP_ERR_STATE, "strict_reference_quirks: the early topology search is not available");
   if (quirk && n > 0) {
     // delete_interrobot_factors as written: the robots within range become their own CSR (q_woff, q_wnbr); the new
     // rows are the old edges that survive the lossy deletion merged with fresh edges (k_quirk_rows).  A test mode:
@@ -1646,6 +1673,8 @@ int topo_search(gbp_world *w) {
     w->launches += 6;
   }
   for (int attempt = 0; attempt < 2; ++attempt) {
+    const bool enqueue = !(mode == 2 && attempt == 0);  // mode 2: the first attempt was enqueued by mode 1
+    if (enqueue) {
     if (n > 0 && !quirk) {
       gbp::k_neighbours_fill<<<blocks_for(n, T), T, 0, st>>>(nall, g0, n, gx, gz, w->t_cx, w->t_cz, w->t_keys_sorted,
                                                              w->t_idx_sorted, R, w->t_off, w->t_park, spare->egid,
@@ -1678,8 +1707,10 @@ int topo_search(gbp_world *w) {
     k_words_to_host<<<1, 64, 0, st>>>(w->t_result_host, w->t_result_dev, int(kResultWords));
     CK(cudaGetLastError());
     w->launches += 1;
+    if (mode == 1) return 0;  // the sizes are read by the mode-2 call
     CK(cudaStreamSynchronize(st));
     w->launches += 1;
+    }  // enqueue
     if (w->t_result_host[3] != 0)
       return fail(GBP_ERR_STATE, "sharded topology: a cross-shard robot_number lookup failed in an earlier pass "
                                  "(neighbour lists of two shards disagree)");
@@ -1857,6 +1888,78 @@ int topo_apply(gbp_world *w, const int64_t (*hdr)[4]) {
   return 0;
 }
 
+// Every shard learns every robot's Transform (x, z), radius and despawned flag: 16 bytes per robot per tick.
+// `early`: on the topo streams (group_topology_early), else on the shards' own streams.
+int group_exchange_positions(gbp_group *g, bool early) {
+  const int ws = g->ws;
+  const size_t nm = g->members.size();
+  std::vector<gbp::XferPlan> plans(nm);
+  for (size_t m = 0; m < nm; ++m) {
+    gbp_world *w = g->members[m];
+    CK(cudaSetDevice(w->device));
+    Store &s = w->s;
+    cudaStream_t st = early ? w->topo_stream : w->stream;
+    const int rank = w->sh.rank, ntot = w->Ntot, n = s.Nloc, g0 = w->sh.gfirst[rank];
+    const float *src[4] = {s.pos, s.pos + s.cap, s.radius, s.gone};
+    for (int k = 0; k < 4; ++k) {
+      if (n > 0)
+        CK(cudaMemcpyAsync(w->gpos + int64_t(k) * ntot + g0, src[k], size_t(n) * 4, cudaMemcpyDeviceToDevice, st));
+      for (int q = 0; q < ws; ++q) {
+        if (q == rank) continue;
+        const int nq = w->sh.gfirst[q + 1] - w->sh.gfirst[q];
+        if (n > 0) plans[m].sends.push_back({q, const_cast<float *>(src[k]), size_t(n) * 4});
+        if (nq > 0) plans[m].recvs.push_back({q, w->gpos + int64_t(k) * ntot + w->sh.gfirst[q], size_t(nq) * 4});
+      }
+    }
+  }
+  // sends are grouped by plane then peer on both sides, so the k-th send to a peer pairs with its k-th receive
+  return exchange(g, plans, false, early);
+}
+
+// Host and the shards' own streams wait for a search that group_topology_early started (if any).
+int group_topology_early_wait(gbp_group *g) {
+  if (!g->early_pending) return 0;
+  for (gbp_world *w : g->members) {
+    CK(cudaSetDevice(w->device));
+    CK(cudaEventSynchronize(w->ev_topo));
+    if (w->topo_stream != w->stream) CK(cudaStreamWaitEvent(w->stream, w->ev_topo, 0));
+  }
+  g->early_pending = false;
+  return 0;
+}
+
+// The next tick's neighbour search, started as soon as the positions it reads are final (the end of
+// update_prior_of_current_state): it runs on the topo streams next to iterate_gbp, which neither reads what it writes
+// (scratch, the spare edge set) nor writes what it reads (positions, the live edge lists).
+int group_topology_early(gbp_group *g) {
+  gbp_world *w0 = g->members[0];
+  if (!w0->topo_early || w0->cfg.strict_reference_quirks || (g->ws > 1 && !g->committed)) return 0;
+  if (int rc = group_topology_early_wait(g)) return rc;  // an earlier one nobody used
+  for (gbp_world *w : g->members) {
+    CK(cudaSetDevice(w->device));
+    if (w->topo_stream != w->stream) {
+      CK(cudaEventRecord(w->ev_prior, w->stream));
+      CK(cudaStreamWaitEvent(w->topo_stream, w->ev_prior, 0));
+    }
+  }
+  if (g->ws > 1) {
+    ProfileScope pp(w0, GBP_PROFILE_TOPO_POSITIONS, w0->topo_stream);
+    if (int rc = group_exchange_positions(g, true)) return rc;
+  }
+  {
+    ProfileScope pq(w0, GBP_PROFILE_TOPO_SEARCH, w0->topo_stream);
+    for (gbp_world *w : g->members)
+      if (int rc = topo_search(w, 1)) return rc;
+  }
+  for (gbp_world *w : g->members) {
+    CK(cudaSetDevice(w->device));
+    CK(cudaEventRecord(w->ev_topo, w->topo_stream));
+  }
+  g->early_pending = true;
+  g->early_version = g->topo_version;
+  return 0;
+}
+
 // update_robot_neighbours + delete_interrobot_factors + create_interrobot_factors for every
 // shard of the group (robot.rs:1362-1586).
 int group_update_topology(gbp_group *g) {
@@ -1866,33 +1969,20 @@ int group_update_topology(gbp_group *g) {
   ProfileScope ps(g->members[0], GBP_PROFILE_TOPOLOGY);
   const size_t nm = g->members.size();
   std::vector<gbp::XferPlan> plans(nm);
-  if (ws > 1) {
+  // a search started early is used if nothing it read has changed since; either way it is waited for first
+  const bool early = g->early_pending && g->early_version == g->topo_version;
+  if (int rc = group_topology_early_wait(g)) return rc;
+  if (ws > 1 && !early) {
     ProfileScope pp(g->members[0], GBP_PROFILE_TOPO_POSITIONS);
-    // every shard learns every robot's Transform (x, z), radius and despawned flag: 16 bytes per robot per tick
-    for (size_t m = 0; m < nm; ++m) {
-      gbp_world *w = g->members[m];
-      CK(cudaSetDevice(w->device));
-      Store &s = w->s;
-      const int rank = w->sh.rank, ntot = w->Ntot, n = s.Nloc, g0 = w->sh.gfirst[rank];
-      const float *src[4] = {s.pos, s.pos + s.cap, s.radius, s.gone};
-      for (int k = 0; k < 4; ++k) {
-        if (n > 0)
-          CK(cudaMemcpyAsync(w->gpos + int64_t(k) * ntot + g0, src[k], size_t(n) * 4, cudaMemcpyDeviceToDevice, w->stream));
-        for (int q = 0; q < ws; ++q) {
-          if (q == rank) continue;
-          const int nq = w->sh.gfirst[q + 1] - w->sh.gfirst[q];
-          if (n > 0) plans[m].sends.push_back({q, const_cast<float *>(src[k]), size_t(n) * 4});
-          if (nq > 0) plans[m].recvs.push_back({q, w->gpos + int64_t(k) * ntot + w->sh.gfirst[q], size_t(nq) * 4});
-        }
-      }
-    }
-    // sends are grouped by plane then peer on both sides, so the k-th send to a peer pairs with its k-th receive
-    if (int rc = exchange(g, plans)) return rc;
+    if (int rc = group_exchange_positions(g, false)) return rc;
   }
-  {
+  if (early) {  // timed where it ran (group_topology_early); here the host only reads its sizes
+    for (gbp_world *w : g->members)
+      if (int rc = topo_search(w, 2)) return rc;
+  } else {
     ProfileScope pq(g->members[0], GBP_PROFILE_TOPO_SEARCH);
     for (gbp_world *w : g->members)
-      if (int rc = topo_search(w)) return rc;
+      if (int rc = topo_search(w, 0)) return rc;
   }
   ProfileScope pa(g->members[0], GBP_PROFILE_TOPO_APPLY);
   int64_t hdr[gbp::kMaxShards][4];
@@ -1930,6 +2020,7 @@ int group_commit(gbp_group *g) {
   const int ws = g->ws;
   const size_t nm = g->members.size();
   std::vector<gbp::XferPlan> plans(nm);
+  if (int rc = topology_inputs_change(g->members[0])) return rc;
   for (size_t m = 0; m < nm; ++m) {
     gbp_world *w = g->members[m];
     CK(cudaSetDevice(w->device));
@@ -2068,6 +2159,14 @@ void join_group(gbp_world *w, gbp_group *g, int rank) {
   cudaEventCreateWithFlags(&w->ev_halo, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&w->ev_fence, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&w->ev_start, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&w->ev_prior, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&w->ev_topo, cudaEventDisableTiming);
+  w->topo_stream = w->stream;
+  if (g->nccl || g->ws == 1) {
+    cudaSetDevice(w->device);
+    cudaStreamCreateWithFlags(&w->topo_stream, cudaStreamNonBlocking);
+  }
+  if (const char *e = std::getenv("GBP_TOPO_EARLY")) w->topo_early = e[0] != '0';
   w->border_stream = w->stream;
   if (g->nccl) {
     int lo = 0, hi = 0;
@@ -2182,6 +2281,12 @@ void gbp_world_destroy(gbp_world_t *w) {
     cudaStreamSynchronize(w->border_stream);
     cudaStreamDestroy(w->border_stream);
   }
+  if (w->topo_stream && w->topo_stream != w->stream) {
+    cudaStreamSynchronize(w->topo_stream);
+    cudaStreamDestroy(w->topo_stream);
+  }
+  for (cudaEvent_t e : {w->ev_prior, w->ev_topo})
+    if (e) cudaEventDestroy(e);
   cudaFree(w->msg_cnt);
   cudaFree(w->border_gen_list);
   cudaFree(w->border_gen_count);
@@ -2480,6 +2585,7 @@ int gbp_world_add_robots(gbp_world_t *w, int32_t n, const float *radii, const ui
     return fail(GBP_ERR_STATE, "gbp_world_add_robots: a sharded world takes robots only before gbp_world_commit_shards "
                                "(global ids are contiguous per shard)");
   const int64_t N0 = s.Nloc, N1 = int64_t(s.Nloc) + n;
+  if (int rc = topology_inputs_change(w)) return rc;
   if (int rc = reserve_robots(w, N1)) return rc;
   const int64_t newNV = s.NV, used = N0 * V;
   {  // eoff: new robots start without edges
@@ -2659,6 +2765,7 @@ int gbp_world_remove_robots(gbp_world_t *w, int32_t m, const int32_t *robots) {
     if (robots[k] < 0 || robots[k] >= w->s.Nloc)
       return fail(GBP_ERR_BAD_ARGUMENT, "gbp_world_remove_robots: robot index out of range");
   if (m == 0) return 0;
+  if (int rc = topology_inputs_change(w)) return rc;
   w->gone_host.resize(size_t(w->s.Nloc), 0);
   for (int k = 0; k < m; ++k)
     if (!w->gone_host[robots[k]]) {
@@ -2825,7 +2932,8 @@ int gbp_world_update_prior_of_current_state(gbp_world_t *w0) {
     w->launches += 1;
   }
   w0->grp->halo_stale = true;
-  return 0;
+  w0->grp->topo_version += 1;  // Transform.translation moved
+  return group_topology_early(w0->grp);
 }
 
 int gbp_world_change_prior_of_variable(gbp_world_t *w, int32_t var, int32_t m, const int32_t *robots,
