@@ -312,52 +312,85 @@ __device__ void change_prior_dev(const Store &s, int p, uint32_t epoch, int64_t 
 
 // change_prior_dev spread over the 32 lanes of a warp (one robot per warp): a prior change touches
 // ~70 scattered sectors of one robot, so one thread per robot is pure latency; every lane must
-// hold the same `nm`, computed from reads that happened before the __syncwarp below.
-__device__ void change_prior_warp(const Store &s, int p, uint32_t epoch, int64_t r, int var, const double (&nm)[4],
-                                  unsigned lane) {
+// hold the same `nm`, computed from reads that happened before the __syncwarp between the two phases.
+// Two phases — everything a change reads (prior_load), then its stores (prior_store) — so that a warp making
+// both prior changes of a tick (k_prior_both) has the loads of both in flight together.
+struct PriorLoad {
+  bool latest;
+  double keep, pl, mark, mir0;
+  int64_t eo0, eo1;
+  uint8_t frz0;
+};
+__device__ PriorLoad prior_load(const Store &s, int p, int64_t r, int var, unsigned lane) {
+  const int64_t vi = r * s.V + var;
+  PriorLoad q;
+  q.latest = s.latest[r] != 0;
+  q.keep = 0.0;
+  if (q.latest && lane < 20) q.keep = s.bel_ext[s.at<gbp::kRec>(lane, vi)];
+  q.pl = s.prior_lam[vi];
+  q.mark = 0.0;
+  if (lane == 25) q.mark = s.m_dynL[p][s.at<20>(0, vi)];
+  else if (lane == 26) q.mark = s.m_dynR[p][s.at<20>(0, vi)];
+  else if (lane == 27) q.mark = s.m_obs[s.at<4>(0, vi)];
+  else if (lane == 28) q.mark = s.m_trk[s.at<3>(0, vi)];
+  q.eo0 = q.eo1 = 0;
+  q.mir0 = 0.0;
+  q.frz0 = 0;
+  if (var >= 1 && s.eoff) {
+    q.eo0 = s.eoff[r];
+    q.eo1 = s.eoff[r + 1];
+    const int64_t e = q.eo0 + lane;
+    if (e < q.eo1) {
+      q.mir0 = s.mir[e * (s.V - 1) + (var - 1)];
+      q.frz0 = s.e_frozen[e];
+    }
+  }
+  return q;
+}
+__device__ void prior_store(const Store &s, int p, uint32_t epoch, int64_t r, int var, const double (&nm)[4],
+                            unsigned lane, const PriorLoad &q) {
   // Every store below lands in a 32-byte sector of which it fills 8 bytes (a read-modify-write in DRAM), so
   // nothing is written that already holds the value: the (eta, Lambda) rows move only when the current belief
   // lives in bel_ext, bel_ext is left alone while nothing reads it (latest == 0: every reader takes
   // `latest ? bel_ext : pub[p]`), an Empty marker is not stored over an Empty marker, and mu_frozen is
   // only meaningful while the edge's frozen bit is set (otherwise A's factor holds mu_ext).
   const int64_t vi = r * s.V + var;
-  const bool latest = s.latest[r] != 0;
-  double keep = 0.0;
-  if (latest && lane < 20) keep = s.bel_ext[s.at<gbp::kRec>(lane, vi)];
-  const double pl = s.prior_lam[vi];
-  double mark = 0.0;
-  if (lane == 25) mark = s.m_dynL[p][s.at<20>(0, vi)];
-  else if (lane == 26) mark = s.m_dynR[p][s.at<20>(0, vi)];
-  else if (lane == 27) mark = s.m_obs[s.at<4>(0, vi)];
-  else if (lane == 28) mark = s.m_trk[s.at<3>(0, vi)];
-  __syncwarp();
   if (lane < 20) {
-    if (latest) s.pub[p][s.at<gbp::kRec>(lane, vi)] = keep;
+    if (q.latest) s.pub[p][s.at<gbp::kRec>(lane, vi)] = q.keep;
   } else if (lane < 24) {
     const int k = int(lane) - 20;
     s.pub[p][s.at<gbp::kRec>(20 + k, vi)] = nm[k];
-    if (latest) s.bel_ext[s.at<gbp::kRec>(20 + k, vi)] = nm[k];
-    s.prior_eta[s.at<4>(k, vi)] = pl * nm[k];
+    if (q.latest) s.bel_ext[s.at<gbp::kRec>(20 + k, vi)] = nm[k];
+    s.prior_eta[s.at<4>(k, vi)] = q.pl * nm[k];
   } else if (lane == 24) {
     s.pub_epoch[p][vi] = epoch;
     s.mu_ext[s.at<2>(0, vi)] = nm[0];
     s.mu_ext[s.at<2>(1, vi)] = nm[1];
-  } else if (lane <= 28 && !gbp::is_empty_marker(mark)) {
+  } else if (lane <= 28 && !gbp::is_empty_marker(q.mark)) {
     if (lane == 25) s.m_dynL[p][s.at<20>(0, vi)] = gbp::empty_marker();
     else if (lane == 26) s.m_dynR[p][s.at<20>(0, vi)] = gbp::empty_marker();
     else if (lane == 27) s.m_obs[s.at<4>(0, vi)] = gbp::empty_marker();
     else s.m_trk[s.at<3>(0, vi)] = gbp::empty_marker();
   }
   if (var >= 1 && s.eoff)
-    for (int64_t e = s.eoff[r] + lane; e < s.eoff[r + 1]; e += 32) {
+    for (int64_t e = q.eo0 + lane; e < q.eo1; e += 32) {
       const int64_t m = e * (s.V - 1) + (var - 1);
-      if (!gbp::is_empty_marker(s.mir[m])) s.mir[m] = gbp::empty_marker();
+      const bool first = e == q.eo0 + lane;
+      const double mir = first ? q.mir0 : s.mir[m];
+      const uint8_t frz = first ? q.frz0 : s.e_frozen[e];
+      if (!gbp::is_empty_marker(mir)) s.mir[m] = gbp::empty_marker();
       // external factors receive the new mean whatever the antenna state (robot.rs:2272-2282)
-      if (s.e_frozen[e] & 1) {
+      if (frz & 1) {
         s.mu_frozen[m] = nm[0];
         s.mu_frozen[s.EV + m] = nm[1];
       }
     }
+}
+__device__ void change_prior_warp(const Store &s, int p, uint32_t epoch, int64_t r, int var, const double (&nm)[4],
+                                  unsigned lane) {
+  const PriorLoad q = prior_load(s, p, r, var, lane);
+  __syncwarp();
+  prior_store(s, p, epoch, r, var, nm, lane, q);
 }
 
 // update_prior_of_horizon_state (planner/robot.rs:2182-2283), one warp per robot.
@@ -408,6 +441,71 @@ __global__ void k_prior_current(Store s, int p, uint32_t epoch, float delta_t) {
   }
   const float px = s.pos[r], pz = s.pos[s.cap + r];
   change_prior_warp(s, p, epoch, r, 0, nm, lane);
+  if (lane == 0) {
+    s.pos[r] = __fadd_rn(px, float(ch[0]));
+    s.pos[s.cap + r] = __fadd_rn(pz, float(ch[1]));
+  }
+}
+
+// update_prior_of_horizon_state followed by update_prior_of_current_state (the order of a tick, robot.rs:85-108) in
+// one launch, one warp per robot: the two changes touch different variables (V - 1 and 0; the second reads the means
+// of 0 and 1), so for V >= 3 the result is that of k_prior_horizon then k_prior_current, with the scattered loads of
+// both in flight at once (each kernel alone is bound by its chain of dependent loads, not by bytes).
+__global__ void k_prior_both(Store s, int p, uint32_t epoch_h, uint32_t epoch_c, double delta_t, double max_speed,
+                             int iterations_internal, float delta_t_f) {
+  const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31u;
+  if (r >= s.Nloc) return;
+  if (s.idle[r]) return;
+  const bool finished = s.finished[r] != 0;
+  const int32_t w0 = s.wp_off[r], nwp = s.wp_off[r + 1] - w0, k = s.next_wp[r];
+  const float t0 = s.t0[r], px = s.pos[r], pz = s.pos[s.cap + r];
+  bool do_h = !finished;
+  if (do_h && (k < 0 || k >= nwp)) {
+    if (lane == 0) s.finished[r] = 1;
+    do_h = false;
+  }
+  if (iterations_internal == 0) do_h = false;
+  const int64_t v0 = r * s.V, v1 = v0 + 1, vh = v0 + (s.V - 1);
+  const double *src = s.latest[r] ? s.bel_ext : s.pub[p];
+  double ex = 0.0, ey = 0.0, wx = 0.0, wy = 0.0, c0[4], c1[4];
+  if (do_h) {
+    ex = src[s.at<gbp::kRec>(20, vh)];
+    ey = src[s.at<gbp::kRec>(21, vh)];
+    const float *wp = s.wp_xy + 2 * (size_t(w0) + k);
+    wx = double(wp[0]);
+    wy = double(wp[1]);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    c0[q] = src[s.at<gbp::kRec>(20 + q, v0)];
+    c1[q] = src[s.at<gbp::kRec>(20 + q, v1)];
+  }
+  PriorLoad qh{};
+  if (do_h) qh = prior_load(s, p, r, s.V - 1, lane);
+  const PriorLoad qc = prior_load(s, p, r, 0, lane);
+  // horizon (k_prior_horizon)
+  const double hx = wx - ex, hy = wy - ey;
+  const double dist = gbp::norm2(hx, hy);
+  double nx = hx, ny = hy;
+  if (!(dist == 0.0 || isinf(dist))) {
+    nx /= dist;
+    ny /= dist;
+  }
+  const double sp = fmin(max_speed, dist);
+  const double vx = sp * nx, vy = sp * ny;
+  const double nmh[4] = {ex + vx * delta_t, ey + vy * delta_t, vx, vy};
+  // current state (k_prior_current)
+  const float time_scale = __fdiv_rn(delta_t_f, t0);
+  double ch[4], nmc[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    ch[q] = double(time_scale) * (c1[q] - c0[q]);
+    nmc[q] = c0[q] + ch[q];
+  }
+  __syncwarp();
+  if (do_h) prior_store(s, p, epoch_h, r, s.V - 1, nmh, lane, qh);
+  prior_store(s, p, epoch_c, r, 0, nmc, lane, qc);
   if (lane == 0) {
     s.pos[r] = __fadd_rn(px, float(ch[0]));
     s.pos[s.cap + r] = __fadd_rn(pz, float(ch[1]));
@@ -2936,6 +3034,33 @@ int gbp_world_update_prior_of_current_state(gbp_world_t *w0) {
   return group_topology_early(w0->grp);
 }
 
+namespace {
+// Both prior updates of a tick in one launch (k_prior_both); false if the world has to take them one by one.
+bool priors_fusable(const gbp_world *w0) {
+  static const bool off = [] { const char *e = std::getenv("GBP_PRIORS_FUSED"); return e && e[0] == '0'; }();
+  if (off) return false;
+  for (const gbp_world *w : w0->grp->members)
+    if (w->s.V < 3 || w->count_messages) return false;
+  return true;
+}
+int update_priors_fused(gbp_world *w0) {
+  for (gbp_world *w : w0->grp->members) {
+    if (set_device(w)) return GBP_ERR_CUDA;
+    w->epoch += 2;
+    if (w->s.Nloc == 0) continue;
+    ProfileScope ps(w, GBP_PROFILE_PRIORS);
+    k_prior_both<<<blocks_for(int64_t(w->s.Nloc) * 32, 128), 128, 0, w->stream>>>(
+        w->s, w->p, w->epoch - 1, w->epoch, double(w->cfg.delta_t), double(w->cfg.target_speed),
+        w->cfg.iterations_internal, w->cfg.delta_t);
+    CK(cudaGetLastError());
+    w->launches += 1;
+  }
+  w0->grp->halo_stale = true;
+  w0->grp->topo_version += 1;  // Transform.translation moved
+  return group_topology_early(w0->grp);
+}
+}  // namespace
+
 int gbp_world_change_prior_of_variable(gbp_world_t *w, int32_t var, int32_t m, const int32_t *robots,
                                        const double *new_means) {
   if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
@@ -3175,8 +3300,12 @@ int gbp_world_external_variable_iteration(gbp_world_t *w) {
 int gbp_world_step(gbp_world_t *w) {
   int rc;
   if ((rc = gbp_world_update_topology(w))) return rc;
-  if ((rc = gbp_world_update_prior_of_horizon_state(w))) return rc;
-  if ((rc = gbp_world_update_prior_of_current_state(w))) return rc;
+  if (priors_fusable(w)) {
+    if ((rc = update_priors_fused(w))) return rc;
+  } else {
+    if ((rc = gbp_world_update_prior_of_horizon_state(w))) return rc;
+    if ((rc = gbp_world_update_prior_of_current_state(w))) return rc;
+  }
   return gbp_world_iterate(w);
 }
 

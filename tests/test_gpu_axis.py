@@ -211,3 +211,30 @@ def test_fullsize_lattice_is_entirely_in_the_axis_kernel():
     for _ in range(3):
         b.step()
     assert_same_bits(b.read_beliefs(), ba, "lattice-100k general_only vs auto")
+
+
+def test_step_equals_its_four_calls_made_one_by_one():
+    """gbp_world_step makes both prior updates in one launch (k_prior_both) and starts the next tick's neighbour
+    search early; a world driven by the four calls of a tick one by one (two prior kernels, and robots removed /
+    added between ticks so that a search in flight has to be thrown away) must hold the same bits."""
+    sw = scenarios.circle(14, 9.0)
+    a, b = World(sw.cfg), World(sw.cfg)
+    o = OracleWorld(sw.cfg)
+    for w in (a, b, o):
+        sw.add_to(w)
+    for tick in range(24):
+        a.step()
+        b.update_topology()
+        b.update_prior_of_horizon_state()
+        b.update_prior_of_current_state()
+        b.iterate()
+        o.step()
+        if tick == 9:
+            for w in (a, b, o):
+                w.remove_robots([3, 7])
+        if tick == 15:
+            for w in (a, b, o):
+                sw.add_to(w, set_sdf=False)  # a second copy of the swarm on top of the first
+        if tick % 4 == 3 or tick in (10, 16):
+            _same(a, b, f"tick {tick}")
+            check(a, o, f"tick {tick}")
