@@ -264,6 +264,46 @@ int gbp_world_read_collision_totals(gbp_world_t *w, int64_t *num_collisions, int
 /* RobotRobotCollisions::get(entity) for every own robot: per_robot[n]. */
 int gbp_world_read_robot_collisions(gbp_world_t *w, uint32_t *per_robot);
 
+/* ---- robot-environment collisions (planner/collisions.rs:368-455) ------------------------------
+ * The `Colliders` resource (gbp_global_planner::Colliders, filled by environment/map_generator.rs:141-536,
+ * :537-1298): one convex parry2d shape per collider in its own frame plus an Isometry2.  kind 0 = Ball
+ * (radius), 1 = Cuboid (half_extents), 2 = Triangle (3 vertices), 3 = ConvexPolygon (num_vertices >= 3,
+ * counter-clockwise as ConvexPolygon::from_convex_hull leaves them); vertices index into `vertices_xy`. */
+typedef struct gbp_collider {
+  int32_t kind;
+  float translation[2]; /* isometry.translation (world x, z) */
+  float angle;          /* isometry.rotation angle, radians */
+  float radius;
+  float half_extents[2];
+  int32_t first_vertex, num_vertices;
+} gbp_collider_t;
+/* Replaces the collider set and clears every robot's collision history (RobotEnvironmentCollisions::clear on
+ * LoadSimulation / ReloadSimulation, collisions.rs:40-46).  Per handle: a shard tests its own robots. */
+int gbp_world_set_environment_colliders(gbp_world_t *w, int32_t n, const gbp_collider_t *colliders,
+                                        int32_t num_vertices, const float *vertices_xy);
+/* update_robot_environment_collisions (collisions.rs:368-431): parry2d intersection_test of every own robot's Ball
+ * at its Transform against every collider, CollisionHistory::update per (robot, collider) (:455-493); a
+ * Free -> Colliding transition is one collision.  num_collisions = RobotEnvironmentCollisions::num_collisions(),
+ * colliding_now = pairs in state Colliding; either pointer may be NULL (no host sync then). */
+int gbp_world_update_environment_collisions(gbp_world_t *w, int64_t *num_collisions, int64_t *colliding_now);
+/* RobotEnvironmentCollisions::get(entity) for every own robot: per_robot[n]. */
+int gbp_world_read_environment_collisions(gbp_world_t *w, uint32_t *per_robot);
+
+/* ---- PositionTracker / VelocityTracker (planner/tracking.rs:36-260) ------------------------------
+ * Every robot carries two ring buffers of `capacity` samples and a repeating Timer of `sample_ns`
+ * (spawner.rs:627-628: 10000 samples, 100 ms).  Memory: 32 bytes x capacity x robots on the device. */
+int gbp_world_set_tracking_buffers(gbp_world_t *w, int32_t capacity, uint64_t sample_ns);
+/* track_positions + track_velocities for one FixedUpdate (tracking.rs:117-137, :226-260): call once per tick after
+ * update_prior_of_current_state and before the next set_comms.  delta_ns = Time<Fixed>::delta(), elapsed_seconds =
+ * Time::elapsed_seconds_f64().  Robots whose Transform changed this tick (not idle, or added since the last call) tick
+ * their Timer; when it fires the position (x, z) and the velocity over the time since the previous sample are pushed. */
+int gbp_world_track(gbp_world_t *w, uint64_t delta_ns, double elapsed_seconds);
+/* The raw rings of the own robots, slot-major: num_*[n] = samples pushed so far (sample k sits in slot
+ * k % capacity); positions_xy / velocities_xy [capacity][2][n], velocity_timestamp / velocity_measured_over
+ * [capacity][n] (VelocityMeasurement.timestamp, .measured_over in seconds).  Any pointer may be NULL. */
+int gbp_world_read_tracks(gbp_world_t *w, uint32_t *num_positions, float *positions_xy, uint32_t *num_velocities,
+                          float *velocities_xy, double *velocity_timestamp, double *velocity_measured_over);
+
 /* update_prior_of_horizon_state (robot.rs:2182-2283) for every robot. */
 int gbp_world_update_prior_of_horizon_state(gbp_world_t *w);
 /* update_prior_of_current_state_v3 (robot.rs:2286-2338) for every robot;

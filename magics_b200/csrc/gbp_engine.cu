@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/gbp_b200.h"
+#include "gbp_collide.cuh"
 #include "gbp_comm.cuh"
 #include "gbp_iterate.cuh"
 #include "gbp_iterate_axis.cuh"
@@ -1018,6 +1019,17 @@ struct gbp_world {
   int sm_count = 148;
   int par = 0;                // launch parity: which Store::gen_count the current launch appends to
   unsigned long long *coll_totals = nullptr;              // [0] Hit events so far, [1] pairs colliding now
+  // robot-environment collisions (gbp_collide.cuh): the Colliders resource, CollisionHistory bits per (robot, collider)
+  gbp::ColliderDev *env_cols = nullptr;
+  float *env_verts = nullptr;
+  int32_t env_ncol = 0, env_words = 0;
+  uint32_t *env_state = nullptr, *env_hits = nullptr;  // [robots][words], [robots]
+  int64_t env_robots = 0;                               // robots the two arrays are sized for
+  unsigned long long *env_totals = nullptr;             // [0] Hit events so far, [1] pairs colliding now
+  // position / velocity sample buffers (planner/tracking.rs)
+  gbp::TrackRings trk{};
+  uint64_t trk_duration_ns = 0;
+  int32_t trk_seen = 0;  // robots that existed when the trackers last ran (later ones count as Changed<Transform>)
   gbp::ShardInfo sh{};          // ws, rank, gfirst
   int32_t Ntot = 0;             // robots of the whole swarm
   int32_t nghost = 0;
@@ -2363,6 +2375,9 @@ int gbp_world_create_local_shards(const gbp_config_t *cfg, int32_t device, int32
   return 0;
 }
 
+namespace {
+void free_track_rings(gbp_world *w);
+}
 void gbp_world_destroy(gbp_world_t *w) {
   if (!w) return;
   cudaSetDevice(w->device);
@@ -2385,6 +2400,12 @@ void gbp_world_destroy(gbp_world_t *w) {
   }
   for (cudaEvent_t e : {w->ev_prior, w->ev_topo})
     if (e) cudaEventDestroy(e);
+  cudaFree(w->env_cols);
+  cudaFree(w->env_verts);
+  cudaFree(w->env_state);
+  cudaFree(w->env_hits);
+  cudaFree(w->env_totals);
+  free_track_rings(w);
   cudaFree(w->msg_cnt);
   cudaFree(w->border_gen_list);
   cudaFree(w->border_gen_count);
@@ -2993,6 +3014,172 @@ int gbp_world_read_waypoint_index(gbp_world_t *w, int32_t *next_index) {
 }
 
 // Both prior updates run for every shard of the group living in this process.
+// ---- robot-environment collisions (planner/collisions.rs:368-455) --------------------------------------------
+int gbp_world_set_environment_colliders(gbp_world_t *w, int32_t n, const gbp_collider_t *colliders, int32_t num_vertices,
+                                        const float *vertices_xy) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (n < 0 || num_vertices < 0 || (n > 0 && !colliders) || (num_vertices > 0 && !vertices_xy))
+    return fail(GBP_ERR_BAD_ARGUMENT, "gbp_world_set_environment_colliders: bad argument");
+  std::vector<gbp::ColliderDev> h(size_t(std::max(n, 1)));
+  for (int k = 0; k < n; ++k) {
+    const gbp_collider_t &c = colliders[k];
+    if (c.kind < 0 || c.kind > 3) return fail(GBP_ERR_BAD_ARGUMENT, "collider kind out of range");
+    if (c.kind >= 2) {
+      if (c.num_vertices < 3 || c.first_vertex < 0 || int64_t(c.first_vertex) + c.num_vertices > num_vertices ||
+          (c.kind == 2 && c.num_vertices != 3))
+        return fail(GBP_ERR_BAD_ARGUMENT, "collider vertex range out of bounds");
+    }
+    // Isometry2::new(translation, angle): UnitComplex::new(angle) = (cos, sin) in f32
+    h[k] = {c.kind, c.translation[0], c.translation[1], std::cos(c.angle), std::sin(c.angle), c.radius,
+            c.half_extents[0], c.half_extents[1], c.first_vertex, c.num_vertices};
+  }
+  if (set_device(w)) return GBP_ERR_CUDA;
+  CK(cudaStreamSynchronize(w->stream));
+  cudaFree(w->env_cols);
+  cudaFree(w->env_verts);
+  cudaFree(w->env_state);
+  cudaFree(w->env_hits);
+  w->env_cols = nullptr;
+  w->env_verts = nullptr;
+  w->env_state = w->env_hits = nullptr;  // RobotEnvironmentCollisions::clear (a new environment was loaded)
+  w->env_robots = 0;
+  w->env_ncol = n;
+  w->env_words = (n + 31) / 32;
+  if (!w->env_totals) CK(dalloc(w->env_totals, 2));
+  CK(cudaMemsetAsync(w->env_totals, 0, 2 * sizeof(unsigned long long), w->stream));
+  if (n > 0) {
+    CK(dalloc(w->env_cols, size_t(n)));
+    CK(cudaMemcpy(w->env_cols, h.data(), size_t(n) * sizeof(gbp::ColliderDev), cudaMemcpyHostToDevice));
+  }
+  CK(dalloc(w->env_verts, size_t(2) * size_t(std::max(num_vertices, 1))));
+  if (num_vertices > 0)
+    CK(cudaMemcpy(w->env_verts, vertices_xy, size_t(2) * size_t(num_vertices) * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int gbp_world_update_environment_collisions(gbp_world_t *w, int64_t *num_collisions, int64_t *colliding_now) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (!w->env_totals) return fail(GBP_ERR_STATE, "gbp_world_update_environment_collisions: no colliders set");
+  if (set_device(w)) return GBP_ERR_CUDA;
+  const int32_t n = w->s.Nloc;
+  if (n > w->env_robots) {  // robots were added: their histories start Free
+    const int64_t cap = std::max<int64_t>(w->s.cap, n);
+    CK(regrow(w->env_state, 1, w->env_robots * w->env_words, cap * std::max(w->env_words, 1),
+              w->env_robots * w->env_words, w->stream));
+    CK(regrow(w->env_hits, 1, w->env_robots, cap, w->env_robots, w->stream));
+    w->env_robots = cap;
+  }
+  CK(cudaMemsetAsync(w->env_totals + 1, 0, sizeof(unsigned long long), w->stream));
+  if (n > 0 && w->env_ncol > 0) {
+    gbp::k_env_collisions<<<blocks_for(n, 128), 128, 0, w->stream>>>(n, w->s.pos, w->s.cap, w->s.radius, w->s.gone,
+                                                                     w->env_ncol, w->env_cols, w->env_verts, w->env_words,
+                                                                     w->env_state, w->env_hits, w->env_totals);
+    CK(cudaGetLastError());
+    w->launches += 1;
+  }
+  unsigned long long h[2] = {0, 0};
+  if (num_collisions || colliding_now) {
+    CK(cudaMemcpyAsync(h, w->env_totals, sizeof(h), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+  }
+  if (num_collisions) *num_collisions = int64_t(h[0]);
+  if (colliding_now) *colliding_now = int64_t(h[1]);
+  return 0;
+}
+
+int gbp_world_read_environment_collisions(gbp_world_t *w, uint32_t *per_robot) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (!per_robot) return fail(GBP_ERR_BAD_ARGUMENT, "null output");
+  if (set_device(w)) return GBP_ERR_CUDA;
+  const int64_t n = w->s.Nloc, have = std::min<int64_t>(n, w->env_robots);
+  std::fill(per_robot, per_robot + n, 0u);
+  if (have > 0 && w->env_hits) {
+    CK(cudaMemcpyAsync(per_robot, w->env_hits, size_t(have) * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+  }
+  return 0;
+}
+
+// ---- PositionTracker / VelocityTracker (planner/tracking.rs:117-260) ------------------------------------------
+namespace {
+void free_track_rings(gbp_world *w) {
+  gbp::TrackRings &t = w->trk;
+  void *ptrs[] = {t.elapsed_ns, t.npos, t.nvel, t.has_prev, t.prev_xy, t.prev_t, t.pos_xy, t.vel_xy, t.vel_t, t.vel_over};
+  for (void *q : ptrs) cudaFree(q);
+  t = gbp::TrackRings{};
+}
+}  // namespace
+
+int gbp_world_set_tracking_buffers(gbp_world_t *w, int32_t capacity, uint64_t sample_ns) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (capacity < 1) return fail(GBP_ERR_BAD_ARGUMENT, "gbp_world_set_tracking_buffers: capacity must be >= 1");
+  if (set_device(w)) return GBP_ERR_CUDA;
+  CK(cudaStreamSynchronize(w->stream));
+  free_track_rings(w);
+  w->trk.capacity = capacity;
+  w->trk_duration_ns = sample_ns;
+  w->trk_seen = 0;
+  return 0;
+}
+
+int gbp_world_track(gbp_world_t *w, uint64_t delta_ns, double elapsed_seconds) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (w->trk.capacity < 1) return fail(GBP_ERR_STATE, "gbp_world_track: gbp_world_set_tracking_buffers first");
+  if (set_device(w)) return GBP_ERR_CUDA;
+  gbp::TrackRings &t = w->trk;
+  const int32_t n = w->s.Nloc;
+  if (n > t.stride) {
+    const int64_t cap = std::max<int64_t>(w->s.cap, n), old = t.stride, keep = std::min<int64_t>(w->trk_seen, old);
+    cudaStream_t st = w->stream;
+    CK(regrow(t.elapsed_ns, 1, old, cap, keep, st));
+    CK(regrow(t.npos, 1, old, cap, keep, st));
+    CK(regrow(t.nvel, 1, old, cap, keep, st));
+    CK(regrow(t.has_prev, 1, old, cap, keep, st));
+    CK(regrow(t.prev_xy, 2, old, cap, keep, st));
+    CK(regrow(t.prev_t, 1, old, cap, keep, st));
+    CK(regrow(t.pos_xy, 2 * t.capacity, old, cap, keep, st));
+    CK(regrow(t.vel_xy, 2 * t.capacity, old, cap, keep, st));
+    CK(regrow(t.vel_t, t.capacity, old, cap, keep, st));
+    CK(regrow(t.vel_over, t.capacity, old, cap, keep, st));
+    t.stride = cap;
+  }
+  if (n > 0) {
+    gbp::k_track<<<blocks_for(n, 128), 128, 0, w->stream>>>(n, w->trk_seen, w->s.pos, w->s.cap, w->s.idle, w->s.gone, t,
+                                                            w->trk_duration_ns, delta_ns, elapsed_seconds);
+    CK(cudaGetLastError());
+    w->launches += 1;
+  }
+  w->trk_seen = n;
+  return 0;
+}
+
+int gbp_world_read_tracks(gbp_world_t *w, uint32_t *num_positions, float *positions_xy, uint32_t *num_velocities,
+                          float *velocities_xy, double *velocity_timestamp, double *velocity_measured_over) {
+  if (!w) return fail(GBP_ERR_BAD_HANDLE, "null world");
+  if (w->trk.capacity < 1) return fail(GBP_ERR_STATE, "gbp_world_read_tracks: gbp_world_set_tracking_buffers first");
+  if (set_device(w)) return GBP_ERR_CUDA;
+  const gbp::TrackRings &t = w->trk;
+  const int64_t n = std::min<int64_t>(w->s.Nloc, t.stride), C = t.capacity;
+  const int64_t nall = w->s.Nloc;
+  if (num_positions) std::fill(num_positions, num_positions + nall, 0u);
+  if (num_velocities) std::fill(num_velocities, num_velocities + nall, 0u);
+  if (n == 0) return 0;
+  cudaStream_t st = w->stream;
+  // device planes [k][r] -> caller rows [k][n] (slot-major, n robots per plane)
+  auto rows = [&](void *dst, const void *src, size_t elem, int64_t planes) {
+    return cudaMemcpy2DAsync(dst, size_t(nall) * elem, src, size_t(t.stride) * elem, size_t(n) * elem, size_t(planes),
+                             cudaMemcpyDeviceToHost, st);
+  };
+  if (num_positions) CK(rows(num_positions, t.npos, 4, 1));
+  if (num_velocities) CK(rows(num_velocities, t.nvel, 4, 1));
+  if (positions_xy) CK(rows(positions_xy, t.pos_xy, 4, 2 * C));
+  if (velocities_xy) CK(rows(velocities_xy, t.vel_xy, 4, 2 * C));
+  if (velocity_timestamp) CK(rows(velocity_timestamp, t.vel_t, 8, C));
+  if (velocity_measured_over) CK(rows(velocity_measured_over, t.vel_over, 8, C));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
 int gbp_world_update_prior_of_horizon_state(gbp_world_t *w0) {
   if (!w0) return fail(GBP_ERR_BAD_HANDLE, "null world");
   for (gbp_world *w : w0->grp->members) {

@@ -132,3 +132,91 @@ class Environment:
                           self.path_width, self.resolution, self.expansion, self.blur, len(self.obstacles),
                           C.cast(obs, C.POINTER(CObstacle)), pts.ctypes.data_as(C.POINTER(C.c_double)))
         return ce, (codes, obs, pts)
+
+
+class CCollider(C.Structure):
+    """include/gbp_b200.h gbp_collider_t"""
+    _fields_ = [("kind", C.c_int32), ("translation", C.c_float * 2), ("angle", C.c_float), ("radius", C.c_float),
+                ("half_extents", C.c_float * 2), ("first_vertex", C.c_int32), ("num_vertices", C.c_int32)]
+
+
+@dataclass
+class Collider:
+    """One entry of `gbp_global_planner::Colliders`: a parry2d shape in its own frame + Isometry2 (translation, angle).
+    kind: "ball" (radius), "cuboid" (half_extents), "triangle" / "convex-polygon" (points, counter-clockwise)."""
+    kind: str
+    translation: tuple = (0.0, 0.0)
+    angle: float = 0.0
+    radius: float = 0.0
+    half_extents: tuple = (0.0, 0.0)
+    points: tuple = ()
+
+
+COLLIDER_KINDS = {"ball": 0, "cuboid": 1, "triangle": 2, "convex-polygon": 3}
+
+
+def pack_colliders(colliders):
+    """(CCollider array, vertices (m, 2) f32, plain (n, 9) f32 rows for the oracle)"""
+    arr = (CCollider * max(1, len(colliders)))()
+    verts: list[tuple[float, float]] = []
+    rows = np.zeros((max(1, len(colliders)), 9), np.float32)
+    for k, c in enumerate(colliders):
+        kind = COLLIDER_KINDS[c.kind]
+        arr[k] = CCollider(kind, (C.c_float * 2)(*c.translation), c.angle, c.radius, (C.c_float * 2)(*c.half_extents),
+                           len(verts), len(c.points))
+        rows[k] = (kind, c.translation[0], c.translation[1], c.angle, c.radius, c.half_extents[0], c.half_extents[1],
+                   len(verts), len(c.points))
+        verts.extend(c.points)
+    return arr, np.ascontiguousarray(verts if verts else [(0.0, 0.0)], dtype=np.float32), rows
+
+
+# Tile -> cuboids of `build_tile_grid` (crates/magics/src/environment/map_generator.rs:537-1298): per tile character a
+# list of (x length, z length, x offset, z offset) in units of (T = tile_size, B = base_dim, P = pos_offset,
+# W = path_width * tile_size) — dims as ("T" | "B" | "T/2" | "W"), offsets as signed multiples of P or T/4.
+_TILE_CUBOIDS = {
+    "─": [("T", "B", 0, "-P"), ("T", "B", 0, "+P")],
+    "│": [("B", "T", "-P", 0), ("B", "T", "+P", 0)],
+    "╴": [("T", "B", 0, "-P"), ("T", "B", 0, "+P"), ("T/2", "W", "+Q", 0)],
+    "╶": [("T", "B", 0, "-P"), ("T", "B", 0, "+P"), ("T/2", "W", "-Q", 0)],
+    "╷": [("B", "T", "-P", 0), ("B", "T", "+P", 0), ("W", "T/2", 0, "+Q")],
+    "╵": [("B", "T", "-P", 0), ("B", "T", "+P", 0), ("W", "T/2", 0, "-Q")],
+    "┌": [("B", "B", "+P", "-P"), ("B", "T", "-P", 0), ("T", "B", 0, "+P")],
+    "┐": [("B", "B", "-P", "-P"), ("B", "T", "+P", 0), ("T", "B", 0, "+P")],
+    "└": [("B", "B", "+P", "+P"), ("B", "T", "-P", 0), ("T", "B", 0, "-P")],
+    "┘": [("B", "B", "-P", "+P"), ("B", "T", "+P", 0), ("T", "B", 0, "-P")],
+    "┬": [("B", "B", "-P", "-P"), ("B", "B", "+P", "-P"), ("T", "B", 0, "+P")],
+    "┴": [("B", "B", "-P", "+P"), ("B", "B", "+P", "+P"), ("T", "B", 0, "-P")],
+    "├": [("B", "B", "+P", "-P"), ("B", "B", "+P", "+P"), ("B", "T", "-P", 0)],
+    "┤": [("B", "B", "-P", "-P"), ("B", "B", "-P", "+P"), ("B", "T", "+P", 0)],
+    "┼": [("B", "B", "-P", "-P"), ("B", "B", "+P", "-P"), ("B", "B", "-P", "+P"), ("B", "B", "+P", "+P")],
+    " ": [("T", "T", 0, 0)],
+}
+_TILE_CUBOIDS["-"] = _TILE_CUBOIDS["─"]
+_TILE_CUBOIDS["|"] = _TILE_CUBOIDS["│"]
+
+
+def tile_colliders(env: "Environment") -> list:
+    """The cuboid colliders `build_tile_grid` pushes for the tile grid (map_generator.rs:537-1298), f32 arithmetic in
+    the reference's order.  A Bevy `Cuboid::new(x, h, z)` becomes a parry2d Cuboid through the fork's Bevy conversion
+    (not in the reference tree): half extents (x / 2, z / 2) are assumed."""
+    f = np.float32
+    T, pw = f(env.tile_size), f(env.path_width)
+    B = T * (f(1.0) - pw) / f(2.0)
+    P = (pw * T + B) / f(2.0)  # path_width.mul_add(tile_size, base_dim) / 2.0 (fused in the reference; equal here
+    #                             whenever path_width * tile_size is exact in f32)
+    dims = {"T": T, "B": B, "T/2": T / f(2.0), "W": pw * T}
+    offs = {0: f(0.0), "+P": P, "-P": -P, "+Q": T / f(4.0), "-Q": -(T / f(4.0))}
+    gx = f(env.ncols) / f(2.0) - f(0.5)
+    gz = -(f(env.nrows) / f(2.0) - f(0.5))
+    out = []
+    for y, row in enumerate(env.grid):
+        for x, ch in enumerate(row):
+            rules = _TILE_CUBOIDS.get(ch)
+            if not rules:
+                continue
+            ox = (f(x) - gx) * T
+            oz = (-f(y) - gz) * T
+            for dx, dz, sx, sz in rules:
+                out.append(Collider("cuboid", (float(ox + offs[sx]), float(oz + offs[sz])), 0.0,
+                                    half_extents=(float(dims[dx] / f(2.0)), float(dims[dz] / f(2.0)))))
+    return out

@@ -272,6 +272,52 @@ class World:
         self._call("gbp_world_read_robot_collisions", _p(out, C.c_uint32))
         return out
 
+    def set_environment_colliders(self, colliders):
+        """`Colliders` resource (environment.Collider list); clears the collision histories."""
+        from .environment import pack_colliders
+        arr, verts, _ = pack_colliders(colliders)
+        self._call("gbp_world_set_environment_colliders", C.c_int32(len(colliders)), C.cast(arr, C.c_void_p),
+                   C.c_int32(int(verts.shape[0]) if any(c.points for c in colliders) else 0), _p(verts, C.c_float))
+
+    def update_environment_collisions(self):
+        """update_robot_environment_collisions (planner/collisions.rs:368-431): (collisions so far, colliding now)."""
+        total, now = C.c_int64(0), C.c_int64(0)
+        self._call("gbp_world_update_environment_collisions", C.byref(total), C.byref(now))
+        return int(total.value), int(now.value)
+
+    def read_environment_collisions(self):
+        out = np.zeros(self.num_robots, np.uint32)
+        self._call("gbp_world_read_environment_collisions", _p(out, C.c_uint32))
+        return out
+
+    def set_tracking_buffers(self, capacity=10000, sample_ns=100_000_000):
+        """PositionTracker::new / VelocityTracker::new (spawner.rs:627-628)."""
+        self._track_capacity = int(capacity)
+        self._call("gbp_world_set_tracking_buffers", C.c_int32(capacity), C.c_uint64(sample_ns))
+
+    def track(self, delta_ns: int, elapsed_seconds: float):
+        """track_positions + track_velocities for one FixedUpdate (planner/tracking.rs:117-137, 226-260)."""
+        self._call("gbp_world_track", C.c_uint64(delta_ns), C.c_double(elapsed_seconds))
+
+    def read_tracks(self):
+        """Per robot, oldest sample first: (positions (k, 2) f32, velocities (m, 2) f32, timestamps (m,), measured_over
+        (m,)) — `PositionTracker::positions()` and `VelocityTracker::measurements()`."""
+        n, cap = self.num_robots, self._track_capacity
+        npos, nvel = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        pos = np.zeros((cap, 2, n), np.float32)
+        vel = np.zeros((cap, 2, n), np.float32)
+        vt, vo = np.zeros((cap, n), np.float64), np.zeros((cap, n), np.float64)
+        self._call("gbp_world_read_tracks", _p(npos, C.c_uint32), _p(pos, C.c_float), _p(nvel, C.c_uint32),
+                   _p(vel, C.c_float), _p(vt, C.c_double), _p(vo, C.c_double))
+        out = []
+        for r in range(n):
+            def order(k):
+                k = int(k)
+                return np.arange(k) if k <= cap else (np.arange(cap) + k) % cap
+            ip, iv = order(npos[r]), order(nvel[r])
+            out.append((pos[ip, :, r], vel[iv, :, r], vt[iv, r], vo[iv, r]))
+        return out
+
     def update_prior_of_horizon_state(self):
         self._call("gbp_world_update_prior_of_horizon_state")
 
@@ -407,10 +453,19 @@ class World:
     def export_totals(self) -> dict:
         """The per-robot totals `export.rs` writes (RobotData, export.rs:112-277) as far as the engine keeps them:
         radius, collisions.robots (planner/collisions.rs RobotRobotCollisions::get), messages sent / received
-        (internal, external) when the counters are on, the mission's next waypoint index.  collisions.environment and
-        the position / velocity histories are not kept by the engine."""
+        (internal, external) when the counters are on, the mission's next waypoint index, collisions.environment
+        (RobotEnvironmentCollisions::get) once colliders are set and the position / velocity histories once
+        `set_tracking_buffers` has been called.  `magics_b200.export.export_data` shapes them like the reference's JSON."""
         out = {"collisions_robots": self.read_robot_collisions(), "next_waypoint": self.read_waypoint_index(),
                "removed": self.read_removed().astype(bool)}
+        try:
+            out["collisions_environment"] = self.read_environment_collisions()
+        except RuntimeError:
+            out["collisions_environment"] = None
+        try:
+            out["tracks"] = self.read_tracks()
+        except (RuntimeError, AttributeError):
+            out["tracks"] = None
         try:
             c = self.read_message_counts()
             out["messages"] = {"sent": {"internal": c[:, 0], "external": c[:, 1]},

@@ -36,6 +36,7 @@
 // Build: g++ -O3 -std=c++17 -ffp-contract=off -pthread -shared -fPIC (see Makefile).
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -715,6 +716,127 @@ struct Robot {
   int next_wp = 1;
 };
 
+// ---- parry2d 0.13.7 (un-vendored git dependency, Cargo.lock:5372-5374), restated for the one call the path makes:
+// query::intersection_test(&collider.isometry, collider.shape, &robot_pos, ball) (planner/collisions.rs:402-408).
+// f32 throughout; this file is built with -ffp-contract=off like rustc (no fused multiply-add).
+struct V2 {
+  float x, y;
+};
+inline V2 operator-(V2 a, V2 b) { return {a.x - b.x, a.y - b.y}; }
+inline V2 operator+(V2 a, V2 b) { return {a.x + b.x, a.y + b.y}; }
+inline V2 operator*(V2 a, float t) { return {a.x * t, a.y * t}; }
+inline float dot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
+inline float perp(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }  // nalgebra Vector2::perp
+inline float norm_squared(V2 a) { return dot(a, a); }
+struct PointProjection {
+  bool is_inside;
+  V2 point;
+};
+struct EnvCollider {
+  int kind;  // 0 Ball, 1 Cuboid, 2 Triangle, 3 ConvexPolygon
+  V2 translation;
+  float re, im;  // UnitComplex::new(angle)
+  float radius;
+  V2 half_extents;
+  std::vector<V2> points;
+};
+// Aabb::project_local_point (bounding_volume/aabb_utils / query/point/point_aabb.rs), solid = true
+inline PointProjection project_cuboid(V2 he, V2 pt) {
+  const V2 mins{-he.x, -he.y}, maxs = he;
+  const V2 mins_pt = mins - pt, pt_maxs = pt - maxs;
+  const V2 shift{std::max(mins_pt.x, 0.0f) - std::max(pt_maxs.x, 0.0f), std::max(mins_pt.y, 0.0f) - std::max(pt_maxs.y, 0.0f)};
+  const bool inside = shift.x == 0.0f && shift.y == 0.0f;
+  if (!inside) return {false, pt + shift};
+  return {true, pt};
+}
+// Triangle::project_local_point_and_get_location (query/point/point_triangle.rs), 2-D
+inline PointProjection project_triangle(V2 a, V2 b, V2 c, V2 pt) {
+  const V2 ab = b - a, ac = c - a, ap = pt - a;
+  const float ab_ap = dot(ab, ap), ac_ap = dot(ac, ap);
+  if (ab_ap <= 0.0f && ac_ap <= 0.0f) return {false, a};
+  const V2 bp = pt - b;
+  const float ab_bp = dot(ab, bp), ac_bp = dot(ac, bp);
+  if (ab_bp >= 0.0f && ac_bp <= ab_bp) return {false, b};
+  const V2 cp = pt - c;
+  const float ab_cp = dot(ab, cp), ac_cp = dot(ac, cp);
+  if (ac_cp >= 0.0f && ab_cp <= ac_cp) return {false, c};
+  // stable_check_edges_voronoi, DIM == 2
+  const float n = perp(ab, ac);
+  const float vc = n * perp(ab, ap);
+  if (vc < 0.0f && ab_ap >= 0.0f && ab_bp <= 0.0f) {
+    const float v = ab_ap / norm_squared(ab);
+    return {false, a + ab * v};
+  }
+  const float vb = -n * perp(ac, cp);
+  if (vb < 0.0f && ac_ap >= 0.0f && ac_cp <= 0.0f) {
+    const float w = ac_ap / norm_squared(ac);
+    return {false, a + ac * w};
+  }
+  const V2 bc = c - b;
+  const float va = n * perp(bc, bp);
+  if (va < 0.0f && ac_bp - ab_bp >= 0.0f && ab_cp - ac_cp >= 0.0f) {
+    const float w = dot(bc, bp) / norm_squared(bc);
+    return {false, b + bc * w};
+  }
+  return {true, pt};  // on the face: inside in two dimensions
+}
+// ConvexPolygon: parry projects through GJK on the support map (query/point/point_support_map.rs); restated as the
+// predicate GJK converges to — inside every edge of the counter-clockwise hull, else the nearest point of an edge.
+inline PointProjection project_convex_polygon(const std::vector<V2> &pts, V2 pt) {
+  bool inside = pts.size() >= 3;
+  float best = 3.4e38f;
+  V2 bestp = pt;
+  for (size_t k = 0; k < pts.size(); ++k) {
+    const V2 a = pts[k], b = pts[k + 1 == pts.size() ? 0 : k + 1];
+    const V2 e = b - a, w = pt - a;
+    inside = inside && perp(e, w) >= 0.0f;
+    const float ee = dot(e, e);
+    float t = ee > 0.0f ? dot(w, e) / ee : 0.0f;
+    t = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t);
+    const V2 q = a + e * t;
+    const float d2 = norm_squared(pt - q);
+    if (d2 < best) {
+      best = d2;
+      bestp = q;
+    }
+  }
+  if (inside) return {true, pt};
+  return {false, bestp};
+}
+// query::intersection_test -> DefaultQueryDispatcher::intersection_test (query/default_query_dispatcher.rs):
+// Ball / Ball -> intersection_test_ball_ball, otherwise shape2 is the Ball -> intersection_test_point_query_ball.
+inline bool intersection_test(const EnvCollider &c, V2 robot, float ball_radius) {
+  // pos12 = pos1.inv_mul(&pos2): translation = rotation1.inverse() * (t2 - t1)  (nalgebra Isometry::inv_mul)
+  const V2 tr = robot - c.translation;
+  const float r = c.re, i = -c.im;  // UnitComplex::inverse = conjugate
+  const V2 local{r * tr.x - i * tr.y, i * tr.x + r * tr.y};
+  if (c.kind == 0) {
+    const float sum_radius = c.radius + ball_radius;
+    return norm_squared(local) <= sum_radius * sum_radius;
+  }
+  PointProjection proj;
+  if (c.kind == 1) proj = project_cuboid(c.half_extents, local);
+  else if (c.kind == 2) proj = project_triangle(c.points[0], c.points[1], c.points[2], local);
+  else proj = project_convex_polygon(c.points, local);
+  return proj.is_inside || norm_squared(local - proj.point) <= ball_radius * ball_radius;
+}
+
+// PositionTracker + VelocityTracker of one robot (planner/tracking.rs:36-200); both Timers are created together with
+// the same duration and tick on the same frames, so one stopwatch serves both.
+struct Tracker {
+  uint64_t elapsed_ns = 0;
+  std::vector<std::array<float, 2>> positions;  // HeapRb contents, oldest first
+  struct Vel {
+    float v[2];
+    double timestamp, measured_over;
+  };
+  std::vector<Vel> velocities;
+  uint64_t npos = 0, nvel = 0;
+  bool has_prev = false;
+  float prev[2] = {0, 0};
+  double prev_t = 0;
+};
+
 struct World {
   // RobotRobotCollisions (planner/collisions.rs:146-200): state per unordered pair, total Hit count
   std::map<std::pair<int, int>, bool> coll_state;
@@ -726,6 +848,16 @@ struct World {
   std::vector<Robot> robots;
   uint64_t robot_number = 1;  // RobotNumberGenerator (robot.rs:121-144)
   int threads = 1;
+  // Colliders resource + RobotEnvironmentCollisions (planner/collisions.rs:202-330)
+  std::vector<EnvCollider> colliders;
+  std::map<std::pair<int, int>, bool> env_state;  // (robot, collider) -> CollisionState::Colliding
+  std::vector<uint32_t> env_hits;
+  int64_t env_collisions = 0;
+  // PositionTracker / VelocityTracker per robot (planner/tracking.rs:36-200)
+  int track_capacity = 0;
+  uint64_t track_duration_ns = 0;
+  std::vector<Tracker> trackers;
+  size_t track_seen = 0;
 };
 
 // FactorGraph::add_internal_edge (factorgraph.rs:304-330).
@@ -1870,6 +2002,123 @@ int gbpo_read_tracking(void *p, int robot, int var, int64_t *record, float *pos,
     return 1;
   }
   return 0;
+}
+
+// Colliders resource; clears RobotEnvironmentCollisions (collisions.rs:40-46).  cols: [n][9] floats
+// (kind, tx, ty, angle, radius, hx, hy, first_vertex, num_vertices).
+int gbpo_set_environment_colliders(void *p, int n, const float *cols, int nverts, const float *verts) {
+  World *w = static_cast<World *>(p);
+  w->colliders.clear();
+  w->env_state.clear();
+  w->env_hits.clear();
+  w->env_collisions = 0;
+  for (int k = 0; k < n; ++k) {
+    const float *c = cols + 9 * k;
+    EnvCollider e;
+    e.kind = int(c[0]);
+    e.translation = {c[1], c[2]};
+    e.re = std::cos(c[3]);  // UnitComplex::new(angle): f32 sin_cos
+    e.im = std::sin(c[3]);
+    e.radius = c[4];
+    e.half_extents = {c[5], c[6]};
+    const int v0 = int(c[7]), nv = int(c[8]);
+    if (e.kind >= 2 && (v0 < 0 || nv < 3 || v0 + nv > nverts)) return -2;
+    for (int q = 0; q < (e.kind >= 2 ? nv : 0); ++q) e.points.push_back({verts[2 * (v0 + q)], verts[2 * (v0 + q) + 1]});
+    w->colliders.push_back(e);
+  }
+  return 0;
+}
+// update_robot_environment_collisions (planner/collisions.rs:368-431): every living robot against every collider.
+int gbpo_update_environment_collisions(void *p, int64_t *num_collisions, int64_t *colliding_now, uint32_t *per_robot) {
+  World *w = static_cast<World *>(p);
+  const int n = int(w->robots.size());
+  w->env_hits.resize(size_t(n), 0u);
+  int64_t now_count = 0;
+  for (int r = 0; r < n; ++r) {
+    const Robot &rb = w->robots[r];
+    if (rb.gone) continue;
+    for (int c = 0; c < int(w->colliders.size()); ++c) {
+      const bool now = intersection_test(w->colliders[c], {rb.pos[0], rb.pos[1]}, rb.radius);
+      bool &state = w->env_state[{r, c}];
+      if (now && !state) {  // CollisionStatus::Hit
+        w->env_collisions += 1;
+        w->env_hits[r] += 1;
+      }
+      state = now;
+      if (now) ++now_count;
+    }
+  }
+  if (num_collisions) *num_collisions = w->env_collisions;
+  if (colliding_now) *colliding_now = now_count;
+  if (per_robot)
+    for (int r = 0; r < n; ++r) per_robot[r] = w->env_hits[r];
+  return 0;
+}
+int gbpo_set_tracking_buffers(void *p, int capacity, uint64_t sample_ns) {
+  World *w = static_cast<World *>(p);
+  if (capacity < 1) return -2;
+  w->track_capacity = capacity;
+  w->track_duration_ns = sample_ns;
+  w->trackers.clear();
+  w->track_seen = 0;
+  return 0;
+}
+// track_positions + track_velocities (planner/tracking.rs:117-137, 226-260) for one FixedUpdate.
+int gbpo_track(void *p, uint64_t delta_ns, double now) {
+  World *w = static_cast<World *>(p);
+  if (w->track_capacity < 1) return -5;
+  w->trackers.resize(w->robots.size());
+  const size_t cap = size_t(w->track_capacity);
+  for (size_t r = 0; r < w->robots.size(); ++r) {
+    const Robot &rb = w->robots[r];
+    if (rb.gone) continue;
+    if (rb.idle && r < w->track_seen) continue;  // Changed<Transform>: update_prior_of_current_state skipped it
+    Tracker &t = w->trackers[r];
+    // bevy_time Timer::tick, TimerMode::Repeating
+    t.elapsed_ns += delta_ns;
+    const bool finished = t.elapsed_ns >= w->track_duration_ns;
+    if (finished) t.elapsed_ns = w->track_duration_ns ? t.elapsed_ns % w->track_duration_ns : 0;
+    if (!finished) continue;
+    if (t.positions.size() == cap) t.positions.erase(t.positions.begin());  // push_overwrite
+    t.positions.push_back({rb.pos[0], rb.pos[1]});
+    t.npos += 1;
+    if (t.has_prev) {
+      const double dt = now - t.prev_t;
+      Tracker::Vel v;
+      v.v[0] = (rb.pos[0] - t.prev[0]) / float(dt);
+      v.v[1] = (rb.pos[1] - t.prev[1]) / float(dt);
+      v.timestamp = now;
+      v.measured_over = dt;
+      if (t.velocities.size() == cap) t.velocities.erase(t.velocities.begin());
+      t.velocities.push_back(v);
+      t.nvel += 1;
+    }
+    t.prev[0] = rb.pos[0];
+    t.prev[1] = rb.pos[1];
+    t.prev_t = now;
+    t.has_prev = true;
+  }
+  w->track_seen = w->robots.size();
+  return 0;
+}
+// Ring contents of one robot, oldest first; returns the number of position samples, *nvel the velocity samples.
+int gbpo_read_track(void *p, int robot, float *pos_xy, int *nvel, float *vel_xy, double *vel_t, double *vel_over) {
+  World *w = static_cast<World *>(p);
+  *nvel = 0;
+  if (size_t(robot) >= w->trackers.size()) return 0;
+  const Tracker &t = w->trackers[robot];
+  for (size_t k = 0; k < t.positions.size(); ++k) {
+    pos_xy[2 * k] = t.positions[k][0];
+    pos_xy[2 * k + 1] = t.positions[k][1];
+  }
+  for (size_t k = 0; k < t.velocities.size(); ++k) {
+    vel_xy[2 * k] = t.velocities[k].v[0];
+    vel_xy[2 * k + 1] = t.velocities[k].v[1];
+    vel_t[k] = t.velocities[k].timestamp;
+    vel_over[k] = t.velocities[k].measured_over;
+  }
+  *nvel = int(t.velocities.size());
+  return int(t.positions.size());
 }
 
 }  // extern "C"

@@ -192,6 +192,39 @@ class OracleWorld:
         robots = np.ascontiguousarray(robots, np.int32)
         self._call("gbpo_remove_robots", int(robots.shape[0]), _p(robots, C.c_int32))
 
+    def set_environment_colliders(self, colliders):
+        from magics_b200.environment import pack_colliders  # plain data packing, no engine involved
+        _, verts, rows = pack_colliders(colliders)
+        self._call("gbpo_set_environment_colliders", len(colliders), _p(rows, C.c_float), int(verts.shape[0]),
+                   _p(verts, C.c_float))
+
+    def update_environment_collisions(self):
+        total, now = C.c_int64(0), C.c_int64(0)
+        self._env_hits = np.zeros(self.num_robots, np.uint32)
+        self._call("gbpo_update_environment_collisions", C.byref(total), C.byref(now), _p(self._env_hits, C.c_uint32))
+        return int(total.value), int(now.value)
+
+    def read_environment_collisions(self):
+        return self._env_hits
+
+    def set_tracking_buffers(self, capacity=10000, sample_ns=100_000_000):
+        self._track_capacity = int(capacity)
+        self._call("gbpo_set_tracking_buffers", int(capacity), C.c_uint64(sample_ns))
+
+    def track(self, delta_ns: int, elapsed_seconds: float):
+        self._call("gbpo_track", C.c_uint64(delta_ns), C.c_double(elapsed_seconds))
+
+    def read_tracks(self):
+        cap, out = self._track_capacity, []
+        for r in range(self.num_robots):
+            pos, vel = np.zeros((cap, 2), np.float32), np.zeros((cap, 2), np.float32)
+            vt, vo = np.zeros(cap, np.float64), np.zeros(cap, np.float64)
+            nv = C.c_int(0)
+            k = self._call("gbpo_read_track", r, _p(pos, C.c_float), C.byref(nv), _p(vel, C.c_float), _p(vt, C.c_double),
+                           _p(vo, C.c_double))
+            out.append((pos[:k], vel[:nv.value], vt[:nv.value], vo[:nv.value]))
+        return out
+
     def set_waypoint_index(self, idx):
         idx = np.ascontiguousarray(idx, np.int32)
         self._call("gbpo_set_waypoint_index", _p(idx, C.c_int32))

@@ -1,0 +1,148 @@
+"""SURVEY §8 next-3, CPU side: the oracle's restatement of the robot-environment collision test
+(planner/collisions.rs:368-455 + parry2d's intersection_test), of the tile colliders
+(environment/map_generator.rs:537-1298) and of the position / velocity trackers (planner/tracking.rs:117-260),
+checked against independent float64 geometry, against the SDF rasteriser's tile rules (a different reference
+source for the same walls) and against hand-computed timer sequences."""
+import ctypes as C
+
+import numpy as np
+
+from magics_b200 import GbpConfig, scenarios
+from magics_b200.environment import Collider, Environment, tile_colliders
+from oracle import oracle as O
+from oracle.oracle import OracleWorld
+
+
+def _world_with_robots_at(points, radius):
+    """An oracle world whose robots sit at `points` (no tick is ever run: only Transform and Ball are read)."""
+    sw = scenarios.circle(len(points), 10.0, robot_radius=radius)
+    sw.positions[:] = np.asarray(points, np.float32)
+    w = OracleWorld(sw.cfg)
+    sw.add_to(w)
+    return w
+
+
+def _dist_to_polygon(p, poly):
+    """float64: (inside, distance to the boundary) of a counter-clockwise convex polygon."""
+    p, poly = np.asarray(p, np.float64), np.asarray(poly, np.float64)
+    inside, best = True, np.inf
+    for k in range(len(poly)):
+        a, b = poly[k], poly[(k + 1) % len(poly)]
+        e, w = b - a, p - a
+        inside &= e[0] * w[1] - e[1] * w[0] >= 0
+        t = np.clip(np.dot(w, e) / np.dot(e, e), 0.0, 1.0)
+        best = min(best, np.linalg.norm(p - (a + t * e)))
+    return inside, best
+
+
+def test_intersection_test_agrees_with_float64_geometry_for_every_shape_kind():
+    rng = np.random.default_rng(7)
+    ang = 0.7
+    rot = np.array([[np.cos(ang), -np.sin(ang)], [np.sin(ang), np.cos(ang)]])
+    tri = [(-1.0, -0.5), (2.0, -0.5), (0.3, 1.7)]
+    hexagon = [(1.5 * np.cos(k * np.pi / 3), 1.5 * np.sin(k * np.pi / 3)) for k in range(6)]
+    box = [(-2.0, -0.5), (2.0, -0.5), (2.0, 0.5), (-2.0, 0.5)]
+    cols = [Collider("ball", (3.0, -2.0), 0.0, radius=1.25),
+            Collider("cuboid", (-4.0, 1.0), ang, half_extents=(2.0, 0.5)),
+            Collider("triangle", (0.5, 5.0), ang, points=tuple(tri)),
+            Collider("convex-polygon", (6.0, 6.0), -ang, points=tuple(hexagon))]
+    pts = rng.uniform(-9, 11, size=(4000, 2))
+    R = 0.6
+    w = _world_with_robots_at(pts, R)
+    per_collider = []
+    for c in cols:  # one collider at a time, so that the per-robot count is the boolean itself
+        w.set_environment_colliders([c])
+        w.update_environment_collisions()
+        per_collider.append(w.read_environment_collisions().copy())
+    pts32 = pts.astype(np.float32).astype(np.float64)
+    checked = 0
+    for c, got in zip(cols, per_collider):
+        a = c.angle
+        Rm = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+        local = (pts32 - np.asarray(c.translation)) @ Rm  # R^-1 (p - t) as row vectors
+        for k, p in enumerate(local):
+            if c.kind == "ball":
+                inside, d = False, np.linalg.norm(p) - c.radius
+            else:
+                poly = box if c.kind == "cuboid" else c.points
+                inside, d = _dist_to_polygon(p, poly)
+            if not inside and abs(d - R) < 1e-4:
+                continue  # on the rim: f32 rounding decides
+            checked += 1
+            assert bool(got[k]) == (inside or d <= R), (c.kind, k, p, d)
+    assert checked > 15000 and all(g.sum() > 20 for g in per_collider)
+    assert rot.shape == (2, 2)
+
+
+def test_collision_history_counts_entries_not_ticks():
+    w = _world_with_robots_at([(0.0, 0.0), (10.0, 0.0)], 1.0)
+    w.set_environment_colliders([Collider("cuboid", (0.0, 0.0), 0.0, half_extents=(1.0, 1.0)),
+                                 Collider("ball", (10.5, 0.0), 0.0, radius=0.2)])
+    assert w.update_environment_collisions() == (2, 2)  # Free -> Colliding: Hit
+    assert w.update_environment_collisions() == (2, 2)  # Colliding -> Colliding
+    assert list(w.read_environment_collisions()) == [1, 1]
+    w.set_environment_colliders([Collider("ball", (40.0, 0.0), 0.0, radius=0.2)])  # a reload clears the history
+    assert w.update_environment_collisions() == (0, 0)
+    w.remove_robots([0])
+    w.set_environment_colliders([Collider("ball", (0.0, 0.0), 0.0, radius=5.0)])
+    assert w.update_environment_collisions() == (0, 0)  # a despawned robot is not in the query; robot 1 is 10 m away
+
+
+def test_tile_colliders_cover_exactly_what_the_sdf_tile_rules_call_obstacle():
+    """map_generator's cuboids and env_to_png's `is_tile_obstacle` describe the same walls from two different
+    reference sources; sampled away from the wall faces they must agree for every tile kind."""
+    L = O.lib()
+    tiles = "─│╴╶╷╵┌┐└┘┬┴├┤┼ "
+    env = Environment(grid=[tiles[:8], tiles[8:]], tile_size=10.0, path_width=0.4)
+    cols = tile_colliders(env)
+    rng = np.random.default_rng(3)
+    T = 10.0
+    n_checked = 0
+    for row in range(env.nrows):
+        for col in range(env.ncols):
+            u = rng.uniform(0.02, 0.98, size=(300, 2))  # percentage within the tile, v measured from the top
+            cx, cz = (col - (env.ncols / 2 - 0.5)) * T, ((env.nrows / 2 - 0.5) - row) * T
+            for px, py in u:
+                x, z = cx + (px - 0.5) * T, cz + (0.5 - py) * T
+                # distance to the nearest wall face decides whether the sample is safely inside or outside
+                hit, margin = False, np.inf
+                for c in cols:
+                    dx, dz = abs(x - c.translation[0]) - c.half_extents[0], abs(z - c.translation[1]) - c.half_extents[1]
+                    hit |= dx <= 0 and dz <= 0
+                    margin = min(margin, abs(max(dx, dz)))
+                if margin < 0.05:
+                    continue
+                want = bool(L.gbpo_is_tile_obstacle(ord(env.grid[row][col]), C.c_float(env.path_width), C.c_float(px),
+                                                    C.c_float(py), C.c_float(0.0)))
+                assert hit == want, (env.grid[row][col], px, py)
+                n_checked += 1
+    assert n_checked > 3000
+
+
+def test_trackers_fire_on_the_timer_and_overwrite_the_oldest_sample():
+    sw = scenarios.circle(3, 10.0)
+    w = OracleWorld(sw.cfg)
+    sw.add_to(w)
+    w.set_tracking_buffers(capacity=4, sample_ns=100_000_000)
+    dt_ns = 30_000_000  # 30 ms per FixedUpdate: the timer fires on ticks 4, 7, 10, 14, ... (elapsed % 100 ms carries)
+    fired, elapsed = [], 0
+    for tick in range(1, 41):
+        w.step()
+        if tick == 20:
+            w.set_comms(idle=np.array([0, 1, 0], np.uint8))  # robot 1 stops: its Transform no longer changes
+        w.track(dt_ns, tick * 0.03)
+        elapsed += dt_ns
+        if elapsed >= 100_000_000:
+            elapsed %= 100_000_000
+            fired.append(tick)
+    tr = w.read_tracks()
+    assert len(tr[0][0]) == 4 and len(tr[0][1]) == 4  # capacity
+    n_before_idle = sum(1 for t in fired if t < 20)
+    assert len(tr[1][0]) == min(4, n_before_idle)
+    # velocity = (p_k - p_{k-1}) / dt in f32, timestamps are the tick times of the last four firings
+    pos, vel, vt, vo = tr[0]
+    assert np.allclose(vt, [t * 0.03 for t in fired[-4:]])
+    for k in range(1, 4):
+        want = (pos[k] - pos[k - 1]) / np.float32(vo[k])
+        assert np.array_equal(vel[k], want.astype(np.float32))
+    assert np.allclose(vo, np.diff([t * 0.03 for t in fired[-5:]]))
