@@ -1017,6 +1017,7 @@ struct gbp_world {
   bool t0_seen = false, t0_uniform = true;
   float t0_first = 0.0f;
   int sm_count = 148;
+  int iter_occ[4] = {0, 0, 0, 0};  // resident CTAs per SM of k_iterate<EXT, INT>, by (EXT ? 2 : 0) + (INT ? 1 : 0)
   int par = 0;                // launch parity: which Store::gen_count the current launch appends to
   unsigned long long *coll_totals = nullptr;              // [0] Hit events so far, [1] pairs colliding now
   // robot-environment collisions (gbp_collide.cuh): the Colliders resource, CollisionHistory bits per (robot, collider)
@@ -1393,7 +1394,15 @@ int launch_iterate(gbp_world *w, int part) {
       }
       CK(cudaGetLastError());
       const int64_t warps = (nrob + rpw - 1) / rpw;
-      const unsigned grid = unsigned(std::min<int64_t>((warps + wpb - 1) / wpb, int64_t(w->sm_count) * 4));
+      // a persistent grid of exactly the CTAs that fit at once: the kernel walks the hand-over list with a grid
+      // stride, so a grid of 4 CTAs per SM at 3 resident ran a second, one-third-full wave (r02y: SMs busy 75 %)
+      int &occ = w->iter_occ[which];
+      if (occ <= 0) {
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gbp::k_iterate<EXT, INT>, gbp::kIterBlock, 0));
+        if (occ <= 0) occ = 1;
+        if (const char *e = std::getenv("GBP_ITER_GRID_PER_SM")) occ = std::max(1, atoi(e));
+      }
+      const unsigned grid = unsigned(std::min<int64_t>((warps + wpb - 1) / wpb, int64_t(w->sm_count) * occ));
       ProfileScope pg(w, GBP_PROFILE_ITERATE_GENERAL, st);
       CK(launch_pdl(w->use_pdl, gbp::k_iterate<EXT, INT>, grid, unsigned(gbp::kIterBlock), size_t(0), st, s, w->p,
                     w->epoch, *par));

@@ -94,7 +94,14 @@ GBP_DEV void divide_all(const double (&c)[N], double det, double (&o)[N]) {
 }
 
 // `Inverse::inv`, general 4x4: 16 cofactors by explicit expansion, det by Laplace along row 0.
-GBP_DEV bool inv4_general(const double (&m)[16], double (&o)[16]) {
+// -DGBP_INV4_GENERAL_NOINLINE: one out-of-line copy instead of one per call site (k_iterate<1,1> is 165 kB of SASS
+// and misses the instruction cache 30 % of the time in the dense regime: profiles/r02y).
+#ifdef GBP_INV4_GENERAL_NOINLINE
+#define GBP_INV4G_DEV GBP_NOINLINE_DEV
+#else
+#define GBP_INV4G_DEV GBP_DEV
+#endif
+GBP_INV4G_DEV bool inv4_general(const double (&m)[16], double (&o)[16]) {
   double c[16];
   c[0] = minor3<0, 0>(m);
   c[4] = -minor3<0, 1>(m);

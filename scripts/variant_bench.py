@@ -20,7 +20,7 @@ from magics_b200 import World, gbp_schedule, scenarios  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="lattice", choices=["lattice", "rings"])
+    ap.add_argument("--workload", default="lattice", choices=["lattice", "rings", "dense"])
     ap.add_argument("--robots", type=int, default=None)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
@@ -46,6 +46,9 @@ def main():
         n = a.robots or 1_000_000
         side = int(round(n ** 0.5))
         sw = scenarios.lattice(side, side)
+    elif a.workload == "dense":
+        side = int(round((a.robots or 250_000) ** 0.5))
+        sw = scenarios.dense_lattice(side, side)
     else:
         sw = scenarios.rings(a.robots or 100_000)
     g = World(sw.cfg, device=0)

@@ -114,8 +114,9 @@ def test_trackers_match_sample_for_sample():
 
 def test_export_data_has_the_reference_shape():
     sw = scenarios.circle(5, 8.0)
-    g, o = _both(sw)
-    g.set_message_counting(True)
+    g = World(sw.cfg)
+    g.set_message_counting(True)  # before the first robot: the reference counts from the creation of the graph on
+    sw.add_to(g)
     g.set_tracking_buffers(capacity=8, sample_ns=50_000_000)
     g.set_environment_colliders([Collider("ball", (0.0, 0.0), 0.0, radius=1.0)])
     for tick in range(1, 31):
