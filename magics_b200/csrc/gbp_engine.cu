@@ -950,6 +950,7 @@ struct gbp_world {
     uint64_t *e_rnum = nullptr;
     uint32_t *e_birth = nullptr;
     uint8_t *e_frozen = nullptr;
+    uint8_t *e_act = nullptr;  // scratch of one sub-step (k_edge_messages -> k_iterate)
     double *mir = nullptr;
     double *mu_frozen = nullptr;
     int64_t *map = nullptr;
@@ -1017,6 +1018,7 @@ struct gbp_world {
   bool t0_seen = false, t0_uniform = true;
   float t0_first = 0.0f;
   int sm_count = 148;
+  int edge_occ = 0;                // resident CTAs per SM of k_edge_messages
   int iter_occ[4] = {0, 0, 0, 0};  // resident CTAs per SM of k_iterate<EXT, INT>, by (EXT ? 2 : 0) + (INT ? 1 : 0)
   int par = 0;                // launch parity: which Store::gen_count the current launch appends to
   unsigned long long *coll_totals = nullptr;              // [0] Hit events so far, [1] pairs colliding now
@@ -1370,6 +1372,13 @@ int launch_iterate(gbp_world *w, int part) {
     const int64_t warps = (int64_t(s.Nloc) + rpw - 1) / rpw;
     const unsigned grid = unsigned((warps + wpb - 1) / wpb);
     ProfileScope ps(w, kind);
+#if GBP_EDGE_SPLIT
+    if (EXT && s.E > 0) {  // the neighbours' InterRobot factors first, one thread per (edge, variable)
+      const unsigned eg = unsigned(std::min<int64_t>((int64_t(s.Nloc) + 3) / 4, int64_t(w->sm_count) * 16));
+      gbp::k_edge_messages<<<eg, gbp::kEdgeBlock, 0, st>>>(s, w->p, -1);
+      w->launches += 1;
+    }
+#endif
     gbp::k_iterate<EXT, INT><<<grid, gbp::kIterBlock, 0, st>>>(s, w->p, w->epoch, -1);
     w->launches += 1;
   } else {
@@ -1404,6 +1413,19 @@ int launch_iterate(gbp_world *w, int part) {
       }
       const unsigned grid = unsigned(std::min<int64_t>((warps + wpb - 1) / wpb, int64_t(w->sm_count) * occ));
       ProfileScope pg(w, GBP_PROFILE_ITERATE_GENERAL, st);
+#if GBP_EDGE_SPLIT
+      if (EXT && s.E > 0) {
+        // InterRobot factors of the handed-over robots first, one thread per (edge, variable); a warp per robot, a
+        // persistent grid (the list's length is only known on the device)
+        if (w->edge_occ <= 0) {
+          CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w->edge_occ, gbp::k_edge_messages, gbp::kEdgeBlock, 0));
+          if (w->edge_occ <= 0) w->edge_occ = 1;
+        }
+        const unsigned eg = unsigned(std::min<int64_t>((nrob + 3) / 4, int64_t(w->sm_count) * w->edge_occ));
+        gbp::k_edge_messages<<<eg, gbp::kEdgeBlock, 0, st>>>(s, w->p, *par);
+        w->launches += 1;
+      }
+#endif
       CK(launch_pdl(w->use_pdl, gbp::k_iterate<EXT, INT>, grid, unsigned(gbp::kIterBlock), size_t(0), st, s, w->p,
                     w->epoch, *par));
       *par ^= 1;
@@ -1521,6 +1543,7 @@ void bind_edge_set(gbp_world *w) {
   s.e_rnum = e.e_rnum;
   s.e_birth = e.e_birth;
   s.e_frozen = e.e_frozen;
+  s.e_act = e.e_act;
   s.mir = e.mir;
   s.mu_frozen = e.mu_frozen;
   s.EV = e.cap * (s.V - 1);
@@ -1529,7 +1552,7 @@ void bind_edge_set(gbp_world *w) {
 void free_edge_set(gbp_world *w, EdgeSet *e) {
   if (e->egid != e->enbr) cudaFree(e->egid);
   cudaFree(e->enbr); cudaFree(e->e_own); cudaFree(e->e_dsafe); cudaFree(e->e_rnum); cudaFree(e->e_birth);
-  cudaFree(e->e_frozen); cudaFree(e->mir); cudaFree(e->map); cudaFree(e->mu_frozen); cudaFree(e->e_msg);
+  cudaFree(e->e_frozen); cudaFree(e->e_act); cudaFree(e->mir); cudaFree(e->map); cudaFree(e->mu_frozen); cudaFree(e->e_msg);
   *e = EdgeSet();
 }
 
@@ -1545,6 +1568,7 @@ int grow_edge_set(gbp_world *w, EdgeSet *e, int64_t cap) {
   CK(dalloc(e->e_rnum, size_t(cap)));
   CK(dalloc(e->e_birth, size_t(cap)));
   CK(dalloc(e->e_frozen, size_t(cap)));
+  CK(dalloc(e->e_act, size_t(cap)));
   CK(dalloc(e->mu_frozen, size_t(2) * size_t(cap) * Vm1));
   CK(dalloc(e->map, size_t(cap)));
   CK(dalloc(e->mir, size_t(6) * size_t(cap) * Vm1));

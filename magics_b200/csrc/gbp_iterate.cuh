@@ -412,6 +412,81 @@ GBP_DEV void ext_edge(const Store &s, const double *__restrict__ pubr, const Edg
   }
 }
 
+// ---- InterRobot messages of an external half, one thread per (edge, variable) -------------------------------
+// The general kernel below keeps a robot's V variables in V lanes of one warp; evaluating the neighbours' InterRobot
+// factors inside it makes every lane walk the robot's K edges one after the other — K dependent load chains and, for
+// every factor inside its safety distance, a 20-double record fetch and a Schur complement, at 168 registers and
+// 3 warps per scheduler (profiles/r02y: 43 % long-scoreboard, 31 % instruction-fetch stalls in a dense swarm).  The
+// messages of one external half do not depend on each other, so they are computed FIRST, by this kernel, with one
+// thread per (edge, variable) — K (V - 1) independent threads per robot, a third of the registers, 2 kB of code —
+// and stored where the receiver keeps them anyway (Store::mir).  k_iterate then adds the stored messages in inbox
+// order; the sums see the same doubles in the same order as when they came from registers.
+// Also leaves Store::e_act[e] = "the neighbour's radio is on and it is not idle" (what decides between delivery and
+// freeze, robot.rs:1843-1858) so that k_iterate reads one byte per edge instead of chasing the neighbour slot.
+// par >= 0: the robots of Store::gen_list (length gen_count[par]); par < 0: every robot of the shard.
+#ifndef GBP_EDGE_SPLIT
+#define GBP_EDGE_SPLIT 1
+#endif
+constexpr int kEdgeBlock = 128;
+#ifndef GBP_EDGE_MIN_BLOCKS
+#define GBP_EDGE_MIN_BLOCKS 4  // 126 registers without a cap: 16 warps / SM
+#endif
+__global__ void __launch_bounds__(kEdgeBlock, GBP_EDGE_MIN_BLOCKS)
+    k_edge_messages(const __grid_constant__ Store s, const int p, const int par) {
+  const int V = s.V, Vm1 = V - 1;
+  const unsigned lane = threadIdx.x & 31u;
+  const int64_t nrob = par >= 0 ? int64_t(s.gen_count[par]) : int64_t(s.Nloc);
+  const int64_t wstride = (int64_t(gridDim.x) * kEdgeBlock) >> 5;
+  const double *const pubr = s.pub[p];
+  for (int64_t k = (int64_t(blockIdx.x) * kEdgeBlock + threadIdx.x) >> 5; k < nrob; k += wstride) {
+    const int64_t r = par >= 0 ? int64_t(s.gen_list[k]) : k;
+    if (s.idle[r] != 0 || s.antenna[r] == 0) continue;  // no external half for this robot (robot.rs:1800-1812)
+    const int64_t e0 = s.eoff[r], e1 = s.eoff[r + 1], elow = e0 + s.nlow[r];
+    const int64_t npairs = (e1 - e0) * Vm1;
+    for (int64_t q = lane; q < npairs; q += 32) {
+      const int64_t eo = q / Vm1;
+      const int i = 1 + int(q - eo * Vm1);
+      const int64_t e = e0 + eo, m = e0 * Vm1 + q;  // == e * (V - 1) + (i - 1)
+      const int A = s.enbr[e];
+      const bool act = s.en_ir && s.antenna[A] != 0 && s.idle[A] == 0;
+      if (i == 1) s.e_act[e] = act ? 1 : 0;
+      if (!act) continue;  // undelivered: the receiver keeps the message it has
+      const int64_t va = int64_t(A) * V + i, vi = r * V + i;
+      const double a0 = pubr[s.at<kRec>(20, va)], a1 = pubr[s.at<kRec>(21, va)];
+      const uint32_t epochA = s.pub_epoch[p][va], birth = s.e_birth[e];
+      const bool frozen = (s.e_frozen[e] & 1) != 0;
+      const double dsafe = s.e_dsafe[e];
+      const uint64_t rnum = s.e_rnum[e];
+      double mb[2] = {s.mu_ext[s.at<2>(0, vi)], s.mu_ext[s.at<2>(1, vi)]};
+      if (frozen) {  // rare: edge just created, or A's radio was off at the last delivery
+        mb[0] = s.mu_frozen[m];
+        mb[1] = s.mu_frozen[s.EV + m];
+      }
+      const bool a_ne = epochA > birth;
+      const double muA[2] = {a_ne ? a0 : 0.0, a_ne ? a1 : 0.0};
+      bool ok = false;
+      double me[2], ml[4];
+      if (!interrobot_skip(e < elow, muA, mb, dsafe)) {
+        double rec[20];
+#pragma unroll
+        for (int c = 0; c < 20; ++c) rec[c] = pubr[s.at<kRec>(c, va)];
+        const double tiny = s.tiny_scale * double(rnum + uint64_t(i - 1));
+        ok = interrobot_message(e < elow, muA, mb, a_ne, rec, dsafe, tiny, s.lm_ir, me, ml);
+      }
+      if (ok) {
+        s.mir[m] = me[0];
+        s.mir[s.EV + m] = me[1];
+        s.mir[2 * s.EV + m] = ml[0];
+        s.mir[3 * s.EV + m] = ml[1];
+        s.mir[4 * s.EV + m] = ml[2];
+        s.mir[5 * s.EV + m] = ml[3];
+      } else {
+        s.mir[m] = empty_marker();
+      }
+    }
+  }
+}
+
 #ifdef GBP_ITER_MAXREG  // experiments: exact register cap instead of a CTAs-per-SM target
 #define GBP_ITER_BOUNDS __maxnreg__(GBP_ITER_MAXREG)
 #else
@@ -490,6 +565,23 @@ GBP_DEV void iterate_warp(const Store &s, const int p, const uint32_t epoch, con
       mu_sent[0] = s.mu_ext[s.at<2>(0, vi)];
       mu_sent[1] = s.mu_ext[s.at<2>(1, vi)];
     }
+#if GBP_EDGE_SPLIT
+    // the neighbours' factors have been evaluated by k_edge_messages: every edge's message (new, or the one kept
+    // because nothing was delivered) sits in Store::mir
+    for (int64_t e = e0;; ++e) {
+      if (e == eadd) add_internal(s, p, vi, ae, al);
+      if (e >= e1) break;
+      const int64_t m = e * (V - 1) + (i - 1);
+      const bool act = s.e_act[e] != 0, frozen = (s.e_frozen[e] & 1) != 0;
+      if (add_mirror(s, m, ae, al) && e - e0 < 64) mir_ne |= 1ull << (e - e0);
+      // undelivered: A's factor keeps the mean it already holds from this variable while this variable's belief
+      // moves on (robot.rs:1851): freeze it
+      if (!act && !frozen) {
+        s.mu_frozen[m] = mu_sent[0];
+        s.mu_frozen[s.EV + m] = mu_sent[1];
+      }
+    }
+#else
     int A_next = (e0 < e1) ? s.enbr[e0] : 0;
     for (int64_t e = e0;; ++e) {
       if (e == eadd) add_internal(s, p, vi, ae, al);
@@ -499,6 +591,7 @@ GBP_DEV void iterate_warp(const Store &s, const int p, const uint32_t epoch, con
       if (e + 1 < e1) A_next = s.enbr[e + 1];
       ext_edge(s, pubr, h, e, e0, elow, V, i, mu_sent, ae, al, mir_ne);
     }
+#endif
     double cov[16];
     bool valid = false;
     const bool taken = belief_moments(ae, al, mu, cov, valid);
@@ -526,8 +619,12 @@ GBP_DEV void iterate_warp(const Store &s, const int p, const uint32_t epoch, con
       // delivered edges hold mu_ext again; undelivered ones are (stay) frozen; the robot's lanes
       // share the edges (every lane has finished reading e_frozen: __syncwarp above)
       for (int64_t e = eo0 + i; e < eo1; e += V) {
+#if GBP_EDGE_SPLIT
+        const uint8_t fr = s.e_act[e] ? 0 : 1;
+#else
         const int A = s.enbr[e];
         const uint8_t fr = (s.en_ir && s.antenna[A] != 0 && s.idle[A] == 0) ? 0 : 1;
+#endif
         const uint8_t cur = s.e_frozen[e];
         if ((cur & 1) != fr) s.e_frozen[e] = uint8_t((cur & 2) | fr);  // bit 1 belongs to the collision monitor
       }

@@ -114,6 +114,8 @@ struct Store {
   uint32_t *e_birth;   // [E]   epoch at which the edge was created
   uint8_t *e_frozen;   // [E]   bit 0: A's factor holds an older mean of B than mu_ext (see mu_frozen);
                        //       bit 1: CollisionState::Colliding of the pair (planner/collisions.rs:455-493)
+  uint8_t *e_act;      // [E]   1: the neighbour's radio is on and it is not idle — written by k_edge_messages for the
+                       //       robots k_iterate runs in the same sub-step, read there (scratch: not carried over a rebuild)
   uint32_t *coll_hits; // [cap] per robot: collisions it has been part of (RobotRobotCollisions::get)
   double *mu_frozen;   // [2][E*(V-1)] position mean of B's variable that A's factor holds while the
                        //   edge is frozen: B's belief at edge creation (robot.rs:1557-1585), or the
