@@ -1019,6 +1019,7 @@ struct gbp_world {
   float t0_first = 0.0f;
   int sm_count = 148;
   int edge_occ = 0;                // resident CTAs per SM of k_edge_messages
+  bool iter_opted_in[4] = {false, false, false, false};
   int iter_occ[4] = {0, 0, 0, 0};  // resident CTAs per SM of k_iterate<EXT, INT>, by (EXT ? 2 : 0) + (INT ? 1 : 0)
   int par = 0;                // launch parity: which Store::gen_count the current launch appends to
   unsigned long long *coll_totals = nullptr;              // [0] Hit events so far, [1] pairs colliding now
@@ -1365,6 +1366,11 @@ int launch_iterate(gbp_world *w, int part) {
   }
   const int which = (EXT ? 2 : 0) + (INT ? 1 : 0);
   if (s.Nloc == 0) return 0;
+  if (!w->iter_opted_in[which]) {
+    CK(cudaFuncSetAttribute(gbp::k_iterate<EXT, INT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            int(gbp::kIterSmemBytes)));
+    w->iter_opted_in[which] = true;
+  }
   const int rpw = 32 / s.V;
   const int wpb = gbp::kIterBlock / 32;
   const int kind = EXT ? (INT ? GBP_PROFILE_ITERATE_EXT_INT : GBP_PROFILE_ITERATE_EXT) : GBP_PROFILE_ITERATE_INT;
@@ -1379,7 +1385,7 @@ int launch_iterate(gbp_world *w, int part) {
       w->launches += 1;
     }
 #endif
-    gbp::k_iterate<EXT, INT><<<grid, gbp::kIterBlock, 0, st>>>(s, w->p, w->epoch, -1);
+    gbp::k_iterate<EXT, INT><<<grid, gbp::kIterBlock, gbp::kIterSmemBytes, st>>>(s, w->p, w->epoch, -1);
     w->launches += 1;
   } else {
     // the decoupled robots (two lanes per variable), then whatever that kernel handed over
@@ -1407,7 +1413,8 @@ int launch_iterate(gbp_world *w, int part) {
       // stride, so a grid of 4 CTAs per SM at 3 resident ran a second, one-third-full wave (r02y: SMs busy 75 %)
       int &occ = w->iter_occ[which];
       if (occ <= 0) {
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gbp::k_iterate<EXT, INT>, gbp::kIterBlock, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gbp::k_iterate<EXT, INT>, gbp::kIterBlock,
+                                                         gbp::kIterSmemBytes));
         if (occ <= 0) occ = 1;
         if (const char *e = std::getenv("GBP_ITER_GRID_PER_SM")) occ = std::max(1, atoi(e));
       }
@@ -1426,7 +1433,7 @@ int launch_iterate(gbp_world *w, int part) {
         w->launches += 1;
       }
 #endif
-      CK(launch_pdl(w->use_pdl, gbp::k_iterate<EXT, INT>, grid, unsigned(gbp::kIterBlock), size_t(0), st, s, w->p,
+      CK(launch_pdl(w->use_pdl, gbp::k_iterate<EXT, INT>, grid, unsigned(gbp::kIterBlock), gbp::kIterSmemBytes, st, s, w->p,
                     w->epoch, *par));
       *par ^= 1;
       w->launches += 2;

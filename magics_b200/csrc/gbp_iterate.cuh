@@ -36,7 +36,6 @@ namespace gbp {
 #define GBP_ITER_MIN_BLOCKS 3
 #endif
 constexpr int kIterBlock = GBP_ITER_BLOCK;
-constexpr size_t kIterSmemBytes = 0;
 
 // ---- L2 prefetch -----------------------------------------------------------------------------
 // The kernel is a chain of ~16 dependent load phases per thread at 12 warps per SM, so the
@@ -179,6 +178,92 @@ GBP_DEV bool add_mirror(const Store &s, int64_t m, double (&ae)[4], double (&al)
   double v[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) v[k] = s.mir[k * s.EV + m];
+  if (is_empty_marker(v[0])) return false;
+  ae[0] = ae[0] + v[0];
+  ae[1] = ae[1] + v[1];
+  al[0] = al[0] + v[2];
+  al[1] = al[1] + v[3];
+  al[4] = al[4] + v[4];
+  al[5] = al[5] + v[5];
+  return true;
+}
+
+// ---- mirror messages streamed through shared memory --------------------------------------------------------
+// A variable's inbox sum walks its InterRobot edges in FactorId order; the adds are a serial chain by definition, but
+// in a loop of add_mirror calls every add also waits for ITS edge's six loads (profiles/r02y2: 52 % of k_iterate's
+// stall samples in a dense swarm sit on the Empty-marker test).  All addresses are known up front (m = e (V - 1) +
+// (i - 1)), so the loads run kMirDepth edges ahead as cp.async copies into a per-thread strip of shared memory: no
+// registers are held while they are in flight.  A thread reads only what its own copies wrote (cp.async.wait_group).
+#ifndef GBP_MIR_STREAM
+#define GBP_MIR_STREAM 1
+#endif
+#ifndef GBP_MIR_DEPTH
+#define GBP_MIR_DEPTH 4  // 4: 36.8 ms, 8: 37.3 ms, 12: 44.1 ms per dense tick (r02v3); 24 KiB of shared memory per CTA
+#endif
+constexpr int kMirDepth = GBP_MIR_DEPTH;
+constexpr size_t kIterSmemBytes = GBP_MIR_STREAM ? size_t(kMirDepth) * 6 * GBP_ITER_BLOCK * sizeof(double) : 0;
+GBP_DEV void cp_async8(double *smem, const double *gmem) {
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(unsigned(__cvta_generic_to_shared(smem))), "l"(gmem)
+               : "memory");
+#endif
+}
+GBP_DEV void cp_async_commit() {
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+GBP_DEV void cp_async_wait() {
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+// For every edge e of [lo, hi) in order: `pre(e)` (sums that sit between two mirror messages in the inbox order), then,
+// unless `skip(e)`, `use(e, v)` with the six stored doubles of the variable's mirror message; `pre(hi)` at the end.
+template <class Pre, class Skip, class Use>
+GBP_DEV void stream_mirrors(const Store &s, double *strip, int64_t lo, int64_t hi, int Vm1, int im1, Pre &&pre,
+                            Skip &&skip, Use &&use) {
+#if GBP_MIR_STREAM
+  const int T = GBP_ITER_BLOCK;
+  auto issue = [&](int64_t e) {
+    if (e < hi && !skip(e)) {
+      const int slot = int((e - lo) % kMirDepth);
+      const int64_t m = e * Vm1 + im1;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) cp_async8(strip + (slot * 6 + k) * T, s.mir + k * s.EV + m);
+    }
+    cp_async_commit();  // an empty group keeps the count of groups in flight the same for every edge
+  };
+  for (int d = 0; d < kMirDepth; ++d) issue(lo + d);
+  for (int64_t e = lo; e < hi; ++e) {
+    pre(e);
+    cp_async_wait<kMirDepth - 1>();
+    if (!skip(e)) {
+      const int slot = int((e - lo) % kMirDepth);
+      double v[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v[k] = strip[(slot * 6 + k) * T];
+      use(e, v);
+    }
+    issue(e + kMirDepth);  // into the slot just read (the reads above have been consumed)
+  }
+  cp_async_wait<0>();
+  pre(hi);
+#else
+  for (int64_t e = lo; e < hi; ++e) {
+    pre(e);
+    if (skip(e)) continue;
+    double v[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v[k] = s.mir[k * s.EV + (e * Vm1 + im1)];
+    use(e, v);
+  }
+  pre(hi);
+#endif
+}
+// add_mirror on values already loaded.
+GBP_DEV bool add_mirror_values(const double (&v)[6], double (&ae)[4], double (&al)[16]) {
   if (is_empty_marker(v[0])) return false;
   ae[0] = ae[0] + v[0];
   ae[1] = ae[1] + v[1];
@@ -497,7 +582,7 @@ __global__ void __launch_bounds__(kEdgeBlock, GBP_EDGE_MIN_BLOCKS)
 // launch is handed back to k_iterate_axis.
 template <bool EXT, bool INT>
 GBP_DEV void iterate_warp(const Store &s, const int p, const uint32_t epoch, const int64_t r, const bool live,
-                          const int rl, const int i, const unsigned lane, const bool requalify) {
+                          const int rl, const int i, const unsigned lane, const bool requalify, double *strip) {
   const int V = s.V;
   const int64_t vi = live ? r * V + i : 0;
   if (live && s.cov_lazy[vi]) materialise_cov(s, p, r, vi);
@@ -568,19 +653,22 @@ GBP_DEV void iterate_warp(const Store &s, const int p, const uint32_t epoch, con
 #if GBP_EDGE_SPLIT
     // the neighbours' factors have been evaluated by k_edge_messages: every edge's message (new, or the one kept
     // because nothing was delivered) sits in Store::mir
-    for (int64_t e = e0;; ++e) {
-      if (e == eadd) add_internal(s, p, vi, ae, al);
-      if (e >= e1) break;
-      const int64_t m = e * (V - 1) + (i - 1);
-      const bool act = s.e_act[e] != 0, frozen = (s.e_frozen[e] & 1) != 0;
-      if (add_mirror(s, m, ae, al) && e - e0 < 64) mir_ne |= 1ull << (e - e0);
-      // undelivered: A's factor keeps the mean it already holds from this variable while this variable's belief
-      // moves on (robot.rs:1851): freeze it
-      if (!act && !frozen) {
-        s.mu_frozen[m] = mu_sent[0];
-        s.mu_frozen[s.EV + m] = mu_sent[1];
-      }
-    }
+    stream_mirrors(
+        s, strip, e0, e1, V - 1, i - 1,
+        [&](int64_t e) {
+          if (e == eadd) add_internal(s, p, vi, ae, al);
+        },
+        [](int64_t) { return false; },
+        [&](int64_t e, const double(&v)[6]) {
+          if (add_mirror_values(v, ae, al) && e - e0 < 64) mir_ne |= 1ull << (e - e0);
+          // undelivered: A's factor keeps the mean it already holds from this variable while this variable's belief
+          // moves on (robot.rs:1851): freeze it
+          if (!s.e_act[e] && !(s.e_frozen[e] & 1)) {
+            const int64_t m = e * (V - 1) + (i - 1);
+            s.mu_frozen[m] = mu_sent[0];
+            s.mu_frozen[s.EV + m] = mu_sent[1];
+          }
+        });
 #else
     int A_next = (e0 < e1) ? s.enbr[e0] : 0;
     for (int64_t e = e0;; ++e) {
@@ -671,12 +759,16 @@ GBP_DEV void iterate_warp(const Store &s, const int p, const uint32_t epoch, con
       const int64_t eadd = elow < e1 ? elow : e1;
       bool any_mir = false;
       load_prior(s, vi, ae, al);
-      for (int64_t e = e0; e < eadd; ++e) {
+      auto known_empty = [&](int64_t e) {
 #if GBP_MIRROR_MASK
-        if (EXT && do_ext && e - e0 < 64 && !((mir_ne >> (e - e0)) & 1ull)) continue;  // known Empty
+        return EXT && do_ext && e - e0 < 64 && !((mir_ne >> (e - e0)) & 1ull);
+#else
+        return false;
 #endif
-        any_mir |= add_mirror(s, e * (V - 1) + (i - 1), ae, al);
-      }
+      };
+      stream_mirrors(
+          s, strip, e0, eadd, V - 1, i - 1, [](int64_t) {}, known_empty,
+          [&](int64_t, const double(&v)[6]) { any_mir |= add_mirror_values(v, ae, al); });
       if (s.en_dyn) {
         if (i >= 1) {  // Dynamic factor i-1 -> variable i (slot 1)
           double dcL[4];
@@ -752,12 +844,9 @@ GBP_DEV void iterate_warp(const Store &s, const int p, const uint32_t epoch, con
 
       // ---- belief update + new record (variable.rs:251-297)
       const unsigned unary = add_unary_stored(s, vi, ae, al);
-      for (int64_t e = eadd; e < e1; ++e) {
-#if GBP_MIRROR_MASK
-        if (EXT && do_ext && e - e0 < 64 && !((mir_ne >> (e - e0)) & 1ull)) continue;  // known Empty
-#endif
-        any_mir |= add_mirror(s, e * (V - 1) + (i - 1), ae, al);
-      }
+      stream_mirrors(
+          s, strip, eadd, e1, V - 1, i - 1, [](int64_t) {}, known_empty,
+          [&](int64_t, const double(&v)[6]) { any_mir |= add_mirror_values(v, ae, al); });
       double cov[16];
       bool valid = false;
       const bool taken = belief_moments(ae, al, mu, cov, valid);
@@ -804,6 +893,7 @@ GBP_DEV void iterate_warp(const Store &s, const int p, const uint32_t epoch, con
 template <bool EXT, bool INT>
 __global__ void GBP_ITER_BOUNDS
     k_iterate(const __grid_constant__ Store s, const int p, const uint32_t epoch, const int par) {
+  extern __shared__ double iter_smem[];  // kIterSmemBytes: the threads' mirror-message strips (stream_mirrors)
   const int V = s.V;
   const int rpw = 32 / V;
   const unsigned lane = threadIdx.x & 31u;
@@ -822,7 +912,7 @@ __global__ void GBP_ITER_BOUNDS
     const int64_t k = warp * rpw + rl;
     const bool live = rl < rpw && k < nrob;
     const int64_t r = live ? (par >= 0 ? int64_t(s.gen_list[k]) : k) : 0;
-    iterate_warp<EXT, INT>(s, p, epoch, r, live, rl, i, lane, par >= 0);
+    iterate_warp<EXT, INT>(s, p, epoch, r, live, rl, i, lane, par >= 0, iter_smem + threadIdx.x);
   }
 }
 

@@ -27,4 +27,6 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_it
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/ncu_full.log" 2>&1; echo "ncu full rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_iterate_axis -s 40 -c 1 -o "$OUT/prof_axis_rings" -f \
   python bench.py --workload rings --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/ncu_full_rings.log" 2>&1; echo "ncu full rings rc=$?"
+timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/bench_reference.json" 2> "$OUT/bench_reference.err"; echo "bench reference rc=$?"
+cut -c1-400 "$OUT/bench_reference.json"
 ls -la "$OUT"
