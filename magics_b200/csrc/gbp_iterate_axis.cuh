@@ -516,16 +516,16 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
       }
 #else
       if (i >= 1) {  // Dynamic factor i-1 -> variable i (slot 1); the other message comes from variable i-1
-        const int tn = t - 2, tq = (t ^ 1) - 2;
+        const int tn = t - 2, tx = (t & ~1) - 2, ty = (t | 1) - 2;  // own axis, x lane, y lane of variable i-1
         const double oe[2] = {xr[tn], xr[T + tn]};
-        const double oP[4] = {xr[2 * T + tn], xr[3 * T + tn], xr[4 * T + tn], xr[5 * T + tn]};
-        const double oQ[4] = {xr[2 * T + tq], xr[3 * T + tq], xr[4 * T + tq], xr[5 * T + tq]};
+        const double oX[4] = {xr[2 * T + tx], xr[3 * T + tx], xr[4 * T + tx], xr[5 * T + tx]};
+        const double oY[4] = {xr[2 * T + ty], xr[3 * T + ty], xr[4 * T + ty], xr[5 * T + ty]};
         double dc[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) dc[k] = s.dyn_tab ? dtab[4 * (i - 1) + k] : s.dyn_c[s.at<4>(k, vi - 1)];
         const DynM M = dyn_potential_q(dc[0], dc[1], dc[2], dc[3]);
         double ne_[2], nl[4];
-        if (dyn_message_axis<1>(a, M, xne[tn] != 0, oe, oP, oQ, ne_, nl)) {
+        if (dyn_message_axis_xy<1>(a, M, xne[tn] != 0, oe, oX, oY, ne_, nl)) {
           st_axis(s.m_dynL[1 - p], qm, ne_, nl);
 #pragma unroll
           for (int k = 0; k < 2; ++k) ae[k] = ae[k] + ne_[k];
@@ -536,16 +536,16 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
         }
       }
       if (i <= V - 2) {  // Dynamic factor i -> variable i (slot 0); the other message comes from variable i+1
-        const int tn = t + 2, tq = (t ^ 1) + 2;
+        const int tn = t + 2, tx = (t & ~1) + 2, ty = (t | 1) + 2;
         const double oe[2] = {xl[tn], xl[T + tn]};
-        const double oP[4] = {xl[2 * T + tn], xl[3 * T + tn], xl[4 * T + tn], xl[5 * T + tn]};
-        const double oQ[4] = {xl[2 * T + tq], xl[3 * T + tq], xl[4 * T + tq], xl[5 * T + tq]};
+        const double oX[4] = {xl[2 * T + tx], xl[3 * T + tx], xl[4 * T + tx], xl[5 * T + tx]};
+        const double oY[4] = {xl[2 * T + ty], xl[3 * T + ty], xl[4 * T + ty], xl[5 * T + ty]};
         double dc[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) dc[k] = s.dyn_tab ? dtab[4 * i + k] : s.dyn_c[s.at<4>(k, vi)];
         const DynM M = dyn_potential_q(dc[0], dc[1], dc[2], dc[3]);
         double ne_[2], nl[4];
-        if (dyn_message_axis<0>(a, M, xne[tn] != 0, oe, oP, oQ, ne_, nl)) {
+        if (dyn_message_axis_xy<0>(a, M, xne[tn] != 0, oe, oX, oY, ne_, nl)) {
           st_axis(s.m_dynR[1 - p], qm, ne_, nl);
 #pragma unroll
           for (int k = 0; k < 2; ++k) ae[k] = ae[k] + ne_[k];

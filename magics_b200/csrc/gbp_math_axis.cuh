@@ -25,11 +25,12 @@ namespace gbp {
 // Own block of inv4(m) for the decoupled m made of block P (this lane's axis) and Q (the other
 // axis).  False: singular (det == 0) or a non-finite determinant (the general path of inv4) —
 // the caller sends the robot to the general kernel.
-GBP_DEV bool inv_axis(int a, const double (&P)[4], const double (&Q)[4], double (&O)[4]) {
+// X = the x chain's block (m0, m2, m8, m10), Y = the y chain's (m5, m7, m13, m15), whichever lane holds which.
+GBP_DEV bool inv_axis_xy(int a, const double (&X)[4], const double (&Y)[4], double (&O)[4]) {
   const bool y = a != 0;
   // entries by their row-major index in the 4x4
-  const double m0 = y ? Q[0] : P[0], m2 = y ? Q[1] : P[1], m8 = y ? Q[2] : P[2], m10 = y ? Q[3] : P[3];
-  const double m5 = y ? P[0] : Q[0], m7 = y ? P[1] : Q[1], m13 = y ? P[2] : Q[2], m15 = y ? P[3] : Q[3];
+  const double m0 = X[0], m2 = X[1], m8 = X[2], m10 = X[3];
+  const double m5 = Y[0], m7 = Y[1], m13 = Y[2], m15 = Y[3];
   const double c0 = (m5 * m10) * m15 - (m7 * m10) * m13;  // minor<0,0>
   const double c1 = (m7 * m8) * m13 - (m5 * m8) * m15;    // minor<0,2>
   const double det = m0 * c0 + m2 * c1;
@@ -46,8 +47,14 @@ GBP_DEV bool inv_axis(int a, const double (&P)[4], const double (&Q)[4], double 
     c[2] = (m2 * m8) * m13 - (m0 * m10) * m13;  // minor<1,3>
     c[3] = (m0 * m5) * m10 - (m2 * m5) * m8;    // minor<3,3>
   }
-  divide_all(c, det, O);
+  divide_all_nz(c, det, O);
   return true;
+}
+GBP_DEV bool inv_axis(int a, const double (&P)[4], const double (&Q)[4], double (&O)[4]) {
+  const bool y = a != 0;
+  const double X[4] = {y ? Q[0] : P[0], y ? Q[1] : P[1], y ? Q[2] : P[2], y ? Q[3] : P[3]};
+  const double Y[4] = {y ? P[0] : Q[0], y ? P[1] : Q[1], y ? P[2] : Q[2], y ? P[3] : Q[3]};
+  return inv_axis_xy(a, X, Y, O);
 }
 
 // belief_moments (variable.rs:273-297) for one axis: false unless the update is taken AND valid
@@ -78,21 +85,23 @@ GBP_DEV bool belief_axis(int a, const double (&e)[2], const double (&P)[4], cons
 // dyn_message<KEEP> (factor/mod.rs:412-450 + marginalise_factor_distance.rs:55-127) for one axis.
 // oe / oP: this axis' part of the OTHER variable's message, oQ: the other axis' block of it.
 // False: Message::empty() or a non-finite input — general kernel.
+// oX / oY: the x chain's and the y chain's block of the OTHER variable's message (the kernel reads them from the
+// even and the odd lane's shared-memory slot: no selects), oe: this axis' part of its vector.
 template <int KEEP>
-GBP_DEV bool dyn_message_axis(int a, const DynM &M, bool other_nonempty, const double (&oe)[2], const double (&oP)[4],
-                              const double (&oQ)[4], double (&eta)[2], double (&lam)[4]) {
+GBP_DEV bool dyn_message_axis_xy(int a, const DynM &M, bool other_nonempty, const double (&oe)[2],
+                                 const double (&oX)[4], const double (&oY)[4], double (&eta)[2], double (&lam)[4]) {
   constexpr int A = KEEP * 2, B = (1 - KEEP) * 2;
-  double bP[4], bQ[4];
+  double bX[4], bY[4];
 #pragma unroll
   for (int r = 0; r < 2; ++r)
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const double p = M.m[B + r][B + c];
-      bP[r * 2 + c] = other_nonempty ? p + oP[r * 2 + c] : p;
-      bQ[r * 2 + c] = other_nonempty ? p + oQ[r * 2 + c] : p;
+      bX[r * 2 + c] = other_nonempty ? p + oX[r * 2 + c] : p;
+      bY[r * 2 + c] = other_nonempty ? p + oY[r * 2 + c] : p;
     }
   double I[4];
-  if (!inv_axis(a, bP, bQ, I)) return false;
+  if (!inv_axis_xy(a, bX, bY, I)) return false;
   const double eb[2] = {other_nonempty ? 0.0 + oe[0] : 0.0, other_nonempty ? 0.0 + oe[1] : 0.0};
   if (!(isfinite(eb[0]) & isfinite(eb[1]))) return false;
   bool inf = false;
@@ -111,6 +120,13 @@ GBP_DEV bool dyn_message_axis(int a, const DynM &M, bool other_nonempty, const d
     }
   }
   return !inf;
+}
+// oP: this axis' block of the other variable's message, oQ: the other axis' block of it.
+template <int KEEP>
+GBP_DEV bool dyn_message_axis(int a, const DynM &M, bool other_nonempty, const double (&oe)[2], const double (&oP)[4],
+                              const double (&oQ)[4], double (&eta)[2], double (&lam)[4]) {
+  return a ? dyn_message_axis_xy<KEEP>(a, M, other_nonempty, oe, oQ, oP, eta, lam)
+           : dyn_message_axis_xy<KEEP>(a, M, other_nonempty, oe, oP, oQ, eta, lam);
 }
 
 // ---- both Dynamic messages of a variable at once ------------------------------------------------------------
