@@ -1349,6 +1349,15 @@ cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), unsigned grid, unsign
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// Warps that share one robot's (edge, variable) pairs in k_edge_messages: enough of them to fill the GPU twice when
+// the swarm is small (at most `nrob` robots can be on the list), one per robot when the swarm alone does.
+int edge_chunks(const gbp_world *w, int64_t nrob) {
+  const int64_t want = int64_t(w->sm_count) * 16 * 2;  // 16 resident warps per SM
+  int chunks = 1;
+  while (chunks < 32 && nrob * chunks < want) chunks *= 2;
+  return chunks;
+}
+
 // One iterate launch pair (k_iterate_axis, then k_iterate over what it handed over) for one part of a shard:
 // part 0 = every own robot, 1 = the border robots (send lists), 2 = the others.
 template <bool EXT, bool INT>
@@ -1380,8 +1389,9 @@ int launch_iterate(gbp_world *w, int part) {
     ProfileScope ps(w, kind);
 #if GBP_EDGE_SPLIT
     if (EXT && s.E > 0) {  // the neighbours' InterRobot factors first, one thread per (edge, variable)
-      const unsigned eg = unsigned(std::min<int64_t>((int64_t(s.Nloc) + 3) / 4, int64_t(w->sm_count) * 16));
-      gbp::k_edge_messages<<<eg, gbp::kEdgeBlock, 0, st>>>(s, w->p, -1);
+      const int chunks = edge_chunks(w, s.Nloc);
+      const unsigned eg = unsigned(std::min<int64_t>((int64_t(s.Nloc) * chunks + 3) / 4, int64_t(w->sm_count) * 16));
+      gbp::k_edge_messages<<<eg, gbp::kEdgeBlock, 0, st>>>(s, w->p, -1, chunks);
       w->launches += 1;
     }
 #endif
@@ -1428,8 +1438,9 @@ int launch_iterate(gbp_world *w, int part) {
           CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w->edge_occ, gbp::k_edge_messages, gbp::kEdgeBlock, 0));
           if (w->edge_occ <= 0) w->edge_occ = 1;
         }
-        const unsigned eg = unsigned(std::min<int64_t>((nrob + 3) / 4, int64_t(w->sm_count) * w->edge_occ));
-        gbp::k_edge_messages<<<eg, gbp::kEdgeBlock, 0, st>>>(s, w->p, *par);
+        const int chunks = edge_chunks(w, nrob);
+        const unsigned eg = unsigned(std::min<int64_t>((nrob * chunks + 3) / 4, int64_t(w->sm_count) * w->edge_occ));
+        gbp::k_edge_messages<<<eg, gbp::kEdgeBlock, 0, st>>>(s, w->p, *par, chunks);
         w->launches += 1;
       }
 #endif

@@ -517,18 +517,23 @@ constexpr int kEdgeBlock = 128;
 #define GBP_EDGE_MIN_BLOCKS 4  // 126 registers without a cap: 16 warps / SM
 #endif
 __global__ void __launch_bounds__(kEdgeBlock, GBP_EDGE_MIN_BLOCKS)
-    k_edge_messages(const __grid_constant__ Store s, const int p, const int par) {
+    k_edge_messages(const __grid_constant__ Store s, const int p, const int par, const int chunks) {
+  // `chunks` warps share a robot's (edge, variable) pairs: 1 for a large swarm, up to 32 for a few dozen robots
+  // with dozens of neighbours each (the reference's Circle Experiment), where a warp per robot would leave the
+  // GPU to 30 warps walking 18 rounds each
   const int V = s.V, Vm1 = V - 1;
   const unsigned lane = threadIdx.x & 31u;
   const int64_t nrob = par >= 0 ? int64_t(s.gen_count[par]) : int64_t(s.Nloc);
   const int64_t wstride = (int64_t(gridDim.x) * kEdgeBlock) >> 5;
   const double *const pubr = s.pub[p];
-  for (int64_t k = (int64_t(blockIdx.x) * kEdgeBlock + threadIdx.x) >> 5; k < nrob; k += wstride) {
+  for (int64_t item = (int64_t(blockIdx.x) * kEdgeBlock + threadIdx.x) >> 5; item < nrob * chunks; item += wstride) {
+    const int64_t k = item / chunks;
+    const int chunk = int(item - k * chunks);
     const int64_t r = par >= 0 ? int64_t(s.gen_list[k]) : k;
     if (s.idle[r] != 0 || s.antenna[r] == 0) continue;  // no external half for this robot (robot.rs:1800-1812)
     const int64_t e0 = s.eoff[r], e1 = s.eoff[r + 1], elow = e0 + s.nlow[r];
     const int64_t npairs = (e1 - e0) * Vm1;
-    for (int64_t q = lane; q < npairs; q += 32) {
+    for (int64_t q = chunk * 32 + lane; q < npairs; q += 32 * chunks) {
       const int64_t eo = q / Vm1;
       const int i = 1 + int(q - eo * Vm1);
       const int64_t e = e0 + eo, m = e0 * Vm1 + q;  // == e * (V - 1) + (i - 1)
