@@ -20,4 +20,4 @@ timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > "$OUT/benc
 timeout 600 python bench.py --workload rings --steps 10 --warmup 3 --no-cpu-baseline > "$OUT/bench_rings.json" 2> "$OUT/bench_rings.err"; echo "bench rings rc=$?"; summ "$OUT/bench_rings.json"
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
   bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu-baseline > "$OUT/bench_n2.json" 2> "$OUT/bench_n2.err"; echo "bench n=2 rc=$?"; summ "$OUT/bench_n2.json"
-GBP_PRIORS_FUSED=0 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > "$OUT/bench_n1_unfused.json" 2> "$OUT/bench_n1_unfused.err"; echo "bench n=1 unfused rc=$?"; summ "$OUT/bench_n1_unfused.json"
+
