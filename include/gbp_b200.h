@@ -218,7 +218,11 @@ int32_t gbp_world_num_ghosts(const gbp_world_t *w);
  * (robot.rs:1362-1586; FactorGraph::delete_interrobot_factors_connected_to
  * factorgraph.rs:380-436; add_internal_edge/add_external_edge :304-353).
  * Sort-based spatial hash; connectivity, creation order and robot_number are
- * bit-exact with the reference's all-pairs search. */
+ * bit-exact with the reference's all-pairs search.
+ * The search itself (it reads positions and the live factor lists only) is started by the preceding
+ * gbp_world_update_prior_of_current_state / gbp_world_step on a side stream and runs next to the iterations; this call
+ * waits for it, reads its sizes and applies it.  A search whose inputs changed since (robots added or removed) is
+ * thrown away and repeated here; GBP_TOPO_EARLY=0 in the environment always searches here. */
 int gbp_world_update_topology(gbp_world_t *w);
 
 /* update_failed_comms result (robot.rs:1593-1601): antenna_active[n] (0/1), and
@@ -360,7 +364,8 @@ int gbp_world_internal_variable_iteration(gbp_world_t *w);
 int gbp_world_external_factor_iteration(gbp_world_t *w);
 int gbp_world_external_variable_iteration(gbp_world_t *w);
 
-/* One full tick = FixedUpdate chain items 1-7. */
+/* One full tick = FixedUpdate chain items 1-7: update_topology, the two prior updates (one launch
+ * for both when V >= 3 and message counting is off: they touch different variables of a robot), iterate. */
 int gbp_world_step(gbp_world_t *w);
 
 /* ---- setters used by the UI hooks (ui/settings.rs:437,495,590) ---------- */
@@ -436,13 +441,13 @@ int64_t gbp_world_kernel_launches(const gbp_world_t *w);
 /* Optional per-launch CUDA-event timing on the engine's stream (bench.py's
  * roofline leg): accumulated count / device milliseconds per kernel family. */
 enum gbp_profile_kind {
-  GBP_PROFILE_ITERATE_INT = 0,     /* k_iterate_axis<EXT=0,INT=1> (k_iterate when general_only) */
+  GBP_PROFILE_ITERATE_INT = 0,     /* k_iterate_axis<EXT=0,INT=1> (k_edge_messages + k_iterate when general_only) */
   GBP_PROFILE_ITERATE_EXT = 1,     /* k_iterate_axis<EXT=1,INT=0> */
   GBP_PROFILE_ITERATE_EXT_INT = 2, /* k_iterate_axis<EXT=1,INT=1>, the dominant kernel */
   GBP_PROFILE_TOPOLOGY = 3,        /* whole gbp_world_update_topology */
   GBP_PROFILE_PRIORS = 4,          /* horizon + current prior kernels */
   GBP_PROFILE_HALO = 5,            /* the send/recv part of the per-sub-step halo exchange */
-  GBP_PROFILE_ITERATE_GENERAL = 6, /* k_iterate over the robots k_iterate_axis handed over (any EXT/INT) */
+  GBP_PROFILE_ITERATE_GENERAL = 6, /* k_edge_messages + k_iterate over the robots k_iterate_axis handed over (any EXT/INT) */
   GBP_PROFILE_TOPO_POSITIONS = 7,  /* sharded worlds: the exchange of every robot's position / radius / despawned flag */
   GBP_PROFILE_TOPO_SEARCH = 8,     /* neighbour search + diff against the live edges, up to the size read-back */
   GBP_PROFILE_TOPO_APPLY = 9,      /* sharded: header / cross-shard robot_number exchange; then the new edge set */

@@ -2314,7 +2314,15 @@ void join_group(gbp_world *w, gbp_group *g, int rank) {
   w->comm_stream = w->stream;
   if (g->nccl) {
     cudaSetDevice(w->device);
-    cudaStreamCreateWithFlags(&w->comm_stream, cudaStreamNonBlocking);
+    // Highest priority, like the border stream: the pack / send-recv / unpack kernels of a halo exchange are a few
+    // CTAs that must slip in between the 15 000 CTAs of the interior launch queued before them; at the default
+    // priority they waited for that grid to drain and the exchange landed on the critical path after all
+    // (r02z8: ~80 us of every 330 us sub-step at 8 GPUs).  GBP_COMM_PRIORITY=0: default priority.
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    const char *e = std::getenv("GBP_COMM_PRIORITY");
+    if (e && e[0] == '0') cudaStreamCreateWithFlags(&w->comm_stream, cudaStreamNonBlocking);
+    else cudaStreamCreateWithPriority(&w->comm_stream, cudaStreamNonBlocking, hi);
   }
   cudaEventCreateWithFlags(&w->ev_border, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&w->ev_halo, cudaEventDisableTiming);
