@@ -73,7 +73,42 @@ class ClockSampler:
         self.rows = []
         self.proc = None
 
+    def _nvml_loop(self):
+        import pynvml as nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        while not self.halt.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                self.nvml_rows.append((float(sm), [k for k, b in names.items() if bits & b]))
+            except Exception:
+                pass
+            self.halt.wait(0.004)
+
     def start(self):
+        # NVML in-process (a sample every 4 ms: multi-GPU timed regions last tens of milliseconds); nvidia-smi -lms as
+        # the fallback when the binding is missing
+        self.nvml_rows, self.handle = [], None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            phys = self.index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    phys = int(vis.split(",")[self.index])
+                except (ValueError, IndexError):
+                    phys = self.index
+            self.handle = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            self.halt = threading.Event()
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            self.proc = None
+            return
+        except Exception:
+            self.handle = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
@@ -88,6 +123,13 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self) -> dict:
+        if getattr(self, "handle", None) is not None:
+            self.halt.set()
+            self.t.join(timeout=1)
+            sm = [r[0] for r in self.nvml_rows]
+            reasons = sorted({x for r in self.nvml_rows for x in r[1]})
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max, "samples": len(sm),
+                    "reasons": reasons, "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
