@@ -33,6 +33,12 @@
 // Gaussian instead (tests/test_oracle_env.py).  The RRT* hand-off functions (next-4) restate
 // factorgraph.rs:1467-1590 literally; the reference has no test for them.
 //
+// Evaluation outputs: update_robot_environment_collisions (planner/collisions.rs:368-455) calls
+// parry2d 0.13.7 (a git fork, Cargo.lock:5372-5374, absent) and the trackers (planner/tracking.rs:117-260) bevy_time's
+// Timer (absent): PARITY UNPINNED — intersection_test / project_local_point and Timer::tick are restated from the
+// crates' published algorithms and checked against float64 geometry and hand-computed timer sequences
+// (tests/test_oracle_evaluation.py).
+//
 // Build: g++ -O3 -std=c++17 -ffp-contract=off -pthread -shared -fPIC (see Makefile).
 
 #include <algorithm>
