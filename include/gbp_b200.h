@@ -167,7 +167,10 @@ int gbp_world_set_sdf_from_environment(gbp_world_t *w, const gbp_environment_t *
  *   positions[n*2]      f32 Transform.translation (x, z) (spawner.rs:530)
  *   wp_offsets[n+1], wp_xy[2*wp_offsets[n]]  f32 waypoint polyline of each robot
  *                       (mission route; also the TrackingFactor path, :1316-1322)
- * Robot ids are assigned consecutively in insertion order. */
+ * Robot ids are assigned consecutively in insertion order.  Sharded worlds: before gbp_world_commit_shards every
+ * shard takes its own robots; afterwards (robots spawned while the simulation runs) only the last shard does — the
+ * new ids lie above every existing one — and every rank calls gbp_world_commit_shards again before the next
+ * collective call. */
 int gbp_world_add_robots(gbp_world_t *w, int32_t n, const float *radii,
                          const uint32_t *timesteps, const double *init_means,
                          const float *positions, const int32_t *wp_offsets,

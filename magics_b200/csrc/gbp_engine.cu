@@ -2759,9 +2759,16 @@ int gbp_world_add_robots(gbp_world_t *w, int32_t n, const float *radii, const ui
     return fail(GBP_ERR_BAD_ARGUMENT, "gbp_world_add_robots: variable_timesteps differ from the world's");
   w->timesteps.assign(timesteps, timesteps + V);
   cudaStream_t st = w->stream;
-  if (w->sh.ws > 1 && w->grp->committed)
-    return fail(GBP_ERR_STATE, "gbp_world_add_robots: a sharded world takes robots only before gbp_world_commit_shards "
-                               "(global ids are contiguous per shard)");
+  if (w->sh.ws > 1 && w->grp->committed) {
+    // Spawned later (FormationSpawner repeats, spawner.rs:186-323): new entities get ids above every existing one, so
+    // they can only join the LAST shard without renumbering anybody (ids are contiguous per shard); where they stand
+    // does not matter for correctness — neighbours are found by position.  The group must publish the new total:
+    // gbp_world_commit_shards again, on every rank, before the next collective call.
+    if (w->sh.rank != w->sh.ws - 1)
+      return fail(GBP_ERR_STATE, "gbp_world_add_robots: after gbp_world_commit_shards robots can join the last shard only "
+                                 "(global ids are contiguous per shard and follow spawn order)");
+    w->grp->committed = false;
+  }
   const int64_t N0 = s.Nloc, N1 = int64_t(s.Nloc) + n;
   if (int rc = topology_inputs_change(w)) return rc;
   if (int rc = reserve_robots(w, N1)) return rc;

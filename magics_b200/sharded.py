@@ -83,6 +83,15 @@ class LocalShards:
 
     def add_robots(self, radii, timesteps, init_means, positions, wp_offsets, wp_xy):
         n = int(np.asarray(radii).shape[0])
+        if getattr(self, "_committed", False):
+            # robots spawned later take the ids above every existing one: they join the last shard, and the group
+            # publishes the new total (gbp_world_commit_shards again)
+            self.shards[-1].add_robots(radii, timesteps, init_means, positions, wp_offsets, wp_xy)
+            self.bounds = self.bounds.copy()
+            self.bounds[-1] += n
+            self.shards[0].commit_shards()
+            return
+        self._committed = True
         if self.bounds is None:
             self.bounds = partition(n, self.ws)
         b = self.bounds

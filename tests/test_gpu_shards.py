@@ -179,3 +179,32 @@ def test_sharded_equals_single_gpu_bitwise_lattice_moving():
                 assert np.array_equal(x, y), f"shear tick {tick}: connectivity / robot_number"
             edges.append(a[1].size)
     assert np.array_equal(many.read_positions(), one.read_positions())
+
+
+def test_robots_spawned_after_commit_join_the_last_shard():
+    """FormationSpawner repeats (spawner.rs:186-323): robots that appear while the simulation runs take the ids above
+    every existing one, i.e. they join the last shard whatever their position, and the group publishes the new total
+    (gbp_world_commit_shards again).  Connectivity, robot_number and beliefs must stay those of the oracle and the
+    bits those of a single-GPU world that received the same robots at the same tick."""
+    sw = scenarios.circle(12, 14.0)
+    late = scenarios.circle(9, 11.0)  # a second wave, spawned inside the first one's circle
+    g, o = make_pair(sw, 3)
+    one = World(sw.cfg)
+    sw.add_to(one)
+    worlds = (g, one, o)
+    for tick in range(30):
+        for w in worlds:
+            w.step()
+        if tick == 7:
+            for w in worlds:
+                late.add_to(w, set_sdf=False)
+        if tick == 15:
+            for w in worlds:
+                late.add_to(w, set_sdf=False)
+        if tick in (7, 8, 12, 16, 22, 29):
+            check(g, o, f"late spawn tick {tick}")
+            assert_same_bits(g.read_beliefs(), one.read_beliefs(), f"late spawn tick {tick}")
+            assert np.array_equal(g.read_positions(), one.read_positions())
+    assert g.num_robots == sw.n + 2 * late.n and g.shards[-1].num_robots == sw.n // 3 + 2 * late.n
+    with pytest.raises(RuntimeError, match="last shard"):
+        late.slice(0, 2).add_to(g.shards[0], set_sdf=False)
