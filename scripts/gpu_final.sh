@@ -6,14 +6,14 @@ TAG=${1:-final}
 OUT=gpurun_out/$TAG
 mkdir -p "$OUT"
 python -c "import __graft_entry__ as g; g.build(); g.smoke()" > "$OUT/smoke.log" 2>&1; echo "smoke rc=$?"; tail -1 "$OUT/smoke.log"
-timeout 1500 python -m pytest tests -m gpu -q > "$OUT/pytest_gpu.log" 2>&1; echo "pytest rc=$?"
+if [ "${2:-}" != "skip-tests" ]; then timeout 1500 python -m pytest tests -m gpu -q > "$OUT/pytest_gpu.log" 2>&1; echo "pytest rc=$?"; fi
 tail -6 "$OUT/pytest_gpu.log"
-/usr/bin/time -v timeout 900 python bench.py > "$OUT/bench_default.json" 2> "$OUT/bench_default.err"; echo "bench default rc=$?"
-grep -E "Elapsed" "$OUT/bench_default.err"
+SECONDS=0; timeout 900 python bench.py > "$OUT/bench_default.json" 2> "$OUT/bench_default.err"; echo "bench default rc=$?"
+echo "wall ${SECONDS}s"
 python - <<PY
 import json
 d=json.load(open("$OUT/bench_default.json"))
 print("value %.1f M/s e2e %.1f M/s ms/step %.2f"%(d["value"]/1e6, d["e2e"]["value"]/1e6, d["ms_per_step"]), d["clocks"], "frac %.3f traffic_frac %.3f"%(d["roofline"]["frac"], d["roofline"]["traffic_frac"]), d["cpu_baseline"]["value"] if d["cpu_baseline"] else None, d["gpu_launches"])
 PY
-/usr/bin/time -v timeout 900 python bench.py --impl reference > "$OUT/bench_reference_default.json" 2> "$OUT/bench_reference_default.err"; echo "bench reference rc=$?"
-grep -E "Elapsed" "$OUT/bench_reference_default.err"; cut -c1-300 "$OUT/bench_reference_default.json"
+SECONDS=0; timeout 900 python bench.py --impl reference > "$OUT/bench_reference_default.json" 2> "$OUT/bench_reference_default.err"; echo "bench reference rc=$?"
+echo "wall ${SECONDS}s"; cut -c1-300 "$OUT/bench_reference_default.json"

@@ -29,7 +29,12 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     which = sys.argv[1] if len(sys.argv) > 1 else "circle"
-    if which == "circle":
+    late = None
+    if which == "late":
+        # robots spawned while the simulation runs: the last rank takes them, every rank commits again
+        sw, ticks = scenarios.circle(16, 14.0), 24
+        late = scenarios.circle(9, 11.0)
+    elif which == "circle":
         sw, ticks = scenarios.circle(30), 25
     elif which == "lattice":
         sw, ticks = scenarios.lattice(60, 40), 4
@@ -41,8 +46,13 @@ def main():
     mine.add_to(g)
     g.commit_shards()
     assert g.first_global_id == int(b[rank]) and g.num_robots_global == sw.n
-    for _ in range(ticks):
+    for tick in range(ticks):
         g.step()
+        if late is not None and tick == 8:
+            if rank == ws - 1:
+                late.add_to(g, set_sdf=False)
+            g.commit_shards()
+            assert g.num_robots_global == sw.n + late.n
     bel = g.read_beliefs()
     off, nb, rn = g.read_connections()
     parts = gather_arrays({**bel, "deg": np.diff(off), "nb": nb, "rn": rn, "ghosts": np.array([g.num_ghosts])}, rank, ws)
@@ -50,26 +60,30 @@ def main():
         got = {k: np.concatenate([p[k] for p in parts], axis=0) for k in parts[0]}
         one = World(sw.cfg, device=local)
         sw.add_to(one)
-        for _ in range(ticks):
+        for tick in range(ticks):
             one.step()
+            if late is not None and tick == 8:
+                late.add_to(one, set_sdf=False)
         ref = one.read_beliefs()
         for k in ("eta", "lam", "mean", "cov", "valid"):
             assert np.array_equal(got[k], ref[k], equal_nan=True), f"{which}: {k} differs from the single-GPU engine"
         o1, n1, r1 = one.read_connections()
         assert np.array_equal(got["deg"], np.diff(o1)) and np.array_equal(got["nb"], n1) and np.array_equal(got["rn"], r1)
         assert got["ghosts"].sum() > 0
-        if which == "circle":
+        if which in ("circle", "late"):
             from oracle.oracle import OracleWorld
             from tests.parity import assert_beliefs_match
 
             o = OracleWorld(sw.cfg)
             sw.add_to(o)
-            for _ in range(ticks):
+            for tick in range(ticks):
                 o.step()
+                if late is not None and tick == 8:
+                    late.add_to(o, set_sdf=False)
             assert_beliefs_match(got, o.read_beliefs(), what="nccl shards vs oracle")
             oo, no, ro = o.read_connections()
             assert np.array_equal(got["nb"], no) and np.array_equal(got["rn"], ro)
-        print(f"NCCL-SHARDS-OK {which} ws={ws} robots={sw.n} ghosts={got['ghosts'].tolist()}", flush=True)
+        print(f"NCCL-SHARDS-OK {which} ws={ws} robots={sw.n + (late.n if late else 0)} ghosts={got['ghosts'].tolist()}", flush=True)
     dist.barrier()
     g.close()
     dist.destroy_process_group()

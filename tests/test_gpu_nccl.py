@@ -16,7 +16,7 @@ def _gpus() -> int:
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("scenario", ["circle", "lattice", "rings"])
+@pytest.mark.parametrize("scenario", ["circle", "lattice", "rings", "late"])
 def test_nccl_shards_match_single_gpu_and_oracle(scenario):
     n = _gpus()
     if n < 2:
