@@ -226,9 +226,10 @@ GBP_DEV void stream_mirrors(const Store &s, double *strip, int64_t lo, int64_t h
                             Skip &&skip, Use &&use) {
 #if GBP_MIR_STREAM
   const int T = GBP_ITER_BLOCK;
+  static_assert((kMirDepth & (kMirDepth - 1)) == 0, "GBP_MIR_DEPTH must be a power of two");
   auto issue = [&](int64_t e) {
     if (e < hi && !skip(e)) {
-      const int slot = int((e - lo) % kMirDepth);
+      const int slot = int(unsigned(e - lo) & unsigned(kMirDepth - 1));
       const int64_t m = e * Vm1 + im1;
 #pragma unroll
       for (int k = 0; k < 6; ++k) cp_async8(strip + (slot * 6 + k) * T, s.mir + k * s.EV + m);
@@ -240,7 +241,7 @@ GBP_DEV void stream_mirrors(const Store &s, double *strip, int64_t lo, int64_t h
     pre(e);
     cp_async_wait<kMirDepth - 1>();
     if (!skip(e)) {
-      const int slot = int((e - lo) % kMirDepth);
+      const int slot = int(unsigned(e - lo) & unsigned(kMirDepth - 1));
       double v[6];
 #pragma unroll
       for (int k = 0; k < 6; ++k) v[k] = strip[(slot * 6 + k) * T];
@@ -540,8 +541,16 @@ __global__ void __launch_bounds__(kEdgeBlock, GBP_EDGE_MIN_BLOCKS)
       const int A = s.enbr[e];
       const bool act = s.en_ir && s.antenna[A] != 0 && s.idle[A] == 0;
       if (i == 1) s.e_act[e] = act ? 1 : 0;
-      if (!act) continue;  // undelivered: the receiver keeps the message it has
       const int64_t va = int64_t(A) * V + i, vi = r * V + i;
+      if (!act) {
+        // undelivered: the receiver keeps the message it has, and A's factor keeps the mean it already holds from
+        // this variable while this variable's belief moves on (robot.rs:1851): freeze it
+        if (!(s.e_frozen[e] & 1)) {
+          s.mu_frozen[m] = s.mu_ext[s.at<2>(0, vi)];
+          s.mu_frozen[s.EV + m] = s.mu_ext[s.at<2>(1, vi)];
+        }
+        continue;
+      }
       const double a0 = pubr[s.at<kRec>(20, va)], a1 = pubr[s.at<kRec>(21, va)];
       const uint32_t epochA = s.pub_epoch[p][va], birth = s.e_birth[e];
       const bool frozen = (s.e_frozen[e] & 1) != 0;
@@ -650,11 +659,13 @@ GBP_DEV void iterate_warp(const Store &s, const int p, const uint32_t epoch, con
     // where the own factors' messages sit in the inbox order (id.rs:25-61): after the mirror
     // factors of lower-id robots, before those of higher-id robots
     const int64_t eadd = elow < e1 ? elow : e1;
+#if !GBP_EDGE_SPLIT
     double mu_sent[2] = {0.0, 0.0};
     if (e1 > e0) {
       mu_sent[0] = s.mu_ext[s.at<2>(0, vi)];
       mu_sent[1] = s.mu_ext[s.at<2>(1, vi)];
     }
+#endif
 #if GBP_EDGE_SPLIT
     // the neighbours' factors have been evaluated by k_edge_messages: every edge's message (new, or the one kept
     // because nothing was delivered) sits in Store::mir
@@ -665,14 +676,8 @@ GBP_DEV void iterate_warp(const Store &s, const int p, const uint32_t epoch, con
         },
         [](int64_t) { return false; },
         [&](int64_t e, const double(&v)[6]) {
+          // (an undelivered edge's mean was frozen by k_edge_messages)
           if (add_mirror_values(v, ae, al) && e - e0 < 64) mir_ne |= 1ull << (e - e0);
-          // undelivered: A's factor keeps the mean it already holds from this variable while this variable's belief
-          // moves on (robot.rs:1851): freeze it
-          if (!s.e_act[e] && !(s.e_frozen[e] & 1)) {
-            const int64_t m = e * (V - 1) + (i - 1);
-            s.mu_frozen[m] = mu_sent[0];
-            s.mu_frozen[s.EV + m] = mu_sent[1];
-          }
         });
 #else
     int A_next = (e0 < e1) ? s.enbr[e0] : 0;
