@@ -134,3 +134,52 @@ def test_export_data_has_the_reference_shape():
     assert set(r0["messages"]["sent"]) == {"internal", "external"} and r0["messages"]["sent"]["internal"] > 0
     assert len(r0["positions"]) == 8 and set(r0["velocities"][0]) == {"velocity", "timestamp", "measured_over"}
     assert back["gbp"]["iterations"] == {"internal": sw.cfg.iterations_internal, "external": sw.cfg.iterations_external}
+
+
+@pytest.mark.parametrize("name, obstacle_factors", [("Collaborative Complex", True), ("Structured Junction Twoway", False)])
+def test_reference_scenarios_with_their_tile_colliders_and_trackers(name, obstacle_factors):
+    """The reference's own scenario inputs (tests/golden/scenarios.json) with the evaluation systems running every tick:
+    the tile colliders of the scenario's environment (map_generator.rs:537-1298), the environment-collision monitor and
+    the position / velocity trackers at the reference's 100 ms period.  The junction run also gets a bollard on the
+    crossing (and no Obstacle factors), so that collisions begin and end; either way engine == oracle."""
+    from oracle import oracle as O
+
+    sc = scenarios.ReferenceScenario(name)
+    g, o = World(sc.cfg), OracleWorld(sc.cfg)
+    g.set_sdf_from_environment(sc.env)
+    o.set_sdf(O.env_to_sdf_image(sc.env))
+    cols = tile_colliders(sc.env)
+    assert len(cols) > 3
+    if not obstacle_factors:
+        cols = cols + [Collider("ball", (0.0, 0.0), 0.0, radius=4.0)]  # a bollard on the crossing: the lanes pass it
+    rng = np.random.default_rng(0)
+    ticks = 60 if obstacle_factors else 95  # the first robots reach the crossing after ~70 ticks
+    events = sc.spawn_events(ticks)
+    dt_ns = int(round(float(sc.cfg.delta_t) * 1e9))
+    for w in (g, o):
+        w.set_environment_colliders(cols)
+        w.set_tracking_buffers(capacity=16, sample_ns=100_000_000)
+        if not obstacle_factors:
+            w.change_factor_enabled(2, 0)
+    totals = (0, 0)
+    for tick in range(ticks):
+        for _, k in [e for e in events if e[0] == tick]:
+            sw = sc.spawn(k, rng)
+            for w in (g, o):
+                sw.add_to(w, set_sdf=False)
+        if g.num_robots == 0:
+            continue
+        for w in (g, o):
+            w.step()
+        tg, to = g.update_environment_collisions(), o.update_environment_collisions()
+        assert tg == to, f"{name} tick {tick}"
+        totals = tg
+        for w in (g, o):
+            w.track(dt_ns, (tick + 1) * float(sc.cfg.delta_t))
+    assert np.array_equal(g.read_environment_collisions(), o.read_environment_collisions())
+    for r, (a, b) in enumerate(zip(g.read_tracks(), o.read_tracks())):
+        for x, y in zip(a, b):
+            assert x.shape == y.shape and np.array_equal(x, y), (name, r)
+    assert g.num_robots >= 12 and len(g.read_tracks()[0][0]) >= 2
+    if not obstacle_factors:
+        assert totals[0] > 0, "the lanes of the junction pass the bollard"
