@@ -642,6 +642,19 @@ __global__ void k_sdf_lookup(Store s, int m, const double *xy, uint32_t *px, uin
   val[t] = gbp::sdf_measure(s, xy[2 * t], xy[2 * t + 1], px + t, py + t);
 }
 
+// Store::ell_*: the first kEll edge heads of every own robot at fixed positions (gbp_store.cuh).
+__global__ void k_ell_fill(Store s) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= int64_t(s.Nloc) * gbp::kEll) return;
+  const int64_t r = t / gbp::kEll, e = s.eoff[r] + (t - r * gbp::kEll);
+  const bool ok = e < s.eoff[r + 1];
+  s.ell_nbr[t] = ok ? s.enbr[e] : -1;
+  if (ok) {
+    s.ell_birth[t] = s.e_birth[e];
+    s.ell_dsafe[t] = s.e_dsafe[e];
+  }
+}
+
 __global__ void k_set_dsafe(Store s, double mult) {
   const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (r >= s.Nloc) return;
@@ -1567,6 +1580,17 @@ void bind_edge_set(gbp_world *w) {
   s.EV = e.cap * (s.V - 1);
 }
 
+// Store::ell_* follows the live CSR: after every change of the edge lists, of the neighbour slots or of the safety
+// distances.
+int refresh_ell(gbp_world *w) {
+  Store &s = w->s;
+  if (!s.ell_nbr || s.Nloc == 0 || !s.eoff) return 0;
+  k_ell_fill<<<blocks_for(int64_t(s.Nloc) * gbp::kEll, 256), 256, 0, w->stream>>>(s);
+  CK(cudaGetLastError());
+  w->launches += 1;
+  return 0;
+}
+
 void free_edge_set(gbp_world *w, EdgeSet *e) {
   if (e->egid != e->enbr) cudaFree(e->egid);
   cudaFree(e->enbr); cudaFree(e->e_own); cudaFree(e->e_dsafe); cudaFree(e->e_rnum); cudaFree(e->e_birth);
@@ -1722,6 +1746,11 @@ int reserve_robots(gbp_world *w, int64_t newcap) {
   CK(regrow(s.next_wp, 1, oldcap, newcap, keep, st));
   CK(regrow(s.coll_hits, 1, oldcap, newcap, keep, st));
   CK(regrow(s.nlow, 1, oldcap, newcap, keep, st));
+#if GBP_AXIS_ELL
+  CK(regrow(s.ell_nbr, 1, oldcap * gbp::kEll, newcap * gbp::kEll, keep * gbp::kEll, st));
+  CK(regrow(s.ell_birth, 1, oldcap * gbp::kEll, newcap * gbp::kEll, keep * gbp::kEll, st));
+  CK(regrow(s.ell_dsafe, 1, oldcap * gbp::kEll, newcap * gbp::kEll, keep * gbp::kEll, st));
+#endif
   s.NV = newNV;
   s.cap = newcap;
   // ghost slots were dropped by the re-stride: the next topology pass rebuilds them
@@ -2046,7 +2075,7 @@ int topo_apply(gbp_world *w, const int64_t (*hdr)[4]) {
   w->send_po = w->tp.send_po;
   w->force_rebuild = false;
   mark_halo_stale(w);
-  return 0;
+  return refresh_ell(w);
 }
 
 // Every shard learns every robot's Transform (x, z), radius and despawned flag: 16 bytes per robot per tick.
@@ -2476,7 +2505,7 @@ void gbp_world_destroy(gbp_world_t *w) {
   void *ptrs[] = {s.prior_eta, s.prior_lam, s.pub[0], s.pub[1], s.pub_epoch[0], s.pub_epoch[1], s.bel_ext,
                   s.mu_ext, s.cov, s.valid, s.cov_lazy, s.mode, s.gen_list, s.gen_count, s.m_dynL[0], s.m_dynL[1], s.m_dynR[0], s.m_dynR[1], s.m_obs, s.m_trk, s.dyn_c,
                   s.trk_record, s.trk_timeout, s.trk_seed, s.trk_last, s.trk_value, s.radius, s.t0, s.pos, s.antenna,
-                  s.idle, s.finished, s.gone, s.latest, s.iter_factor, s.gid, s.next_wp, s.coll_hits, w->coll_totals, s.wp_off, s.wp_xy, s.eoff,
+                  s.idle, s.finished, s.gone, s.latest, s.iter_factor, s.gid, s.next_wp, s.coll_hits, s.ell_nbr, s.ell_birth, s.ell_dsafe, w->coll_totals, s.wp_off, s.wp_xy, s.eoff,
                   s.nlow, w->t_nlow, w->t_result_dev, w->sdf_dev, w->t_cx,
                   w->t_cz, w->t_box, w->t_park, w->q_wnbr, w->q_maxlost, w->q_woff, w->q_zombie, w->t_idx, w->t_idx_sorted, w->t_keys, w->t_keys_sorted, w->t_cnt, w->t_off,
                   w->t_newcnt, w->t_newoff, w->t_cub, w->rb_dev, w->gpos, w->t_gflag, w->t_gslot, w->t_sflag,
@@ -2864,6 +2893,7 @@ int gbp_world_add_robots(gbp_world_t *w, int32_t n, const float *radii, const ui
     w->launches += 1;
     s.dyn_tab = w->dyn_tab_dev;
   }
+  if (int rc = refresh_ell(w)) return rc;  // the new robots have no edges yet
   CK(cudaStreamSynchronize(st));  // staging vectors go out of scope
   cudaFree(d_mu);
   return 0;
@@ -3581,6 +3611,7 @@ int gbp_world_set_safety_distance_multiplier(gbp_world_t *w, float multiplier) {
     k_set_dsafe<<<blocks_for(w->s.Nloc, 128), 128, 0, w->stream>>>(w->s, double(multiplier));
     CK(cudaGetLastError());
     w->launches += 1;
+    if (int rc = refresh_ell(w)) return rc;
   }
   return 0;
 }

@@ -208,6 +208,12 @@ GBP_DEV void cp_async8(double *smem, const double *gmem) {
                : "memory");
 #endif
 }
+GBP_DEV void cp_async4(void *smem, const void *gmem) {
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(unsigned(__cvta_generic_to_shared(smem))), "l"(gmem)
+               : "memory");
+#endif
+}
 GBP_DEV void cp_async_commit() {
 #ifdef __CUDA_ARCH__
   asm volatile("cp.async.commit_group;" ::: "memory");

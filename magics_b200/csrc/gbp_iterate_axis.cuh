@@ -60,6 +60,13 @@ constexpr int kAxisBatch = GBP_AXIS_BATCH;
 #ifndef GBP_AXIS_DYN_PAIR
 #define GBP_AXIS_DYN_PAIR 0  // 1: the two Dynamic messages of a variable as one straight-line block (two inverses in flight)
 #endif
+#ifndef GBP_AXIS_ELL
+#define GBP_AXIS_ELL 0  // 1: the first kEll edge heads come from Store::ell_* (a fixed-position copy kept by k_ell_fill) in the
+                        // FIRST wave of loads, by cp.async straight into the staging arrays, instead of waiting for
+                        // eoff[r]; the frozen bit of an edge is read with the neighbour's data in the third wave.
+                        // Bit-identical (110 GPU tests), one dependent load level fewer — and 3.4 % slower: 84 B of
+                        // spills at the 96-register cap (profiles/README.md r02v6).  Off; the copy is not even built.
+#endif
 #ifndef GBP_AXIS_PREFETCH
 #define GBP_AXIS_PREFETCH 0  // CTAs ahead whose wave-1 rows this CTA pulls into L2 (592 = 148 SMs x 4 resident CTAs:
                              // +1.5 % DRAM bytes, no time gained — profiles/README.md r02e/r02f; off)
@@ -236,6 +243,11 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
   bool own_ne = false;
   double pe[2] = {0.0, 0.0}, pl = 0.0, mu[2] = {0.0, 0.0}, pos = 0.0, vel = 0.0;
   double mu_sent[2] = {0.0, 0.0};
+#if GBP_AXIS_ELL
+  const bool use_ell = 2 * V >= kEll;  // every ELL slot has a lane (any V >= 4)
+#else
+  const bool use_ell = false;
+#endif
   double eRec[2] = {0.0, 0.0}, LRec[4] = {0.0, 0.0, 0.0, 0.0};
   double eL[2] = {0.0, 0.0}, LL[4] = {0.0, 0.0, 0.0, 0.0}, eR[2] = {0.0, 0.0}, LR[4] = {0.0, 0.0, 0.0, 0.0};
 #if !GBP_AXIS_MARK_SHFL
@@ -267,6 +279,15 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
     if (EXT) {
       mu_sent[0] = s.mu_ext[s.at<2>(0, vi)];
       mu_sent[1] = s.mu_ext[s.at<2>(1, vi)];
+#if GBP_AXIS_ELL
+      if (use_ell && 2 * i + a < kEll) {  // straight into the staging arrays: no register waits for them
+        const int64_t q = r * kEll + (2 * i + a);
+        const int k = rl * kAxisEdges + 2 * i + a;  // slots past the robot's last edge hold -1 and are never read
+        cp_async4(hd_nbr + k, s.ell_nbr + q);
+        cp_async4(hd_birth + k, s.ell_birth + q);
+        cp_async8(hd_dsafe + k, s.ell_dsafe + q);
+      }
+#endif
     }
   }
   // ---- wave 2: edge heads, Dynamic-factor constants ------------------------------------------------
@@ -274,10 +295,11 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
   const int ne = ne_all < kAxisEdges ? ne_all : kAxisEdges;
   if (EXT && live) {
     for (int k = 2 * i + a; k < ne; k += 2 * V) {
+      if (use_ell && k < kEll) continue;
       const int64_t e = eo0 + k;
       hd_nbr[rl * kAxisEdges + k] = s.enbr[e];
       hd_birth[rl * kAxisEdges + k] = s.e_birth[e];
-      hd_frozen[rl * kAxisEdges + k] = s.e_frozen[e];
+      if (!use_ell) hd_frozen[rl * kAxisEdges + k] = s.e_frozen[e];
       hd_dsafe[rl * kAxisEdges + k] = s.e_dsafe[e];
     }
   }
@@ -290,6 +312,12 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
     mu[0] = s.bel_ext[qp.v + 20 * kTile];
     mu[1] = s.bel_ext[qp.v + 22 * kTile];
   }
+#if GBP_AXIS_ELL
+  if (EXT) {
+    cp_async_commit();
+    cp_async_wait<0>();
+  }
+#endif
   __syncthreads();
 
   const bool work = live && !was_general && !skipped;
@@ -307,12 +335,15 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
   double m0[kAxisBatch] = {}, m1[kAxisBatch] = {};
   uint32_t epA[kAxisBatch] = {};
   unsigned onA = 0u;  // bit q: neighbour q of the batch has its radio on and is not idle
+  unsigned frzA = 0u; // bit q: edge q of the batch is frozen (use_ell: read here, else staged with the heads)
   auto fetch = [&](int b0) {
     onA = 0u;
+    frzA = 0u;
 #pragma unroll
     for (int q = 0; q < kAxisBatch; ++q) {
       const int k = (b0 + q < nmine) ? a + 2 * (b0 + q) : a;  // past the end: a valid edge again, result unused
       const int A = hd_nbr[rl * kAxisEdges + k];
+      if (use_ell) frzA |= (s.e_frozen[eo0 + k] & 1) ? (1u << q) : 0u;
       const int64_t va = int64_t(A) * V + i;
       m0[q] = pubr[s.at<kRec>(20, va)];
       m1[q] = pubr[s.at<kRec>(21, va)];
@@ -389,7 +420,7 @@ __global__ void __maxnreg__(GBP_AXIS_MAXREG)
         const int k = a + 2 * (b0 + q);
         const bool act = s.en_ir && ((onA >> q) & 1u);
         const uint32_t birth = hd_birth[rl * kAxisEdges + k];
-        const bool frozen = (hd_frozen[rl * kAxisEdges + k] & 1) != 0;
+        const bool frozen = use_ell ? ((frzA >> q) & 1u) != 0u : (hd_frozen[rl * kAxisEdges + k] & 1) != 0;
         const double dsafe = hd_dsafe[rl * kAxisEdges + k];
         flip |= frozen == act;  // bit 0 has to end up as !act
         if (act) {

@@ -34,6 +34,8 @@
 
 namespace gbp {
 
+constexpr int kEll = 8;  // edge heads per robot in the fixed-position copy (Store::ell_*)
+
 constexpr int kRec = 24;  // eta 0..3, lambda 4..19 (row major), mu 20..23
 
 #ifndef GBP_TILED
@@ -114,6 +116,12 @@ struct Store {
   uint32_t *e_birth;   // [E]   epoch at which the edge was created
   uint8_t *e_frozen;   // [E]   bit 0: A's factor holds an older mean of B than mu_ext (see mu_frozen);
                        //       bit 1: CollisionState::Colliding of the pair (planner/collisions.rs:455-493)
+  // The first kEll edge heads of every robot once more, at fixed positions (slot k of robot r at r * kEll + k): the hot
+  // kernel can ask for them in its first wave of loads instead of waiting for eoff[r] first.  Rebuilt from the CSR
+  // whenever it changes (k_ell_fill); a missing edge has ell_nbr = -1.
+  int32_t *ell_nbr;    // [cap * kEll] neighbour slot
+  uint32_t *ell_birth; // [cap * kEll]
+  double *ell_dsafe;   // [cap * kEll]
   uint8_t *e_act;      // [E]   1: the neighbour's radio is on and it is not idle — written by k_edge_messages for the
                        //       robots k_iterate runs in the same sub-step, read there (scratch: not carried over a rebuild)
   uint32_t *coll_hits; // [cap] per robot: collisions it has been part of (RobotRobotCollisions::get)
