@@ -254,36 +254,47 @@ def scenario_point(name: str, ticks: int, cores: int) -> dict:
     from oracle.oracle import OracleWorld
 
     sc = scenarios.ReferenceScenario(name)
-    g, o = World(sc.cfg, device=0), OracleWorld(sc.cfg, threads=cores)
+    # g: the default path (a launch per half-step); f: the same world with the whole iterate_gbp in one cooperative
+    # launch (gbp_world_set_iterate_path(w, 2)); o: the CPU restatement
+    g, f, o = World(sc.cfg, device=0), World(sc.cfg, device=0), OracleWorld(sc.cfg, threads=cores)
+    f.set_single_launch_tick(True)
     g.set_sdf_from_environment(sc.env)
+    f.set_sdf_from_environment(sc.env)
     o.set_sdf(_oracle.env_to_sdf_image(sc.env))
     rng = np.random.default_rng(0)
     events = sc.spawn_events(ticks)
-    t_gpu = t_cpu = 0.0
+    t_gpu = t_fused = t_cpu = 0.0
     timed = 0
     for tick in range(ticks):
         for _, k in [e for e in events if e[0] == tick]:
             sw = sc.spawn(k, rng)
             if sw is not None:
-                sw.add_to(g, set_sdf=False)
-                sw.add_to(o, set_sdf=False)
+                for w in (g, f, o):
+                    sw.add_to(w, set_sdf=False)
         if g.num_robots == 0:
             continue
-        g.sync()
-        t = time.perf_counter()
-        g.step()
-        g.sync()
-        t_gpu += time.perf_counter() - t
+        for w in (g, f):
+            w.sync()
+            t = time.perf_counter()
+            w.step()
+            w.sync()
+            if w is g:
+                t_gpu += time.perf_counter() - t
+            else:
+                t_fused += time.perf_counter() - t
         t = time.perf_counter()
         o.step()
         t_cpu += time.perf_counter() - t
         timed += 1
     n = g.num_robots
     edges = int(g.read_connections()[0][-1])
+    same = bool(np.array_equal(g.read_beliefs()["mean"], f.read_beliefs()["mean"], equal_nan=True))
     g.close()
+    f.close()
     o.close()
     return {"scenario": name, "robots_at_end": n, "variables": int(sc.cfg.num_variables), "ticks_timed": timed,
             "edges_at_end": edges, "ms_per_step_gpu": t_gpu * 1e3 / max(1, timed),
+            "ms_per_step_gpu_single_launch": t_fused * 1e3 / max(1, timed), "single_launch_same_bits": same,
             "ms_per_step_cpu_port": t_cpu * 1e3 / max(1, timed), "cpu_threads": cores}
 
 

@@ -435,8 +435,11 @@ int gbp_world_node_counts(gbp_world_t *w, int64_t out[5]);
 /* Which iterate kernel runs a robot is decided on the device per launch: k_iterate_axis (two lanes per
  * variable) while the robot's x and y chains are decoupled — no InterRobot factor inside its safety
  * distance, flat SDF, no Tracking message — and k_iterate otherwise; both produce the bits of the
- * reference's update order.  general_only != 0 sends every robot through k_iterate
- * (A/B tests).  read: robots of this shard currently assigned to each kernel. */
+ * reference's update order.  general_only = 1 sends every robot through k_iterate
+ * (A/B tests); 2 does the same and runs a whole gbp_world_iterate as ONE cooperative launch (k_tick_fused) while the
+ * swarm fits the GPU at once (a few thousand robots on one GPU, no message counting / profiling) — for the
+ * reference's own scenarios of 10 - 50 robots, where a tick is otherwise 30 launches of microseconds each.
+ * read: robots of this shard currently assigned to each kernel. */
 int gbp_world_set_iterate_path(gbp_world_t *w, int32_t general_only);
 int gbp_world_read_iterate_path(gbp_world_t *w, int64_t *robots_axis, int64_t *robots_general);
 /* number of GPU kernels this handle has launched so far (bench `gpu_launches`) */

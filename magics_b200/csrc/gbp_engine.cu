@@ -1024,6 +1024,8 @@ struct gbp_world {
   bool smem_opted_in[4] = {false, false, false, false};  // k_iterate<EXT,INT> dynamic shared memory opt-in
   bool axis_opted_in[12] = {};  // k_iterate_axis<EXT,INT,PART> likewise
   bool general_only = false;  // gbp_world_set_iterate_path: every robot through k_iterate
+  bool fused_tick = false;    // gbp_world_set_iterate_path(w, 2): a whole iterate_gbp in one cooperative launch (k_tick_fused)
+  int fused_occ = 0;          // resident CTAs per SM of k_tick_fused
   bool halo_overlap = true;   // sharded: border robots first, their halo behind the interior launch (GBP_HALO_OVERLAP=0:
                               // one launch for all robots, the exchange before the next external half)
   bool use_pdl = true;        // iterate kernels launched with programmatic stream serialization (GBP_PDL=0: off)
@@ -1526,6 +1528,52 @@ int group_launch(gbp_group *g) {
 // iterate_gbp_v2 (robot.rs:1769-1861): flatten the schedule into half-steps
 // I (internal factor+variable) and E (external factor+variable); an E directly
 // followed by an I runs as one fused launch.
+// The launches of run_schedule as one cooperative launch (k_tick_fused) when the world asked for it and fits:
+// one GPU, every robot's warp resident at once, at most 64 launches, no per-launch accounting wanted.
+// Returns 1 if it ran, 0 if the caller has to launch half-step by half-step, < 0 on error.
+int try_fused_tick(gbp_group *g, const std::vector<char> &ph) {
+  gbp_world *w = g->members[0];
+  if (!w->fused_tick || g->ws != 1 || w->count_messages || w->profiling || w->s.Nloc == 0) return 0;
+  gbp::TickPlan plan{};
+  int n_int = 0;
+  for (size_t k = 0; k < ph.size();) {
+    if (plan.n >= 64) return 0;
+    const bool fused = ph[k] == 'E' && k + 1 < ph.size() && ph[k + 1] == 'I';
+    plan.ext[plan.n] = ph[k] == 'E';
+    plan.in[plan.n] = fused || ph[k] == 'I';
+    n_int += plan.in[plan.n];
+    plan.n += 1;
+    k += fused ? 2 : 1;
+  }
+  if (plan.n == 0) return 1;
+  CK(cudaSetDevice(w->device));
+  if (w->fused_occ <= 0) {
+    CK(cudaFuncSetAttribute(gbp::k_tick_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gbp::kIterSmemBytes)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w->fused_occ, gbp::k_tick_fused, gbp::kIterBlock,
+                                                     gbp::kIterSmemBytes));
+    if (w->fused_occ <= 0) return 0;
+  }
+  Store s = w->s;
+  const int rpw = 32 / s.V, wpb = gbp::kIterBlock / 32;
+  const int64_t warps = (int64_t(s.Nloc) + rpw - 1) / rpw;
+  const int64_t resident = int64_t(w->sm_count) * w->fused_occ;
+  const int64_t need = (warps + wpb - 1) / wpb;
+  if (need > resident) return 0;  // a grid barrier needs every CTA resident, and one pass per half-step
+  // the edge kernel's body shares this grid: as many warps per robot as the grid has to spare
+  int chunks = 1;
+  while (chunks < 32 && int64_t(s.Nloc) * chunks * 2 <= resident * wpb) chunks *= 2;
+  const unsigned grid = unsigned(std::max<int64_t>(need, std::min<int64_t>(resident, (int64_t(s.Nloc) * chunks + wpb - 1) / wpb)));
+  int p = w->p;
+  uint32_t epoch = w->epoch;
+  void *args[] = {&s, &p, &epoch, &chunks, &plan};
+  CK(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(gbp::k_tick_fused), dim3(grid), dim3(gbp::kIterBlock), args,
+                                 gbp::kIterSmemBytes, w->stream));
+  w->epoch += uint32_t(plan.n);
+  if (n_int & 1) w->p ^= 1;
+  w->launches += 1;
+  return 1;
+}
+
 int run_schedule(gbp_group *g, int n, const uint8_t *internal, const uint8_t *external) {
   std::vector<char> ph;
   ph.reserve(size_t(n) * 2);
@@ -1533,6 +1581,7 @@ int run_schedule(gbp_group *g, int n, const uint8_t *internal, const uint8_t *ex
     if (internal[i]) ph.push_back('I');
     if (external[i]) ph.push_back('E');
   }
+  if (int rc = try_fused_tick(g, ph)) return rc < 0 ? rc : 0;
   for (size_t k = 0; k < ph.size();) {
     int rc;
     if (ph[k] == 'E' && k + 1 < ph.size() && ph[k + 1] == 'I') {
@@ -3835,6 +3884,7 @@ int gbp_world_set_iterate_path(gbp_world_t *w0, int32_t general_only) {
   if (!w0) return fail(GBP_ERR_BAD_HANDLE, "null world");
   for (gbp_world *w : w0->grp->members) {
     w->general_only = general_only != 0;
+    w->fused_tick = general_only == 2;
     // k_iterate does not maintain Store::mode while it runs alone: every robot re-qualifies from scratch
     if (w->s.Nloc > 0) {
       CK(cudaSetDevice(w->device));

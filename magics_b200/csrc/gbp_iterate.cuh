@@ -26,6 +26,9 @@
 #pragma once
 #include "gbp_math.cuh"
 #include "gbp_store.cuh"
+#ifdef __CUDACC__
+#include <cooperative_groups.h>
+#endif
 
 namespace gbp {
 
@@ -523,17 +526,16 @@ constexpr int kEdgeBlock = 128;
 #ifndef GBP_EDGE_MIN_BLOCKS
 #define GBP_EDGE_MIN_BLOCKS 4  // 126 registers without a cap: 16 warps / SM
 #endif
-__global__ void __launch_bounds__(kEdgeBlock, GBP_EDGE_MIN_BLOCKS)
-    k_edge_messages(const __grid_constant__ Store s, const int p, const int par, const int chunks) {
+GBP_DEV void edge_messages_body(const Store &s, const int p, const int par, const int chunks) {
   // `chunks` warps share a robot's (edge, variable) pairs: 1 for a large swarm, up to 32 for a few dozen robots
   // with dozens of neighbours each (the reference's Circle Experiment), where a warp per robot would leave the
   // GPU to 30 warps walking 18 rounds each
   const int V = s.V, Vm1 = V - 1;
   const unsigned lane = threadIdx.x & 31u;
   const int64_t nrob = par >= 0 ? int64_t(s.gen_count[par]) : int64_t(s.Nloc);
-  const int64_t wstride = (int64_t(gridDim.x) * kEdgeBlock) >> 5;
+  const int64_t wstride = (int64_t(gridDim.x) * blockDim.x) >> 5;
   const double *const pubr = s.pub[p];
-  for (int64_t item = (int64_t(blockIdx.x) * kEdgeBlock + threadIdx.x) >> 5; item < nrob * chunks; item += wstride) {
+  for (int64_t item = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; item < nrob * chunks; item += wstride) {
     const int64_t k = item / chunks;
     const int chunk = int(item - k * chunks);
     const int64_t r = par >= 0 ? int64_t(s.gen_list[k]) : k;
@@ -590,6 +592,10 @@ __global__ void __launch_bounds__(kEdgeBlock, GBP_EDGE_MIN_BLOCKS)
       }
     }
   }
+}
+__global__ void __launch_bounds__(kEdgeBlock, GBP_EDGE_MIN_BLOCKS)
+    k_edge_messages(const __grid_constant__ Store s, const int p, const int par, const int chunks) {
+  edge_messages_body(s, p, par, chunks);
 }
 
 #ifdef GBP_ITER_MAXREG  // experiments: exact register cap instead of a CTAs-per-SM target
@@ -929,6 +935,54 @@ __global__ void GBP_ITER_BOUNDS
     const bool live = rl < rpw && k < nrob;
     const int64_t r = live ? (par >= 0 ? int64_t(s.gen_list[k]) : k) : 0;
     iterate_warp<EXT, INT>(s, p, epoch, r, live, rl, i, lane, par >= 0, iter_smem + threadIdx.x);
+  }
+}
+
+// ---- a whole iterate_gbp in ONE launch, for swarms that fit the GPU at once ----------------------------------------
+// The reference's own scenarios have 10 - 50 robots: there a tick is 30 kernel launches of a few microseconds of work
+// each, and launch latency is all there is.  k_tick_fused runs the launches of run_schedule back to back inside one
+// cooperative grid — k_edge_messages' body, a grid barrier, k_iterate's body (every robot, as under
+// gbp_world_set_iterate_path(general_only)), a grid barrier — with the same device functions, so the bits are those of
+// the launch-per-half-step path.  Opt-in (gbp_world_set_iterate_path(w, 2)); the host falls back to separate launches
+// when the swarm needs more warps than are resident at once.
+struct TickPlan {
+  int n;             // launches
+  uint8_t ext[64];   // launch j runs an external half
+  uint8_t in[64];    // ... and / or an internal half (both: external of sub-step t fused with internal of t + 1)
+};
+template <bool EXT, bool INT>
+GBP_DEV void iterate_all_body(const Store &s, const int p, const uint32_t epoch, double *strip) {
+  const int V = s.V;
+  const int rpw = 32 / V;
+  const unsigned lane = threadIdx.x & 31u;
+  const int rl = int(lane) / V;
+  const int i = int(lane) - rl * V;
+  const int64_t nrob = s.Nloc;
+  const int64_t nwarps = (nrob + rpw - 1) / rpw;
+  const int64_t wstride = (int64_t(gridDim.x) * kIterBlock) >> 5;
+  for (int64_t warp = (int64_t(blockIdx.x) * kIterBlock + threadIdx.x) >> 5; warp < nwarps; warp += wstride) {
+    const int64_t k = warp * rpw + rl;
+    const bool live = rl < rpw && k < nrob;
+    iterate_warp<EXT, INT>(s, p, epoch, live ? k : 0, live, rl, i, lane, false, strip);
+  }
+}
+__global__ void GBP_ITER_BOUNDS k_tick_fused(const __grid_constant__ Store s, int p, uint32_t epoch, const int chunks,
+                                             const __grid_constant__ TickPlan plan) {
+  extern __shared__ double iter_smem[];
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  double *const strip = iter_smem + threadIdx.x;
+  for (int j = 0; j < plan.n; ++j) {
+    epoch += 1;  // group_launch steps the epoch once per launch
+    const bool ext = plan.ext[j] != 0, in = plan.in[j] != 0;
+    if (ext && s.E > 0) {
+      edge_messages_body(s, p, -1, chunks);
+      grid.sync();
+    }
+    if (ext && in) iterate_all_body<true, true>(s, p, epoch, strip);
+    else if (ext) iterate_all_body<true, false>(s, p, epoch, strip);
+    else iterate_all_body<false, true>(s, p, epoch, strip);
+    if (in) p ^= 1;
+    grid.sync();
   }
 }
 

@@ -512,7 +512,12 @@ class World:
     def set_iterate_path(self, general_only: bool):
         """general_only: every robot through k_iterate (A/B tests); default: k_iterate_axis for the robots
         whose x and y chains are decoupled, decided on the device per launch."""
-        self._call("gbp_world_set_iterate_path", C.c_int32(int(bool(general_only))))
+        self._call("gbp_world_set_iterate_path", C.c_int32(int(general_only)))
+
+    def set_single_launch_tick(self, on: bool = True):
+        """A whole `iterate` as one cooperative launch (k_tick_fused) while the swarm fits the GPU at once — the
+        reference's own 10 - 50 robot scenarios; implies the general kernel for every robot."""
+        self._call("gbp_world_set_iterate_path", C.c_int32(2 if on else 0))
 
     def read_iterate_path(self):
         """(robots currently iterated by k_iterate_axis, robots iterated by k_iterate) on this shard."""

@@ -238,3 +238,37 @@ def test_step_equals_its_four_calls_made_one_by_one():
         if tick % 4 == 3 or tick in (10, 16):
             _same(a, b, f"tick {tick}")
             check(a, o, f"tick {tick}")
+
+
+@pytest.mark.parametrize("scenario", ["circle", "junction", "lattice"])
+def test_single_launch_tick_has_the_bits_of_the_launch_per_half_step_path(scenario):
+    """gbp_world_set_iterate_path(w, 2): a whole iterate_gbp as one cooperative launch (k_tick_fused) for swarms that fit
+    the GPU at once.  Same device functions, grid barriers where the launch boundaries were: the bits must be those
+    of the default path and of the oracle, for every schedule shape, with robots added and removed in between."""
+    sw = {"circle": lambda: scenarios.circle(14, 9.0), "junction": lambda: scenarios.junction_twoway(per_lane=1),
+          "lattice": lambda: scenarios.lattice(12, 9)}[scenario]()
+    a, c, o = World(sw.cfg), World(sw.cfg), OracleWorld(sw.cfg)
+    c.set_single_launch_tick(True)
+    for w in (a, c, o):
+        sw.add_to(w)
+    launches = []
+    for tick in range(16):
+        if tick == 6:
+            for w in (a, c, o):
+                w.set_schedule(0, 3, 5)  # centered, more external than internal halves: E E I E I E ...
+        if tick == 9:
+            for w in (a, c, o):
+                w.set_schedule(1, 10, 10)
+                w.remove_robots([2])
+        if tick == 11:
+            for w in (a, c, o):
+                sw.slice(0, 3).add_to(w, set_sdf=False)
+        l0 = (a.kernel_launches, c.kernel_launches)
+        for w in (a, c, o):
+            w.step()
+        launches.append((a.kernel_launches - l0[0], c.kernel_launches - l0[1]))
+        _same(a, c, f"{scenario} tick {tick}")
+        if tick % 5 == 4 or tick == 15:
+            check(c, o, f"{scenario} tick {tick}")
+    assert all(lc + 8 < la for la, lc in launches[1:]), launches  # one launch instead of ~20-30 for the iterations
+    assert c.read_iterate_path() == (0, c.num_robots)
