@@ -220,3 +220,94 @@ def tile_colliders(env: "Environment") -> list:
                 out.append(Collider("cuboid", (float(ox + offs[sx]), float(oz + offs[sz])), 0.0,
                                     half_extents=(float(dims[dx] / f(2.0)), float(dims[dz] / f(2.0)))))
     return out
+
+
+def _fma32(a, b, c):
+    """f32 mul_add: the product of two f32 is exact in f64; one rounding after the sum."""
+    return np.float32(np.float64(a) * np.float64(b) + np.float64(c))
+
+
+def _convex_hull_ccw(pts):
+    """Counter-clockwise convex hull without collinear points (what parry2d's ConvexPolygon::from_convex_hull keeps)."""
+    p = sorted({(float(x), float(y)) for x, y in pts})
+    if len(p) < 3:
+        return p
+
+    def cross(o, a, b):
+        return (a[0] - o[0]) * (b[1] - o[1]) - (a[1] - o[1]) * (b[0] - o[0])
+
+    lower, upper = [], []
+    for q in p:
+        while len(lower) >= 2 and cross(lower[-2], lower[-1], q) <= 0:
+            lower.pop()
+        lower.append(q)
+    for q in reversed(p):
+        while len(upper) >= 2 and cross(upper[-2], upper[-1], q) <= 0:
+            upper.pop()
+        upper.append(q)
+    return lower[:-1] + upper[:-1]
+
+
+def obstacle_colliders(env: "Environment") -> list:
+    """The colliders `build_obstacles` pushes for the placeable obstacles (crates/magics/src/environment/
+    map_generator.rs:141-536), f32 arithmetic in the reference's order: Circle -> Ball, Triangle -> Triangle (vertices
+    rotated by Quat::from_rotation_y(pi/2 - rotation), isometry angle -rotation), RegularPolygon / Polygon ->
+    ConvexPolygon::from_convex_hull, Rectangle -> Cuboid.  As written in the reference, the circle's and the polygon's
+    vertical placement is not mirrored like the other shapes' (`1 - y` resp. no sign flip, :186 / :389): kept.
+    glam's quaternion rotations are restated as the plane rotations they are (the last bits may differ)."""
+    f = np.float32
+    T = f(env.tile_size)
+    gox, goz = f(env.ncols) / f(2.0) - f(0.5), f(env.nrows) / f(2.0) - f(0.5)
+    half = T / f(2.0)
+    pi = f(np.pi)
+    out = []
+    for o in env.obstacles:
+        if isinstance(o, dict):
+            o = Obstacle(**o)
+        ox, oz = (f(o.col) - gox) * T, (f(o.row) - goz) * T
+        tx, ty = f(o.translation[0]), f(o.translation[1])
+        x = _fma32(tx, T, ox) - half
+        z_plain = _fma32(ty, T, oz) - half
+        rot = f(o.rotation)
+        if o.shape == "circle":
+            z = _fma32(f(1.0) - ty, T, oz) - half
+            out.append(Collider("ball", (float(x), float(z)), 0.0, radius=float(f(o.radius) * T)))
+        elif o.shape == "triangle":
+            a, b = f(o.angles[0]), f(o.angles[1])
+            c = pi - (a + b)
+            r = f(o.radius)
+            hyp = [r / np.sin(a), r / np.sin(b), r / np.sin(c)]
+            ang = [pi + a / f(2.0), -b / f(2.0), pi - b - c / f(2.0)]
+            pts = [(f(np.cos(t)) * h, f(np.sin(t)) * h) for t, h in zip(ang, hyp)]  # Triangle::points
+            pts = [(-px * T, py * T) for px, py in pts]
+            th = pi / f(2.0) - rot  # Quat::from_rotation_y(th) on (px, 0, py): x' = x cos + z sin, z' = -x sin + z cos
+            ct, st = f(np.cos(th)), f(np.sin(th))
+            rp = tuple((float(px * ct + py * st), float(-px * st + py * ct)) for px, py in pts)
+            out.append(Collider("triangle", (float(x), float(-z_plain)), float(th - pi / f(2.0)), points=rp))
+        elif o.shape == "regular-polygon":
+            n = int(o.sides)
+            off = pi + (f(0.0) if n == 4 else (pi / f(2.0) if n % 2 else -pi / f(2.0)))
+            ang = rot + off
+            ca, sa = f(np.cos(ang)), f(np.sin(ang))
+            scale = T / f(2.0)
+            pts = []
+            for i in range(n):  # RegularPolygon::point_at in f64, then `as f32`
+                t = 2.0 * np.pi / n * i + np.pi / 4.0
+                px, py = f(np.cos(t) * float(o.radius)), f(np.sin(t) * float(o.radius))
+                pts.append(((px * ca - py * sa) * scale, (px * sa + py * ca) * scale))  # Quat::from_rotation_z(ang)
+            hull = tuple(_convex_hull_ccw(pts))
+            out.append(Collider("convex-polygon", (float(x), float(-z_plain)), float(ang), points=hull))
+        elif o.shape == "polygon":
+            pts = [(f(px) * T, f(py) * T) for px, py in o.points]
+            out.append(Collider("convex-polygon", (float(x), float(z_plain)), 0.0, points=tuple(_convex_hull_ccw(pts))))
+        elif o.shape == "rectangle":
+            out.append(Collider("cuboid", (float(x), float(-z_plain)), 0.0,
+                                half_extents=(float(f(o.width) * T / f(4.0)), float(f(o.height) * T / f(4.0)))))
+        else:
+            raise ValueError(f"unknown placeable shape {o.shape!r}")
+    return out
+
+
+def colliders(env: "Environment") -> list:
+    """Everything `Colliders` holds after the map has been generated: tile walls, then placeable obstacles."""
+    return tile_colliders(env) + obstacle_colliders(env)

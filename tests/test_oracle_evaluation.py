@@ -146,3 +146,54 @@ def test_trackers_fire_on_the_timer_and_overwrite_the_oldest_sample():
         want = (pos[k] - pos[k - 1]) / np.float32(vo[k])
         assert np.array_equal(vel[k], want.astype(np.float32))
     assert np.allclose(vo, np.diff([t * 0.03 for t in fired[-5:]]))
+
+
+def _inside(c, X, Z):
+    """float64 point-in-shape for a Collider over coordinate arrays."""
+    a = c.angle
+    dx, dz = X - c.translation[0], Z - c.translation[1]
+    lx, ly = np.cos(a) * dx + np.sin(a) * dz, -np.sin(a) * dx + np.cos(a) * dz
+    if c.kind == "ball":
+        return lx * lx + ly * ly <= c.radius ** 2
+    if c.kind == "cuboid":
+        return (np.abs(lx) <= c.half_extents[0]) & (np.abs(ly) <= c.half_extents[1])
+    pts = np.asarray(c.points)
+    s = np.array([(pts[(k + 1) % len(pts)][0] - pts[k][0]) * (ly - pts[k][1]) -
+                  (pts[(k + 1) % len(pts)][1] - pts[k][1]) * (lx - pts[k][0]) for k in range(len(pts))])
+    return (s >= 0).all(axis=0) | (s <= 0).all(axis=0)
+
+
+def test_placeable_obstacle_colliders_against_the_sdf_rasteriser(golden_dir):
+    """map_generator.rs:141-536 (colliders) and env_to_png (SDF image) place the same obstacles from two code paths.
+    On the reference's `Obstacle Shapes Showcase` they coincide for the circle, the rectangle, the squares and the
+    unrotated triangle; regular polygons with 3, 5, 6, 7 sides and the rotated triangle keep their area but the two
+    reference paths orient them differently (the collider path rotates the vertices AND the isometry) — restated as
+    written, so only the area is asserted for those."""
+    import json
+    import os
+
+    from magics_b200.environment import Obstacle, obstacle_colliders
+
+    gold = json.load(open(os.path.join(golden_dir, "env_to_png.json")))
+    e = dict(gold["environments_with_obstacles"]["Obstacle Shapes Showcase"])
+    e.update(expansion=0.0, blur=0.0, resolution=1000)
+    e["obstacles"] = [Obstacle(**o) for o in e["obstacles"]]
+    env = Environment(**e)
+    dark = O.env_to_sdf_image(env)[:, :, 0] < 128
+    H, W = dark.shape
+    Ww, Hw = env.world_size
+    ys, xs = np.mgrid[0:H, 0:W]
+    X, Z = (xs + 0.5) / W * Ww - Ww / 2, Hw / 2 - (ys + 0.5) / H * Hw
+    cols = obstacle_colliders(env)
+    assert [c.kind for c in cols].count("convex-polygon") == 10 and len(cols) == 14
+    union = np.zeros_like(dark)
+    for o, c in zip(env.obstacles, cols):
+        m = _inside(c, X, Z)
+        union |= m
+        same_orientation = o.shape in ("circle", "rectangle") or (o.shape == "regular-polygon" and o.sides == 4) or \
+            (o.shape == "triangle" and o.rotation == 0.0)
+        if same_orientation:
+            assert (m & dark).sum() >= 0.995 * m.sum(), (o.shape, o.sides)
+        else:
+            assert (m & dark).sum() >= 0.55 * m.sum(), (o.shape, o.sides)  # same place, other orientation
+    assert abs(int(union.sum()) - int(dark.sum())) <= 0.01 * dark.sum()  # areas agree shape by shape
