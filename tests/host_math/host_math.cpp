@@ -3,6 +3,7 @@
 #define GBP_HOST_MATH_TEST 1
 #include "../../magics_b200/csrc/gbp_math.cuh"
 #include "../../magics_b200/csrc/gbp_math_axis.cuh"
+#include "../../magics_b200/csrc/gbp_collide.cuh"
 
 extern "C" {
 int hm_inv4(const double *m, double *out) {
@@ -83,5 +84,13 @@ int hm_dyn_message_axis(int keep, int a, double dt, double qs, int other_nonempt
   for (int k = 0; k < 2; ++k) eta[k] = re[k];
   for (int k = 0; k < 4; ++k) lam[k] = rl[k];
   return ok ? 1 : 0;
+}
+// gbp_collide.cuh: the device predicate of the environment-collision monitor (collider_hits_ball), one collider
+// (kind, tx, ty, cos, sin, radius, hx, hy, first vertex, vertex count) against n robot balls.
+int hm_collider_hits(int kind, float tx, float ty, float re, float im, float radius, float hx, float hy, int nv,
+                     const float *verts, int n, const float *xz, float robot_radius, unsigned char *out) {
+  const gbp::ColliderDev c{kind, tx, ty, re, im, radius, hx, hy, 0, nv};
+  for (int k = 0; k < n; ++k) out[k] = gbp::collider_hits_ball(c, verts, xz[2 * k], xz[2 * k + 1], robot_radius) ? 1 : 0;
+  return 0;
 }
 }

@@ -26,7 +26,8 @@ def _build(tag: str, flags: list[str]) -> C.CDLL:
     out = os.path.join(out_dir, f"libhost_math_{tag}.so")
     deps = [SRC, os.path.join(HERE, "host_math", "host_math_shim.h"),
             os.path.join(HERE, "..", "magics_b200", "csrc", "gbp_math.cuh"),
-            os.path.join(HERE, "..", "magics_b200", "csrc", "gbp_math_axis.cuh")]
+            os.path.join(HERE, "..", "magics_b200", "csrc", "gbp_math_axis.cuh"),
+            os.path.join(HERE, "..", "magics_b200", "csrc", "gbp_collide.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(out) < os.path.getmtime(d) for d in deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
                         "-I", os.path.join(HERE, "host_math")] + flags + ["-o", out, SRC], check=True)
@@ -372,3 +373,51 @@ def test_dyn_message_axis_has_the_bits_of_dyn_message(libs):
         else:
             assert oks[0] == oks[1] or ok == 0
     assert n_ok > 4000
+
+
+# ---- gbp_collide.cuh: the environment-collision predicate of the engine against the oracle's restatement of
+# parry2d's intersection_test — two independent sources, every shape kind, bit-equal booleans incl. rim points
+def test_collider_predicate_of_the_engine_equals_the_oracle_restatement(libs):
+    dev, _, _ = libs
+    from magics_b200 import scenarios
+    from magics_b200.environment import Collider
+    from oracle.oracle import OracleWorld
+
+    rng = np.random.default_rng(21)
+    R = np.float32(0.6)
+    hexagon = tuple((float(np.float32(1.5 * np.cos(k * np.pi / 3))), float(np.float32(1.5 * np.sin(k * np.pi / 3))))
+                    for k in range(6))
+    cols = [Collider("ball", (3.0, -2.0), 0.0, radius=1.25),
+            Collider("cuboid", (-4.0, 1.0), 0.7, half_extents=(2.0, 0.5)),
+            Collider("cuboid", (0.0, -6.0), 0.0, half_extents=(3.0, 1.0)),
+            Collider("triangle", (0.5, 5.0), 0.7, points=((-1.0, -0.5), (2.0, -0.5), (0.3, 1.7))),
+            Collider("triangle", (5.0, -5.0), -2.1, points=((2.0, -0.5), (-1.0, -0.5), (0.3, 1.7))),  # clockwise
+            Collider("convex-polygon", (6.0, 6.0), -0.7, points=hexagon)]
+    pts = rng.uniform(-9, 11, size=(20000, 2)).astype(np.float32)
+    # rim: points at exactly the robot radius from a face / corner / ball, and their f32 neighbours
+    rim = [(3.0 + 1.25 + R, -2.0), (3.0 + R, -6.0), (0.0, -5.0 + R), (-3.0 - R, -7.0 - R), (3.0, -5.0 + R)]
+    k = 0
+    for x, z in rim:
+        for dx in (-1, 0, 1):
+            pts[k] = (np.nextafter(np.float32(x), np.float32(np.inf * dx)) if dx else np.float32(x), np.float32(z))
+            k += 1
+    sw = scenarios.circle(len(pts), 10.0, robot_radius=float(R))
+    sw.positions[:] = pts
+    o = OracleWorld(sw.cfg)
+    sw.add_to(o)
+    kinds = {"ball": 0, "cuboid": 1, "triangle": 2, "convex-polygon": 3}
+    F = C.POINTER(C.c_float)
+    for c in cols:
+        o.set_environment_colliders([c])
+        o.update_environment_collisions()
+        want = o.read_environment_collisions().astype(np.uint8)
+        verts = np.ascontiguousarray(c.points if c.points else [(0.0, 0.0)], np.float32)
+        got = np.zeros(len(pts), np.uint8)
+        a = np.float32(c.angle)
+        dev.hm_collider_hits(kinds[c.kind], C.c_float(c.translation[0]), C.c_float(c.translation[1]),
+                             C.c_float(float(np.cos(a))), C.c_float(float(np.sin(a))), C.c_float(c.radius),
+                             C.c_float(c.half_extents[0]), C.c_float(c.half_extents[1]), len(c.points),
+                             verts.ctypes.data_as(F), len(pts), pts.ctypes.data_as(F), C.c_float(float(R)),
+                             got.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        assert np.array_equal(got, want), (c.kind, int((got != want).sum()))
+        assert 10 < want.sum() < len(pts) - 10
