@@ -202,3 +202,29 @@ def test_reference_scripts_read_the_export_unchanged(junction_export, tmp_path):
     for rid in ids:
         want = ev["robots"][rid]["path_deviation"]
         assert (np.isnan(want) and np.isnan(got[rid])) or abs(got[rid] - want) <= 6e-4, (rid, got[rid], want)
+
+
+def test_export_data_over_a_world_like_object_keeps_the_old_keys():
+    """`export_data(world, ...)` as tests/test_gpu_evaluation.py calls it (no mission clock, no colliders): the keys of
+    the first version of the export stay where they were."""
+    from magics_b200.export import export_data
+
+    class FakeWorld:
+        num_robots = 2
+        cfg = scenarios.circle(2, 8.0).cfg
+
+        def export_totals(self):
+            tr = (np.array([[0.0, 1.0], [2.0, 3.0]], np.float32), np.array([[4.0, 5.0]], np.float32), np.array([0.25]),
+                  np.array([0.05]))
+            return {"collisions_robots": np.array([1, 0], np.uint32), "next_waypoint": np.array([1, 2], np.int32),
+                    "removed": np.array([False, True]), "collisions_environment": np.array([0, 3], np.uint32),
+                    "tracks": [tr, tr], "messages": {"sent": {"internal": np.array([7, 8]), "external": np.array([1, 2])},
+                                                      "received": {"internal": np.array([5, 6]), "external": np.array([3, 4])}}}
+
+    d = json.loads(json.dumps(export_data(FakeWorld(), scenario="s", makespan=1.0, radii=[1.0, 2.0], prng_seed=3,
+                                          waypoints=[[(0, 0), (1, 1)], [(2, 2), (3, 3)]])))
+    r1 = d["robots"]["1"]
+    assert r1["mission"] == {"waypoints": [[2.0, 2.0], [3.0, 3.0]], "next_waypoint": 2, "despawned": True}
+    assert r1["collisions"] == {"robots": 0, "environment": 3} and r1["messages"]["received"] == {"internal": 6, "external": 4}
+    assert r1["velocities"] == [{"velocity": [4.0, 0.0, 5.0], "timestamp": 0.25, "measured_over": {"secs": 0, "nanos": 50_000_000}}]
+    assert d["obstacles"] == {} and d["prng_seed"] == 3 and d["gbp"]["iterations"]["internal"] == FakeWorld.cfg.iterations_internal
