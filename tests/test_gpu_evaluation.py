@@ -136,6 +136,50 @@ def test_export_data_has_the_reference_shape():
     assert back["gbp"]["iterations"] == {"internal": sw.cfg.iterations_internal, "external": sw.cfg.iterations_external}
 
 
+def test_exported_mission_run_equals_the_oracles_and_evaluates():
+    """A whole mission run exported: 12 robots through the junction (3 waypoints each), `reached_waypoint` on the device
+    feeding the host's Mission / Route clocks (magics_b200/mission.py; robot.rs:331-490, 815-1012), robot-robot monitor
+    and 100 ms trackers every tick.  The engine's `ExportData` equals the one assembled from the oracle's read-backs key
+    for key, and the reference's evaluation metrics (magics_b200/metrics.py; pinned to the reference's own scripts in
+    tests/test_metrics_host.py) come out of it."""
+    from magics_b200 import metrics
+    from magics_b200.export import export_from_totals
+    from magics_b200.mission import MissionClock, secs_f64
+
+    sw = scenarios.junction_twoway(per_lane=1)
+    g, o = _both(sw)
+    for w in (g, o):
+        w.set_tracking_buffers(capacity=256, sample_ns=100_000_000)
+    clock = MissionClock()
+    clock.spawn([sw.wp_xy[sw.wp_offsets[r]:sw.wp_offsets[r + 1]] for r in range(sw.n)], started_at=0.0)
+    dt_ns = int(round(sw.cfg.delta_t * 1e9))
+    task, fin = (2, 4, 1, 6.0), (2, 99, 1, 3.0)
+    ticks = 150
+    for tick in range(1, ticks + 1):
+        rg, ro = g.reached_waypoint(task, fin), o.reached_waypoint(task, fin)
+        assert np.array_equal(rg, ro), f"tick {tick}"
+        clock.observe(rg, tick * dt_ns)
+        for w in (g, o):
+            w.step()
+            w.update_robot_collisions()
+            w.track(dt_ns, secs_f64(tick * dt_ns))
+    assert clock.next_waypoint_index() == g.read_waypoint_index().tolist() == o.read_waypoint_index().tolist()
+    kw = dict(scenario="Structured Junction Twoway", makespan=ticks * dt_ns * 1e-9, radii=sw.radii, missions=clock,
+              now_ns=ticks * dt_ns)
+    dg = export_data(g, **kw)
+    oracle_totals = {"collisions_robots": o.read_robot_collisions(), "next_waypoint": o.read_waypoint_index(),
+                     "removed": np.zeros(sw.n, bool), "collisions_environment": None, "tracks": o.read_tracks(),
+                     "messages": None}
+    do = export_from_totals(oracle_totals, sw.n, sw.cfg, **kw)
+    assert json.loads(json.dumps(dg)) == json.loads(json.dumps(do))
+    r0 = dg["robots"]["0"]
+    assert len(r0["positions"]) == ticks and set(r0["mission"]) >= {"waypoints", "started_at", "finished_at", "routes"}
+    ev = metrics.evaluate(dg, projection="segments")
+    assert ev["ldj"]["robots"] == sw.n and all(np.isfinite(e["ldj"]) and 30.0 < e["distance_travelled"] < 140.0 and
+                                               e["path_deviation"] < 3.0 for e in ev["robots"].values())
+    assert sum(m.completed for m in clock.missions) >= sw.n // 2
+
+
 @pytest.mark.parametrize("name, obstacle_factors", [("Collaborative Complex", True), ("Structured Junction Twoway", False)])
 def test_reference_scenarios_with_their_tile_colliders_and_trackers(name, obstacle_factors):
     """The reference's own scenario inputs (tests/golden/scenarios.json) with the evaluation systems running every tick:
