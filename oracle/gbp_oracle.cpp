@@ -124,7 +124,13 @@ Mat matmul(const Mat &A, const Mat &B) {
   for (int i = 0; i < A.r; ++i)
     for (int j = 0; j < B.c; ++j) {
       double acc = 0.0;
+#ifdef GBPO_FMA_MATMUL
+      // sensitivity build only (Makefile target `fma`): matrixmultiply's x86-64 dgemm kernels with the `fma` feature
+      // detected at run time accumulate with fused multiply-adds; everything else stays rounded per operation.
+      for (int k = 0; k < A.c; ++k) acc = std::fma(A(i, k), B(k, j), acc);
+#else
       for (int k = 0; k < A.c; ++k) acc = acc + A(i, k) * B(k, j);
+#endif
       C(i, j) = acc;
     }
   return C;

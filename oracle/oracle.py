@@ -51,7 +51,28 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+def build_fma() -> str:
+    """The FMA-contracted sensitivity build (Makefile target `fma`); never the parity checker."""
+    src = os.path.join(_HERE, "gbp_oracle.cpp")
+    out = os.path.join(_HERE, "_build", "libgbp_oracle_fma.so")
+    if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-s", "fma"], check=True)
+    return out
+
+
+def lib_fma():
+    """A second, independent instance of the library compiled with fused multiply-adds."""
+    global _lib_fma
+    if _lib_fma is None:
+        _lib_fma = C.CDLL(build_fma())
+        _lib_fma.gbpo_create.restype = C.c_void_p
+        _lib_fma.gbpo_create.argtypes = [C.c_void_p]
+        _lib_fma.gbpo_read_connections.restype = C.c_int64
+    return _lib_fma
+
+
 _lib = None
+_lib_fma = None
 
 
 def lib():
@@ -134,11 +155,11 @@ def env_to_sdf_image(env) -> np.ndarray:
 class OracleWorld:
     """Same surface as magics_b200.World, executed by the CPU restatement."""
 
-    def __init__(self, cfg, threads: int = 1):
+    def __init__(self, cfg, threads: int = 1, fma: bool = False):
         self._cfg = OracleConfig(**{f[0]: getattr(cfg, f[0]) for f in OracleConfig._fields_})
-        self._h = lib().gbpo_create(C.byref(self._cfg))
+        self._lib = lib_fma() if fma else lib()
+        self._h = self._lib.gbpo_create(C.byref(self._cfg))
         self.V = int(cfg.num_variables)
-        self._lib = lib()
         self._lib.gbpo_set_threads(C.c_void_p(self._h), threads)
 
     def close(self):
