@@ -296,6 +296,17 @@ int gbp_world_update_environment_collisions(gbp_world_t *w, int64_t *num_collisi
 /* RobotEnvironmentCollisions::get(entity) for every own robot: per_robot[n]. */
 int gbp_world_read_environment_collisions(gbp_world_t *w, uint32_t *per_robot);
 
+/* Which collider, and where (host functions, no device needed; gbp_collide_host.cpp).  The monitors above count; the
+ * reference also keeps one entry per pair that ever hit with the Aabb intersection of every hit (collisions.rs:402-431,
+ * :700-716, exported by export.rs:171-206, :552-555).  Hits are rare, so the host derives those entries from the
+ * counters that moved (magics_b200/collisions.py) and asks these two about the few robots concerned.
+ * hits_ball: out[k] = parry2d intersection_test(collider, Ball(radii[k]) at robots_xz[k]) — the very predicate
+ * k_env_collisions runs, compiled for the host from the same header.  aabb: Collider::aabb()
+ * (gbp_global_planner/src/lib.rs:94-98) as mins_maxs = {min x, min z, max x, max z}. */
+int gbp_collider_hits_ball(const gbp_collider_t *collider, int32_t num_vertices, const float *vertices_xy, int32_t m,
+                           const float *robots_xz, const float *radii, uint8_t *out);
+int gbp_collider_aabb(const gbp_collider_t *collider, int32_t num_vertices, const float *vertices_xy, float *mins_maxs);
+
 /* ---- PositionTracker / VelocityTracker (planner/tracking.rs:36-260) ------------------------------
  * Every robot carries two ring buffers of `capacity` samples and a repeating Timer of `sample_ns`
  * (spawner.rs:627-628: 10000 samples, 100 ms).  Memory: 32 bytes x capacity x robots on the device. */

@@ -21,7 +21,9 @@
 #pragma once
 #include <cstdint>
 
+#ifndef GBP_DEV  // gbp_collide_host.cpp compiles the predicate below for the host and defines GBP_DEV itself
 #include "gbp_math.cuh"
+#endif
 
 namespace gbp {
 

@@ -4,7 +4,8 @@ The reference serialises, per robot: radius, positions (PositionTracker::positio
 (VelocityTracker::measurements), collisions {robots, environment}, messages {sent, received} x {internal, external},
 mission {waypoints, started_at, finished_at, routes}, planning_strategy, color; and globally scenario, makespan, delta_t,
 gbp.iterations, prng_seed, config, obstacles, collisions, goal_areas.  What lives outside the iteration path (theme
-colours, goal areas, the TOML config, the per-collision Aabb lists) is passed in by the caller or left out; the keys and
+colours, goal areas, the TOML config) is passed in by the caller or left out; the top-level `collisions` entry lists
+(one entry per pair that ever hit, with the Aabb of every hit) come from a `magics_b200.collisions.CollisionLog`; the keys and
 nesting of what is present follow the reference, and with a `magics_b200.mission.MissionClock` fed during the run the
 reference's own consumers (scripts/ldj.py, scripts/distance-travelled.py, scripts/perpendicular-path-deviation.py) read
 the JSON unchanged — tests/test_metrics_host.py runs them on it.  `magics_b200.metrics` computes the same numbers.
@@ -55,7 +56,7 @@ def obstacles_data(colliders) -> dict:
 def export_from_totals(t: dict, n: int, cfg, *, scenario: str = "", makespan: float = 0.0, delta_t: float | None = None,
                        iterations: tuple | None = None, prng_seed: int = 0, radii=None, waypoints=None,
                        planning_strategy: str = "only-local", robot_ids=None, missions=None, now_ns: int | None = None,
-                       colors=None, colliders=None) -> dict:
+                       colors=None, colliders=None, collision_log=None) -> dict:
     """Dict shaped like the reference's `ExportData` from the read-backs in `t` (`World.export_totals`).
 
     radii / waypoints: the per-robot inputs the caller gave `add_robots` (the engine does not read them back);
@@ -63,7 +64,8 @@ def export_from_totals(t: dict, n: int, cfg, *, scenario: str = "", makespan: fl
     missions + now_ns: a `magics_b200.mission.MissionClock` fed during the run and the fixed clock at export time — fills
     `mission.started_at / finished_at / routes` (export.rs:381-409), which scripts/ldj.py and
     scripts/perpendicular-path-deviation.py read; colors: per-robot "#rrggbb" (`format_color`); colliders: see
-    `obstacles_data`."""
+    `obstacles_data`; collision_log: a `magics_b200.collisions.CollisionLog` fed during the run — fills the top-level
+    `collisions: {robots, environment}` entry lists (export.rs:208-214, :552-555), keyed like `robots` / `obstacles`."""
     ids = list(range(n)) if robot_ids is None else list(robot_ids)
     robots = {}
     for r in range(n):
@@ -92,10 +94,16 @@ def export_from_totals(t: dict, n: int, cfg, *, scenario: str = "", makespan: fl
             "color": colors[r] if colors is not None else "#000000",
         }
     it = iterations if iterations is not None else (cfg.iterations_internal, cfg.iterations_external)
-    return {"scenario": scenario, "makespan": float(makespan),
-            "delta_t": float(cfg.delta_t if delta_t is None else delta_t),
-            "gbp": {"iterations": {"internal": int(it[0]), "external": int(it[1])}},
-            "robots": robots, "prng_seed": int(prng_seed), "obstacles": obstacles_data(colliders)}
+    out = {"scenario": scenario, "makespan": float(makespan),
+           "delta_t": float(cfg.delta_t if delta_t is None else delta_t),
+           "gbp": {"iterations": {"internal": int(it[0]), "external": int(it[1])}},
+           "robots": robots, "prng_seed": int(prng_seed), "obstacles": obstacles_data(colliders)}
+    if collision_log is not None:
+        data = collision_log.collision_data(robot_ids=None if robot_ids is None else ids)
+        for e in data["environment"]:  # `obstacles` is keyed by position in the collider list, as a string
+            e["obstacle"] = str(e["obstacle"])
+        out["collisions"] = data
+    return out
 
 
 def export_data(world, **kw) -> dict:

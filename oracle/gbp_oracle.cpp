@@ -865,6 +865,13 @@ struct World {
   std::map<std::pair<int, int>, bool> env_state;  // (robot, collider) -> CollisionState::Colliding
   std::vector<uint32_t> env_hits;
   int64_t env_collisions = 0;
+  // CollisionHistory::aabbs (collisions.rs:463-470): one Aabb per Hit, pushed by record_aabb_when_two_robots_collide /
+  // record_aabb_when_robot_collides_with_environment (:700-716) from the events the update systems send
+  struct CollEvent {
+    int a, b;       // robot-robot: the map key (r, c), r < c; robot-environment: (robot, collider index)
+    float aabb[4];  // mins x, mins z, maxs x, maxs z of the intersection
+  };
+  std::vector<CollEvent> robot_events, env_events;
   // PositionTracker / VelocityTracker per robot (planner/tracking.rs:36-200)
   int track_capacity = 0;
   uint64_t track_duration_ns = 0;
@@ -1709,6 +1716,47 @@ int gbpo_reached_waypoint(void *p, const int32_t *crit, const float *meters, uin
   }
   return 0;
 }
+// Ball::aabb(&Isometry2::translation(x, z)) (parry2d shape/ball.rs -> bounding_volume::ball_aabb): centre -+ radius.
+static void ball_aabb(const float pos[2], float radius, float out[4]) {
+  out[0] = pos[0] - radius;
+  out[1] = pos[1] - radius;
+  out[2] = pos[0] + radius;
+  out[3] = pos[1] + radius;
+}
+// Aabb::intersection (bounding_volume/aabb.rs): sup of the mins, inf of the maxs (None when they cross; the reference
+// unwraps / expects right after a positive intersection test, so the box is kept as computed).
+static void aabb_intersection(const float a[4], const float b[4], float out[4]) {
+  out[0] = std::max(a[0], b[0]);
+  out[1] = std::max(a[1], b[1]);
+  out[2] = std::min(a[2], b[2]);
+  out[3] = std::min(a[3], b[3]);
+}
+// Collider::aabb = shape.compute_aabb(&isometry) (gbp_global_planner/src/lib.rs:94-98; parry2d, PARITY UNPINNED):
+// Ball: translation -+ radius; Cuboid: translation -+ |R| half_extents; Triangle / ConvexPolygon: min / max over the
+// vertices moved by the isometry (rotation (re x - im y, im x + re y), then the translation).
+static void collider_aabb(const EnvCollider &c, float out[4]) {
+  out[0] = out[1] = out[2] = out[3] = 0.0f;
+  if (c.kind == 0 || c.kind == 1) {
+    float hx = c.radius, hy = c.radius;
+    if (c.kind == 1) {
+      hx = std::fabs(c.re) * c.half_extents.x + std::fabs(c.im) * c.half_extents.y;
+      hy = std::fabs(c.im) * c.half_extents.x + std::fabs(c.re) * c.half_extents.y;
+    }
+    out[0] = c.translation.x - hx;
+    out[1] = c.translation.y - hy;
+    out[2] = c.translation.x + hx;
+    out[3] = c.translation.y + hy;
+    return;
+  }
+  for (size_t k = 0; k < c.points.size(); ++k) {
+    const V2 p = c.points[k];
+    const float x = (c.re * p.x - c.im * p.y) + c.translation.x, y = (c.im * p.x + c.re * p.y) + c.translation.y;
+    out[0] = k ? std::min(out[0], x) : x;
+    out[1] = k ? std::min(out[1], y) : y;
+    out[2] = k ? std::max(out[2], x) : x;
+    out[3] = k ? std::max(out[3], y) : y;
+  }
+}
 // update_robot_robot_collisions (planner/collisions.rs:72-143): ALL pairs (r < c) in robot order;
 // parry2d BoundingSphere::intersects (un-vendored crate, restated: |c_b - c_a|^2 <= (r_a + r_b)^2 in
 // f32); CollisionHistory::update (:472-488): Free -> Colliding is a Hit.
@@ -1730,6 +1778,13 @@ int gbpo_update_robot_collisions(void *p, int64_t *num_collisions, int64_t *coll
         w->collisions += 1;
         w->coll_hits[r] += 1;
         w->coll_hits[c] += 1;
+        // :117-138: r_aabb.intersection(&c_aabb) travels in the event and lands in the pair's history (:190-196)
+        World::CollEvent ev{r, c, {0, 0, 0, 0}};
+        float ra[4], ca[4];
+        ball_aabb(a.pos, a.radius, ra);
+        ball_aabb(b.pos, b.radius, ca);
+        aabb_intersection(ra, ca, ev.aabb);
+        w->robot_events.push_back(ev);
       }
       state = now;
       if (now) ++now_count;
@@ -2024,6 +2079,7 @@ int gbpo_set_environment_colliders(void *p, int n, const float *cols, int nverts
   w->env_state.clear();
   w->env_hits.clear();
   w->env_collisions = 0;
+  w->env_events.clear();
   for (int k = 0; k < n; ++k) {
     const float *c = cols + 9 * k;
     EnvCollider e;
@@ -2055,6 +2111,13 @@ int gbpo_update_environment_collisions(void *p, int64_t *num_collisions, int64_t
       if (now && !state) {  // CollisionStatus::Hit
         w->env_collisions += 1;
         w->env_hits[r] += 1;
+        // :417-426: robot_aabb.intersection(&env_aabb)
+        World::CollEvent ev{r, c, {0, 0, 0, 0}};
+        float ra[4], ca[4];
+        ball_aabb(rb.pos, rb.radius, ra);
+        collider_aabb(w->colliders[c], ca);
+        aabb_intersection(ra, ca, ev.aabb);
+        w->env_events.push_back(ev);
       }
       state = now;
       if (now) ++now_count;
@@ -2064,6 +2127,25 @@ int gbpo_update_environment_collisions(void *p, int64_t *num_collisions, int64_t
   if (colliding_now) *colliding_now = now_count;
   if (per_robot)
     for (int r = 0; r < n; ++r) per_robot[r] = w->env_hits[r];
+  return 0;
+}
+// Every Hit so far in the order the update systems produced them: kind 0 robot-robot (pairs = (r, c), r < c), kind 1
+// robot-environment (pairs = (robot, collider)); aabbs [k][4].  Returns the number of events (fills at most `cap`).
+int64_t gbpo_read_collision_events(void *p, int kind, int64_t cap, int32_t *pairs, float *aabbs) {
+  World *w = static_cast<World *>(p);
+  const std::vector<World::CollEvent> &ev = kind == 0 ? w->robot_events : w->env_events;
+  for (int64_t k = 0; k < int64_t(ev.size()) && k < cap; ++k) {
+    if (pairs) {
+      pairs[2 * k] = ev[size_t(k)].a;
+      pairs[2 * k + 1] = ev[size_t(k)].b;
+    }
+    if (aabbs) std::memcpy(aabbs + 4 * k, ev[size_t(k)].aabb, sizeof(float) * 4);
+  }
+  return int64_t(ev.size());
+}
+int gbpo_read_removed(void *p, uint8_t *out) {
+  World *w = static_cast<World *>(p);
+  for (size_t k = 0; k < w->robots.size(); ++k) out[k] = w->robots[k].gone ? 1 : 0;
   return 0;
 }
 int gbpo_set_tracking_buffers(void *p, int capacity, uint64_t sample_ns) {

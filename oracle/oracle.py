@@ -272,6 +272,21 @@ class OracleWorld:
         self._call("gbpo_read_waypoint_index", _p(out, C.c_int32))
         return out
 
+    def read_removed(self):
+        out = np.zeros(self.num_robots, np.uint8)
+        self._call("gbpo_read_removed", _p(out, C.c_uint8))
+        return out
+
+    def read_collision_events(self, kind: int):
+        """Every Hit so far with its Aabb intersection (CollisionHistory::aabbs, collisions.rs:463-470, :700-716):
+        kind 0 robot-robot -> pairs (r, c), r < c; kind 1 robot-environment -> (robot, collider index)."""
+        self._lib.gbpo_read_collision_events.restype = C.c_int64
+        n = self._lib.gbpo_read_collision_events(C.c_void_p(self._h), C.c_int(kind), C.c_int64(0), None, None)
+        pairs, aabbs = np.zeros((max(n, 1), 2), np.int32), np.zeros((max(n, 1), 4), np.float32)
+        self._lib.gbpo_read_collision_events(C.c_void_p(self._h), C.c_int(kind), C.c_int64(n), _p(pairs, C.c_int32),
+                                             _p(aabbs, C.c_float))
+        return pairs[:n], aabbs[:n]
+
     def update_prior_of_horizon_state(self):
         self._call("gbpo_update_prior_of_horizon_state")
 

@@ -1,0 +1,176 @@
+"""The entry lists of RobotRobotCollisions / RobotEnvironmentCollisions (planner/collisions.rs:117-138, :417-426,
+:463-470, :700-716; exported by export.rs:171-214, :552-555) without a GPU.
+
+`magics_b200.collisions.CollisionLog` derives them from a world's counters; here the world is the ORACLE (it has the
+monitor methods of `magics_b200.World`), which also records every Hit with its Aabb itself — so the log's logic is
+checked entry for entry, box for box.  The predicate the log asks about robot-environment pairs
+(`gbp_collider_hits_ball`) and `gbp_collider_aabb` are host functions of the product library: they run here.
+tests/test_gpu_zz_collision_pairs.py repeats the comparison with the engine as the world."""
+import ctypes as C
+import json
+
+import numpy as np
+import pytest
+
+from magics_b200 import scenarios
+from magics_b200.collisions import CollisionLog, collider_aabbs
+from magics_b200.environment import Collider, Environment, pack_colliders, tile_colliders
+from magics_b200.export import export_from_totals
+from magics_b200.world import load_library
+from oracle.oracle import OracleWorld
+
+
+def entries_of(pairs, aabbs):
+    out = {}
+    for (a, b), box in zip(pairs.tolist(), aabbs):
+        out.setdefault((a, b), []).append(box)
+    return out
+
+
+def assert_same_entries(log_entries, oracle_events, what):
+    want = entries_of(*oracle_events)
+    assert set(log_entries) == set(want), f"{what}: pairs {sorted(set(log_entries) ^ set(want))}"
+    for k in want:
+        assert len(log_entries[k]) == len(want[k]), (what, k)
+        for got, ref in zip(log_entries[k], want[k]):
+            assert np.array_equal(np.asarray(got, np.float32), ref), (what, k, got, ref)
+
+
+SHAPES = [Collider("ball", (3.0, -2.0), 0.0, radius=1.25),
+          Collider("cuboid", (-4.0, 1.0), 0.7, half_extents=(2.0, 0.5)),
+          Collider("cuboid", (0.0, -6.0), 0.0, half_extents=(3.0, 1.0)),
+          Collider("triangle", (0.5, 5.0), 0.7, points=((-1.0, -0.5), (2.0, -0.5), (0.3, 1.7))),
+          Collider("convex-polygon", (6.0, 6.0), -0.7,
+                   points=tuple((float(1.5 * np.cos(k * np.pi / 3)), float(1.5 * np.sin(k * np.pi / 3))) for k in range(6)))]
+
+
+def test_host_predicate_of_the_library_equals_the_oracles_incl_rim_points():
+    """gbp_collider_hits_ball (gbp_collide.cuh compiled for the host inside libgbp_b200.so) against the oracle's
+    restatement of parry2d's intersection_test: random points and points at exactly one robot radius from a face."""
+    rng = np.random.default_rng(3)
+    R = np.float32(0.6)
+    pts = rng.uniform(-9, 11, size=(5000, 2)).astype(np.float32)
+    rim = [(3.0 + 1.25 + R, -2.0), (3.0, -2.0 + 1.25 + R), (3.0 + R, -6.0), (0.0, -5.0 + R), (-3.0 - R, -7.0 - R),
+           (3.0 + R * np.float32(np.sqrt(0.5)), -5.0 + R * np.float32(np.sqrt(0.5)))]
+    pts[: len(rim)] = np.asarray(rim, np.float32)
+    sw = scenarios.circle(len(pts), 10.0, robot_radius=float(R))
+    sw.positions[:] = pts
+    o = OracleWorld(sw.cfg)
+    sw.add_to(o)
+    lib = load_library()
+    arr, verts, _ = pack_colliders(SHAPES)
+    radii = np.full(len(pts), R, np.float32)
+    for k, c in enumerate(SHAPES):
+        o.set_environment_colliders([c])
+        o.update_environment_collisions()
+        want = o.read_environment_collisions().astype(bool)
+        out = np.zeros(len(pts), np.uint8)
+        rc = lib.gbp_collider_hits_ball(C.byref(arr[k]), C.c_int32(verts.shape[0]), verts.ctypes.data_as(C.POINTER(C.c_float)),
+                                        C.c_int32(len(pts)), pts.ctypes.data_as(C.POINTER(C.c_float)),
+                                        radii.ctypes.data_as(C.POINTER(C.c_float)), out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        assert rc == 0
+        assert np.array_equal(out.astype(bool), want), c.kind
+        assert want.sum() > 20
+    bad = arr[0].__class__(7, (C.c_float * 2)(0, 0), 0.0, 1.0, (C.c_float * 2)(0, 0), 0, 0)
+    assert lib.gbp_collider_hits_ball(C.byref(bad), 0, None, 0, None, None, None) == -2  # GBP_ERR_BAD_ARGUMENT
+
+
+def test_collider_aabbs_contain_their_shapes_tightly():
+    """Collider::aabb against float64 geometry: ball centre -+ r, |R| half extents, min / max of the moved vertices."""
+    boxes = collider_aabbs(SHAPES)
+    for c, box in zip(SHAPES, boxes):
+        a = float(np.float32(c.angle))
+        rot = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+        if c.kind == "ball":
+            pts = np.asarray(c.translation) + c.radius * np.array([[-1, -1], [1, 1]])
+        elif c.kind == "cuboid":
+            hx, hy = c.half_extents
+            pts = np.array([[-hx, -hy], [hx, -hy], [hx, hy], [-hx, hy]]) @ rot.T + np.asarray(c.translation)
+        else:
+            pts = np.asarray(c.points) @ rot.T + np.asarray(c.translation)
+        want = np.concatenate([pts.min(axis=0), pts.max(axis=0)])
+        assert np.allclose(box, want, rtol=0, atol=2e-6), (c.kind, box, want)
+
+
+@pytest.mark.parametrize("interrobot", [0, 1])
+def test_robot_robot_entries_equal_the_oracles(interrobot):
+    """Circle swarm driving through its centre (InterRobot factors off: they collide, several pairs per tick, pairs
+    that part and hit again), every tick through the log."""
+    sw = scenarios.circle(8, circle_radius=8.0, robot_radius=1.0)
+    sw.cfg.enable_interrobot = interrobot
+    o = OracleWorld(sw.cfg)
+    sw.add_to(o)
+    log = CollisionLog(o, sw.radii)
+    for tick in range(70):
+        o.step()
+        total, now = log.update_robot_collisions()
+        if tick == 40:
+            o.remove_robots([2])  # a despawned robot leaves the query; its pairs stop being updated
+    assert_same_entries(log.robot_entries, o.read_collision_events(0), "robot-robot")
+    if not interrobot:
+        assert total >= 4 and len(log.robot_entries) >= 4
+        assert sum(len(v) for v in log.robot_entries.values()) == total
+    d = log.collision_data()
+    assert [set(e) for e in d["robots"]] == [{"robot_a", "robot_b", "aabbs"}] * len(log.robot_entries)
+    for e in d["robots"]:
+        assert e["robot_a"] < e["robot_b"] and all(set(b) == {"mins", "maxs"} for b in e["aabbs"])
+        assert all(b["mins"][0] <= b["maxs"][0] and b["mins"][1] <= b["maxs"][1] for b in e["aabbs"])
+
+
+def test_robot_environment_entries_equal_the_oracles_with_robots_added_and_removed():
+    """The '+' junction's tile colliders plus a ball in the middle, Obstacle factors off: robots drive over the walls,
+    enter and leave colliders, a second swarm is spawned mid-run and two robots despawn."""
+    env = Environment(grid=["┼"], tile_size=100.0, path_width=0.1325)
+    cols = tile_colliders(env) + [Collider("ball", (0.0, 0.0), 0.0, radius=2.0)] + SHAPES[3:]
+    sw = scenarios.circle(12, 45.0, robot_radius=1.0)
+    o = OracleWorld(sw.cfg)
+    sw.add_to(o)
+    o.change_factor_enabled(2, 0)
+    o.set_environment_colliders(cols)
+    log = CollisionLog(o, sw.radii, cols)
+    seen_now = []
+    for tick in range(140):
+        o.step()
+        total, now = log.update_environment_collisions()
+        log.update_robot_collisions()
+        seen_now.append(now)
+        if tick == 30:
+            sw.add_to(o, set_sdf=False)
+            log.add_robots(sw.radii)
+        if tick == 60:
+            o.remove_robots([1, 13])
+    assert total >= 12 and max(seen_now) > min(seen_now)
+    assert_same_entries(log.environment_entries, o.read_collision_events(1), "robot-environment")
+    assert_same_entries(log.robot_entries, o.read_collision_events(0), "robot-robot")
+    assert sum(len(v) for v in log.environment_entries.values()) == total
+    # and in the export: top-level `collisions`, obstacles keyed like the `obstacles` table
+    n = o.num_robots
+    totals = {"collisions_robots": o.read_robot_collisions(), "next_waypoint": o.read_waypoint_index(),
+              "removed": o.read_removed(), "collisions_environment": o.read_environment_collisions(), "tracks": None,
+              "messages": None}
+    d = json.loads(json.dumps(export_from_totals(totals, n, sw.cfg, scenario="junction", colliders=cols,
+                                                 collision_log=log)))
+    assert set(d["collisions"]) == {"robots", "environment"}
+    assert len(d["collisions"]["environment"]) == len(log.environment_entries)
+    assert all(e["obstacle"] in d["obstacles"] and str(e["robot"]) in d["robots"] for e in d["collisions"]["environment"])
+    # per-robot counts of the export are the sums over the robot's entries (RobotEnvironmentCollisions::get)
+    for r in range(n):
+        mine = sum(len(e["aabbs"]) for e in d["collisions"]["environment"] if e["robot"] == r)
+        assert mine == d["robots"][str(r)]["collisions"]["environment"]
+
+
+def test_a_monitor_update_that_bypasses_the_log_is_noticed():
+    """Hits that began AND ended behind the log's back cannot be reconstructed: it raises instead of exporting a guess."""
+    sw = scenarios.circle(8, circle_radius=8.0, robot_radius=1.0)
+    sw.cfg.enable_interrobot = 0
+    o = OracleWorld(sw.cfg)
+    sw.add_to(o)
+    log = CollisionLog(o, sw.radii)
+    for tick in range(200):
+        o.step()
+        total, now = o.update_robot_collisions()  # not through the log
+        if total > 0 and now == 0:
+            break
+    assert total > 0 and now == 0
+    with pytest.raises(RuntimeError, match="out of step"):
+        log.update_robot_collisions()
