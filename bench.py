@@ -523,6 +523,14 @@ def main():
                    "sample": f"{swc.n} robots of the {args.workload} workload, 1 sim tick ({substeps} sub-steps), "
                              f"best of 2 after warm-up, {secs * 1e3:.1f} ms; C++ restatement of the reference "
                              "algorithm (Rust toolchain absent)"}
+            try:  # "also report the 1-thread figure" - a quarter of the sample, one timed tick
+                sw1, _ = build_workload(args.workload, max(64, args.cpu_robots // 4))
+                v1, secs1, _ = run_cpu(sw1, 1, 1)
+                cpu["value_1_thread"] = v1
+                cpu["sample_1_thread"] = f"{sw1.n} robots, 1 sim tick after warm-up, {secs1 * 1e3:.1f} ms, 1 thread"
+            except Exception as e:  # the extra figure must never cost the bench line
+                cpu["value_1_thread"] = None
+                cpu["sample_1_thread"] = f"failed: {e}"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
