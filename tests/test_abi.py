@@ -30,6 +30,15 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), f"{s} declared in include/gbp_b200.h but not exported"
 
 
+def test_integration_listing_names_every_function_of_the_header():
+    """INTEGRATION.md section 1 is the `-sys` crate a maintainer pastes: no entry point may be missing from it."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    listing = text[text.index("```rust"):text.index("## 2.")]
+    bound = set(re.findall(r"pub fn (gbp_[a-z0-9_]+)\s*\(", listing))
+    assert set(declared_symbols()) <= bound, sorted(set(declared_symbols()) - bound)
+    assert bound <= set(declared_symbols()), sorted(bound - set(declared_symbols()))
+
+
 def test_config_struct_layout_matches_header():
     # 11 x 4-byte scalars, 4 x u8, 3 x i32, 2 x f64, 1 x i32 (+ tail padding) with natural alignment
     assert ctypes.sizeof(CConfig) == 88
