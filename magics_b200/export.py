@@ -65,7 +65,8 @@ def export_from_totals(t: dict, n: int, cfg, *, scenario: str = "", makespan: fl
     `mission.started_at / finished_at / routes` (export.rs:381-409), which scripts/ldj.py and
     scripts/perpendicular-path-deviation.py read; colors: per-robot "#rrggbb" (`format_color`); colliders: see
     `obstacles_data`; collision_log: a `magics_b200.collisions.CollisionLog` fed during the run — fills the top-level
-    `collisions: {robots, environment}` entry lists (export.rs:208-214, :552-555), keyed like `robots` / `obstacles`."""
+    `collisions: {robots, environment}` entry lists (export.rs:208-214, :552-555); robot and obstacle ids are the numbers whose
+    strings key `robots` / `obstacles`."""
     ids = list(range(n)) if robot_ids is None else list(robot_ids)
     robots = {}
     for r in range(n):
@@ -99,10 +100,9 @@ def export_from_totals(t: dict, n: int, cfg, *, scenario: str = "", makespan: fl
            "gbp": {"iterations": {"internal": int(it[0]), "external": int(it[1])}},
            "robots": robots, "prng_seed": int(prng_seed), "obstacles": obstacles_data(colliders)}
     if collision_log is not None:
-        data = collision_log.collision_data(robot_ids=None if robot_ids is None else ids)
-        for e in data["environment"]:  # `obstacles` is keyed by position in the collider list, as a string
-            e["obstacle"] = str(e["obstacle"])
-        out["collisions"] = data
+        # `Entity` serialises as a number: scripts/plot-robot-positions.py:197-200 compares collision['obstacle'] with
+        # int(key of `obstacles`), so the obstacle stays the integer position in the collider list
+        out["collisions"] = collision_log.collision_data(robot_ids=None if robot_ids is None else ids)
     return out
 
 

@@ -158,4 +158,10 @@ def evaluate(data: dict, projection: str = "lines") -> dict:
             out[key] = summary(vals)
     out["collisions"] = {k: sum(int(e["collisions"].get(k, 0)) for e in per_robot.values())
                          for k in ("robots", "environment")}
+    if isinstance(data.get("collisions"), dict):
+        # `collisions()` of the thesis notebooks (analyse-structured-junction-twoway.ipynb, analyse-collaborative-complex
+        # .ipynb, analyse-environment-collisions.ipynb, analyse-comms-failure.ipynb): the NUMBER OF ENTRIES, i.e. of
+        # pairs that ever hit — a pair that parts and hits again counts once here and twice in the totals above
+        out["collision_entries"] = {"interrobot": len(data["collisions"].get("robots", [])),
+                                    "environment": len(data["collisions"].get("environment", []))}
     return out

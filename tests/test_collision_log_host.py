@@ -152,7 +152,15 @@ def test_robot_environment_entries_equal_the_oracles_with_robots_added_and_remov
                                                  collision_log=log)))
     assert set(d["collisions"]) == {"robots", "environment"}
     assert len(d["collisions"]["environment"]) == len(log.environment_entries)
-    assert all(e["obstacle"] in d["obstacles"] and str(e["robot"]) in d["robots"] for e in d["collisions"]["environment"])
+    assert all(str(e["obstacle"]) in d["obstacles"] and str(e["robot"]) in d["robots"] for e in d["collisions"]["environment"])
+    # what the reference's consumers do with it: plot-robot-positions.py:197-200 (obstacle == int(key)), and the
+    # notebooks' collisions() = number of entries
+    hit_obstacles = {entity for entity in d["obstacles"] for c in d["collisions"]["environment"] if c["obstacle"] == int(entity)}
+    assert hit_obstacles == {str(c) for _, c in log.environment_entries}
+    from magics_b200 import metrics
+    ev = metrics.evaluate(d)
+    assert ev["collision_entries"] == {"interrobot": len(log.robot_entries), "environment": len(log.environment_entries)}
+    assert ev["collisions"]["environment"] == total >= ev["collision_entries"]["environment"]
     # per-robot counts of the export are the sums over the robot's entries (RobotEnvironmentCollisions::get)
     for r in range(n):
         mine = sum(len(e["aabbs"]) for e in d["collisions"]["environment"] if e["robot"] == r)
@@ -174,3 +182,60 @@ def test_a_monitor_update_that_bypasses_the_log_is_noticed():
     assert total > 0 and now == 0
     with pytest.raises(RuntimeError, match="out of step"):
         log.update_robot_collisions()
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference/scripts"),
+                    reason="the reference tree exists only in the build container")
+def test_reference_plot_script_reads_obstacles_and_collision_entries_unchanged(tmp_path):
+    """scripts/plot-robot-positions.py, run as a program on an exported run with obstacles and collision entries: the
+    one reference consumer that walks `collisions.environment` next to `obstacles` (:193-208, red = an obstacle that was
+    hit).  matplotlib / plotly are not in this image and are mocked; the colour each obstacle patch gets is recorded."""
+    import subprocess
+    import sys
+
+    from magics_b200.mission import MissionClock
+
+    env = Environment(grid=["┼"], tile_size=100.0, path_width=0.1325)
+    cols = tile_colliders(env) + [Collider("ball", (0.0, 0.0), 0.0, radius=2.0)]
+    sw = scenarios.circle(6, 45.0, robot_radius=1.0)
+    o = OracleWorld(sw.cfg)
+    sw.add_to(o)
+    o.change_factor_enabled(2, 0)
+    o.set_environment_colliders(cols)
+    o.set_tracking_buffers(capacity=256, sample_ns=100_000_000)
+    clock = MissionClock()
+    clock.spawn([sw.wp_xy[sw.wp_offsets[r]:sw.wp_offsets[r + 1]] for r in range(sw.n)], started_at=0.0)
+    log = CollisionLog(o, sw.radii, cols)
+    dt_ns = int(round(sw.cfg.delta_t * 1e9))
+    for tick in range(1, 61):
+        o.step()
+        log.update_environment_collisions()
+        log.update_robot_collisions()
+        o.track(dt_ns, tick * dt_ns * 1e-9)
+    assert log.environment_entries
+    totals = {"collisions_robots": o.read_robot_collisions(), "next_waypoint": o.read_waypoint_index(),
+              "removed": o.read_removed(), "collisions_environment": o.read_environment_collisions(),
+              "tracks": o.read_tracks(), "messages": None}
+    data = export_from_totals(totals, sw.n, sw.cfg, scenario="junction", radii=sw.radii, colliders=cols, missions=clock,
+                              now_ns=60 * dt_ns, collision_log=log, colors=["#1e66f5"] * sw.n)
+    path = tmp_path / "run.json"
+    path.write_text(json.dumps(data))
+    runner = (
+        "import sys, runpy, json\n"
+        "from unittest import mock\n"
+        "mpl, plotly = mock.MagicMock(name='matplotlib'), mock.MagicMock(name='plotly')\n"
+        "sys.modules.update({'matplotlib': mpl, 'matplotlib.pyplot': mpl.pyplot, 'plotly': plotly,\n"
+        "                    'plotly.graph_objects': plotly.graph_objects})\n"
+        "fig, ax = mock.MagicMock(), mock.MagicMock()\n"
+        "mpl.pyplot.subplots.return_value = (fig, ax)\n"
+        "script = sys.argv[1]; sys.argv = sys.argv[1:]\n"
+        "runpy.run_path(script, run_name='__main__')\n"
+        "patches = [c.kwargs.get('color') for c in mpl.pyplot.Circle.call_args_list + mpl.pyplot.Polygon.call_args_list]\n"
+        "print('PATCH_COLOURS ' + json.dumps(patches))\n")
+    p = subprocess.run([sys.executable, "-c", runner, "/root/reference/scripts/plot-robot-positions.py", "-i", str(path),
+                        "-o", str(tmp_path / "out.svg")], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = [ln for ln in p.stdout.splitlines() if ln.startswith("PATCH_COLOURS ")][0]
+    colours = json.loads(line[len("PATCH_COLOURS "):])
+    assert len(colours) == len(cols)
+    assert colours.count("red") == len({c for _, c in log.environment_entries}) >= 1  # one red patch per obstacle hit
