@@ -1,9 +1,8 @@
-"""The export's collision entry lists with the ENGINE as the world (the file sorts last on purpose: it was added after
-the last GPU visit of round 2 — every piece of it is verified without a GPU in tests/test_collision_log_host.py, and the
-engine's counters it feeds on are the ones tests/test_gpu_mission.py and tests/test_gpu_evaluation.py compare with the
-oracle; the two runs below are the scenarios of those verified tests, so only engine paths that have run on a B200 are
-exercised — despawn and mid-run spawn under the robot-robot monitor are covered on the CPU side only).  `CollisionLog` over `magics_b200.World` must produce the entries, box for box, that the oracle records itself
-(planner/collisions.rs:117-138, :417-426, :700-716; export.rs:171-214, :552-555)."""
+"""The export's collision entry lists with the ENGINE as the world: `CollisionLog` over `magics_b200.World` must produce
+the entries, box for box, that the oracle records itself (planner/collisions.rs:117-138, :417-426, :700-716;
+export.rs:171-214, :552-555).  The log's logic is checked without a GPU in tests/test_collision_log_host.py (despawn and
+mid-run spawn under the robot-robot monitor included); the two runs here are the scenarios of the monitor tests in
+tests/test_gpu_mission.py / tests/test_gpu_evaluation.py.  Verified on a B200: profiles/r02w."""
 import json
 
 import numpy as np
