@@ -99,6 +99,9 @@ def export_from_totals(t: dict, n: int, cfg, *, scenario: str = "", makespan: fl
            "delta_t": float(cfg.delta_t if delta_t is None else delta_t),
            "gbp": {"iterations": {"internal": int(it[0]), "external": int(it[1])}},
            "robots": robots, "prng_seed": int(prng_seed), "obstacles": obstacles_data(colliders)}
+    # `goal_areas`: the reference spawns none (the set-up system is commented out, goal_area.rs:8-11), so its exports
+    # carry an empty map; kept for the shape
+    out["goal_areas"] = {}
     if collision_log is not None:
         # `Entity` serialises as a number: scripts/plot-robot-positions.py:197-200 compares collision['obstacle'] with
         # int(key of `obstacles`), so the obstacle stays the integer position in the collider list
