@@ -516,7 +516,7 @@ def main():
                             "launch from the committed ncu capture (scaled to this rank's robots when sharded); "
                             "traffic_frac = traffic / time / peak"}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is an N = 1 figure (rank 0 alone would hold up the others)
             swc, _ = build_workload(args.workload, args.cpu_robots)
             v, secs, _ = run_cpu(swc, cores, 2)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
