@@ -117,7 +117,8 @@ def formation_from_dict(f: dict) -> Formation:
     if rep:
         every = _duration(rep["every"])
         t = rep.get("times", "infinite")
-        times = None if t == "infinite" else int(t["value"])
+        # RepeatTimes (formation.rs:111-118): `infinite`, `!infinite` (unit variant as a tag) or `!finite N`
+        times = None if t == "infinite" or (isinstance(t, dict) and t.get("kind") == "infinite") else int(t["value"])
     ps = f["initial-position"]["placement-strategy"]
     placement, attempts = ("equal", 0) if ps == "equal" else ("random", int(ps["attempts"]))
     return Formation(

@@ -257,6 +257,43 @@ _SCHEDULES = {"centered": 0, "interleave-evenly": 1, "soon-as-possible": 2, "lat
               "half-beginning-half-end": 4}
 
 
+def read_scenario_directory(path: str) -> dict:
+    """The three input files of one `config/scenarios/<name>/` directory of the reference as plain data:
+    `formation.yaml` (FormationGroup, gbp_config/src/formation.rs; serde's `!tag` variants kept as {"kind": tag, ...}),
+    `environment.yaml` (gbp_environment/src/lib.rs) and the sections of `config.toml` the path reads ([gbp], [robot],
+    [simulation].hz and the despawn flag; gbp_config/src/lib.rs).  This is the form tests/golden/scenarios.json holds
+    (tests/golden/make_golden.py calls this function) and `ReferenceScenario` consumes."""
+    import os
+    import tomllib
+    from dataclasses import asdict
+
+    import yaml
+
+    from .environment import Environment
+
+    class Loader(yaml.SafeLoader):
+        pass
+
+    def tagged(loader, suffix, node):
+        if isinstance(node, yaml.MappingNode):
+            return {"kind": suffix, **loader.construct_mapping(node, deep=True)}
+        if isinstance(node, yaml.SequenceNode):
+            return {"kind": suffix, "value": loader.construct_sequence(node, deep=True)}
+        return {"kind": suffix, "value": loader.construct_scalar(node)}
+
+    Loader.add_multi_constructor("!", tagged)
+    with open(os.path.join(path, "config.toml"), "rb") as f:
+        cfg = tomllib.load(f)
+    with open(os.path.join(path, "formation.yaml"), encoding="utf-8") as f:
+        form = yaml.load(f.read(), Loader=Loader)
+    with open(os.path.join(path, "environment.yaml"), encoding="utf-8") as f:
+        env = Environment.from_yaml(f.read())
+    name = os.path.basename(os.path.normpath(path))
+    return {"source": f"config/scenarios/{name}/", "formations": form["formations"], "environment": asdict(env),
+            "gbp": cfg["gbp"], "robot": cfg["robot"],
+            "simulation": {k: cfg["simulation"][k] for k in ("hz", "despawn-robot-when-final-waypoint-reached")}}
+
+
 class ReferenceScenario:
     """One of the reference's `config/scenarios/<name>/` directories, as extracted into tests/golden/scenarios.json by
     tests/golden/make_golden.py: the formation group (`formation.yaml`), the environment (`environment.yaml`) and the
@@ -267,16 +304,18 @@ class ReferenceScenario:
     Inputs the reference draws from its PRNG (robot radii in [radius.min, radius.max], random placement along a line
     segment) come from the numpy Generator passed to `spawn`."""
 
-    def __init__(self, name: str, golden_path: str | None = None):
+    def __init__(self, name: str, golden_path: str | None = None, data: dict | None = None):
         import json
         import os
 
         from .environment import Environment, Obstacle
         from .formation import formation_from_dict
 
-        path = golden_path or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
-                                           "scenarios.json")
-        d = json.load(open(path))[name]
+        if data is None:
+            path = golden_path or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests",
+                                               "golden", "scenarios.json")
+            data = json.load(open(path))[name]
+        d = data
         self.name = name
         e = dict(d["environment"])
         e["obstacles"] = [Obstacle(**{k: (tuple(map(tuple, v)) if k == "points" else tuple(v) if isinstance(v, list) else v)
@@ -311,6 +350,13 @@ class ReferenceScenario:
         # gbp_world_reached_waypoint takes one criterion pair per call; the shipped scenarios use one per group
         self.reached_when, self.finished_when = next(iter(crit)) if len(crit) == 1 else (None, None)
 
+    @classmethod
+    def from_directory(cls, path: str) -> "ReferenceScenario":
+        """Straight from a scenario directory of the reference (`config.toml`, `formation.yaml`, `environment.yaml`)."""
+        import os
+
+        return cls(os.path.basename(os.path.normpath(path)), data=read_scenario_directory(path))
+
     def spawn_events(self, ticks: int) -> list[tuple[int, int]]:
         """(tick, formation index) of every spawn in the first `ticks` fixed steps, in time then formation order."""
         ev = []
@@ -326,6 +372,8 @@ class ReferenceScenario:
         from .formation import as_positions, routes
 
         f = self.formations[formation_index]
+        if f.robots == 0:
+            return None  # `robots: 0` (Obstacle Shapes Showcase): the spawn loop has nothing to iterate over
         lo, hi = self.radius_range
         radii = np.asarray([f32(lo) if lo == hi else f32(rng.uniform(lo, hi)) for _ in range(f.robots)], f32)
         placed = as_positions(f, self.world_w, self.world_h, radii, rng)

@@ -134,34 +134,13 @@ def scenarios():
     tags kept as {"kind": tag, ...}), the environment (same form as env_to_png.json) and the scalars of config.toml
     the hot path reads ([gbp], [robot], [simulation].hz / despawn flag)."""
     import sys
-    import tomllib
-    from dataclasses import asdict
-
-    import yaml
 
     sys.path.insert(0, os.path.join(HERE, "..", ".."))
-    from magics_b200.environment import Environment
+    from magics_b200.scenarios import read_scenario_directory
 
-    class Loader(yaml.SafeLoader):
-        pass
-
-    def tagged(loader, suffix, node):
-        if isinstance(node, yaml.MappingNode):
-            return {"kind": suffix, **loader.construct_mapping(node, deep=True)}
-        if isinstance(node, yaml.SequenceNode):
-            return {"kind": suffix, "value": loader.construct_sequence(node, deep=True)}
-        return {"kind": suffix, "value": loader.construct_scalar(node)}
-
-    Loader.add_multi_constructor("!", tagged)
     out = {}
     for name in ("Circle Experiment", "Structured Junction Twoway", "Collaborative Complex"):
-        base = f"/root/reference/config/scenarios/{name}"
-        cfg = tomllib.load(open(f"{base}/config.toml", "rb"))
-        form = yaml.load(open(f"{base}/formation.yaml").read(), Loader=Loader)
-        env = Environment.from_yaml(open(f"{base}/environment.yaml").read())
-        out[name] = {"source": f"config/scenarios/{name}/", "formations": form["formations"], "environment": asdict(env),
-                     "gbp": cfg["gbp"], "robot": cfg["robot"],
-                     "simulation": {k: cfg["simulation"][k] for k in ("hz", "despawn-robot-when-final-waypoint-reached")}}
+        out[name] = read_scenario_directory(f"/root/reference/config/scenarios/{name}")
     return out
 
 
