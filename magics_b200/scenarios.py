@@ -331,6 +331,7 @@ class ReferenceScenario:
         self.planning_horizon = float(r["planning-horizon"])
         self.lookahead_multiple = int(g.get("lookahead-multiple", 3))
         self.radius_range = (float(r["radius"]["min"]), float(r["radius"]["max"]))
+        self.failure_rate = float(r["communication"].get("failure-rate", 0.0))
         trk = g.get("tracking", {})
         cfg = GbpConfig(
             sigma_factor_dynamics=float(g["sigma-factor-dynamics"]), sigma_factor_interrobot=float(g["sigma-factor-interrobot"]),
@@ -356,6 +357,14 @@ class ReferenceScenario:
         import os
 
         return cls(os.path.basename(os.path.normpath(path)), data=read_scenario_directory(path))
+
+    def draw_antennas(self, n: int, rng) -> np.ndarray:
+        """update_failed_comms (robot.rs:1592-1601) for one tick: `antenna.active = !prng.gen_bool(failure_rate)` per
+        robot, in robot order — the `antenna_active` argument of `set_comms`.  The draws come from the numpy Generator
+        (the reference's WyRand stream is third-party and not reproduced, like its other random inputs)."""
+        if self.failure_rate <= 0.0:
+            return np.ones(n, np.uint8)
+        return (~(rng.random(n) < self.failure_rate)).astype(np.uint8)
 
     def spawn_events(self, ticks: int) -> list[tuple[int, int]]:
         """(tick, formation index) of every spawn in the first `ticks` fixed steps, in time then formation order."""

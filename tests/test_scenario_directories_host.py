@@ -73,3 +73,16 @@ def test_every_shipped_scenario_loads_spawns_and_steps_on_the_oracle(name):
     assert (moved <= 1e-3).all()  # Transform follows variable 0 (robot.rs:2286-2338)
     if sc.cfg.num_variables > ENGINE_MAX_V:
         assert name in ("Communications Failure Experiment", "Varying Network Connectivity Experiment")
+
+
+def test_communications_failure_rate_is_read_and_drawn_per_robot_and_tick():
+    sc = ReferenceScenario.from_directory(os.path.join(REF, "Communications Failure Experiment"))
+    assert 0.0 <= sc.failure_rate <= 1.0
+    raw = read_scenario_directory(os.path.join(REF, "Communications Failure Experiment"))
+    assert sc.failure_rate == float(raw["robot"]["communication"]["failure-rate"])
+    sc.failure_rate = 0.3
+    rng = np.random.default_rng(1)
+    draws = np.stack([sc.draw_antennas(2000, rng) for _ in range(10)])
+    assert draws.dtype == np.uint8 and abs(1.0 - draws.mean() - 0.3) < 0.02 and (draws[0] != draws[1]).any()
+    sc.failure_rate = 0.0
+    assert sc.draw_antennas(5, rng).tolist() == [1] * 5
