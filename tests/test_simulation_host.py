@@ -1,0 +1,108 @@
+"""`magics_b200.simulation.Simulation` — the headless runner of a reference scenario directory — driven without a GPU:
+the world it steps is the CPU oracle behind the method surface of `magics_b200.World`.  Checks the order of the systems
+around the iteration (spawner clock, mission clocks, despawn, antenna draws, collision monitors + entry lists, trackers)
+and that what comes out is the reference's ExportData, readable by `magics_b200.metrics`."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from magics_b200 import metrics
+from magics_b200.scenarios import ReferenceScenario
+from magics_b200.simulation import Simulation
+from oracle import oracle
+from oracle.oracle import OracleWorld
+
+
+class OracleAsWorld(OracleWorld):
+    """The oracle with the two members of `magics_b200.World` it lacks (`cfg`, `export_totals`)."""
+
+    def __init__(self, cfg, env):
+        super().__init__(cfg, threads=4)
+        self.cfg = cfg
+        self.set_sdf(oracle.env_to_sdf_image(env))
+        self._has_colliders = False
+
+    def set_environment_colliders(self, colliders):
+        self._has_colliders = True
+        return super().set_environment_colliders(colliders)
+
+    def export_totals(self):
+        n = self.num_robots
+        if n:
+            self.update_robot_collisions()  # refreshes the per-robot counts the wrapper caches (state unchanged)
+        return {"collisions_robots": self.read_robot_collisions() if n else np.zeros(0, np.uint32),
+                "next_waypoint": self.read_waypoint_index(), "removed": self.read_removed().astype(bool),
+                "collisions_environment": self.read_environment_collisions() if self._has_colliders and n else None,
+                "tracks": self.read_tracks() if n else None, "messages": None}
+
+
+def _sim(name, **kw):
+    sc = ReferenceScenario(name)  # tests/golden/scenarios.json: the reference's own files, extracted
+    return sc, Simulation(sc, OracleAsWorld(sc.cfg, sc.env), np.random.default_rng(4), **kw)
+
+
+def test_structured_junction_twoway_runs_spawns_despawns_and_exports():
+    sc, sim = _sim("Structured Junction Twoway")
+    assert sim.dt_ns == 100_000_000 and len(sim.colliders) == 4
+    sim.run(ticks=1)
+    assert sim.world.num_robots == 4  # the four lanes with delay 0; the others follow after 2 s and 4 s
+    sim.run(ticks=230)  # every lane repeats after 6 s; the first robots cross the junction and leave after ~16 s
+    n = sim.world.num_robots
+    assert n == 48 and len(sim.clock.missions) == n and sim.radii.shape == (n,)
+    assert sim.gone.sum() >= 6 and np.array_equal(sim.gone, sim.world.read_removed().astype(bool))
+    assert all(m.completed for m, g in zip(sim.clock.missions, sim.gone) if g)
+    d = json.loads(json.dumps(sim.export()))
+    assert d["scenario"] == "Structured Junction Twoway" and d["makespan"] == pytest.approx(23.1)
+    assert d["delta_t"] == pytest.approx(0.1) and set(d["collisions"]) == {"robots", "environment"}
+    assert len(d["robots"]) == n and len(d["obstacles"]) == 4 and d["goal_areas"] == {}
+    first = d["robots"]["0"]
+    assert first["mission"]["started_at"] == 0.0 and first["mission"]["finished_at"] > 5.0
+    assert d["robots"]["12"]["mission"]["started_at"] == pytest.approx(6.0)  # the second wave
+    assert 100 <= len(first["positions"]) <= 231  # 100 ms tracker: one sample per tick while it moves
+    ev = metrics.evaluate(d, projection="segments")
+    done = [rid for rid, g in enumerate(sim.gone) if g]
+    assert all(40.0 < ev["robots"][str(r)]["distance_travelled"] < 140.0 for r in done)
+    assert ev["collision_entries"] == {"interrobot": len(sim.log.robot_entries),
+                                       "environment": len(sim.log.environment_entries)}
+
+
+def test_run_until_every_mission_is_complete():
+    sc, sim = _sim("Circle Experiment", environment_collisions=False)
+    sc.formations[0].robots = 4  # the experiment sweeps 5 ... 50 robots; four keep the CPU oracle quick (V = 21, 50 / 10 iterations)
+    steps = sim.run(max_ticks=400)
+    assert sim.world.num_robots == 4 and all(m.completed for m in sim.clock.missions)
+    assert 30 < steps < 400, steps  # 100 m at 15 m / s and 10 Hz: about 70 ticks
+    d = sim.export()
+    assert d["makespan"] == pytest.approx(steps * 0.1) and len(d["collisions"]["robots"]) == 0
+    finished = [r["mission"]["finished_at"] for r in d["robots"].values()]
+    assert max(finished) <= d["makespan"] + 1e-9 and min(finished) > 3.0
+
+
+def test_antenna_draws_reach_the_world_when_the_scenario_has_a_failure_rate():
+    sc, sim = _sim("Circle Experiment", environment_collisions=False)
+    sc.formations[0].robots = 6
+    sc.failure_rate = 0.5
+    calls = []
+    real = sim.world.set_comms
+    sim.world.set_comms = lambda antenna_active=None, idle=None: (calls.append(np.array(antenna_active)), real(antenna_active, idle))[1]
+    first = sim.scenario.spawn_events(200)[0][0]  # the formation's delay
+    sim.run(ticks=first + 6)
+    assert len(calls) == 6 and all(c.shape == (6,) for c in calls) and 0 < np.concatenate(calls).mean() < 1
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/config/scenarios"), reason="reference tree only in the build container")
+def test_command_line_runner_refuses_to_run_without_a_gpu(tmp_path):
+    """`python -m magics_b200.simulation <dir>` parses the scenario directory, then needs the engine: no CPU fallback."""
+    import subprocess
+    import sys
+
+    from tests.conftest import _cuda_devices
+
+    if _cuda_devices() > 0:
+        pytest.skip("a GPU is present")
+    p = subprocess.run([sys.executable, "-m", "magics_b200.simulation", "/root/reference/config/scenarios/Junction Twoway",
+                        "--ticks", "3", "--export", str(tmp_path / "o.json")], capture_output=True, text=True, timeout=120,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert p.returncode != 0 and "CUDA" in p.stderr and not (tmp_path / "o.json").exists()
