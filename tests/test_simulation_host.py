@@ -68,6 +68,37 @@ def test_structured_junction_twoway_runs_spawns_despawns_and_exports():
                                        "environment": len(sim.log.environment_entries)}
 
 
+def _run_reference_script(script, *args):
+    import subprocess
+    import sys
+
+    runner = (
+        "import sys, runpy\n"
+        "from unittest import mock\n"
+        "for name in ('matplotlib', 'matplotlib.pyplot', 'toolz', 'toolz.curried', 'seaborn', 'result'):\n"
+        "    sys.modules[name] = mock.MagicMock(name=name)\n"  # plotting only; not in this image
+        "script = sys.argv[1]; sys.argv = sys.argv[1:]\n"
+        "sys.path.insert(0, '/root/reference/scripts')\n"
+        "runpy.run_path(script, run_name='__main__')\n")
+    return subprocess.run([sys.executable, "-c", runner, f"/root/reference/scripts/{script}", *args],
+                          capture_output=True, text=True, timeout=120, env={**os.environ, "COLUMNS": "200"})
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/scripts"), reason="reference tree only in the build container")
+def test_reference_scripts_read_what_the_runner_exports(tmp_path):
+    """The INTEGRATION.md recipe end to end (minus the GPU): run a scenario, export, feed the reference's own scripts."""
+    sc, sim = _sim("Structured Junction Twoway")
+    sim.run(ticks=60)
+    path = tmp_path / "export_structured junction twoway_0.json"
+    path.write_text(json.dumps(sim.export()))
+    # (perpendicular-path-deviation.py divides by x2 - x1 of a route segment, :41, and trips over its own NaN on the
+    # exactly vertical lanes of this formation; tests/test_metrics_host.py runs it on routes it can handle)
+    for script, args in (("ldj.py", ("-i", str(path))), ("distance-travelled.py", (str(path),))):
+        p = _run_reference_script(script, *args)
+        assert p.returncode == 0, (script, p.stderr[-1500:])
+        assert len(p.stdout) > 100, script
+
+
 def test_run_until_every_mission_is_complete():
     sc, sim = _sim("Circle Experiment", environment_collisions=False)
     sc.formations[0].robots = 4  # the experiment sweeps 5 ... 50 robots; four keep the CPU oracle quick (V = 21, 50 / 10 iterations)
