@@ -8,7 +8,8 @@ reference does — including `Route::advance` adding the route's start time to a
 
 Times are `Time<Fixed>::elapsed()` durations in integer nanoseconds, converted like `Duration::as_secs_f64`.
 Missions built by `Mission::global` (one route per pair of taskpoints, filled in by the RRT* planner) are outside this
-repo's scope.
+repo's scope; what happens when ONE planned path arrives for a robot — the host arithmetic in front
+of `set_tracking_path` / `reset_variables` / `reset_tracking_factors` — is `path_arrival` / `apply_global_paths` below.
 """
 from __future__ import annotations
 
@@ -102,3 +103,75 @@ class MissionClock:
             "routes": [{"waypoints": [[p[0], p[1]] for p in m.route.waypoints], "started_at": m.route.started_at,
                         "finished_at": m.route.finished_at if m.route.finished_at is not None else now}],
         }
+
+
+# ---- the global planner's path arrives (planner/robot.rs:655-776) ---------------------------------------------------
+def path_arrival(path, target_speed: float, planning_horizon: float, num_variables: int):
+    """What `update_robot_mission` computes on the host when a robot's RRT* task has finished, f32 as written:
+
+    waypoints (m, 4)  per path point `from` (the last one paired with itself): (from, target_speed * normalize(from - to)),
+                      NaN directions -> 0 (robot.rs:655-668).  The direction is `from - to` in the reference, i.e. the
+                      velocity part points back along the path: kept;
+    tracking  (m, 2)  the positions of those waypoints — `set_tracking_path` of every tracking factor (:676-684);
+    means  (V, 4) f64 the linearisation points `reset_variables` receives (:694-758): with start / next the first two
+                      waypoints AS 4-VECTORS, dir = next - start, next' = start + min(speed * horizon, 0.9 |dir|) *
+                      normalize(dir); variable i sits at lerp(start.xy, next'.xy, i / V) with velocity
+                      (target_speed * normalize(dir)).xy.
+
+    The caller then hands `tracking` to `World.set_tracking_path` (which also replaces the route's waypoints and sets
+    the next index to 1, Route::update_waypoints :389-392), `means` to `World.reset_variables(…, 1e30, inf)` and calls
+    `World.reset_tracking_factors` — `apply_global_paths` below.  glam (Vec2 / Vec4 normalize, length, lerp) is a
+    third-party crate: restated with every f32 operation rounded on its own, parity unpinned in the last bit."""
+    import numpy as np
+
+    f = np.float32
+    p = np.asarray(path, f).reshape(-1, 2)
+    if p.shape[0] < 2:
+        raise ValueError("a path has at least two points (min_len_vec::TwoOrMore)")
+    speed = f(target_speed)
+    wps = np.zeros((p.shape[0], 4), f)
+    for k in range(p.shape[0]):
+        frm, to = p[k], p[min(k + 1, p.shape[0] - 1)]
+        d = frm - to
+        n = np.sqrt(f(d[0] * d[0] + d[1] * d[1]))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            d = d * (f(1.0) / n)  # glam Vec2::normalize: self * length_recip()
+        if np.isnan(d).any():
+            d = np.zeros(2, f)
+        wps[k] = (frm[0], frm[1], speed * d[0], speed * d[1])
+    start, nxt = wps[0], wps[1]
+    dirv = nxt - start
+    with np.errstate(divide="ignore", invalid="ignore"):
+        length = np.sqrt(f(f(dirv[0] * dirv[0] + dirv[2] * dirv[2]) + f(dirv[1] * dirv[1] + dirv[3] * dirv[3])))
+        dn = dirv / length  # glam Vec4 (SSE2): self / sqrt(dot)
+    l = f(speed * f(planning_horizon))
+    mx = f(length * f(0.9))
+    s = l if l < mx else mx
+    nxt2 = start + s * dn
+    vel = speed * dn
+    V = int(num_variables)
+    means = np.zeros((V, 4), np.float64)
+    for i in range(V):
+        r = f(i) / f(V)
+        pos = start[:2] + (nxt2[:2] - start[:2]) * r  # glam lerp: self + (rhs - self) * s
+        means[i] = (pos[0], pos[1], vel[0], vel[1])
+    return wps, wps[:, :2].copy(), means
+
+
+def apply_global_paths(world, robots, paths, target_speed: float, planning_horizon: float, clock: "MissionClock | None" = None):
+    """The device side of the hand-off for the listed robots (robot.rs:676-766): new tracking path, variables reset
+    around the first path segment, tracking factors reset; the robots' routes (and their host clocks) restart at index 1."""
+    import numpy as np
+
+    robots = [int(r) for r in robots]
+    if not robots:
+        return
+    arrivals = [path_arrival(p, target_speed, planning_horizon, world.V) for p in paths]
+    world.set_tracking_path(robots, [a[1] for a in arrivals])
+    world.reset_variables(robots, np.stack([a[2] for a in arrivals]), 1e30, float("inf"))
+    world.reset_tracking_factors(robots)
+    if clock is not None:
+        for r, a in zip(robots, arrivals):
+            route = clock.missions[r].route
+            route.waypoints = [(float(x), float(y)) for x, y in a[1]]
+            route.target_index = 1
