@@ -7,9 +7,11 @@ restates that bookkeeping so `magics_b200.export` can fill `mission.started_at /
 reference does — including `Route::advance` adding the route's start time to an already absolute clock (robot.rs:436-438).
 
 Times are `Time<Fixed>::elapsed()` durations in integer nanoseconds, converted like `Duration::as_secs_f64`.
-Missions built by `Mission::global` (one route per pair of taskpoints, filled in by the RRT* planner) are outside this
-repo's scope; what happens when ONE planned path arrives for a robot — the host arithmetic in front
-of `set_tracking_path` / `reset_variables` / `reset_tracking_factors` — is `path_arrival` / `apply_global_paths` below.
+Missions built by `Mission::global` (one route per pair of taskpoints, filled in by the global planner) are
+`GlobalMissionState` + `MissionClock.progress`; the RRT* SEARCH itself (the third-party `rrt` crate behind
+gbp_global_planner/src/rrtstar.rs) is outside this repo's scope — the caller supplies the planner.  What happens when a
+planned path arrives for a robot — the host arithmetic in front of `set_tracking_path` / `reset_variables` /
+`reset_tracking_factors` — is `path_arrival` / `apply_global_paths` below.
 """
 from __future__ import annotations
 
@@ -60,6 +62,70 @@ class MissionState:
             self.completed = True
             self.finished_at = secs_f64(elapsed_ns)
 
+    @property
+    def routes(self) -> list:
+        return [self.route]
+
+    @property
+    def idle(self) -> bool:
+        return False  # Mission::local starts Active (robot.rs:853)
+
+
+@dataclass
+class GlobalMissionState:
+    """`Mission::global` (robot.rs:859-905) with the state machine `progress_missions` drives for the RrtStar planning
+    strategy (robot.rs:562-812): one route per pair of consecutive taskpoints, created when the previous one completes;
+    a new route starts Idle, asks the global planner for a path (Idle { waiting_for_waypoints: true }), becomes Active
+    when the path has arrived and replaced the route's two waypoints, and hands over to the next route — or completes
+    the mission — when its last waypoint is reached."""
+    taskpoints: list
+    started_at: float
+    routes: list = field(default_factory=list)
+    active_route: int = 0
+    finished_at: float | None = None
+    state: str = "idle"  # "idle" | "waiting" | "active" | "completed"
+    pending_path: object = None  # the planner's answer, held until the next progress pass (the task is polled per frame)
+
+    def __post_init__(self):
+        if len(self.taskpoints) < 2:
+            raise ValueError("a mission has at least two taskpoints (min_len_vec::TwoOrMore)")
+        if not self.routes:
+            self.routes.append(RouteClock(list(self.taskpoints[:2]), self.started_at))  # Mission::new :881-890
+
+    @property
+    def route(self) -> RouteClock:
+        return self.routes[min(self.active_route, len(self.routes) - 1)]
+
+    @property
+    def completed(self) -> bool:
+        return self.state == "completed"
+
+    @property
+    def idle(self) -> bool:
+        """MissionState::idle(): the robot neither iterates nor moves (robot.rs:1794-1851, :2212, :2303)."""
+        return self.state in ("idle", "waiting")
+
+    def next_route(self, elapsed_ns: int) -> None:
+        """Mission::next_route (robot.rs:961-993)."""
+        if self.completed:
+            return
+        self.active_route += 1
+        if self.active_route >= len(self.taskpoints) - 1:
+            self.state = "completed"
+            self.finished_at = secs_f64(elapsed_ns)
+        else:
+            k = self.active_route
+            self.routes.append(RouteClock(list(self.taskpoints[k:k + 2]), secs_f64(elapsed_ns)))
+            self.state = "idle"
+
+    def advance_to_next_waypoint(self, elapsed_ns: int) -> None:
+        """Mission::advance_to_next_waypoint (robot.rs:995-1006): only an Active mission advances."""
+        if self.state != "active":
+            return
+        self.route.advance(elapsed_ns)
+        if self.route.is_completed():
+            self.next_route(elapsed_ns)
+
 
 class MissionClock:
     """One `MissionState` per robot of a world, in the world's robot order.
@@ -71,14 +137,18 @@ class MissionClock:
     def __init__(self):
         self.missions: list[MissionState] = []
 
-    def spawn(self, waypoints, started_at: float) -> None:
-        """waypoints: per new robot a sequence of (x, y) with at least two entries."""
+    def spawn(self, waypoints, started_at: float, planning_strategy: str = "only-local") -> None:
+        """waypoints: per new robot a sequence of (x, y) with at least two entries; planning_strategy "only-local"
+        (Mission::local) or "rrt-star" (Mission::global), robot.rs:1287-1300."""
         for wps in waypoints:
             wps = [(float(p[0]), float(p[1])) for p in wps]
             if len(wps) < 2:
                 raise ValueError("a route has at least two waypoints (min_len_vec::TwoOrMore)")
-            self.missions.append(MissionState(RouteClock(wps, float(started_at)), float(started_at),
-                                              taskpoints=[wps[0], wps[-1]]))
+            if planning_strategy == "rrt-star":
+                self.missions.append(GlobalMissionState(taskpoints=wps, started_at=float(started_at)))
+            else:
+                self.missions.append(MissionState(RouteClock(wps, float(started_at)), float(started_at),
+                                                  taskpoints=[wps[0], wps[-1]]))
 
     def observe(self, reached, elapsed_ns: int) -> None:
         """reached: per robot, whether `reached_waypoint` advanced it in the tick whose fixed clock reads elapsed_ns."""
@@ -100,9 +170,41 @@ class MissionClock:
             "waypoints": [[p[0], p[1]] for p in m.taskpoints],
             "started_at": m.started_at,
             "finished_at": m.finished_at if m.finished_at is not None else now,
-            "routes": [{"waypoints": [[p[0], p[1]] for p in m.route.waypoints], "started_at": m.route.started_at,
-                        "finished_at": m.route.finished_at if m.route.finished_at is not None else now}],
+            "routes": [{"waypoints": [[p[0], p[1]] for p in r.waypoints], "started_at": r.started_at,
+                        "finished_at": r.finished_at if r.finished_at is not None else now} for r in m.routes],
         }
+
+    def idle_mask(self):
+        """MissionState::idle() per robot: the `idle` argument of `set_comms`."""
+        return [1 if m.idle else 0 for m in self.missions]
+
+    def progress(self, world, elapsed_ns: int, planner, target_speed: float, planning_horizon: float, colliders=(),
+                 rng=None) -> None:
+        """`progress_missions` (robot.rs:562-812) for the RrtStar missions of `world`'s robots, once per frame:
+        Idle -> the planner is asked for a path from taskpoint k to k + 1, `planner(start, end, colliders, rng)` ->
+        sequence of (x, y) or None (the reference spawns an async RRT* task; the search itself is not part of this repo)
+        -> Idle { waiting }; waiting -> the path arrives on the next pass: `apply_global_paths`, Active (a failed search
+        goes back to Idle and is tried again); Active with a completed route -> `next_route`."""
+        arrived, paths = [], []
+        for r, m in enumerate(self.missions):
+            if not isinstance(m, GlobalMissionState) or m.completed:
+                continue
+            if m.state == "waiting":
+                if m.pending_path is None or len(m.pending_path) < 2:
+                    m.state = "idle"  # Err(e) / empty Path: "try again" (robot.rs:786-791)
+                else:
+                    arrived.append(r)
+                    paths.append(m.pending_path)
+                    m.state = "active"
+                m.pending_path = None
+            elif m.state == "idle":
+                k = m.active_route
+                m.pending_path = planner(m.taskpoints[k], m.taskpoints[k + 1], colliders, rng)
+                m.state = "waiting"
+            elif m.state == "active" and m.route.is_completed():
+                m.next_route(elapsed_ns)
+        if arrived:
+            apply_global_paths(world, arrived, paths, target_speed, planning_horizon, self)
 
 
 # ---- the global planner's path arrives (planner/robot.rs:655-776) ---------------------------------------------------
@@ -172,6 +274,6 @@ def apply_global_paths(world, robots, paths, target_speed: float, planning_horiz
     world.reset_tracking_factors(robots)
     if clock is not None:
         for r, a in zip(robots, arrivals):
-            route = clock.missions[r].route
+            route = clock.missions[r].route  # Route::update_waypoints (robot.rs:389-392)
             route.waypoints = [(float(x), float(y)) for x, y in a[1]]
             route.target_index = 1

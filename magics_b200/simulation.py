@@ -5,7 +5,8 @@ scripts drive the windowed app and read the exported JSON.  `Simulation` plays t
 
   per fixed step (Time<Fixed>, 1 / simulation.hz)
     1. FormationSpawner clock -> `spawn_formation` for every formation that is due   (spawner.rs:186-323, :415-600)
-    2. `reached_waypoint` on the device, Mission / Route clocks on the host, despawn  (robot.rs:2080-2176, :331-490)
+    2. `reached_waypoint` on the device, Mission / Route clocks on the host, `progress_missions` for formations planned
+       by the global planner (path hand-off, idle robots), despawn          (robot.rs:2080-2176, :331-490, :562-812)
     3. `update_failed_comms` draws the antennas                                       (robot.rs:1592-1601)
     4. the RobotPlugin chain: neighbours, InterRobot factor deletion / creation, the two prior updates,
        `iterate_gbp_v2` = `world.step()`                                             (robot.rs:85-108)
@@ -30,7 +31,7 @@ from .mission import MissionClock, secs_f64
 
 class Simulation:
     def __init__(self, scenario, world, rng=None, *, environment_collisions: bool = True, tracker_capacity: int = 10000,
-                 tracker_sample_ns: int = 100_000_000, prng_seed: int = 0):
+                 tracker_sample_ns: int = 100_000_000, prng_seed: int = 0, global_planner=None):
         self.scenario, self.world = scenario, world
         self.rng = rng if rng is not None else np.random.default_rng(prng_seed)
         self.prng_seed = int(prng_seed)
@@ -38,9 +39,12 @@ class Simulation:
         self.tick_count = 0
         self.clock = MissionClock()
         self.radii = np.zeros(0, np.float32)
-        self.route_points = np.zeros(0, np.int64)  # waypoints per robot: mission completed <=> next index == this
         self.gone = np.zeros(0, bool)
         self.skipped_spawns = 0
+        # formations with `planning-strategy: rrt-star` wait for a path from taskpoint to taskpoint; the RRT* search is not
+        # part of this repo: `global_planner(start, end, colliders, rng) -> [(x, y), ...] | None`, default a straight line
+        self.global_planner = global_planner or (lambda start, end, colliders, rng: [start, end])
+        self._any_global = False
         self.colliders = environment_colliders(scenario.env) if environment_collisions else []
         if self.colliders:
             world.set_environment_colliders(self.colliders)
@@ -81,10 +85,11 @@ class Simulation:
             sw.add_to(self.world, set_sdf=False)
             self.radii = np.concatenate([self.radii, sw.radii])
             self.log.add_robots(sw.radii)
-            self.route_points = np.concatenate([self.route_points, np.diff(sw.wp_offsets)])
             self.gone = np.concatenate([self.gone, np.zeros(sw.n, bool)])
+            strategy = self.scenario.formations[k].planning_strategy
+            self._any_global |= strategy == "rrt-star"
             self.clock.spawn([sw.wp_xy[sw.wp_offsets[r]:sw.wp_offsets[r + 1]] for r in range(sw.n)],
-                             started_at=secs_f64(self.elapsed_ns))
+                             started_at=secs_f64(self.elapsed_ns), planning_strategy=strategy)
 
     def tick(self) -> None:
         sc, w = self.scenario, self.world
@@ -95,13 +100,17 @@ class Simulation:
         if sc.reached_when is not None:
             reached = w.reached_waypoint(sc.reached_when, sc.finished_when)
             self.clock.observe(reached, self.elapsed_ns)
-            if sc.despawn:
-                done = (np.asarray(w.read_waypoint_index()) >= self.route_points) & ~self.gone
-                if done.any():
-                    w.remove_robots(np.flatnonzero(done).astype(np.int32))
-                    self.gone |= done
-        if sc.failure_rate > 0.0:
-            w.set_comms(antenna_active=sc.draw_antennas(w.num_robots, self.rng))
+        if self._any_global:  # progress_missions (robot.rs:562-812)
+            self.clock.progress(w, self.elapsed_ns, self.global_planner, sc.cfg.target_speed, sc.planning_horizon,
+                                self.colliders, self.rng)
+        if sc.reached_when is not None and sc.despawn:
+            done = np.array([m.completed for m in self.clock.missions], bool) & ~self.gone
+            if done.any():
+                w.remove_robots(np.flatnonzero(done).astype(np.int32))
+                self.gone |= done
+        if sc.failure_rate > 0.0 or self._any_global:
+            w.set_comms(antenna_active=sc.draw_antennas(w.num_robots, self.rng),
+                        idle=np.asarray(self.clock.idle_mask(), np.uint8) if self._any_global else None)
         w.step()
         self.log.update_robot_collisions()
         if self.colliders:

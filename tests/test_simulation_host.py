@@ -137,3 +137,61 @@ def test_command_line_runner_refuses_to_run_without_a_gpu(tmp_path):
                         "--ticks", "3", "--export", str(tmp_path / "o.json")], capture_output=True, text=True, timeout=120,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert p.returncode != 0 and "CUDA" in p.stderr and not (tmp_path / "o.json").exists()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/config/scenarios"), reason="reference tree only in the build container")
+def test_rrt_star_formations_wait_for_the_planner_follow_its_path_and_hand_over_route_by_route():
+    """`Solo GP` (planning-strategy: rrt-star, tracking factors on) with a second waypoint added, so that the mission has
+    three taskpoints = two routes.  The planner is a stub returning a dog-leg (the RRT* search is outside this repo);
+    what is checked is progress_missions' state machine around it (robot.rs:562-812) and the hand-off calls."""
+    import copy
+
+    sc = ReferenceScenario.from_directory("/root/reference/config/scenarios/Solo GP")
+    f = sc.formations[0]
+    assert f.planning_strategy == "rrt-star" and sc.cfg.enable_tracking == 1
+    f.waypoints.append(copy.deepcopy(f.waypoints[0]))  # taskpoint 2: back where taskpoint 1's shape puts it, shifted below
+    asked = []
+
+    def planner(start, end, colliders, rng):
+        asked.append((tuple(start), tuple(end), len(colliders)))
+        if len(asked) == 2:
+            return None  # a failed search: the mission goes back to Idle and asks again
+        mid = (0.5 * (start[0] + end[0]) + 6.0, 0.5 * (start[1] + end[1]) - 6.0)
+        return [start, mid, end]
+
+    world = OracleAsWorld(sc.cfg, sc.env)
+    world.change_factor_enabled(2, 0)  # the stub's dog-leg cuts through walls: Obstacle factors off, or the robot stops at one
+    idle_seen = []
+    real = world.set_comms
+    world.set_comms = lambda antenna_active=None, idle=None: (idle_seen.append(None if idle is None else int(idle[0])),
+                                                              real(antenna_active, idle))[1]
+    sim = Simulation(sc, world, np.random.default_rng(2), global_planner=planner)
+    first = sc.spawn_events(100)[0][0]
+    sim.run(ticks=first + 1)
+    m = sim.clock.missions[0]
+    # identical second waypoint -> the route from taskpoint 1 to 2 is degenerate; move taskpoint 2 so the test has a second leg
+    m.taskpoints[2] = (m.taskpoints[1][0] - 40.0, m.taskpoints[1][1])
+    assert len(m.taskpoints) == 3 and m.state == "waiting" and idle_seen[-1] == 1 and len(asked) == 1
+    start0 = sim.world.read_positions()[0].copy()
+    assert np.array_equal(start0, np.asarray(m.taskpoints[0], np.float32)), "an idle robot does not move (robot.rs:2303)"
+    sim.run(ticks=1)
+    assert m.state == "active" and len(m.route.waypoints) == 3 and m.route.target_index == 1  # the dog-leg replaced the 2 taskpoints
+    assert idle_seen[-1] == 0 and not np.array_equal(sim.world.read_positions()[0], start0)  # Active: it iterates and moves
+    assert int(sim.world.read_waypoint_index()[0]) == 1
+    states = []
+    for _ in range(1500):
+        sim.tick()
+        states.append(m.state)
+        if m.completed:
+            break
+    assert m.completed and m.finished_at is not None and len(m.routes) == 2
+    # seen once per tick: route 1 active -> (its last waypoint is reached: next_route, Idle, the planner is asked in the same
+    # pass) waiting -> (failed search) idle -> waiting -> active -> completed
+    order = [s for k, s in enumerate(states) if k == 0 or s != states[k - 1]]
+    assert order == ["active", "waiting", "idle", "waiting", "active", "completed"], order
+    assert len(asked) == 3 and asked[1][0] == pytest.approx(m.taskpoints[1]) and asked[1][2] == len(sim.colliders) > 0
+    assert m.routes[0].finished_at is not None and m.routes[1].started_at >= m.routes[0].started_at
+    d = sim.export()
+    md = d["robots"]["0"]["mission"]
+    assert len(md["routes"]) == 2 and len(md["waypoints"]) == 3 and all(len(r["waypoints"]) == 3 for r in md["routes"])
+    assert sim.gone[0] == sc.despawn
