@@ -332,6 +332,7 @@ class ReferenceScenario:
         self.lookahead_multiple = int(g.get("lookahead-multiple", 3))
         self.radius_range = (float(r["radius"]["min"]), float(r["radius"]["max"]))
         self.failure_rate = float(r["communication"].get("failure-rate", 0.0))
+        self.rrt: dict = {}
         trk = g.get("tracking", {})
         cfg = GbpConfig(
             sigma_factor_dynamics=float(g["sigma-factor-dynamics"]), sigma_factor_interrobot=float(g["sigma-factor-interrobot"]),
@@ -355,8 +356,12 @@ class ReferenceScenario:
     def from_directory(cls, path: str) -> "ReferenceScenario":
         """Straight from a scenario directory of the reference (`config.toml`, `formation.yaml`, `environment.yaml`)."""
         import os
+        import tomllib
 
-        return cls(os.path.basename(os.path.normpath(path)), data=read_scenario_directory(path))
+        sc = cls(os.path.basename(os.path.normpath(path)), data=read_scenario_directory(path))
+        with open(os.path.join(path, "config.toml"), "rb") as f:
+            sc.rrt = tomllib.load(f).get("rrt", {})  # `[rrt]`: the global planner's parameters (gbp_config RRTSection)
+        return sc
 
     def draw_antennas(self, n: int, rng) -> np.ndarray:
         """update_failed_comms (robot.rs:1592-1601) for one tick: `antenna.active = !prng.gen_bool(failure_rate)` per

@@ -41,8 +41,9 @@ class Simulation:
         self.radii = np.zeros(0, np.float32)
         self.gone = np.zeros(0, bool)
         self.skipped_spawns = 0
-        # formations with `planning-strategy: rrt-star` wait for a path from taskpoint to taskpoint; the RRT* search is not
-        # part of this repo: `global_planner(start, end, colliders, rng) -> [(x, y), ...] | None`, default a straight line
+        # formations with `planning-strategy: rrt-star` wait for a path from taskpoint to taskpoint:
+        # `global_planner(start, end, colliders, rng) -> [(x, y), ...] | None` (magics_b200.planner.RRTStarPlanner is one;
+        # the reference's search is the third-party `rrt` crate), default a straight line
         self.global_planner = global_planner or (lambda start, end, colliders, rng: [start, end])
         self._any_global = False
         self.colliders = environment_colliders(scenario.env) if environment_collisions else []
@@ -164,7 +165,12 @@ def main(argv=None) -> int:
     ap.add_argument("--no-environment-collisions", action="store_true")
     args = ap.parse_args(argv)
     sc = ReferenceScenario.from_directory(args.scenario)
-    sim = Simulation.on_gpu(sc, device=args.device, prng_seed=args.seed,
+    planner = None
+    if any(f.planning_strategy == "rrt-star" for f in sc.formations):
+        from .planner import RRTStarPlanner
+
+        planner = RRTStarPlanner.from_config(sc.rrt)  # this repo's RRT* behind the reference's CollisionProblem
+    sim = Simulation.on_gpu(sc, device=args.device, prng_seed=args.seed, global_planner=planner,
                             environment_collisions=not args.no_environment_collisions)
     steps = sim.run(args.ticks, max_ticks=args.max_ticks)
     data = sim.export()
