@@ -46,6 +46,9 @@ class Simulation:
         # the reference's search is the third-party `rrt` crate), default a straight line
         self.global_planner = global_planner or (lambda start, end, colliders, rng: [start, end])
         self._any_global = False
+        # (taskpoint, finished) criterion of every robot's formation; `reached_waypoint` takes ONE pair per call
+        self.criteria: list = []
+        self.robot_criterion = np.zeros(0, np.int64)
         self.colliders = environment_colliders(scenario.env) if environment_collisions else []
         if self.colliders:
             world.set_environment_colliders(self.colliders)
@@ -87,10 +90,35 @@ class Simulation:
             self.radii = np.concatenate([self.radii, sw.radii])
             self.log.add_robots(sw.radii)
             self.gone = np.concatenate([self.gone, np.zeros(sw.n, bool)])
-            strategy = self.scenario.formations[k].planning_strategy
+            fm = self.scenario.formations[k]
+            crit = (fm.reached_when, fm.finished_when)
+            if crit not in self.criteria:
+                self.criteria.append(crit)
+            self.robot_criterion = np.concatenate([self.robot_criterion, np.full(sw.n, self.criteria.index(crit))])
+            strategy = fm.planning_strategy
             self._any_global |= strategy == "rrt-star"
             self.clock.spawn([sw.wp_xy[sw.wp_offsets[r]:sw.wp_offsets[r + 1]] for r in range(sw.n)],
                              started_at=secs_f64(self.elapsed_ns), planning_strategy=strategy)
+
+    def _reached_waypoint(self) -> np.ndarray:
+        """`reached_waypoint` for every robot under ITS formation's criteria.  The engine call applies one criterion pair
+        to all robots and touches nothing but the waypoint index, so with several pairs in play (`Collaborative GP`) it
+        runs once per pair from the same starting indices and every robot keeps the outcome of its own pair."""
+        w = self.world
+        if len(self.criteria) == 1:
+            return np.asarray(w.reached_waypoint(*self.criteria[0]), bool)
+        cur = np.array(w.read_waypoint_index(), np.int32)
+        flags = np.zeros(cur.shape[0], bool)
+        for g, crit in enumerate(self.criteria):
+            members = self.robot_criterion == g
+            if not members.any():
+                continue
+            w.set_waypoint_index(cur)  # undo what the previous pair's call did to the other robots
+            reached = np.asarray(w.reached_waypoint(*crit), bool)
+            new = np.asarray(w.read_waypoint_index(), np.int32)
+            cur[members], flags[members] = new[members], reached[members]
+        w.set_waypoint_index(cur)
+        return flags
 
     def tick(self) -> None:
         sc, w = self.scenario, self.world
@@ -98,13 +126,11 @@ class Simulation:
         self.tick_count += 1
         if w.num_robots == 0:
             return
-        if sc.reached_when is not None:
-            reached = w.reached_waypoint(sc.reached_when, sc.finished_when)
-            self.clock.observe(reached, self.elapsed_ns)
+        self.clock.observe(self._reached_waypoint(), self.elapsed_ns)
         if self._any_global:  # progress_missions (robot.rs:562-812)
             self.clock.progress(w, self.elapsed_ns, self.global_planner, sc.cfg.target_speed, sc.planning_horizon,
                                 self.colliders, self.rng)
-        if sc.reached_when is not None and sc.despawn:
+        if sc.despawn:
             done = np.array([m.completed for m in self.clock.missions], bool) & ~self.gone
             if done.any():
                 w.remove_robots(np.flatnonzero(done).astype(np.int32))

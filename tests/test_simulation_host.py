@@ -195,3 +195,33 @@ def test_rrt_star_formations_wait_for_the_planner_follow_its_path_and_hand_over_
     md = d["robots"]["0"]["mission"]
     assert len(md["routes"]) == 2 and len(md["waypoints"]) == 3 and all(len(r["waypoints"]) == 3 for r in md["routes"])
     assert sim.gone[0] == sc.despawn
+
+
+def test_formations_with_different_waypoint_criteria_each_get_their_own():
+    """Two formations of one scenario with different `finished-when-intersects` (as in `Collaborative GP`): the engine's
+    reached_waypoint takes one criterion pair for all robots, the runner calls it per pair and keeps, per robot, the
+    outcome of the robot's own formation — equal to running each formation alone."""
+    import copy
+
+    def scenario(which):
+        sc = ReferenceScenario("Structured Junction Twoway")
+        a, b = copy.deepcopy(sc.formations[0]), copy.deepcopy(sc.formations[3])  # two lanes that spawn at t = 0
+        b.finished_when = (0, 0, 1, 25.0)  # `current` within 25 m: finishes far earlier than lane a's criterion
+        assert a.finished_when != b.finished_when
+        sc.formations = [f for f, keep in ((a, "a" in which), (b, "b" in which)) if keep]
+        for f in sc.formations:
+            f.repeat_every_s, f.repeat_times = None, None  # one robot each
+            f.placement = "equal"  # no random draw: the robot of a lane starts at the same point in every run
+        return sc
+
+    def run(which, ticks=260):
+        sc = scenario(which)
+        world = OracleAsWorld(sc.cfg, sc.env)
+        world.change_factor_enabled(1, 0)  # no InterRobot factors: the two robots do not influence each other
+        sim = Simulation(sc, world, np.random.default_rng(3), environment_collisions=False)
+        sim.run(ticks=ticks)
+        return [(m.route.target_index, m.finished_at) for m in sim.clock.missions]
+
+    both, only_a, only_b = run("ab"), run("a"), run("b")
+    assert both == only_a + only_b
+    assert both[0][1] is not None and both[1][1] is not None and both[1][1] < both[0][1] - 1.0
