@@ -225,3 +225,28 @@ def test_formations_with_different_waypoint_criteria_each_get_their_own():
     both, only_a, only_b = run("ab"), run("a"), run("b")
     assert both == only_a + only_b
     assert both[0][1] is not None and both[1][1] is not None and both[1][1] < both[0][1] - 1.0
+
+
+_REF = "/root/reference/config/scenarios"
+
+
+@pytest.mark.skipif(not os.path.isdir(_REF), reason="reference tree only in the build container")
+@pytest.mark.parametrize("name", sorted(os.listdir(_REF)) if os.path.isdir(_REF) else [])
+def test_every_shipped_scenario_runs_through_the_runner_and_exports(name):
+    """All 18 scenario directories of the reference, 25 fixed steps past their first spawn on the oracle (swarm sizes cut
+    where the oracle would be slow: V up to 35, 50 internal iterations), colliders from the scenario's own environment,
+    export serialisable."""
+    sc = ReferenceScenario.from_directory(os.path.join(_REF, name))
+    for f in sc.formations:
+        f.robots = min(f.robots, 4 if (sc.cfg.num_variables > 21 or sc.cfg.iterations_internal > 20) else 8)
+    sim = Simulation(sc, OracleAsWorld(sc.cfg, sc.env), np.random.default_rng(0))
+    events = sc.spawn_events(600)
+    sim.run(ticks=(events[0][0] if events else 0) + 25)
+    d = json.loads(json.dumps(sim.export()))
+    assert d["scenario"] == name and len(d["robots"]) == sim.world.num_robots == len(sim.clock.missions)
+    assert len(d["obstacles"]) == len(sim.colliders) and set(d["collisions"]) == {"robots", "environment"}
+    if sim.world.num_robots:
+        assert all(len(r["positions"]) >= 1 or r["mission"]["routes"] for r in d["robots"].values())
+        assert np.isfinite(sim.world.read_beliefs()["mean"]).all()
+    else:
+        assert name == "Obstacle Shapes Showcase"
