@@ -1,4 +1,4 @@
-"""Mission / Route clocks of single-route (`Mission::local`) robots, kept on the host next to the engine.
+"""Mission / Route clocks of the robots (`Mission::local` and `Mission::global`), kept on the host next to the engine.
 
 The engine advances a robot's waypoint index on the device (`gbp_world_reached_waypoint`, planner/robot.rs:2080-2176) and
 tells the caller who advanced; WHEN a route / mission started and finished is bookkeeping of the reference's `Mission`
