@@ -239,3 +239,102 @@ def test_reference_plot_script_reads_obstacles_and_collision_entries_unchanged(t
     colours = json.loads(line[len("PATCH_COLOURS "):])
     assert len(colours) == len(cols)
     assert colours.count("red") == len({c for _, c in log.environment_entries}) >= 1  # one red patch per obstacle hit
+
+
+class _RandomWalkWorld:
+    """A world made of nothing but the two monitors (numpy all-pairs state machines, robots on a random walk): dense,
+    simultaneous events — robots in several pairs at once, many hits per update — which the oracle-driven runs above
+    only touch lightly.  It keeps its own record of every Hit."""
+
+    def __init__(self, n, colliders, rng, box=12.0):
+        self.rng, self.box = rng, box
+        self.pos = rng.uniform(-box, box, (n, 2)).astype(np.float32)
+        self.radii = rng.uniform(0.4, 1.2, n).astype(np.float32)
+        self.gone = np.zeros(n, bool)
+        self.colliders = colliders
+        self.rr_state, self.env_state = {}, {}
+        self.rr_hits, self.env_hits = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        self.rr_total = self.env_total = 0
+        self.rr_events, self.env_events = [], []
+        self.lib = load_library()
+        self.arr, self.verts, _ = pack_colliders(colliders)
+
+    num_robots = property(lambda self: self.pos.shape[0])
+
+    def move(self):
+        self.pos = (self.pos + self.rng.normal(0.0, 0.6, self.pos.shape)).clip(-self.box, self.box).astype(np.float32)
+
+    def read_positions(self):
+        return self.pos.copy()
+
+    def read_removed(self):
+        return self.gone.astype(np.uint8)
+
+    def read_robot_collisions(self):
+        return self.rr_hits.copy()
+
+    def read_environment_collisions(self):
+        return self.env_hits.copy()
+
+    def update_robot_collisions(self):
+        from magics_b200.collisions import balls_intersect
+
+        n, now_count = self.num_robots, 0
+        for i in range(n):
+            for j in range(i + 1, n):
+                if self.gone[i] or self.gone[j]:
+                    continue
+                now = bool(balls_intersect(self.pos[i], self.radii[i], self.pos[j], self.radii[j]))
+                if now and not self.rr_state.get((i, j), False):
+                    self.rr_total += 1
+                    self.rr_hits[i] += 1
+                    self.rr_hits[j] += 1
+                    self.rr_events.append((i, j))
+                self.rr_state[(i, j)] = now
+                now_count += now
+        return self.rr_total, now_count
+
+    def update_environment_collisions(self):
+        n, now_count = self.num_robots, 0
+        for c in range(len(self.colliders)):
+            out = np.zeros(n, np.uint8)
+            self.lib.gbp_collider_hits_ball(C.byref(self.arr[c]), C.c_int32(self.verts.shape[0]),
+                                            self.verts.ctypes.data_as(C.POINTER(C.c_float)), C.c_int32(n),
+                                            self.pos.ctypes.data_as(C.POINTER(C.c_float)),
+                                            self.radii.ctypes.data_as(C.POINTER(C.c_float)),
+                                            out.ctypes.data_as(C.POINTER(C.c_uint8)))
+            for r in range(n):
+                if self.gone[r]:
+                    continue
+                now = bool(out[r])
+                if now and not self.env_state.get((r, c), False):
+                    self.env_total += 1
+                    self.env_hits[r] += 1
+                    self.env_events.append((r, c))
+                self.env_state[(r, c)] = now
+                now_count += now
+        return self.env_total, now_count
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_dense_random_walk_every_hit_lands_in_the_right_entry(seed):
+    rng = np.random.default_rng(seed)
+    cols = SHAPES + [Collider("ball", (float(x), float(y)), 0.0, radius=1.0) for x, y in rng.uniform(-10, 10, (6, 2))]
+    w = _RandomWalkWorld(40, cols, rng)
+    log = CollisionLog(w, w.radii, cols)
+    log._CHUNK = 7  # several blocks of the candidate x candidate pair test
+    for tick in range(60):
+        w.move()
+        if tick == 30:
+            w.gone[[3, 11]] = True
+        assert log.update_robot_collisions()[0] == w.rr_total
+        assert log.update_environment_collisions()[0] == w.env_total
+    assert w.rr_total > 60 and w.env_total > 40  # dense: several hits per update
+    want_rr, want_env = {}, {}
+    for p in w.rr_events:
+        want_rr[p] = want_rr.get(p, 0) + 1
+    for p in w.env_events:
+        want_env[p] = want_env.get(p, 0) + 1
+    assert {k: len(v) for k, v in log.robot_entries.items()} == want_rr
+    assert {k: len(v) for k, v in log.environment_entries.items()} == want_env
+    assert max(want_rr.values()) >= 2  # pairs that parted and hit again
